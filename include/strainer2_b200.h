@@ -1,0 +1,160 @@
+/* strainer2_b200.h - C ABI of the B200-native k-mer scan path of strainer2.
+ *
+ * The reference (jeremiahfaith/strainer2) has no plugin / FFI interface: its three mains call the C
+ * functions of src/genome_compare.h directly and those hand out raw pointers into BIO_hash slots, so
+ * they cannot front a device-resident table.  This header is the thin replacement boundary: every
+ * entry point names the reference function (file:line under /root/reference/) whose work it takes
+ * over.  Plain pointers and sizes only; no CUDA or torch types appear in a signature.  Device
+ * pointers are passed as const void* / void* with an explicit on_device flag.
+ *
+ * Error convention.  The reference prints to stderr and exit(EXIT_FAILURE)s from inside the library
+ * (e.g. src/genome_compare.c:124-127).  A shared library must not kill its host process, so every
+ * call returns 0 / a valid handle on success and -1 / NULL on failure with the text available from
+ * s2_last_error(); the drop-in executables (kmer_scrub_count, strain_detect) turn that into the
+ * reference's "message on stderr + EXIT_FAILURE".  There is NO CPU fallback: without a usable
+ * sm_100 device s2_init() fails.
+ *
+ * Threading.  A context belongs to one GPU.  s2_batch_acquire / s2_batch_submit_* / s2_sync are
+ * thread safe (reader threads fill pinned batches concurrently); everything else on a context or a
+ * table must be called from one thread at a time.
+ */
+#ifndef STRAINER2_B200_H
+#define STRAINER2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2_K 31                 /* seed length, hard-coded in src/kmer_scrub_count.c:39, src/strain_detect.c:78 */
+#define S2_ABI_VERSION 1
+
+typedef struct s2_ctx s2_ctx;         /* one GPU: streams, pinned batch ring, scratch            */
+typedef struct s2_table s2_table;     /* device-resident strain table = the BIO_hash replacement */
+
+typedef struct s2_scan_stats {
+    uint64_t hits;            /* windows found in the table (count[vec_column] += 1 executions)  */
+    uint64_t valid_windows;   /* windows probed, i.e. not skipped by the N rule                  */
+} s2_scan_stats;
+
+/* ---------------------------------------------------------------- context ------------------- */
+int         s2_abi_version(void);
+const char *s2_last_error(void);                 /* text of the calling thread's last failure    */
+int         s2_device_count(void);               /* -1 if the CUDA runtime is unusable           */
+/* batch_bytes: capacity of each pinned/device batch buffer (0 = 64 MiB); n_lanes: batches in flight
+ * (0 = 4).  Fails (NULL) when `device` is not an sm_100 GPU. */
+s2_ctx     *s2_init(int device, uint64_t batch_bytes, int n_lanes);
+void        s2_shutdown(s2_ctx *ctx);
+int         s2_ctx_device(const s2_ctx *ctx);
+int         s2_ctx_sm_count(const s2_ctx *ctx);
+
+/* ---------------------------------------------------------------- strain table -------------- */
+/* Replaces BIO_initHash(8,000,000) + GEN_hash_sequences_set_count_vec()
+ * (src/kmer_scrub_count.c:87-89, src/genome_compare.c:967-1030).
+ * `bases` is the reference genome as ONE flat byte stream: the records' sequence bytes exactly as the
+ * parser yields them (any case), consecutive records separated by one byte that is not in ACGTacgt
+ * ('\n' by convention).  Every 31-byte window made only of ACGTacgt is canonicalised and inserted;
+ * column 0 of a new key starts at 1 and grows by 1 per repeat (default_count = increment = 1; the
+ * strain_detect caller ignores column 0).  n_cols: 4 (kmer_scrub_count) or 6 (strain_detect).
+ * load_factor: keys / slots, 0 = default 0.5.  on_device: `bases` is a device pointer. */
+s2_table   *s2_table_build(s2_ctx *ctx, const void *bases, uint64_t n_bytes, int n_cols,
+                           double load_factor, int on_device);
+void        s2_table_free(s2_table *t);
+uint64_t    s2_table_n_keys(const s2_table *t);          /* BIO_getHashSize()                     */
+uint64_t    s2_table_n_slots(const s2_table *t);
+uint64_t    s2_table_hbm_bytes(const s2_table *t);       /* fingerprints + keys + counters        */
+uint64_t    s2_table_probe_bytes(const s2_table *t);     /* the fingerprint array only            */
+/* keys[n_keys] (62-bit, A0 C1 G2 T3, first base highest) and djb2[n_keys] = hashU() of each key's
+ * ASCII spelling before "% M" (src/BIO_hash.c:208-216), both in FIRST-OCCURRENCE order = the order
+ * the reference inserted them, which is all s2_roworder_emulate() needs.  Either may be NULL. */
+int         s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2);
+/* counter column `col` in first-occurrence order (host buffers of n_keys uint32) */
+int         s2_table_counts_fetch(s2_table *t, int col, uint32_t *host_out);
+int         s2_table_counts_store(s2_table *t, int col, const uint32_t *host_in);
+int         s2_table_counts_clear(s2_table *t, int col);
+/* same, device to device, for the one collective of the path: the caller all-reduces (sum, uint32)
+ * the dense n_keys vector across GPUs (NCCL) between gather and scatter.  First-occurrence order is
+ * identical on every replica, whatever slot each replica's build happened to give a key. */
+int         s2_table_counts_gather_dev(s2_table *t, int col, void *dev_out);
+int         s2_table_counts_scatter_dev(s2_table *t, int col, const void *dev_in);
+/* hash_scrubbed_kmers() labelling, src/strain_detect.c:687-717: mark canonical 62-bit k-mers as
+ * INFORMATIVE.  found[i] (may be NULL) = 1 if kmers[i] is a key of the table. */
+int         s2_table_flag(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found);
+int         s2_table_lookup(s2_table *t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out);
+
+/* ---------------------------------------------------------------- count scan ---------------- */
+/* The per-window loop of GEN_calculate_kmer_count() (src/genome_compare.c:203-229) over one batch:
+ * flat byte stream as for s2_table_build (records shorter than 31 contribute no window by
+ * construction).  Adds 1 to counter column `col` for every window found.  Synchronous.
+ * If on_device, `bases` must be 16-byte aligned and readable up to the next multiple of 16. */
+int         s2_scan_count(s2_ctx *ctx, s2_table *t, const void *bases, uint64_t n_bytes, int col,
+                          int on_device, s2_scan_stats *stats);
+/* pipelined form: pinned double(+)-buffered batches, H2D copy and kernel overlapped on a stream per
+ * lane.  acquire blocks until a lane is free and returns its pinned host buffer. */
+uint8_t    *s2_batch_acquire(s2_ctx *ctx, uint64_t *capacity);
+int         s2_batch_submit_count(s2_ctx *ctx, s2_table *t, uint8_t *batch, uint64_t n_bytes, int col);
+int         s2_batch_release(s2_ctx *ctx, uint8_t *batch);               /* give back unused      */
+/* wait for every batch in flight; returns totals accumulated since the previous s2_sync */
+int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
+
+/* ---------------------------------------------------------------- detect scan --------------- */
+/* Pass 1 of quantify_hits_PE() (src/strain_detect.c:465-491, :514-539) for every record of a batch,
+ * plus the positions pass 2 (:554-623) will print.  rec_off[n_rec+1] are the ascending byte offsets of
+ * the records inside `bases` (rec_off[n_rec] = n_bytes; the separator byte belongs to the record
+ * before it).  Outputs (host): read_hits[n_rec], read_inf[n_rec]; inf_pos[<= inf_cap] = byte offsets
+ * of windows whose k-mer is INFORMATIVE, ascending; *n_inf = how many there were (may exceed inf_cap:
+ * call again with a larger buffer). */
+int         s2_scan_detect(s2_ctx *ctx, s2_table *t, const void *bases, uint64_t n_bytes,
+                           const uint64_t *rec_off, uint32_t n_rec, uint32_t *read_hits,
+                           uint32_t *read_inf, uint64_t *inf_pos, uint64_t inf_cap, uint64_t *n_inf,
+                           int on_device, s2_scan_stats *stats);
+
+/* ---------------------------------------------------------------- timing -------------------- */
+/* CUDA-event time (ms) and launch count of the scan kernels since the last reset, measured on the
+ * streams they were launched on. */
+int         s2_kernel_time(s2_ctx *ctx, double *ms, uint64_t *launches, int reset);
+
+/* ---------------------------------------------------------------- codecs -------------------- */
+/* bit-compatible with encode_DNA_2_bit / decode_DNA_2_bit (src/up2bit.c:53-98): A0 C1 T2 G3 */
+uint64_t    s2_encode_2bit(const char *dna, int len);
+void        s2_decode_2bit(uint64_t v, int len, char *out);
+/* device 2-bit pack kernel (order-preserving code A0 C1 G2 T3 + validity), results to host:
+ * words[ceil(n/16)], masks[ceil(n/16)] */
+int         s2_pack_2bit(s2_ctx *ctx, const void *bases, uint64_t n_bytes, int on_device,
+                         uint32_t *words, uint16_t *masks);
+/* canonical 62-bit k-mer of 31 ASCII bases (orient_string, src/genome_compare.c:1100-1120);
+ * returns 0 and sets *out, or -1 if a byte is not in ACGTacgt */
+int         s2_kmer_from_ascii(const char *s, uint64_t *out);
+void        s2_kmer_to_ascii(uint64_t kmer, char *out32);      /* 31 letters + NUL */
+
+/* ---------------------------------------------------------------- host helpers -------------- */
+/* Replays BIO_hash's slot placement (src/BIO_hash.c:129-139 insert + doubling at N++ >= M/2,
+ * :39-61 re-insertion in old-slot order, :174-188 slot-order walk) on the djb2 values of the keys in
+ * insertion order; order_out[i] = insertion index of the i-th emitted row.  initial_capacity = 0
+ * means the reference's DEFAULT_GENOME_HASH_SIZE (8,000,000, src/genome_compare.h:20). */
+int         s2_roworder_emulate(const uint32_t *djb2, uint64_t n, uint32_t initial_capacity,
+                                uint32_t *order_out, uint32_t *final_capacity);
+/* print_hash_counts() (src/kmer_scrub_count.c:134-156): header + one row per key in `order`.
+ * cols[c] are first-occurrence-order counter columns; n_print_cols = 3 or 4 (-C given). */
+int         s2_format_count_table(FILE *out, const uint64_t *keys, const uint32_t *order, uint64_t n,
+                                  const uint32_t *const *cols, int n_print_cols, int n_threads);
+
+/* FASTA/FASTQ (plain or gzip) reader with the record semantics of the parser the reference vendors
+ * (src/kseq.h:171-211).  s2_reader_next returns the sequence length, -1 at end of file, -2 on a
+ * truncated / mismatched quality string; the sequence stays valid until the next call. */
+typedef struct s2_reader s2_reader;
+s2_reader  *s2_reader_open(const char *path);
+int64_t     s2_reader_next(s2_reader *r, const char **seq);
+uint64_t    s2_reader_len(const s2_reader *r);      /* kseq's seq.l, stale after EOF like the original */
+void        s2_reader_close(s2_reader *r);
+
+/* whole programs, argv-compatible with the reference executables */
+int         s2_kmer_scrub_count_main(int argc, char **argv);   /* src/kmer_scrub_count.c:29-123 */
+int         s2_strain_detect_main(int argc, char **argv);      /* src/strain_detect.c:61-158    */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

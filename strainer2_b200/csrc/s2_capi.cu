@@ -1,0 +1,567 @@
+// s2_capi.cu - device half of the C ABI declared in include/strainer2_b200.h:
+// contexts (streams + pinned batch ring), strain tables, count / detect scans, codecs.
+// There is no CPU fallback anywhere in this file: every path ends in a kernel launch or an error.
+#include "../../include/strainer2_b200.h"
+#include "s2_kernels.cuh"
+#include "s2_kmer.cuh"
+#include "s2_internal.h"
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void s2_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *s2_last_error(void) { return g_err; }
+extern "C" int s2_abi_version(void) { return S2_ABI_VERSION; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            s2_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,   \
+                         cudaGetErrorString(e_));                                                  \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+#define CKN(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            s2_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,   \
+                         cudaGetErrorString(e_));                                                  \
+            return nullptr;                                                                        \
+        }                                                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+enum LaneState { LANE_FREE = 0, LANE_HELD = 1, LANE_INFLIGHT = 2 };
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    uint8_t *h_buf = nullptr;          // pinned
+    uint8_t *d_buf = nullptr;
+    cudaEvent_t k0 = nullptr, k1 = nullptr;   // bracket the scan kernel on this lane's stream
+    LaneState state = LANE_FREE;
+    bool timed = false;
+    uint64_t seq = 0;                  // submission order, to recycle the oldest first
+};
+
+struct s2_ctx {
+    int device = 0, n_sm = 0;
+    uint64_t batch_bytes = 0;
+    int n_lanes = 0;
+    std::vector<Lane> lanes;
+    std::mutex mu;
+    uint64_t next_seq = 1;
+    unsigned long long *d_stats = nullptr;     // [0] hits [1] valid windows, accumulated on device
+    unsigned long long *h_stats = nullptr;     // pinned mirror
+    int grid_count = 0, grid_detect = 0;
+    double kernel_ms = 0.0;
+    uint64_t kernel_launches = 0;
+};
+
+extern "C" int s2_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { s2_set_error("no usable CUDA runtime / driver"); return -1; }
+    return n;
+}
+
+extern "C" s2_ctx *s2_init(int device, uint64_t batch_bytes, int n_lanes)
+{
+    int n = s2_device_count();
+    if (n <= 0) { s2_set_error("no CUDA device: this library has no CPU path"); return nullptr; }
+    if (device < 0 || device >= n) { s2_set_error("device %d out of range (0..%d)", device, n - 1); return nullptr; }
+    cudaDeviceProp prop;
+    CKN(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        s2_set_error("device %d (%s) is sm_%d%d; this library is built for sm_100a only", device, prop.name,
+                     prop.major, prop.minor);
+        return nullptr;
+    }
+    CKN(cudaSetDevice(device));
+    s2_ctx *c = new s2_ctx();
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    c->batch_bytes = batch_bytes ? batch_bytes : (64ull << 20);
+    c->batch_bytes = (c->batch_bytes + 511) & ~511ull;
+    c->n_lanes = n_lanes > 0 ? n_lanes : 4;
+    c->lanes.resize(c->n_lanes);
+    for (auto &l : c->lanes) {
+        CKN(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CKN(cudaHostAlloc((void **)&l.h_buf, c->batch_bytes, cudaHostAllocDefault));
+        CKN(cudaMalloc((void **)&l.d_buf, c->batch_bytes + 64));
+        CKN(cudaEventCreate(&l.k0));
+        CKN(cudaEventCreate(&l.k1));
+    }
+    CKN(cudaMalloc((void **)&c->d_stats, 2 * sizeof(unsigned long long)));
+    CKN(cudaMemset(c->d_stats, 0, 2 * sizeof(unsigned long long)));
+    CKN(cudaHostAlloc((void **)&c->h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    c->grid_count = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_COUNT);
+    c->grid_detect = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_DETECT);
+    return c;
+}
+
+extern "C" void s2_shutdown(s2_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &l : c->lanes) {
+        if (l.k0) cudaEventDestroy(l.k0);
+        if (l.k1) cudaEventDestroy(l.k1);
+        if (l.d_buf) cudaFree(l.d_buf);
+        if (l.h_buf) cudaFreeHost(l.h_buf);
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    if (c->d_stats) cudaFree(c->d_stats);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    delete c;
+}
+
+extern "C" int s2_ctx_device(const s2_ctx *c) { return c->device; }
+extern "C" int s2_ctx_sm_count(const s2_ctx *c) { return c->n_sm; }
+
+// wait for a lane's work and fold its kernel time into the context (caller holds c->mu)
+static int lane_retire(s2_ctx *c, Lane &l)
+{
+    if (l.state != LANE_INFLIGHT) return 0;
+    CK(cudaEventSynchronize(l.k1));
+    if (l.timed) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, l.k0, l.k1));
+        c->kernel_ms += ms;
+        c->kernel_launches += 1;
+        l.timed = false;
+    }
+    l.state = LANE_FREE;
+    return 0;
+}
+
+extern "C" int s2_kernel_time(s2_ctx *c, double *ms, uint64_t *launches, int reset)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    if (ms) *ms = c->kernel_ms;
+    if (launches) *launches = c->kernel_launches;
+    if (reset) { c->kernel_ms = 0.0; c->kernel_launches = 0; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// strain table
+// ------------------------------------------------------------------------------------------------
+struct s2_table {
+    s2_ctx *ctx = nullptr;
+    S2TableView v = {};
+    uint32_t *rank_slot = nullptr;     // first-occurrence rank -> slot
+    uint32_t *scratch = nullptr;       // n_keys uint32 staging for fetch / store
+    uint64_t n_keys = 0;
+};
+
+extern "C" uint64_t s2_table_n_keys(const s2_table *t) { return t->n_keys; }
+extern "C" uint64_t s2_table_n_slots(const s2_table *t) { return t->v.n_slots; }
+extern "C" uint64_t s2_table_probe_bytes(const s2_table *t) { return t->v.n_slots * sizeof(uint16_t); }
+extern "C" uint64_t s2_table_hbm_bytes(const s2_table *t)
+{
+    return t->v.n_slots * (sizeof(uint16_t) + sizeof(uint64_t) + sizeof(uint32_t) * (uint64_t)t->v.n_cols) +
+           t->n_keys * 2 * sizeof(uint32_t);
+}
+
+extern "C" void s2_table_free(s2_table *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaFree(t->v.fp); cudaFree(t->v.keys); cudaFree(t->v.counts); cudaFree(t->rank_slot); cudaFree(t->scratch);
+    delete t;
+}
+
+static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t n_bytes, int n_cols,
+                            double load, int on_device)
+{
+    CK(cudaSetDevice(c->device));
+    if (n_bytes >= 0xFFFFFFF0ull) { s2_set_error("reference genome of %llu bytes exceeds the 4 GiB build limit", (unsigned long long)n_bytes); return -1; }
+    if (n_cols < 1 || n_cols > 8) { s2_set_error("n_cols must be 1..8"); return -1; }
+    if (load <= 0.0) load = 0.5;
+    if (load > 0.9) load = 0.9;
+    cudaStream_t st = c->lanes[0].stream;
+
+    const uint8_t *d_bases = (const uint8_t *)bases;
+    uint8_t *tmp_bases = nullptr;
+    if (!on_device && n_bytes) {
+        CK(cudaMalloc((void **)&tmp_bases, n_bytes + 64));
+        CK(cudaMemcpyAsync(tmp_bases, bases, n_bytes, cudaMemcpyHostToDevice, st));
+        d_bases = tmp_bases;
+    }
+    const uint64_t upper = n_bytes >= S2_K ? n_bytes - S2_K + 1 : 0;          // windows, hence keys, at most
+    uint64_t n_buckets = (uint64_t)((double)upper / (S2_BUCKET_SLOTS * load)) + 2;
+    if (n_buckets * S2_BUCKET_SLOTS >= 0xFFFFFFF0ull) { s2_set_error("table too large"); return -1; }
+    t->ctx = c;
+    t->v.n_buckets = (uint32_t)n_buckets;
+    t->v.n_slots = n_buckets * S2_BUCKET_SLOTS;
+    t->v.n_cols = n_cols;
+    CK(cudaMalloc((void **)&t->v.fp, t->v.n_slots * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&t->v.keys, t->v.n_slots * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&t->v.counts, t->v.n_slots * sizeof(uint32_t) * n_cols));
+    CK(cudaMemsetAsync(t->v.fp, 0, t->v.n_slots * sizeof(uint16_t), st));
+    CK(cudaMemsetAsync(t->v.keys, 0xFF, t->v.n_slots * sizeof(uint64_t), st));
+    CK(cudaMemsetAsync(t->v.counts, 0, t->v.n_slots * sizeof(uint32_t) * n_cols, st));
+
+    uint32_t *first_pos = nullptr, *slot_of_pos = nullptr, *block_sums = nullptr, *rank_tmp = nullptr;
+    unsigned long long *d_n = nullptr;
+    const uint32_t n_blocks = (uint32_t)((n_bytes + 1023) / 1024);
+    CK(cudaMalloc((void **)&first_pos, t->v.n_slots * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&slot_of_pos, (n_bytes + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&block_sums, (n_blocks + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&rank_tmp, (upper + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&d_n, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(first_pos, 0xFF, t->v.n_slots * sizeof(uint32_t), st));
+
+    s2_launch_build_insert(d_bases, n_bytes, t->v, first_pos, slot_of_pos, st);
+    s2_launch_build_rank(n_bytes, first_pos, slot_of_pos, block_sums, n_blocks, rank_tmp, d_n, st);
+    CK(cudaGetLastError());
+    unsigned long long n_keys = 0;
+    CK(cudaMemcpyAsync(&n_keys, d_n, sizeof n_keys, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    t->n_keys = n_keys;
+    CK(cudaMalloc((void **)&t->rank_slot, (n_keys + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&t->scratch, (n_keys + 1) * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(t->rank_slot, rank_tmp, n_keys * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(first_pos); cudaFree(slot_of_pos); cudaFree(block_sums); cudaFree(rank_tmp); cudaFree(d_n);
+    if (tmp_bases) cudaFree(tmp_bases);
+    return 0;
+}
+
+extern "C" s2_table *s2_table_build(s2_ctx *c, const void *bases, uint64_t n_bytes, int n_cols,
+                                    double load_factor, int on_device)
+{
+    if (!c) { s2_set_error("s2_table_build: NULL context"); return nullptr; }
+    s2_table *t = new s2_table();
+    if (table_build_impl(c, t, bases, n_bytes, n_cols, load_factor, on_device) != 0) {
+        t->ctx = c;
+        s2_table_free(t);
+        return nullptr;
+    }
+    return t;
+}
+
+extern "C" int s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2)
+{
+    s2_ctx *c = t->ctx;
+    CK(cudaSetDevice(c->device));
+    if (t->n_keys == 0) return 0;
+    cudaStream_t st = c->lanes[0].stream;
+    uint64_t *d_keys = nullptr; uint32_t *d_h = nullptr;
+    CK(cudaMalloc((void **)&d_keys, t->n_keys * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&d_h, t->n_keys * sizeof(uint32_t)));
+    s2_launch_export(t->v, t->rank_slot, t->n_keys, d_keys, d_h, st);
+    CK(cudaGetLastError());
+    if (keys) CK(cudaMemcpyAsync(keys, d_keys, t->n_keys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (djb2) CK(cudaMemcpyAsync(djb2, d_h, t->n_keys * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_keys); cudaFree(d_h);
+    return 0;
+}
+
+static int check_col(const s2_table *t, int col)
+{
+    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column %d out of range (table has %d)", col, t->v.n_cols); return -1; }
+    return 0;
+}
+
+extern "C" int s2_table_counts_gather_dev(s2_table *t, int col, void *dev_out)
+{
+    if (check_col(t, col)) return -1;
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t st = t->ctx->lanes[0].stream;
+    s2_launch_gather_counts(t->v, col, t->rank_slot, t->n_keys, (uint32_t *)dev_out, st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int s2_table_counts_scatter_dev(s2_table *t, int col, const void *dev_in)
+{
+    if (check_col(t, col)) return -1;
+    CK(cudaSetDevice(t->ctx->device));
+    cudaStream_t st = t->ctx->lanes[0].stream;
+    s2_launch_scatter_counts(t->v, col, t->rank_slot, t->n_keys, (const uint32_t *)dev_in, st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int s2_table_counts_fetch(s2_table *t, int col, uint32_t *host_out)
+{
+    if (s2_table_counts_gather_dev(t, col, t->scratch)) return -1;
+    if (t->n_keys) CK(cudaMemcpy(host_out, t->scratch, t->n_keys * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int s2_table_counts_store(s2_table *t, int col, const uint32_t *host_in)
+{
+    if (check_col(t, col)) return -1;
+    CK(cudaSetDevice(t->ctx->device));
+    if (t->n_keys) CK(cudaMemcpy(t->scratch, host_in, t->n_keys * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return s2_table_counts_scatter_dev(t, col, t->scratch);
+}
+
+extern "C" int s2_table_counts_clear(s2_table *t, int col)
+{
+    if (check_col(t, col)) return -1;
+    CK(cudaSetDevice(t->ctx->device));
+    CK(cudaMemset(t->v.counts + (uint64_t)col * t->v.n_slots, 0, t->v.n_slots * sizeof(uint32_t)));
+    return 0;
+}
+
+static int table_query(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found, uint32_t *slots, bool flag)
+{
+    s2_ctx *c = t->ctx;
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    cudaStream_t st = c->lanes[0].stream;
+    uint64_t *d_k = nullptr; void *d_o = nullptr;
+    const size_t osz = flag ? n : n * sizeof(uint32_t);
+    CK(cudaMalloc((void **)&d_k, n * sizeof(uint64_t)));
+    CK(cudaMalloc(&d_o, osz));
+    CK(cudaMemcpyAsync(d_k, kmers, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (flag) s2_launch_flag(t->v, d_k, n, (uint8_t *)d_o, st);
+    else s2_launch_lookup(t->v, d_k, n, (uint32_t *)d_o, st);
+    CK(cudaGetLastError());
+    void *dst = flag ? (void *)found : (void *)slots;
+    if (dst) CK(cudaMemcpyAsync(dst, d_o, osz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_k); cudaFree(d_o);
+    return 0;
+}
+
+extern "C" int s2_table_flag(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found)
+{
+    return table_query(t, kmers, n, found, nullptr, true);
+}
+
+extern "C" int s2_table_lookup(s2_table *t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out)
+{
+    return table_query(t, kmers, n, nullptr, slot_out, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// count scan
+// ------------------------------------------------------------------------------------------------
+static int fetch_stats(s2_ctx *c, cudaStream_t st, s2_scan_stats *out)
+{
+    CK(cudaMemcpyAsync(c->h_stats, c->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(c->d_stats, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaStreamSynchronize(st));
+    if (out) { out->hits = c->h_stats[0]; out->valid_windows = c->h_stats[1]; }
+    return 0;
+}
+
+extern "C" int s2_scan_count(s2_ctx *c, s2_table *t, const void *bases, uint64_t n_bytes, int col,
+                             int on_device, s2_scan_stats *stats)
+{
+    if (check_col(t, col)) return -1;
+    CK(cudaSetDevice(c->device));
+    if (on_device) {
+        if (((uintptr_t)bases & 15) != 0) { s2_set_error("device batch must be 16-byte aligned"); return -1; }
+        std::lock_guard<std::mutex> g(c->mu);
+        Lane &l = c->lanes[0];
+        if (lane_retire(c, l)) return -1;
+        CK(cudaEventRecord(l.k0, l.stream));
+        s2_launch_scan_count((const uint8_t *)bases, n_bytes, t->v, col, c->d_stats, c->grid_count, l.stream);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(l.k1, l.stream));
+        l.state = LANE_INFLIGHT; l.timed = true; l.seq = c->next_seq++;
+        if (lane_retire(c, l)) return -1;
+        return fetch_stats(c, l.stream, stats);
+    }
+    // host input: stream it through the pinned lanes in batch_bytes pieces overlapping by 30 bytes
+    // (a window never straddles two pieces un-scanned: the next piece restarts 30 bytes early)
+    s2_scan_stats dummy;
+    if (s2_sync(c, &dummy)) return -1;
+    const uint8_t *src = (const uint8_t *)bases;
+    uint64_t off = 0;
+    while (off < n_bytes) {
+        uint64_t cap = 0;
+        uint8_t *buf = s2_batch_acquire(c, &cap);
+        if (!buf) return -1;
+        uint64_t take = std::min<uint64_t>(cap, n_bytes - off);
+        memcpy(buf, src + off, take);
+        if (s2_batch_submit_count(c, t, buf, take, col)) return -1;
+        if (off + take >= n_bytes) break;
+        off += take - (S2_K - 1);
+        // windows fully inside the 30-byte overlap would be counted twice; there are none: a
+        // window is 31 bytes long, the overlap is 30.
+    }
+    return s2_sync(c, stats);
+}
+
+extern "C" uint8_t *s2_batch_acquire(s2_ctx *c, uint64_t *capacity)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    if (cudaSetDevice(c->device) != cudaSuccess) { s2_set_error("cudaSetDevice failed"); return nullptr; }
+    if (capacity) *capacity = c->batch_bytes;
+    Lane *pick = nullptr;
+    for (auto &l : c->lanes) if (l.state == LANE_FREE) { pick = &l; break; }
+    if (!pick) {
+        for (auto &l : c->lanes)
+            if (l.state == LANE_INFLIGHT && (!pick || l.seq < pick->seq)) pick = &l;
+        if (!pick) { s2_set_error("s2_batch_acquire: every lane is held by a caller (n_lanes=%d)", c->n_lanes); return nullptr; }
+        if (lane_retire(c, *pick)) return nullptr;
+    }
+    pick->state = LANE_HELD;
+    return pick->h_buf;
+}
+
+static Lane *find_lane(s2_ctx *c, const uint8_t *buf)
+{
+    for (auto &l : c->lanes) if (l.h_buf == buf) return &l;
+    return nullptr;
+}
+
+extern "C" int s2_batch_release(s2_ctx *c, uint8_t *batch)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    Lane *l = find_lane(c, batch);
+    if (!l || l->state != LANE_HELD) { s2_set_error("s2_batch_release: not an acquired batch"); return -1; }
+    l->state = LANE_FREE;
+    return 0;
+}
+
+extern "C" int s2_batch_submit_count(s2_ctx *c, s2_table *t, uint8_t *batch, uint64_t n_bytes, int col)
+{
+    if (check_col(t, col)) return -1;
+    std::lock_guard<std::mutex> g(c->mu);
+    CK(cudaSetDevice(c->device));
+    Lane *l = find_lane(c, batch);
+    if (!l || l->state != LANE_HELD) { s2_set_error("s2_batch_submit_count: not an acquired batch"); return -1; }
+    if (n_bytes > c->batch_bytes) { s2_set_error("batch of %llu bytes exceeds capacity", (unsigned long long)n_bytes); return -1; }
+    if (n_bytes == 0) { l->state = LANE_FREE; return 0; }
+    CK(cudaMemcpyAsync(l->d_buf, l->h_buf, n_bytes, cudaMemcpyHostToDevice, l->stream));
+    CK(cudaEventRecord(l->k0, l->stream));
+    s2_launch_scan_count(l->d_buf, n_bytes, t->v, col, c->d_stats, c->grid_count, l->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(l->k1, l->stream));
+    l->state = LANE_INFLIGHT; l->timed = true; l->seq = c->next_seq++;
+    return 0;
+}
+
+extern "C" int s2_sync(s2_ctx *c, s2_scan_stats *totals)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    CK(cudaSetDevice(c->device));
+    for (auto &l : c->lanes) if (lane_retire(c, l)) return -1;
+    return fetch_stats(c, c->lanes[0].stream, totals);
+}
+
+// ------------------------------------------------------------------------------------------------
+// detect scan
+// ------------------------------------------------------------------------------------------------
+extern "C" int s2_scan_detect(s2_ctx *c, s2_table *t, const void *bases, uint64_t n_bytes,
+                              const uint64_t *rec_off, uint32_t n_rec, uint32_t *read_hits,
+                              uint32_t *read_inf, uint64_t *inf_pos, uint64_t inf_cap, uint64_t *n_inf,
+                              int on_device, s2_scan_stats *stats)
+{
+    CK(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> g(c->mu);
+    Lane &l = c->lanes[0];
+    if (lane_retire(c, l)) return -1;
+    cudaStream_t st = l.stream;
+    if (n_inf) *n_inf = 0;
+    if (n_rec == 0 || n_bytes == 0) { if (stats) { stats->hits = 0; stats->valid_windows = 0; } return 0; }
+
+    const uint8_t *d_bases = (const uint8_t *)bases;
+    uint8_t *tmp = nullptr;
+    if (!on_device) {
+        CK(cudaMalloc((void **)&tmp, n_bytes + 64));
+        CK(cudaMemcpyAsync(tmp, bases, n_bytes, cudaMemcpyHostToDevice, st));
+        d_bases = tmp;
+    } else if (((uintptr_t)bases & 15) != 0) { s2_set_error("device batch must be 16-byte aligned"); return -1; }
+
+    uint64_t *d_off = nullptr, *d_pos = nullptr; uint32_t *d_hits = nullptr, *d_inf = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    CK(cudaMalloc((void **)&d_off, (n_rec + 1ull) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&d_hits, n_rec * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&d_inf, n_rec * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&d_pos, (inf_cap + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&d_cnt, sizeof(unsigned long long)));
+    CK(cudaMemcpyAsync(d_off, rec_off, (n_rec + 1ull) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_hits, 0, n_rec * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d_inf, 0, n_rec * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+
+    S2DetectOut out;
+    out.rec_off = d_off; out.n_rec = n_rec; out.read_hits = d_hits; out.read_inf = d_inf;
+    out.inf_pos = d_pos; out.inf_count = d_cnt; out.inf_cap = inf_cap;
+    CK(cudaEventRecord(l.k0, st));
+    s2_launch_scan_detect(d_bases, n_bytes, t->v, out, c->d_stats, c->grid_detect, st);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(l.k1, st));
+    l.state = LANE_INFLIGHT; l.timed = true; l.seq = c->next_seq++;
+    if (lane_retire(c, l)) return -1;
+
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(read_hits, d_hits, n_rec * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(read_inf, d_inf, n_rec * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t have = std::min<uint64_t>(cnt, inf_cap);
+    if (have && inf_pos) {
+        CK(cudaMemcpy(inf_pos, d_pos, have * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        std::sort(inf_pos, inf_pos + have);          // the kernel appends in arbitrary order
+    }
+    if (n_inf) *n_inf = cnt;
+    cudaFree(d_off); cudaFree(d_hits); cudaFree(d_inf); cudaFree(d_pos); cudaFree(d_cnt);
+    if (tmp) cudaFree(tmp);
+    return fetch_stats(c, st, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// codecs
+// ------------------------------------------------------------------------------------------------
+extern "C" int s2_pack_2bit(s2_ctx *c, const void *bases, uint64_t n_bytes, int on_device,
+                            uint32_t *words, uint16_t *masks)
+{
+    CK(cudaSetDevice(c->device));
+    const uint64_t n_chunks = (n_bytes + 15) / 16;
+    if (!n_chunks) return 0;
+    cudaStream_t st = c->lanes[0].stream;
+    const uint8_t *d_bases = (const uint8_t *)bases;
+    uint8_t *tmp = nullptr;
+    if (!on_device) {
+        CK(cudaMalloc((void **)&tmp, n_chunks * 16));
+        CK(cudaMemcpyAsync(tmp, bases, n_bytes, cudaMemcpyHostToDevice, st));
+        d_bases = tmp;
+    }
+    uint32_t *d_w = nullptr; uint16_t *d_m = nullptr;
+    CK(cudaMalloc((void **)&d_w, n_chunks * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&d_m, n_chunks * sizeof(uint16_t)));
+    s2_launch_pack(d_bases, n_bytes, d_w, d_m, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(words, d_w, n_chunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(masks, d_m, n_chunks * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_w); cudaFree(d_m);
+    if (tmp) cudaFree(tmp);
+    return 0;
+}

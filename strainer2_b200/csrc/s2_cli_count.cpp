@@ -1,0 +1,259 @@
+// s2_cli_count.cpp - the drop-in `kmer_scrub_count` program (/root/reference/src/kmer_scrub_count.c:29-156,
+// list drivers src/genome_compare.c:115-177) on top of the C ABI.  Same getopt string, same required
+// arguments, usage text, progress file, stderr notes and count-table bytes; the scanning itself is
+// s2_batch_submit_count() on the GPU.  Host threads only inflate + parse files into pinned batches.
+//
+// Extra controls come from the environment so argv stays drop-in:
+//   S2_DEVICE (0)  S2_THREADS (min(nproc,16) reader threads)  S2_BATCH_MB (64)  S2_LOAD (0.5)
+//   S2_STATS=1 prints a one-line throughput summary on stderr.
+#include "../../include/strainer2_b200.h"
+#include "s2_internal.h"
+
+#include <getopt.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+static void count_usage()
+{
+    fprintf(stderr, "Usage: kmer_scrub_count -r <reference genome>  -A <file with multiple genome filenames> -B <file with multiple "
+                    "metagenome filenames> -C <(optional) file with multiple genome filenames of drug strains> -p [progress output "
+                    "file, optional]\n");
+}
+
+// One flat byte stream for s2_table_build: sequence bytes of every record, '\n' between records.
+// Returns -1 if the file cannot be opened.
+int s2_load_flat(const char *path, std::vector<uint8_t> &flat)
+{
+    s2_reader *r = s2_reader_open(path);
+    if (!r) return -1;
+    const char *seq;
+    int64_t l;
+    while ((l = s2_reader_next(r, &seq)) >= 0) {
+        flat.insert(flat.end(), (const uint8_t *)seq, (const uint8_t *)seq + l);
+        flat.push_back('\n');
+    }
+    s2_reader_close(r);
+    return 0;
+}
+
+struct WorkItem { std::string path; int col; bool skip; };
+
+// reads the newline separated list exactly like the reference: getline, cut at the first '\n' only
+static int read_list(const char *list_file, int col, const char *skip_file, std::vector<WorkItem> &out)
+{
+    FILE *fp = fopen(list_file, "r");
+    if (!fp) {
+        fprintf(stderr, "could not read file %s in GEN_all_kmer_counts()\n", list_file);   // src/genome_compare.c:125,159
+        return -1;
+    }
+    char *line = nullptr; size_t cap = 0;
+    while (getline(&line, &cap, fp) != -1) {
+        char *pos = strchr(line, '\n');
+        if (pos) *pos = '\0';
+        out.push_back({ line, col, skip_file && strcmp(skip_file, line) == 0 });
+    }
+    free(line);
+    fclose(fp);
+    return 0;
+}
+
+struct BatchWriter {
+    s2_ctx *ctx; s2_table *table;
+    uint8_t *buf = nullptr; uint64_t cap = 0, used = 0; int col = -1;
+    bool failed = false;
+
+    bool flush()
+    {
+        if (!buf) return true;
+        int rc = used ? s2_batch_submit_count(ctx, table, buf, used, col) : s2_batch_release(ctx, buf);
+        buf = nullptr; used = 0;
+        if (rc) failed = true;
+        return rc == 0;
+    }
+    bool ensure(int want_col)
+    {
+        if (buf && col != want_col && !flush()) return false;
+        if (!buf) {
+            buf = s2_batch_acquire(ctx, &cap);
+            if (!buf) { failed = true; return false; }
+            used = 0; col = want_col;
+        }
+        return true;
+    }
+    // append one record (+ separator); records longer than the space left are split with a 30 byte
+    // overlap so that every 31-byte window lands in exactly one batch
+    bool append(const char *seq, uint64_t len, int want_col)
+    {
+        if (len < S2_K) return true;                       // src/genome_compare.c:204: no window fits
+        while (len) {
+            if (!ensure(want_col)) return false;
+            if (cap - used < 4096 && used) { if (!flush()) return false; continue; }
+            const uint64_t space = cap - used - 1;
+            const uint64_t take = len < space ? len : space;
+            memcpy(buf + used, seq, take);
+            used += take;
+            if (take < len) {
+                if (!flush()) return false;
+                seq += take - (S2_K - 1); len -= take - (S2_K - 1);
+            } else {
+                buf[used++] = '\n';
+                len = 0;
+            }
+        }
+        return true;
+    }
+};
+
+extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
+{
+    char *A_file = nullptr, *B_file = nullptr, *C_file = nullptr, *r_file = nullptr, *p_file = nullptr;
+    int c;
+    optind = 1;
+    while ((c = getopt(argc, argv, "A:B:C:r:p:Hhud")) != EOF)     // src/kmer_scrub_count.c:52
+        switch (c) {
+        case 'A': A_file = optarg; break;
+        case 'B': B_file = optarg; break;
+        case 'C': C_file = optarg; break;
+        case 'r': r_file = optarg; break;
+        case 'p': p_file = optarg; break;
+        case 'd': break;                                         // parsed and ignored (:63)
+        case 'u': count_usage(); break;                          // usage, but no exit (:64-66)
+        case 'h': count_usage(); break;
+        default: count_usage(); break;
+        }
+    if (!r_file || !A_file || !B_file) { count_usage(); return 1; }   // :72-75
+
+    FILE *progress = nullptr;
+    if (p_file) {
+        progress = fopen(p_file, "w");
+        if (!progress) { fprintf(stderr, "could not open progress file %s\n", p_file); return EXIT_FAILURE; }
+        fprintf(progress, "adding kmer counts for:\n");          // :84
+    }
+    auto fail = [&](const char *msg) {
+        if (msg) fprintf(stderr, "%s\n", msg);
+        if (progress) fclose(progress);                           // exit() would flush it the same way
+        return EXIT_FAILURE;
+    };
+
+    const auto t_start = std::chrono::steady_clock::now();
+    int n_threads = s2_env_int("S2_THREADS", 0);
+    if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads > 16) n_threads = 16; if (n_threads < 1) n_threads = 1; }
+    s2_ctx *ctx = s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 64) << 20, n_threads + 2);
+    if (!ctx) return fail(s2_last_error());
+
+    // ---- table from -r (GEN_hash_sequences_set_count_vec, default 1 / increment 1 / column 0 / 4 wide)
+    std::vector<uint8_t> flat;
+    if (s2_load_flat(r_file, flat) != 0) {
+        fprintf(stderr, "could not read file %s GEN_hash_sequences_set_count_vec()\n", r_file);   // src/genome_compare.c:986
+        return fail(nullptr);
+    }
+    const char *load_env = getenv("S2_LOAD");
+    s2_table *table = s2_table_build(ctx, flat.data(), flat.size(), 4, load_env ? atof(load_env) : 0.0, 0);
+    if (!table) return fail(s2_last_error());
+    std::vector<uint8_t>().swap(flat);
+    const auto t_built = std::chrono::steady_clock::now();
+
+    // ---- work list: -A into column 1, -B into column 2, -C (skipping -r itself) into column 3
+    // The reference opens each list only when it gets to it, so an unreadable later list is reported
+    // after the earlier lists have been scanned; the output (nothing on stdout, EXIT_FAILURE) is the same.
+    std::vector<WorkItem> work;
+    if (read_list(A_file, 1, nullptr, work)) return fail(nullptr);
+    if (read_list(B_file, 2, nullptr, work)) return fail(nullptr);
+    if (C_file && read_list(C_file, 3, r_file, work)) return fail(nullptr);
+
+    std::mutex mu;                      // guards next / progress / stderr ordering
+    size_t next = 0;
+    std::atomic<bool> stop(false);
+    std::string open_error;
+    std::atomic<uint64_t> total_bases(0), total_lookups(0);
+
+    auto reader = [&]() {
+        BatchWriter w{ ctx, table };
+        for (;;) {
+            s2_reader *r = nullptr; int col = 0;
+            {
+                std::lock_guard<std::mutex> g(mu);
+                while (!r) {
+                    if (stop.load() || next >= work.size()) break;
+                    WorkItem &it = work[next++];
+                    if (progress) {
+                        time_t now = time(nullptr);
+                        fprintf(progress, "%s\t%s", it.path.c_str(), asctime(localtime(&now)));   // src/genome_compare.c:167-170
+                    }
+                    if (it.skip) { fprintf(stderr, "skipping %s (identical match)\n", it.path.c_str()); continue; }   // :141
+                    r = s2_reader_open(it.path.c_str());
+                    if (!r) {
+                        open_error = "could not read file " + it.path + " in GEN_calculate_kmer_count()";   // :196
+                        stop.store(true);
+                        break;
+                    }
+                    col = it.col;
+                }
+            }
+            if (!r) break;
+            const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
+            while ((l = s2_reader_next(r, &seq)) >= 0) {
+                bases += (uint64_t)l;
+                if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
+                if (!w.append(seq, (uint64_t)l, col)) { stop.store(true); break; }
+            }
+            s2_reader_close(r);
+            total_bases += bases; total_lookups += lookups;
+            if (w.failed) break;
+        }
+        if (!w.flush()) stop.store(true);
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < n_threads; ++i) pool.emplace_back(reader);
+    reader();
+    for (auto &t : pool) t.join();
+
+    s2_scan_stats st = {};
+    if (s2_sync(ctx, &st)) return fail(s2_last_error());
+    if (!open_error.empty()) return fail(open_error.c_str());
+    if (stop.load()) return fail(s2_last_error());
+    const auto t_scanned = std::chrono::steady_clock::now();
+
+    // ---- print_hash_counts: rows in the reference table's slot order
+    const uint64_t n = s2_table_n_keys(table);
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> djb2(n), order(n), cols[4];
+    if (s2_table_export(table, keys.data(), djb2.data())) return fail(s2_last_error());
+    const int n_print = C_file ? 4 : 3;
+    const uint32_t *colp[4] = { nullptr, nullptr, nullptr, nullptr };
+    for (int k = 0; k < n_print; ++k) {
+        cols[k].resize(n);
+        if (s2_table_counts_fetch(table, k, cols[k].data())) return fail(s2_last_error());
+        colp[k] = cols[k].data();
+    }
+    if (s2_roworder_emulate(djb2.data(), n, 0, order.data(), nullptr)) return fail(s2_last_error());
+    if (s2_format_count_table(stdout, keys.data(), order.data(), n, colp, n_print, n_threads)) return fail(s2_last_error());
+    fflush(stdout);
+    const auto t_done = std::chrono::steady_clock::now();
+
+    if (s2_env_int("S2_STATS", 0)) {
+        auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+        double kms = 0; uint64_t kl = 0;
+        s2_kernel_time(ctx, &kms, &kl, 0);
+        fprintf(stderr, "[s2] keys=%llu build=%.3fs scan=%.3fs print=%.3fs bases=%llu lookups=%llu hits=%llu "
+                        "kernel_ms=%.3f launches=%llu scan_Gbases_per_s=%.3f\n",
+                (unsigned long long)n, sec(t_start, t_built), sec(t_built, t_scanned), sec(t_scanned, t_done),
+                (unsigned long long)total_bases.load(), (unsigned long long)total_lookups.load(),
+                (unsigned long long)st.hits, kms, (unsigned long long)kl,
+                total_bases.load() / 1e9 / std::max(1e-9, sec(t_built, t_scanned)));
+    }
+    s2_table_free(table);
+    s2_shutdown(ctx);
+    if (progress) fclose(progress);
+    return 0;
+}

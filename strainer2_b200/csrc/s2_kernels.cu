@@ -1,0 +1,466 @@
+// s2_kernels.cu - hand-written sm_100a kernels for the strainer2 k-mer scan path.
+//
+// What they replace in the reference (paths under /root/reference/):
+//   scan kernels   : the per-window loop of GEN_calculate_kmer_count  src/genome_compare.c:213-229
+//                    and pass 1 of quantify_hits_PE                    src/strain_detect.c:465-491,514-539
+//   build kernels  : GEN_hash_sequences_set_count_vec                  src/genome_compare.c:967-1030
+//   probe          : BIO_searchHash + hashU                            src/BIO_hash.c:161-172,208-216
+//
+// This path is hashing + random access over bytes: HBM/L2-bound integer work, so no tensor cores.
+// Design: one warp owns a 512-base tile of the flat ASCII stream; every lane packs
+// 16 bases with one 128-bit load, neighbours' packed words arrive by warp shuffle (the 30-base halo),
+// forward and reverse-complement k-mers are funnel-shift extractions from three packed words, the
+// canonical k-mer is an integer max, and the probe is ONE 256-bit load of a 32-byte fingerprint
+// bucket tested with 8 HSET2 (half2 ==) instructions.  Only fingerprint matches (true hits and
+// ~2^-15 false ones) touch the key array and the counters, in a compacted slow path.
+#include "s2_kernels.cuh"
+#include "s2_kmer.cuh"
+#include <cuda_fp16.h>
+
+#define S2_THREADS 256
+#define S2_NONE 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld_bucket256(const uint16_t *fp, uint32_t bucket, uint32_t (&x)[8])
+{
+    const uint16_t *p = fp + (uint64_t)bucket * S2_BUCKET_SLOTS;
+    // one 32-byte sector, read-only path, do not allocate in L1 (the table never fits, the input does)
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "l"(p));
+}
+
+__device__ __forceinline__ uint32_t fp_any_match(const uint32_t (&x)[8], uint32_t fp2)
+{
+    const __half2 f = *reinterpret_cast<const __half2 *>(&fp2);
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m |= __heq2_mask(*reinterpret_cast<const __half2 *>(&x[i]), f);
+    return m;
+}
+
+// 16 bases of the stream -> packed word + validity mask; bytes at or beyond n_bytes are invalid.
+// The buffer must be 16-byte aligned and readable up to the next multiple of 16 after n_bytes.
+__device__ __forceinline__ void load_chunk(const uint8_t *__restrict__ bases, uint64_t n_bytes, uint64_t chunk,
+                                           uint32_t &w, uint32_t &m)
+{
+    const uint64_t s = chunk * 16;
+    w = 0; m = 0;
+    if (s < n_bytes) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bases) + chunk);
+        s2_pack16(v.x, v.y, v.z, v.w, &w, &m);
+        const uint64_t rem = n_bytes - s;
+        if (rem < 16) m &= (0xFFFFu << (16 - (unsigned)rem)) & 0xFFFFu;
+    }
+}
+
+// One warp tile = 32 chunks = 512 bases.  After this call lane L holds the packed words / masks of
+// chunks L, L+1, L+2 of the tile (48 bases = its 16 window starts + the 30-base halo).  The two chunks
+// past the tile are loaded by lanes 0 and 1 and handed to lanes 30/31 by shuffle.
+__device__ __forceinline__ void load_tile(const uint8_t *__restrict__ bases, uint64_t n_bytes, uint64_t tile,
+                                          int lane, uint32_t &w0, uint32_t &w1, uint32_t &w2,
+                                          uint32_t &m0, uint32_t &m1, uint32_t &m2)
+{
+    const uint64_t chunk0 = tile * 32;
+    load_chunk(bases, n_bytes, chunk0 + lane, w0, m0);
+    uint32_t wx = 0, mx = 0;
+    if (lane < 2) load_chunk(bases, n_bytes, chunk0 + 32 + lane, wx, mx);
+    const uint32_t a1 = __shfl_sync(0xFFFFFFFFu, w0, (lane + 1) & 31), b1 = __shfl_sync(0xFFFFFFFFu, wx, (lane + 1) & 31);
+    const uint32_t a2 = __shfl_sync(0xFFFFFFFFu, w0, (lane + 2) & 31), b2 = __shfl_sync(0xFFFFFFFFu, wx, (lane + 2) & 31);
+    const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, m0, (lane + 1) & 31), d1 = __shfl_sync(0xFFFFFFFFu, mx, (lane + 1) & 31);
+    const uint32_t c2 = __shfl_sync(0xFFFFFFFFu, m0, (lane + 2) & 31), d2 = __shfl_sync(0xFFFFFFFFu, mx, (lane + 2) & 31);
+    w1 = lane < 31 ? a1 : b1;  m1 = lane < 31 ? c1 : d1;
+    w2 = lane < 30 ? a2 : b2;  m2 = lane < 30 ? c2 : d2;
+}
+
+// canonical k-mer of window j (0..15) of the lane's 48 bases; r0:r1:r2 is the reverse complement
+// of w0:w1:w2, so the window's reverse complement starts at base 17-j of it.
+__device__ __forceinline__ uint64_t window_canon(uint32_t w0, uint32_t w1, uint32_t w2,
+                                                 uint32_t r0, uint32_t r1, uint32_t r2, unsigned j)
+{
+    return s2_canonical(s2_extract31(w0, w1, w2, j), s2_extract31(r0, r1, r2, 17u - j));
+}
+
+// exact probe (slow path, flagging, tests): fingerprint bucket -> key compare -> slot
+__device__ __forceinline__ bool probe_exact(const S2TableView &t, uint64_t canon, uint32_t &slot_out, uint64_t &key_out)
+{
+    const s2_hash_t hh = s2_hash(canon);
+    uint32_t b = s2_bucket_of(hh.h, t.n_buckets);
+    for (;;) {
+        uint32_t x[8];
+        ld_bucket256(t.fp, b, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if ((x[i] & 0xFFFFu) == hh.fp) {
+                const uint32_t slot = b * S2_BUCKET_SLOTS + 2 * i;
+                const uint64_t key = t.keys[slot];
+                if ((key & S2_KMER_MASK) == canon) { slot_out = slot; key_out = key; return true; }
+            }
+            if ((x[i] >> 16) == hh.fp) {
+                const uint32_t slot = b * S2_BUCKET_SLOTS + 2 * i + 1;
+                const uint64_t key = t.keys[slot];
+                if ((key & S2_KMER_MASK) == canon) { slot_out = slot; key_out = key; return true; }
+            }
+        }
+        if ((x[7] >> 16) == 0) return false;          // slots fill in order: last slot empty => bucket not full
+        b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan + probe + count   (the hot kernel)
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(S2_THREADS, 2)
+s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView t,
+               uint32_t *__restrict__ counts_col, S2DetectOut dout, unsigned long long *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_tiles = (n_bytes + 511) / 512;
+    uint32_t n_hits = 0, n_valid = 0;
+
+    for (uint64_t tile = gwarp; tile < n_tiles; tile += n_warps) {
+        uint32_t w0, w1, w2, m0, m1, m2;
+        load_tile(bases, n_bytes, tile, lane, w0, w1, w2, m0, m1, m2);
+        const uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
+        uint32_t cand = 0;                                   // windows that need the exact slow path
+
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t x[4][8];
+            uint32_t fp2[4];
+            bool valid[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = 4 * g + u;
+                valid[u] = s2_window_valid(m0, m1, m2, j);
+                const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
+                const s2_hash_t hh = s2_hash(canon);
+                fp2[u] = hh.fp * 0x00010001u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[u][i] = 0;
+                if (valid[u]) ld_bucket256(t.fp, s2_bucket_of(hh.h, t.n_buckets), x[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t any = fp_any_match(x[u], fp2[u]);
+                const bool full = (x[u][7] >> 16) != 0;
+                if (valid[u] && (any != 0 || full)) cand |= 1u << (4 * g + u);
+                n_valid += valid[u];
+            }
+        }
+
+        // slow path, compacted: every round resolves at most one pending window per lane
+        while (__any_sync(0xFFFFFFFFu, cand != 0)) {
+            if (cand) {
+                const unsigned j = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
+                uint32_t slot; uint64_t key;
+                if (probe_exact(t, canon, slot, key)) {
+                    ++n_hits;
+                    if (MODE == S2_MODE_COUNT) {
+                        atomicAdd(&counts_col[slot], 1u);                 // count[vec_column] += 1
+                    } else {
+                        const uint64_t pos = tile * 512 + (uint64_t)lane * 16 + j;
+                        uint32_t lo = 0, hi = dout.n_rec;                 // record r: rec_off[r] <= pos < rec_off[r+1]
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (dout.rec_off[mid] <= pos) lo = mid; else hi = mid;
+                        }
+                        atomicAdd(&dout.read_hits[lo], 1u);
+                        if (key & S2_INFORMATIVE_BIT) {
+                            atomicAdd(&dout.read_inf[lo], 1u);
+                            const unsigned long long idx = atomicAdd(dout.inf_count, 1ull);
+                            if (idx < dout.inf_cap) dout.inf_pos[idx] = pos;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
+    n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
+    if (lane == 0 && stats) {
+        if (n_hits) atomicAdd(&stats[0], (unsigned long long)n_hits);
+        if (n_valid) atomicAdd(&stats[1], (unsigned long long)n_valid);
+    }
+}
+
+int s2_scan_blocks_per_sm(int mode)
+{
+    int n = 0;
+    if (mode == S2_MODE_COUNT)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, s2_scan_kernel<S2_MODE_COUNT>, S2_THREADS, 0);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, s2_scan_kernel<S2_MODE_DETECT>, S2_THREADS, 0);
+    return n > 0 ? n : 1;
+}
+
+void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t, int col,
+                          unsigned long long *stats, int grid_blocks, cudaStream_t stream)
+{
+    if (n_bytes == 0) return;
+    S2DetectOut none = {};
+    s2_scan_kernel<S2_MODE_COUNT><<<grid_blocks, S2_THREADS, 0, stream>>>(
+        bases, n_bytes, t, t.counts + (uint64_t)col * t.n_slots, none, stats);
+}
+
+void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
+                           const S2DetectOut &out, unsigned long long *stats, int grid_blocks,
+                           cudaStream_t stream)
+{
+    if (n_bytes == 0) return;
+    s2_scan_kernel<S2_MODE_DETECT><<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// table build: insert-if-absent with first-occurrence position and reference count (column 0)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t table_insert(const S2TableView &t, uint64_t canon)
+{
+    const s2_hash_t hh = s2_hash(canon);
+    uint32_t b = s2_bucket_of(hh.h, t.n_buckets);
+    for (;;) {
+        for (int i = 0; i < S2_BUCKET_SLOTS; ++i) {
+            const uint32_t slot = b * S2_BUCKET_SLOTS + i;
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&t.keys[slot]);
+            if (cur == S2_EMPTY_KEY) {
+                cur = atomicCAS(reinterpret_cast<unsigned long long *>(&t.keys[slot]), S2_EMPTY_KEY, canon);
+                if (cur == S2_EMPTY_KEY) {                       // we own the slot: publish its fingerprint
+                    t.fp[slot] = (uint16_t)hh.fp;
+                    return slot;
+                }
+            }
+            if ((cur & S2_KMER_MASK) == canon) return slot;      // somebody (maybe just now) inserted it
+        }
+        b = (b + 1 == t.n_buckets) ? 0 : b + 1;                  // bucket full: linear probing by bucket
+    }
+}
+
+__global__ void __launch_bounds__(S2_THREADS)
+s2_build_insert_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView t,
+                       uint32_t *__restrict__ first_pos, uint32_t *__restrict__ slot_of_pos)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_tiles = (n_bytes + 511) / 512;
+    for (uint64_t tile = gwarp; tile < n_tiles; tile += n_warps) {
+        uint32_t w0, w1, w2, m0, m1, m2;
+        load_tile(bases, n_bytes, tile, lane, w0, w1, w2, m0, m1, m2);
+        const uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
+        for (unsigned j = 0; j < 16; ++j) {
+            const uint64_t pos = tile * 512 + (uint64_t)lane * 16 + j;
+            if (pos >= n_bytes) break;
+            uint32_t slot = S2_NONE;
+            if (s2_window_valid(m0, m1, m2, j)) {
+                slot = table_insert(t, window_canon(w0, w1, w2, r0, r1, r2, j));
+                atomicMin(&first_pos[slot], (uint32_t)pos);      // insertion order = first occurrence in file order
+                atomicAdd(&t.counts[slot], 1u);                  // column 0: default 1, +1 per repeat
+            }
+            slot_of_pos[pos] = slot;
+        }
+    }
+}
+
+void s2_launch_build_insert(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
+                            uint32_t *first_pos, uint32_t *slot_of_pos, cudaStream_t stream)
+{
+    if (n_bytes == 0) return;
+    const uint64_t n_tiles = (n_bytes + 511) / 512;
+    const uint64_t blocks = (n_tiles + (S2_THREADS / 32) - 1) / (S2_THREADS / 32);
+    s2_build_insert_kernel<<<(unsigned)(blocks < 148ull * 16 ? blocks : 148ull * 16), S2_THREADS, 0, stream>>>(
+        bases, n_bytes, t, first_pos, slot_of_pos);
+}
+
+// ---- first-occurrence ranking: flag[p] = (p is the first position of its key); rank = exclusive scan
+#define S2_RANK_PER_THREAD 4
+#define S2_RANK_PER_BLOCK (S2_THREADS * S2_RANK_PER_THREAD)
+
+__device__ __forceinline__ uint32_t rank_flag(uint64_t p, uint64_t n, const uint32_t *first_pos,
+                                              const uint32_t *slot_of_pos, uint32_t &slot)
+{
+    slot = S2_NONE;
+    if (p >= n) return 0;
+    slot = slot_of_pos[p];
+    return (slot != S2_NONE && first_pos[slot] == (uint32_t)p) ? 1u : 0u;
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t &total)
+{
+    __shared__ uint32_t warp_sums[S2_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < S2_THREADS / 32; ++i) { const uint32_t s = warp_sums[i]; if (i < wid) base += s; tot += s; }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(S2_THREADS)
+s2_rank_count_kernel(uint64_t n, const uint32_t *__restrict__ first_pos, const uint32_t *__restrict__ slot_of_pos,
+                     uint32_t *__restrict__ block_sums)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * S2_RANK_PER_BLOCK + (uint64_t)threadIdx.x * S2_RANK_PER_THREAD;
+    uint32_t c = 0, slot;
+#pragma unroll
+    for (int i = 0; i < S2_RANK_PER_THREAD; ++i) c += rank_flag(base + i, n, first_pos, slot_of_pos, slot);
+    uint32_t total;
+    block_exclusive_scan(c, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(S2_THREADS)
+s2_rank_scan_kernel(uint32_t *__restrict__ block_sums, uint32_t n_blocks, unsigned long long *__restrict__ d_n_keys)
+{
+    // single CTA: exclusive scan of the per-block counts in place, carrying across 256-element strips
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_blocks; base += S2_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, total);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *d_n_keys = carry;
+}
+
+__global__ void __launch_bounds__(S2_THREADS)
+s2_rank_write_kernel(uint64_t n, const uint32_t *__restrict__ first_pos, const uint32_t *__restrict__ slot_of_pos,
+                     const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ rank_slot)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * S2_RANK_PER_BLOCK + (uint64_t)threadIdx.x * S2_RANK_PER_THREAD;
+    uint32_t f[S2_RANK_PER_THREAD], s[S2_RANK_PER_THREAD], c = 0;
+#pragma unroll
+    for (int i = 0; i < S2_RANK_PER_THREAD; ++i) { f[i] = rank_flag(base + i, n, first_pos, slot_of_pos, s[i]); c += f[i]; }
+    uint32_t total;
+    uint32_t r = block_offsets[blockIdx.x] + block_exclusive_scan(c, total);
+#pragma unroll
+    for (int i = 0; i < S2_RANK_PER_THREAD; ++i) if (f[i]) rank_slot[r++] = s[i];
+}
+
+void s2_launch_build_rank(uint64_t n_bytes, const uint32_t *first_pos, const uint32_t *slot_of_pos,
+                          uint32_t *block_sums, uint32_t n_blocks, uint32_t *rank_slot,
+                          unsigned long long *d_n_keys, cudaStream_t stream)
+{
+    if (n_blocks == 0) { cudaMemsetAsync(d_n_keys, 0, sizeof(unsigned long long), stream); return; }
+    s2_rank_count_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(n_bytes, first_pos, slot_of_pos, block_sums);
+    s2_rank_scan_kernel<<<1, S2_THREADS, 0, stream>>>(block_sums, n_blocks, d_n_keys);
+    s2_rank_write_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(n_bytes, first_pos, slot_of_pos, block_sums, rank_slot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// export / gather / scatter / flag / lookup / pack / fill
+// ------------------------------------------------------------------------------------------------
+__global__ void s2_export_kernel(S2TableView t, const uint32_t *__restrict__ rank_slot, uint64_t n_keys,
+                                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ djb2_out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_keys) return;
+    const uint64_t k = t.keys[rank_slot[i]] & S2_KMER_MASK;
+    keys_out[i] = k;
+    djb2_out[i] = s2_djb2_of_kmer(k);          // hashU of the key's ASCII spelling, before "% M"
+}
+
+__global__ void s2_gather_kernel(const uint32_t *__restrict__ col, const uint32_t *__restrict__ rank_slot,
+                                 uint64_t n_keys, uint32_t *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_keys) out[i] = col[rank_slot[i]];
+}
+
+__global__ void s2_scatter_kernel(uint32_t *__restrict__ col, const uint32_t *__restrict__ rank_slot,
+                                  uint64_t n_keys, const uint32_t *__restrict__ in)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_keys) col[rank_slot[i]] = in[i];
+}
+
+__global__ void s2_flag_kernel(S2TableView t, const uint64_t *__restrict__ kmers, uint64_t n, uint8_t *__restrict__ found)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t slot; uint64_t key;
+    const bool hit = probe_exact(t, kmers[i] & S2_KMER_MASK, slot, key);
+    if (hit) atomicOr(reinterpret_cast<unsigned long long *>(&t.keys[slot]), S2_INFORMATIVE_BIT);
+    if (found) found[i] = hit ? 1 : 0;
+}
+
+__global__ void s2_lookup_kernel(S2TableView t, const uint64_t *__restrict__ kmers, uint64_t n, uint32_t *__restrict__ slot_out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t slot; uint64_t key;
+    slot_out[i] = probe_exact(t, kmers[i] & S2_KMER_MASK, slot, key) ? slot : S2_NONE;
+}
+
+// standalone 2-bit pack: one 128-bit coalesced load per thread -> 32-bit word + 16-bit validity mask
+__global__ void s2_pack_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes,
+                               uint32_t *__restrict__ words, uint16_t *__restrict__ masks)
+{
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk * 16 >= n_bytes) return;
+    uint32_t w, m;
+    load_chunk(bases, n_bytes, chunk, w, m);
+    words[chunk] = w;
+    masks[chunk] = (uint16_t)m;
+}
+
+__global__ void s2_fill_u32_kernel(uint32_t *p, uint64_t n, uint32_t v)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+void s2_launch_export(const S2TableView &t, const uint32_t *rank_slot, uint64_t n_keys,
+                      uint64_t *keys_out, uint32_t *djb2_out, cudaStream_t stream)
+{
+    if (n_keys) s2_export_kernel<<<blocks_for(n_keys, 256), 256, 0, stream>>>(t, rank_slot, n_keys, keys_out, djb2_out);
+}
+
+void s2_launch_gather_counts(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys,
+                             uint32_t *out, cudaStream_t stream)
+{
+    if (n_keys) s2_gather_kernel<<<blocks_for(n_keys, 256), 256, 0, stream>>>(t.counts + (uint64_t)col * t.n_slots, rank_slot, n_keys, out);
+}
+
+void s2_launch_scatter_counts(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys,
+                              const uint32_t *in, cudaStream_t stream)
+{
+    if (n_keys) s2_scatter_kernel<<<blocks_for(n_keys, 256), 256, 0, stream>>>(t.counts + (uint64_t)col * t.n_slots, rank_slot, n_keys, in);
+}
+
+void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found, cudaStream_t stream)
+{
+    if (n) s2_flag_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(t, kmers, n, found);
+}
+
+void s2_launch_lookup(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out, cudaStream_t stream)
+{
+    if (n) s2_lookup_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(t, kmers, n, slot_out);
+}
+
+void s2_launch_pack(const uint8_t *bases, uint64_t n_bytes, uint32_t *words, uint16_t *masks, cudaStream_t stream)
+{
+    const uint64_t n_chunks = (n_bytes + 15) / 16;
+    if (n_chunks) s2_pack_kernel<<<blocks_for(n_chunks, 256), 256, 0, stream>>>(bases, n_bytes, words, masks);
+}
+
+void s2_launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream)
+{
+    if (n) s2_fill_u32_kernel<<<148 * 8, 256, 0, stream>>>(p, n, v);
+}

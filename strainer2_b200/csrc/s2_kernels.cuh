@@ -1,0 +1,58 @@
+// s2_kernels.cuh - launch interfaces of the sm_100a kernels (implemented in s2_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// Device view of one strain table.  Layout in HBM (DESIGN.md "data layout"):
+//   fp     : n_buckets x 16 x uint16  - 32-byte fingerprint buckets, the only array a miss touches
+//   keys   : n_slots  x uint64        - canonical 62-bit k-mer (+ informative flag in bit 63), EMPTY = ~0
+//   counts : n_cols x n_slots x uint32 (column major) - what BIO_hash hangs off each key as unsigned[4|6]
+struct S2TableView {
+    uint16_t *fp;
+    uint64_t *keys;
+    uint32_t *counts;
+    uint32_t n_buckets;
+    uint64_t n_slots;
+    int n_cols;
+};
+
+struct S2DetectOut {
+    const uint64_t *rec_off;     // n_rec + 1 ascending byte offsets of the records inside the batch
+    uint32_t n_rec;
+    uint32_t *read_hits;         // per record: table hits                 (src/strain_detect.c:481)
+    uint32_t *read_inf;          // per record: informative hits           (src/strain_detect.c:482-483)
+    uint64_t *inf_pos;           // batch byte offsets of informative windows (unordered)
+    unsigned long long *inf_count;
+    uint64_t inf_cap;
+};
+
+enum { S2_MODE_COUNT = 0, S2_MODE_DETECT = 1 };
+
+// scan stats written by the scan kernels: [0] table hits, [1] valid (non-N) windows probed
+void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t, int col,
+                          unsigned long long *stats, int grid_blocks, cudaStream_t stream);
+void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
+                           const S2DetectOut &out, unsigned long long *stats, int grid_blocks,
+                           cudaStream_t stream);
+int  s2_scan_blocks_per_sm(int mode);
+
+// table build (one-off, not the hot path)
+void s2_launch_build_insert(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
+                            uint32_t *first_pos, uint32_t *slot_of_pos, cudaStream_t stream);
+// number of distinct keys is returned through *d_n_keys (device); rank_slot must hold >= n windows
+void s2_launch_build_rank(uint64_t n_bytes, const uint32_t *first_pos, const uint32_t *slot_of_pos,
+                          uint32_t *block_sums, uint32_t n_blocks, uint32_t *rank_slot,
+                          unsigned long long *d_n_keys, cudaStream_t stream);
+void s2_launch_export(const S2TableView &t, const uint32_t *rank_slot, uint64_t n_keys,
+                      uint64_t *keys_out, uint32_t *djb2_out, cudaStream_t stream);
+void s2_launch_gather_counts(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys,
+                             uint32_t *out, cudaStream_t stream);
+void s2_launch_scatter_counts(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys,
+                              const uint32_t *in, cudaStream_t stream);
+void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found,
+                    cudaStream_t stream);
+void s2_launch_lookup(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out,
+                      cudaStream_t stream);
+void s2_launch_pack(const uint8_t *bases, uint64_t n_bytes, uint32_t *words, uint16_t *masks,
+                    cudaStream_t stream);
+void s2_launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream);

@@ -1,0 +1,283 @@
+"""CPU-side tests (no GPU needed): the C ABI loads and exports every declared symbol, the host half of
+the library (reader, row-order replay, formatter, codecs) agrees with the oracle and the golden
+vectors, and the bit primitives shared with the kernels agree with string arithmetic."""
+import ctypes as C
+import os
+import random
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+ROOT = ou.ROOT
+
+
+def test_abi_exports_every_declared_symbol():
+    import strainer2_b200 as s2
+    from strainer2_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "strainer2_b200.h")).read()
+    declared = set(re.findall(r"\b(s2_[a-z0-9_]+)\s*\(", header))
+    declared -= {"s2_roworder_emulate()"}
+    assert len(declared) >= 40
+    for name in sorted(declared):
+        assert hasattr(s2.lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert s2.lib.s2_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import strainer2_b200 as s2
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(s2.S2Error):
+        s2.Context(0)
+
+
+def test_up2bit_codec_known_answers():
+    import strainer2_b200 as s2
+    L = ou.lib()
+    r = random.Random(11)
+    for _ in range(300):
+        n = r.randint(1, 32)
+        s = "".join(r.choice("ACGTacgtNRY") for _ in range(n)).encode()
+        v = s2.encode_2bit(s)
+        assert v == L.s2o_encode_2bit(s, n)
+        out = C.create_string_buffer(40)
+        L.s2o_decode_2bit(v, n, out)
+        assert s2.decode_2bit(v, n) == out.value
+    assert s2.encode_2bit(b"ACTG") == 0b00011011
+    assert s2.decode_2bit(0b00011011, 4) == b"ACTG"
+
+
+def test_kmer_ascii_roundtrip_and_orientation():
+    import strainer2_b200 as s2
+    r = random.Random(3)
+    assert s2.kmer_to_ascii(s2.kmer_from_ascii(b"A" * 31)) == b"T" * 31
+    assert s2.kmer_to_ascii(s2.kmer_from_ascii(b"ATGCAAATGACGCTTGTATCAGCGGATTTCA")) == b"TGAAATCCGCTGATACAAGCGTCATTTGCAT"
+    for _ in range(500):
+        w = "".join(r.choice("ACGTacgt") for _ in range(31)).encode()
+        assert s2.kmer_to_ascii(s2.kmer_from_ascii(w)) == ou.orient(w.upper())
+    assert s2.kmer_from_ascii(b"ACGTN" + b"A" * 26) is None
+
+
+def test_reader_matches_reference_parser_dumps(golden_dir):
+    import strainer2_b200 as s2
+    d = os.path.join(golden_dir, "count_edge")
+    n = 0
+    for f in sorted(os.listdir(os.path.join(d, "kseq"))):
+        src = f[:-len(".dump.gz")]
+        rd = s2.Reader(os.path.join(d, src))
+        out = []
+        while True:
+            ret, seq = rd.next()
+            if ret < 0:
+                out.append(b"%d\t%d\t<END>\n" % (ret, len(seq)))
+                break
+            out.append(b"%d\t%d\t%s\n" % (ret, len(seq), seq))
+        rd.close()
+        assert b"".join(out) == ou.gunzip(os.path.join(d, "kseq", f)), src
+        n += 1
+    assert n >= 10
+
+
+def test_reader_randomised_against_oracle_reader(tmp_path):
+    """fuzz: random mixes of FASTA/FASTQ fragments, CR/LF, blank lines, stray '>' '@' '+'"""
+    import strainer2_b200 as s2
+    r = random.Random(99)
+    pieces = [">h1 c\n", "@q1\n", "ACGT", "acgtn", "\n", "\r\n", "+\n", "+x\n", "IIII", ">", "@", " ", "\t", "N" * 40,
+              "ACGTACGTACGTACGTACGTACGTACGTACGTACGT\n", "\r", "\n\n", "+", "GATTACA\r\n"]
+    for t in range(120):
+        text = "".join(r.choice(pieces) for _ in range(r.randint(0, 60)))
+        p = tmp_path / f"f{t}.txt"
+        p.write_bytes(text.encode())
+        o = ou.oracle_cli(["kseq", str(p)]).stdout
+        rd = s2.Reader(str(p))
+        out = []
+        while True:
+            ret, seq = rd.next()
+            if ret < 0:
+                out.append(b"%d\t%d\t<END>\n" % (ret, len(seq)))
+                break
+            out.append(b"%d\t%d\t%s\n" % (ret, len(seq), seq))
+        rd.close()
+        assert b"".join(out) == o, text
+
+
+def _djb2_str(s: bytes) -> int:
+    h = 5381
+    for c in s:
+        h = (h * 33 + c) & 0xFFFFFFFF
+    return h
+
+
+def test_roworder_replay_matches_oracle_table_small_capacity():
+    """the doubling rule (N++ >= M/2) and re-insertion order, exercised with tiny capacities"""
+    import strainer2_b200 as s2
+    L = ou.lib()
+    r = random.Random(8)
+    for cap in (10, 16, 37, 100):
+        keys = list({("".join(r.choice("ACGT") for _ in range(31))).encode() for _ in range(r.randint(1, 400))})
+        r.shuffle(keys)
+        t = L.s2o_table_new(cap, 4)
+        L.s2o_table_add.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint)]
+        L.s2o_table_key_at.restype = C.c_char_p
+        L.s2o_table_key_at.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
+        for k in keys:
+            L.s2o_table_add(t, k, None)
+        want = [L.s2o_table_key_at(t, i, None) for i in range(len(keys))]
+        order, final_cap = s2.roworder_emulate([_djb2_str(k) for k in keys], cap)
+        assert [keys[i] for i in order] == want
+        assert final_cap == L.s2o_table_capacity(t)
+        L.s2o_table_free(t)
+
+
+def test_roworder_and_formatter_reproduce_golden_table(golden_dir, tmp_path):
+    """rebuild expected_ABC.tsv from (keys in first-occurrence order, counts) with the product's
+    row-order replay + formatter; the key list comes from the oracle, the bytes must equal the
+    reference's."""
+    import strainer2_b200 as s2
+    d = os.path.join(golden_dir, "count_edge")
+    want = open(os.path.join(d, "expected_ABC.tsv"), "rb").read()
+    kmers, vals = ou.parse_table(want)
+    # first-occurrence order = order of first appearance in the reference genome
+    rd = s2.Reader(os.path.join(d, "ref.fa.gz"))
+    seen, first = set(), []
+    while True:
+        ret, seq = rd.next()
+        if ret < 0:
+            break
+        s = seq.upper()
+        for i in range(len(s) - 30):
+            w = s[i:i + 31]
+            if b"N" in w:
+                continue
+            k = ou.orient(w)
+            if k not in seen:
+                seen.add(k)
+                first.append(k)
+    rd.close()
+    assert len(first) == len(kmers)
+    row_of = {k: i for i, k in enumerate(kmers)}
+    keys = np.array([s2.kmer_from_ascii(k) for k in first], dtype=np.uint64)
+    assert all(s2.kmer_to_ascii(int(k)) == f for k, f in zip(keys, first))
+    djb2 = np.array([_djb2_str(k) for k in first], dtype=np.uint32)
+    order, _ = s2.roworder_emulate(djb2)
+    cols = [np.array([vals[row_of[k]][c] for k in first], dtype=np.uint32) for c in range(4)]
+    out = tmp_path / "t.tsv"
+    s2.format_count_table(str(out), keys, order, cols, n_threads=3)
+    assert out.read_bytes() == want
+
+
+def test_formatter_prints_counters_with_percent_d(tmp_path):
+    import strainer2_b200 as s2
+    keys = np.array([s2.kmer_from_ascii(b"T" * 31)], dtype=np.uint64)
+    cols = [np.array([v], dtype=np.uint32) for v in (1, 0x80000000, 0xFFFFFFFF)]
+    out = tmp_path / "t.tsv"
+    s2.format_count_table(str(out), keys, np.array([0], np.uint32), cols)
+    assert out.read_bytes().split(b"\n")[1] == b"T" * 31 + b"\t1\t-2147483648\t-1"
+
+
+# ---- bit primitives shared with the kernels, compiled for the host ---------------------------------
+@pytest.fixture(scope="module")
+def sim(tmp_path_factory):
+    so = tmp_path_factory.mktemp("sim") / "libsim.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                           os.path.join(ROOT, "tests", "sim", "kmer_prims_harness.cpp"), "-o", str(so)])
+    L = C.CDLL(str(so))
+    L.sim_rc16.restype = C.c_uint32
+    L.sim_rc16.argtypes = [C.c_uint32]
+    L.sim_extract31.restype = C.c_uint64
+    L.sim_extract31.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint]
+    L.sim_revcomp31.restype = C.c_uint64
+    L.sim_revcomp31.argtypes = [C.c_uint64]
+    L.sim_djb2.restype = C.c_uint32
+    L.sim_djb2.argtypes = [C.c_uint64]
+    L.sim_window_canon.restype = C.c_uint64
+    L.sim_window_canon.argtypes = [C.c_char_p, C.c_uint, C.POINTER(C.c_int)]
+    L.sim_hash.argtypes = [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.sim_bucket.restype = C.c_uint32
+    L.sim_bucket.argtypes = [C.c_uint32, C.c_uint32]
+    return L
+
+
+CODE = {65: 0, 67: 1, 71: 2, 84: 3}
+
+
+def test_pack16_all_byte_values(sim):
+    r = random.Random(1)
+    for t in range(400):
+        b = bytes(r.randrange(256) for _ in range(16)) if t % 2 else bytes(r.choice(b"ACGTacgtNn\n>@RYKM-. ") for _ in range(16))
+        w, m = C.c_uint32(), C.c_uint32()
+        sim.sim_pack16(b, C.byref(w), C.byref(m))
+        for i, c in enumerate(b):
+            up = c - 32 if 97 <= c <= 122 else c
+            ok = up in CODE
+            assert ((m.value >> (15 - i)) & 1) == (1 if ok else 0), (b, i)
+            if ok:
+                assert ((w.value >> (30 - 2 * i)) & 3) == CODE[up]
+    # every single byte value in every position class
+    for c in range(256):
+        b = bytes([c] * 16)
+        w, m = C.c_uint32(), C.c_uint32()
+        sim.sim_pack16(b, C.byref(w), C.byref(m))
+        up = c - 32 if 97 <= c <= 122 else c
+        assert m.value == (0xFFFF if up in CODE else 0), c
+
+
+def test_window_canon_matches_reference_orientation(sim):
+    import strainer2_b200 as s2
+    r = random.Random(2)
+    for _ in range(300):
+        s = bytes(r.choice(b"ACGTacgt" if r.random() < 0.8 else b"ACGTN\n") for _ in range(48))
+        for j in range(16):
+            valid = C.c_int()
+            k = sim.sim_window_canon(s, j, C.byref(valid))
+            w = s[j:j + 31].upper()
+            good = all(c in b"ACGT" for c in w)
+            assert valid.value == (1 if good else 0)
+            if good:
+                assert s2.kmer_to_ascii(k) == ou.orient(w), (s, j)
+
+
+def test_revcomp_and_djb2_of_packed_kmer(sim):
+    import strainer2_b200 as s2
+    L = ou.lib()
+    r = random.Random(4)
+    for _ in range(500):
+        w = "".join(r.choice("ACGT") for _ in range(31)).encode()
+        v = 0
+        for c in w:
+            v = (v << 2) | CODE[c]
+        rc = w.translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
+        vr = 0
+        for c in rc:
+            vr = (vr << 2) | CODE[c]
+        assert sim.sim_revcomp31(v) == vr
+        assert sim.sim_djb2(v) == L.s2o_djb2(w)
+    assert sim.sim_djb2(s2.kmer_from_ascii(b"T" * 31)) == 3948423441
+
+
+def test_hash_spreads_real_kmers(sim):
+    """bucket occupancy of canonical k-mers from a random genome stays near Poisson and fingerprints
+    are legal fp16 'normal' bit patterns (0x0400..0x7BFF), never 0"""
+    import strainer2_b200 as s2
+    rng = np.random.default_rng(5)
+    n = 200000
+    keys = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    nb = n // 8                                     # load 0.5 with 16-slot buckets
+    cnt = np.zeros(nb, dtype=np.int64)
+    h, fp = C.c_uint32(), C.c_uint32()
+    fps = set()
+    for k in keys[:50000]:
+        sim.sim_hash(int(k), C.byref(h), C.byref(fp))
+        assert 0x0400 <= fp.value <= 0x7BFF
+        fps.add(fp.value)
+        cnt[sim.sim_bucket(h.value, nb)] += 1
+    assert len(fps) > 20000
+    lam = 50000 / nb
+    assert abs(cnt.mean() - lam) < 1e-9
+    assert cnt.var() < 1.3 * lam        # Poisson variance = lam
