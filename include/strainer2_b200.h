@@ -91,6 +91,12 @@ int         s2_table_lookup(s2_table *t, const uint64_t *kmers, uint64_t n, uint
  * If on_device, `bases` must be 16-byte aligned and readable up to the next multiple of 16. */
 int         s2_scan_count(s2_ctx *ctx, s2_table *t, const void *bases, uint64_t n_bytes, int col,
                           int on_device, s2_scan_stats *stats);
+/* enqueue-only form for device-resident batches: launches on the context's first stream and
+ * returns immediately; s2_sync() waits and returns the accumulated stats. */
+int         s2_scan_count_enqueue(s2_ctx *ctx, s2_table *t, const void *dev_bases, uint64_t n_bytes, int col);
+/* pinned host memory for batches handed to s2_scan_count(on_device = 0) at full PCIe rate */
+void       *s2_pinned_alloc(uint64_t n_bytes);
+void        s2_pinned_free(void *p);
 /* pipelined form: pinned double(+)-buffered batches, H2D copy and kernel overlapped on a stream per
  * lane.  acquire blocks until a lane is free and returns its pinned host buffer. */
 uint8_t    *s2_batch_acquire(s2_ctx *ctx, uint64_t *capacity);
@@ -115,6 +121,9 @@ int         s2_scan_detect(s2_ctx *ctx, s2_table *t, const void *bases, uint64_t
 /* CUDA-event time (ms) and launch count of the scan kernels since the last reset, measured on the
  * streams they were launched on. */
 int         s2_kernel_time(s2_ctx *ctx, double *ms, uint64_t *launches, int reset);
+/* four user events on the stream the enqueue-only scans run on: bracket a timed region on the device */
+int         s2_event_record(s2_ctx *ctx, int which);
+int         s2_event_elapsed_ms(s2_ctx *ctx, int from, int to, double *ms);
 
 /* ---------------------------------------------------------------- codecs -------------------- */
 /* bit-compatible with encode_DNA_2_bit / decode_DNA_2_bit (src/up2bit.c:53-98): A0 C1 T2 G3 */

@@ -7,7 +7,7 @@ compute and NO fallback: importing it without the built library raises.
 """
 from ._lib import lib, LIB_PATH, S2Error            # noqa: F401  (raises if the .so is missing)
 from .api import (                                  # noqa: F401
-    K, Context, StrainTable, Reader, ScanStats,
+    K, Context, StrainTable, Reader, ScanStats, PinnedBuffer,
     encode_2bit, decode_2bit, kmer_from_ascii, kmer_to_ascii,
     roworder_emulate, format_count_table, load_flat, flatten_records,
     run_kmer_scrub_count, run_strain_detect, BIN_DIR,

@@ -51,6 +51,11 @@ SIGNATURES = {
     "s2_table_lookup": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u32p]),
     "s2_scan_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
                                 C.POINTER(ScanStatsStruct)]),
+    "s2_scan_count_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
+    "s2_pinned_alloc": (C.c_void_p, [C.c_uint64]),
+    "s2_pinned_free": (None, [C.c_void_p]),
+    "s2_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "s2_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "s2_batch_acquire": (C.c_void_p, [C.c_void_p, c_u64p]),
     "s2_batch_submit_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "s2_batch_release": (C.c_int, [C.c_void_p, C.c_void_p]),

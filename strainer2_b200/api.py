@@ -75,6 +75,24 @@ class Context:
         check(lib.s2_scan_count(self.h, table.h, p, n, col, dev, C.byref(st)), "s2_scan_count")
         return ScanStats(st.hits, st.valid_windows)
 
+    def scan_count_enqueue(self, table, dev_tensor, col):
+        """device-resident batch, no host synchronisation (bench: K launches between two events)"""
+        check(lib.s2_scan_count_enqueue(self.h, table.h, dev_tensor.data_ptr(),
+                                        dev_tensor.numel() * dev_tensor.element_size(), col), "s2_scan_count_enqueue")
+
+    def scan_count_ptr(self, table, ptr, n_bytes, col, on_device=0):
+        st = ScanStatsStruct()
+        check(lib.s2_scan_count(self.h, table.h, ptr, n_bytes, col, on_device, C.byref(st)), "s2_scan_count")
+        return ScanStats(st.hits, st.valid_windows)
+
+    def event_record(self, which):
+        check(lib.s2_event_record(self.h, which), "s2_event_record")
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        check(lib.s2_event_elapsed_ms(self.h, a, b, C.byref(ms)), "s2_event_elapsed_ms")
+        return ms.value
+
     def batch_acquire(self):
         cap = C.c_uint64()
         p = lib.s2_batch_acquire(self.h, C.byref(cap))
@@ -239,6 +257,23 @@ def flatten_records(records):
         off.append(off[-1] + len(s) + 1)
     flat = np.frombuffer(b"".join(s + b"\n" for s in records), dtype=np.uint8).copy() if records else np.zeros(0, np.uint8)
     return flat, np.asarray(off, dtype=np.uint64)
+
+
+class PinnedBuffer:
+    """page-locked host memory (cudaHostAlloc) exposed as a numpy uint8 array"""
+
+    def __init__(self, n_bytes):
+        self.ptr = lib.s2_pinned_alloc(n_bytes)
+        if not self.ptr:
+            raise S2Error("s2_pinned_alloc: " + _lib.last_error())
+        self.n = n_bytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * n_bytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib.s2_pinned_free(self.ptr)
+            self.ptr = None
 
 
 # ---- codecs / host helpers --------------------------------------------------------------------

@@ -78,6 +78,9 @@ struct s2_ctx {
     int grid_count = 0, grid_detect = 0;
     double kernel_ms = 0.0;
     uint64_t kernel_launches = 0;
+    // enqueue-only scans on lane 0 (device-resident batches): one event pair per launch, harvested at sync
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    cudaEvent_t user_ev[4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 extern "C" int s2_device_count(void)
@@ -117,6 +120,7 @@ extern "C" s2_ctx *s2_init(int device, uint64_t batch_bytes, int n_lanes)
     CKN(cudaMalloc((void **)&c->d_stats, 2 * sizeof(unsigned long long)));
     CKN(cudaMemset(c->d_stats, 0, 2 * sizeof(unsigned long long)));
     CKN(cudaHostAlloc((void **)&c->h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    for (auto &e : c->user_ev) CKN(cudaEventCreate(&e));
     c->grid_count = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_COUNT);
     c->grid_detect = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_DETECT);
     return c;
@@ -134,6 +138,9 @@ extern "C" void s2_shutdown(s2_ctx *c)
         if (l.h_buf) cudaFreeHost(l.h_buf);
         if (l.stream) cudaStreamDestroy(l.stream);
     }
+    for (auto &e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : c->user_ev) if (e) cudaEventDestroy(e);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     delete c;
@@ -155,6 +162,21 @@ static int lane_retire(s2_ctx *c, Lane &l)
         l.timed = false;
     }
     l.state = LANE_FREE;
+    return 0;
+}
+
+// fold the event pairs of finished enqueue-only launches into the kernel time (caller holds c->mu;
+// lane 0's stream must have been synchronised)
+static int harvest_events(s2_ctx *c)
+{
+    for (auto &e : c->ev_pending) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e.first, e.second));
+        c->kernel_ms += ms;
+        c->kernel_launches += 1;
+        c->ev_free.push_back(e);
+    }
+    c->ev_pending.clear();
     return 0;
 }
 
@@ -395,26 +417,89 @@ extern "C" int s2_scan_count(s2_ctx *c, s2_table *t, const void *bases, uint64_t
         if (lane_retire(c, l)) return -1;
         return fetch_stats(c, l.stream, stats);
     }
-    // host input: stream it through the pinned lanes in batch_bytes pieces overlapping by 30 bytes
-    // (a window never straddles two pieces un-scanned: the next piece restarts 30 bytes early)
+    // host input: H2D straight from the caller's buffer (pinned memory from s2_pinned_alloc gives
+    // full PCIe rate) in batch_bytes pieces, one lane per piece, copy and kernel overlapped across
+    // lanes.  Pieces overlap by 30 bytes so every 31-byte window lies in exactly one piece.
     s2_scan_stats dummy;
     if (s2_sync(c, &dummy)) return -1;
     const uint8_t *src = (const uint8_t *)bases;
     uint64_t off = 0;
     while (off < n_bytes) {
-        uint64_t cap = 0;
-        uint8_t *buf = s2_batch_acquire(c, &cap);
-        if (!buf) return -1;
-        uint64_t take = std::min<uint64_t>(cap, n_bytes - off);
-        memcpy(buf, src + off, take);
-        if (s2_batch_submit_count(c, t, buf, take, col)) return -1;
+        const uint64_t take = std::min<uint64_t>(c->batch_bytes, n_bytes - off);
+        {
+            std::lock_guard<std::mutex> g(c->mu);
+            Lane *l = nullptr;
+            for (auto &x : c->lanes) if (x.state == LANE_FREE) { l = &x; break; }
+            if (!l) {
+                for (auto &x : c->lanes) if (x.state == LANE_INFLIGHT && (!l || x.seq < l->seq)) l = &x;
+                if (!l) { s2_set_error("s2_scan_count: no lane available"); return -1; }
+                if (lane_retire(c, *l)) return -1;
+            }
+            CK(cudaMemcpyAsync(l->d_buf, src + off, take, cudaMemcpyHostToDevice, l->stream));
+            CK(cudaEventRecord(l->k0, l->stream));
+            s2_launch_scan_count(l->d_buf, take, t->v, col, c->d_stats, c->grid_count, l->stream);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(l->k1, l->stream));
+            l->state = LANE_INFLIGHT; l->timed = true; l->seq = c->next_seq++;
+        }
         if (off + take >= n_bytes) break;
         off += take - (S2_K - 1);
-        // windows fully inside the 30-byte overlap would be counted twice; there are none: a
-        // window is 31 bytes long, the overlap is 30.
     }
     return s2_sync(c, stats);
 }
+
+// enqueue-only form for device-resident batches: launches on lane 0's stream and returns at once.
+extern "C" int s2_scan_count_enqueue(s2_ctx *c, s2_table *t, const void *dev_bases, uint64_t n_bytes, int col)
+{
+    if (check_col(t, col)) return -1;
+    if (((uintptr_t)dev_bases & 15) != 0) { s2_set_error("device batch must be 16-byte aligned"); return -1; }
+    std::lock_guard<std::mutex> g(c->mu);
+    CK(cudaSetDevice(c->device));
+    Lane &l = c->lanes[0];
+    if (l.state == LANE_INFLIGHT && lane_retire(c, l)) return -1;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!c->ev_free.empty()) { ev = c->ev_free.back(); c->ev_free.pop_back(); }
+    else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
+    CK(cudaEventRecord(ev.first, l.stream));
+    s2_launch_scan_count((const uint8_t *)dev_bases, n_bytes, t->v, col, c->d_stats, c->grid_count, l.stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev.second, l.stream));
+    c->ev_pending.push_back(ev);
+    return 0;
+}
+
+// user timing events on lane 0's stream (the stream the enqueue-only scans run on)
+extern "C" int s2_event_record(s2_ctx *c, int which)
+{
+    if (which < 0 || which >= 4) { s2_set_error("event index out of range"); return -1; }
+    std::lock_guard<std::mutex> g(c->mu);
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->user_ev[which], c->lanes[0].stream));
+    return 0;
+}
+
+extern "C" int s2_event_elapsed_ms(s2_ctx *c, int from, int to, double *ms)
+{
+    if (from < 0 || from >= 4 || to < 0 || to >= 4) { s2_set_error("event index out of range"); return -1; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->user_ev[to]));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, c->user_ev[from], c->user_ev[to]));
+    *ms = f;
+    return 0;
+}
+
+extern "C" void *s2_pinned_alloc(uint64_t n_bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n_bytes ? n_bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        s2_set_error("cudaHostAlloc(%llu) failed", (unsigned long long)n_bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void s2_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" uint8_t *s2_batch_acquire(s2_ctx *c, uint64_t *capacity)
 {
@@ -471,6 +556,8 @@ extern "C" int s2_sync(s2_ctx *c, s2_scan_stats *totals)
     std::lock_guard<std::mutex> g(c->mu);
     CK(cudaSetDevice(c->device));
     for (auto &l : c->lanes) if (lane_retire(c, l)) return -1;
+    CK(cudaStreamSynchronize(c->lanes[0].stream));
+    if (harvest_events(c)) return -1;
     return fetch_stats(c, c->lanes[0].stream, totals);
 }
 

@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and through the drop-in
+executables, against the CPU oracle and the reference-generated golden vectors.  Bit-exact: this path
+is integer / byte work, there is no tolerance anywhere."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+pytestmark = pytest.mark.gpu
+
+CODE = {65: 0, 67: 1, 71: 2, 84: 3}
+
+
+@pytest.fixture(scope="module")
+def s2():
+    import strainer2_b200 as s2
+    return s2
+
+
+@pytest.fixture(scope="module")
+def ctx(s2):
+    c = s2.Context(0, batch_bytes=8 << 20, n_lanes=3)
+    yield c
+    c.close()
+
+
+def table_bytes(s2, table, n_print, tmp_path, name="t.tsv"):
+    keys, djb2 = table.export()
+    order, _ = s2.roworder_emulate(djb2)
+    out = os.path.join(str(tmp_path), name)
+    s2.format_count_table(out, keys, order, [table.counts(c) for c in range(n_print)])
+    return open(out, "rb").read()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_pack_kernel_matches_definition(s2, ctx):
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 15, 16, 17, 511, 512, 513, 100003):
+        b = rng.choice(np.frombuffer(b"ACGTacgtNn\n>RY", dtype=np.uint8), size=n)
+        if n > 40:
+            b[7:30] = rng.integers(0, 256, size=23, dtype=np.uint8)
+        words, masks = ctx.pack_2bit(b)
+        assert words.size == (n + 15) // 16
+        pad = np.concatenate([b, np.full((-n) % 16, ord("\n"), np.uint8)]).reshape(-1, 16)
+        up = np.where((pad >= 97) & (pad <= 122), pad - 32, pad)
+        ok = np.isin(up, [65, 67, 71, 84])
+        code = np.zeros_like(up, dtype=np.uint32)
+        for a, c in CODE.items():
+            code[up == a] = c
+        want_m = (ok.astype(np.uint32) << (15 - np.arange(16, dtype=np.uint32))).sum(axis=1)
+        assert np.array_equal(masks.astype(np.uint32), want_m)
+        want_w = (np.where(ok, code, 0) << (30 - 2 * np.arange(16, dtype=np.uint32))).sum(axis=1).astype(np.uint32)
+        keep = np.repeat(ok.astype(np.uint32) * 3, 1, axis=1)
+        sel = (keep << (30 - 2 * np.arange(16, dtype=np.uint32))).sum(axis=1).astype(np.uint32)
+        assert np.array_equal(words & sel, want_w)
+
+
+def test_table_build_matches_oracle_on_golden_genome(s2, ctx, golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "count_edge")
+    ref = os.path.join(d, "ref.fa.gz")
+    t = s2.StrainTable(ctx, s2.load_flat(ref), n_cols=4)
+    o = ou.OracleTable(4)
+    o.build(ref)
+    assert t.n_keys == o.size
+    got = table_bytes(s2, t, 3, tmp_path)
+    assert got == o.table_text(False, str(tmp_path / "o.tsv"))
+    # export: keys really are in first-occurrence order and djb2 is hashU of the spelling
+    keys, djb2 = t.export()
+    L = ou.lib()
+    for k, h in list(zip(keys, djb2))[:200]:
+        assert L.s2o_djb2(s2.kmer_to_ascii(int(k))) == int(h)
+    assert np.unique(keys).size == keys.size
+    t.free(); o.free()
+
+
+@pytest.mark.parametrize("name,args", [
+    ("ABC", ["-r", "ref.fa.gz", "-A", "listA.txt", "-B", "listB.txt", "-C", "listC.txt"]),
+    ("AB", ["-r", "ref.fa.gz", "-A", "listA.txt", "-B", "listB.txt"]),
+    ("A_only", ["-r", "ref.fa.gz", "-A", "listA.txt", "-B", "listB_empty.txt"]),
+])
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_kmer_scrub_count_executable_matches_reference_bytes(s2, golden_dir, tmp_path, name, args, threads):
+    d = os.path.join(golden_dir, "count_edge")
+    prog = str(tmp_path / "progress")
+    p = s2.run_kmer_scrub_count(args + ["-p", prog], cwd=d, env={"S2_THREADS": threads, "S2_BATCH_MB": "1"})
+    assert p.returncode == 0, p.stderr
+    assert p.stdout == open(os.path.join(d, f"expected_{name}.tsv"), "rb").read()
+    assert p.stderr == open(os.path.join(d, f"expected_{name}.stderr"), "rb").read()
+    exp = os.path.join(d, f"expected_{name}.progress")
+    if os.path.exists(exp):
+        assert ou.mask_progress(open(prog).read()) == open(exp).read()
+
+
+def test_kmer_scrub_count_executable_error_paths(s2, golden_dir):
+    d = os.path.join(golden_dir, "count_edge")
+    p = s2.run_kmer_scrub_count(["-r", "ref.fa.gz", "-A", "listA.txt"], cwd=d)
+    assert p.returncode == 1 and p.stdout == b""
+    assert p.stderr == open(os.path.join(d, "expected_usage.stderr"), "rb").read()
+    p = s2.run_kmer_scrub_count(["-r", "ref.fa.gz", "-A", "listA_missing.txt", "-B", "listB_empty.txt"], cwd=d,
+                                env={"S2_THREADS": "1"})
+    assert p.returncode == 1 and p.stdout == b""
+    assert p.stderr == open(os.path.join(d, "expected_missing.stderr"), "rb").read()
+    p = s2.run_kmer_scrub_count(["-r", "nope.fa", "-A", "listA.txt", "-B", "listB.txt"], cwd=d)
+    assert p.returncode == 1 and p.stdout == b""
+    assert p.stderr == b"could not read file nope.fa GEN_hash_sequences_set_count_vec()\n"
+
+
+def _write_inputs(s2, tmp, strain_bp, n_rel, n_rand, n_reads, seed=0):
+    from strainer2_b200 import synth
+    rng = synth.rng_for(2, seed)
+    strain = synth.genome(rng, strain_bp, 8, n_runs=6)
+    synth.write_fasta(os.path.join(tmp, "strain.fa.gz"), strain)
+    A, B = [], []
+    for i in range(n_rel):
+        g = [synth.mutate(c, 0.005 + 0.01 * i, rng) for c in strain]
+        p = os.path.join(tmp, f"rel{i}.fa.gz")
+        synth.write_fasta(p, g)
+        A.append(p)
+    for i in range(n_rand):
+        p = os.path.join(tmp, f"rand{i}.fa")
+        synth.write_fasta(p, synth.genome(rng, strain_bp, 5))
+        A.append(p)
+    clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for c in strain]
+    for i in range(2):
+        other = synth.genome(rng, strain_bp, 4)
+        reads = synth.sample_reads(rng, clean + other * 3, n_reads, 150, sub_rate=0.005, n_rate=1e-4)
+        p = os.path.join(tmp, f"meta{i}.fastq.gz")
+        synth.write_reads_fastq(p, reads)
+        B.append(p)
+    open(os.path.join(tmp, "A.txt"), "w").write("".join(a + "\n" for a in A))
+    open(os.path.join(tmp, "B.txt"), "w").write("".join(b + "\n" for b in B))
+    open(os.path.join(tmp, "C.txt"), "w").write(os.path.join(tmp, "strain.fa.gz") + "\n" + A[0] + "\n")
+    return ["-r", os.path.join(tmp, "strain.fa.gz"), "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"),
+            "-C", os.path.join(tmp, "C.txt")]
+
+
+def test_synthetic_count_run_matches_oracle(s2, tmp_path):
+    """down-scaled configs #2/#3: 400 kb strain, relatives + random genomes, FASTQ.gz metagenomes"""
+    args = _write_inputs(s2, str(tmp_path), 400_000, 3, 2, 30_000)
+    o = ou.oracle_cli(["count"] + args)
+    p = s2.run_kmer_scrub_count(args, env={"S2_BATCH_MB": "2"})
+    assert o.returncode == 0 and p.returncode == 0, p.stderr
+    assert p.stdout == o.stdout
+    assert p.stderr == o.stderr
+    k, v = ou.parse_table(p.stdout)
+    assert v[:, 1].sum() > 100000 and v[:, 2].sum() > 1000 and v[:, 3].sum() > 0       # the case is not vacuous
+
+
+def test_five_megabase_strain_crosses_the_table_doubling(s2, tmp_path):
+    """5 Mb strain => > 4,000,000 keys => the reference table doubles once (8M -> 16M): row order
+    must still be identical (BASELINE config #2 strain shape, 2 genomes instead of 2,000)."""
+    args = _write_inputs(s2, str(tmp_path), 5_000_000, 1, 1, 20_000, seed=1)
+    o = ou.oracle_cli(["count"] + args)
+    p = s2.run_kmer_scrub_count(args)
+    assert o.returncode == 0 and p.returncode == 0, p.stderr
+    assert p.stdout.count(b"\n") > 4_000_001
+    assert p.stdout == o.stdout
+
+
+def test_scan_api_host_and_device_inputs_agree_and_are_additive(s2, ctx):
+    import torch
+    from strainer2_b200 import synth
+    rng = synth.rng_for(3, 7)
+    strain = synth.genome(rng, 200_000, 4, n_runs=3)
+    flat = synth.contigs_to_flat(strain)
+    t = s2.StrainTable(ctx, flat, n_cols=4)
+    clean = [np.where(c == ord("N"), ord("C"), c).astype(np.uint8) for c in strain]
+    reads = synth.sample_reads(rng, clean + synth.genome(rng, 200_000, 2), 40_000, 150, sub_rate=0.01, n_rate=1e-3)
+    batch = synth.reads_to_flat(reads)
+    st_host = ctx.scan_count(t, batch, 1)
+    dev = torch.from_numpy(batch).cuda()
+    st_dev = ctx.scan_count(t, dev, 2)
+    c1, c2 = t.counts(1), t.counts(2)
+    assert st_host.hits == st_dev.hits == int(c1.sum()) == int(c2.sum()) > 0
+    assert st_host.valid_windows == st_dev.valid_windows
+    assert np.array_equal(c1, c2)
+    # additivity: scanning two halves (split on a record boundary) into one column = the whole
+    half = (reads.shape[0] // 2) * 151
+    ctx.scan_count(t, batch[:half], 3)
+    ctx.scan_count(t, batch[half:], 3)
+    assert np.array_equal(t.counts(3), c1)
+    # every ragged length: the tail masking must not invent or lose windows
+    t.clear_counts(3)
+    total = 0
+    for n in (0, 1, 30, 31, 32, 47, 48, 511, 512, 513, 1000, 4097):
+        total += ctx.scan_count(t, dev[:n], 3).valid_windows
+        want = sum(1 for i in range(max(0, n - 30)) if all(c in b"ACGTacgt" for c in batch[i:i + 31].tobytes()))
+        assert ctx.scan_count(t, batch[:n].copy(), 3).valid_windows == want, n
+    t.free()
+
+
+def test_scan_counts_equal_oracle_dictionary(s2, ctx, tmp_path):
+    """API-level: counter columns, key by key, against a dictionary built with the oracle's orient()"""
+    from strainer2_b200 import synth
+    rng = synth.rng_for(3, 11)
+    strain = synth.genome(rng, 30_000, 3, n_runs=2)
+    synth.write_fasta(str(tmp_path / "s.fa"), strain, wrap=70)
+    reads = synth.sample_reads(rng, [np.where(c == ord("N"), ord("G"), c).astype(np.uint8) for c in strain], 3000, 100,
+                               sub_rate=0.02, n_rate=2e-3)
+    synth.write_reads_fastq(str(tmp_path / "m.fastq"), reads)
+    o = ou.OracleTable(4)
+    o.build(str(tmp_path / "s.fa"))
+    o.count_file(str(tmp_path / "m.fastq"), 2)
+    want = o.table_text(False, str(tmp_path / "o.tsv"))
+    t = s2.StrainTable(ctx, s2.load_flat(str(tmp_path / "s.fa")), n_cols=4)
+    ctx.scan_count(t, s2.load_flat(str(tmp_path / "m.fastq")), 2)
+    assert table_bytes(s2, t, 3, tmp_path) == want
+    t.free(); o.free()
+
+
+def test_detect_scan_matches_python_restatement(s2, ctx):
+    from strainer2_b200 import synth
+    rng = synth.rng_for(4, 3)
+    strain = synth.genome(rng, 20_000, 2)
+    flat = synth.contigs_to_flat(strain)
+    t = s2.StrainTable(ctx, flat, n_cols=6)
+    keys, _ = t.export()
+    inf_keys = keys[::50]
+    found = t.flag(np.concatenate([inf_keys, np.array([12345], dtype=np.uint64)]))
+    assert found[:-1].all() and not found[-1]
+    reads = synth.sample_reads(rng, strain + synth.genome(rng, 20_000, 1), 1500, 120, sub_rate=0.01, n_rate=2e-3)
+    recs = [r.tobytes() for r in reads] + [b"ACGT", b"", b"N" * 50]
+    batch, off = s2.flatten_records(recs)
+    hits, inf, pos, st = ctx.scan_detect(t, batch, off)
+    keyset = {s2.kmer_to_ascii(int(k)) for k in keys}
+    infset = {s2.kmer_to_ascii(int(k)) for k in inf_keys}
+    want_hits, want_inf, want_pos = [], [], []
+    for r, s in enumerate(recs):
+        h = i_ = 0
+        for j in range(len(s) - 30):
+            w = s[j:j + 31].upper()
+            if b"N" in w:
+                continue
+            k = ou.orient(w)
+            if k in keyset:
+                h += 1
+                if k in infset:
+                    i_ += 1
+                    want_pos.append(int(off[r]) + j)
+        want_hits.append(h); want_inf.append(i_)
+    assert hits.tolist() == want_hits
+    assert inf.tolist() == want_inf
+    assert pos.tolist() == want_pos
+    assert st.hits == sum(want_hits)
+    t.free()
