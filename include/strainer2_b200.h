@@ -125,6 +125,13 @@ int         s2_kernel_time(s2_ctx *ctx, double *ms, uint64_t *launches, int rese
 int         s2_event_record(s2_ctx *ctx, int which);
 int         s2_event_elapsed_ms(s2_ctx *ctx, int from, int to, double *ms);
 
+/* ---------------------------------------------------------------- tuning -------------------- */
+/* The scan kernel is compiled in several shapes (loads in flight per lane, CTAs per SM, software
+ * pipelining).  v < 0 returns the number of shapes; otherwise selects shape v for subsequent scans
+ * (process-wide).  The default is the shape DESIGN.md names; S2_SCAN_VARIANT overrides it. */
+int         s2_tune_scan_variant(s2_ctx *ctx, int v);
+const char *s2_tune_scan_variant_name(int v);
+
 /* ---------------------------------------------------------------- codecs -------------------- */
 /* bit-compatible with encode_DNA_2_bit / decode_DNA_2_bit (src/up2bit.c:53-98): A0 C1 T2 G3 */
 uint64_t    s2_encode_2bit(const char *dna, int len);

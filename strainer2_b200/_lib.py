@@ -63,6 +63,8 @@ SIGNATURES = {
     "s2_scan_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, c_u64p, C.c_uint32, c_u32p,
                                  c_u32p, c_u64p, C.c_uint64, c_u64p, C.c_int, C.POINTER(ScanStatsStruct)]),
     "s2_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), c_u64p, C.c_int]),
+    "s2_tune_scan_variant": (C.c_int, [C.c_void_p, C.c_int]),
+    "s2_tune_scan_variant_name": (C.c_char_p, [C.c_int]),
     "s2_encode_2bit": (C.c_uint64, [C.c_char_p, C.c_int]),
     "s2_decode_2bit": (None, [C.c_uint64, C.c_int, C.c_char_p]),
     "s2_pack_2bit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, c_u32p, c_u16p]),

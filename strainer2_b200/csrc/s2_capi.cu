@@ -121,6 +121,10 @@ extern "C" s2_ctx *s2_init(int device, uint64_t batch_bytes, int n_lanes)
     CKN(cudaMemset(c->d_stats, 0, 2 * sizeof(unsigned long long)));
     CKN(cudaHostAlloc((void **)&c->h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
     for (auto &e : c->user_ev) CKN(cudaEventCreate(&e));
+    if (getenv("S2_SCAN_VARIANT") && s2_scan_variant_set(atoi(getenv("S2_SCAN_VARIANT")))) {
+        s2_set_error("S2_SCAN_VARIANT out of range");
+        return nullptr;
+    }
     c->grid_count = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_COUNT);
     c->grid_detect = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_DETECT);
     return c;
@@ -145,6 +149,19 @@ extern "C" void s2_shutdown(s2_ctx *c)
     if (c->h_stats) cudaFreeHost(c->h_stats);
     delete c;
 }
+
+// kernel-shape selection for the sweep tool (tools/scan_sweep.py) and S2_SCAN_VARIANT
+extern "C" int s2_tune_scan_variant(s2_ctx *c, int v)
+{
+    if (v < 0) return s2_scan_variant_count();
+    if (s2_scan_variant_set(v)) { s2_set_error("scan variant %d out of range", v); return -1; }
+    CK(cudaSetDevice(c->device));
+    c->grid_count = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_COUNT);
+    c->grid_detect = c->n_sm * s2_scan_blocks_per_sm(S2_MODE_DETECT);
+    return s2_scan_variant_count();
+}
+
+extern "C" const char *s2_tune_scan_variant_name(int v) { return s2_scan_variant_name(v); }
 
 extern "C" int s2_ctx_device(const s2_ctx *c) { return c->device; }
 extern "C" int s2_ctx_sm_count(const s2_ctx *c) { return c->n_sm; }

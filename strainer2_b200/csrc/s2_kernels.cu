@@ -27,7 +27,7 @@ __device__ __forceinline__ void ld_bucket256(const uint16_t *fp, uint32_t bucket
 {
     const uint16_t *p = fp + (uint64_t)bucket * S2_BUCKET_SLOTS;
     // one 32-byte sector, read-only path, do not allocate in L1 (the table never fits, the input does)
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
                  : "l"(p));
 }
@@ -112,77 +112,217 @@ __device__ __forceinline__ bool probe_exact(const S2TableView &t, uint64_t canon
 // ------------------------------------------------------------------------------------------------
 // scan + probe + count   (the hot kernel)
 // ------------------------------------------------------------------------------------------------
+// Template knobs (the shipped configuration is chosen in s2_scan_config(); the others exist so that
+// the sweep tool can measure them on the same binary):
+//   G     windows whose bucket loads are issued together (independent 256-bit loads in flight per lane)
+//   MINB  __launch_bounds__ minimum CTAs per SM (register budget 65536 / (256 * MINB))
+//   PIPE  software pipelining: bucket loads of group g+1 and the next tile's bases are issued before
+//         group g is consumed
+// Slow path: windows whose fingerprint matched (or whose bucket is full) are pushed onto a per-warp
+// shared-memory queue and resolved 32 at a time with every lane busy, instead of diverging per lane.
+#define S2_WARPS (S2_THREADS / 32)
+#define S2_QCAP 64
+
+// raw 16 input bytes with an L2 evict-first policy: the stream is read once, the table must stay
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t *__restrict__ bases, uint64_t n_bytes, uint64_t chunk, uint64_t policy)
+{
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (chunk * 16 < n_bytes)
+        asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+            : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+            : "l"(reinterpret_cast<const uint4 *>(bases) + chunk), "l"(policy));
+    return v;
+}
+
+__device__ __forceinline__ void pack_chunk(const uint4 &v, uint64_t n_bytes, uint64_t chunk, uint32_t &w, uint32_t &m)
+{
+    const uint64_t s = chunk * 16;
+    s2_pack16(v.x, v.y, v.z, v.w, &w, &m);
+    if (s >= n_bytes) m = 0;
+    else if (n_bytes - s < 16) m &= (0xFFFFu << (16 - (unsigned)(n_bytes - s))) & 0xFFFFu;
+}
+
+struct S2Hit { uint32_t slot; uint64_t key; };
+
 template <int MODE>
-__global__ void __launch_bounds__(S2_THREADS, 2)
+__device__ __forceinline__ void resolve_hit(const S2TableView &t, uint64_t canon, uint64_t pos,
+                                            uint32_t *__restrict__ counts_col, const S2DetectOut &dout, uint32_t &n_hits)
+{
+    uint32_t slot; uint64_t key;
+    if (!probe_exact(t, canon, slot, key)) return;
+    ++n_hits;
+    if (MODE == S2_MODE_COUNT) {
+        atomicAdd(&counts_col[slot], 1u);                         // count[vec_column] += 1
+    } else {
+        uint32_t lo = 0, hi = dout.n_rec;                         // record r: rec_off[r] <= pos < rec_off[r+1]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (dout.rec_off[mid] <= pos) lo = mid; else hi = mid;
+        }
+        atomicAdd(&dout.read_hits[lo], 1u);
+        if (key & S2_INFORMATIVE_BIT) {
+            atomicAdd(&dout.read_inf[lo], 1u);
+            const unsigned long long idx = atomicAdd(dout.inf_count, 1ull);
+            if (idx < dout.inf_cap) dout.inf_pos[idx] = pos;
+        }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void issue_group(const S2TableView &t, uint32_t w0, uint32_t w1, uint32_t w2,
+                                            uint32_t r0, uint32_t r1, uint32_t r2, uint32_t vmask, int g,
+                                            uint32_t (&x)[G][8], uint32_t (&fp2)[G])
+{
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        const unsigned j = G * g + u;
+        const s2_hash_t hh = s2_hash(window_canon(w0, w1, w2, r0, r1, r2, j));
+        fp2[u] = hh.fp * 0x00010001u;
+        // windows broken by N / a record boundary probe bucket 0: every such lane of the warp then asks for
+        // the same sector (one L1 wavefront), and the result is masked by vmask.  (A predicated load
+        // makes ptxas keep all previous bucket registers alive and spill.)
+        ld_bucket256(t.fp, ((vmask >> j) & 1u) ? s2_bucket_of(hh.h, t.n_buckets) : 0u, x[u]);
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void consume_group(uint32_t vmask, int g, const uint32_t (&x)[G][8],
+                                              const uint32_t (&fp2)[G], uint32_t &cand)
+{
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        const unsigned j = G * g + u;
+        const uint32_t any = fp_any_match(x[u], fp2[u]);
+        const bool full = x[u][7] > 0xFFFFu;
+        if (((vmask >> j) & 1u) && (any != 0 || full)) cand |= 1u << j;
+    }
+}
+
+// resolve `count` (<= 32) queued windows from the top of the warp's queue
+template <int MODE>
+__device__ __forceinline__ void drain_queue(const S2TableView &t, const uint64_t *q_canon, const uint64_t *q_pos,
+                                            uint32_t &qlen, uint32_t count, int lane,
+                                            uint32_t *__restrict__ counts_col, const S2DetectOut &dout, uint32_t &n_hits)
+{
+    const uint32_t base = qlen - count;
+    if ((uint32_t)lane < count) {
+        const uint64_t canon = q_canon[base + lane];
+        const uint64_t pos = MODE == S2_MODE_DETECT ? q_pos[base + lane] : 0;
+        resolve_hit<MODE>(t, canon, pos, counts_col, dout, n_hits);
+    }
+    qlen = base;
+    __syncwarp();
+}
+
+template <int MODE, int G, int MINB, bool PIPE>
+__global__ void __launch_bounds__(S2_THREADS, MINB)
 s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView t,
                uint32_t *__restrict__ counts_col, S2DetectOut dout, unsigned long long *__restrict__ stats)
 {
-    const int lane = threadIdx.x & 31;
+    constexpr int NG = 16 / G;
+    __shared__ uint64_t q_canon_s[S2_WARPS][S2_QCAP];
+    __shared__ uint64_t q_pos_s[MODE == S2_MODE_DETECT ? S2_WARPS : 1][MODE == S2_MODE_DETECT ? S2_QCAP : 1];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t *q_canon = q_canon_s[wid];
+    uint64_t *q_pos = q_pos_s[MODE == S2_MODE_DETECT ? wid : 0];
     const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_tiles = (n_bytes + 511) / 512;
-    uint32_t n_hits = 0, n_valid = 0;
+    uint32_t n_hits = 0, n_valid = 0, qlen = 0;
+    uint64_t policy;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
-    for (uint64_t tile = gwarp; tile < n_tiles; tile += n_warps) {
+    uint64_t tile = gwarp;
+    uint4 raw = make_uint4(0, 0, 0, 0), rawx = make_uint4(0, 0, 0, 0);
+    if (tile < n_tiles) {
+        raw = ld_stream16(bases, n_bytes, tile * 32 + lane, policy);
+        if (lane < 2) rawx = ld_stream16(bases, n_bytes, tile * 32 + 32 + lane, policy);
+    }
+    for (; tile < n_tiles; tile += n_warps) {
+        // ---- this tile's 48 packed bases per lane; (PIPE) the next tile's bytes start moving now ------
         uint32_t w0, w1, w2, m0, m1, m2;
-        load_tile(bases, n_bytes, tile, lane, w0, w1, w2, m0, m1, m2);
-        const uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
-        uint32_t cand = 0;                                   // windows that need the exact slow path
-
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            uint32_t x[4][8];
-            uint32_t fp2[4];
-            bool valid[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned j = 4 * g + u;
-                valid[u] = s2_window_valid(m0, m1, m2, j);
-                const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
-                const s2_hash_t hh = s2_hash(canon);
-                fp2[u] = hh.fp * 0x00010001u;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[u][i] = 0;
-                if (valid[u]) ld_bucket256(t.fp, s2_bucket_of(hh.h, t.n_buckets), x[u]);
+        {
+            uint32_t wx = 0, mx = 0;
+            pack_chunk(raw, n_bytes, tile * 32 + lane, w0, m0);
+            if (lane < 2) pack_chunk(rawx, n_bytes, tile * 32 + 32 + lane, wx, mx);
+            if (PIPE) {
+                const uint64_t nt = tile + n_warps;
+                raw = make_uint4(0, 0, 0, 0); rawx = raw;
+                if (nt < n_tiles) {
+                    raw = ld_stream16(bases, n_bytes, nt * 32 + lane, policy);
+                    if (lane < 2) rawx = ld_stream16(bases, n_bytes, nt * 32 + 32 + lane, policy);
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t any = fp_any_match(x[u], fp2[u]);
-                const bool full = (x[u][7] >> 16) != 0;
-                if (valid[u] && (any != 0 || full)) cand |= 1u << (4 * g + u);
-                n_valid += valid[u];
-            }
+            const uint32_t a1 = __shfl_sync(0xFFFFFFFFu, w0, (lane + 1) & 31), b1 = __shfl_sync(0xFFFFFFFFu, wx, (lane + 1) & 31);
+            const uint32_t a2 = __shfl_sync(0xFFFFFFFFu, w0, (lane + 2) & 31), b2 = __shfl_sync(0xFFFFFFFFu, wx, (lane + 2) & 31);
+            const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, m0, (lane + 1) & 31), d1 = __shfl_sync(0xFFFFFFFFu, mx, (lane + 1) & 31);
+            const uint32_t c2 = __shfl_sync(0xFFFFFFFFu, m0, (lane + 2) & 31), d2 = __shfl_sync(0xFFFFFFFFu, mx, (lane + 2) & 31);
+            w1 = lane < 31 ? a1 : b1;  m1 = lane < 31 ? c1 : d1;
+            w2 = lane < 30 ? a2 : b2;  m2 = lane < 30 ? c2 : d2;
         }
+        uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
 
-        // slow path, compacted: every round resolves at most one pending window per lane
-        while (__any_sync(0xFFFFFFFFu, cand != 0)) {
-            if (cand) {
-                const unsigned j = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
-                uint32_t slot; uint64_t key;
-                if (probe_exact(t, canon, slot, key)) {
-                    ++n_hits;
-                    if (MODE == S2_MODE_COUNT) {
-                        atomicAdd(&counts_col[slot], 1u);                 // count[vec_column] += 1
+        // ---- fast path: 16 windows per lane, G bucket loads in flight (2G when pipelined) -------------
+        // The whole tile is one basic block; without a fence the compiler hoists the hashing of all 16
+        // windows above the first load and spills.  An empty asm that "rewrites" the packed words pins
+        // each group's arithmetic between its neighbours (no instruction is emitted).
+#define S2_GROUP_FENCE() asm volatile("" : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(r0), "+r"(r1), "+r"(r2), "+r"(vmask))
+        uint32_t vmask = 0, cand = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) vmask |= (s2_window_valid(m0, m1, m2, j) ? 1u : 0u) << j;
+        {
+            uint32_t xa[G][8], xb[PIPE ? G : 1][8], fa[G], fb[PIPE ? G : 1];
+            if (PIPE) {
+                issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, 0, xa, fa);
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (g & 1) {
+                        if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, g + 1, xa, fa);
+                        consume_group<G>(vmask, g, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb), cand);
+                        S2_GROUP_FENCE();
                     } else {
-                        const uint64_t pos = tile * 512 + (uint64_t)lane * 16 + j;
-                        uint32_t lo = 0, hi = dout.n_rec;                 // record r: rec_off[r] <= pos < rec_off[r+1]
-                        while (hi - lo > 1) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (dout.rec_off[mid] <= pos) lo = mid; else hi = mid;
-                        }
-                        atomicAdd(&dout.read_hits[lo], 1u);
-                        if (key & S2_INFORMATIVE_BIT) {
-                            atomicAdd(&dout.read_inf[lo], 1u);
-                            const unsigned long long idx = atomicAdd(dout.inf_count, 1ull);
-                            if (idx < dout.inf_cap) dout.inf_pos[idx] = pos;
-                        }
+                        if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, g + 1, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb));
+                        consume_group<G>(vmask, g, xa, fa, cand);
+                        S2_GROUP_FENCE();
                     }
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, g, xa, fa);
+                    consume_group<G>(vmask, g, xa, fa, cand);
+                    S2_GROUP_FENCE();
                 }
             }
         }
+        n_valid += __popc(vmask);
+
+        // ---- slow path: queue the candidates of the whole warp, resolve them 32 at a time -------------
+        while (__any_sync(0xFFFFFFFFu, cand != 0)) {
+            const uint32_t has = cand != 0;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+            if (has) {
+                const unsigned j = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const uint32_t at = qlen + __popc(bal & ((1u << lane) - 1u));
+                q_canon[at] = window_canon(w0, w1, w2, r0, r1, r2, j);
+                if (MODE == S2_MODE_DETECT) q_pos[at] = tile * 512 + (uint64_t)lane * 16 + j;
+            }
+            qlen += __popc(bal);
+            __syncwarp();
+            if (qlen >= 32) drain_queue<MODE>(t, q_canon, q_pos, qlen, 32, lane, counts_col, dout, n_hits);
+        }
+        if (!PIPE) {
+            const uint64_t nt = tile + n_warps;
+            raw = make_uint4(0, 0, 0, 0); rawx = raw;
+            if (nt < n_tiles) {
+                raw = ld_stream16(bases, n_bytes, nt * 32 + lane, policy);
+                if (lane < 2) rawx = ld_stream16(bases, n_bytes, nt * 32 + 32 + lane, policy);
+            }
+        }
     }
+    if (qlen) drain_queue<MODE>(t, q_canon, q_pos, qlen, qlen, lane, counts_col, dout, n_hits);
 
     n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
     n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
@@ -192,13 +332,42 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
     }
 }
 
+// ---- variants -------------------------------------------------------------------------------------
+typedef void (*s2_scan_fn)(const uint8_t *, uint64_t, S2TableView, uint32_t *, S2DetectOut, unsigned long long *);
+struct S2ScanVariant { const char *name; s2_scan_fn count_fn, detect_fn; };
+
+#define S2_VARIANT(G, MINB, PIPE) \
+    { "G" #G "_B" #MINB "_P" #PIPE, s2_scan_kernel<S2_MODE_COUNT, G, MINB, PIPE>, s2_scan_kernel<S2_MODE_DETECT, G, MINB, PIPE> }
+
+static const S2ScanVariant g_variants[] = {
+    S2_VARIANT(4, 2, false),   // 0: round-1a shape
+    S2_VARIANT(4, 3, false),   // 1
+    S2_VARIANT(2, 3, false),   // 2
+    S2_VARIANT(2, 4, false),   // 3
+    S2_VARIANT(4, 2, true),    // 4
+    S2_VARIANT(2, 3, true),    // 5
+    S2_VARIANT(2, 4, true),    // 6
+    S2_VARIANT(8, 2, false),   // 7
+    S2_VARIANT(4, 3, true),    // 8
+    S2_VARIANT(1, 4, true),    // 9
+};
+static int g_variant = 0;
+
+int s2_scan_variant_count(void) { return (int)(sizeof g_variants / sizeof g_variants[0]); }
+const char *s2_scan_variant_name(int v) { return (v >= 0 && v < s2_scan_variant_count()) ? g_variants[v].name : "?"; }
+int s2_scan_variant_get(void) { return g_variant; }
+int s2_scan_variant_set(int v)
+{
+    if (v < 0 || v >= s2_scan_variant_count()) return -1;
+    g_variant = v;
+    return 0;
+}
+
 int s2_scan_blocks_per_sm(int mode)
 {
     int n = 0;
-    if (mode == S2_MODE_COUNT)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, s2_scan_kernel<S2_MODE_COUNT>, S2_THREADS, 0);
-    else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, s2_scan_kernel<S2_MODE_DETECT>, S2_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &n, mode == S2_MODE_COUNT ? g_variants[g_variant].count_fn : g_variants[g_variant].detect_fn, S2_THREADS, 0);
     return n > 0 ? n : 1;
 }
 
@@ -207,7 +376,7 @@ void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableV
 {
     if (n_bytes == 0) return;
     S2DetectOut none = {};
-    s2_scan_kernel<S2_MODE_COUNT><<<grid_blocks, S2_THREADS, 0, stream>>>(
+    g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(
         bases, n_bytes, t, t.counts + (uint64_t)col * t.n_slots, none, stats);
 }
 
@@ -216,7 +385,7 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
                            cudaStream_t stream)
 {
     if (n_bytes == 0) return;
-    s2_scan_kernel<S2_MODE_DETECT><<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats);
+    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats);
 }
 
 // ------------------------------------------------------------------------------------------------

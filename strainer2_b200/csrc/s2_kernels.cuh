@@ -35,6 +35,11 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
                            const S2DetectOut &out, unsigned long long *stats, int grid_blocks,
                            cudaStream_t stream);
 int  s2_scan_blocks_per_sm(int mode);
+// kernel shape selection (sweep tool / S2_SCAN_VARIANT); see s2_kernels.cu
+int  s2_scan_variant_count(void);
+const char *s2_scan_variant_name(int v);
+int  s2_scan_variant_get(void);
+int  s2_scan_variant_set(int v);
 
 // table build (one-off, not the hot path)
 void s2_launch_build_insert(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,

@@ -124,18 +124,20 @@ S2_HD uint32_t s2_mulhi32(uint32_t a, uint32_t b)
 }
 
 // ---- hashing for the device table ---------------------------------------------------------------
-// one 64-bit multiply + a 32-bit avalanche; bucket and fingerprint come from different bit ranges.
+// One 64-bit multiply.  Canonical k-mers of real sequence are close to uniform already (only skewed
+// towards large values by the max(fwd, rc) rule), so a Fibonacci multiply is enough: every input bit
+// reaches the high word, which picks the bucket (mulhi by n_buckets uses its top bits); the
+// fingerprint comes from the top of the LOW product word, i.e. from different bits.
 struct s2_hash_t { uint32_t h; uint32_t fp; };
 
 S2_HD s2_hash_t s2_hash(uint64_t canon)
 {
     const uint64_t x = canon * 0x9E3779B97F4A7C15ull;
-    uint32_t h = (uint32_t)(x >> 32) ^ (uint32_t)x;
-    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    s2_hash_t r;
+    r.h = (uint32_t)(x >> 32);
     // fingerprint: a *normal positive fp16 bit pattern* (0x0400..0x7BFF) so that the probe can test 16
     // fingerprints with 8 HSET2 (half2 equality) instructions; 0x0000 is the empty slot.
-    const uint32_t g = (uint32_t)(x >> 29) * 0x9E3779B1u;
-    s2_hash_t r; r.h = h; r.fp = 0x0400u + s2_mulhi32(g, 30720u);
+    r.fp = 0x0400u + s2_mulhi32((uint32_t)x, 30720u);
     return r;
 }
 

@@ -268,6 +268,8 @@ def test_hash_spreads_real_kmers(sim):
     rng = np.random.default_rng(5)
     n = 200000
     keys = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    # canonical k-mers are skewed towards large values (max of forward / reverse complement)
+    keys[:50000] = [max(int(k), sim.sim_revcomp31(int(k))) for k in keys[:50000]]
     nb = n // 8                                     # load 0.5 with 16-slot buckets
     cnt = np.zeros(nb, dtype=np.int64)
     h, fp = C.c_uint32(), C.c_uint32()
@@ -281,3 +283,15 @@ def test_hash_spreads_real_kmers(sim):
     lam = 50000 / nb
     assert abs(cnt.mean() - lam) < 1e-9
     assert cnt.var() < 1.3 * lam        # Poisson variance = lam
+    # overlapping windows of one sequence (consecutive k-mers share 30 bases) must spread as well
+    seq = rng.integers(0, 4, size=60000, dtype=np.uint64)
+    cnt2 = np.zeros(nb, dtype=np.int64)
+    fwd = 0
+    for i, b in enumerate(seq):
+        fwd = ((fwd << 2) | int(b)) & ((1 << 62) - 1)
+        if i >= 30:
+            k = max(fwd, sim.sim_revcomp31(fwd))
+            sim.sim_hash(k, C.byref(h), C.byref(fp))
+            cnt2[sim.sim_bucket(h.value, nb)] += 1
+    lam2 = cnt2.sum() / nb
+    assert cnt2.var() < 1.3 * lam2 and cnt2.max() <= 12
