@@ -142,73 +142,85 @@ __device__ __forceinline__ void pack_chunk(const uint4 &v, uint64_t n_bytes, uin
     else if (n_bytes - s < 16) m &= (0xFFFFu << (16 - (unsigned)(n_bytes - s))) & 0xFFFFu;
 }
 
-struct S2Hit { uint32_t slot; uint64_t key; };
-
-template <int MODE>
-__device__ __forceinline__ void resolve_hit(const S2TableView &t, uint64_t canon, uint64_t pos,
-                                            uint32_t *__restrict__ counts_col, const S2DetectOut &dout, uint32_t &n_hits)
-{
-    uint32_t slot; uint64_t key;
-    if (!probe_exact(t, canon, slot, key)) return;
-    ++n_hits;
-    if (MODE == S2_MODE_COUNT) {
-        atomicAdd(&counts_col[slot], 1u);                         // count[vec_column] += 1
-    } else {
-        uint32_t lo = 0, hi = dout.n_rec;                         // record r: rec_off[r] <= pos < rec_off[r+1]
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (dout.rec_off[mid] <= pos) lo = mid; else hi = mid;
-        }
-        atomicAdd(&dout.read_hits[lo], 1u);
-        if (key & S2_INFORMATIVE_BIT) {
-            atomicAdd(&dout.read_inf[lo], 1u);
-            const unsigned long long idx = atomicAdd(dout.inf_count, 1ull);
-            if (idx < dout.inf_cap) dout.inf_pos[idx] = pos;
-        }
-    }
-}
-
 template <int G>
 __device__ __forceinline__ void issue_group(const S2TableView &t, uint32_t w0, uint32_t w1, uint32_t w2,
-                                            uint32_t r0, uint32_t r1, uint32_t r2, uint32_t vmask, int g,
-                                            uint32_t (&x)[G][8], uint32_t (&fp2)[G])
+                                            uint32_t r0, uint32_t r1, uint32_t r2, uint32_t vmask, uint32_t dummy_bucket,
+                                            int g, uint32_t (&x)[G][8], uint32_t (&fp2)[G])
 {
 #pragma unroll
     for (int u = 0; u < G; ++u) {
         const unsigned j = G * g + u;
         const s2_hash_t hh = s2_hash(window_canon(w0, w1, w2, r0, r1, r2, j));
         fp2[u] = hh.fp * 0x00010001u;
-        // windows broken by N / a record boundary probe bucket 0: every such lane of the warp then asks for
-        // the same sector (one L1 wavefront), and the result is masked by vmask.  (A predicated load
-        // makes ptxas keep all previous bucket registers alive and spill.)
-        ld_bucket256(t.fp, ((vmask >> j) & 1u) ? s2_bucket_of(hh.h, t.n_buckets) : 0u, x[u]);
+        // windows broken by N / a record boundary probe the warp's dummy bucket: all such lanes of the
+        // warp ask for the same sector (one extra L1 wavefront), different warps ask different L2
+        // slices (a single shared dummy sector becomes an L2 hot spot: 20 % of the windows of 150-base
+        // reads are broken), and the result is masked by vmask.  (A predicated load makes ptxas keep
+        // all previous bucket registers alive and spill.)
+        ld_bucket256(t.fp, ((vmask >> j) & 1u) ? s2_bucket_of(hh.h, t.n_buckets) : dummy_bucket, x[u]);
     }
 }
 
 template <int G>
 __device__ __forceinline__ void consume_group(uint32_t vmask, int g, const uint32_t (&x)[G][8],
-                                              const uint32_t (&fp2)[G], uint32_t &cand)
+                                              const uint32_t (&fp2)[G], uint32_t &cand, uint64_t &candpos)
 {
 #pragma unroll
     for (int u = 0; u < G; ++u) {
         const unsigned j = G * g + u;
         const uint32_t any = fp_any_match(x[u], fp2[u]);
         const bool full = x[u][7] > 0xFFFFu;
-        if (((vmask >> j) & 1u) && (any != 0 || full)) cand |= 1u << j;
+        if (((vmask >> j) & 1u) && (any != 0 || full)) {
+            // rare: remember which of the 16 slots matched first, so the slow path can go straight to
+            // the key (4 bits per window; a full bucket without a match records 0 and falls back)
+            const uint32_t fp = fp2[u] & 0xFFFFu;
+            uint32_t bm = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                bm |= ((x[u][i] & 0xFFFFu) == fp ? 1u : 0u) << (2 * i);
+                bm |= ((x[u][i] >> 16) == fp ? 1u : 0u) << (2 * i + 1);
+            }
+            const uint32_t first = bm ? (uint32_t)__ffs(bm) - 1u : 0u;
+            cand |= 1u << j;
+            candpos |= (uint64_t)first << (4 * j);
+        }
     }
 }
 
-// resolve `count` (<= 32) queued windows from the top of the warp's queue
+// resolve `count` (<= 32) queued windows from the top of the warp's queue: the recorded slot is checked
+// against the key array first (one 8-byte load); anything else (false fingerprint match, second match
+// in the bucket, overflowed bucket) goes through the exact probe.
 template <int MODE>
-__device__ __forceinline__ void drain_queue(const S2TableView &t, const uint64_t *q_canon, const uint64_t *q_pos,
-                                            uint32_t &qlen, uint32_t count, int lane,
+__device__ __forceinline__ void drain_queue(const S2TableView &t, const uint64_t *q_canon, const uint32_t *q_slot,
+                                            const uint64_t *q_pos, uint32_t &qlen, uint32_t count, int lane,
                                             uint32_t *__restrict__ counts_col, const S2DetectOut &dout, uint32_t &n_hits)
 {
     const uint32_t base = qlen - count;
     if ((uint32_t)lane < count) {
         const uint64_t canon = q_canon[base + lane];
+        uint32_t slot = q_slot[base + lane];
         const uint64_t pos = MODE == S2_MODE_DETECT ? q_pos[base + lane] : 0;
-        resolve_hit<MODE>(t, canon, pos, counts_col, dout, n_hits);
+        uint64_t key = t.keys[slot];
+        bool hit = (key & S2_KMER_MASK) == canon && key != S2_EMPTY_KEY;
+        if (!hit) hit = probe_exact(t, canon, slot, key);
+        if (hit) {
+            ++n_hits;
+            if (MODE == S2_MODE_COUNT) {
+                atomicAdd(&counts_col[slot], 1u);                     // count[vec_column] += 1
+            } else {
+                uint32_t lo = 0, hi = dout.n_rec;                     // record r: rec_off[r] <= pos < rec_off[r+1]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (dout.rec_off[mid] <= pos) lo = mid; else hi = mid;
+                }
+                atomicAdd(&dout.read_hits[lo], 1u);
+                if (key & S2_INFORMATIVE_BIT) {
+                    atomicAdd(&dout.read_inf[lo], 1u);
+                    const unsigned long long idx = atomicAdd(dout.inf_count, 1ull);
+                    if (idx < dout.inf_cap) dout.inf_pos[idx] = pos;
+                }
+            }
+        }
     }
     qlen = base;
     __syncwarp();
@@ -221,15 +233,18 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
 {
     constexpr int NG = 16 / G;
     __shared__ uint64_t q_canon_s[S2_WARPS][S2_QCAP];
+    __shared__ uint32_t q_slot_s[S2_WARPS][S2_QCAP];
     __shared__ uint64_t q_pos_s[MODE == S2_MODE_DETECT ? S2_WARPS : 1][MODE == S2_MODE_DETECT ? S2_QCAP : 1];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t *q_canon = q_canon_s[wid];
+    uint32_t *q_slot = q_slot_s[wid];
     uint64_t *q_pos = q_pos_s[MODE == S2_MODE_DETECT ? wid : 0];
     const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_tiles = (n_bytes + 511) / 512;
     uint32_t n_hits = 0, n_valid = 0, qlen = 0;
+    const uint32_t dummy_bucket = s2_bucket_of((uint32_t)gwarp * 0x9E3779B1u, t.n_buckets);
     uint64_t policy;
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
@@ -269,29 +284,30 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
         // each group's arithmetic between its neighbours (no instruction is emitted).
 #define S2_GROUP_FENCE() asm volatile("" : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(r0), "+r"(r1), "+r"(r2), "+r"(vmask))
         uint32_t vmask = 0, cand = 0;
+        uint64_t candpos = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) vmask |= (s2_window_valid(m0, m1, m2, j) ? 1u : 0u) << j;
         {
             uint32_t xa[G][8], xb[PIPE ? G : 1][8], fa[G], fb[PIPE ? G : 1];
             if (PIPE) {
-                issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, 0, xa, fa);
+                issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, dummy_bucket, 0, xa, fa);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     if (g & 1) {
-                        if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, g + 1, xa, fa);
-                        consume_group<G>(vmask, g, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb), cand);
+                        if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, dummy_bucket, g + 1, xa, fa);
+                        consume_group<G>(vmask, g, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb), cand, candpos);
                         S2_GROUP_FENCE();
                     } else {
-                        if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, g + 1, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb));
-                        consume_group<G>(vmask, g, xa, fa, cand);
+                        if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, dummy_bucket, g + 1, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb));
+                        consume_group<G>(vmask, g, xa, fa, cand, candpos);
                         S2_GROUP_FENCE();
                     }
                 }
             } else {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, g, xa, fa);
-                    consume_group<G>(vmask, g, xa, fa, cand);
+                    issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, dummy_bucket, g, xa, fa);
+                    consume_group<G>(vmask, g, xa, fa, cand, candpos);
                     S2_GROUP_FENCE();
                 }
             }
@@ -306,12 +322,14 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
                 const unsigned j = __ffs(cand) - 1;
                 cand &= cand - 1;
                 const uint32_t at = qlen + __popc(bal & ((1u << lane) - 1u));
-                q_canon[at] = window_canon(w0, w1, w2, r0, r1, r2, j);
+                const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
+                q_canon[at] = canon;
+                q_slot[at] = s2_bucket_of(s2_hash(canon).h, t.n_buckets) * S2_BUCKET_SLOTS + ((uint32_t)(candpos >> (4 * j)) & 15u);
                 if (MODE == S2_MODE_DETECT) q_pos[at] = tile * 512 + (uint64_t)lane * 16 + j;
             }
             qlen += __popc(bal);
             __syncwarp();
-            if (qlen >= 32) drain_queue<MODE>(t, q_canon, q_pos, qlen, 32, lane, counts_col, dout, n_hits);
+            if (qlen >= 32) drain_queue<MODE>(t, q_canon, q_slot, q_pos, qlen, 32, lane, counts_col, dout, n_hits);
         }
         if (!PIPE) {
             const uint64_t nt = tile + n_warps;
@@ -322,7 +340,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
             }
         }
     }
-    if (qlen) drain_queue<MODE>(t, q_canon, q_pos, qlen, qlen, lane, counts_col, dout, n_hits);
+    if (qlen) drain_queue<MODE>(t, q_canon, q_slot, q_pos, qlen, qlen, lane, counts_col, dout, n_hits);
 
     n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
     n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
@@ -351,7 +369,7 @@ static const S2ScanVariant g_variants[] = {
     S2_VARIANT(4, 3, true),    // 8
     S2_VARIANT(1, 4, true),    // 9
 };
-static int g_variant = 0;
+static int g_variant = 3;   // G2_B4_Pfalse: best of the round-1 sweep (profiles/r1b_scan_sweep.txt)
 
 int s2_scan_variant_count(void) { return (int)(sizeof g_variants / sizeof g_variants[0]); }
 const char *s2_scan_variant_name(int v) { return (v >= 0 && v < s2_scan_variant_count()) ? g_variants[v].name : "?"; }
