@@ -1,3 +1,377 @@
-// placeholder, replaced below
+// s2_cli_detect.cpp - the drop-in `strain_detect` program (/root/reference/src/strain_detect.c) on top of
+// the C ABI.  Same getopt string, validations, stdout chatter, stderr errors and kmer_hits text/.gz.
+//
+// Split of work: the GPU does pass 1 of quantify_hits_PE for every read of a batch (table hits,
+// informative hits, positions of informative windows: s2_scan_detect).  The host keeps what is
+// inherently sequential: the reference's read-pairing loop with its stale-state behaviour for reads
+// shorter than 31 (src/strain_detect.c:444-448, :497-504) and the ordered emission of
+// pass 2 (:547-623) into one gzip stream ("wb9", :299).
+//
+// Environment: S2_DEVICE (0), S2_DETECT_BATCH_MB (32).
 #include "../../include/strainer2_b200.h"
-extern "C" int s2_strain_detect_main(int, char **) { return 1; }
+#include "s2_internal.h"
+
+#include <getopt.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+int s2_load_flat(const char *path, std::vector<uint8_t> &flat);   // s2_cli_count.cpp
+
+enum { NOT_PAIRED_END = 0, IS_PAIRED_END = 1, IS_PAIRED_END_INTERLEAVE = 2, UNKNOWN_FILE_TYPE = -1 };
+
+static void detect_usage()                                          // src/strain_detect.c:750-764
+{
+    fprintf(stderr, "Usage paired end with 2 files:\n\tstrain_detect -r <reference_genome.fna> -a <informative_kmer_file.txt> -b <paired-end-file1> -c <paired-end-file1> -t PE -o <kmer outfile>\n");
+    fprintf(stderr, "Usage paired end interleaved 1 file:\n\tstrain_detect -r <reference_genome.fna> -a <informative_kmer_file.txt> -b <paired-end-file1>  -t PEI -o <kmer outfile>\n");
+    fprintf(stderr, "Usage single end 1 file:\n\tstrain_detect -r <reference_genome.fna> -a <informative_kmer_file.txt> -b <single-end-file1>  -t SE -o <kmer outfile>\n");
+    fprintf(stderr, "Usage single end 1 file:\n\tstrain_detect -r <reference_genome.fna> -a <informative_kmer_file.txt> -B <batch-list-of-metagenomes> -o <kmer outfile>\n\n");
+    fprintf(stderr, "format for metagenomics batch file is:\n");
+    fprintf(stderr, "PE\tfile1_PE1.fasta\tfile1_PE2.fasta\n");
+    fprintf(stderr, "SE\tfile1_PE1.fasta\n");
+    fprintf(stderr, "PEI\tfile1_PE1.fasta\n");
+    fprintf(stderr, "\nlines that begin with # are considered comments and ignored\n");
+    fprintf(stderr, "\ninformative kmer file is a list of all of the kmers left in the reference genome post scrubbing\n");
+}
+
+static int get_file_type(const char *s)                             // src/strain_detect.c:728-747
+{
+    if (!strcmp(s, "SE") || !strcmp(s, "se")) return NOT_PAIRED_END;
+    if (!strcmp(s, "PE") || !strcmp(s, "pe")) return IS_PAIRED_END;
+    if (!strcmp(s, "PEI") || !strcmp(s, "pei") || !strcmp(s, "IPE") || !strcmp(s, "ipe")) return IS_PAIRED_END_INTERLEAVE;
+    return UNKNOWN_FILE_TYPE;
+}
+
+struct Detect {
+    s2_ctx *ctx = nullptr;
+    s2_table *table = nullptr;
+    gzFile gzout = nullptr;
+    unsigned genome_kmers = 0, genome_informative = 0;
+    uint64_t batch_bytes = 32ull << 20;
+    std::string out;                    // pending text for gzout
+
+    void flush_out(bool force)
+    {
+        if (out.size() >= (1u << 20) || (force && !out.empty())) {
+            size_t off = 0;
+            while (off < out.size()) {
+                const unsigned n = (unsigned)std::min<size_t>(out.size() - off, 1u << 30);
+                gzwrite(gzout, out.data() + off, n);
+                off += n;
+            }
+            out.clear();
+        }
+    }
+};
+
+// hash_scrubbed_kmers (src/strain_detect.c:668-726): label the listed k-mers INFORMATIVE.
+// Lines are read with gzgets into a 100-byte buffer exactly like the reference (longer lines split).
+static int label_informative(Detect &d, const char *a_file, unsigned *num_lines_found)
+{
+    gzFile fp = gzopen(a_file, "r");
+    if (!fp) {
+        fprintf(stderr, "could not read file %s in hash_scrubbed_kmers()\n", a_file);
+        return -1;
+    }
+    struct Line { std::string text; bool right_len; bool acgt; uint64_t kmer; };
+    std::vector<Line> lines;
+    char line[100];
+    while (gzgets(fp, line, 100)) {
+        if (line[0] == '#') continue;
+        char *pos = strchr(line, '\n');
+        if (pos) *pos = '\0';
+        Line L; L.text = line; L.right_len = strlen(line) == S2_K; L.acgt = false; L.kmer = 0;
+        if (L.right_len) {
+            // the reference does NOT upper-case these lines: only upper-case ACGT spellings can equal a key
+            bool upper = true;
+            for (int i = 0; i < S2_K; ++i) upper = upper && (line[i] == 'A' || line[i] == 'C' || line[i] == 'G' || line[i] == 'T');
+            if (upper && s2_kmer_from_ascii(line, &L.kmer) == 0) L.acgt = true;
+        }
+        lines.push_back(L);
+    }
+    gzclose(fp);
+    std::vector<uint64_t> q;
+    for (auto &L : lines) if (L.acgt) q.push_back(L.kmer);
+    std::vector<uint8_t> found(q.size() + 1);
+    if (s2_table_flag(d.table, q.data(), q.size(), found.data())) return -2;
+    size_t qi = 0; unsigned n_found = 0;
+    std::unordered_set<uint64_t> distinct;
+    for (auto &L : lines) {
+        if (!L.right_len) {
+            printf("error string length in the scrubbed kmer file (%s) must be the same size as the kmer length (scrubbed kmer, "
+                   "scrubbed kmer len, seed len): %s, %d, %d\n", a_file, L.text.c_str(), (int)L.text.size(), S2_K);
+            continue;
+        }
+        const bool hit = L.acgt && found[qi++];
+        if (hit) { ++n_found; distinct.insert(L.kmer); }
+        else printf("error could not find informative kmer %s in the total kmer list\n", L.text.c_str());
+    }
+    *num_lines_found = n_found;
+    d.genome_informative = (unsigned)distinct.size();              // src/strain_detect.c:285-290
+    return 0;
+}
+
+// one record handed to the GPU
+struct Rec { uint64_t off; uint32_t len; };
+
+// quantify_hits_PE (src/strain_detect.c:387-663).  Returns 0 or EXIT_FAILURE (message already printed).
+static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
+{
+    s2_reader *r1 = s2_reader_open(pe1), *r2 = nullptr;
+    if (!r1) {
+        fprintf(stderr, "could not read file (read1) %s in quantify_hits_PE() (error: %s)\n", pe1, strerror(errno));
+        return EXIT_FAILURE;
+    }
+    if (is_pe == IS_PAIRED_END) {
+        r2 = s2_reader_open(pe2);
+        if (!r2) {
+            fprintf(stderr, "could not read file (read2) is_PE %s in quantify_hits_PE() (error: %s)\n", pe2, strerror(errno));
+            s2_reader_close(r1);
+            return EXIT_FAILURE;
+        }
+    } else if (is_pe == IS_PAIRED_END_INTERLEAVE) r2 = r1;
+
+    // sequential state of the reference loop
+    int h1 = 0, i1 = 0, h2 = 0, i2 = 0;
+    std::vector<std::string> copy_kmers;       // informative k-mers (canonical spelling, in order) of the PE1 copy
+    bool have_copy = false;
+    unsigned long long evaluated = 0, reads = 0;
+    int rc = 0;
+    bool eof = false;
+
+    std::vector<uint8_t> batch;
+    std::vector<uint64_t> rec_off;
+    struct Iter { int32_t r1, r2; bool pe2_valid; bool fatal; };   // record indices in the batch (-1: shorter than 31)
+    std::vector<Iter> iters;
+    std::vector<uint32_t> hits, inf;
+    std::vector<uint64_t> pos;
+    char kbuf[S2_K + 1];
+
+    while (!eof && rc == 0) {
+        // ---- phase A: run the pairing loop ahead, collecting records >= 31 into one batch -------------
+        batch.clear(); rec_off.assign(1, 0); iters.clear();
+        auto add = [&](const char *seq, uint64_t len) -> int32_t {
+            batch.insert(batch.end(), (const uint8_t *)seq, (const uint8_t *)seq + len);
+            batch.push_back('\n');
+            rec_off.push_back(batch.size());
+            return (int32_t)rec_off.size() - 2;
+        };
+        do {                                  // at least one loop iteration per batch
+            const char *seq;
+            if (s2_reader_next(r1, &seq) < 0) { eof = true; break; }                       // :443
+            Iter it = { -1, -1, false, false };
+            if (s2_reader_len(r1) >= S2_K) it.r1 = add(seq, s2_reader_len(r1));             // :444
+            if (is_pe) {
+                const char *seq2;
+                const int64_t l2 = s2_reader_next(r2, &seq2);                              // :496
+                if (s2_reader_len(r2) >= S2_K) {                                           // :497
+                    if (l2 < 0) it.fatal = true;                                           // :501-504
+                    else { it.r2 = add(seq2, s2_reader_len(r2)); it.pe2_valid = true; }
+                }
+            }
+            iters.push_back(it);
+            if (it.fatal) { eof = true; break; }
+        } while (batch.size() < d.batch_bytes);
+        // ---- phase B: pass 1 of every collected read on the GPU -----------------------------------
+        const uint32_t n_rec = (uint32_t)rec_off.size() - 1;
+        hits.assign(n_rec + 1, 0); inf.assign(n_rec + 1, 0);
+        uint64_t n_inf = 0;
+        if (n_rec) {
+            uint64_t cap = std::max<uint64_t>(4096, batch.size() / 32);
+            for (;;) {
+                pos.resize(cap);
+                if (s2_scan_detect(d.ctx, d.table, batch.data(), batch.size(), rec_off.data(), n_rec, hits.data(), inf.data(),
+                                   pos.data(), cap, &n_inf, 0, nullptr)) {
+                    fprintf(stderr, "%s\n", s2_last_error());
+                    rc = EXIT_FAILURE;
+                    break;
+                }
+                if (n_inf <= cap) break;
+                cap = n_inf;
+            }
+            if (rc) break;
+        }
+        // informative windows per record: pos is ascending, so each record owns a contiguous range
+        std::vector<uint64_t> first(n_rec + 1, 0);
+        {
+            uint64_t p = 0;
+            for (uint32_t r = 0; r < n_rec; ++r) {
+                first[r] = p;
+                while (p < n_inf && pos[p] < rec_off[r + 1]) ++p;
+            }
+            first[n_rec] = p;
+        }
+        auto kmer_at = [&](uint64_t byte_off) -> const char * {
+            uint64_t k = 0;
+            s2_kmer_from_ascii((const char *)batch.data() + byte_off, &k);
+            s2_kmer_to_ascii(k, kbuf);
+            return kbuf;
+        };
+        auto emit = [&](const char *kmer) {
+            char head[96];
+            d.out += pe1;
+            const int n = snprintf(head, sizeof head, "\t%d\t%d\t%d\t%d\t", h1, i1, h2, i2);      // :567, :608
+            d.out.append(head, n);
+            d.out += kmer;
+            d.out += '\n';
+        };
+        // ---- phase C: replay the loop in order with the counts filled in ---------------------------------
+        for (const Iter &it : iters) {
+            if (it.r1 >= 0) {                                                              // :444-449
+                ++reads;
+                h1 = (int)hits[it.r1]; i1 = (int)inf[it.r1];
+                evaluated += (rec_off[it.r1 + 1] - rec_off[it.r1] - 1) - (S2_K - 1);
+                copy_kmers.clear();
+                have_copy = true;
+                if (i1) for (uint64_t p = first[it.r1]; p < first[it.r1 + 1]; ++p) copy_kmers.push_back(kmer_at(pos[p]));
+            }
+            if (it.fatal) {
+                fprintf(stderr, "reached end of PE2 (%s) before end of PE1 (%s), check that file names are correct\n",
+                        pe2 ? pe2 : "(null)", pe1);
+                rc = EXIT_FAILURE;
+                break;
+            }
+            if (it.r2 >= 0) {                                                              // :497-540
+                h2 = (int)hits[it.r2]; i2 = (int)inf[it.r2];
+                evaluated += (rec_off[it.r2 + 1] - rec_off[it.r2] - 1) - (S2_K - 1);
+            }
+            if (h1 + h2 >= 1 && i1 + i2 >= 1) {                                            // :547
+                if (have_copy) for (const std::string &k : copy_kmers) emit(k.c_str());     // :554-591
+                if (is_pe && it.pe2_valid)                                                 // :594-623
+                    for (uint64_t p = first[it.r2]; p < first[it.r2 + 1]; ++p) emit(kmer_at(pos[p]));
+            }
+            d.flush_out(false);
+        }
+    }
+    if (rc == 0) {
+        char foot[4][512];
+        snprintf(foot[0], sizeof foot[0], "#%s\ttotal_kmer_evaluated\t%lld\n", pe1, (long long)evaluated);          // :633-636
+        snprintf(foot[1], sizeof foot[1], "#%s\ttotal_reads_evaluated\t%lld\n", pe1, (long long)reads);
+        snprintf(foot[2], sizeof foot[2], "#%s\ttotal_genome_kmers\t%lld\n", pe1, (long long)d.genome_kmers);
+        snprintf(foot[3], sizeof foot[3], "#%s\ttotal_genome_informative_kmers\t%lld\n", pe1, (long long)d.genome_informative);
+        for (auto &f : foot) d.out += f;
+    }
+    d.flush_out(true);
+    if (r2 && r2 != r1) s2_reader_close(r2);
+    s2_reader_close(r1);
+    return rc;
+}
+
+extern "C" int s2_strain_detect_main(int argc, char **argv)
+{
+    char *a_file = nullptr, *r_file = nullptr, *b_file = nullptr, *b_file2 = nullptr, *B_file = nullptr;
+    char *seq_file_type = nullptr, *background_file = nullptr, *kmer_outfile = nullptr;
+    int is_paired_end = NOT_PAIRED_END;
+    int c;
+    optind = 1;
+    while ((c = getopt(argc, argv, "g:r:a:A:b:c:B:S:M:o:t:Hhuspn")) != EOF)     // src/strain_detect.c:84
+        switch (c) {
+        case 'a': a_file = optarg; break;
+        case 'A': break;
+        case 'b': b_file = optarg; break;
+        case 'c': b_file2 = optarg; break;
+        case 'B': B_file = optarg; break;
+        case 'r': r_file = optarg; break;
+        case 'g': background_file = optarg; break;
+        case 'o': kmer_outfile = optarg; break;
+        case 'n': is_paired_end = NOT_PAIRED_END; break;
+        case 't': seq_file_type = optarg; break;
+        case 'u': detect_usage(); break;
+        case 'h': detect_usage(); break;
+        default: detect_usage(); break;
+        }
+    if (!a_file || !kmer_outfile || !r_file) { detect_usage(); return 1; }                 // :104-111
+    if (!b_file && !B_file) { detect_usage(); return 1; }
+    if (seq_file_type) {
+        is_paired_end = get_file_type(seq_file_type);
+        if (is_paired_end == UNKNOWN_FILE_TYPE) {
+            printf("unknown filetype specification. allowed are SE, PE, PEI\n\n");
+            detect_usage();
+            return 1;
+        }
+    }
+    if (b_file && is_paired_end == IS_PAIRED_END && !b_file2) {
+        printf("commandline PE mapping requires two files (-b [file1] and -c [file2])\n\n");
+        detect_usage();
+        return 1;
+    }
+    if (b_file && B_file) {
+        printf("cannot have -B flag and -b flag\nEither have a file with metagenomics files to be detect the strain in or specify one "
+               "metagenomic file to detect the strain in\n");
+        detect_usage();
+        return 1;
+    }
+    if (background_file) {
+        fprintf(stderr, "strain_detect (B200): the -g background filter is not implemented in this build\n");
+        return EXIT_FAILURE;
+    }
+
+    Detect d;
+    d.batch_bytes = s2_env_u64("S2_DETECT_BATCH_MB", 32) << 20;
+    d.ctx = s2_init(s2_env_int("S2_DEVICE", 0), 8u << 20, 2);
+    if (!d.ctx) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+
+    // GEN_hash_sequences_set_count_vec(r_file, 31, h, NON_INFORMATIVE, 0, 0, 6)             :139
+    std::vector<uint8_t> flat;
+    if (s2_load_flat(r_file, flat) != 0) {
+        fprintf(stderr, "could not read file %s GEN_hash_sequences_set_count_vec()\n", r_file);
+        return EXIT_FAILURE;
+    }
+    d.table = s2_table_build(d.ctx, flat.data(), flat.size(), 6, 0.0, 0);
+    if (!d.table) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+    std::vector<uint8_t>().swap(flat);
+    d.genome_kmers = (unsigned)s2_table_n_keys(d.table);
+    unsigned n_found = 0;
+    const int lrc = label_informative(d, a_file, &n_found);                                // :140
+    if (lrc == -1) return EXIT_FAILURE;
+    if (lrc) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+
+    // quantify_hits_all_files                                                             :263-384
+    d.gzout = gzopen(kmer_outfile, "wb9");
+    if (!d.gzout) {
+        fprintf(stderr, "could not open *gzout file outfile %s in quantify_hits_all_files()\n", kmer_outfile);
+        return EXIT_FAILURE;
+    }
+    int rc = 0;
+    if (B_file) {
+        FILE *fp = fopen(B_file, "r");
+        if (!fp) {
+            fprintf(stderr, "could not read file file_of_filenames %s in quantify_hits_all_files()\n", B_file);
+            return EXIT_FAILURE;
+        }
+        char *line = nullptr; size_t cap = 0;
+        while (rc == 0 && getline(&line, &cap, fp) != -1) {
+            char *pos = strchr(line, '\n');
+            if (pos) *pos = '\0';
+            char *token = strtok(line, "\t");
+            const int pe = token ? get_file_type(token) : UNKNOWN_FILE_TYPE;
+            if (pe == UNKNOWN_FILE_TYPE) { printf("unknown file type skipping line (%s)\n", token ? token : "(null)"); continue; }
+            char *file1 = strtok(nullptr, "\t");
+            if (!file1) { printf("ERROR: no first file specified for %s\n", line); continue; }
+            if (pe == IS_PAIRED_END) {
+                char *file2 = strtok(nullptr, "\t");
+                if (!file2) { printf("ERROR: no second file specified for PE: %s\n", line); continue; }
+                rc = quantify_hits(d, file1, file2, pe);
+            } else {
+                rc = quantify_hits(d, file1, nullptr, pe);
+            }
+        }
+        free(line);
+        fclose(fp);
+    } else {
+        rc = quantify_hits(d, b_file, b_file2, is_paired_end);
+    }
+    // on a fatal error the reference exit()s with the gz stream unfinished; we close it either way
+    gzclose(d.gzout);
+    fflush(stdout);
+    s2_table_free(d.table);
+    s2_shutdown(d.ctx);
+    return rc;
+}

@@ -246,3 +246,80 @@ def test_detect_scan_matches_python_restatement(s2, ctx):
     assert pos.tolist() == want_pos
     assert st.hits == sum(want_hits)
     t.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# strain_detect executable against the reference-generated golden vectors
+# ---------------------------------------------------------------------------------------------
+DETECT_RUNS = {
+    "batch": ["-r", "ref.fa", "-a", "informative.txt.gz", "-B", "batch.txt"],
+    "single_pe": ["-r", "ref.fa", "-a", "informative_plain.txt", "-b", "s1_R1.fastq.gz", "-c", "s1_R2.fastq.gz", "-t", "PE"],
+    "single_se_default": ["-r", "ref.fa", "-a", "informative.txt.gz", "-b", "s3_single.fa.gz"],
+    "single_pei": ["-r", "ref.fa", "-a", "informative.txt.gz", "-b", "s2_interleaved.fa", "-t", "PEI"],
+}
+
+
+@pytest.mark.parametrize("name", sorted(DETECT_RUNS))
+@pytest.mark.parametrize("batch_mb", ["32", "0"])
+def test_strain_detect_executable_matches_reference_bytes(s2, golden_dir, tmp_path, name, batch_mb):
+    """batch_mb=0 forces one read pair per GPU batch: the stale-state replay must not depend on batching"""
+    import hashlib
+    d = os.path.join(golden_dir, "detect_edge")
+    out = str(tmp_path / "hits.gz")
+    p = s2.run_strain_detect(DETECT_RUNS[name] + ["-o", out], cwd=d, env={"S2_DETECT_BATCH_MB": batch_mb})
+    assert p.returncode == 0, p.stderr
+    assert ou.gunzip(out) == ou.gunzip(os.path.join(d, f"expected_{name}.hits.txt.gz"))
+    assert p.stdout == open(os.path.join(d, f"expected_{name}.stdout"), "rb").read()
+    assert p.stderr == open(os.path.join(d, f"expected_{name}.stderr"), "rb").read()
+    # even the compressed file is identical (same zlib, level 9, same byte stream)
+    want_md5 = open(os.path.join(d, f"expected_{name}.hits.gz.md5")).read().strip()
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == want_md5
+
+
+def test_strain_detect_executable_error_paths(s2, golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "detect_edge")
+    out = str(tmp_path / "o.gz")
+    p = s2.run_strain_detect(["-r", "ref.fa", "-a", "informative.txt.gz", "-b", "s6_R1.fastq", "-c", "s6_R2.fastq", "-t", "PE", "-o", out], cwd=d)
+    assert p.returncode == 1
+    assert p.stderr == open(os.path.join(d, "expected_pe2_short.stderr"), "rb").read()
+    for name, args in {"usage_missing": ["-r", "ref.fa"],
+                       "usage_bad_type": ["-r", "ref.fa", "-a", "informative.txt.gz", "-b", "s3_single.fa.gz", "-t", "QQ", "-o", out],
+                       "usage_pe_needs_c": ["-r", "ref.fa", "-a", "informative.txt.gz", "-b", "s3_single.fa.gz", "-t", "PE", "-o", out]}.items():
+        p = s2.run_strain_detect(args, cwd=d)
+        assert p.returncode == 1
+        assert p.stdout == open(os.path.join(d, f"expected_{name}.stdout"), "rb").read()
+        assert p.stderr == open(os.path.join(d, f"expected_{name}.stderr"), "rb").read()
+
+
+def test_strain_detect_synthetic_matches_oracle(s2, tmp_path):
+    """down-scaled config #4: 300 kb strain, 1 % informative k-mers, PE + SE + interleaved metagenomes"""
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    rng = synth.rng_for(4, 0)
+    strain = synth.genome(rng, 300_000, 6, n_runs=3)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    clean = [np.where(c == ord("N"), ord("T"), c).astype(np.uint8) for c in strain]
+    other = synth.genome(rng, 300_000, 3)
+    # informative = every 100th window of contig 0 (plain text, as kmer_scrub_filter.py prints them)
+    c0 = clean[0].tobytes()
+    with open(os.path.join(tmp, "inf.txt"), "wb") as f:
+        f.write(b"#kmer\n")
+        for i in range(0, len(c0) - 31, 100):
+            f.write(c0[i:i + 31] + b"\n")
+    r1 = synth.sample_reads(rng, clean + other * 4, 20_000, 150, sub_rate=0.004, n_rate=2e-4)
+    r2 = synth.sample_reads(rng, clean + other * 4, 20_000, 150, sub_rate=0.004, n_rate=2e-4)
+    synth.write_reads_fastq(os.path.join(tmp, "a_R1.fastq.gz"), r1)
+    synth.write_reads_fastq(os.path.join(tmp, "a_R2.fastq.gz"), r2)
+    synth.write_fasta(os.path.join(tmp, "b_se.fa"), [r for r in r1[:5000]], wrap=0)
+    inter = np.empty((10_000, 150), dtype=np.uint8)
+    inter[0::2] = r1[:5000]; inter[1::2] = r2[:5000]
+    synth.write_reads_fastq(os.path.join(tmp, "c_inter.fastq"), inter)
+    open(os.path.join(tmp, "batch.txt"), "w").write("PE\ta_R1.fastq.gz\ta_R2.fastq.gz\nSE\tb_se.fa\nPEI\tc_inter.fastq\n")
+    args = ["-r", "strain.fa", "-a", "inf.txt", "-B", "batch.txt"]
+    o = ou.oracle_cli(["detect"] + args + ["-m", os.path.join(tmp, "msg")], cwd=tmp)
+    p = s2.run_strain_detect(args + ["-o", os.path.join(tmp, "hits.gz")], cwd=tmp, env={"S2_DETECT_BATCH_MB": "1"})
+    assert o.returncode == 0 and p.returncode == 0, p.stderr
+    got = ou.gunzip(os.path.join(tmp, "hits.gz"))
+    assert got == o.stdout
+    assert got.count(b"\n") > 1000
+    assert p.stdout == open(os.path.join(tmp, "msg"), "rb").read()
