@@ -32,12 +32,14 @@ __device__ __forceinline__ void ld_bucket256(const uint16_t *fp, uint32_t bucket
                  : "l"(p));
 }
 
-__device__ __forceinline__ uint32_t fp_any_match(const uint32_t (&x)[8], uint32_t fp2)
+// 16 fingerprints against one: 8 HSET2.  Bit i of the result = low half of word i matched (slot 2i),
+// bit 16+i = high half of word i matched (slot 2i+1); 0 = no match.
+__device__ __forceinline__ uint32_t fp_match_bits(const uint32_t (&x)[8], uint32_t fp2)
 {
     const __half2 f = *reinterpret_cast<const __half2 *>(&fp2);
     uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m |= __heq2_mask(*reinterpret_cast<const __half2 *>(&x[i]), f);
+    for (int i = 0; i < 8; ++i) m |= __heq2_mask(*reinterpret_cast<const __half2 *>(&x[i]), f) & (0x00010001u << i);
     return m;
 }
 
@@ -163,26 +165,20 @@ __device__ __forceinline__ void issue_group(const S2TableView &t, uint32_t w0, u
 
 template <int G>
 __device__ __forceinline__ void consume_group(uint32_t vmask, int g, const uint32_t (&x)[G][8],
-                                              const uint32_t (&fp2)[G], uint32_t &cand, uint64_t &candpos)
+                                              const uint32_t (&fp2)[G], uint32_t &cand, uint32_t &cp_lo, uint32_t &cp_hi)
 {
 #pragma unroll
     for (int u = 0; u < G; ++u) {
         const unsigned j = G * g + u;
-        const uint32_t any = fp_any_match(x[u], fp2[u]);
+        const uint32_t m = fp_match_bits(x[u], fp2[u]);
         const bool full = x[u][7] > 0xFFFFu;
-        if (((vmask >> j) & 1u) && (any != 0 || full)) {
-            // rare: remember which of the 16 slots matched first, so the slow path can go straight to
-            // the key (4 bits per window; a full bucket without a match records 0 and falls back)
-            const uint32_t fp = fp2[u] & 0xFFFFu;
-            uint32_t bm = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                bm |= ((x[u][i] & 0xFFFFu) == fp ? 1u : 0u) << (2 * i);
-                bm |= ((x[u][i] >> 16) == fp ? 1u : 0u) << (2 * i + 1);
-            }
-            const uint32_t first = bm ? (uint32_t)__ffs(bm) - 1u : 0u;
+        // branch-free: which of the 16 slots matched (any one; 4 bits per window) so that the slow path
+        // can go straight to the key.  A full bucket without a match records garbage and falls back.
+        const uint32_t b = 31u - (uint32_t)__clz(m);
+        const uint32_t slot4 = ((b & 15u) << 1) | ((b >> 4) & 1u);
+        if (((vmask >> j) & 1u) && (m != 0 || full)) {
             cand |= 1u << j;
-            candpos |= (uint64_t)first << (4 * j);
+            if (j < 8) cp_lo |= slot4 << (4 * j); else cp_hi |= slot4 << (4 * (j - 8));
         }
     }
 }
@@ -284,7 +280,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
         // each group's arithmetic between its neighbours (no instruction is emitted).
 #define S2_GROUP_FENCE() asm volatile("" : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(r0), "+r"(r1), "+r"(r2), "+r"(vmask))
         uint32_t vmask = 0, cand = 0;
-        uint64_t candpos = 0;
+        uint32_t cp_lo = 0, cp_hi = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) vmask |= (s2_window_valid(m0, m1, m2, j) ? 1u : 0u) << j;
         {
@@ -295,11 +291,11 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
                 for (int g = 0; g < NG; ++g) {
                     if (g & 1) {
                         if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, dummy_bucket, g + 1, xa, fa);
-                        consume_group<G>(vmask, g, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb), cand, candpos);
+                        consume_group<G>(vmask, g, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb), cand, cp_lo, cp_hi);
                         S2_GROUP_FENCE();
                     } else {
                         if (g + 1 < NG) issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, dummy_bucket, g + 1, reinterpret_cast<uint32_t (&)[G][8]>(xb), reinterpret_cast<uint32_t (&)[G]>(fb));
-                        consume_group<G>(vmask, g, xa, fa, cand, candpos);
+                        consume_group<G>(vmask, g, xa, fa, cand, cp_lo, cp_hi);
                         S2_GROUP_FENCE();
                     }
                 }
@@ -307,7 +303,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     issue_group<G>(t, w0, w1, w2, r0, r1, r2, vmask, dummy_bucket, g, xa, fa);
-                    consume_group<G>(vmask, g, xa, fa, cand, candpos);
+                    consume_group<G>(vmask, g, xa, fa, cand, cp_lo, cp_hi);
                     S2_GROUP_FENCE();
                 }
             }
@@ -324,7 +320,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
                 const uint32_t at = qlen + __popc(bal & ((1u << lane) - 1u));
                 const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
                 q_canon[at] = canon;
-                q_slot[at] = s2_bucket_of(s2_hash(canon).h, t.n_buckets) * S2_BUCKET_SLOTS + ((uint32_t)(candpos >> (4 * j)) & 15u);
+                q_slot[at] = s2_bucket_of(s2_hash(canon).h, t.n_buckets) * S2_BUCKET_SLOTS + (((j < 8 ? cp_lo >> (4 * j) : cp_hi >> (4 * (j - 8)))) & 15u);
                 if (MODE == S2_MODE_DETECT) q_pos[at] = tile * 512 + (uint64_t)lane * 16 + j;
             }
             qlen += __popc(bal);
