@@ -365,7 +365,7 @@ static const S2ScanVariant g_variants[] = {
     S2_VARIANT(4, 3, true),    // 8
     S2_VARIANT(1, 4, true),    // 9
 };
-static int g_variant = 3;   // G2_B4_Pfalse: best of the round-1 sweep (profiles/r1b_scan_sweep.txt)
+static int g_variant = 9;   // G1_B4_Ptrue: best on the config-2 workload in the round-1 sweeps (profiles/r1d_scan_sweep.txt)
 
 int s2_scan_variant_count(void) { return (int)(sizeof g_variants / sizeof g_variants[0]); }
 const char *s2_scan_variant_name(int v) { return (v >= 0 && v < s2_scan_variant_count()) ? g_variants[v].name : "?"; }
