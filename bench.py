@@ -315,19 +315,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from strainer2_b200 import multigpu
+    ar_buf = torch.empty(table.n_keys, dtype=torch.int32, device=dev) if dist is not None else None
+
     def allreduce_counts():
+        """the ONE collective of the path: dense first-occurrence-order count vector, SUM over ranks"""
         if dist is None:
             return
-        buf = torch.empty(table.n_keys, dtype=torch.int32, device=dev)       # uint32 wrap-around add == int32 add
-        table.gather_counts_dev(1, buf)
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-        table.scatter_counts_dev(1, buf)
+        table.gather_counts_dev(1, ar_buf)                 # slot order -> first-occurrence order (same on all ranks)
+        multigpu.allreduce_counts_(ar_buf, dist)           # NCCL over NVLink; uint32 wrap-around add == int32 add
+        table.scatter_counts_dev(1, ar_buf)
         torch.cuda.synchronize()
 
     # ---- (1) device-resident: K launches between two CUDA events on the launching stream ---------
     for i in range(max(args.warmup, 3)):
         ctx.scan_count_enqueue(table, dev_batches[i % 2], 1)
     ctx.sync()
+    allreduce_counts()                                     # warm-up of the collective (NCCL channel set-up)
     ctx.kernel_time(reset=True)
     table.clear_counts(1)
     sampler = ClockSampler(local)
