@@ -66,10 +66,11 @@ uint64_t    s2_table_n_keys(const s2_table *t);          /* BIO_getHashSize()   
 uint64_t    s2_table_n_slots(const s2_table *t);
 uint64_t    s2_table_hbm_bytes(const s2_table *t);       /* fingerprints + keys + counters        */
 uint64_t    s2_table_probe_bytes(const s2_table *t);     /* the fingerprint array only            */
-/* keys[n_keys] (62-bit, A0 C1 G2 T3, first base highest) and djb2[n_keys] = hashU() of each key's
- * ASCII spelling before "% M" (src/BIO_hash.c:208-216), both in FIRST-OCCURRENCE order = the order
- * the reference inserted them, which is all s2_roworder_emulate() needs.  Either may be NULL. */
-int         s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2);
+/* keys[n_keys] (62-bit, A0 C1 G2 T3, first base highest), djb2[n_keys] = hashU() of each key's ASCII
+ * spelling before "% M" (src/BIO_hash.c:208-216) and first_pos[n_keys] = byte offset in the build
+ * stream of the window that inserted the key, all in FIRST-OCCURRENCE order = the order the reference
+ * inserted them, which is all s2_roworder_emulate() needs.  Any of the three may be NULL. */
+int         s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2, uint32_t *first_pos);
 /* counter column `col` in first-occurrence order (host buffers of n_keys uint32) */
 int         s2_table_counts_fetch(s2_table *t, int col, uint32_t *host_out);
 int         s2_table_counts_store(s2_table *t, int col, const uint32_t *host_in);

@@ -41,7 +41,7 @@ SIGNATURES = {
     "s2_table_n_slots": (C.c_uint64, [C.c_void_p]),
     "s2_table_hbm_bytes": (C.c_uint64, [C.c_void_p]),
     "s2_table_probe_bytes": (C.c_uint64, [C.c_void_p]),
-    "s2_table_export": (C.c_int, [C.c_void_p, c_u64p, c_u32p]),
+    "s2_table_export": (C.c_int, [C.c_void_p, c_u64p, c_u32p, c_u32p]),
     "s2_table_counts_fetch": (C.c_int, [C.c_void_p, C.c_int, c_u32p]),
     "s2_table_counts_store": (C.c_int, [C.c_void_p, C.c_int, c_u32p]),
     "s2_table_counts_clear": (C.c_int, [C.c_void_p, C.c_int]),

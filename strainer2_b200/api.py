@@ -175,13 +175,15 @@ class StrainTable:
     def probe_bytes(self):
         return lib.s2_table_probe_bytes(self.h)
 
-    def export(self):
-        """keys (uint64, A0 C1 G2 T3) and djb2 (uint32), both in first-occurrence order."""
+    def export(self, with_pos=False):
+        """keys (uint64, A0 C1 G2 T3) and djb2 (uint32) [and first_pos (uint32)], all in first-occurrence order."""
         n = self.n_keys
         keys = np.zeros(n, dtype=np.uint64)
         djb2 = np.zeros(n, dtype=np.uint32)
-        check(lib.s2_table_export(self.h, _ptr(keys, C.c_uint64), _ptr(djb2, C.c_uint32)), "s2_table_export")
-        return keys, djb2
+        pos = np.zeros(n, dtype=np.uint32)
+        check(lib.s2_table_export(self.h, _ptr(keys, C.c_uint64), _ptr(djb2, C.c_uint32), _ptr(pos, C.c_uint32)),
+              "s2_table_export")
+        return (keys, djb2, pos) if with_pos else (keys, djb2)
 
     def counts(self, col):
         out = np.zeros(self.n_keys, dtype=np.uint32)

@@ -213,6 +213,7 @@ struct s2_table {
     s2_ctx *ctx = nullptr;
     S2TableView v = {};
     uint32_t *rank_slot = nullptr;     // first-occurrence rank -> slot
+    uint32_t *rank_pos = nullptr;      // first-occurrence rank -> byte offset of that first window in the build stream
     uint32_t *scratch = nullptr;       // n_keys uint32 staging for fetch / store
     uint64_t n_keys = 0;
 };
@@ -230,7 +231,7 @@ extern "C" void s2_table_free(s2_table *t)
 {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
-    cudaFree(t->v.fp); cudaFree(t->v.keys); cudaFree(t->v.counts); cudaFree(t->rank_slot); cudaFree(t->scratch);
+    cudaFree(t->v.fp); cudaFree(t->v.keys); cudaFree(t->v.counts); cudaFree(t->rank_slot); cudaFree(t->rank_pos); cudaFree(t->scratch);
     delete t;
 }
 
@@ -265,18 +266,19 @@ static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t 
     CK(cudaMemsetAsync(t->v.keys, 0xFF, t->v.n_slots * sizeof(uint64_t), st));
     CK(cudaMemsetAsync(t->v.counts, 0, t->v.n_slots * sizeof(uint32_t) * n_cols, st));
 
-    uint32_t *first_pos = nullptr, *slot_of_pos = nullptr, *block_sums = nullptr, *rank_tmp = nullptr;
+    uint32_t *first_pos = nullptr, *slot_of_pos = nullptr, *block_sums = nullptr, *rank_tmp = nullptr, *pos_tmp = nullptr;
     unsigned long long *d_n = nullptr;
     const uint32_t n_blocks = (uint32_t)((n_bytes + 1023) / 1024);
     CK(cudaMalloc((void **)&first_pos, t->v.n_slots * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&slot_of_pos, (n_bytes + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&block_sums, (n_blocks + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&rank_tmp, (upper + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&pos_tmp, (upper + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&d_n, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(first_pos, 0xFF, t->v.n_slots * sizeof(uint32_t), st));
 
     s2_launch_build_insert(d_bases, n_bytes, t->v, first_pos, slot_of_pos, st);
-    s2_launch_build_rank(n_bytes, first_pos, slot_of_pos, block_sums, n_blocks, rank_tmp, d_n, st);
+    s2_launch_build_rank(n_bytes, first_pos, slot_of_pos, block_sums, n_blocks, rank_tmp, pos_tmp, d_n, st);
     CK(cudaGetLastError());
     unsigned long long n_keys = 0;
     CK(cudaMemcpyAsync(&n_keys, d_n, sizeof n_keys, cudaMemcpyDeviceToHost, st));
@@ -284,9 +286,11 @@ static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t 
     t->n_keys = n_keys;
     CK(cudaMalloc((void **)&t->rank_slot, (n_keys + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&t->scratch, (n_keys + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&t->rank_pos, (n_keys + 1) * sizeof(uint32_t)));
     CK(cudaMemcpyAsync(t->rank_slot, rank_tmp, n_keys * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(t->rank_pos, pos_tmp, n_keys * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(first_pos); cudaFree(slot_of_pos); cudaFree(block_sums); cudaFree(rank_tmp); cudaFree(d_n);
+    cudaFree(first_pos); cudaFree(slot_of_pos); cudaFree(block_sums); cudaFree(rank_tmp); cudaFree(pos_tmp); cudaFree(d_n);
     if (tmp_bases) cudaFree(tmp_bases);
     return 0;
 }
@@ -304,7 +308,7 @@ extern "C" s2_table *s2_table_build(s2_ctx *c, const void *bases, uint64_t n_byt
     return t;
 }
 
-extern "C" int s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2)
+extern "C" int s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2, uint32_t *first_pos)
 {
     s2_ctx *c = t->ctx;
     CK(cudaSetDevice(c->device));
@@ -317,6 +321,7 @@ extern "C" int s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2)
     CK(cudaGetLastError());
     if (keys) CK(cudaMemcpyAsync(keys, d_keys, t->n_keys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     if (djb2) CK(cudaMemcpyAsync(djb2, d_h, t->n_keys * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (first_pos) CK(cudaMemcpyAsync(first_pos, t->rank_pos, t->n_keys * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     cudaFree(d_keys); cudaFree(d_h);
     return 0;

@@ -157,6 +157,9 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
         fprintf(stderr, "could not read file %s GEN_hash_sequences_set_count_vec()\n", r_file);   // src/genome_compare.c:986
         return fail(nullptr);
     }
+    // windows of the -r genome with a byte outside ACGTN become string keys on the host;
+    // nullptr (the normal case) means no such window exists and the host never looks at a window again
+    s2_exotic *exotic = s2_exotic_build(flat.data(), flat.size(), 4);
     const char *load_env = getenv("S2_LOAD");
     s2_table *table = s2_table_build(ctx, flat.data(), flat.size(), 4, load_env ? atof(load_env) : 0.0, 0);
     if (!table) return fail(s2_last_error());
@@ -206,6 +209,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
                 bases += (uint64_t)l;
                 if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
                 if (!w.append(seq, (uint64_t)l, col)) { stop.store(true); break; }
+                if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
             }
             s2_reader_close(r);
             total_bases += bases; total_lookups += lookups;
@@ -227,8 +231,8 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     // ---- print_hash_counts: rows in the reference table's slot order
     const uint64_t n = s2_table_n_keys(table);
     std::vector<uint64_t> keys(n);
-    std::vector<uint32_t> djb2(n), order(n), cols[4];
-    if (s2_table_export(table, keys.data(), djb2.data())) return fail(s2_last_error());
+    std::vector<uint32_t> djb2(n), pos(n), cols[4];
+    if (s2_table_export(table, keys.data(), djb2.data(), exotic ? pos.data() : nullptr)) return fail(s2_last_error());
     const int n_print = C_file ? 4 : 3;
     const uint32_t *colp[4] = { nullptr, nullptr, nullptr, nullptr };
     for (int k = 0; k < n_print; ++k) {
@@ -236,8 +240,38 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
         if (s2_table_counts_fetch(table, k, cols[k].data())) return fail(s2_last_error());
         colp[k] = cols[k].data();
     }
-    if (s2_roworder_emulate(djb2.data(), n, 0, order.data(), nullptr)) return fail(s2_last_error());
-    if (s2_format_count_table(stdout, keys.data(), order.data(), n, colp, n_print, n_threads)) return fail(s2_last_error());
+    if (!exotic) {
+        std::vector<uint32_t> order(n);
+        if (s2_roworder_emulate(djb2.data(), n, 0, order.data(), nullptr)) return fail(s2_last_error());
+        if (s2_format_count_table(stdout, keys.data(), order.data(), n, colp, n_print, n_threads)) return fail(s2_last_error());
+    } else {
+        // merge the device keys and the host string keys by first occurrence = the reference's insertion order
+        std::vector<S2ExoRow> xr;
+        s2_exotic_rows(exotic, xr);
+        const uint64_t total = n + xr.size();
+        std::vector<uint32_t> mdjb2(total), src(total), order(total);      // src: < n device key, else n + exotic index
+        uint64_t a = 0, b = 0, o = 0;
+        while (a < n || b < xr.size()) {
+            if (b >= xr.size() || (a < n && pos[a] < xr[b].first_pos)) { mdjb2[o] = djb2[a]; src[o++] = (uint32_t)a++; }
+            else { mdjb2[o] = xr[b].djb2; src[o++] = (uint32_t)(n + b++); }
+        }
+        if (s2_roworder_emulate(mdjb2.data(), total, 0, order.data(), nullptr)) return fail(s2_last_error());
+        fputs("#kmer\treference_count\tpangenome_count\tmetagenome_count\tdrug_count\n", stdout);
+        char spell[S2_K + 1];
+        for (uint64_t r = 0; r < total; ++r) {
+            const uint32_t id = src[order[r]];
+            if (id < n) {
+                s2_kmer_to_ascii(keys[id], spell);
+                fputs(spell, stdout);
+                for (int k = 0; k < n_print; ++k) printf("\t%d", (int)cols[k][id]);
+            } else {
+                const S2ExoRow &x = xr[id - n];
+                fwrite(x.key.data(), 1, x.key.size(), stdout);
+                for (int k = 0; k < n_print; ++k) printf("\t%d", (int)x.counts[k]);
+            }
+            fputc('\n', stdout);
+        }
+    }
     fflush(stdout);
     const auto t_done = std::chrono::steady_clock::now();
 
@@ -252,6 +286,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
                 (unsigned long long)st.hits, kms, (unsigned long long)kl,
                 total_bases.load() / 1e9 / std::max(1e-9, sec(t_built, t_scanned)));
     }
+    s2_exotic_free(exotic);
     s2_table_free(table);
     s2_shutdown(ctx);
     if (progress) fclose(progress);

@@ -52,6 +52,7 @@ static int get_file_type(const char *s)                             // src/strai
 struct Detect {
     s2_ctx *ctx = nullptr;
     s2_table *table = nullptr;
+    s2_exotic *exotic = nullptr;        // string keys for -r windows with bytes outside ACGTN (normally nullptr)
     gzFile gzout = nullptr;
     unsigned genome_kmers = 0, genome_informative = 0;
     uint64_t batch_bytes = 32ull << 20;
@@ -109,12 +110,13 @@ static int label_informative(Detect &d, const char *a_file, unsigned *num_lines_
                    "scrubbed kmer len, seed len): %s, %d, %d\n", a_file, L.text.c_str(), (int)L.text.size(), S2_K);
             continue;
         }
-        const bool hit = L.acgt && found[qi++];
-        if (hit) { ++n_found; distinct.insert(L.kmer); }
+        bool hit = L.acgt && found[qi++];
+        if (!L.acgt && d.exotic) hit = s2_exotic_flag(d.exotic, L.text.c_str());   // raw spelling, string semantics
+        if (hit) { ++n_found; if (L.acgt) distinct.insert(L.kmer); }
         else printf("error could not find informative kmer %s in the total kmer list\n", L.text.c_str());
     }
     *num_lines_found = n_found;
-    d.genome_informative = (unsigned)distinct.size();              // src/strain_detect.c:285-290
+    d.genome_informative = (unsigned)(distinct.size() + s2_exotic_n_informative(d.exotic));   // src/strain_detect.c:285-290
     return 0;
 }
 
@@ -198,6 +200,12 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
             }
             if (rc) break;
         }
+        if (d.exotic)                                   // foreign-byte windows: host string path, pass-1 orientation
+            for (uint32_t r = 0; r < n_rec; ++r) {
+                int xh = 0, xi = 0;
+                s2_exotic_pass1(d.exotic, (const char *)batch.data() + rec_off[r], rec_off[r + 1] - rec_off[r] - 1, &xh, &xi);
+                hits[r] += (uint32_t)xh; inf[r] += (uint32_t)xi;
+            }
         // informative windows per record: pos is ascending, so each record owns a contiguous range
         std::vector<uint64_t> first(n_rec + 1, 0);
         {
@@ -214,6 +222,20 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
             s2_kmer_to_ascii(k, kbuf);
             return kbuf;
         };
+        // informative k-mers of record r in window order (device positions merged with the string path's)
+        std::vector<std::pair<uint64_t, std::string>> xlist;
+        auto record_kmers = [&](int32_t r, std::vector<std::string> &out) {
+            out.clear();
+            xlist.clear();
+            if (d.exotic) s2_exotic_pass2(d.exotic, (const char *)batch.data() + rec_off[r], rec_off[r + 1] - rec_off[r] - 1, xlist);
+            size_t xi = 0;
+            for (uint64_t p = first[r]; p < first[r + 1]; ++p) {
+                while (xi < xlist.size() && rec_off[r] + xlist[xi].first < pos[p]) out.push_back(xlist[xi++].second);
+                out.push_back(kmer_at(pos[p]));
+            }
+            while (xi < xlist.size()) out.push_back(xlist[xi++].second);
+        };
+        std::vector<std::string> pe2_kmers;
         auto emit = [&](const char *kmer) {
             char head[96];
             d.out += pe1;
@@ -230,7 +252,7 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
                 evaluated += (rec_off[it.r1 + 1] - rec_off[it.r1] - 1) - (S2_K - 1);
                 copy_kmers.clear();
                 have_copy = true;
-                if (i1) for (uint64_t p = first[it.r1]; p < first[it.r1 + 1]; ++p) copy_kmers.push_back(kmer_at(pos[p]));
+                if (i1) record_kmers(it.r1, copy_kmers);
             }
             if (it.fatal) {
                 fprintf(stderr, "reached end of PE2 (%s) before end of PE1 (%s), check that file names are correct\n",
@@ -244,8 +266,10 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
             }
             if (h1 + h2 >= 1 && i1 + i2 >= 1) {                                            // :547
                 if (have_copy) for (const std::string &k : copy_kmers) emit(k.c_str());     // :554-591
-                if (is_pe && it.pe2_valid)                                                 // :594-623
-                    for (uint64_t p = first[it.r2]; p < first[it.r2 + 1]; ++p) emit(kmer_at(pos[p]));
+                if (is_pe && it.pe2_valid) {                                               // :594-623
+                    record_kmers(it.r2, pe2_kmers);
+                    for (const std::string &k : pe2_kmers) emit(k.c_str());
+                }
             }
             d.flush_out(false);
         }
@@ -326,8 +350,9 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     }
     d.table = s2_table_build(d.ctx, flat.data(), flat.size(), 6, 0.0, 0);
     if (!d.table) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+    d.exotic = s2_exotic_build(flat.data(), flat.size(), 6);
     std::vector<uint8_t>().swap(flat);
-    d.genome_kmers = (unsigned)s2_table_n_keys(d.table);
+    d.genome_kmers = (unsigned)(s2_table_n_keys(d.table) + s2_exotic_n_keys(d.exotic));
     unsigned n_found = 0;
     const int lrc = label_informative(d, a_file, &n_found);                                // :140
     if (lrc == -1) return EXIT_FAILURE;
@@ -371,6 +396,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     // on a fatal error the reference exit()s with the gz stream unfinished; we close it either way
     gzclose(d.gzout);
     fflush(stdout);
+    s2_exotic_free(d.exotic);
     s2_table_free(d.table);
     s2_shutdown(d.ctx);
     return rc;

@@ -9,3 +9,16 @@ void s2_set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 // environment knobs (argv of the drop-in executables stays identical to the reference's)
 int      s2_env_int(const char *name, int dflt);
 uint64_t s2_env_u64(const char *name, uint64_t dflt);
+
+// ---- host string path for windows containing bytes outside ACGTN (s2_exotic.cpp) ----------
+struct s2_exotic;
+struct S2ExoRow { std::string key; uint64_t first_pos; uint32_t djb2; uint32_t counts[8]; };
+s2_exotic *s2_exotic_build(const uint8_t *flat, uint64_t n, int n_cols);     // nullptr when there is nothing to do
+void       s2_exotic_free(s2_exotic *ex);
+uint64_t   s2_exotic_n_keys(const s2_exotic *ex);
+uint64_t   s2_exotic_n_informative(const s2_exotic *ex);
+void       s2_exotic_count_record(s2_exotic *ex, const char *seq, uint64_t len, int col);
+void       s2_exotic_rows(const s2_exotic *ex, std::vector<S2ExoRow> &rows);
+bool       s2_exotic_flag(s2_exotic *ex, const char *line31);
+void       s2_exotic_pass1(s2_exotic *ex, const char *seq, uint64_t len, int *hits, int *inf);
+void       s2_exotic_pass2(s2_exotic *ex, const char *seq, uint64_t len, std::vector<std::pair<uint64_t, std::string>> &out);

@@ -523,7 +523,8 @@ s2_rank_scan_kernel(uint32_t *__restrict__ block_sums, uint32_t n_blocks, unsign
 
 __global__ void __launch_bounds__(S2_THREADS)
 s2_rank_write_kernel(uint64_t n, const uint32_t *__restrict__ first_pos, const uint32_t *__restrict__ slot_of_pos,
-                     const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ rank_slot)
+                     const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ rank_slot,
+                     uint32_t *__restrict__ rank_pos)
 {
     const uint64_t base = (uint64_t)blockIdx.x * S2_RANK_PER_BLOCK + (uint64_t)threadIdx.x * S2_RANK_PER_THREAD;
     uint32_t f[S2_RANK_PER_THREAD], s[S2_RANK_PER_THREAD], c = 0;
@@ -532,17 +533,18 @@ s2_rank_write_kernel(uint64_t n, const uint32_t *__restrict__ first_pos, const u
     uint32_t total;
     uint32_t r = block_offsets[blockIdx.x] + block_exclusive_scan(c, total);
 #pragma unroll
-    for (int i = 0; i < S2_RANK_PER_THREAD; ++i) if (f[i]) rank_slot[r++] = s[i];
+    for (int i = 0; i < S2_RANK_PER_THREAD; ++i)
+        if (f[i]) { rank_slot[r] = s[i]; rank_pos[r] = (uint32_t)(base + i); ++r; }
 }
 
 void s2_launch_build_rank(uint64_t n_bytes, const uint32_t *first_pos, const uint32_t *slot_of_pos,
-                          uint32_t *block_sums, uint32_t n_blocks, uint32_t *rank_slot,
+                          uint32_t *block_sums, uint32_t n_blocks, uint32_t *rank_slot, uint32_t *rank_pos,
                           unsigned long long *d_n_keys, cudaStream_t stream)
 {
     if (n_blocks == 0) { cudaMemsetAsync(d_n_keys, 0, sizeof(unsigned long long), stream); return; }
     s2_rank_count_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(n_bytes, first_pos, slot_of_pos, block_sums);
     s2_rank_scan_kernel<<<1, S2_THREADS, 0, stream>>>(block_sums, n_blocks, d_n_keys);
-    s2_rank_write_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(n_bytes, first_pos, slot_of_pos, block_sums, rank_slot);
+    s2_rank_write_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(n_bytes, first_pos, slot_of_pos, block_sums, rank_slot, rank_pos);
 }
 
 // ------------------------------------------------------------------------------------------------

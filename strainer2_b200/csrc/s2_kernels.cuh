@@ -46,7 +46,7 @@ void s2_launch_build_insert(const uint8_t *bases, uint64_t n_bytes, const S2Tabl
                             uint32_t *first_pos, uint32_t *slot_of_pos, cudaStream_t stream);
 // number of distinct keys is returned through *d_n_keys (device); rank_slot must hold >= n windows
 void s2_launch_build_rank(uint64_t n_bytes, const uint32_t *first_pos, const uint32_t *slot_of_pos,
-                          uint32_t *block_sums, uint32_t n_blocks, uint32_t *rank_slot,
+                          uint32_t *block_sums, uint32_t n_blocks, uint32_t *rank_slot, uint32_t *rank_pos,
                           unsigned long long *d_n_keys, cudaStream_t stream);
 void s2_launch_export(const S2TableView &t, const uint32_t *rank_slot, uint64_t n_keys,
                       uint64_t *keys_out, uint32_t *djb2_out, cudaStream_t stream);

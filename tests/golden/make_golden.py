@@ -277,6 +277,53 @@ def case_detect(base):
     return d
 
 
+def case_iupac(base):
+    """bytes other than ACGTN are kept, complemented through COMPLEMENT[] and hashed as strings"""
+    r = random.Random(424242)
+    d = os.path.join(base, "iupac")
+    os.makedirs(d, exist_ok=True)
+    g = list(rnd(r, 1500))
+    for p, c in [(100, "R"), (101, "Y"), (400, "K"), (700, "M"), (701, "-"), (900, "r"), (1100, "E"), (1300, "S"), (1301, "N"), (1450, "W")]:
+        g[p] = c
+    g = "".join(g)
+    contigs = [("x1", g), ("x2", rnd(r, 200) + "B" + rnd(r, 200)), ("x3_plain", rnd(r, 300))]
+    write(os.path.join(d, "ref.fa"), fasta(contigs, wrap=60))
+    same = [("y1", g[50:800]), ("y2", revcomp(g[850:1499]).replace("Y", "R")), ("y3", contigs[1][1].lower()), ("y4", g[1080:1130]), ("y5", rnd(r, 100) + "K" + rnd(r, 100))]
+    write(os.path.join(d, "a1.fa"), fasta(same, wrap=70))
+    reads = []
+    for i in range(150):
+        st = r.randrange(0, len(g) - 100)
+        x = g[st:st + 100]
+        reads.append(("q%d" % i, revcomp(x) if i % 3 == 0 else x))
+    write(os.path.join(d, "b1.fastq"), fastq(reads))
+    write(os.path.join(d, "listA.txt"), "a1.fa\n")
+    write(os.path.join(d, "listB.txt"), "b1.fastq\n")
+    write(os.path.join(d, "listC.txt"), "ref.fa\na1.fa\n")
+    rc, out, err = run("kmer_scrub_count", ["-r", "ref.fa", "-A", "listA.txt", "-B", "listB.txt", "-C", "listC.txt"], d)
+    assert rc == 0, err
+    write(os.path.join(d, "expected_count.tsv"), out)
+    write(os.path.join(d, "expected_count.stderr"), err)
+    # informative list: a few plain and a few IUPAC-containing k-mers, some reverse-complemented
+    rows = [l.split(b"\t")[0].decode("latin-1") for l in out.split(b"\n")[1:] if l]
+    odd = [k for k in rows if any(c not in "ACGT" for c in k)]
+    plain = [k for k in rows if all(c in "ACGT" for c in k)]
+    assert len(odd) > 50
+    inf = odd[::3] + plain[::40] + [revcomp(plain[5])]
+    write(os.path.join(d, "informative.txt"), "\n".join(inf) + "\n")
+    pe1 = [("p%d/1" % i, s) for i, (_, s) in enumerate(reads[:60])]
+    pe2 = [("p%d/2" % i, revcomp(s) if "E" not in s else s) for i, (_, s) in enumerate(reads[60:120])]
+    write(os.path.join(d, "r1.fastq"), fastq(pe1))
+    write(os.path.join(d, "r2.fastq"), fastq(pe2))
+    write(os.path.join(d, "batch.txt"), "PE\tr1.fastq\tr2.fastq\nSE\tb1.fastq\n")
+    rc, out, err = run("strain_detect", ["-r", "ref.fa", "-a", "informative.txt", "-B", "batch.txt", "-o", "out.tmp.gz"], d)
+    assert rc == 0, err
+    gzdata = open(os.path.join(d, "out.tmp.gz"), "rb").read()
+    write(os.path.join(d, "expected_detect.hits.txt.gz"), gzip.decompress(gzdata), gz=True)
+    write(os.path.join(d, "expected_detect.stdout"), out)
+    os.remove(os.path.join(d, "out.tmp.gz"))
+    return d
+
+
 if __name__ == "__main__":
     if not os.path.exists(os.path.join(REF, "kmer_scrub_count")):
         sys.exit("oracle/_ref is not built: run `make -C oracle` in the dev container first")
@@ -284,5 +331,6 @@ if __name__ == "__main__":
     os.makedirs(base, exist_ok=True)
     print(case_count(base))
     print(case_detect(base))
+    print(case_iupac(base))
     total = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(base) for f in fs)
     print("golden bytes:", total)

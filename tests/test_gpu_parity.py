@@ -323,3 +323,18 @@ def test_strain_detect_synthetic_matches_oracle(s2, tmp_path):
     assert got == o.stdout
     assert got.count(b"\n") > 1000
     assert p.stdout == open(os.path.join(tmp, "msg"), "rb").read()
+
+
+def test_iupac_bytes_are_hashed_as_strings_like_the_reference(s2, golden_dir, tmp_path):
+    """windows with bytes outside ACGTN go through the host string path; output bytes equal the
+    reference's (rows containing R/Y/K/M/-/E ..., merged into the replayed row order)"""
+    d = os.path.join(golden_dir, "iupac")
+    p = s2.run_kmer_scrub_count(["-r", "ref.fa", "-A", "listA.txt", "-B", "listB.txt", "-C", "listC.txt"], cwd=d)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout == open(os.path.join(d, "expected_count.tsv"), "rb").read()
+    assert p.stderr == open(os.path.join(d, "expected_count.stderr"), "rb").read()
+    out = str(tmp_path / "hits.gz")
+    p = s2.run_strain_detect(["-r", "ref.fa", "-a", "informative.txt", "-B", "batch.txt", "-o", out], cwd=d)
+    assert p.returncode == 0, p.stderr
+    assert ou.gunzip(out) == ou.gunzip(os.path.join(d, "expected_detect.hits.txt.gz"))
+    assert p.stdout == open(os.path.join(d, "expected_detect.stdout"), "rb").read()

@@ -53,6 +53,20 @@ def test_oracle_detect_pe2_short_is_an_error(golden_dir, tmp_path):
     assert p.stderr == open(os.path.join(d, "expected_pe2_short.stderr"), "rb").read()
 
 
+def test_oracle_matches_golden_iupac_case(golden_dir, tmp_path):
+    """IUPAC / foreign bytes are hashed as strings by the reference; so does the oracle"""
+    d = os.path.join(golden_dir, "iupac")
+    p = ou.oracle_cli(["count", "-r", "ref.fa", "-A", "listA.txt", "-B", "listB.txt", "-C", "listC.txt"], cwd=d)
+    assert p.returncode == 0
+    assert p.stdout == open(os.path.join(d, "expected_count.tsv"), "rb").read()
+    assert p.stderr == open(os.path.join(d, "expected_count.stderr"), "rb").read()
+    msg = str(tmp_path / "msg")
+    p = ou.oracle_cli(["detect", "-r", "ref.fa", "-a", "informative.txt", "-B", "batch.txt", "-m", msg], cwd=d)
+    assert p.returncode == 0
+    assert p.stdout == ou.gunzip(os.path.join(d, "expected_detect.hits.txt.gz"))
+    assert open(msg, "rb").read() == open(os.path.join(d, "expected_detect.stdout"), "rb").read()
+
+
 def test_oracle_reader_matches_kseq_dumps(golden_dir):
     d = os.path.join(golden_dir, "count_edge")
     n = 0
