@@ -83,6 +83,8 @@ int         s2_table_counts_scatter_dev(s2_table *t, int col, const void *dev_in
 /* hash_scrubbed_kmers() labelling, src/strain_detect.c:687-717: mark canonical 62-bit k-mers as
  * INFORMATIVE.  found[i] (may be NULL) = 1 if kmers[i] is a key of the table. */
 int         s2_table_flag(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found);
+/* background_filter() demotion, src/strain_detect.c:218-228: back to NON_INFORMATIVE */
+int         s2_table_unflag(s2_table *t, const uint64_t *kmers, uint64_t n);
 int         s2_table_lookup(s2_table *t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out);
 
 /* ---------------------------------------------------------------- count scan ---------------- */

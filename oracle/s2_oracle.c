@@ -28,7 +28,7 @@ uint32_t s2o_djb2(const char *s)
 }
 
 /* src/BIO_sequence.c:203-213, restated as a switch (verified against the real array by
- * tests/test_oracle_vs_reference.py::test_complement_table). -1 = "no complement". */
+ * tests/test_oracle_golden.py::test_complement_table_matches_reference). -1 = "no complement". */
 int s2o_complement(int c)
 {
     switch (c) {
@@ -561,10 +561,59 @@ static int file_type(const char *s)                                     /* src/s
     return -1;
 }
 
-/* src/strain_detect.c:137-146 + :263-384 (no -g; output text uncompressed) */
+static int cmp_desc(const void *a, const void *b)                         /* src/strain_detect.c:255-261 */
+{
+    return (int)(*(const unsigned *)b - *(const unsigned *)a);
+}
+
+static int removed_at(unsigned thr, const unsigned *v, unsigned n)        /* kmer_removed, :242-252 */
+{
+    int c = 0;
+    for (unsigned i = 0; i < n; ++i) if (v[i] >= thr) ++c;
+    return c;
+}
+
+/* background_filter, src/strain_detect.c:160-240 (fraction_to_remove = 0.5, :82).  num_inform = number of
+ * informative-list LINES that matched (duplicates count).  Returns 0 or the reference's exit status. */
+int s2o_background_filter(s2o_table *t, const char *background_file, unsigned num_inform, FILE *msg, FILE *err)
+{
+    const double fraction = 0.5;
+    unsigned keep = (unsigned)(int)(num_inform * fraction);
+    unsigned *v = (unsigned *)calloc(num_inform ? num_inform : 1, sizeof *v);
+    unsigned n = 0, thr = 1;
+    int rc;
+    fprintf(msg, "#removing %f proportion of %s kmers; informative %d keep at least %d\n", fraction, background_file,
+            num_inform, keep);
+    if ((rc = s2o_count_list(t, background_file, NULL, 5, NULL, err)) != 0) return rc;
+    for (unsigned s = 0; s < t->M; ++s) {
+        if (!t->slot[s]) continue;
+        const oentry *e = &t->ent[t->slot[s] - 1];
+        if (e->vec[0] != 2) continue;
+        if (n >= num_inform) { fprintf(err, "Error: too many background kmers\n"); return 1; }
+        v[n++] = e->vec[5];
+    }
+    qsort(v, num_inform, sizeof *v, cmp_desc);
+    if (keep >= 1 && v[keep - 1] > thr) thr = v[keep - 1];
+    while ((unsigned)removed_at(thr, v, num_inform) > keep) ++thr;
+    unsigned demoted = 0;
+    for (size_t i = 0; i < t->n_ent; ++i)
+        if (t->ent[i].vec[0] == 2 && t->ent[i].vec[5] >= thr) { t->ent[i].vec[0] = 1; ++demoted; }
+    fprintf(msg, "#final_threshold %d removes %d background kmers %d removed\n", thr, removed_at(thr, v, num_inform), demoted);
+    free(v);
+    return 0;
+}
+
+/* src/strain_detect.c:137-146 + :263-384 (output text uncompressed) */
 int s2o_strain_detect(const char *r_file, const char *a_file, const char *B_file,
                       const char *b_file, const char *c_file, const char *type,
                       FILE *out, FILE *msg, FILE *err)
+{
+    return s2o_strain_detect_g(r_file, a_file, NULL, B_file, b_file, c_file, type, out, msg, err);
+}
+
+int s2o_strain_detect_g(const char *r_file, const char *a_file, const char *g_file, const char *B_file,
+                        const char *b_file, const char *c_file, const char *type,
+                        FILE *out, FILE *msg, FILE *err)
 {
     s2o_table *t = s2o_table_new(S2O_INITIAL_CAPACITY, 6);
     unsigned n_lines = 0, n_inf = 0;
@@ -577,6 +626,7 @@ int s2o_strain_detect(const char *r_file, const char *a_file, const char *B_file
         fprintf(err, "could not read file %s in hash_scrubbed_kmers()\n", a_file);
         return EXIT_FAILURE;
     }
+    if (g_file && (rc = s2o_background_filter(t, g_file, n_lines, msg, err)) != 0) return rc;   /* :142-143 */
     for (size_t e = 0; e < t->n_ent; ++e) if (t->ent[e].vec[0] == 2) ++n_inf;    /* :285-290 */
     unsigned n_keys = s2o_table_size(t);
 

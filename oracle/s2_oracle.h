@@ -4,7 +4,7 @@
  * reference (citations are file:line under /root/reference/).  It exists to be the *checker* for the
  * CUDA path in tests/, in __graft_entry__.smoke() and as bench.py's cpu_baseline fallback.
  *
- * PARITY STATUS: PINNED.  tests/test_oracle_vs_reference.py runs the unmodified reference
+ * PARITY STATUS: PINNED.  tests/test_oracle_golden.py runs the unmodified reference
  * (oracle/_ref, built from /root/reference/src by oracle/Makefile) beside this restatement on
  * config #1 (test/example.sh) and on the synthetic edge-case corpus and requires byte-identical
  * output; the small reference-generated vectors are committed under tests/golden/ so that the same
@@ -77,6 +77,12 @@ int s2o_quantify_hits(s2o_table *t, const char *pe1, const char *pe2, int is_pe,
 int s2o_strain_detect(const char *r_file, const char *a_file, const char *B_file,
                       const char *b_file, const char *c_file, const char *type,
                       FILE *out, FILE *msg, FILE *err);
+
+/* same with the -g background filter (src/strain_detect.c:142-143, :160-240); g_file may be NULL */
+int s2o_strain_detect_g(const char *r_file, const char *a_file, const char *g_file, const char *B_file,
+                        const char *b_file, const char *c_file, const char *type,
+                        FILE *out, FILE *msg, FILE *err);
+int s2o_background_filter(s2o_table *t, const char *background_file, unsigned num_inform, FILE *msg, FILE *err);
 
 #ifdef __cplusplus
 }

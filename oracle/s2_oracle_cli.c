@@ -26,21 +26,22 @@ int main(int argc, char **argv)
         s2o_reader_close(r);
         return 0;
     }
-    const char *r = NULL, *A = NULL, *B = NULL, *C = NULL, *p = NULL, *a = NULL, *b = NULL, *c = NULL, *t = NULL, *m = NULL;
+    const char *r = NULL, *A = NULL, *B = NULL, *C = NULL, *p = NULL, *a = NULL, *b = NULL, *c = NULL, *t = NULL, *m = NULL, *g = NULL;
     int o;
     optind = 2;
-    while ((o = getopt(argc, argv, "r:A:B:C:p:a:b:c:t:m:")) != -1)
+    while ((o = getopt(argc, argv, "r:A:B:C:p:a:b:c:t:m:g:")) != -1)
         switch (o) {
         case 'r': r = optarg; break; case 'A': A = optarg; break; case 'B': B = optarg; break;
         case 'C': C = optarg; break; case 'p': p = optarg; break; case 'a': a = optarg; break;
         case 'b': b = optarg; break; case 'c': c = optarg; break; case 't': t = optarg; break;
         case 'm': m = optarg; break;
+        case 'g': g = optarg; break;
         default: return 2;
         }
     if (!strcmp(cmd, "count")) return s2o_kmer_scrub_count(r, A, B, C, p, stdout, stderr);
     if (!strcmp(cmd, "detect")) {
         FILE *msg = m ? fopen(m, "w") : stderr;   /* -m FILE: where the reference's stdout chatter goes */
-        int rc = s2o_strain_detect(r, a, B, b, c, t, stdout, msg, stderr);
+        int rc = s2o_strain_detect_g(r, a, g, B, b, c, t, stdout, msg, stderr);
         if (m) fclose(msg);
         return rc;
     }

@@ -48,6 +48,7 @@ SIGNATURES = {
     "s2_table_counts_gather_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "s2_table_counts_scatter_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "s2_table_flag": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u8p]),
+    "s2_table_unflag": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64]),
     "s2_table_lookup": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u32p]),
     "s2_scan_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
                                 C.POINTER(ScanStatsStruct)]),

@@ -378,7 +378,7 @@ extern "C" int s2_table_counts_clear(s2_table *t, int col)
     return 0;
 }
 
-static int table_query(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found, uint32_t *slots, bool flag)
+static int table_query(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found, uint32_t *slots, bool flag, int set = 1)
 {
     s2_ctx *c = t->ctx;
     CK(cudaSetDevice(c->device));
@@ -389,7 +389,7 @@ static int table_query(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *
     CK(cudaMalloc((void **)&d_k, n * sizeof(uint64_t)));
     CK(cudaMalloc(&d_o, osz));
     CK(cudaMemcpyAsync(d_k, kmers, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    if (flag) s2_launch_flag(t->v, d_k, n, (uint8_t *)d_o, st);
+    if (flag) s2_launch_flag(t->v, d_k, n, (uint8_t *)d_o, set, st);
     else s2_launch_lookup(t->v, d_k, n, (uint32_t *)d_o, st);
     CK(cudaGetLastError());
     void *dst = flag ? (void *)found : (void *)slots;
@@ -402,6 +402,11 @@ static int table_query(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *
 extern "C" int s2_table_flag(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found)
 {
     return table_query(t, kmers, n, found, nullptr, true);
+}
+
+extern "C" int s2_table_unflag(s2_table *t, const uint64_t *kmers, uint64_t n)
+{
+    return table_query(t, kmers, n, nullptr, nullptr, true, 0);
 }
 
 extern "C" int s2_table_lookup(s2_table *t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out)

@@ -46,10 +46,9 @@ int s2_load_flat(const char *path, std::vector<uint8_t> &flat)
     return 0;
 }
 
-struct WorkItem { std::string path; int col; bool skip; };
 
 // reads the newline separated list exactly like the reference: getline, cut at the first '\n' only
-static int read_list(const char *list_file, int col, const char *skip_file, std::vector<WorkItem> &out)
+int s2_read_list(const char *list_file, int col, const char *skip_file, std::vector<S2WorkItem> &out)
 {
     FILE *fp = fopen(list_file, "r");
     if (!fp) {
@@ -114,6 +113,82 @@ struct BatchWriter {
     }
 };
 
+int s2_default_reader_threads()
+{
+    int n = s2_env_int("S2_THREADS", 0);
+    if (n <= 0) { n = (int)std::thread::hardware_concurrency(); if (n > 16) n = 16; }
+    return n < 1 ? 1 : n;
+}
+
+// The list drivers GEN_all_kmer_counts / GEN_all_kmer_counts_skip_file (src/genome_compare.c:115-177) for a
+// whole work list: reader threads take files in list order (progress line and "skipping" note written
+// at dispatch, under the lock, so their order is the reference's), inflate + parse them straight into
+// pinned batches and submit those to the GPU.  Returns false after a failure; open_error carries the
+// reference's message when a file could not be opened (dispatch stops there, like the reference's exit).
+bool s2_scan_work_items(s2_ctx *ctx, s2_table *table, s2_exotic *exotic, std::vector<S2WorkItem> &work, int n_threads,
+                        FILE *progress, std::string &open_error, uint64_t *bases_out, uint64_t *lookups_out)
+{
+    std::mutex mu;                      // guards next / progress / stderr ordering
+    size_t next = 0;
+    std::atomic<bool> stop(false);
+    std::atomic<uint64_t> total_bases(0), total_lookups(0);
+
+    auto reader = [&]() {
+        BatchWriter w{ ctx, table };
+        for (;;) {
+            s2_reader *r = nullptr; int col = 0;
+            {
+                std::lock_guard<std::mutex> g(mu);
+                while (!r) {
+                    if (stop.load() || next >= work.size()) break;
+                    S2WorkItem &it = work[next++];
+                    if (progress) {
+                        time_t now = time(nullptr);
+                        fprintf(progress, "%s\t%s", it.path.c_str(), asctime(localtime(&now)));   // src/genome_compare.c:167-170
+                    }
+                    if (it.skip) { fprintf(stderr, "skipping %s (identical match)\n", it.path.c_str()); continue; }   // :141
+                    r = s2_reader_open(it.path.c_str());
+                    if (!r) {
+                        open_error = "could not read file " + it.path + " in GEN_calculate_kmer_count()";   // :196
+                        stop.store(true);
+                        break;
+                    }
+                    col = it.col;
+                }
+            }
+            if (!r) break;
+            const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
+            while ((l = s2_reader_next(r, &seq)) >= 0) {
+                bases += (uint64_t)l;
+                if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
+                if (!w.append(seq, (uint64_t)l, col)) {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (open_error.empty()) open_error = s2_last_error();
+                    stop.store(true);
+                    break;
+                }
+                if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
+            }
+            s2_reader_close(r);
+            total_bases += bases; total_lookups += lookups;
+            if (w.failed) break;
+        }
+        if (!w.flush()) {
+            std::lock_guard<std::mutex> g(mu);
+            if (open_error.empty()) open_error = s2_last_error();
+            stop.store(true);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < n_threads; ++i) pool.emplace_back(reader);
+    reader();
+    for (auto &t : pool) t.join();
+
+    if (bases_out) *bases_out = total_bases.load();
+    if (lookups_out) *lookups_out = total_lookups.load();
+    return !stop.load() || !open_error.empty();
+}
+
 extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
 {
     char *A_file = nullptr, *B_file = nullptr, *C_file = nullptr, *r_file = nullptr, *p_file = nullptr;
@@ -146,8 +221,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     };
 
     const auto t_start = std::chrono::steady_clock::now();
-    int n_threads = s2_env_int("S2_THREADS", 0);
-    if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads > 16) n_threads = 16; if (n_threads < 1) n_threads = 1; }
+    const int n_threads = s2_default_reader_threads();
     s2_ctx *ctx = s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 64) << 20, n_threads + 2);
     if (!ctx) return fail(s2_last_error());
 
@@ -169,63 +243,18 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     // ---- work list: -A into column 1, -B into column 2, -C (skipping -r itself) into column 3
     // The reference opens each list only when it gets to it, so an unreadable later list is reported
     // after the earlier lists have been scanned; the output (nothing on stdout, EXIT_FAILURE) is the same.
-    std::vector<WorkItem> work;
-    if (read_list(A_file, 1, nullptr, work)) return fail(nullptr);
-    if (read_list(B_file, 2, nullptr, work)) return fail(nullptr);
-    if (C_file && read_list(C_file, 3, r_file, work)) return fail(nullptr);
+    std::vector<S2WorkItem> work;
+    if (s2_read_list(A_file, 1, nullptr, work)) return fail(nullptr);
+    if (s2_read_list(B_file, 2, nullptr, work)) return fail(nullptr);
+    if (C_file && s2_read_list(C_file, 3, r_file, work)) return fail(nullptr);
 
-    std::mutex mu;                      // guards next / progress / stderr ordering
-    size_t next = 0;
-    std::atomic<bool> stop(false);
     std::string open_error;
-    std::atomic<uint64_t> total_bases(0), total_lookups(0);
-
-    auto reader = [&]() {
-        BatchWriter w{ ctx, table };
-        for (;;) {
-            s2_reader *r = nullptr; int col = 0;
-            {
-                std::lock_guard<std::mutex> g(mu);
-                while (!r) {
-                    if (stop.load() || next >= work.size()) break;
-                    WorkItem &it = work[next++];
-                    if (progress) {
-                        time_t now = time(nullptr);
-                        fprintf(progress, "%s\t%s", it.path.c_str(), asctime(localtime(&now)));   // src/genome_compare.c:167-170
-                    }
-                    if (it.skip) { fprintf(stderr, "skipping %s (identical match)\n", it.path.c_str()); continue; }   // :141
-                    r = s2_reader_open(it.path.c_str());
-                    if (!r) {
-                        open_error = "could not read file " + it.path + " in GEN_calculate_kmer_count()";   // :196
-                        stop.store(true);
-                        break;
-                    }
-                    col = it.col;
-                }
-            }
-            if (!r) break;
-            const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
-            while ((l = s2_reader_next(r, &seq)) >= 0) {
-                bases += (uint64_t)l;
-                if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
-                if (!w.append(seq, (uint64_t)l, col)) { stop.store(true); break; }
-                if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
-            }
-            s2_reader_close(r);
-            total_bases += bases; total_lookups += lookups;
-            if (w.failed) break;
-        }
-        if (!w.flush()) stop.store(true);
-    };
-    std::vector<std::thread> pool;
-    for (int i = 1; i < n_threads; ++i) pool.emplace_back(reader);
-    reader();
-    for (auto &t : pool) t.join();
-
+    uint64_t total_bases = 0, total_lookups = 0;
+    const bool pool_ok = s2_scan_work_items(ctx, table, exotic, work, n_threads, progress, open_error, &total_bases, &total_lookups);
     s2_scan_stats st = {};
     if (s2_sync(ctx, &st)) return fail(s2_last_error());
     if (!open_error.empty()) return fail(open_error.c_str());
-    if (stop.load()) return fail(s2_last_error());
+    if (!pool_ok) return fail(s2_last_error());
     const auto t_scanned = std::chrono::steady_clock::now();
 
     // ---- print_hash_counts: rows in the reference table's slot order
@@ -282,9 +311,9 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
         fprintf(stderr, "[s2] keys=%llu build=%.3fs scan=%.3fs print=%.3fs bases=%llu lookups=%llu hits=%llu "
                         "kernel_ms=%.3f launches=%llu scan_Gbases_per_s=%.3f\n",
                 (unsigned long long)n, sec(t_start, t_built), sec(t_built, t_scanned), sec(t_scanned, t_done),
-                (unsigned long long)total_bases.load(), (unsigned long long)total_lookups.load(),
+                (unsigned long long)total_bases, (unsigned long long)total_lookups,
                 (unsigned long long)st.hits, kms, (unsigned long long)kl,
-                total_bases.load() / 1e9 / std::max(1e-9, sec(t_built, t_scanned)));
+                total_bases / 1e9 / std::max(1e-9, sec(t_built, t_scanned)));
     }
     s2_exotic_free(exotic);
     s2_table_free(table);

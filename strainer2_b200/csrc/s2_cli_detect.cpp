@@ -57,6 +57,7 @@ struct Detect {
     unsigned genome_kmers = 0, genome_informative = 0;
     uint64_t batch_bytes = 32ull << 20;
     std::string out;                    // pending text for gzout
+    std::unordered_set<uint64_t> informative;   // device keys currently labelled INFORMATIVE
 
     void flush_out(bool force)
     {
@@ -103,7 +104,7 @@ static int label_informative(Detect &d, const char *a_file, unsigned *num_lines_
     std::vector<uint8_t> found(q.size() + 1);
     if (s2_table_flag(d.table, q.data(), q.size(), found.data())) return -2;
     size_t qi = 0; unsigned n_found = 0;
-    std::unordered_set<uint64_t> distinct;
+    std::unordered_set<uint64_t> &distinct = d.informative;
     for (auto &L : lines) {
         if (!L.right_len) {
             printf("error string length in the scrubbed kmer file (%s) must be the same size as the kmer length (scrubbed kmer, "
@@ -117,6 +118,57 @@ static int label_informative(Detect &d, const char *a_file, unsigned *num_lines_
     }
     *num_lines_found = n_found;
     d.genome_informative = (unsigned)(distinct.size() + s2_exotic_n_informative(d.exotic));   // src/strain_detect.c:285-290
+    return 0;
+}
+
+// background_filter (src/strain_detect.c:160-240): count the informative k-mers in background metagenomes
+// (the count scan into column 5, on the GPU), then demote those at or above a threshold chosen so that at
+// most half of them go.  num_inform = matched informative-list LINES (duplicates count), as in the reference.
+static int background_filter(Detect &d, const char *background_file, unsigned num_inform, int n_threads)
+{
+    const double fraction = 0.5;                                                           // :82
+    const unsigned keep = (unsigned)(int)(num_inform * fraction);
+    printf("#removing %f proportion of %s kmers; informative %d keep at least %d\n", fraction, background_file, num_inform, keep);
+    std::vector<S2WorkItem> work;
+    if (s2_read_list(background_file, 5, nullptr, work)) return EXIT_FAILURE;               // GEN_all_kmer_counts(..., 5, NULL)
+    std::string open_error;
+    const bool ok = s2_scan_work_items(d.ctx, d.table, d.exotic, work, n_threads, nullptr, open_error, nullptr, nullptr);
+    if (s2_sync(d.ctx, nullptr)) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+    if (!open_error.empty()) { fprintf(stderr, "%s\n", open_error.c_str()); return EXIT_FAILURE; }
+    if (!ok) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+
+    // background counts of the informative keys (device keys by first-occurrence rank + string keys)
+    const uint64_t n = s2_table_n_keys(d.table);
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> bg(n);
+    if (s2_table_export(d.table, keys.data(), nullptr, nullptr) || s2_table_counts_fetch(d.table, 5, bg.data())) {
+        fprintf(stderr, "%s\n", s2_last_error());
+        return EXIT_FAILURE;
+    }
+    std::vector<unsigned> v;
+    std::vector<uint64_t> inf_keys; std::vector<uint32_t> inf_bg;
+    for (uint64_t i = 0; i < n; ++i)
+        if (d.informative.count(keys[i])) { inf_keys.push_back(keys[i]); inf_bg.push_back(bg[i]); v.push_back(bg[i]); }
+    std::vector<S2ExoRow> xr;
+    s2_exotic_rows(d.exotic, xr);
+    std::vector<std::string> x_inf;
+    for (auto &x : xr) if (s2_exotic_is_informative(d.exotic, x.key.c_str())) { v.push_back(x.counts[5]); x_inf.push_back(x.key); }
+    if (v.size() > num_inform) { fprintf(stderr, "Error: too many background kmers\n"); return 1; }   // :187-190
+    v.resize(num_inform, 0u);                                                              // calloc'd tail
+    std::sort(v.begin(), v.end(), [](unsigned a, unsigned b) { return a > b; });            // qsort, descending (:196)
+    unsigned thr = 1;
+    if (keep >= 1 && v[keep - 1] > thr) thr = v[keep - 1];                                  // :207-208
+    auto removed = [&](unsigned t) { unsigned c = 0; for (unsigned x : v) c += x >= t ? 1 : 0; return c; };
+    while (removed(thr) > keep) ++thr;                                                     // :212-214
+    std::vector<uint64_t> demote;
+    unsigned n_demoted = 0;
+    for (size_t i = 0; i < inf_keys.size(); ++i)
+        if (inf_bg[i] >= thr) { demote.push_back(inf_keys[i]); d.informative.erase(inf_keys[i]); ++n_demoted; }
+    for (auto &x : xr)
+        if (s2_exotic_is_informative(d.exotic, x.key.c_str()) && x.counts[5] >= thr) { s2_exotic_set_informative(d.exotic, x.key.c_str(), false); ++n_demoted; }
+    if (s2_table_unflag(d.table, demote.data(), demote.size())) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+    printf("#final_threshold %d removes %d background kmers %d removed\n", thr, removed(thr), n_demoted);   // :230
+    d.genome_informative = (unsigned)(d.informative.size() + s2_exotic_n_informative(d.exotic));
     return 0;
 }
 
@@ -332,14 +384,11 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
         detect_usage();
         return 1;
     }
-    if (background_file) {
-        fprintf(stderr, "strain_detect (B200): the -g background filter is not implemented in this build\n");
-        return EXIT_FAILURE;
-    }
-
     Detect d;
     d.batch_bytes = s2_env_u64("S2_DETECT_BATCH_MB", 32) << 20;
-    d.ctx = s2_init(s2_env_int("S2_DEVICE", 0), 8u << 20, 2);
+    const int n_threads = s2_default_reader_threads();
+    d.ctx = background_file ? s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 64) << 20, n_threads + 2)
+                            : s2_init(s2_env_int("S2_DEVICE", 0), 8u << 20, 2);
     if (!d.ctx) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
 
     // GEN_hash_sequences_set_count_vec(r_file, 31, h, NON_INFORMATIVE, 0, 0, 6)             :139
@@ -357,6 +406,10 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     const int lrc = label_informative(d, a_file, &n_found);                                // :140
     if (lrc == -1) return EXIT_FAILURE;
     if (lrc) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+    if (background_file) {                                                                 // :142-143
+        const int brc = background_filter(d, background_file, n_found, n_threads);
+        if (brc) return brc;
+    }
 
     // quantify_hits_all_files                                                             :263-384
     d.gzout = gzopen(kmer_outfile, "wb9");

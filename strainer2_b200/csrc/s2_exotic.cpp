@@ -178,6 +178,20 @@ bool s2_exotic_flag(s2_exotic *ex, const char *line31)
     return true;
 }
 
+bool s2_exotic_is_informative(const s2_exotic *ex, const char *key)
+{
+    if (!ex) return false;
+    auto it = ex->map.find(key);
+    return it != ex->map.end() && it->second.informative;
+}
+
+void s2_exotic_set_informative(s2_exotic *ex, const char *key, bool v)
+{
+    if (!ex) return;
+    auto it = ex->map.find(key);
+    if (it != ex->map.end()) it->second.informative = v;
+}
+
 uint64_t s2_exotic_n_informative(const s2_exotic *ex)
 {
     uint64_t n = 0;

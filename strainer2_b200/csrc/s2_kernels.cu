@@ -574,13 +574,16 @@ __global__ void s2_scatter_kernel(uint32_t *__restrict__ col, const uint32_t *__
     if (i < n_keys) col[rank_slot[i]] = in[i];
 }
 
-__global__ void s2_flag_kernel(S2TableView t, const uint64_t *__restrict__ kmers, uint64_t n, uint8_t *__restrict__ found)
+__global__ void s2_flag_kernel(S2TableView t, const uint64_t *__restrict__ kmers, uint64_t n, uint8_t *__restrict__ found, int set)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t slot; uint64_t key;
     const bool hit = probe_exact(t, kmers[i] & S2_KMER_MASK, slot, key);
-    if (hit) atomicOr(reinterpret_cast<unsigned long long *>(&t.keys[slot]), S2_INFORMATIVE_BIT);
+    if (hit) {
+        if (set) atomicOr(reinterpret_cast<unsigned long long *>(&t.keys[slot]), S2_INFORMATIVE_BIT);
+        else atomicAnd(reinterpret_cast<unsigned long long *>(&t.keys[slot]), ~S2_INFORMATIVE_BIT);
+    }
     if (found) found[i] = hit ? 1 : 0;
 }
 
@@ -629,9 +632,9 @@ void s2_launch_scatter_counts(const S2TableView &t, int col, const uint32_t *ran
     if (n_keys) s2_scatter_kernel<<<blocks_for(n_keys, 256), 256, 0, stream>>>(t.counts + (uint64_t)col * t.n_slots, rank_slot, n_keys, in);
 }
 
-void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found, cudaStream_t stream)
+void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found, int set, cudaStream_t stream)
 {
-    if (n) s2_flag_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(t, kmers, n, found);
+    if (n) s2_flag_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(t, kmers, n, found, set);
 }
 
 void s2_launch_lookup(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out, cudaStream_t stream)

@@ -54,7 +54,7 @@ void s2_launch_gather_counts(const S2TableView &t, int col, const uint32_t *rank
                              uint32_t *out, cudaStream_t stream);
 void s2_launch_scatter_counts(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys,
                               const uint32_t *in, cudaStream_t stream);
-void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found,
+void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found, int set,
                     cudaStream_t stream);
 void s2_launch_lookup(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out,
                       cudaStream_t stream);

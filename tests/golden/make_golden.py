@@ -259,6 +259,18 @@ def case_detect(base):
         write(os.path.join(d, "expected_%s.stdout" % name), out)
         write(os.path.join(d, "expected_%s.stderr" % name), err)
         os.remove(os.path.join(d, "out.tmp.gz"))
+    # -g background filter: background = the interleaved + single-end sets
+    write(os.path.join(d, "background.txt"), "s2_interleaved.fa\ns3_single.fa.gz\n")
+    for name, args in {"bg_batch": ["-r", "ref.fa", "-a", "informative.txt.gz", "-g", "background.txt", "-B", "batch.txt", "-o", "out.tmp.gz"],
+                       "bg_single": ["-r", "ref.fa", "-a", "informative_plain.txt", "-g", "background.txt", "-b", "s1_R1.fastq.gz", "-c",
+                                     "s1_R2.fastq.gz", "-t", "PE", "-o", "out.tmp.gz"]}.items():
+        rc, out, err = run("strain_detect", args, d)
+        assert rc == 0, (name, rc, err)
+        gzdata = open(os.path.join(d, "out.tmp.gz"), "rb").read()
+        write(os.path.join(d, "expected_%s.hits.txt.gz" % name), gzip.decompress(gzdata), gz=True)
+        write(os.path.join(d, "expected_%s.stdout" % name), out)
+        write(os.path.join(d, "expected_%s.stderr" % name), err)
+        os.remove(os.path.join(d, "out.tmp.gz"))
     # PE2 runs out while its stale length is >= 31 -> error exit
     v1, v2 = pairs(20, 80, with_short=False)
     write(os.path.join(d, "s6_R1.fastq"), fastq(v1))

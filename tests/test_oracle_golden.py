@@ -15,6 +15,9 @@ COUNT_RUNS = {
     "A_only": ["-r", "ref.fa.gz", "-A", "listA.txt", "-B", "listB_empty.txt"],
 }
 DETECT_RUNS = {
+    "bg_batch": ["-r", "ref.fa", "-a", "informative.txt.gz", "-g", "background.txt", "-B", "batch.txt"],
+    "bg_single": ["-r", "ref.fa", "-a", "informative_plain.txt", "-g", "background.txt", "-b", "s1_R1.fastq.gz", "-c",
+                  "s1_R2.fastq.gz", "-t", "PE"],
     "batch": ["-r", "ref.fa", "-a", "informative.txt.gz", "-B", "batch.txt"],
     "single_pe": ["-r", "ref.fa", "-a", "informative_plain.txt", "-b", "s1_R1.fastq.gz", "-c", "s1_R2.fastq.gz", "-t", "PE"],
     "single_se_default": ["-r", "ref.fa", "-a", "informative.txt.gz", "-b", "s3_single.fa.gz"],
