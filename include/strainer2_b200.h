@@ -80,6 +80,11 @@ int         s2_table_counts_clear(s2_table *t, int col);
  * identical on every replica, whatever slot each replica's build happened to give a key. */
 int         s2_table_counts_gather_dev(s2_table *t, int col, void *dev_out);
 int         s2_table_counts_scatter_dev(s2_table *t, int col, const void *dev_in);
+/* The collective itself for a single process driving several GPUs (what the executables do with
+ * S2_GPUS > 1): tabs[i] are replicas built from the same bytes on n different GPUs; after the call
+ * every replica's column `col` holds the sum over all replicas.  One ncclAllReduce(sum, uint32) over
+ * NVLink on the dense first-occurrence-order vectors; libnccl.so.2 is dlopen()ed on first use. */
+int         s2_tables_allreduce(s2_table **tabs, int n, int col);
 /* hash_scrubbed_kmers() labelling, src/strain_detect.c:687-717: mark canonical 62-bit k-mers as
  * INFORMATIVE.  found[i] (may be NULL) = 1 if kmers[i] is a key of the table. */
 int         s2_table_flag(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found);

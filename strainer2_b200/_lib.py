@@ -47,6 +47,7 @@ SIGNATURES = {
     "s2_table_counts_clear": (C.c_int, [C.c_void_p, C.c_int]),
     "s2_table_counts_gather_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "s2_table_counts_scatter_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "s2_tables_allreduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "s2_table_flag": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u8p]),
     "s2_table_unflag": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64]),
     "s2_table_lookup": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u32p]),

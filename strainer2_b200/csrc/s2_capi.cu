@@ -6,6 +6,9 @@
 #include "s2_kmer.cuh"
 #include "s2_internal.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <condition_variable>
 #include <cstdarg>
@@ -110,10 +113,8 @@ extern "C" s2_ctx *s2_init(int device, uint64_t batch_bytes, int n_lanes)
     c->batch_bytes = (c->batch_bytes + 511) & ~511ull;
     c->n_lanes = n_lanes > 0 ? n_lanes : 4;
     c->lanes.resize(c->n_lanes);
-    for (auto &l : c->lanes) {
+    for (auto &l : c->lanes) {                       // batch buffers are allocated on first use (lane_buffers)
         CKN(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-        CKN(cudaHostAlloc((void **)&l.h_buf, c->batch_bytes, cudaHostAllocDefault));
-        CKN(cudaMalloc((void **)&l.d_buf, c->batch_bytes + 64));
         CKN(cudaEventCreate(&l.k0));
         CKN(cudaEventCreate(&l.k1));
     }
@@ -165,6 +166,15 @@ extern "C" const char *s2_tune_scan_variant_name(int v) { return s2_scan_variant
 
 extern "C" int s2_ctx_device(const s2_ctx *c) { return c->device; }
 extern "C" int s2_ctx_sm_count(const s2_ctx *c) { return c->n_sm; }
+
+// Page-locked allocation is slow (~0.5 GB/s), so a lane gets its device buffer, and its pinned host
+// buffer only if the caller fills batches through s2_batch_acquire, the first time it is used.
+static int lane_buffers(s2_ctx *c, Lane &l, bool need_host)
+{
+    if (!l.d_buf) CK(cudaMalloc((void **)&l.d_buf, c->batch_bytes + 64));
+    if (need_host && !l.h_buf) CK(cudaHostAlloc((void **)&l.h_buf, c->batch_bytes, cudaHostAllocDefault));
+    return 0;
+}
 
 // wait for a lane's work and fold its kernel time into the context (caller holds c->mu)
 static int lane_retire(s2_ctx *c, Lane &l)
@@ -415,6 +425,71 @@ extern "C" int s2_table_lookup(s2_table *t, const uint64_t *kmers, uint64_t n, u
 }
 
 // ------------------------------------------------------------------------------------------------
+// the one collective of the path, for a single process that drives several GPUs (the executables)
+// ------------------------------------------------------------------------------------------------
+// NCCL is dlopen()ed on first use: the library itself has no link-time dependency on it, so loading
+// it next to a framework that bundles its own NCCL (torch) is safe, and single-GPU users need none.
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!h) { s2_set_error("cannot load libnccl.so.2: %s", dlerror()); return false; }
+#define S2_NCCL_SYM(field, name) field = (decltype(field))dlsym(h, name); if (!field) { s2_set_error("libnccl lacks %s", name); return false; }
+        S2_NCCL_SYM(CommInitAll, "ncclCommInitAll") S2_NCCL_SYM(CommDestroy, "ncclCommDestroy") S2_NCCL_SYM(AllReduce, "ncclAllReduce")
+        S2_NCCL_SYM(GroupStart, "ncclGroupStart") S2_NCCL_SYM(GroupEnd, "ncclGroupEnd") S2_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef S2_NCCL_SYM
+        return true;
+    }
+} g_nccl;
+}
+
+#define CKNCCL(call)                                                                               \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) { s2_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(r_)); return -1; } \
+    } while (0)
+
+extern "C" int s2_tables_allreduce(s2_table **tabs, int n, int col)
+{
+    if (n <= 1) return 0;
+    if (!g_nccl.load()) return -1;
+    const uint64_t n_keys = tabs[0]->n_keys;
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; ++i) {
+        if (tabs[i]->n_keys != n_keys) { s2_set_error("replicas differ in key count (%llu vs %llu)", (unsigned long long)tabs[i]->n_keys, (unsigned long long)n_keys); return -1; }
+        if (check_col(tabs[i], col)) return -1;
+        devs[i] = tabs[i]->ctx->device;
+    }
+    if (n_keys == 0) return 0;
+    for (int i = 0; i < n; ++i) if (s2_table_counts_gather_dev(tabs[i], col, tabs[i]->scratch)) return -1;
+    std::vector<ncclComm_t> comms(n);
+    CKNCCL(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    CKNCCL(g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(devs[i]));
+        CKNCCL(g_nccl.AllReduce(tabs[i]->scratch, tabs[i]->scratch, n_keys, ncclUint32, ncclSum, comms[i], tabs[i]->ctx->lanes[0].stream));
+    }
+    CKNCCL(g_nccl.GroupEnd());
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(devs[i]));
+        CK(cudaStreamSynchronize(tabs[i]->ctx->lanes[0].stream));
+    }
+    for (int i = 0; i < n; ++i) g_nccl.CommDestroy(comms[i]);
+    for (int i = 0; i < n; ++i) if (s2_table_counts_scatter_dev(tabs[i], col, tabs[i]->scratch)) return -1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // count scan
 // ------------------------------------------------------------------------------------------------
 static int fetch_stats(s2_ctx *c, cudaStream_t st, s2_scan_stats *out)
@@ -462,6 +537,7 @@ extern "C" int s2_scan_count(s2_ctx *c, s2_table *t, const void *bases, uint64_t
                 if (!l) { s2_set_error("s2_scan_count: no lane available"); return -1; }
                 if (lane_retire(c, *l)) return -1;
             }
+            if (lane_buffers(c, *l, false)) return -1;
             CK(cudaMemcpyAsync(l->d_buf, src + off, take, cudaMemcpyHostToDevice, l->stream));
             CK(cudaEventRecord(l->k0, l->stream));
             s2_launch_scan_count(l->d_buf, take, t->v, col, c->d_stats, c->grid_count, l->stream);
@@ -534,19 +610,22 @@ extern "C" uint8_t *s2_batch_acquire(s2_ctx *c, uint64_t *capacity)
     if (cudaSetDevice(c->device) != cudaSuccess) { s2_set_error("cudaSetDevice failed"); return nullptr; }
     if (capacity) *capacity = c->batch_bytes;
     Lane *pick = nullptr;
-    for (auto &l : c->lanes) if (l.state == LANE_FREE) { pick = &l; break; }
+    for (auto &l : c->lanes) if (l.state == LANE_FREE && l.h_buf) { pick = &l; break; }
+    if (!pick) for (auto &l : c->lanes) if (l.state == LANE_FREE) { pick = &l; break; }
     if (!pick) {
         for (auto &l : c->lanes)
             if (l.state == LANE_INFLIGHT && (!pick || l.seq < pick->seq)) pick = &l;
         if (!pick) { s2_set_error("s2_batch_acquire: every lane is held by a caller (n_lanes=%d)", c->n_lanes); return nullptr; }
         if (lane_retire(c, *pick)) return nullptr;
     }
+    if (lane_buffers(c, *pick, true)) return nullptr;
     pick->state = LANE_HELD;
     return pick->h_buf;
 }
 
 static Lane *find_lane(s2_ctx *c, const uint8_t *buf)
 {
+    if (!buf) return nullptr;
     for (auto &l : c->lanes) if (l.h_buf == buf) return &l;
     return nullptr;
 }

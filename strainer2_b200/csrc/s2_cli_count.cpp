@@ -4,7 +4,7 @@
 // s2_batch_submit_count() on the GPU.  Host threads only inflate + parse files into pinned batches.
 //
 // Extra controls come from the environment so argv stays drop-in:
-//   S2_DEVICE (0)  S2_THREADS (min(nproc,16) reader threads)  S2_BATCH_MB (64)  S2_LOAD (0.5)
+//   S2_GPUS (1: GPUs to shard the input files over)  S2_DEVICE (0)  S2_THREADS (min(nproc,16) reader threads)  S2_BATCH_MB (16)  S2_LOAD (0.5)
 //   S2_STATS=1 prints a one-line throughput summary on stderr.
 #include "../../include/strainer2_b200.h"
 #include "s2_internal.h"
@@ -12,6 +12,7 @@
 #include <getopt.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -128,13 +129,24 @@ int s2_default_reader_threads()
 bool s2_scan_work_items(s2_ctx *ctx, s2_table *table, s2_exotic *exotic, std::vector<S2WorkItem> &work, int n_threads,
                         FILE *progress, std::string &open_error, uint64_t *bases_out, uint64_t *lookups_out)
 {
+    std::vector<s2_ctx *> c(1, ctx);
+    std::vector<s2_table *> t(1, table);
+    return s2_scan_work_items_multi(c, t, exotic, work, n_threads, progress, open_error, bases_out, lookups_out);
+}
+
+// same with one (context, table replica) per GPU: reader thread i feeds GPU i % n_gpus, files are still
+// taken from one queue in list order, so any GPU may end up scanning any file (file sharding)
+bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table *> &tables, s2_exotic *exotic,
+                              std::vector<S2WorkItem> &work, int n_threads, FILE *progress, std::string &open_error,
+                              uint64_t *bases_out, uint64_t *lookups_out)
+{
     std::mutex mu;                      // guards next / progress / stderr ordering
     size_t next = 0;
     std::atomic<bool> stop(false);
     std::atomic<uint64_t> total_bases(0), total_lookups(0);
 
-    auto reader = [&]() {
-        BatchWriter w{ ctx, table };
+    auto reader = [&](int tid) {
+        BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
         for (;;) {
             s2_reader *r = nullptr; int col = 0;
             {
@@ -180,8 +192,8 @@ bool s2_scan_work_items(s2_ctx *ctx, s2_table *table, s2_exotic *exotic, std::ve
         }
     };
     std::vector<std::thread> pool;
-    for (int i = 1; i < n_threads; ++i) pool.emplace_back(reader);
-    reader();
+    for (int i = 1; i < n_threads; ++i) pool.emplace_back(reader, i);
+    reader(0);
     for (auto &t : pool) t.join();
 
     if (bases_out) *bases_out = total_bases.load();
@@ -221,9 +233,18 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     };
 
     const auto t_start = std::chrono::steady_clock::now();
-    const int n_threads = s2_default_reader_threads();
-    s2_ctx *ctx = s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 64) << 20, n_threads + 2);
-    if (!ctx) return fail(s2_last_error());
+    // S2_GPUS > 1: one context + table replica per GPU, files sharded over them, ONE all-reduce at the end
+    int n_gpus = s2_env_int("S2_GPUS", 1);
+    if (n_gpus < 1) n_gpus = 1;
+    if (n_gpus > 1 && n_gpus > s2_device_count()) return fail("S2_GPUS exceeds the number of visible GPUs");
+    const int n_threads = std::max(s2_default_reader_threads(), n_gpus);
+    std::vector<s2_ctx *> ctxs(n_gpus, nullptr);
+    std::vector<s2_table *> tables(n_gpus, nullptr);
+    for (int g = 0; g < n_gpus; ++g) {
+        ctxs[g] = s2_init(s2_env_int("S2_DEVICE", 0) + g, s2_env_u64("S2_BATCH_MB", 16) << 20, (n_threads + n_gpus - 1) / n_gpus + 2);
+        if (!ctxs[g]) return fail(s2_last_error());
+    }
+    s2_ctx *ctx = ctxs[0];
 
     // ---- table from -r (GEN_hash_sequences_set_count_vec, default 1 / increment 1 / column 0 / 4 wide)
     std::vector<uint8_t> flat;
@@ -235,8 +256,18 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     // nullptr (the normal case) means no such window exists and the host never looks at a window again
     s2_exotic *exotic = s2_exotic_build(flat.data(), flat.size(), 4);
     const char *load_env = getenv("S2_LOAD");
-    s2_table *table = s2_table_build(ctx, flat.data(), flat.size(), 4, load_env ? atof(load_env) : 0.0, 0);
-    if (!table) return fail(s2_last_error());
+    {
+        std::vector<std::thread> builders;
+        std::vector<std::string> errs(n_gpus);
+        for (int g = 0; g < n_gpus; ++g)
+            builders.emplace_back([&, g]() {
+                tables[g] = s2_table_build(ctxs[g], flat.data(), flat.size(), 4, load_env ? atof(load_env) : 0.0, 0);
+                if (!tables[g]) errs[g] = s2_last_error();
+            });
+        for (auto &b : builders) b.join();
+        for (int g = 0; g < n_gpus; ++g) if (!tables[g]) return fail(errs[g].c_str());
+    }
+    s2_table *table = tables[0];
     std::vector<uint8_t>().swap(flat);
     const auto t_built = std::chrono::steady_clock::now();
 
@@ -250,11 +281,17 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
 
     std::string open_error;
     uint64_t total_bases = 0, total_lookups = 0;
-    const bool pool_ok = s2_scan_work_items(ctx, table, exotic, work, n_threads, progress, open_error, &total_bases, &total_lookups);
+    const bool pool_ok = s2_scan_work_items_multi(ctxs, tables, exotic, work, n_threads, progress, open_error, &total_bases, &total_lookups);
     s2_scan_stats st = {};
-    if (s2_sync(ctx, &st)) return fail(s2_last_error());
+    for (int g = 0; g < n_gpus; ++g) {
+        s2_scan_stats sg = {};
+        if (s2_sync(ctxs[g], &sg)) return fail(s2_last_error());
+        st.hits += sg.hits; st.valid_windows += sg.valid_windows;
+    }
     if (!open_error.empty()) return fail(open_error.c_str());
     if (!pool_ok) return fail(s2_last_error());
+    for (int k = 1; k < 4 && n_gpus > 1; ++k)                          // sum the replicas' counters over NVLink
+        if (s2_tables_allreduce(tables.data(), n_gpus, k)) return fail(s2_last_error());
     const auto t_scanned = std::chrono::steady_clock::now();
 
     // ---- print_hash_counts: rows in the reference table's slot order
@@ -307,17 +344,16 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     if (s2_env_int("S2_STATS", 0)) {
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         double kms = 0; uint64_t kl = 0;
-        s2_kernel_time(ctx, &kms, &kl, 0);
-        fprintf(stderr, "[s2] keys=%llu build=%.3fs scan=%.3fs print=%.3fs bases=%llu lookups=%llu hits=%llu "
+        for (int g = 0; g < n_gpus; ++g) { double m = 0; uint64_t l = 0; s2_kernel_time(ctxs[g], &m, &l, 0); kms += m; kl += l; }
+        fprintf(stderr, "[s2] gpus=%d keys=%llu build=%.3fs scan=%.3fs print=%.3fs bases=%llu lookups=%llu hits=%llu "
                         "kernel_ms=%.3f launches=%llu scan_Gbases_per_s=%.3f\n",
-                (unsigned long long)n, sec(t_start, t_built), sec(t_built, t_scanned), sec(t_scanned, t_done),
+                n_gpus, (unsigned long long)n, sec(t_start, t_built), sec(t_built, t_scanned), sec(t_scanned, t_done),
                 (unsigned long long)total_bases, (unsigned long long)total_lookups,
                 (unsigned long long)st.hits, kms, (unsigned long long)kl,
                 total_bases / 1e9 / std::max(1e-9, sec(t_built, t_scanned)));
     }
     s2_exotic_free(exotic);
-    s2_table_free(table);
-    s2_shutdown(ctx);
+    for (int g = 0; g < n_gpus; ++g) { s2_table_free(tables[g]); s2_shutdown(ctxs[g]); }
     if (progress) fclose(progress);
     return 0;
 }

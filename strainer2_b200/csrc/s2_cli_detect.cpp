@@ -387,7 +387,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     Detect d;
     d.batch_bytes = s2_env_u64("S2_DETECT_BATCH_MB", 32) << 20;
     const int n_threads = s2_default_reader_threads();
-    d.ctx = background_file ? s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 64) << 20, n_threads + 2)
+    d.ctx = background_file ? s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 16) << 20, n_threads + 2)
                             : s2_init(s2_env_int("S2_DEVICE", 0), 8u << 20, 2);
     if (!d.ctx) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
 

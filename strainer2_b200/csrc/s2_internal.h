@@ -31,4 +31,7 @@ struct S2WorkItem { std::string path; int col; bool skip; };
 int  s2_read_list(const char *list_file, int col, const char *skip_file, std::vector<S2WorkItem> &out);
 bool s2_scan_work_items(s2_ctx *ctx, s2_table *table, s2_exotic *exotic, std::vector<S2WorkItem> &work, int n_threads,
                         FILE *progress, std::string &open_error, uint64_t *bases_out, uint64_t *lookups_out);
+bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table *> &tables, s2_exotic *exotic,
+                              std::vector<S2WorkItem> &work, int n_threads, FILE *progress, std::string &open_error,
+                              uint64_t *bases_out, uint64_t *lookups_out);
 int  s2_default_reader_threads();

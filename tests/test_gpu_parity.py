@@ -342,3 +342,21 @@ def test_iupac_bytes_are_hashed_as_strings_like_the_reference(s2, golden_dir, tm
     assert p.returncode == 0, p.stderr
     assert ou.gunzip(out) == ou.gunzip(os.path.join(d, "expected_detect.hits.txt.gz"))
     assert p.stdout == open(os.path.join(d, "expected_detect.stdout"), "rb").read()
+
+
+def test_executable_shards_files_over_two_gpus_with_one_allreduce(s2, golden_dir, tmp_path):
+    """S2_GPUS=2: replicas on two GPUs, files dealt to both, counters summed by ncclAllReduce; bytes unchanged"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = os.path.join(golden_dir, "count_edge")
+    p = s2.run_kmer_scrub_count(["-r", "ref.fa.gz", "-A", "listA.txt", "-B", "listB.txt", "-C", "listC.txt"], cwd=d,
+                                env={"S2_GPUS": "2", "S2_THREADS": "4", "S2_BATCH_MB": "1"})
+    assert p.returncode == 0, p.stderr
+    assert p.stdout == open(os.path.join(d, "expected_ABC.tsv"), "rb").read()
+    assert p.stderr == open(os.path.join(d, "expected_ABC.stderr"), "rb").read()
+    args = _write_inputs(s2, str(tmp_path), 400_000, 3, 2, 30_000)
+    one = s2.run_kmer_scrub_count(args, env={"S2_BATCH_MB": "2"})
+    two = s2.run_kmer_scrub_count(args, env={"S2_BATCH_MB": "2", "S2_GPUS": "2"})
+    assert one.returncode == 0 and two.returncode == 0, two.stderr
+    assert one.stdout == two.stdout
