@@ -237,6 +237,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     int n_gpus = s2_env_int("S2_GPUS", 1);
     if (n_gpus < 1) n_gpus = 1;
     if (n_gpus > 1 && n_gpus > s2_device_count()) return fail("S2_GPUS exceeds the number of visible GPUs");
+    if (n_gpus > 1) setenv("NCCL_DEBUG_FILE", "/dev/null", 0);        // stdout is the count table: keep NCCL's banner out of it
     const int n_threads = std::max(s2_default_reader_threads(), n_gpus);
     std::vector<s2_ctx *> ctxs(n_gpus, nullptr);
     std::vector<s2_table *> tables(n_gpus, nullptr);
@@ -244,7 +245,6 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
         ctxs[g] = s2_init(s2_env_int("S2_DEVICE", 0) + g, s2_env_u64("S2_BATCH_MB", 16) << 20, (n_threads + n_gpus - 1) / n_gpus + 2);
         if (!ctxs[g]) return fail(s2_last_error());
     }
-    s2_ctx *ctx = ctxs[0];
 
     // ---- table from -r (GEN_hash_sequences_set_count_vec, default 1 / increment 1 / column 0 / 4 wide)
     std::vector<uint8_t> flat;
