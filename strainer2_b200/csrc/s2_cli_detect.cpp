@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,6 +59,8 @@ struct Detect {
     uint64_t batch_bytes = 32ull << 20;
     std::string out;                    // pending text for gzout
     std::unordered_set<uint64_t> informative;   // device keys currently labelled INFORMATIVE
+    double t_read = 0, t_gpu = 0, t_emit = 0;   // S2_STATS
+    uint64_t n_bases = 0, n_out_lines = 0;
 
     void flush_out(bool force)
     {
@@ -208,7 +211,10 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
     std::vector<uint64_t> pos;
     char kbuf[S2_K + 1];
 
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     while (!eof && rc == 0) {
+        const auto tA = now();
         // ---- phase A: run the pairing loop ahead, collecting records >= 31 into one batch -------------
         batch.clear(); rec_off.assign(1, 0); iters.clear();
         auto add = [&](const char *seq, uint64_t len) -> int32_t {
@@ -234,6 +240,9 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
             if (it.fatal) { eof = true; break; }
         } while (batch.size() < d.batch_bytes);
         // ---- phase B: pass 1 of every collected read on the GPU -----------------------------------
+        const auto tB = now();
+        d.t_read += secs(tA, tB);
+        d.n_bases += batch.size();
         const uint32_t n_rec = (uint32_t)rec_off.size() - 1;
         hits.assign(n_rec + 1, 0); inf.assign(n_rec + 1, 0);
         uint64_t n_inf = 0;
@@ -258,6 +267,8 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
                 s2_exotic_pass1(d.exotic, (const char *)batch.data() + rec_off[r], rec_off[r + 1] - rec_off[r] - 1, &xh, &xi);
                 hits[r] += (uint32_t)xh; inf[r] += (uint32_t)xi;
             }
+        const auto tC = now();
+        d.t_gpu += secs(tB, tC);
         // informative windows per record: pos is ascending, so each record owns a contiguous range
         std::vector<uint64_t> first(n_rec + 1, 0);
         {
@@ -325,6 +336,7 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
             }
             d.flush_out(false);
         }
+        d.t_emit += secs(tC, now());
     }
     if (rc == 0) {
         char foot[4][512];
@@ -449,6 +461,12 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     // on a fatal error the reference exit()s with the gz stream unfinished; we close it either way
     gzclose(d.gzout);
     fflush(stdout);
+    if (s2_env_int("S2_STATS", 0)) {
+        double kms = 0; uint64_t kl = 0;
+        s2_kernel_time(d.ctx, &kms, &kl, 0);
+        fprintf(stderr, "[s2 detect] keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu\n",
+                d.genome_kmers, d.genome_informative, (unsigned long long)d.n_bases, d.t_read, d.t_gpu, d.t_emit, kms, (unsigned long long)kl);
+    }
     s2_exotic_free(d.exotic);
     s2_table_free(d.table);
     s2_shutdown(d.ctx);

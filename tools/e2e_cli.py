@@ -78,6 +78,16 @@ def main():
             t1 = time.time()
             p = subprocess.run([exe] + a, cwd=tmp, env=e, stdout=open(os.path.join(tmp, name + ".tsv"), "wb"), stderr=subprocess.PIPE)
             print(f"{name} threads={th or 'default'} rc={p.returncode} wall={time.time() - t1:.2f}s {p.stderr.decode().strip()}", flush=True)
+    # strain_detect on the same metagenomes: informative = every 100th k-mer of the strain's first contig
+    c0 = bytes(strain[0]).replace(b"N", b"A")
+    with open(os.path.join(tmp, "inf.txt"), "wb") as f:
+        for i in range(0, len(c0) - 31, 100):
+            f.write(c0[i:i + 31] + b"\n")
+    open(os.path.join(tmp, "batch.txt"), "w").write("".join(f"SE\t{b}\n" for b in B[:2]) + (f"PE\t{B[2]}\t{B[3]}\n" if len(B) >= 4 else ""))
+    dexe = os.path.join(ROOT, "strainer2_b200", "bin", "strain_detect")
+    t1 = time.time()
+    p = subprocess.run([dexe, "-r", "strain.fa", "-a", "inf.txt", "-B", "batch.txt", "-o", "hits.gz"], cwd=tmp, env=env, capture_output=True)
+    print(f"strain_detect rc={p.returncode} wall={time.time() - t1:.2f}s {p.stderr.decode().strip()[-400:]}", flush=True)
     ref = os.path.join(ROOT, "oracle", "_ref", "kmer_scrub_count")
     if args.ref_genomes and os.path.exists(ref):
         open(os.path.join(tmp, "A_small.txt"), "w").write("".join(a + "\n" for a in A[:args.ref_genomes]))
