@@ -84,7 +84,20 @@ struct s2_ctx {
     // enqueue-only scans on lane 0 (device-resident batches): one event pair per launch, harvested at sync
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
     cudaEvent_t user_ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    // grow-only scratch of s2_scan_detect (no cudaMalloc per call)
+    struct Scratch { void *p = nullptr; size_t cap = 0; } det[6];
 };
+
+static int scratch_reserve(s2_ctx::Scratch &s, size_t bytes)
+{
+    if (bytes <= s.cap) return 0;
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr; s.cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&s.p, want));
+    s.cap = want;
+    return 0;
+}
 
 extern "C" int s2_device_count(void)
 {
@@ -146,6 +159,7 @@ extern "C" void s2_shutdown(s2_ctx *c)
     for (auto &e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : c->user_ev) if (e) cudaEventDestroy(e);
+    for (auto &s : c->det) if (s.p) cudaFree(s.p);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     delete c;
@@ -684,20 +698,18 @@ extern "C" int s2_scan_detect(s2_ctx *c, s2_table *t, const void *bases, uint64_
     if (n_rec == 0 || n_bytes == 0) { if (stats) { stats->hits = 0; stats->valid_windows = 0; } return 0; }
 
     const uint8_t *d_bases = (const uint8_t *)bases;
-    uint8_t *tmp = nullptr;
     if (!on_device) {
-        CK(cudaMalloc((void **)&tmp, n_bytes + 64));
-        CK(cudaMemcpyAsync(tmp, bases, n_bytes, cudaMemcpyHostToDevice, st));
-        d_bases = tmp;
+        if (scratch_reserve(c->det[0], n_bytes + 64)) return -1;
+        CK(cudaMemcpyAsync(c->det[0].p, bases, n_bytes, cudaMemcpyHostToDevice, st));
+        d_bases = (const uint8_t *)c->det[0].p;
     } else if (((uintptr_t)bases & 15) != 0) { s2_set_error("device batch must be 16-byte aligned"); return -1; }
 
-    uint64_t *d_off = nullptr, *d_pos = nullptr; uint32_t *d_hits = nullptr, *d_inf = nullptr;
-    unsigned long long *d_cnt = nullptr;
-    CK(cudaMalloc((void **)&d_off, (n_rec + 1ull) * sizeof(uint64_t)));
-    CK(cudaMalloc((void **)&d_hits, n_rec * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&d_inf, n_rec * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&d_pos, (inf_cap + 1) * sizeof(uint64_t)));
-    CK(cudaMalloc((void **)&d_cnt, sizeof(unsigned long long)));
+    if (scratch_reserve(c->det[1], (n_rec + 1ull) * sizeof(uint64_t)) || scratch_reserve(c->det[2], n_rec * sizeof(uint32_t)) ||
+        scratch_reserve(c->det[3], n_rec * sizeof(uint32_t)) || scratch_reserve(c->det[4], (inf_cap + 1) * sizeof(uint64_t)) ||
+        scratch_reserve(c->det[5], sizeof(unsigned long long))) return -1;
+    uint64_t *d_off = (uint64_t *)c->det[1].p, *d_pos = (uint64_t *)c->det[4].p;
+    uint32_t *d_hits = (uint32_t *)c->det[2].p, *d_inf = (uint32_t *)c->det[3].p;
+    unsigned long long *d_cnt = (unsigned long long *)c->det[5].p;
     CK(cudaMemcpyAsync(d_off, rec_off, (n_rec + 1ull) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_hits, 0, n_rec * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d_inf, 0, n_rec * sizeof(uint32_t), st));
@@ -724,8 +736,6 @@ extern "C" int s2_scan_detect(s2_ctx *c, s2_table *t, const void *bases, uint64_
         std::sort(inf_pos, inf_pos + have);          // the kernel appends in arbitrary order
     }
     if (n_inf) *n_inf = cnt;
-    cudaFree(d_off); cudaFree(d_hits); cudaFree(d_inf); cudaFree(d_pos); cudaFree(d_cnt);
-    if (tmp) cudaFree(tmp);
     return fetch_stats(c, st, stats);
 }
 

@@ -20,7 +20,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -57,23 +61,30 @@ struct Detect {
     gzFile gzout = nullptr;
     unsigned genome_kmers = 0, genome_informative = 0;
     uint64_t batch_bytes = 32ull << 20;
-    std::string out;                    // pending text for gzout
     std::unordered_set<uint64_t> informative;   // device keys currently labelled INFORMATIVE
-    double t_read = 0, t_gpu = 0, t_emit = 0;   // S2_STATS
-    uint64_t n_bases = 0, n_out_lines = 0;
+    std::mutex stat_mu;
+    double t_read = 0, t_gpu = 0, t_emit = 0;   // S2_STATS (summed over worker threads)
+    uint64_t n_bases = 0;
 
-    void flush_out(bool force)
+    void write_out(const std::string &out)
     {
-        if (out.size() >= (1u << 20) || (force && !out.empty())) {
-            size_t off = 0;
-            while (off < out.size()) {
-                const unsigned n = (unsigned)std::min<size_t>(out.size() - off, 1u << 30);
-                gzwrite(gzout, out.data() + off, n);
-                off += n;
-            }
-            out.clear();
+        size_t off = 0;
+        while (off < out.size()) {
+            const unsigned n = (unsigned)std::min<size_t>(out.size() - off, 1u << 30);
+            gzwrite(gzout, out.data() + off, n);
+            off += n;
         }
     }
+};
+
+// one batch line (or the -b/-c pair): processed by a worker thread, written to the gzip stream in order
+struct Job {
+    std::string f1, f2;
+    bool has_f2 = false;
+    int pe = 0;
+    std::string out, err;
+    int rc = 0;
+    bool done = false;
 };
 
 // hash_scrubbed_kmers (src/strain_detect.c:668-726): label the listed k-mers INFORMATIVE.
@@ -179,17 +190,24 @@ static int background_filter(Detect &d, const char *background_file, unsigned nu
 struct Rec { uint64_t off; uint32_t len; };
 
 // quantify_hits_PE (src/strain_detect.c:387-663).  Returns 0 or EXIT_FAILURE (message already printed).
-static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
+static int quantify_hits(Detect &d, Job &job)
 {
+    const char *pe1 = job.f1.c_str();
+    const char *pe2 = job.has_f2 ? job.f2.c_str() : nullptr;
+    const int is_pe = job.pe;
+    char msg[1024];
+    double t_read = 0, t_gpu = 0, t_emit = 0; uint64_t n_bases = 0;
     s2_reader *r1 = s2_reader_open(pe1), *r2 = nullptr;
     if (!r1) {
-        fprintf(stderr, "could not read file (read1) %s in quantify_hits_PE() (error: %s)\n", pe1, strerror(errno));
+        snprintf(msg, sizeof msg, "could not read file (read1) %s in quantify_hits_PE() (error: %s)\n", pe1, strerror(errno));
+        job.err = msg;
         return EXIT_FAILURE;
     }
     if (is_pe == IS_PAIRED_END) {
         r2 = s2_reader_open(pe2);
         if (!r2) {
-            fprintf(stderr, "could not read file (read2) is_PE %s in quantify_hits_PE() (error: %s)\n", pe2, strerror(errno));
+            snprintf(msg, sizeof msg, "could not read file (read2) is_PE %s in quantify_hits_PE() (error: %s)\n", pe2, strerror(errno));
+            job.err = msg;
             s2_reader_close(r1);
             return EXIT_FAILURE;
         }
@@ -241,8 +259,8 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
         } while (batch.size() < d.batch_bytes);
         // ---- phase B: pass 1 of every collected read on the GPU -----------------------------------
         const auto tB = now();
-        d.t_read += secs(tA, tB);
-        d.n_bases += batch.size();
+        t_read += secs(tA, tB);
+        n_bases += batch.size();
         const uint32_t n_rec = (uint32_t)rec_off.size() - 1;
         hits.assign(n_rec + 1, 0); inf.assign(n_rec + 1, 0);
         uint64_t n_inf = 0;
@@ -252,7 +270,7 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
                 pos.resize(cap);
                 if (s2_scan_detect(d.ctx, d.table, batch.data(), batch.size(), rec_off.data(), n_rec, hits.data(), inf.data(),
                                    pos.data(), cap, &n_inf, 0, nullptr)) {
-                    fprintf(stderr, "%s\n", s2_last_error());
+                    job.err = std::string(s2_last_error()) + "\n";
                     rc = EXIT_FAILURE;
                     break;
                 }
@@ -268,7 +286,7 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
                 hits[r] += (uint32_t)xh; inf[r] += (uint32_t)xi;
             }
         const auto tC = now();
-        d.t_gpu += secs(tB, tC);
+        t_gpu += secs(tB, tC);
         // informative windows per record: pos is ascending, so each record owns a contiguous range
         std::vector<uint64_t> first(n_rec + 1, 0);
         {
@@ -301,11 +319,11 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
         std::vector<std::string> pe2_kmers;
         auto emit = [&](const char *kmer) {
             char head[96];
-            d.out += pe1;
+            job.out += pe1;
             const int n = snprintf(head, sizeof head, "\t%d\t%d\t%d\t%d\t", h1, i1, h2, i2);      // :567, :608
-            d.out.append(head, n);
-            d.out += kmer;
-            d.out += '\n';
+            job.out.append(head, n);
+            job.out += kmer;
+            job.out += '\n';
         };
         // ---- phase C: replay the loop in order with the counts filled in ---------------------------------
         for (const Iter &it : iters) {
@@ -318,8 +336,9 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
                 if (i1) record_kmers(it.r1, copy_kmers);
             }
             if (it.fatal) {
-                fprintf(stderr, "reached end of PE2 (%s) before end of PE1 (%s), check that file names are correct\n",
-                        pe2 ? pe2 : "(null)", pe1);
+                snprintf(msg, sizeof msg, "reached end of PE2 (%s) before end of PE1 (%s), check that file names are correct\n",
+                         pe2 ? pe2 : "(null)", pe1);
+                job.err = msg;
                 rc = EXIT_FAILURE;
                 break;
             }
@@ -334,9 +353,8 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
                     for (const std::string &k : pe2_kmers) emit(k.c_str());
                 }
             }
-            d.flush_out(false);
         }
-        d.t_emit += secs(tC, now());
+        t_emit += secs(tC, now());
     }
     if (rc == 0) {
         char foot[4][512];
@@ -344,9 +362,12 @@ static int quantify_hits(Detect &d, const char *pe1, const char *pe2, int is_pe)
         snprintf(foot[1], sizeof foot[1], "#%s\ttotal_reads_evaluated\t%lld\n", pe1, (long long)reads);
         snprintf(foot[2], sizeof foot[2], "#%s\ttotal_genome_kmers\t%lld\n", pe1, (long long)d.genome_kmers);
         snprintf(foot[3], sizeof foot[3], "#%s\ttotal_genome_informative_kmers\t%lld\n", pe1, (long long)d.genome_informative);
-        for (auto &f : foot) d.out += f;
+        for (auto &f : foot) job.out += f;
     }
-    d.flush_out(true);
+    {
+        std::lock_guard<std::mutex> g(d.stat_mu);
+        d.t_read += t_read; d.t_gpu += t_gpu; d.t_emit += t_emit; d.n_bases += n_bases;
+    }
     if (r2 && r2 != r1) s2_reader_close(r2);
     s2_reader_close(r1);
     return rc;
@@ -429,7 +450,9 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
         fprintf(stderr, "could not open *gzout file outfile %s in quantify_hits_all_files()\n", kmer_outfile);
         return EXIT_FAILURE;
     }
-    int rc = 0;
+    // quantify_hits_all_files: one job per usable batch line, in order.  The stdout chatter about unusable
+    // lines depends only on the line text, so it is printed now, in line order.
+    std::vector<Job> jobs;
     if (B_file) {
         FILE *fp = fopen(B_file, "r");
         if (!fp) {
@@ -437,7 +460,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
             return EXIT_FAILURE;
         }
         char *line = nullptr; size_t cap = 0;
-        while (rc == 0 && getline(&line, &cap, fp) != -1) {
+        while (getline(&line, &cap, fp) != -1) {
             char *pos = strchr(line, '\n');
             if (pos) *pos = '\0';
             char *token = strtok(line, "\t");
@@ -445,18 +468,53 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
             if (pe == UNKNOWN_FILE_TYPE) { printf("unknown file type skipping line (%s)\n", token ? token : "(null)"); continue; }
             char *file1 = strtok(nullptr, "\t");
             if (!file1) { printf("ERROR: no first file specified for %s\n", line); continue; }
+            Job j; j.pe = pe; j.f1 = file1;
             if (pe == IS_PAIRED_END) {
                 char *file2 = strtok(nullptr, "\t");
                 if (!file2) { printf("ERROR: no second file specified for PE: %s\n", line); continue; }
-                rc = quantify_hits(d, file1, file2, pe);
-            } else {
-                rc = quantify_hits(d, file1, nullptr, pe);
+                j.f2 = file2; j.has_f2 = true;
             }
+            jobs.push_back(std::move(j));
         }
         free(line);
         fclose(fp);
     } else {
-        rc = quantify_hits(d, b_file, b_file2, is_paired_end);
+        Job j; j.pe = is_paired_end; j.f1 = b_file;
+        if (b_file2) { j.f2 = b_file2; j.has_f2 = true; }
+        jobs.push_back(std::move(j));
+    }
+    fflush(stdout);
+
+    // worker threads read + scan files concurrently; this thread writes the finished blocks in order
+    int rc = 0;
+    {
+        std::mutex mu; std::condition_variable cv;
+        std::atomic<size_t> next(0);
+        std::atomic<bool> stop(false);
+        auto worker = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= jobs.size() || stop.load()) break;
+                jobs[i].rc = quantify_hits(d, jobs[i]);
+                { std::lock_guard<std::mutex> g(mu); jobs[i].done = true; }
+                cv.notify_all();
+            }
+        };
+        const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(jobs.size(), (size_t)s2_default_reader_threads()));
+        std::vector<std::thread> pool;
+        for (int w = 0; w < n_workers; ++w) pool.emplace_back(worker);
+        for (size_t i = 0; i < jobs.size(); ++i) {
+            { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&]() { return jobs[i].done; }); }
+            d.write_out(jobs[i].out);
+            std::string().swap(jobs[i].out);
+            if (jobs[i].rc) {                       // the reference exit()s here: later lines are never processed
+                fputs(jobs[i].err.c_str(), stderr);
+                rc = jobs[i].rc;
+                stop.store(true);
+                break;
+            }
+        }
+        for (auto &t : pool) t.join();
     }
     // on a fatal error the reference exit()s with the gz stream unfinished; we close it either way
     gzclose(d.gzout);
