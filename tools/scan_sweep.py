@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--variants", default="")
     ap.add_argument("--genomes", type=int, default=32)
     ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--union-strains", type=int, default=0,
+                    help="also build ONE table from this many 5 Mb strains (config #5 shape: HBM-resident fingerprints)")
     args = ap.parse_args()
     import torch
     import strainer2_b200 as s2
@@ -44,10 +46,21 @@ def main():
     rel = np.concatenate([synth.contigs_to_flat([synth.mutate(c, 0.01, rng) for c in strain]) for _ in range(8)])
     work["relatives_1pct"] = (torch.from_numpy(rel).cuda(), sum(c.size - 30 for c in strain) * 8)
 
+    tables = {"single": table}
+    if args.union_strains:
+        rng_u = synth.rng_for(5, 0)
+        flat_u = np.concatenate([synth.contigs_to_flat(synth.genome(rng_u, 5_000_000, 40)) for _ in range(args.union_strains - 1)]
+                                + [synth.contigs_to_flat(strain)])
+        tu = s2.StrainTable(ctx, flat_u, n_cols=2, load_factor=args.load)
+        print(f"# union table: {tu.n_keys} keys, {tu.n_slots} slots, probe bytes {tu.probe_bytes}, HBM bytes {tu.hbm_bytes}", flush=True)
+        tables["union"] = tu
+        del flat_u
     n_var = lib.s2_tune_scan_variant(ctx.h, -1)
     sel = [int(v) for v in args.variants.split(",")] if args.variants else list(range(n_var))
     results = []
-    for wname, (dev, lookups) in work.items():
+    for tname, table in tables.items():
+      for wname0, (dev, lookups) in work.items():
+        wname = wname0 if tname == "single" else tname + ":" + wname0
         ref_hits = None
         for v in sel:
             assert lib.s2_tune_scan_variant(ctx.h, v) > 0
@@ -73,7 +86,8 @@ def main():
                   f"{'ok' if ok else 'HITS DIFFER'}", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(results, open(os.path.join(ROOT, "gpurun_out", "scan_sweep.json"), "w"), indent=1)
-    table.free()
+    for t in tables.values():
+        t.free()
     ctx.close()
 
 
