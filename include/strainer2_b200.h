@@ -88,6 +88,9 @@ int         s2_tables_allreduce(s2_table **tabs, int n, int col);
 /* hash_scrubbed_kmers() labelling, src/strain_detect.c:687-717: mark canonical 62-bit k-mers as
  * INFORMATIVE.  found[i] (may be NULL) = 1 if kmers[i] is a key of the table. */
 int         s2_table_flag(s2_table *t, const uint64_t *kmers, uint64_t n, uint8_t *found);
+/* counter column `col` for arbitrary canonical k-mers (0 for keys the table does not hold): how the
+ * multi-strain batch reads one strain's rows out of the union table */
+int         s2_table_counts_by_key(s2_table *t, int col, const uint64_t *kmers, uint64_t n, uint32_t *host_out);
 /* background_filter() demotion, src/strain_detect.c:218-228: back to NON_INFORMATIVE */
 int         s2_table_unflag(s2_table *t, const uint64_t *kmers, uint64_t n);
 int         s2_table_lookup(s2_table *t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out);
@@ -177,6 +180,10 @@ void        s2_reader_close(s2_reader *r);
 /* whole programs, argv-compatible with the reference executables */
 int         s2_kmer_scrub_count_main(int argc, char **argv);   /* src/kmer_scrub_count.c:29-123 */
 int         s2_strain_detect_main(int argc, char **argv);      /* src/strain_detect.c:61-158    */
+/* many strains against the same -A/-B/-C lists in ONE pass over the inputs (union table); every output
+ * table is byte-identical to kmer_scrub_count run on that strain alone.  No reference counterpart:
+ * README.md:47 runs one process per strain. */
+int         s2_kmer_scrub_count_batch_main(int argc, char **argv);
 
 #ifdef __cplusplus
 }

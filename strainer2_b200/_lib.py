@@ -49,6 +49,7 @@ SIGNATURES = {
     "s2_table_counts_scatter_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "s2_tables_allreduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "s2_table_flag": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u8p]),
+    "s2_table_counts_by_key": (C.c_int, [C.c_void_p, C.c_int, c_u64p, C.c_uint64, c_u32p]),
     "s2_table_unflag": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64]),
     "s2_table_lookup": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u32p]),
     "s2_scan_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
@@ -80,6 +81,7 @@ SIGNATURES = {
     "s2_reader_close": (None, [C.c_void_p]),
     "s2_kmer_scrub_count_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "s2_strain_detect_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "s2_kmer_scrub_count_batch_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -353,3 +353,8 @@ def run_kmer_scrub_count(args, cwd=None, env=None, timeout=None):
 
 def run_strain_detect(args, cwd=None, env=None, timeout=None):
     return _run("strain_detect", args, cwd, env, timeout)
+
+
+def run_kmer_scrub_count_batch(args, cwd=None, env=None, timeout=None):
+    """many strains against the same lists in one pass (-R strains.txt -A -B [-C] -O outdir)"""
+    return _run("kmer_scrub_count_batch", args, cwd, env, timeout)

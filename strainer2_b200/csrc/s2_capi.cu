@@ -428,6 +428,25 @@ extern "C" int s2_table_flag(s2_table *t, const uint64_t *kmers, uint64_t n, uin
     return table_query(t, kmers, n, found, nullptr, true);
 }
 
+extern "C" int s2_table_counts_by_key(s2_table *t, int col, const uint64_t *kmers, uint64_t n, uint32_t *host_out)
+{
+    if (check_col(t, col)) return -1;
+    s2_ctx *c = t->ctx;
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    cudaStream_t st = c->lanes[0].stream;
+    uint64_t *d_k = nullptr; uint32_t *d_o = nullptr;
+    CK(cudaMalloc((void **)&d_k, n * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&d_o, n * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(d_k, kmers, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    s2_launch_counts_by_key(t->v, col, d_k, n, d_o, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_out, d_o, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_k); cudaFree(d_o);
+    return 0;
+}
+
 extern "C" int s2_table_unflag(s2_table *t, const uint64_t *kmers, uint64_t n)
 {
     return table_query(t, kmers, n, nullptr, nullptr, true, 0);

@@ -595,6 +595,17 @@ __global__ void s2_lookup_kernel(S2TableView t, const uint64_t *__restrict__ kme
     slot_out[i] = probe_exact(t, kmers[i] & S2_KMER_MASK, slot, key) ? slot : S2_NONE;
 }
 
+// counter of column `col` for each given canonical k-mer (0 when the key is absent): the multi-strain batch
+// reads a strain's rows out of the union table with this
+__global__ void s2_counts_by_key_kernel(S2TableView t, const uint32_t *__restrict__ col, const uint64_t *__restrict__ kmers,
+                                        uint64_t n, uint32_t *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t slot; uint64_t key;
+    out[i] = probe_exact(t, kmers[i] & S2_KMER_MASK, slot, key) ? col[slot] : 0u;
+}
+
 // standalone 2-bit pack: one 128-bit coalesced load per thread -> 32-bit word + 16-bit validity mask
 __global__ void s2_pack_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes,
                                uint32_t *__restrict__ words, uint16_t *__restrict__ masks)
@@ -640,6 +651,11 @@ void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uin
 void s2_launch_lookup(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out, cudaStream_t stream)
 {
     if (n) s2_lookup_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(t, kmers, n, slot_out);
+}
+
+void s2_launch_counts_by_key(const S2TableView &t, int col, const uint64_t *kmers, uint64_t n, uint32_t *out, cudaStream_t stream)
+{
+    if (n) s2_counts_by_key_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(t, t.counts + (uint64_t)col * t.n_slots, kmers, n, out);
 }
 
 void s2_launch_pack(const uint8_t *bases, uint64_t n_bytes, uint32_t *words, uint16_t *masks, cudaStream_t stream)

@@ -58,6 +58,7 @@ void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uin
                     cudaStream_t stream);
 void s2_launch_lookup(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out,
                       cudaStream_t stream);
+void s2_launch_counts_by_key(const S2TableView &t, int col, const uint64_t *kmers, uint64_t n, uint32_t *out, cudaStream_t stream);
 void s2_launch_pack(const uint8_t *bases, uint64_t n_bytes, uint32_t *words, uint16_t *masks,
                     cudaStream_t stream);
 void s2_launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream);

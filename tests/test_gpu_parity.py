@@ -360,3 +360,47 @@ def test_executable_shards_files_over_two_gpus_with_one_allreduce(s2, golden_dir
     two = s2.run_kmer_scrub_count(args, env={"S2_BATCH_MB": "2", "S2_GPUS": "2"})
     assert one.returncode == 0 and two.returncode == 0, two.stderr
     assert one.stdout == two.stdout
+
+
+def test_multi_strain_batch_equals_one_reference_run_per_strain(s2, tmp_path):
+    """BASELINE config #5, down-scaled: 5 strains (pairs share 10 % of their sequence), shared -A/-B lists, -C = all
+    strain genomes (self skipped per strain) + one outsider listed twice; ONE pass over the inputs.  Every
+    strain's table must be byte-identical to the oracle run on that strain alone."""
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    rng = synth.rng_for(5, 1)
+    shared = synth.random_bases(rng, 20_000)
+    strains = []
+    for i in range(5):
+        g = synth.genome(rng, 200_000, 4, n_runs=2)
+        if i % 2 == 0 or i == 1:
+            g[0][1000:21_000] = synth.mutate(shared, 0.002 * i, rng)
+        p = os.path.join(tmp, f"strain{i}.fa" + (".gz" if i % 2 else ""))
+        synth.write_fasta(p, g)
+        strains.append((p, g))
+    A = []
+    for i in range(3):
+        p = os.path.join(tmp, f"a{i}.fa")
+        synth.write_fasta(p, [synth.mutate(c, 0.01, rng) for c in strains[i][1]] if i < 2 else synth.genome(rng, 200_000, 3))
+        A.append(p)
+    clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for _, g in strains for c in g]
+    B = []
+    for i in range(2):
+        p = os.path.join(tmp, f"m{i}.fastq.gz")
+        synth.write_reads_fastq(p, synth.sample_reads(rng, clean + synth.genome(rng, 400_000, 2), 20_000, 150, sub_rate=0.004, n_rate=1e-4))
+        B.append(p)
+    open(os.path.join(tmp, "R.txt"), "w").write("".join(p + "\n" for p, _ in strains))
+    open(os.path.join(tmp, "A.txt"), "w").write("".join(p + "\n" for p in A))
+    open(os.path.join(tmp, "B.txt"), "w").write("".join(p + "\n" for p in B))
+    open(os.path.join(tmp, "C.txt"), "w").write("".join(p + "\n" for p, _ in strains) + A[0] + "\n" + strains[3][0] + "\n")
+    out = os.path.join(tmp, "out")
+    p = s2.run_kmer_scrub_count_batch(["-R", os.path.join(tmp, "R.txt"), "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"),
+                                       "-C", os.path.join(tmp, "C.txt"), "-O", out], env={"S2_BATCH_MB": "2"})
+    assert p.returncode == 0, p.stderr
+    for path, _ in strains:
+        o = ou.oracle_cli(["count", "-r", path, "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"), "-C", os.path.join(tmp, "C.txt")])
+        assert o.returncode == 0
+        got = open(os.path.join(out, os.path.basename(path) + ".scrub_kmer_counts"), "rb").read()
+        assert got == o.stdout, path
+        k, v = ou.parse_table(got)
+        assert v[:, 3].sum() > 0 and v[:, 2].sum() > 0
