@@ -7,7 +7,9 @@
 #include "s2_internal.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -506,7 +508,18 @@ extern "C" int s2_tables_allreduce(s2_table **tabs, int n, int col)
     if (n_keys == 0) return 0;
     for (int i = 0; i < n; ++i) if (s2_table_counts_gather_dev(tabs[i], col, tabs[i]->scratch)) return -1;
     std::vector<ncclComm_t> comms(n);
-    CKNCCL(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    {
+        // NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/WARN; stdout is the count table
+        // of the drop-in executables, so it is parked on /dev/null while the communicators are created
+        fflush(stdout);
+        const int saved = dup(1), nul = open("/dev/null", O_WRONLY);
+        if (saved >= 0 && nul >= 0) dup2(nul, 1);
+        const ncclResult_t r = g_nccl.CommInitAll(comms.data(), n, devs.data());
+        fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+        if (nul >= 0) close(nul);
+        CKNCCL(r);
+    }
     CKNCCL(g_nccl.GroupStart());
     for (int i = 0; i < n; ++i) {
         CK(cudaSetDevice(devs[i]));

@@ -237,7 +237,6 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     int n_gpus = s2_env_int("S2_GPUS", 1);
     if (n_gpus < 1) n_gpus = 1;
     if (n_gpus > 1 && n_gpus > s2_device_count()) return fail("S2_GPUS exceeds the number of visible GPUs");
-    if (n_gpus > 1) setenv("NCCL_DEBUG_FILE", "/dev/null", 0);        // stdout is the count table: keep NCCL's banner out of it
     const int n_threads = std::max(s2_default_reader_threads(), n_gpus);
     std::vector<s2_ctx *> ctxs(n_gpus, nullptr);
     std::vector<s2_table *> tables(n_gpus, nullptr);
