@@ -397,10 +397,13 @@ def test_multi_strain_batch_equals_one_reference_run_per_strain(s2, tmp_path):
     p = s2.run_kmer_scrub_count_batch(["-R", os.path.join(tmp, "R.txt"), "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"),
                                        "-C", os.path.join(tmp, "C.txt"), "-O", out], env={"S2_BATCH_MB": "2"})
     assert p.returncode == 0, p.stderr
+    drug_sums = []
     for path, _ in strains:
         o = ou.oracle_cli(["count", "-r", path, "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"), "-C", os.path.join(tmp, "C.txt")])
         assert o.returncode == 0
         got = open(os.path.join(out, os.path.basename(path) + ".scrub_kmer_counts"), "rb").read()
         assert got == o.stdout, path
         k, v = ou.parse_table(got)
-        assert v[:, 3].sum() > 0 and v[:, 2].sum() > 0
+        assert v[:, 2].sum() > 0
+        drug_sums.append(int(v[:, 3].sum()))
+    assert sum(1 for d in drug_sums if d > 0) >= 3          # the strains that share sequence see each other in -C
