@@ -66,6 +66,9 @@ struct Lane {
     uint8_t *h_buf = nullptr;          // pinned
     uint8_t *d_buf = nullptr;
     cudaEvent_t k0 = nullptr, k1 = nullptr;   // bracket the scan kernel on this lane's stream
+    // scratch of the two-phase (partitioned) scan, allocated on first use and grown on demand
+    uint64_t *part_pool = nullptr; uint64_t part_entries = 0;
+    unsigned long long *part_cursor = nullptr; uint32_t *part_overflow = nullptr;
     LaneState state = LANE_FREE;
     bool timed = false;
     uint64_t seq = 0;                  // submission order, to recycle the oldest first
@@ -156,6 +159,9 @@ extern "C" void s2_shutdown(s2_ctx *c)
         if (l.k1) cudaEventDestroy(l.k1);
         if (l.d_buf) cudaFree(l.d_buf);
         if (l.h_buf) cudaFreeHost(l.h_buf);
+        if (l.part_pool) cudaFree(l.part_pool);
+        if (l.part_cursor) cudaFree(l.part_cursor);
+        if (l.part_overflow) cudaFree(l.part_overflow);
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     for (auto &e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -242,7 +248,30 @@ struct s2_table {
     uint32_t *rank_pos = nullptr;      // first-occurrence rank -> byte offset of that first window in the build stream
     uint32_t *scratch = nullptr;       // n_keys uint32 staging for fetch / store
     uint64_t n_keys = 0;
+    bool partitioned = false;          // fingerprints do not fit L2: count scans go through the two-phase kernels
 };
+
+// the count scan of one batch on one lane's stream: direct kernel, or radix-partition + per-partition
+// probes when the table's fingerprint array is too large to stay L2 resident (caller holds c->mu)
+static int launch_count(s2_ctx *c, Lane &l, const uint8_t *d_bases, uint64_t n_bytes, s2_table *t, int col)
+{
+    if (!t->partitioned || n_bytes < (s2_env_u64("S2_PARTITION_MIN_BATCH_KB", 1024) << 10)) {
+        s2_launch_scan_count(d_bases, n_bytes, t->v, col, c->d_stats, c->grid_count, l.stream);
+        return 0;
+    }
+    const uint64_t region_cap = n_bytes / S2_NPART + n_bytes / (2 * S2_NPART) + 8192;     // 1.5x the even share
+    const uint64_t need = region_cap * S2_NPART;
+    if (need > l.part_entries) {
+        if (l.part_pool) { CK(cudaStreamSynchronize(l.stream)); cudaFree(l.part_pool); l.part_pool = nullptr; l.part_entries = 0; }
+        CK(cudaMalloc((void **)&l.part_pool, need * sizeof(uint64_t)));
+        l.part_entries = need;
+    }
+    if (!l.part_cursor) CK(cudaMalloc((void **)&l.part_cursor, S2_NPART * sizeof(unsigned long long)));
+    if (!l.part_overflow) CK(cudaMalloc((void **)&l.part_overflow, sizeof(uint32_t)));
+    s2_launch_scan_count_partitioned(d_bases, n_bytes, t->v, col, c->d_stats, l.part_pool, l.part_entries / S2_NPART,
+                                     l.part_cursor, l.part_overflow, c->n_sm, c->grid_count, l.stream);
+    return 0;
+}
 
 extern "C" uint64_t s2_table_n_keys(const s2_table *t) { return t->n_keys; }
 extern "C" uint64_t s2_table_n_slots(const s2_table *t) { return t->v.n_slots; }
@@ -310,6 +339,7 @@ static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t 
     CK(cudaMemcpyAsync(&n_keys, d_n, sizeof n_keys, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     t->n_keys = n_keys;
+    t->partitioned = t->v.n_slots * sizeof(uint16_t) > (s2_env_u64("S2_PARTITION_MIN_MB", 64) << 20);
     CK(cudaMalloc((void **)&t->rank_slot, (n_keys + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&t->scratch, (n_keys + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&t->rank_pos, (n_keys + 1) * sizeof(uint32_t)));
@@ -558,7 +588,7 @@ extern "C" int s2_scan_count(s2_ctx *c, s2_table *t, const void *bases, uint64_t
         Lane &l = c->lanes[0];
         if (lane_retire(c, l)) return -1;
         CK(cudaEventRecord(l.k0, l.stream));
-        s2_launch_scan_count((const uint8_t *)bases, n_bytes, t->v, col, c->d_stats, c->grid_count, l.stream);
+        if (launch_count(c, l, (const uint8_t *)bases, n_bytes, t, col)) return -1;
         CK(cudaGetLastError());
         CK(cudaEventRecord(l.k1, l.stream));
         l.state = LANE_INFLIGHT; l.timed = true; l.seq = c->next_seq++;
@@ -586,7 +616,7 @@ extern "C" int s2_scan_count(s2_ctx *c, s2_table *t, const void *bases, uint64_t
             if (lane_buffers(c, *l, false)) return -1;
             CK(cudaMemcpyAsync(l->d_buf, src + off, take, cudaMemcpyHostToDevice, l->stream));
             CK(cudaEventRecord(l->k0, l->stream));
-            s2_launch_scan_count(l->d_buf, take, t->v, col, c->d_stats, c->grid_count, l->stream);
+            if (launch_count(c, *l, l->d_buf, take, t, col)) return -1;
             CK(cudaGetLastError());
             CK(cudaEventRecord(l->k1, l->stream));
             l->state = LANE_INFLIGHT; l->timed = true; l->seq = c->next_seq++;
@@ -610,7 +640,7 @@ extern "C" int s2_scan_count_enqueue(s2_ctx *c, s2_table *t, const void *dev_bas
     if (!c->ev_free.empty()) { ev = c->ev_free.back(); c->ev_free.pop_back(); }
     else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
     CK(cudaEventRecord(ev.first, l.stream));
-    s2_launch_scan_count((const uint8_t *)dev_bases, n_bytes, t->v, col, c->d_stats, c->grid_count, l.stream);
+    if (launch_count(c, l, (const uint8_t *)dev_bases, n_bytes, t, col)) return -1;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev.second, l.stream));
     c->ev_pending.push_back(ev);
@@ -696,7 +726,7 @@ extern "C" int s2_batch_submit_count(s2_ctx *c, s2_table *t, uint8_t *batch, uin
     if (n_bytes == 0) { l->state = LANE_FREE; return 0; }
     CK(cudaMemcpyAsync(l->d_buf, l->h_buf, n_bytes, cudaMemcpyHostToDevice, l->stream));
     CK(cudaEventRecord(l->k0, l->stream));
-    s2_launch_scan_count(l->d_buf, n_bytes, t->v, col, c->d_stats, c->grid_count, l->stream);
+    if (launch_count(c, *l, l->d_buf, n_bytes, t, col)) return -1;
     CK(cudaGetLastError());
     CK(cudaEventRecord(l->k1, l->stream));
     l->state = LANE_INFLIGHT; l->timed = true; l->seq = c->next_seq++;

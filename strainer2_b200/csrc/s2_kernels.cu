@@ -225,9 +225,11 @@ __device__ __forceinline__ void drain_queue(const S2TableView &t, const uint64_t
 template <int MODE, int G, int MINB, bool PIPE>
 __global__ void __launch_bounds__(S2_THREADS, MINB)
 s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView t,
-               uint32_t *__restrict__ counts_col, S2DetectOut dout, unsigned long long *__restrict__ stats)
+               uint32_t *__restrict__ counts_col, S2DetectOut dout, unsigned long long *__restrict__ stats,
+               const uint32_t *__restrict__ run_if)
 {
     constexpr int NG = 16 / G;
+    if (run_if && *run_if == 0) return;            // fallback launch after a partition overflow: normally a no-op
     __shared__ uint64_t q_canon_s[S2_WARPS][S2_QCAP];
     __shared__ uint32_t q_slot_s[S2_WARPS][S2_QCAP];
     __shared__ uint64_t q_pos_s[MODE == S2_MODE_DETECT ? S2_WARPS : 1][MODE == S2_MODE_DETECT ? S2_QCAP : 1];
@@ -347,7 +349,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
 }
 
 // ---- variants -------------------------------------------------------------------------------------
-typedef void (*s2_scan_fn)(const uint8_t *, uint64_t, S2TableView, uint32_t *, S2DetectOut, unsigned long long *);
+typedef void (*s2_scan_fn)(const uint8_t *, uint64_t, S2TableView, uint32_t *, S2DetectOut, unsigned long long *, const uint32_t *);
 struct S2ScanVariant { const char *name; s2_scan_fn count_fn, detect_fn; };
 
 #define S2_VARIANT(G, MINB, PIPE) \
@@ -391,7 +393,7 @@ void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableV
     if (n_bytes == 0) return;
     S2DetectOut none = {};
     g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(
-        bases, n_bytes, t, t.counts + (uint64_t)col * t.n_slots, none, stats);
+        bases, n_bytes, t, t.counts + (uint64_t)col * t.n_slots, none, stats, nullptr);
 }
 
 void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
@@ -399,7 +401,160 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
                            cudaStream_t stream)
 {
     if (n_bytes == 0) return;
-    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats);
+    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats, nullptr);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// two-phase count scan for tables whose fingerprints do not fit L2 (multi-strain union tables)
+// ------------------------------------------------------------------------------------------------
+// Probing a 1.3 GB fingerprint array at random is DRAM row/latency bound (36 G lookups/s measured).
+// Phase A radix-partitions the canonical k-mers of a batch by the top 5 bits of their hash into 32
+// streams (8 bytes written + 8 read per lookup, fully coalesced); phase B probes one partition at a
+// time, whose 1/32 slice of the table (40 MB for 64 strains) stays L2 resident.
+
+#define S2_PSTAGE 48          /* staged entries per (warp, partition): flush threshold 16 + one step of 32 */
+#define S2_PFLUSH 16
+
+struct S2PartView {
+    uint64_t *pool;            // S2_NPART regions of region_cap entries
+    uint64_t region_cap;
+    unsigned long long *cursor;    // [S2_NPART] entries written per partition
+    uint32_t *overflow;        // set when a region would overflow: phase B is skipped and the direct kernel runs
+};
+
+__device__ __forceinline__ void part_flush(uint64_t *stage_p, uint32_t c, int p, const S2PartView &pv, int lane)
+{
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&pv.cursor[p], (unsigned long long)c);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base + c > pv.region_cap) { if (lane == 0) atomicOr(pv.overflow, 1u); return; }
+    uint64_t *dst = pv.pool + (uint64_t)p * pv.region_cap + base;
+    for (uint32_t i = lane; i < c; i += 32) dst[i] = stage_p[i];
+}
+
+__global__ void __launch_bounds__(S2_THREADS, 2)
+s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartView pv, unsigned long long *__restrict__ stats)
+{
+    extern __shared__ uint64_t stage_all[];                       // [S2_WARPS][S2_NPART][S2_PSTAGE]
+    __shared__ uint32_t count_all[S2_WARPS][S2_NPART];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t *stage = stage_all + (size_t)wid * S2_NPART * S2_PSTAGE;
+    uint32_t *count = count_all[wid];
+    count[lane] = 0;
+    __syncwarp();
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_tiles = (n_bytes + 511) / 512;
+    uint32_t n_valid = 0;
+    for (uint64_t tile = gwarp; tile < n_tiles; tile += n_warps) {
+        uint32_t w0, w1, w2, m0, m1, m2;
+        load_tile(bases, n_bytes, tile, lane, w0, w1, w2, m0, m1, m2);
+        const uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
+#pragma unroll 4
+        for (unsigned j = 0; j < 16; ++j) {
+            const bool valid = s2_window_valid(m0, m1, m2, j);
+            const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
+            const uint32_t p = s2_hash(canon).h >> 27;
+            n_valid += valid;
+            // lanes of this step that go to the same partition take consecutive stage slots
+            const uint32_t act = __ballot_sync(0xFFFFFFFFu, valid);
+            if (valid) {
+                const uint32_t same = __match_any_sync(act, p);
+                const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+                const uint32_t at = count[p] + rank;
+                stage[p * S2_PSTAGE + at] = canon;
+                __syncwarp(act);
+                if (rank == 0) count[p] += __popc(same);
+            }
+            __syncwarp();
+            // lane l looks after partition l: flush the ones that reached the threshold
+            uint32_t need = __ballot_sync(0xFFFFFFFFu, count[lane] >= S2_PFLUSH);
+            while (need) {
+                const int p2 = __ffs(need) - 1;
+                need &= need - 1;
+                const uint32_t c = count[p2];
+                part_flush(stage + p2 * S2_PSTAGE, c, p2, pv, lane);
+                __syncwarp();
+                if (lane == 0) count[p2] = 0;
+            }
+            __syncwarp();
+        }
+    }
+    for (int p2 = 0; p2 < S2_NPART; ++p2) {
+        const uint32_t c = count[p2];
+        if (c) part_flush(stage + p2 * S2_PSTAGE, c, p2, pv, lane);
+        __syncwarp();
+    }
+    n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
+    if (lane == 0 && stats && n_valid) atomicAdd(&stats[1], (unsigned long long)n_valid);
+}
+
+// phase B: probe the entries of ONE partition (their table slice is L2 resident)
+__global__ void __launch_bounds__(S2_THREADS, 4)
+s2_probe_partition_kernel(S2PartView pv, int part, S2TableView t, uint32_t *__restrict__ counts_col,
+                          unsigned long long *__restrict__ stats)
+{
+    if (*pv.overflow) return;
+    const uint64_t n = pv.cursor[part];
+    const uint64_t *__restrict__ src = pv.pool + (uint64_t)part * pv.region_cap;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t n_hits = 0;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        uint64_t canon[4]; uint32_t x[4][8], fp2[4], bucket[4]; bool have[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t i = i0 + u * stride;
+            have[u] = i < n;
+            canon[u] = have[u] ? __ldcs(src + i) : 0;              // streamed once
+            const s2_hash_t hh = s2_hash(canon[u]);
+            fp2[u] = hh.fp * 0x00010001u;
+            bucket[u] = s2_bucket_of(hh.h, t.n_buckets);
+            ld_bucket256(t.fp, bucket[u], x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t m = fp_match_bits(x[u], fp2[u]);
+            const bool full = x[u][7] > 0xFFFFu;
+            if (have[u] && (m != 0 || full)) {
+                const uint32_t b = 31u - (uint32_t)__clz(m);
+                uint32_t slot = bucket[u] * S2_BUCKET_SLOTS + ((((b & 15u) << 1) | ((b >> 4) & 1u)) & 15u);
+                uint64_t key = t.keys[slot];
+                bool hit = (key & S2_KMER_MASK) == canon[u] && key != S2_EMPTY_KEY;
+                if (!hit) hit = probe_exact(t, canon[u], slot, key);
+                if (hit) { atomicAdd(&counts_col[slot], 1u); ++n_hits; }
+            }
+        }
+    }
+    n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
+    if ((threadIdx.x & 31) == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)n_hits);
+}
+
+size_t s2_partition_smem_bytes(void) { return (size_t)S2_WARPS * S2_NPART * S2_PSTAGE * sizeof(uint64_t); }
+
+// whole two-phase scan on one stream.  part_pool holds S2_NPART * region_cap entries; cursor[S2_NPART]
+// and overflow[1] are zeroed here.  If a region overflows (pathological low-complexity input) phase B
+// does nothing and the direct scan kernel takes over, so the counters are exact either way.
+void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t, int col,
+                                      unsigned long long *stats, uint64_t *part_pool, uint64_t region_cap,
+                                      unsigned long long *cursor, uint32_t *overflow, int n_sm, int grid_blocks,
+                                      cudaStream_t stream)
+{
+    if (n_bytes == 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(s2_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_partition_smem_bytes());
+        attr_set = true;
+    }
+    cudaMemsetAsync(cursor, 0, S2_NPART * sizeof(unsigned long long), stream);
+    cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
+    S2PartView pv = { part_pool, region_cap, cursor, overflow };
+    s2_partition_kernel<<<n_sm * 2, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats);
+    uint32_t *counts_col = t.counts + (uint64_t)col * t.n_slots;
+    for (int p = 0; p < S2_NPART; ++p)
+        s2_probe_partition_kernel<<<n_sm * 8, S2_THREADS, 0, stream>>>(pv, p, t, counts_col, stats);
+    S2DetectOut none = {};
+    g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow);
 }
 
 // ------------------------------------------------------------------------------------------------

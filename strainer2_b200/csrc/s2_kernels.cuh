@@ -35,6 +35,12 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
                            const S2DetectOut &out, unsigned long long *stats, int grid_blocks,
                            cudaStream_t stream);
 int  s2_scan_blocks_per_sm(int mode);
+// two-phase (radix partition, then per-partition probe) count scan for tables larger than L2
+#define S2_NPART 32
+void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t, int col,
+                                      unsigned long long *stats, uint64_t *part_pool, uint64_t region_cap,
+                                      unsigned long long *cursor, uint32_t *overflow, int n_sm, int grid_blocks,
+                                      cudaStream_t stream);
 // kernel shape selection (sweep tool / S2_SCAN_VARIANT); see s2_kernels.cu
 int  s2_scan_variant_count(void);
 const char *s2_scan_variant_name(int v);

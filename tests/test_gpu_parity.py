@@ -407,3 +407,35 @@ def test_multi_strain_batch_equals_one_reference_run_per_strain(s2, tmp_path):
         assert v[:, 2].sum() > 0
         drug_sums.append(int(v[:, 3].sum()))
     assert sum(1 for d in drug_sums if d > 0) >= 3          # the strains that share sequence see each other in -C
+
+
+def test_two_phase_partitioned_scan_equals_direct_scan(s2, tmp_path, monkeypatch):
+    """tables whose fingerprints exceed L2 are scanned by radix-partition + per-partition probe; forced on
+    here for a small table: counters must equal the direct kernel's, including when a partition overflows
+    (poly-A input: every window lands in one partition) and the direct kernel takes over."""
+    import torch
+    from strainer2_b200 import synth
+    rng = synth.rng_for(6, 0)
+    strain = synth.genome(rng, 300_000, 4, n_runs=3)
+    strain[1][5000:5200] = ord("A")                                  # poly-A keys in the table
+    flat = synth.contigs_to_flat(strain)
+    clean = [np.where(c == ord("N"), ord("C"), c).astype(np.uint8) for c in strain]
+    reads = synth.sample_reads(rng, clean + synth.genome(rng, 600_000, 2), 60_000, 150, sub_rate=0.01, n_rate=1e-3)
+    batch = synth.reads_to_flat(reads)
+    polyA = np.full(3_000_000, ord("A"), dtype=np.uint8)
+    polyA[::1000] = ord("\n")
+    with s2.Context(0, batch_bytes=4 << 20, n_lanes=3) as ctx:
+        direct = s2.StrainTable(ctx, flat, n_cols=4)
+        monkeypatch.setenv("S2_PARTITION_MIN_MB", "0")
+        monkeypatch.setenv("S2_PARTITION_MIN_BATCH_KB", "0")
+        part = s2.StrainTable(ctx, flat, n_cols=4)
+        for col, data in ((1, batch), (2, polyA)):
+            a = ctx.scan_count(direct, torch.from_numpy(data).cuda(), col)
+            b = ctx.scan_count(part, torch.from_numpy(data).cuda(), col)
+            assert (a.hits, a.valid_windows) == (b.hits, b.valid_windows) and a.hits > 0
+            assert np.array_equal(direct.counts(col), part.counts(col))
+        # host batches through the lanes use the same two-phase path
+        c = ctx.scan_count(part, batch, 3)
+        assert c.hits == int(direct.counts(1).sum())
+        assert np.array_equal(part.counts(3), direct.counts(1))
+        direct.free(); part.free()
