@@ -168,6 +168,10 @@ int         s2_roworder_emulate(const uint32_t *djb2, uint64_t n, uint32_t initi
 int         s2_format_count_table(FILE *out, const uint64_t *keys, const uint32_t *order, uint64_t n,
                                   const uint32_t *const *cols, int n_print_cols, int n_threads);
 
+/* the same table formatted ON THE DEVICE straight from a strain table (keys, counters and row text never
+ * exist on the host except as the finished bytes): header + one row per key in `order`. */
+int         s2_table_format(s2_table *t, const uint32_t *order, int n_print_cols, FILE *out);
+
 /* FASTA/FASTQ (plain or gzip) reader with the record semantics of the parser the reference vendors
  * (src/kseq.h:171-211).  s2_reader_next returns the sequence length, -1 at end of file, -2 on a
  * truncated / mismatched quality string; the sequence stays valid until the next call. */

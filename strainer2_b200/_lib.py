@@ -75,6 +75,7 @@ SIGNATURES = {
     "s2_kmer_to_ascii": (None, [C.c_uint64, C.c_char_p]),
     "s2_roworder_emulate": (C.c_int, [c_u32p, C.c_uint64, C.c_uint32, c_u32p, c_u32p]),
     "s2_format_count_table": (C.c_int, [C.c_void_p, c_u64p, c_u32p, C.c_uint64, C.POINTER(c_u32p), C.c_int, C.c_int]),
+    "s2_table_format": (C.c_int, [C.c_void_p, c_u32p, C.c_int, C.c_void_p]),
     "s2_reader_open": (C.c_void_p, [C.c_char_p]),
     "s2_reader_next": (C.c_int64, [C.c_void_p, C.POINTER(C.c_char_p)]),
     "s2_reader_len": (C.c_uint64, [C.c_void_p]),

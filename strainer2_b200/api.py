@@ -204,6 +204,17 @@ class StrainTable:
     def scatter_counts_dev(self, col, dev_tensor):
         check(lib.s2_table_counts_scatter_dev(self.h, col, dev_tensor.data_ptr()), "s2_table_counts_scatter_dev")
 
+    def format_to(self, path, order, n_print_cols):
+        """print_hash_counts formatted on the device (s2_table_format) into `path`"""
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        fp = _libc.fopen(os.fsencode(path), b"w")
+        if not fp:
+            raise OSError(f"cannot open {path}")
+        try:
+            check(lib.s2_table_format(self.h, _ptr(order, C.c_uint32), n_print_cols, fp), "s2_table_format")
+        finally:
+            _libc.fclose(fp)
+
     def flag(self, kmers):
         k = np.ascontiguousarray(kmers, dtype=np.uint64)
         found = np.zeros(max(k.size, 1), dtype=np.uint8)

@@ -383,6 +383,58 @@ extern "C" int s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2, uint
     return 0;
 }
 
+static int check_col(const s2_table *t, int col);
+
+// print_hash_counts() on the device: rows in `order` (insertion indices, from s2_roworder_emulate), formatted by
+// one thread per row, copied back through a pinned staging buffer and written to `out`.
+extern "C" int s2_table_format(s2_table *t, const uint32_t *order, int n_print_cols, FILE *out)
+{
+    static const char header[] = "#kmer\treference_count\tpangenome_count\tmetagenome_count\tdrug_count\n";
+    s2_ctx *c = t->ctx;
+    CK(cudaSetDevice(c->device));
+    if (n_print_cols < 1 || n_print_cols > 4 || n_print_cols > t->v.n_cols) { s2_set_error("n_print_cols out of range"); return -1; }
+    if (fwrite(header, 1, sizeof header - 1, out) != sizeof header - 1) { s2_set_error("write failed"); return -1; }
+    const uint64_t n = t->n_keys;
+    if (n == 0) return 0;
+    cudaStream_t st = c->lanes[0].stream;
+    uint64_t *d_keys = nullptr; uint32_t *d_djb2 = nullptr, *d_order = nullptr, *d_cols[4] = { nullptr, nullptr, nullptr, nullptr };
+    unsigned long long *d_sums = nullptr, *d_total = nullptr;
+    char *d_text = nullptr, *h_stage = nullptr;
+    const uint32_t n_blocks = (uint32_t)((n + 1023) / 1024);
+    CK(cudaMalloc((void **)&d_keys, n * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&d_djb2, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&d_order, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&d_sums, (n_blocks + 1) * sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&d_total, sizeof(unsigned long long)));
+    CK(cudaMemcpyAsync(d_order, order, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    s2_launch_export(t->v, t->rank_slot, n, d_keys, d_djb2, st);
+    for (int k = 0; k < n_print_cols; ++k) {
+        CK(cudaMalloc((void **)&d_cols[k], n * sizeof(uint32_t)));
+        s2_launch_gather_counts(t->v, k, t->rank_slot, n, d_cols[k], st);
+    }
+    s2_launch_format(d_keys, d_order, n, d_cols, n_print_cols, d_sums, d_total, nullptr, 0, st);
+    CK(cudaGetLastError());
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMalloc((void **)&d_text, total + 1));
+    s2_launch_format(d_keys, d_order, n, d_cols, n_print_cols, d_sums, d_total, d_text, 1, st);
+    CK(cudaGetLastError());
+    const size_t stage = 32u << 20;
+    CK(cudaHostAlloc((void **)&h_stage, stage, cudaHostAllocDefault));
+    int rc = 0;
+    for (unsigned long long off = 0; off < total && rc == 0; off += stage) {
+        const size_t take = (size_t)std::min<unsigned long long>(stage, total - off);
+        CK(cudaMemcpyAsync(h_stage, d_text + off, take, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (fwrite(h_stage, 1, take, out) != take) { s2_set_error("write failed"); rc = -1; }
+    }
+    cudaFreeHost(h_stage);
+    cudaFree(d_text); cudaFree(d_keys); cudaFree(d_djb2); cudaFree(d_order); cudaFree(d_sums); cudaFree(d_total);
+    for (auto p : d_cols) if (p) cudaFree(p);
+    return rc;
+}
+
 static int check_col(const s2_table *t, int col)
 {
     if (col < 0 || col >= t->v.n_cols) { s2_set_error("column %d out of range (table has %d)", col, t->v.n_cols); return -1; }

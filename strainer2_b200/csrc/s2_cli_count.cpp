@@ -295,20 +295,27 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
 
     // ---- print_hash_counts: rows in the reference table's slot order
     const uint64_t n = s2_table_n_keys(table);
-    std::vector<uint64_t> keys(n);
-    std::vector<uint32_t> djb2(n), pos(n), cols[4];
-    if (s2_table_export(table, keys.data(), djb2.data(), exotic ? pos.data() : nullptr)) return fail(s2_last_error());
     const int n_print = C_file ? 4 : 3;
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> djb2(n), pos, cols[4];
     const uint32_t *colp[4] = { nullptr, nullptr, nullptr, nullptr };
-    for (int k = 0; k < n_print; ++k) {
-        cols[k].resize(n);
-        if (s2_table_counts_fetch(table, k, cols[k].data())) return fail(s2_last_error());
-        colp[k] = cols[k].data();
-    }
+    const bool host_format = exotic != nullptr || s2_env_int("S2_HOST_FORMAT", 0);
+    if (host_format) {
+        keys.resize(n);
+        if (exotic) pos.resize(n);
+        if (s2_table_export(table, keys.data(), djb2.data(), exotic ? pos.data() : nullptr)) return fail(s2_last_error());
+        for (int k = 0; k < n_print; ++k) {
+            cols[k].resize(n);
+            if (s2_table_counts_fetch(table, k, cols[k].data())) return fail(s2_last_error());
+            colp[k] = cols[k].data();
+        }
+    } else if (s2_table_export(table, nullptr, djb2.data(), nullptr)) return fail(s2_last_error());
     if (!exotic) {
+        // only the djb2 values leave the device for the row-order replay; the text is formatted on the GPU
         std::vector<uint32_t> order(n);
         if (s2_roworder_emulate(djb2.data(), n, 0, order.data(), nullptr)) return fail(s2_last_error());
-        if (s2_format_count_table(stdout, keys.data(), order.data(), n, colp, n_print, n_threads)) return fail(s2_last_error());
+        if (host_format ? s2_format_count_table(stdout, keys.data(), order.data(), n, colp, n_print, n_threads)
+                        : s2_table_format(table, order.data(), n_print, stdout)) return fail(s2_last_error());
     } else {
         // merge the device keys and the host string keys by first occurrence = the reference's insertion order
         std::vector<S2ExoRow> xr;

@@ -702,6 +702,108 @@ void s2_launch_build_rank(uint64_t n_bytes, const uint32_t *first_pos, const uin
     s2_rank_write_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(n_bytes, first_pos, slot_of_pos, block_sums, rank_slot, rank_pos);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// count-table formatting on the device  (print_hash_counts, src/kmer_scrub_count.c:134-156)
+// ------------------------------------------------------------------------------------------------
+// One thread per row: "<31 letters>\t%d\t%d\t%d[\t%d]\n" with the counters printed as signed int like
+// the reference's %d.  Three launches: row lengths per 1024-row block, scan of the block sums, write.
+#define S2_FMT_MAXROW 96
+
+__device__ __forceinline__ int fmt_int(char *p, uint32_t u)
+{
+    int32_t v = (int32_t)u;
+    uint32_t a = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    char tmp[12]; int n = 0, w = 0;
+    do { tmp[n++] = (char)('0' + a % 10); a /= 10; } while (a);
+    if (v < 0) p[w++] = '-';
+    while (n) p[w++] = tmp[--n];
+    return w;
+}
+
+__device__ __forceinline__ int fmt_row(char *row, uint64_t key, const uint32_t *const *cols, int n_cols, uint32_t id)
+{
+    int w = 0;
+#pragma unroll
+    for (int i = 0; i < S2_K; ++i) row[w++] = s2_letter((uint32_t)(key >> (2 * (S2_K - 1 - i))) & 3u);
+    for (int c = 0; c < n_cols; ++c) { row[w++] = '\t'; w += fmt_int(row + w, cols[c][id]); }
+    row[w++] = '\n';
+    return w;
+}
+
+struct S2FmtCols { const uint32_t *col[4]; int n; };
+
+__global__ void __launch_bounds__(S2_THREADS)
+s2_fmt_len_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ order, uint64_t n, S2FmtCols fc,
+                  unsigned long long *__restrict__ block_sums)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * S2_RANK_PER_BLOCK + (uint64_t)threadIdx.x * S2_RANK_PER_THREAD;
+    uint32_t len = 0;
+    char row[S2_FMT_MAXROW];
+    for (int i = 0; i < S2_RANK_PER_THREAD; ++i)
+        if (base + i < n) { const uint32_t id = order[base + i]; len += fmt_row(row, keys[id], fc.col, fc.n, id); }
+    uint32_t total;
+    block_exclusive_scan(len, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(S2_THREADS)
+s2_fmt_scan_kernel(unsigned long long *__restrict__ block_sums, uint32_t n_blocks, unsigned long long *__restrict__ total_out)
+{
+    // single CTA, sequential over strips of 256 blocks (a few thousand blocks at most)
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += S2_THREADS) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t v = i < n_blocks ? (uint32_t)block_sums[i] : 0;     // a block is < 100 KB of text
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, total);
+        const unsigned long long carry = carry_s;
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+__global__ void __launch_bounds__(S2_THREADS)
+s2_fmt_write_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ order, uint64_t n, S2FmtCols fc,
+                    const unsigned long long *__restrict__ block_offsets, char *__restrict__ out)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * S2_RANK_PER_BLOCK + (uint64_t)threadIdx.x * S2_RANK_PER_THREAD;
+    char rows[S2_RANK_PER_THREAD][S2_FMT_MAXROW];
+    int lens[S2_RANK_PER_THREAD];
+    uint32_t len = 0;
+    for (int i = 0; i < S2_RANK_PER_THREAD; ++i) {
+        lens[i] = 0;
+        if (base + i < n) { const uint32_t id = order[base + i]; lens[i] = fmt_row(rows[i], keys[id], fc.col, fc.n, id); }
+        len += lens[i];
+    }
+    uint32_t total;
+    unsigned long long at = block_offsets[blockIdx.x] + block_exclusive_scan(len, total);
+    for (int i = 0; i < S2_RANK_PER_THREAD; ++i) {
+        for (int b = 0; b < lens[i]; ++b) out[at + b] = rows[i][b];
+        at += lens[i];
+    }
+}
+
+void s2_launch_format(const uint64_t *keys, const uint32_t *order, uint64_t n, const uint32_t *const *cols, int n_cols,
+                      unsigned long long *block_sums, unsigned long long *d_total, char *out, int phase, cudaStream_t stream)
+{
+    if (n == 0) { if (phase == 0) cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), stream); return; }
+    S2FmtCols fc; fc.n = n_cols;
+    for (int c = 0; c < 4; ++c) fc.col[c] = c < n_cols ? cols[c] : nullptr;
+    const uint32_t n_blocks = (uint32_t)((n + S2_RANK_PER_BLOCK - 1) / S2_RANK_PER_BLOCK);
+    if (phase == 0) {
+        s2_fmt_len_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(keys, order, n, fc, block_sums);
+        s2_fmt_scan_kernel<<<1, S2_THREADS, 0, stream>>>(block_sums, n_blocks, d_total);
+    } else {
+        s2_fmt_write_kernel<<<n_blocks, S2_THREADS, 0, stream>>>(keys, order, n, fc, block_sums, out);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // export / gather / scatter / flag / lookup / pack / fill
 // ------------------------------------------------------------------------------------------------

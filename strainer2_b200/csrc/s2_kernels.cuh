@@ -68,3 +68,7 @@ void s2_launch_counts_by_key(const S2TableView &t, int col, const uint64_t *kmer
 void s2_launch_pack(const uint8_t *bases, uint64_t n_bytes, uint32_t *words, uint16_t *masks,
                     cudaStream_t stream);
 void s2_launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream);
+
+// device-side count-table formatting: phase 0 = row lengths + offsets (+ total bytes), phase 1 = write the text
+void s2_launch_format(const uint64_t *keys, const uint32_t *order, uint64_t n, const uint32_t *const *cols, int n_cols,
+                      unsigned long long *block_sums, unsigned long long *d_total, char *out, int phase, cudaStream_t stream);

@@ -439,3 +439,25 @@ def test_two_phase_partitioned_scan_equals_direct_scan(s2, tmp_path, monkeypatch
         assert c.hits == int(direct.counts(1).sum())
         assert np.array_equal(part.counts(3), direct.counts(1))
         direct.free(); part.free()
+
+
+def test_device_formatter_equals_host_formatter(s2, ctx, golden_dir, tmp_path):
+    """s2_table_format (rows formatted by a kernel) against s2_format_count_table (host) and the golden bytes,
+    including counters above 2^31 that the reference prints negative (%d of unsigned)"""
+    d = os.path.join(golden_dir, "count_edge")
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(d, "ref.fa.gz")), n_cols=4)
+    keys, djb2 = t.export()
+    order, _ = s2.roworder_emulate(djb2)
+    big = np.arange(t.n_keys, dtype=np.uint64) * 1_000_003 % (2 ** 32)
+    big[:5] = [0, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1, 10]
+    t.set_counts(2, big.astype(np.uint32))
+    t.set_counts(3, (big[::-1] // 7).astype(np.uint32))
+    for n_print in (3, 4):
+        host, dev = str(tmp_path / f"h{n_print}.tsv"), str(tmp_path / f"d{n_print}.tsv")
+        s2.format_count_table(host, keys, order, [t.counts(c) for c in range(n_print)])
+        t.format_to(dev, order, n_print)
+        assert open(dev, "rb").read() == open(host, "rb").read()
+    p = s2.run_kmer_scrub_count(["-r", "ref.fa.gz", "-A", "listA.txt", "-B", "listB.txt", "-C", "listC.txt"], cwd=d,
+                                env={"S2_HOST_FORMAT": "1"})
+    assert p.returncode == 0 and p.stdout == open(os.path.join(d, "expected_ABC.tsv"), "rb").read()
+    t.free()
