@@ -344,7 +344,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
     n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
     if (lane == 0 && stats) {
         if (n_hits) atomicAdd(&stats[0], (unsigned long long)n_hits);
-        if (n_valid) atomicAdd(&stats[1], (unsigned long long)n_valid);
+        if (n_valid && !run_if) atomicAdd(&stats[1], (unsigned long long)n_valid);   // fallback run: phase A counted them
     }
 }
 
