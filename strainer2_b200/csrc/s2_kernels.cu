@@ -413,8 +413,7 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
 // streams (8 bytes written + 8 read per lookup, fully coalesced); phase B probes one partition at a
 // time, whose 1/32 slice of the table (40 MB for 64 strains) stays L2 resident.
 
-#define S2_PSTAGE 48          /* staged entries per (warp, partition): flush threshold 16 + one step of 32 */
-#define S2_PFLUSH 16
+#define S2_PSTAGE 384          /* staged entries per (CTA, partition) and round: 3x the even share of 4096 windows */
 
 struct S2PartView {
     uint64_t *pool;            // S2_NPART regions of region_cap entries
@@ -423,68 +422,61 @@ struct S2PartView {
     uint32_t *overflow;        // set when a region would overflow: phase B is skipped and the direct kernel runs
 };
 
-__device__ __forceinline__ void part_flush(uint64_t *stage_p, uint32_t c, int p, const S2PartView &pv, int lane)
-{
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&pv.cursor[p], (unsigned long long)c);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base + c > pv.region_cap) { if (lane == 0) atomicOr(pv.overflow, 1u); return; }
-    uint64_t *dst = pv.pool + (uint64_t)p * pv.region_cap + base;
-    for (uint32_t i = lane; i < c; i += 32) dst[i] = stage_p[i];
-}
-
+// Phase A.  A CTA works in rounds of 8 tiles (4096 windows): every valid window's canonical k-mer goes to
+// the shared-memory stage of its partition (one shared atomic for the slot), then the CTA reserves room
+// in each partition's global region with ONE global atomic per partition and round and copies the stage
+// out in coalesced runs (about 1 KB each).  Skewed rounds that overflow a stage append straight to global.
 __global__ void __launch_bounds__(S2_THREADS, 2)
 s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartView pv, unsigned long long *__restrict__ stats)
 {
-    extern __shared__ uint64_t stage_all[];                       // [S2_WARPS][S2_NPART][S2_PSTAGE]
-    __shared__ uint32_t count_all[S2_WARPS][S2_NPART];
+    extern __shared__ uint64_t stage[];                           // [S2_NPART][S2_PSTAGE]
+    __shared__ uint32_t cnt[S2_NPART];
+    __shared__ unsigned long long gbase[S2_NPART];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint64_t *stage = stage_all + (size_t)wid * S2_NPART * S2_PSTAGE;
-    uint32_t *count = count_all[wid];
-    count[lane] = 0;
-    __syncwarp();
-    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_tiles = (n_bytes + 511) / 512;
+    const uint64_t n_rounds = (n_tiles + S2_WARPS - 1) / S2_WARPS;
     uint32_t n_valid = 0;
-    for (uint64_t tile = gwarp; tile < n_tiles; tile += n_warps) {
-        uint32_t w0, w1, w2, m0, m1, m2;
-        load_tile(bases, n_bytes, tile, lane, w0, w1, w2, m0, m1, m2);
-        const uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
+    if (threadIdx.x < S2_NPART) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t round = blockIdx.x; round < n_rounds; round += gridDim.x) {
+        const uint64_t tile = round * S2_WARPS + wid;
+        if (tile < n_tiles) {
+            uint32_t w0, w1, w2, m0, m1, m2;
+            load_tile(bases, n_bytes, tile, lane, w0, w1, w2, m0, m1, m2);
+            const uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
 #pragma unroll 4
-        for (unsigned j = 0; j < 16; ++j) {
-            const bool valid = s2_window_valid(m0, m1, m2, j);
-            const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
-            const uint32_t p = s2_hash(canon).h >> 27;
-            n_valid += valid;
-            // lanes of this step that go to the same partition take consecutive stage slots
-            const uint32_t act = __ballot_sync(0xFFFFFFFFu, valid);
-            if (valid) {
-                const uint32_t same = __match_any_sync(act, p);
-                const uint32_t rank = __popc(same & ((1u << lane) - 1u));
-                const uint32_t at = count[p] + rank;
-                stage[p * S2_PSTAGE + at] = canon;
-                __syncwarp(act);
-                if (rank == 0) count[p] += __popc(same);
+            for (unsigned j = 0; j < 16; ++j) {
+                if (s2_window_valid(m0, m1, m2, j)) {
+                    const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
+                    const uint32_t p = s2_hash(canon).h >> 27;
+                    const uint32_t at = atomicAdd(&cnt[p], 1u);
+                    ++n_valid;
+                    if (at < S2_PSTAGE) {
+                        stage[p * S2_PSTAGE + at] = canon;
+                    } else {                                      // rare: this round is skewed towards one partition
+                        const unsigned long long g = atomicAdd(&pv.cursor[p], 1ull);
+                        if (g < pv.region_cap) pv.pool[(uint64_t)p * pv.region_cap + g] = canon;
+                        else atomicOr(pv.overflow, 1u);
+                    }
+                }
             }
-            __syncwarp();
-            // lane l looks after partition l: flush the ones that reached the threshold
-            uint32_t need = __ballot_sync(0xFFFFFFFFu, count[lane] >= S2_PFLUSH);
-            while (need) {
-                const int p2 = __ffs(need) - 1;
-                need &= need - 1;
-                const uint32_t c = count[p2];
-                part_flush(stage + p2 * S2_PSTAGE, c, p2, pv, lane);
-                __syncwarp();
-                if (lane == 0) count[p2] = 0;
-            }
-            __syncwarp();
         }
-    }
-    for (int p2 = 0; p2 < S2_NPART; ++p2) {
-        const uint32_t c = count[p2];
-        if (c) part_flush(stage + p2 * S2_PSTAGE, c, p2, pv, lane);
-        __syncwarp();
+        __syncthreads();
+        if (threadIdx.x < S2_NPART) {                             // one global reservation per partition and round
+            const uint32_t c = min(cnt[threadIdx.x], (uint32_t)S2_PSTAGE);
+            gbase[threadIdx.x] = c ? atomicAdd(&pv.cursor[threadIdx.x], (unsigned long long)c) : 0ull;
+        }
+        __syncthreads();
+        for (int p = wid; p < S2_NPART; p += S2_WARPS) {          // each warp copies out four partitions
+            const uint32_t c = min(cnt[p], (uint32_t)S2_PSTAGE);
+            const unsigned long long g = gbase[p];
+            if (g + c > pv.region_cap) { if (lane == 0 && c) atomicOr(pv.overflow, 1u); continue; }
+            uint64_t *dst = pv.pool + (uint64_t)p * pv.region_cap + g;
+            for (uint32_t i = lane; i < c; i += 32) dst[i] = stage[p * S2_PSTAGE + i];
+        }
+        __syncthreads();
+        if (threadIdx.x < S2_NPART) cnt[threadIdx.x] = 0;
+        __syncthreads();
     }
     n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
     if (lane == 0 && stats && n_valid) atomicAdd(&stats[1], (unsigned long long)n_valid);
@@ -530,7 +522,21 @@ s2_probe_partition_kernel(S2PartView pv, int part, S2TableView t, uint32_t *__re
     if ((threadIdx.x & 31) == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)n_hits);
 }
 
-size_t s2_partition_smem_bytes(void) { return (size_t)S2_WARPS * S2_NPART * S2_PSTAGE * sizeof(uint64_t); }
+// pull one partition's slice of the fingerprint array into L2 with sequential 256-bit loads (evict-last):
+// the probes that follow then find it there instead of fetching it at random, sector by sector
+__global__ void __launch_bounds__(S2_THREADS)
+s2_prefetch_slice_kernel(const uint16_t *__restrict__ fp, uint32_t bucket_lo, uint32_t bucket_hi, uint32_t *__restrict__ sink)
+{
+    uint32_t acc = 0;
+    for (uint64_t b = bucket_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < bucket_hi; b += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t x[8];
+        ld_bucket256(fp, (uint32_t)b, x);
+        acc |= x[0] ^ x[7];
+    }
+    if (acc == 0x12345679u) *sink = acc;              // never true in practice; keeps the loads alive
+}
+
+size_t s2_partition_smem_bytes(void) { return (size_t)S2_NPART * S2_PSTAGE * sizeof(uint64_t); }
 
 // whole two-phase scan on one stream.  part_pool holds S2_NPART * region_cap entries; cursor[S2_NPART]
 // and overflow[1] are zeroed here.  If a region overflows (pathological low-complexity input) phase B
@@ -551,8 +557,13 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     S2PartView pv = { part_pool, region_cap, cursor, overflow };
     s2_partition_kernel<<<n_sm * 2, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats);
     uint32_t *counts_col = t.counts + (uint64_t)col * t.n_slots;
-    for (int p = 0; p < S2_NPART; ++p)
+    for (int p = 0; p < S2_NPART; ++p) {
+        // buckets whose hash has top bits == p: [ceil(p * nb / 32), ceil((p+1) * nb / 32))
+        const uint32_t lo = (uint32_t)(((uint64_t)p * t.n_buckets + S2_NPART - 1) / S2_NPART);
+        const uint32_t hi = (uint32_t)(((uint64_t)(p + 1) * t.n_buckets + S2_NPART - 1) / S2_NPART);
+        s2_prefetch_slice_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(t.fp, lo, hi, overflow + 1);
         s2_probe_partition_kernel<<<n_sm * 8, S2_THREADS, 0, stream>>>(pv, p, t, counts_col, stats);
+    }
     S2DetectOut none = {};
     g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow);
 }
