@@ -266,7 +266,7 @@ static int launch_count(s2_ctx *c, Lane &l, const uint8_t *d_bases, uint64_t n_b
         CK(cudaMalloc((void **)&l.part_pool, need * sizeof(uint64_t)));
         l.part_entries = need;
     }
-    if (!l.part_cursor) CK(cudaMalloc((void **)&l.part_cursor, S2_NPART * sizeof(unsigned long long)));
+    if (!l.part_cursor) CK(cudaMalloc((void **)&l.part_cursor, (S2_NPART + 1) * sizeof(unsigned long long)));
     if (!l.part_overflow) CK(cudaMalloc((void **)&l.part_overflow, 2 * sizeof(uint32_t)));
     s2_launch_scan_count_partitioned(d_bases, n_bytes, t->v, col, c->d_stats, l.part_pool, l.part_entries / S2_NPART,
                                      l.part_cursor, l.part_overflow, c->n_sm, c->grid_count, l.stream);

@@ -522,6 +522,84 @@ s2_probe_partition_kernel(S2PartView pv, int part, S2TableView t, uint32_t *__re
     if ((threadIdx.x & 31) == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)n_hits);
 }
 
+
+// phase B, all partitions in ONE launch: CTAs draw work items (4096 entries of one partition) from a global
+// counter in partition order, so at any moment the whole grid works on one or two neighbouring partitions
+// and their slices of the table stay L2 resident without a barrier between partitions.  While it probes
+// partition p an item also pulls its share of slice p+1 into L2 with sequential loads.
+#define S2_PITEM 4096
+__global__ void __launch_bounds__(S2_THREADS, 4)
+s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_col,
+                    unsigned long long *__restrict__ stats, unsigned long long *__restrict__ work_counter)
+{
+    if (*pv.overflow) return;
+    __shared__ unsigned long long pre[S2_NPART + 1];
+    __shared__ unsigned long long item_s;
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int p = 0; p < S2_NPART; ++p) { pre[p] = acc; acc += (pv.cursor[p] + S2_PITEM - 1) / S2_PITEM; }
+        pre[S2_NPART] = acc;
+    }
+    __syncthreads();
+    const unsigned long long total = pre[S2_NPART];
+    uint32_t n_hits = 0, sink = 0;
+    for (;;) {
+        if (threadIdx.x == 0) item_s = atomicAdd(work_counter, 1ull);
+        __syncthreads();
+        const unsigned long long item = item_s;
+        __syncthreads();
+        if (item >= total) break;
+        int part = 0;
+        while (pre[part + 1] <= item) ++part;
+        const uint64_t n = pv.cursor[part];
+        const uint64_t off = (item - pre[part]) * S2_PITEM;
+        const uint64_t *__restrict__ src = pv.pool + (uint64_t)part * pv.region_cap;
+        // this item's share of the next partition's slice -> L2
+        if (part + 1 < S2_NPART) {
+            const uint64_t items_here = pre[part + 1] - pre[part];
+            const uint64_t lo = ((uint64_t)(part + 1) * t.n_buckets + S2_NPART - 1) / S2_NPART;
+            const uint64_t hi = ((uint64_t)(part + 2) * t.n_buckets + S2_NPART - 1) / S2_NPART;
+            const uint64_t share = (hi - lo + items_here - 1) / items_here;
+            const uint64_t b0 = lo + (item - pre[part]) * share;
+            for (uint64_t b = b0 + threadIdx.x; b < b0 + share && b < hi; b += S2_THREADS) {
+                uint32_t x[8];
+                ld_bucket256(t.fp, (uint32_t)b, x);
+                sink |= x[0] ^ x[7];
+            }
+        }
+#pragma unroll 1
+        for (int round = 0; round < S2_PITEM / (4 * S2_THREADS); ++round) {
+            uint64_t canon[4]; uint32_t x[4][8], fp2[4], bucket[4]; bool have[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t i = off + (uint64_t)(round * 4 + u) * S2_THREADS + threadIdx.x;
+                have[u] = i < n;
+                canon[u] = have[u] ? __ldcs(src + i) : 0;
+                const s2_hash_t hh = s2_hash(canon[u]);
+                fp2[u] = hh.fp * 0x00010001u;
+                bucket[u] = s2_bucket_of(hh.h, t.n_buckets);
+                ld_bucket256(t.fp, bucket[u], x[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t m = fp_match_bits(x[u], fp2[u]);
+                const bool full = x[u][7] > 0xFFFFu;
+                if (have[u] && (m != 0 || full)) {
+                    const uint32_t b = 31u - (uint32_t)__clz(m);
+                    uint32_t slot = bucket[u] * S2_BUCKET_SLOTS + ((((b & 15u) << 1) | ((b >> 4) & 1u)) & 15u);
+                    uint64_t key = t.keys[slot];
+                    bool hit = (key & S2_KMER_MASK) == canon[u] && key != S2_EMPTY_KEY;
+                    if (!hit) hit = probe_exact(t, canon[u], slot, key);
+                    if (hit) { atomicAdd(&counts_col[slot], 1u); ++n_hits; }
+                }
+            }
+        }
+    }
+    n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
+    if ((threadIdx.x & 31) == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)n_hits);
+    if (sink == 0x12345679u) atomicOr(pv.overflow + 1, sink);     // never true; keeps the prefetch loads alive
+}
+
 // pull one partition's slice of the fingerprint array into L2 with sequential 256-bit loads (evict-last):
 // the probes that follow then find it there instead of fetching it at random, sector by sector
 __global__ void __launch_bounds__(S2_THREADS)
@@ -547,6 +625,7 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
                                       cudaStream_t stream)
 {
     if (n_bytes == 0) return;
+    unsigned long long *work_counter = cursor + S2_NPART;        // cursor[] has one spare slot for the item counter
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(s2_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_partition_smem_bytes());
@@ -557,13 +636,12 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     S2PartView pv = { part_pool, region_cap, cursor, overflow };
     s2_partition_kernel<<<n_sm * 2, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats);
     uint32_t *counts_col = t.counts + (uint64_t)col * t.n_slots;
-    for (int p = 0; p < S2_NPART; ++p) {
-        // buckets whose hash has top bits == p: [ceil(p * nb / 32), ceil((p+1) * nb / 32))
-        const uint32_t lo = (uint32_t)(((uint64_t)p * t.n_buckets + S2_NPART - 1) / S2_NPART);
-        const uint32_t hi = (uint32_t)(((uint64_t)(p + 1) * t.n_buckets + S2_NPART - 1) / S2_NPART);
-        s2_prefetch_slice_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(t.fp, lo, hi, overflow + 1);
-        s2_probe_partition_kernel<<<n_sm * 8, S2_THREADS, 0, stream>>>(pv, p, t, counts_col, stats);
-    }
+    // buckets whose hash has top bits == p: [ceil(p * nb / 32), ceil((p+1) * nb / 32)); slice 0 is prefetched
+    // by its own small kernel, every later slice by the items of the partition before it
+    const uint32_t hi0 = (uint32_t)(((uint64_t)t.n_buckets + S2_NPART - 1) / S2_NPART);
+    s2_prefetch_slice_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(t.fp, 0, hi0, overflow + 1);
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    s2_probe_all_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter);
     S2DetectOut none = {};
     g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow);
 }
