@@ -482,47 +482,6 @@ s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartV
     if (lane == 0 && stats && n_valid) atomicAdd(&stats[1], (unsigned long long)n_valid);
 }
 
-// phase B: probe the entries of ONE partition (their table slice is L2 resident)
-__global__ void __launch_bounds__(S2_THREADS, 4)
-s2_probe_partition_kernel(S2PartView pv, int part, S2TableView t, uint32_t *__restrict__ counts_col,
-                          unsigned long long *__restrict__ stats)
-{
-    if (*pv.overflow) return;
-    const uint64_t n = pv.cursor[part];
-    const uint64_t *__restrict__ src = pv.pool + (uint64_t)part * pv.region_cap;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t n_hits = 0;
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
-        uint64_t canon[4]; uint32_t x[4][8], fp2[4], bucket[4]; bool have[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint64_t i = i0 + u * stride;
-            have[u] = i < n;
-            canon[u] = have[u] ? __ldcs(src + i) : 0;              // streamed once
-            const s2_hash_t hh = s2_hash(canon[u]);
-            fp2[u] = hh.fp * 0x00010001u;
-            bucket[u] = s2_bucket_of(hh.h, t.n_buckets);
-            ld_bucket256(t.fp, bucket[u], x[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t m = fp_match_bits(x[u], fp2[u]);
-            const bool full = x[u][7] > 0xFFFFu;
-            if (have[u] && (m != 0 || full)) {
-                const uint32_t b = 31u - (uint32_t)__clz(m);
-                uint32_t slot = bucket[u] * S2_BUCKET_SLOTS + ((((b & 15u) << 1) | ((b >> 4) & 1u)) & 15u);
-                uint64_t key = t.keys[slot];
-                bool hit = (key & S2_KMER_MASK) == canon[u] && key != S2_EMPTY_KEY;
-                if (!hit) hit = probe_exact(t, canon[u], slot, key);
-                if (hit) { atomicAdd(&counts_col[slot], 1u); ++n_hits; }
-            }
-        }
-    }
-    n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
-    if ((threadIdx.x & 31) == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)n_hits);
-}
-
-
 // phase B, all partitions in ONE launch: CTAs draw work items (4096 entries of one partition) from a global
 // counter in partition order, so at any moment the whole grid works on one or two neighbouring partitions
 // and their slices of the table stay L2 resident without a barrier between partitions.  While it probes

@@ -16,7 +16,9 @@ ctx = s2.Context(0, batch_bytes=64 << 20, n_lanes=2)
 t = s2.StrainTable(ctx, flat, n_cols=2)
 batch, bases, lookups = bench.make_batch(strain, 0, 32)
 dev = torch.from_numpy(batch).cuda()
-for i in range(3):
+ctx.scan_count(t, dev, 1)          # warm-up: allocates the partition pool
+ctx.kernel_time(reset=True)
+for i in range(5):
     st = ctx.scan_count(t, dev, 1)
 ms, n = ctx.kernel_time(reset=True)
 print(f"strains={n_strains} probe_bytes={t.probe_bytes} hits={st.hits} valid={st.valid_windows} avg_ms={ms / n:.3f} Glookups/s={lookups / (ms / n) / 1e6:.1f}")
