@@ -93,7 +93,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -347,7 +347,6 @@ def main():
     allreduce_counts()
     ar_ms = (time.perf_counter() - t_ar) * 1e3 if dist is not None else 0.0
     barrier()
-    clocks = sampler.stop()
     kernel_ms, launches = ctx.kernel_time(reset=True)
     my_bases = sum(step_bases[i % 2] for i in range(args.steps))
     my_lookups = sum(step_lookups[i % 2] for i in range(args.steps))
@@ -366,6 +365,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()                                # sampled through both timed regions
     parity_ok = bool(np.array_equal(table.counts(2), table.counts(1))) if dist is None else None
 
     # ---- reduce over ranks ----------------------------------------------------------------------
