@@ -1,0 +1,111 @@
+// Probe of the Blackwell hardware decompression engine through the CUDA driver API
+// (the batch-decompress entry point of cuda.h, CUDA 12.8+): is DEFLATE offered on this device, what is the longest single
+// operation, and how fast is one long raw-deflate stream / a batch of streams of FASTQ-like text?
+// Build: nvcc -O2 -o hwdecomp_probe tools/hwdecomp_probe.cu -lcuda -lz
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <zlib.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define CKD(x) do { CUresult r_ = (x); if (r_ != CUDA_SUCCESS) { const char *s; cuGetErrorString(r_, &s); printf("driver error %d (%s) at line %d\n", (int)r_, s ? s : "?", __LINE__); return 1; } } while (0)
+
+static std::vector<unsigned char> make_fastq(size_t approx)
+{
+    std::vector<unsigned char> t;
+    unsigned long long s = 88172645463325252ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    size_t n = 0;
+    while (t.size() < approx) {
+        char hdr[64]; int h = snprintf(hdr, sizeof hdr, "@r%zu\n", n++);
+        t.insert(t.end(), hdr, hdr + h);
+        for (int i = 0; i < 150; ++i) t.push_back("ACGT"[rnd() & 3]);
+        t.push_back('\n'); t.push_back('+'); t.push_back('\n');
+        for (int i = 0; i < 150; ++i) t.push_back('I');
+        t.push_back('\n');
+    }
+    return t;
+}
+
+static std::vector<unsigned char> raw_deflate(const std::vector<unsigned char> &in)
+{
+    z_stream z; memset(&z, 0, sizeof z);
+    deflateInit2(&z, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    std::vector<unsigned char> out(deflateBound(&z, in.size()));
+    z.next_in = (Bytef *)in.data(); z.avail_in = (uInt)in.size();
+    z.next_out = out.data(); z.avail_out = (uInt)out.size();
+    deflate(&z, Z_FINISH);
+    out.resize(z.total_out);
+    deflateEnd(&z);
+    return out;
+}
+
+int main(int argc, char **argv)
+{
+    cudaFree(0);
+    CUdevice dev; CKD(cuInit(0)); CKD(cuDeviceGet(&dev, 0));
+    int mask = 0, maxlen = 0;
+    CKD(cuDeviceGetAttribute(&mask, CU_DEVICE_ATTRIBUTE_MEM_DECOMPRESS_ALGORITHM_MASK, dev));
+    CKD(cuDeviceGetAttribute(&maxlen, CU_DEVICE_ATTRIBUTE_MEM_DECOMPRESS_MAXIMUM_LENGTH, dev));
+    printf("decompress algorithm mask = 0x%x (deflate=%d snappy=%d lz4=%d), maximum length = %d bytes\n", mask, mask & 1, (mask >> 1) & 1, (mask >> 2) & 1, maxlen);
+    if (!(mask & CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE)) { printf("no hardware deflate\n"); return 0; }
+    size_t sizes_mb[] = { 1, 16, 64, 256 };
+    int nsz = argc > 1 ? atoi(argv[1]) : 4;
+    cudaStream_t st; cudaStreamCreate(&st);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int k = 0; k < nsz; ++k) {
+        std::vector<unsigned char> text = make_fastq(sizes_mb[k] << 20), comp = raw_deflate(text);
+        CUdeviceptr dsrc, ddst, dact;
+        CKD(cuMemAlloc(&dsrc, comp.size() + 64)); CKD(cuMemAlloc(&ddst, text.size() + 64)); CKD(cuMemAlloc(&dact, 64));
+        CKD(cuMemcpyHtoD(dsrc, comp.data(), comp.size()));
+        cudaMemset((void *)ddst, 0, text.size());
+        CUmemDecompressParams p; memset(&p, 0, sizeof p);
+        p.srcNumBytes = comp.size(); p.dstNumBytes = text.size(); p.dstActBytes = (cuuint32_t *)dact;
+        p.src = (const void *)dsrc; p.dst = (void *)ddst; p.algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
+        size_t err = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0, st);
+            CUresult r = cuMemBatchDecompressAsync(&p, 1, 0, &err, st);
+            cudaEventRecord(e1, st);
+            cudaError_t se = cudaStreamSynchronize(st);
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            unsigned act = 0; cuMemcpyDtoH(&act, dact, 4);
+            std::vector<unsigned char> back(text.size());
+            cuMemcpyDtoH(back.data(), ddst, text.size());
+            printf("one stream %4zu MB text (%6.1f MB deflate): submit=%d sync=%d act=%u ok=%d  %.3f ms  %.2f GB/s of text\n", sizes_mb[k], comp.size() / 1048576.0,
+                   (int)r, (int)se, act, (int)(act == text.size() && memcmp(back.data(), text.data(), text.size()) == 0), ms, text.size() / 1e6 / ms);
+            if (r != CUDA_SUCCESS || se != cudaSuccess) return 1;
+        }
+        cuMemFree(dsrc); cuMemFree(ddst); cuMemFree(dact);
+    }
+    // batch: 64 independent streams of 4 MB text each
+    {
+        const int B = 64;
+        std::vector<unsigned char> text = make_fastq(4 << 20), comp = raw_deflate(text);
+        const size_t cs = (comp.size() + 255) & ~255ull, ts = (text.size() + 255) & ~255ull;
+        CUdeviceptr dsrc, ddst, dact;
+        CKD(cuMemAlloc(&dsrc, cs * B)); CKD(cuMemAlloc(&ddst, ts * B)); CKD(cuMemAlloc(&dact, 4 * B));
+        std::vector<CUmemDecompressParams> ps(B);
+        for (int i = 0; i < B; ++i) {
+            CKD(cuMemcpyHtoD(dsrc + cs * i, comp.data(), comp.size()));
+            memset(&ps[i], 0, sizeof ps[i]);
+            ps[i].srcNumBytes = comp.size(); ps[i].dstNumBytes = text.size(); ps[i].dstActBytes = (cuuint32_t *)(dact + 4 * i);
+            ps[i].src = (const void *)(dsrc + cs * i); ps[i].dst = (void *)(ddst + ts * i); ps[i].algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
+        }
+        size_t err = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0, st);
+            CUresult r = cuMemBatchDecompressAsync(ps.data(), B, 0, &err, st);
+            cudaEventRecord(e1, st);
+            cudaError_t se = cudaStreamSynchronize(st);
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            std::vector<unsigned char> back(text.size());
+            cuMemcpyDtoH(back.data(), ddst + ts * (B - 1), text.size());
+            printf("batch of %d x 4 MB: submit=%d sync=%d last ok=%d  %.3f ms  %.2f GB/s of text\n", B, (int)r, (int)se,
+                   (int)(memcmp(back.data(), text.data(), text.size()) == 0), ms, B * text.size() / 1e6 / ms);
+        }
+    }
+    return 0;
+}
