@@ -116,6 +116,15 @@ int         s2_batch_release(s2_ctx *ctx, uint8_t *batch);               /* give
 /* wait for every batch in flight; returns totals accumulated since the previous s2_sync */
 int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
 
+/* GPU-side ingest: GEN_calculate_kmer_count() for one FILE without the host inflating or
+ * parsing it.  BGZF-compressed (bgzip) and uncompressed strict 4-line FASTQ are inflated by the Blackwell
+ * hardware decompression engine and split into records by kernels; the file is first proven regular in a
+ * pass that counts nothing.  Returns 0 = done, 1 = not handled (nothing was counted; use the reader +
+ * s2_batch_submit_count), -1 = error.  Thread safe (one ingest pipeline per calling thread; call
+ * s2_ingest_thread_cleanup() before the thread exits). */
+int         s2_ingest_count_file(s2_ctx *ctx, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups);
+void        s2_ingest_thread_cleanup(void);
+
 /* ---------------------------------------------------------------- detect scan --------------- */
 /* Pass 1 of quantify_hits_PE() (src/strain_detect.c:465-491, :514-539) for every record of a batch,
  * plus the positions pass 2 (:554-623) will print.  rec_off[n_rec+1] are the ascending byte offsets of

@@ -108,6 +108,14 @@ class Context:
         check(lib.s2_sync(self.h, C.byref(st)), "s2_sync")
         return ScanStats(st.hits, st.valid_windows)
 
+    def ingest_count_file(self, table, path, col):
+        """GPU-side ingest of one BGZF / plain strict-FASTQ file -> (rc, bases, lookups); rc 1 = not handled"""
+        b, l = C.c_uint64(), C.c_uint64()
+        rc = lib.s2_ingest_count_file(self.h, table.h, os.fsencode(path), col, C.byref(b), C.byref(l))
+        if rc < 0:
+            raise S2Error("s2_ingest_count_file: " + _lib.last_error())
+        return rc, b.value, l.value
+
     def kernel_time(self, reset=False):
         ms, n = C.c_double(), C.c_uint64()
         check(lib.s2_kernel_time(self.h, C.byref(ms), C.byref(n), 1 if reset else 0), "s2_kernel_time")

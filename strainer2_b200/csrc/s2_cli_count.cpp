@@ -5,6 +5,7 @@
 //
 // Extra controls come from the environment so argv stays drop-in:
 //   S2_GPUS (1: GPUs to shard the input files over)  S2_DEVICE (0)  S2_THREADS (min(nproc,16) reader threads)  S2_BATCH_MB (16)  S2_LOAD (0.5)
+//   S2_GPU_INGEST (1: BGZF / plain strict FASTQ are inflated and split into records on the GPU)
 //   S2_STATS=1 prints a one-line throughput summary on stderr.
 #include "../../include/strainer2_b200.h"
 #include "s2_internal.h"
@@ -141,6 +142,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                               uint64_t *bases_out, uint64_t *lookups_out)
 {
     std::mutex mu;                      // guards next / progress / stderr ordering
+    const bool gpu_ingest = s2_env_int("S2_GPU_INGEST", 1) != 0;
     size_t next = 0;
     std::atomic<bool> stop(false);
     std::atomic<uint64_t> total_bases(0), total_lookups(0);
@@ -149,9 +151,10 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
         for (;;) {
             s2_reader *r = nullptr; int col = 0;
+            std::string path;
             {
                 std::lock_guard<std::mutex> g(mu);
-                while (!r) {
+                while (path.empty()) {
                     if (stop.load() || next >= work.size()) break;
                     S2WorkItem &it = work[next++];
                     if (progress) {
@@ -166,6 +169,21 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                         break;
                     }
                     col = it.col;
+                    path = it.path;
+                }
+            }
+            if (!r) break;
+            // BGZF / plain strict FASTQ: hardware inflate + record splitting on the GPU, nothing parsed here
+            if (gpu_ingest && !exotic) {
+                uint64_t gb = 0, gl = 0;
+                const int irc = s2_ingest_count_file(w.ctx, w.table, path.c_str(), col, &gb, &gl);
+                if (irc == 0) { s2_reader_close(r); total_bases += gb; total_lookups += gl; continue; }
+                if (irc < 0) {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (open_error.empty()) open_error = s2_last_error();
+                    stop.store(true);
+                    s2_reader_close(r);
+                    break;
                 }
             }
             if (!r) break;
@@ -190,6 +208,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
             if (open_error.empty()) open_error = s2_last_error();
             stop.store(true);
         }
+        s2_ingest_thread_cleanup();
     };
     std::vector<std::thread> pool;
     for (int i = 1; i < n_threads; ++i) pool.emplace_back(reader, i);

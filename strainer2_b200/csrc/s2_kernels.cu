@@ -226,10 +226,11 @@ template <int MODE, int G, int MINB, bool PIPE>
 __global__ void __launch_bounds__(S2_THREADS, MINB)
 s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView t,
                uint32_t *__restrict__ counts_col, S2DetectOut dout, unsigned long long *__restrict__ stats,
-               const uint32_t *__restrict__ run_if)
+               const uint32_t *__restrict__ run_if, const unsigned long long *__restrict__ n_bytes_dev)
 {
     constexpr int NG = 16 / G;
     if (run_if && *run_if == 0) return;            // fallback launch after a partition overflow: normally a no-op
+    if (n_bytes_dev) n_bytes = *n_bytes_dev;       // batch produced on the device (GPU ingest): its length lives there
     __shared__ uint64_t q_canon_s[S2_WARPS][S2_QCAP];
     __shared__ uint32_t q_slot_s[S2_WARPS][S2_QCAP];
     __shared__ uint64_t q_pos_s[MODE == S2_MODE_DETECT ? S2_WARPS : 1][MODE == S2_MODE_DETECT ? S2_QCAP : 1];
@@ -349,7 +350,8 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
 }
 
 // ---- variants -------------------------------------------------------------------------------------
-typedef void (*s2_scan_fn)(const uint8_t *, uint64_t, S2TableView, uint32_t *, S2DetectOut, unsigned long long *, const uint32_t *);
+typedef void (*s2_scan_fn)(const uint8_t *, uint64_t, S2TableView, uint32_t *, S2DetectOut, unsigned long long *, const uint32_t *,
+                           const unsigned long long *);
 struct S2ScanVariant { const char *name; s2_scan_fn count_fn, detect_fn; };
 
 #define S2_VARIANT(G, MINB, PIPE) \
@@ -393,7 +395,16 @@ void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableV
     if (n_bytes == 0) return;
     S2DetectOut none = {};
     g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(
-        bases, n_bytes, t, t.counts + (uint64_t)col * t.n_slots, none, stats, nullptr);
+        bases, n_bytes, t, t.counts + (uint64_t)col * t.n_slots, none, stats, nullptr, nullptr);
+}
+
+// same, but the batch length is read from device memory (the batch was produced by the GPU ingest kernels)
+void s2_launch_scan_count_devlen(const uint8_t *bases, const unsigned long long *n_bytes_dev, const S2TableView &t, int col,
+                                 unsigned long long *stats, int grid_blocks, cudaStream_t stream)
+{
+    S2DetectOut none = {};
+    g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(
+        bases, 0, t, t.counts + (uint64_t)col * t.n_slots, none, stats, nullptr, n_bytes_dev);
 }
 
 void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
@@ -401,7 +412,7 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
                            cudaStream_t stream)
 {
     if (n_bytes == 0) return;
-    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats, nullptr);
+    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats, nullptr, nullptr);
 }
 
 
@@ -602,7 +613,7 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     s2_probe_all_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter);
     S2DetectOut none = {};
-    g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow);
+    g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

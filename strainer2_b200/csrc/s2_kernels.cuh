@@ -34,6 +34,8 @@ void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableV
 void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
                            const S2DetectOut &out, unsigned long long *stats, int grid_blocks,
                            cudaStream_t stream);
+void s2_launch_scan_count_devlen(const uint8_t *bases, const unsigned long long *n_bytes_dev, const S2TableView &t, int col,
+                                 unsigned long long *stats, int grid_blocks, cudaStream_t stream);
 int  s2_scan_blocks_per_sm(int mode);
 // two-phase (radix partition, then per-partition probe) count scan for tables larger than L2
 #define S2_NPART 32

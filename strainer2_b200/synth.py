@@ -135,6 +135,28 @@ def write_reads_fastq(path, reads: np.ndarray, gz=None):
             f.write(b"".join(b"@r%d\n%s\n+\n%s\n" % (s + i, chunk[i].tobytes(), qual) for i in range(chunk.shape[0])))
 
 
+def write_bgzf(path, data: bytes, block: int = 65280, level: int = 6):
+    """BGZF (bgzip) container: independent gzip members of <= 64 KB of text each, sizes in the 'BC' extra
+    field, empty EOF member at the end.  A valid multi-member .gz for zlib (what the reference uses); the
+    block structure is what lets the hardware decompression engine inflate it in parallel."""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        for off in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if off is None else data[off:off + block]
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            bsize = len(comp) + 25                                   # total member size - 1
+            f.write(b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize))
+            f.write(comp + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+
+def fastq_bytes(reads: np.ndarray) -> bytes:
+    n, L = reads.shape
+    qual = b"I" * L
+    return b"".join(b"@r%d\n%s\n+\n%s\n" % (i, reads[i].tobytes(), qual) for i in range(n))
+
+
 def ensure_dir(p):
     os.makedirs(p, exist_ok=True)
     return p

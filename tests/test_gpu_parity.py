@@ -461,3 +461,91 @@ def test_device_formatter_equals_host_formatter(s2, ctx, golden_dir, tmp_path):
                                 env={"S2_HOST_FORMAT": "1"})
     assert p.returncode == 0 and p.stdout == open(os.path.join(d, "expected_ABC.tsv"), "rb").read()
     t.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU-side ingest: hardware DEFLATE (BGZF) + record splitting kernels
+# ---------------------------------------------------------------------------------------------
+def _ingest_fixture(s2, tmp, n_reads=60_000, seed=0):
+    from strainer2_b200 import synth
+    rng = synth.rng_for(7, seed)
+    strain = synth.genome(rng, 300_000, 4, n_runs=2)
+    clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for c in strain]
+    reads = synth.sample_reads(rng, clean + synth.genome(rng, 600_000, 2), n_reads, 150, sub_rate=0.005, n_rate=1e-4)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    return strain, reads
+
+
+def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path):
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    strain, reads = _ingest_fixture(s2, tmp, 340_000)                  # ~100 MB of text: several ingest chunks
+    data = synth.fastq_bytes(reads)
+    # a few irregular-but-legal records at known places: short reads, an empty read, N runs
+    data += b"@short\nACGT\n+\nIIII\n@empty\n\n+\n\n@n\n" + b"N" * 80 + b"\n+\n" + b"#" * 80 + b"\n"
+    synth.write_bgzf(os.path.join(tmp, "m.fastq.gz"), data)
+    open(os.path.join(tmp, "m.fastq"), "wb").write(data[:-1])          # plain, last line without '\n'
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    want = ctx.scan_count(t, s2.load_flat(os.path.join(tmp, "m.fastq.gz")), 1)
+    n_bases = len(reads) * 150 + 4 + 80
+    for col, name in ((2, "m.fastq.gz"), (3, "m.fastq")):
+        rc, bases, lookups = ctx.ingest_count_file(t, os.path.join(tmp, name), col)
+        st = ctx.sync()
+        assert rc == 0
+        assert bases == n_bases and lookups == len(reads) * 120 + 50
+        assert st.hits == want.hits and st.valid_windows == want.valid_windows
+        assert np.array_equal(t.counts(col), t.counts(1))
+    t.free()
+
+
+def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path):
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    strain, reads = _ingest_fixture(s2, tmp, 3000, seed=1)
+    good = synth.fastq_bytes(reads)
+    r0 = reads[0].tobytes()
+    cases = {
+        "crlf": good.replace(b"\n", b"\r\n"),
+        "multiline": good + b"@ml\n" + r0[:75] + b"\n" + r0[75:] + b"\n+\n" + b"I" * 75 + b"\n" + b"I" * 75 + b"\n",
+        "truncated": good + b"@t\n" + r0 + b"\n+\n",
+        "qual_len": good + b"@q\n" + r0 + b"\n+\n" + b"I" * 149 + b"\n",
+        "fasta_inside": good + b">fa\n" + r0 + b"\n",
+        "junk_first": b"junk\n" + good,
+    }
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    for name, data in cases.items():
+        p = os.path.join(tmp, name + ".fastq.gz")
+        synth.write_bgzf(p, data)
+        rc, _, _ = ctx.ingest_count_file(t, p, 1)
+        assert rc == 1, name
+        assert int(t.counts(1).sum()) == 0, name                     # the validation pass counted nothing
+    # a plain single-member gzip is not BGZF: host reader
+    synth.write_reads_fastq(os.path.join(tmp, "plain.fastq.gz"), reads)
+    assert ctx.ingest_count_file(t, os.path.join(tmp, "plain.fastq.gz"), 1)[0] == 1
+    t.free()
+
+
+def test_executable_with_bgzf_inputs_matches_oracle(s2, golden_dir, tmp_path):
+    """-B lists mixing BGZF, plain and ordinary .gz FASTQ (GPU ingest for the first two, host reader for the rest,
+    and for every irregular golden edge case re-packed as BGZF): stdout bytes equal the oracle's"""
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    strain, reads = _ingest_fixture(s2, tmp, 40_000, seed=2)
+    synth.write_bgzf(os.path.join(tmp, "a.fastq.gz"), synth.fastq_bytes(reads[:20_000]))
+    open(os.path.join(tmp, "b.fastq"), "wb").write(synth.fastq_bytes(reads[20_000:30_000]))
+    synth.write_reads_fastq(os.path.join(tmp, "c.fastq.gz"), reads[30_000:])
+    edge = os.path.join(golden_dir, "count_edge")
+    names = []
+    for f in ("m1_reads.fastq.gz", "m3_truncated_quality.fastq", "m4_crlf.fastq", "m2_multiline_reads.fa"):
+        raw = ou.gunzip(os.path.join(edge, f)) if f.endswith(".gz") else open(os.path.join(edge, f), "rb").read()
+        synth.write_bgzf(os.path.join(tmp, "edge_" + f + ".bgz"), raw)
+        names.append("edge_" + f + ".bgz")
+    open(os.path.join(tmp, "A.txt"), "w").write("")
+    open(os.path.join(tmp, "B.txt"), "w").write("\n".join(["a.fastq.gz", "b.fastq", "c.fastq.gz"] + names) + "\n")
+    args = ["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"]
+    o = ou.oracle_cli(["count"] + args, cwd=tmp)
+    assert o.returncode == 0
+    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1"}):
+        p = s2.run_kmer_scrub_count(args, cwd=tmp, env=env)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout == o.stdout, env

@@ -51,8 +51,8 @@ int main(int argc, char **argv)
     CKD(cuDeviceGetAttribute(&maxlen, CU_DEVICE_ATTRIBUTE_MEM_DECOMPRESS_MAXIMUM_LENGTH, dev));
     printf("decompress algorithm mask = 0x%x (deflate=%d snappy=%d lz4=%d), maximum length = %d bytes\n", mask, mask & 1, (mask >> 1) & 1, (mask >> 2) & 1, maxlen);
     if (!(mask & CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE)) { printf("no hardware deflate\n"); return 0; }
-    size_t sizes_mb[] = { 1, 16, 64, 256 };
-    int nsz = argc > 1 ? atoi(argv[1]) : 4;
+    size_t sizes_mb[] = { 1, 2, 3 };
+    int nsz = argc > 1 ? atoi(argv[1]) : 3;
     cudaStream_t st; cudaStreamCreate(&st);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int k = 0; k < nsz; ++k) {
@@ -80,13 +80,15 @@ int main(int argc, char **argv)
         }
         cuMemFree(dsrc); cuMemFree(ddst); cuMemFree(dact);
     }
-    // batch: 64 independent streams of 4 MB text each
-    {
-        const int B = 64;
-        std::vector<unsigned char> text = make_fastq(4 << 20), comp = raw_deflate(text);
-        const size_t cs = (comp.size() + 255) & ~255ull, ts = (text.size() + 255) & ~255ull;
+    // batches of independent 64 KB-of-text streams (the BGZF block shape) and of 1 MB streams
+    const size_t shapes[][2] = { { 65280, 1024 }, { 65280, 4096 }, { 1 << 20, 256 }, { 3 << 20, 64 } };
+    for (auto &sh : shapes) {
+        const size_t tsz = sh[0]; const int B = (int)sh[1];
+        std::vector<unsigned char> big = make_fastq(tsz + 4096);
+        std::vector<unsigned char> text(big.begin(), big.begin() + tsz), comp = raw_deflate(text);
+        const size_t cs = (comp.size() + 255) & ~255ull, ts = tsz;            // outputs packed back to back
         CUdeviceptr dsrc, ddst, dact;
-        CKD(cuMemAlloc(&dsrc, cs * B)); CKD(cuMemAlloc(&ddst, ts * B)); CKD(cuMemAlloc(&dact, 4 * B));
+        CKD(cuMemAlloc(&dsrc, cs * B)); CKD(cuMemAlloc(&ddst, ts * B + 256)); CKD(cuMemAlloc(&dact, 4 * B));
         std::vector<CUmemDecompressParams> ps(B);
         for (int i = 0; i < B; ++i) {
             CKD(cuMemcpyHtoD(dsrc + cs * i, comp.data(), comp.size()));
@@ -103,9 +105,11 @@ int main(int argc, char **argv)
             float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
             std::vector<unsigned char> back(text.size());
             cuMemcpyDtoH(back.data(), ddst + ts * (B - 1), text.size());
-            printf("batch of %d x 4 MB: submit=%d sync=%d last ok=%d  %.3f ms  %.2f GB/s of text\n", B, (int)r, (int)se,
+            printf("batch of %5d x %7zu B text (dst unaligned, packed): submit=%d sync=%d last ok=%d  %.3f ms  %.2f GB/s of text\n", B, tsz, (int)r, (int)se,
                    (int)(memcmp(back.data(), text.data(), text.size()) == 0), ms, B * text.size() / 1e6 / ms);
+            if (r != CUDA_SUCCESS || se != cudaSuccess) break;
         }
+        cuMemFree(dsrc); cuMemFree(ddst); cuMemFree(dact);
     }
     return 0;
 }
