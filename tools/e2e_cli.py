@@ -37,7 +37,10 @@ def _gen_meta(a):
     r2 = synth.sample_reads(rng, others, n_reads - n_reads // 100, 150, sub_rate=0.005, n_rate=1e-5)
     reads = np.concatenate([r1, r2])
     rng.shuffle(reads)
-    synth.write_reads_fastq(path, reads)
+    if path.endswith(".bgz"):
+        synth.write_bgzf(path, synth.fastq_bytes(reads))             # block gzip: the GPU ingest path
+    else:
+        synth.write_reads_fastq(path, reads)
     return path
 
 
@@ -58,18 +61,23 @@ def main():
     synth.write_fasta(os.path.join(tmp, "strain.fa"), strain, gz=False)
     jobs = [(os.path.join(tmp, f"g{i}.fa" + (".gz" if i < args.gz_genomes else "")), i, i < args.gz_genomes) for i in range(args.genomes)]
     mjobs = [(os.path.join(tmp, f"m{i}.fastq.gz"), i, args.reads) for i in range(args.metas)]
+    mjobs += [(os.path.join(tmp, f"m{i}.fastq.bgz"), i, args.reads) for i in range(args.metas)]
     with mp.Pool(min(24, os.cpu_count() or 1)) as pool:
         A = pool.map(_gen_genome, jobs)
         B = pool.map(_gen_meta, mjobs)
     open(os.path.join(tmp, "A.txt"), "w").write("".join(a + "\n" for a in A))
+    Bz = [b for b in B if b.endswith(".bgz")]
+    B = [b for b in B if not b.endswith(".bgz")]
     open(os.path.join(tmp, "B.txt"), "w").write("".join(b + "\n" for b in B))
+    open(os.path.join(tmp, "Bz.txt"), "w").write("".join(b + "\n" for b in Bz))
     open(os.path.join(tmp, "empty.txt"), "w").write("")
     print(f"# generated {len(A)} genomes ({args.gz_genomes} gz), {len(B)} metagenomes x {args.reads} reads in {time.time() - t0:.1f}s "
           f"under {tmp}", flush=True)
     exe = os.path.join(ROOT, "strainer2_b200", "bin", "kmer_scrub_count")
     env = dict(os.environ, S2_STATS="1")
     runs = [("genomes_only", ["-r", "strain.fa", "-A", "A.txt", "-B", "empty.txt"]),
-            ("metagenomes_only", ["-r", "strain.fa", "-A", "empty.txt", "-B", "B.txt"])]
+            ("metagenomes_only", ["-r", "strain.fa", "-A", "empty.txt", "-B", "B.txt"]),
+            ("metagenomes_bgzf_gpu_ingest", ["-r", "strain.fa", "-A", "empty.txt", "-B", "Bz.txt"])]
     for th in ([t for t in args.threads.split(",") if t] or [""]):
         for name, a in runs:
             e = dict(env)
@@ -78,6 +86,8 @@ def main():
             t1 = time.time()
             p = subprocess.run([exe] + a, cwd=tmp, env=e, stdout=open(os.path.join(tmp, name + ".tsv"), "wb"), stderr=subprocess.PIPE)
             print(f"{name} threads={th or 'default'} rc={p.returncode} wall={time.time() - t1:.2f}s {p.stderr.decode().strip()}", flush=True)
+    a = subprocess.run(["cmp", os.path.join(tmp, "metagenomes_only.tsv"), os.path.join(tmp, "metagenomes_bgzf_gpu_ingest.tsv")])
+    print("tables from .gz (host inflate) and .bgz (GPU ingest) identical:", a.returncode == 0, flush=True)
     # strain_detect on the same metagenomes: informative = every 100th k-mer of the strain's first contig
     c0 = bytes(strain[0]).replace(b"N", b"A")
     with open(os.path.join(tmp, "inf.txt"), "wb") as f:
