@@ -241,12 +241,15 @@ typedef CUresult (*devattr_fn)(int *, CUdevice_attribute, CUdevice);
 struct s2_ingest {
     s2_ctx *ctx = nullptr;
     cudaStream_t stream = nullptr;
-    uint8_t *h_comp = nullptr, *d_comp = nullptr, *d_text = nullptr, *d_flat = nullptr, *d_carry = nullptr;
+    uint8_t *h_comp[2] = { nullptr, nullptr }, *d_comp = nullptr, *d_text = nullptr, *d_flat = nullptr, *d_carry = nullptr;
+    cudaEvent_t h_free[2] = { nullptr, nullptr };      // pinned buffer b may be overwritten once its H2D copy is done
+    uint8_t *d_file = nullptr; size_t d_file_cap = 0;  // the whole compressed file, kept on the device between the two passes
     unsigned *d_block_nl = nullptr, *d_line_end = nullptr, *d_out = nullptr, *d_total = nullptr, *d_act = nullptr;
     IngState *d_state = nullptr, *h_state = nullptr;
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
-    std::vector<CUmemDecompressParams> params;
+    struct Chunk { std::vector<CUmemDecompressParams> params; size_t src_off = 0, src_len = 0, text_len = 0; bool eof = false; };
+    std::vector<Chunk> chunks;                         // pass 1 records them, pass 2 replays them without touching the host
 };
 
 static void ingest_free(s2_ingest *g)
@@ -254,7 +257,8 @@ static void ingest_free(s2_ingest *g)
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
-    cudaFreeHost(g->h_comp); cudaFree(g->d_comp); cudaFree(g->d_text); cudaFree(g->d_flat); cudaFree(g->d_carry);
+    for (int b = 0; b < 2; ++b) { cudaFreeHost(g->h_comp[b]); if (g->h_free[b]) cudaEventDestroy(g->h_free[b]); }
+    cudaFree(g->d_file); cudaFree(g->d_comp); cudaFree(g->d_text); cudaFree(g->d_flat); cudaFree(g->d_carry);
     cudaFree(g->d_block_nl); cudaFree(g->d_line_end); cudaFree(g->d_out); cudaFree(g->d_total); cudaFree(g->d_act);
     cudaFree(g->d_state); cudaFreeHost(g->h_state);
     delete g;
@@ -265,7 +269,10 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     g->ctx = c;
     CK(cudaSetDevice(c->device));
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-    CK(cudaHostAlloc((void **)&g->h_comp, ING_COMP_CHUNK, cudaHostAllocDefault));
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaHostAlloc((void **)&g->h_comp[b], ING_COMP_CHUNK, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&g->h_free[b], cudaEventDisableTiming));
+    }
     CK(cudaMalloc((void **)&g->d_comp, ING_COMP_CHUNK + 256));
     CK(cudaMalloc((void **)&g->d_text, (size_t)ING_MAXCARRY + ING_TEXT_CAP + 4096));
     CK(cudaMalloc((void **)&g->d_flat, (size_t)ING_TEXT_CAP + ING_MAXCARRY + 4096));
@@ -321,37 +328,75 @@ static bool is_bgzf_header(const uint8_t *p, ssize_t n)
            p[12] == 'B' && p[13] == 'C' && p[14] == 2 && p[15] == 0;
 }
 
-// one pass over the file.  scan = false: validate only.  Returns 0 ok, 1 irregular / unsupported, -1 error.
-static int ingest_pass(s2_ingest *g, s2_table *t, int fd, bool bgzf, int col, bool scan)
+// device work for one chunk whose bytes are already on the device: inflate (or copy), index, validate,
+// and - when scan is set - copy the sequence lines out and count them
+static int ingest_chunk(s2_ingest *g, s2_table *t, int col, bool scan, bool bgzf, const s2_ingest::Chunk &ch, const uint8_t *d_src, bool first)
 {
     s2_ctx *c = g->ctx;
     cudaStream_t st = g->stream;
     const unsigned text_blocks = (unsigned)(((size_t)ING_MAXCARRY + ING_TEXT_CAP) / 4096 + 1);
-    if (lseek(fd, 0, SEEK_SET) < 0) return 1;
+    ing_begin_chunk<<<1, 1, 0, st>>>(g->d_state, ch.text_len, ch.eof ? 1u : 0u, first ? 1u : 0u);
+    if (bgzf) {
+        if (!ch.params.empty()) {
+            size_t err_index = 0;
+            const CUresult r = g->decompress(const_cast<CUmemDecompressParams *>(ch.params.data()), ch.params.size(), 0, &err_index, (CUstream)st);
+            if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, err_index); return -1; }
+        }
+    } else if (ch.src_len) {
+        CK(cudaMemcpyAsync(g->d_text + ING_MAXCARRY, d_src, ch.src_len, cudaMemcpyDeviceToDevice, st));
+    }
+    ing_terminate_last_line<<<1, 1, 0, st>>>(g->d_text, g->d_state);
+    ing_nl_count<<<text_blocks, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_block_nl);
+    ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_block_nl, text_blocks, nullptr, &g->d_state->n_lines);
+    ing_nl_scatter<<<text_blocks, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_block_nl, g->d_line_end);
+    ing_fastq_prepare<<<1, 1, 0, st>>>(g->d_state);
+    ing_fastq_len<<<c->n_sm * 4, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, scan ? 1 : 0);
+    if (scan) {
+        ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_out, 0, &g->d_state->n_rec, g->d_total);
+        ing_set_flat_len<<<1, 1, 0, st>>>(g->d_state, g->d_total);
+        ing_fastq_copy<<<c->n_sm * 8, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, g->d_flat);
+        s2_launch_scan_count_devlen(g->d_flat, &g->d_state->flat_len, t->v, col, c->d_stats, c->grid_count, st);
+    }
+    ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 0);
+    ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 1);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Pass over the file FROM THE HOST: read() chunks of whole BGZF blocks (or of raw text) into two alternating
+// pinned buffers, copy them to the device (into the file cache when the file fits, so that the second pass
+// needs no I/O), and run the device stage.  Returns 0 ok, 1 irregular / unsupported, -1 error.
+static int ingest_pass_host(s2_ingest *g, s2_table *t, int fd, bool bgzf, int col, bool scan, bool cache)
+{
+    cudaStream_t st = g->stream;
     CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), st));
+    g->chunks.clear();
     off_t file_off = 0;
     bool first = true, eof = false;
+    int buf = 0;
     while (!eof) {
-        // ---- host: next chunk of whole BGZF blocks (or of raw text) into pinned memory -------------------
-        CK(cudaStreamSynchronize(st));                                           // h_comp / params are reused per chunk
-        const ssize_t got = pread(fd, g->h_comp, ING_COMP_CHUNK, file_off);
+        uint8_t *h = g->h_comp[buf];
+        CK(cudaEventSynchronize(g->h_free[buf]));                                // its previous H2D copy is done
+        const ssize_t got = pread(fd, h, ING_COMP_CHUNK, file_off);
         if (got < 0) { s2_set_error("read failed"); return -1; }
+        uint8_t *d_dst = cache ? g->d_file + file_off : g->d_comp;
+        s2_ingest::Chunk local, &ch = cache ? (g->chunks.emplace_back(), g->chunks.back()) : local;
         size_t used = 0, text_len = 0;
         if (bgzf) {
-            g->params.clear();
             while (used < (size_t)got) {
                 size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
-                if (!bgzf_block(g->h_comp + used, (size_t)got - used, &bs, &doff, &dlen, &isz)) return 1;   // not BGZF after all
-                if (dlen == (size_t)-1) break;                                   // partial block: next chunk starts here
-                if (isz > 65536 || text_len + isz > ING_TEXT_CAP) { if (isz > 65536) return 1; break; }
+                if (!bgzf_block(h + used, (size_t)got - used, &bs, &doff, &dlen, &isz)) return 1;        // not BGZF after all
+                if (dlen == (size_t)-1) break;                                   // partial block: the next chunk starts here
+                if (isz > 65536) return 1;
+                if (text_len + isz > ING_TEXT_CAP) break;
                 if (isz) {
                     CUmemDecompressParams p; memset(&p, 0, sizeof p);
                     p.srcNumBytes = dlen; p.dstNumBytes = isz;
-                    p.dstActBytes = (cuuint32_t *)(g->d_act + g->params.size());
-                    p.src = g->d_comp + used + doff;
+                    p.dstActBytes = (cuuint32_t *)(g->d_act + ch.params.size());
+                    p.src = d_dst + used + doff;
                     p.dst = g->d_text + ING_MAXCARRY + text_len;
                     p.algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
-                    g->params.push_back(p);
+                    ch.params.push_back(p);
                     text_len += isz;
                 }
                 used += bs;
@@ -361,37 +406,32 @@ static int ingest_pass(s2_ingest *g, s2_table *t, int fd, bool bgzf, int col, bo
             used = (size_t)got;
             text_len = used;
         }
-        file_off += (off_t)used;
         eof = (size_t)got < ING_COMP_CHUNK && used == (size_t)got;              // short read and everything consumed
-        // ---- device: H2D, inflate, index, validate, copy, carry ------------------------------------------
-        ing_begin_chunk<<<1, 1, 0, st>>>(g->d_state, text_len, eof ? 1u : 0u, first ? 1u : 0u);
-        if (bgzf) {
-            if (used) CK(cudaMemcpyAsync(g->d_comp, g->h_comp, used, cudaMemcpyHostToDevice, st));
-            if (!g->params.empty()) {
-                size_t err_index = 0;
-                const CUresult r = g->decompress(g->params.data(), g->params.size(), 0, &err_index, (CUstream)st);
-                if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, err_index); return -1; }
-            }
-        } else if (used) {
-            CK(cudaMemcpyAsync(g->d_text + ING_MAXCARRY, g->h_comp, used, cudaMemcpyHostToDevice, st));
-        }
-        ing_terminate_last_line<<<1, 1, 0, st>>>(g->d_text, g->d_state);
-        ing_nl_count<<<text_blocks, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_block_nl);
-        ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_block_nl, text_blocks, nullptr, &g->d_state->n_lines);
-        ing_nl_scatter<<<text_blocks, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_block_nl, g->d_line_end);
-        ing_fastq_prepare<<<1, 1, 0, st>>>(g->d_state);
-        ing_fastq_len<<<c->n_sm * 4, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, scan ? 1 : 0);
-        if (scan) {
-            ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_out, 0, &g->d_state->n_rec, g->d_total);
-            ing_set_flat_len<<<1, 1, 0, st>>>(g->d_state, g->d_total);
-            ing_fastq_copy<<<c->n_sm * 8, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, g->d_flat);
-            s2_launch_scan_count_devlen(g->d_flat, &g->d_state->flat_len, t->v, col, c->d_stats, c->grid_count, st);
-        }
-        ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 0);
-        ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 1);
-        CK(cudaGetLastError());
+        ch.src_off = (size_t)file_off; ch.src_len = used; ch.text_len = text_len; ch.eof = eof;
+        file_off += (off_t)used;
+        if (!cache) CK(cudaStreamSynchronize(st));                               // ch.params (a local) and d_comp are reused
+        if (used) CK(cudaMemcpyAsync(d_dst, h, used, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(g->h_free[buf], st));
+        if (ingest_chunk(g, t, col, scan, bgzf, ch, d_dst, first)) return -1;
+        if (!cache) CK(cudaStreamSynchronize(st));
         first = false;
+        buf ^= 1;
         if (got == 0) break;
+    }
+    CK(cudaMemcpyAsync(g->h_state, g->d_state, sizeof(IngState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return g->h_state->irregular ? 1 : 0;
+}
+
+// second pass when the compressed file is resident on the device: replay the recorded chunks, no host I/O
+static int ingest_pass_cached(s2_ingest *g, s2_table *t, bool bgzf, int col)
+{
+    cudaStream_t st = g->stream;
+    CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), st));
+    bool first = true;
+    for (const auto &ch : g->chunks) {
+        if (ingest_chunk(g, t, col, true, bgzf, ch, g->d_file + ch.src_off, first)) return -1;
+        first = false;
     }
     CK(cudaMemcpyAsync(g->h_state, g->d_state, sizeof(IngState), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -421,8 +461,18 @@ extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, in
     }
     s2_ingest *g = tl_ingest;
     if (bgzf && !g->hw_deflate) { close(fd); return 1; }
-    int rc = ingest_pass(g, t, fd, bgzf, col, false);                // pass 1: prove the file is strict FASTQ
-    if (rc == 0) rc = ingest_pass(g, t, fd, bgzf, col, true);        // pass 2: count
+    // keep the compressed file on the device between the two passes when it fits (S2_INGEST_CACHE_MB, default 2048)
+    struct stat sb;
+    bool cache = fstat(fd, &sb) == 0 && (uint64_t)sb.st_size <= (s2_env_u64("S2_INGEST_CACHE_MB", 2048) << 20);
+    if (cache && (size_t)sb.st_size + ING_COMP_CHUNK > g->d_file_cap) {
+        cudaStreamSynchronize(g->stream);
+        cudaFree(g->d_file); g->d_file = nullptr; g->d_file_cap = 0;
+        const size_t want = (size_t)sb.st_size + ING_COMP_CHUNK + ((size_t)sb.st_size >> 2);
+        if (cudaMalloc((void **)&g->d_file, want) == cudaSuccess) g->d_file_cap = want; else { cudaGetLastError(); cache = false; }
+    }
+    int rc = ingest_pass_host(g, t, fd, bgzf, col, false, cache);    // pass 1: prove the file is strict FASTQ
+    if (rc == 0) rc = cache ? ingest_pass_cached(g, t, bgzf, col)     // pass 2: count
+                            : ingest_pass_host(g, t, fd, bgzf, col, true, false);
     close(fd);
     if (rc == 0) {
         if (bases) *bases = g->h_state->bases;
