@@ -123,6 +123,17 @@ int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
  * s2_batch_submit_count), -1 = error.  Thread safe (one ingest pipeline per calling thread; call
  * s2_ingest_thread_cleanup() before the thread exits). */
 int         s2_ingest_count_file(s2_ctx *ctx, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups);
+/* the detect form: pass 1 of quantify_hits_PE for every read of one file.  len / hits / inf are per record in
+ * file order (ALL records, also those shorter than 31, which the pairing loop needs); inf_* list the informative
+ * windows sorted by (record, offset) with their canonical k-mer.  Arrays are malloc()ed by the call. */
+typedef struct s2_ingest_detect_result {
+    uint64_t n_records, n_inf, bases;
+    uint32_t *len, *hits, *inf;
+    uint32_t *inf_rec, *inf_off;
+    uint64_t *inf_kmer;
+} s2_ingest_detect_result;
+int         s2_ingest_detect_file(s2_ctx *ctx, s2_table *t, const char *path, s2_ingest_detect_result *out);
+void        s2_ingest_detect_free(s2_ingest_detect_result *r);
 void        s2_ingest_thread_cleanup(void);
 
 /* ---------------------------------------------------------------- detect scan --------------- */

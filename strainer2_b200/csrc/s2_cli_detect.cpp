@@ -7,7 +7,7 @@
 // shorter than 31 (src/strain_detect.c:444-448, :497-504) and the ordered emission of
 // pass 2 (:547-623) into one gzip stream ("wb9", :299).
 //
-// Environment: S2_DEVICE (0), S2_DETECT_BATCH_MB (32).
+// Environment: S2_DEVICE (0), S2_DETECT_BATCH_MB (32), S2_GPU_INGEST (1), S2_THREADS (worker threads over batch lines).
 #include "../../include/strainer2_b200.h"
 #include "s2_internal.h"
 
@@ -62,6 +62,7 @@ struct Detect {
     unsigned genome_kmers = 0, genome_informative = 0;
     uint64_t batch_bytes = 32ull << 20;
     std::unordered_set<uint64_t> informative;   // device keys currently labelled INFORMATIVE
+    bool gpu_ingest = true;             // S2_GPU_INGEST: BGZF / plain strict FASTQ are inflated + split on the GPU
     std::mutex stat_mu;
     double t_read = 0, t_gpu = 0, t_emit = 0;   // S2_STATS (summed over worker threads)
     uint64_t n_bases = 0;
@@ -189,6 +190,85 @@ static int background_filter(Detect &d, const char *background_file, unsigned nu
 // one record handed to the GPU
 struct Rec { uint64_t off; uint32_t len; };
 
+// quantify_hits_PE for files that went through the GPU ingest (s2_ingest_detect_file): every record's length,
+// hits and informative hits are already known, so the reference's pairing loop (src/strain_detect.c:443-627)
+// is replayed directly, including what happens when PE2 runs out (stale length, :496-504).
+static int replay_ingested(Detect &d, Job &job, const s2_ingest_detect_result &A, const s2_ingest_detect_result *B, int is_pe)
+{
+    const char *pe1 = job.f1.c_str();
+    const char *pe2 = job.has_f2 ? job.f2.c_str() : nullptr;
+    int h1 = 0, i1 = 0, h2 = 0, i2 = 0;
+    std::vector<std::string> copy_kmers, pe2_kmers;
+    bool have_copy = false;
+    unsigned long long evaluated = 0, reads = 0;
+    uint64_t a = 0, b = 0, pa = 0, pb = 0;
+    uint32_t stale_a = 0, stale_b = 0;                    // kseq's seq.l after the last successful read of each reader
+    char kbuf[S2_K + 1], head[96];
+    auto kmers_of = [&](const s2_ingest_detect_result &X, uint64_t rec, uint64_t &p, std::vector<std::string> &out) {
+        out.clear();
+        while (p < X.n_inf && X.inf_rec[p] < rec) ++p;
+        for (; p < X.n_inf && X.inf_rec[p] == rec; ++p) { s2_kmer_to_ascii(X.inf_kmer[p], kbuf); out.push_back(kbuf); }
+    };
+    auto emit = [&](const std::string &kmer) {
+        job.out += pe1;
+        const int n = snprintf(head, sizeof head, "\t%d\t%d\t%d\t%d\t", h1, i1, h2, i2);
+        job.out.append(head, n);
+        job.out += kmer;
+        job.out += '\n';
+    };
+    int rc = 0;
+    while (a < A.n_records) {                                                        // :443
+        const uint64_t rec1 = a++;
+        const uint32_t len1 = A.len[rec1];
+        stale_a = len1;
+        if (len1 >= S2_K) {                                                          // :444-449
+            ++reads; h1 = (int)A.hits[rec1]; i1 = (int)A.inf[rec1];
+            evaluated += len1 - (S2_K - 1);
+            have_copy = true;
+            kmers_of(A, rec1, pa, copy_kmers);
+        }
+        bool pe2_valid = false; uint64_t rec2 = 0;
+        if (is_pe) {
+            const bool shared = is_pe == IS_PAIRED_END_INTERLEAVE;
+            const s2_ingest_detect_result &S = shared ? A : *B;
+            uint64_t &cur = shared ? a : b;
+            uint32_t &stale = shared ? stale_a : stale_b;
+            int64_t l2 = -1;
+            if (cur < S.n_records) { rec2 = cur++; stale = S.len[rec2]; l2 = stale; }
+            if (stale >= S2_K) {                                                     // :497
+                if (l2 < 0) {                                                        // :501-504
+                    char msg[1024];
+                    snprintf(msg, sizeof msg, "reached end of PE2 (%s) before end of PE1 (%s), check that file names are correct\n",
+                             pe2 ? pe2 : "(null)", pe1);
+                    job.err = msg;
+                    rc = EXIT_FAILURE;
+                    break;
+                }
+                h2 = (int)S.hits[rec2]; i2 = (int)S.inf[rec2];
+                evaluated += stale - (S2_K - 1);
+                pe2_valid = true;
+            }
+        }
+        if (h1 + h2 >= 1 && i1 + i2 >= 1) {                                          // :547
+            if (have_copy) for (const std::string &k : copy_kmers) emit(k);
+            if (pe2_valid) {
+                const bool shared = is_pe == IS_PAIRED_END_INTERLEAVE;
+                kmers_of(shared ? A : *B, rec2, shared ? pa : pb, pe2_kmers);
+                for (const std::string &k : pe2_kmers) emit(k);
+            }
+        }
+    }
+    if (rc == 0) {
+        char foot[4][512];
+        snprintf(foot[0], sizeof foot[0], "#%s\ttotal_kmer_evaluated\t%lld\n", pe1, (long long)evaluated);
+        snprintf(foot[1], sizeof foot[1], "#%s\ttotal_reads_evaluated\t%lld\n", pe1, (long long)reads);
+        snprintf(foot[2], sizeof foot[2], "#%s\ttotal_genome_kmers\t%lld\n", pe1, (long long)d.genome_kmers);
+        snprintf(foot[3], sizeof foot[3], "#%s\ttotal_genome_informative_kmers\t%lld\n", pe1, (long long)d.genome_informative);
+        for (auto &f : foot) job.out += f;
+    }
+    return rc;
+}
+
 // quantify_hits_PE (src/strain_detect.c:387-663).  Returns 0 or EXIT_FAILURE (message already printed).
 static int quantify_hits(Detect &d, Job &job)
 {
@@ -197,6 +277,28 @@ static int quantify_hits(Detect &d, Job &job)
     const int is_pe = job.pe;
     char msg[1024];
     double t_read = 0, t_gpu = 0, t_emit = 0; uint64_t n_bases = 0;
+    // ---- GPU ingest: BGZF / plain strict FASTQ never reach the host parser ------------------------------
+    if (d.gpu_ingest && !d.exotic) {
+        const auto tI = std::chrono::steady_clock::now();
+        s2_ingest_detect_result A, B;
+        memset(&A, 0, sizeof A); memset(&B, 0, sizeof B);
+        int ra = s2_ingest_detect_file(d.ctx, d.table, pe1, &A), rb = 0;
+        if (ra == 0 && is_pe == IS_PAIRED_END) rb = s2_ingest_detect_file(d.ctx, d.table, pe2, &B);
+        if (ra < 0 || rb < 0) { job.err = std::string(s2_last_error()) + "\n"; s2_ingest_detect_free(&A); s2_ingest_detect_free(&B); return EXIT_FAILURE; }
+        if (ra == 0 && rb == 0) {
+            const auto tJ = std::chrono::steady_clock::now();
+            const int rc = replay_ingested(d, job, A, is_pe == IS_PAIRED_END ? &B : nullptr, is_pe);
+            {
+                std::lock_guard<std::mutex> g(d.stat_mu);
+                d.t_gpu += std::chrono::duration<double>(tJ - tI).count();
+                d.t_emit += std::chrono::duration<double>(std::chrono::steady_clock::now() - tJ).count();
+                d.n_bases += A.bases + B.bases;
+            }
+            s2_ingest_detect_free(&A); s2_ingest_detect_free(&B);
+            return rc;
+        }
+        s2_ingest_detect_free(&A); s2_ingest_detect_free(&B);          // not strict FASTQ / not BGZF: the host parser below
+    }
     s2_reader *r1 = s2_reader_open(pe1), *r2 = nullptr;
     if (!r1) {
         snprintf(msg, sizeof msg, "could not read file (read1) %s in quantify_hits_PE() (error: %s)\n", pe1, strerror(errno));
@@ -419,6 +521,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     }
     Detect d;
     d.batch_bytes = s2_env_u64("S2_DETECT_BATCH_MB", 32) << 20;
+    d.gpu_ingest = s2_env_int("S2_GPU_INGEST", 1) != 0;
     const int n_threads = s2_default_reader_threads();
     d.ctx = background_file ? s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 16) << 20, n_threads + 2)
                             : s2_init(s2_env_int("S2_DEVICE", 0), 8u << 20, 2);
@@ -499,6 +602,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
                 { std::lock_guard<std::mutex> g(mu); jobs[i].done = true; }
                 cv.notify_all();
             }
+            s2_ingest_thread_cleanup();
         };
         const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(jobs.size(), (size_t)s2_default_reader_threads()));
         std::vector<std::thread> pool;

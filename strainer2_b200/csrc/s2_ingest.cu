@@ -30,6 +30,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -46,6 +48,7 @@ struct IngState {                 // lives in device memory, one per ingest obje
     unsigned long long bases, lookups, records;   // totals over the file (pass 2)
     unsigned int n_lines, n_rec;
     unsigned int irregular;       // sticky: the file is not strict FASTQ
+    unsigned int inf_overflow;    // a chunk produced more informative windows than the chunk list holds
     unsigned int last_chunk;
 };
 
@@ -232,6 +235,54 @@ __global__ void ing_terminate_last_line(uint8_t *text, IngState *st)
 
 __global__ void ing_set_flat_len(IngState *st, const unsigned *total) { st->flat_len = *total; }
 
+// ---- detect mode (strain_detect pass 1 on ingested reads) ------------------------------------------
+__global__ void __launch_bounds__(ING_THREADS) ing_make_rec_off(const IngState *st, const unsigned *__restrict__ out_off, unsigned long long *__restrict__ rec_off)
+{
+    const unsigned n_rec = st->n_rec;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_rec; r += gridDim.x * blockDim.x)
+        rec_off[r] = r < n_rec ? out_off[r] : st->flat_len;
+}
+
+// per-record results of this chunk -> the file-level arrays (record numbering continues across chunks)
+__global__ void __launch_bounds__(ING_THREADS) ing_store_records(const IngState *st, const unsigned *__restrict__ line_end, const unsigned *__restrict__ hits_c,
+                                                                  const unsigned *__restrict__ inf_c, unsigned *__restrict__ len_all,
+                                                                  unsigned *__restrict__ hits_all, unsigned *__restrict__ inf_all, unsigned long long cap)
+{
+    const unsigned n_rec = st->n_rec;
+    const unsigned long long base = st->records;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+        if (base + r >= cap) break;
+        len_all[base + r] = line_end[4 * r + 1] - (line_end[4 * r] + 1);
+        hits_all[base + r] = hits_c[r];
+        inf_all[base + r] = inf_c[r];
+    }
+}
+
+// informative windows of this chunk (byte offsets in the flat batch) -> (record number, offset, canonical k-mer)
+__global__ void __launch_bounds__(ING_THREADS) ing_collect_inf(IngState *st, const uint8_t *__restrict__ flat, const unsigned long long *__restrict__ rec_off,
+                                                                const unsigned long long *__restrict__ pos_c, const unsigned long long *__restrict__ cnt_c,
+                                                                unsigned long long cap_c, unsigned *__restrict__ f_rec, unsigned *__restrict__ f_off,
+                                                                unsigned long long *__restrict__ f_kmer, unsigned long long *__restrict__ f_cnt, unsigned long long cap_f)
+{
+    const unsigned long long n = *cnt_c;
+    if (n > cap_c) { if (blockIdx.x == 0 && threadIdx.x == 0) st->inf_overflow = 1; }
+    const unsigned n_rec = st->n_rec;
+    const unsigned long long base = st->records;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap_c; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long pos = pos_c[i];
+        unsigned lo = 0, hi = n_rec;
+        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (rec_off[mid] <= pos) lo = mid; else hi = mid; }
+        unsigned long long fwd = 0;
+        for (int b = 0; b < S2_K; ++b) {
+            const unsigned c = flat[pos + b];
+            const unsigned x = (c >> 1) & 3u;
+            fwd = (fwd << 2) | (x ^ (x >> 1));
+        }
+        const unsigned long long at = atomicAdd(f_cnt, 1ull);
+        if (at < cap_f) { f_rec[at] = (unsigned)(base + lo); f_off[at] = (unsigned)(pos - rec_off[lo]); f_kmer[at] = s2_canonical(fwd, s2_revcomp31(fwd)); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -248,6 +299,11 @@ struct s2_ingest {
     IngState *d_state = nullptr, *h_state = nullptr;
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
+    // detect mode: chunk-local and file-level result arrays
+    unsigned *d_hits_c = nullptr, *d_inf_c = nullptr;
+    unsigned long long *d_rec_off = nullptr, *d_pos_c = nullptr, *d_cnt_c = nullptr, *d_fcnt = nullptr;
+    unsigned *d_len_all = nullptr, *d_hits_all = nullptr, *d_inf_all = nullptr; unsigned long long rec_cap = 0;
+    unsigned *d_frec = nullptr, *d_foff = nullptr; unsigned long long *d_fkmer = nullptr; unsigned long long f_cap = 0;
     struct Chunk { std::vector<CUmemDecompressParams> params; size_t src_off = 0, src_len = 0, text_len = 0; bool eof = false; };
     std::vector<Chunk> chunks;                         // pass 1 records them, pass 2 replays them without touching the host
 };
@@ -261,6 +317,8 @@ static void ingest_free(s2_ingest *g)
     cudaFree(g->d_file); cudaFree(g->d_comp); cudaFree(g->d_text); cudaFree(g->d_flat); cudaFree(g->d_carry);
     cudaFree(g->d_block_nl); cudaFree(g->d_line_end); cudaFree(g->d_out); cudaFree(g->d_total); cudaFree(g->d_act);
     cudaFree(g->d_state); cudaFreeHost(g->h_state);
+    cudaFree(g->d_hits_c); cudaFree(g->d_inf_c); cudaFree(g->d_rec_off); cudaFree(g->d_pos_c); cudaFree(g->d_cnt_c); cudaFree(g->d_fcnt);
+    cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all); cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);
     delete g;
 }
 
@@ -330,8 +388,12 @@ static bool is_bgzf_header(const uint8_t *p, ssize_t n)
 
 // device work for one chunk whose bytes are already on the device: inflate (or copy), index, validate,
 // and - when scan is set - copy the sequence lines out and count them
-static int ingest_chunk(s2_ingest *g, s2_table *t, int col, bool scan, bool bgzf, const s2_ingest::Chunk &ch, const uint8_t *d_src, bool first)
+#define ING_CAP_C (8ull << 20)        /* informative windows one chunk may report */
+enum { ING_VALIDATE = 0, ING_COUNT = 1, ING_DETECT = 2 };
+
+static int ingest_chunk(s2_ingest *g, s2_table *t, int col, int mode, bool bgzf, const s2_ingest::Chunk &ch, const uint8_t *d_src, bool first)
 {
+    const bool scan = mode != ING_VALIDATE;
     s2_ctx *c = g->ctx;
     cudaStream_t st = g->stream;
     const unsigned text_blocks = (unsigned)(((size_t)ING_MAXCARRY + ING_TEXT_CAP) / 4096 + 1);
@@ -355,7 +417,23 @@ static int ingest_chunk(s2_ingest *g, s2_table *t, int col, bool scan, bool bgzf
         ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_out, 0, &g->d_state->n_rec, g->d_total);
         ing_set_flat_len<<<1, 1, 0, st>>>(g->d_state, g->d_total);
         ing_fastq_copy<<<c->n_sm * 8, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, g->d_flat);
-        s2_launch_scan_count_devlen(g->d_flat, &g->d_state->flat_len, t->v, col, c->d_stats, c->grid_count, st);
+        if (mode == ING_COUNT) {
+            s2_launch_scan_count_devlen(g->d_flat, &g->d_state->flat_len, t->v, col, c->d_stats, c->grid_count, st);
+        } else {
+            const size_t max_rec = (size_t)ING_MAX_LINES / 4 + 4;
+            ing_make_rec_off<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_out, g->d_rec_off);
+            CK(cudaMemsetAsync(g->d_hits_c, 0, max_rec * sizeof(unsigned), st));
+            CK(cudaMemsetAsync(g->d_inf_c, 0, max_rec * sizeof(unsigned), st));
+            CK(cudaMemsetAsync(g->d_cnt_c, 0, sizeof(unsigned long long), st));
+            S2DetectOut out;
+            out.rec_off = (const uint64_t *)g->d_rec_off; out.n_rec = 0; out.n_rec_dev = &g->d_state->n_rec; out.n_bytes_dev = &g->d_state->flat_len;
+            out.read_hits = g->d_hits_c; out.read_inf = g->d_inf_c; out.inf_pos = (uint64_t *)g->d_pos_c; out.inf_count = g->d_cnt_c; out.inf_cap = ING_CAP_C;
+            s2_launch_scan_detect_dev(g->d_flat, t->v, out, c->d_stats, c->grid_detect, st);
+            ing_collect_inf<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_flat, g->d_rec_off, g->d_pos_c, g->d_cnt_c, ING_CAP_C,
+                                                                  g->d_frec, g->d_foff, g->d_fkmer, g->d_fcnt, g->f_cap);
+            ing_store_records<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_line_end, g->d_hits_c, g->d_inf_c, g->d_len_all, g->d_hits_all,
+                                                                    g->d_inf_all, g->rec_cap);
+        }
     }
     ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 0);
     ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 1);
@@ -366,7 +444,7 @@ static int ingest_chunk(s2_ingest *g, s2_table *t, int col, bool scan, bool bgzf
 // Pass over the file FROM THE HOST: read() chunks of whole BGZF blocks (or of raw text) into two alternating
 // pinned buffers, copy them to the device (into the file cache when the file fits, so that the second pass
 // needs no I/O), and run the device stage.  Returns 0 ok, 1 irregular / unsupported, -1 error.
-static int ingest_pass_host(s2_ingest *g, s2_table *t, int fd, bool bgzf, int col, bool scan, bool cache)
+static int ingest_pass_host(s2_ingest *g, s2_table *t, int fd, bool bgzf, int col, int mode, bool cache)
 {
     cudaStream_t st = g->stream;
     CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), st));
@@ -412,7 +490,7 @@ static int ingest_pass_host(s2_ingest *g, s2_table *t, int fd, bool bgzf, int co
         if (!cache) CK(cudaStreamSynchronize(st));                               // ch.params (a local) and d_comp are reused
         if (used) CK(cudaMemcpyAsync(d_dst, h, used, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(g->h_free[buf], st));
-        if (ingest_chunk(g, t, col, scan, bgzf, ch, d_dst, first)) return -1;
+        if (ingest_chunk(g, t, col, mode, bgzf, ch, d_dst, first)) return -1;
         if (!cache) CK(cudaStreamSynchronize(st));
         first = false;
         buf ^= 1;
@@ -424,13 +502,13 @@ static int ingest_pass_host(s2_ingest *g, s2_table *t, int fd, bool bgzf, int co
 }
 
 // second pass when the compressed file is resident on the device: replay the recorded chunks, no host I/O
-static int ingest_pass_cached(s2_ingest *g, s2_table *t, bool bgzf, int col)
+static int ingest_pass_cached(s2_ingest *g, s2_table *t, bool bgzf, int col, int mode)
 {
     cudaStream_t st = g->stream;
     CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), st));
     bool first = true;
     for (const auto &ch : g->chunks) {
-        if (ingest_chunk(g, t, col, true, bgzf, ch, g->d_file + ch.src_off, first)) return -1;
+        if (ingest_chunk(g, t, col, mode, bgzf, ch, g->d_file + ch.src_off, first)) return -1;
         first = false;
     }
     CK(cudaMemcpyAsync(g->h_state, g->d_state, sizeof(IngState), cudaMemcpyDeviceToHost, st));
@@ -440,13 +518,10 @@ static int ingest_pass_cached(s2_ingest *g, s2_table *t, bool bgzf, int col)
 
 static thread_local s2_ingest *tl_ingest = nullptr;
 
-// GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed or plain strict
-// FASTQ.  Returns 0 = done (counters updated, *bases / *lookups set), 1 = not handled (nothing was counted: use
-// the host reader), -1 = error.
-extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups)
+// open + classify a file for the GPU path and make sure this thread's pipeline (and its file cache) exists.
+// Returns 0 ready, 1 not eligible, -1 error.
+static int ingest_open(s2_ctx *c, const char *path, int *fd_out, bool *bgzf_out, bool *cache_out, s2_ingest **g_out)
 {
-    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
-    if (t->partitioned) return 1;                                    // union tables keep the host reader + two-phase scan
     const int fd = open(path, O_RDONLY);
     if (fd < 0) return 1;
     uint8_t head[32];
@@ -470,15 +545,103 @@ extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, in
         const size_t want = (size_t)sb.st_size + ING_COMP_CHUNK + ((size_t)sb.st_size >> 2);
         if (cudaMalloc((void **)&g->d_file, want) == cudaSuccess) g->d_file_cap = want; else { cudaGetLastError(); cache = false; }
     }
-    int rc = ingest_pass_host(g, t, fd, bgzf, col, false, cache);    // pass 1: prove the file is strict FASTQ
-    if (rc == 0) rc = cache ? ingest_pass_cached(g, t, bgzf, col)     // pass 2: count
-                            : ingest_pass_host(g, t, fd, bgzf, col, true, false);
+    *fd_out = fd; *bgzf_out = bgzf; *cache_out = cache; *g_out = g;
+    return 0;
+}
+
+// GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed or plain strict
+// FASTQ.  Returns 0 = done (counters updated, *bases / *lookups set), 1 = not handled (nothing was counted: use
+// the host reader), -1 = error.
+extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups)
+{
+    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
+    if (t->partitioned) return 1;                                    // union tables keep the host reader + two-phase scan
+    int fd; bool bgzf, cache; s2_ingest *g;
+    int rc = ingest_open(c, path, &fd, &bgzf, &cache, &g);
+    if (rc) return rc;
+    rc = ingest_pass_host(g, t, fd, bgzf, col, ING_VALIDATE, cache);             // pass 1: prove the file is strict FASTQ
+    if (rc == 0) rc = cache ? ingest_pass_cached(g, t, bgzf, col, ING_COUNT)      // pass 2: count
+                            : ingest_pass_host(g, t, fd, bgzf, col, ING_COUNT, false);
     close(fd);
     if (rc == 0) {
         if (bases) *bases = g->h_state->bases;
         if (lookups) *lookups = g->h_state->lookups;
     }
     return rc;
+}
+
+// Pass 1 of quantify_hits_PE (src/strain_detect.c:465-491) for every read of one file, inflated and split on the
+// GPU.  out->len / hits / inf are per record in file order (all records, also those shorter than 31);
+// out->inf_* list the informative windows sorted by (record, offset) with their canonical k-mer.  The arrays are
+// malloc()ed here and released by s2_ingest_detect_free.  Returns 0 / 1 (not handled) / -1 like the count form.
+extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s2_ingest_detect_result *out)
+{
+    memset(out, 0, sizeof *out);
+    if (t->partitioned) return 1;
+    int fd; bool bgzf, cache; s2_ingest *g;
+    int rc = ingest_open(c, path, &fd, &bgzf, &cache, &g);
+    if (rc) return rc;
+    rc = ingest_pass_host(g, t, fd, bgzf, 0, ING_VALIDATE, cache);
+    if (rc) { close(fd); return rc; }
+    const unsigned long long n_rec = g->h_state->records;
+    const size_t max_rec = (size_t)ING_MAX_LINES / 4 + 4;
+    auto dev_alloc = [](void **p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
+    if (dev_alloc((void **)&g->d_hits_c, max_rec * 4) || dev_alloc((void **)&g->d_inf_c, max_rec * 4) ||
+        dev_alloc((void **)&g->d_rec_off, (max_rec + 1) * 8) || dev_alloc((void **)&g->d_pos_c, (ING_CAP_C + 1) * 8) ||
+        dev_alloc((void **)&g->d_cnt_c, 8) || dev_alloc((void **)&g->d_fcnt, 8)) { s2_set_error("out of device memory"); close(fd); return -1; }
+    if (n_rec + 1 > g->rec_cap) {
+        cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all);
+        g->d_len_all = g->d_hits_all = g->d_inf_all = nullptr;
+        g->rec_cap = n_rec + n_rec / 8 + 1024;
+        if (cudaMalloc((void **)&g->d_len_all, g->rec_cap * 4) || cudaMalloc((void **)&g->d_hits_all, g->rec_cap * 4) ||
+            cudaMalloc((void **)&g->d_inf_all, g->rec_cap * 4)) { s2_set_error("out of device memory"); g->rec_cap = 0; close(fd); return -1; }
+    }
+    unsigned long long n_inf = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!g->d_frec) {
+            if (!g->f_cap) g->f_cap = 1ull << 20;
+            if (cudaMalloc((void **)&g->d_frec, g->f_cap * 4) || cudaMalloc((void **)&g->d_foff, g->f_cap * 4) ||
+                cudaMalloc((void **)&g->d_fkmer, g->f_cap * 8)) { s2_set_error("out of device memory"); close(fd); return -1; }
+        }
+        CK(cudaMemsetAsync(g->d_fcnt, 0, 8, g->stream));
+        rc = cache ? ingest_pass_cached(g, t, bgzf, 0, ING_DETECT) : ingest_pass_host(g, t, fd, bgzf, 0, ING_DETECT, false);
+        if (rc) break;
+        CK(cudaMemcpy(&n_inf, g->d_fcnt, 8, cudaMemcpyDeviceToHost));
+        if (g->h_state->inf_overflow) { rc = 1; break; }                         // absurdly dense chunk: host path
+        if (n_inf <= g->f_cap) break;
+        cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);          // list too small: grow and run the pass again
+        g->d_frec = g->d_foff = nullptr; g->d_fkmer = nullptr;
+        g->f_cap = n_inf + n_inf / 8 + 1024;
+        rc = 2;
+    }
+    close(fd);
+    if (rc) return rc == 2 ? -1 : rc;
+    out->n_records = n_rec; out->n_inf = n_inf; out->bases = g->h_state->bases;
+    out->len = (uint32_t *)malloc((n_rec + 1) * 4); out->hits = (uint32_t *)malloc((n_rec + 1) * 4); out->inf = (uint32_t *)malloc((n_rec + 1) * 4);
+    out->inf_rec = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_off = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_kmer = (uint64_t *)malloc((n_inf + 1) * 8);
+    CK(cudaMemcpy(out->len, g->d_len_all, n_rec * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->hits, g->d_hits_all, n_rec * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->inf, g->d_inf_all, n_rec * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->inf_rec, g->d_frec, n_inf * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->inf_off, g->d_foff, n_inf * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->inf_kmer, g->d_fkmer, n_inf * 8, cudaMemcpyDeviceToHost));
+    // the kernels append in arbitrary order: sort by (record, offset) = the order pass 2 prints them
+    std::vector<uint32_t> perm(n_inf);
+    for (uint32_t i = 0; i < n_inf; ++i) perm[i] = i;
+    std::sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
+        return out->inf_rec[a] != out->inf_rec[b] ? out->inf_rec[a] < out->inf_rec[b] : out->inf_off[a] < out->inf_off[b];
+    });
+    std::vector<uint32_t> r2(n_inf), o2(n_inf); std::vector<uint64_t> k2(n_inf);
+    for (uint64_t i = 0; i < n_inf; ++i) { r2[i] = out->inf_rec[perm[i]]; o2[i] = out->inf_off[perm[i]]; k2[i] = out->inf_kmer[perm[i]]; }
+    if (n_inf) { memcpy(out->inf_rec, r2.data(), n_inf * 4); memcpy(out->inf_off, o2.data(), n_inf * 4); memcpy(out->inf_kmer, k2.data(), n_inf * 8); }
+    return 0;
+}
+
+extern "C" void s2_ingest_detect_free(s2_ingest_detect_result *r)
+{
+    if (!r) return;
+    free(r->len); free(r->hits); free(r->inf); free(r->inf_rec); free(r->inf_off); free(r->inf_kmer);
+    memset(r, 0, sizeof *r);
 }
 
 extern "C" void s2_ingest_thread_cleanup(void)

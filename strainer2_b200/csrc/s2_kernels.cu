@@ -231,6 +231,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
     constexpr int NG = 16 / G;
     if (run_if && *run_if == 0) return;            // fallback launch after a partition overflow: normally a no-op
     if (n_bytes_dev) n_bytes = *n_bytes_dev;       // batch produced on the device (GPU ingest): its length lives there
+    if (MODE == S2_MODE_DETECT && dout.n_rec_dev) { dout.n_rec = *dout.n_rec_dev; n_bytes = *dout.n_bytes_dev; }
     __shared__ uint64_t q_canon_s[S2_WARPS][S2_QCAP];
     __shared__ uint32_t q_slot_s[S2_WARPS][S2_QCAP];
     __shared__ uint64_t q_pos_s[MODE == S2_MODE_DETECT ? S2_WARPS : 1][MODE == S2_MODE_DETECT ? S2_QCAP : 1];
@@ -415,6 +416,13 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
     g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, nullptr, out, stats, nullptr, nullptr);
 }
 
+
+// detect scan of a batch that was produced on the device (GPU ingest): lengths are in device memory
+void s2_launch_scan_detect_dev(const uint8_t *bases, const S2TableView &t, const S2DetectOut &out, unsigned long long *stats,
+                               int grid_blocks, cudaStream_t stream)
+{
+    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, 0, t, nullptr, out, stats, nullptr, nullptr);
+}
 
 // ------------------------------------------------------------------------------------------------
 // two-phase count scan for tables whose fingerprints do not fit L2 (multi-strain union tables)

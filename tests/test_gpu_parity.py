@@ -549,3 +549,57 @@ def test_executable_with_bgzf_inputs_matches_oracle(s2, golden_dir, tmp_path):
         p = s2.run_kmer_scrub_count(args, cwd=tmp, env=env)
         assert p.returncode == 0, p.stderr
         assert p.stdout == o.stdout, env
+
+
+def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_path):
+    """strain_detect on BGZF / plain FASTQ (GPU ingest) with reads shorter than 31 sprinkled in (the reference's
+    stale-state behaviour), SE + PE + PEI lines, a PE2 that ends early on a short read (silent) and one that
+    ends early on a long read (error exit)"""
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    rng = synth.rng_for(8, 0)
+    strain = synth.genome(rng, 200_000, 4, n_runs=2)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    clean = [np.where(c == ord("N"), ord("G"), c).astype(np.uint8) for c in strain]
+    c0 = clean[0].tobytes()
+    with open(os.path.join(tmp, "inf.txt"), "wb") as f:
+        for i in range(0, len(c0) - 31, 60):
+            f.write(c0[i:i + 31] + b"\n")
+
+    def fq(reads, shorten_every, seed):
+        r = np.random.default_rng(seed)
+        out = []
+        for i, x in enumerate(reads):
+            s = x.tobytes()
+            if i % shorten_every == 3:
+                s = s[:int(r.choice([0, 7, 30]))]
+            out.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+        return out
+
+    r1 = fq(synth.sample_reads(rng, clean + synth.genome(rng, 200_000, 2), 6000, 120, sub_rate=0.004, n_rate=3e-4), 9, 1)
+    r2 = fq(synth.sample_reads(rng, clean + synth.genome(rng, 200_000, 2), 6000, 120, sub_rate=0.004, n_rate=3e-4), 11, 2)
+    synth.write_bgzf(os.path.join(tmp, "a_R1.fastq.gz"), b"".join(r1))
+    synth.write_bgzf(os.path.join(tmp, "a_R2.fastq.gz"), b"".join(r2))
+    open(os.path.join(tmp, "b_se.fastq"), "wb").write(b"".join(r1[:3000]))
+    inter = [x for pair in zip(r1[:2000], r2[:2000]) for x in pair] + [r1[2000]]          # odd count: PE2 runs out
+    synth.write_bgzf(os.path.join(tmp, "c_inter.fastq.gz"), b"".join(inter[:-1]))
+    # PE2 shorter than PE1 and ending on a short (stale < 31) read: the reference silently keeps going
+    synth.write_bgzf(os.path.join(tmp, "d_R2_short.fastq.gz"), b"".join(r2[:1500]) + b"@s\nACGT\n+\nIIII\n")
+    open(os.path.join(tmp, "batch.txt"), "w").write(
+        "PE\ta_R1.fastq.gz\ta_R2.fastq.gz\nSE\tb_se.fastq\nPEI\tc_inter.fastq.gz\nPE\ta_R1.fastq.gz\td_R2_short.fastq.gz\nse\ta_R2.fastq.gz\n")
+    args = ["-r", "strain.fa", "-a", "inf.txt", "-B", "batch.txt"]
+    o = ou.oracle_cli(["detect"] + args + ["-m", os.path.join(tmp, "msg")], cwd=tmp)
+    assert o.returncode == 0, o.stderr
+    assert o.stdout.count(b"\n") > 500
+    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1"}):
+        out = os.path.join(tmp, "hits.gz")
+        p = s2.run_strain_detect(args + ["-o", out], cwd=tmp, env=env)
+        assert p.returncode == 0, p.stderr
+        assert ou.gunzip(out) == o.stdout, env
+        assert p.stdout == open(os.path.join(tmp, "msg"), "rb").read()
+    # PE2 ends early on a long read: error exit with the reference's message
+    synth.write_bgzf(os.path.join(tmp, "e_R2.fastq.gz"), b"".join(x for x in r2[:100] if len(x) > 200))
+    o = ou.oracle_cli(["detect", "-r", "strain.fa", "-a", "inf.txt", "-b", "a_R1.fastq.gz", "-c", "e_R2.fastq.gz", "-t", "PE", "-m", os.path.join(tmp, "m2")], cwd=tmp)
+    p = s2.run_strain_detect(["-r", "strain.fa", "-a", "inf.txt", "-b", "a_R1.fastq.gz", "-c", "e_R2.fastq.gz", "-t", "PE", "-o", os.path.join(tmp, "x.gz")], cwd=tmp)
+    assert o.returncode == 1 and p.returncode == 1
+    assert p.stderr == o.stderr
