@@ -98,6 +98,14 @@ def main():
     t1 = time.time()
     p = subprocess.run([dexe, "-r", "strain.fa", "-a", "inf.txt", "-B", "batch.txt", "-o", "hits.gz"], cwd=tmp, env=env, capture_output=True)
     print(f"strain_detect rc={p.returncode} wall={time.time() - t1:.2f}s {p.stderr.decode().strip()[-400:]}", flush=True)
+    if len(Bz) >= 4:
+        open(os.path.join(tmp, "batchz.txt"), "w").write("".join(f"SE\t{b}\n" for b in Bz[:2]) + f"PE\t{Bz[2]}\t{Bz[3]}\n")
+        t1 = time.time()
+        p = subprocess.run([dexe, "-r", "strain.fa", "-a", "inf.txt", "-B", "batchz.txt", "-o", "hitsz.gz"], cwd=tmp, env=env, capture_output=True)
+        print(f"strain_detect_bgzf_gpu_ingest rc={p.returncode} wall={time.time() - t1:.2f}s {p.stderr.decode().strip()[-400:]}", flush=True)
+        import gzip
+        a = gzip.open(os.path.join(tmp, "hits.gz")).read().replace(b".fastq.gz", b".fastq.bgz")
+        print("kmer_hits from .gz and .bgz identical (file names aside):", a == gzip.open(os.path.join(tmp, "hitsz.gz")).read(), flush=True)
     ref = os.path.join(ROOT, "oracle", "_ref", "kmer_scrub_count")
     if args.ref_genomes and os.path.exists(ref):
         open(os.path.join(tmp, "A_small.txt"), "w").write("".join(a + "\n" for a in A[:args.ref_genomes]))
