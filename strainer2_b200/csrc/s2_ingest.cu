@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 #include <fcntl.h>
+#include <zlib.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -49,7 +50,9 @@ struct IngState {                 // lives in device memory, one per ingest obje
     unsigned int n_lines, n_rec;
     unsigned int irregular;       // sticky: the file is not strict FASTQ
     unsigned int inf_overflow;    // a chunk produced more informative windows than the chunk list holds
-    unsigned int last_chunk;
+    unsigned int last_chunk, first_chunk;
+    unsigned int tail_len;        // FASTA: last bytes of the previous chunk's flat stream, re-scanned in front of this one
+    unsigned char tail[32];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -220,7 +223,8 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_finish(uint8_t *__restr
 
 __global__ void ing_begin_chunk(IngState *st, unsigned long long new_bytes, unsigned last_chunk, unsigned first_chunk)
 {
-    if (first_chunk) st->carry_len = 0;
+    if (first_chunk) { st->carry_len = 0; st->tail_len = 0; }
+    st->first_chunk = first_chunk;
     st->t0 = ING_MAXCARRY - st->carry_len;
     st->t1 = ING_MAXCARRY + new_bytes;
     st->last_chunk = last_chunk;
@@ -234,6 +238,79 @@ __global__ void ing_terminate_last_line(uint8_t *text, IngState *st)
 }
 
 __global__ void ing_set_flat_len(IngState *st, const unsigned *total) { st->flat_len = *total; }
+
+// ------------------------------------------------------------------------------------------------
+// strict FASTA: '>' lines are headers, every other line is sequence (joined), nothing else
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ING_THREADS) ing_fasta_len(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ line_end,
+                                                              unsigned *__restrict__ out_len, int count_stats)
+{
+    const unsigned n_lines = st->n_lines;
+    unsigned long long bases = 0, recs = 0;
+    for (unsigned L = blockIdx.x * blockDim.x + threadIdx.x; L < n_lines; L += gridDim.x * blockDim.x) {
+        const unsigned long long s0 = L ? (unsigned long long)line_end[L - 1] + 1 : st->t0;
+        const unsigned len = line_end[L] - (unsigned)s0;
+        const uint8_t first = len ? text[s0] : 0;
+        const bool header = first == '>';
+        if (first == '@' || first == '+') atomicOr(&st->irregular, 1u);              // the reference's parser would switch to FASTQ rules
+        if (L == 0 && st->first_chunk && !header) atomicOr(&st->irregular, 1u);       // text before the first record
+        out_len[L] = header ? 1u : len;                                               // a header becomes the record separator
+        if (header) ++recs; else bases += len;
+    }
+    if (count_stats) {
+        if (bases) atomicAdd(&st->bases, bases);
+        if (recs) atomicAdd(&st->records, recs);
+    }
+}
+
+__global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ line_end,
+                                                               const unsigned *__restrict__ out_off, uint8_t *__restrict__ flat)
+{
+    const unsigned n_lines = st->n_lines, tail = st->tail_len;
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (warp == 0) for (unsigned i = lane; i < tail; i += 32) flat[i] = st->tail[i];
+    for (unsigned L = warp; L < n_lines; L += n_warps) {
+        const unsigned long long s0 = L ? (unsigned long long)line_end[L - 1] + 1 : st->t0;
+        const unsigned len = line_end[L] - (unsigned)s0;
+        uint8_t *dst = flat + tail + out_off[L];
+        if (len && text[s0] == '>') { if (lane == 0) dst[0] = '\n'; continue; }
+        for (unsigned i = lane; i < len; i += 32) dst[i] = text[s0 + i];
+    }
+}
+
+__global__ void ing_fasta_set_flat_len(IngState *st, const unsigned *total) { st->flat_len = (unsigned long long)st->tail_len + *total; }
+
+// end of a FASTA chunk: carry the partial last line, remember the last 30 bytes of the flat stream
+__global__ void __launch_bounds__(ING_THREADS) ing_fasta_finish(uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ line_end,
+                                                                 uint8_t *__restrict__ carry_tmp, const uint8_t *__restrict__ flat, int phase, int scan)
+{
+    __shared__ unsigned long long c_from, c_len;
+    if (threadIdx.x == 0) {
+        const unsigned n_lines = st->n_lines;
+        c_from = n_lines ? (unsigned long long)line_end[n_lines - 1] + 1 : st->t0;
+        c_len = st->t1 - c_from;
+        if (c_len > ING_MAXCARRY) { st->irregular = 1; c_len = 0; }
+    }
+    __syncthreads();
+    if (phase == 0) {
+        for (unsigned long long i = threadIdx.x; i < c_len; i += blockDim.x) carry_tmp[i] = text[c_from + i];
+    } else {
+        for (unsigned long long i = threadIdx.x; i < c_len; i += blockDim.x) text[ING_MAXCARRY - c_len + i] = carry_tmp[i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st->carry_len = c_len;
+            if (scan) {
+                const unsigned long long fl = st->flat_len;
+                const unsigned keep = fl < (S2_K - 1) ? (unsigned)fl : (S2_K - 1);
+                unsigned char tmp[32];
+                for (unsigned i = 0; i < keep; ++i) tmp[i] = flat[fl - keep + i];
+                for (unsigned i = 0; i < keep; ++i) st->tail[i] = tmp[i];
+                st->tail_len = keep;
+            }
+        }
+    }
+}
 
 // ---- detect mode (strain_detect pass 1 on ingested reads) ------------------------------------------
 __global__ void __launch_bounds__(ING_THREADS) ing_make_rec_off(const IngState *st, const unsigned *__restrict__ out_off, unsigned long long *__restrict__ rec_off)
@@ -299,6 +376,7 @@ struct s2_ingest {
     IngState *d_state = nullptr, *h_state = nullptr;
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
+    bool fasta = false;                // format of the file being ingested (strict FASTA instead of strict FASTQ)
     // detect mode: chunk-local and file-level result arrays
     unsigned *d_hits_c = nullptr, *d_inf_c = nullptr;
     unsigned long long *d_rec_off = nullptr, *d_pos_c = nullptr, *d_cnt_c = nullptr, *d_fcnt = nullptr;
@@ -338,7 +416,7 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     const size_t n_blocks = ((size_t)ING_MAXCARRY + ING_TEXT_CAP) / 4096 + 2;
     CK(cudaMalloc((void **)&g->d_block_nl, n_blocks * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_line_end, (size_t)ING_MAX_LINES * sizeof(unsigned)));
-    CK(cudaMalloc((void **)&g->d_out, ((size_t)ING_MAX_LINES / 4 + 4) * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&g->d_out, ((size_t)ING_MAX_LINES + 4) * sizeof(unsigned)));     // per record (FASTQ) or per line (FASTA)
     CK(cudaMalloc((void **)&g->d_total, 4 * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_act, (ING_TEXT_CAP / 256) * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_state, sizeof(IngState)));
@@ -394,6 +472,7 @@ enum { ING_VALIDATE = 0, ING_COUNT = 1, ING_DETECT = 2 };
 static int ingest_chunk(s2_ingest *g, s2_table *t, int col, int mode, bool bgzf, const s2_ingest::Chunk &ch, const uint8_t *d_src, bool first)
 {
     const bool scan = mode != ING_VALIDATE;
+    const bool fasta = g->fasta;
     s2_ctx *c = g->ctx;
     cudaStream_t st = g->stream;
     const unsigned text_blocks = (unsigned)(((size_t)ING_MAXCARRY + ING_TEXT_CAP) / 4096 + 1);
@@ -412,6 +491,19 @@ static int ingest_chunk(s2_ingest *g, s2_table *t, int col, int mode, bool bgzf,
     ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_block_nl, text_blocks, nullptr, &g->d_state->n_lines);
     ing_nl_scatter<<<text_blocks, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_block_nl, g->d_line_end);
     ing_fastq_prepare<<<1, 1, 0, st>>>(g->d_state);
+    if (fasta) {
+        ing_fasta_len<<<c->n_sm * 4, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, scan ? 1 : 0);
+        if (scan) {
+            ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_out, 0, &g->d_state->n_lines, g->d_total);
+            ing_fasta_set_flat_len<<<1, 1, 0, st>>>(g->d_state, g->d_total);
+            ing_fasta_copy<<<c->n_sm * 8, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, g->d_flat);
+            s2_launch_scan_count_devlen(g->d_flat, &g->d_state->flat_len, t->v, col, c->d_stats, c->grid_count, st);
+        }
+        ing_fasta_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, g->d_flat, 0, scan ? 1 : 0);
+        ing_fasta_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, g->d_flat, 1, scan ? 1 : 0);
+        CK(cudaGetLastError());
+        return 0;
+    }
     ing_fastq_len<<<c->n_sm * 4, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, scan ? 1 : 0);
     if (scan) {
         ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_out, 0, &g->d_state->n_rec, g->d_total);
@@ -518,6 +610,31 @@ static int ingest_pass_cached(s2_ingest *g, s2_table *t, bool bgzf, int col, int
 
 static thread_local s2_ingest *tl_ingest = nullptr;
 
+// first byte of the text inside a BGZF file ('@' FASTQ, '>' FASTA): inflate the first non-empty block on the host
+static int bgzf_first_text_byte(int fd)
+{
+    std::vector<uint8_t> buf(1 << 17);
+    const ssize_t got = pread(fd, buf.data(), buf.size(), 0);
+    size_t used = 0;
+    while (got > 0 && used < (size_t)got) {
+        size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
+        if (!bgzf_block(buf.data() + used, (size_t)got - used, &bs, &doff, &dlen, &isz) || dlen == (size_t)-1) return -1;
+        if (isz) {
+            z_stream z; memset(&z, 0, sizeof z);
+            if (inflateInit2(&z, -15) != Z_OK) return -1;
+            uint8_t out[16];
+            z.next_in = buf.data() + used + doff; z.avail_in = (uInt)dlen;
+            z.next_out = out; z.avail_out = sizeof out;
+            inflate(&z, Z_SYNC_FLUSH);
+            const int first = z.total_out ? out[0] : -1;
+            inflateEnd(&z);
+            return first;
+        }
+        used += bs;
+    }
+    return -1;
+}
+
 // open + classify a file for the GPU path and make sure this thread's pipeline (and its file cache) exists.
 // Returns 0 ready, 1 not eligible, -1 error.
 static int ingest_open(s2_ctx *c, const char *path, int *fd_out, bool *bgzf_out, bool *cache_out, s2_ingest **g_out)
@@ -527,8 +644,8 @@ static int ingest_open(s2_ctx *c, const char *path, int *fd_out, bool *bgzf_out,
     uint8_t head[32];
     const ssize_t hn = pread(fd, head, sizeof head, 0);
     const bool bgzf = is_bgzf_header(head, hn);
-    const bool plain = !bgzf && hn >= 1 && head[0] == '@';
-    if (!bgzf && !plain) { close(fd); return 1; }
+    const int first = bgzf ? bgzf_first_text_byte(fd) : (hn >= 1 ? head[0] : -1);
+    if (first != '@' && first != '>') { close(fd); return 1; }            // neither FASTQ nor FASTA (or an ordinary .gz): host reader
     if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
     if (!tl_ingest) {
         tl_ingest = new s2_ingest();
@@ -545,6 +662,7 @@ static int ingest_open(s2_ctx *c, const char *path, int *fd_out, bool *bgzf_out,
         const size_t want = (size_t)sb.st_size + ING_COMP_CHUNK + ((size_t)sb.st_size >> 2);
         if (cudaMalloc((void **)&g->d_file, want) == cudaSuccess) g->d_file_cap = want; else { cudaGetLastError(); cache = false; }
     }
+    g->fasta = first == '>';
     *fd_out = fd; *bgzf_out = bgzf; *cache_out = cache; *g_out = g;
     return 0;
 }
@@ -565,7 +683,9 @@ extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, in
     close(fd);
     if (rc == 0) {
         if (bases) *bases = g->h_state->bases;
-        if (lookups) *lookups = g->h_state->lookups;
+        // FASTA records are not measured one by one on the device: every record is assumed to have at least one window
+        if (lookups) *lookups = g->fasta ? (g->h_state->bases > 30 * g->h_state->records ? g->h_state->bases - 30 * g->h_state->records : 0)
+                                         : g->h_state->lookups;
     }
     return rc;
 }
@@ -581,6 +701,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     int fd; bool bgzf, cache; s2_ingest *g;
     int rc = ingest_open(c, path, &fd, &bgzf, &cache, &g);
     if (rc) return rc;
+    if (g->fasta) { close(fd); return 1; }                            // per-read results are a FASTQ feature here
     rc = ingest_pass_host(g, t, fd, bgzf, 0, ING_VALIDATE, cache);
     if (rc) { close(fd); return rc; }
     const unsigned long long n_rec = g->h_state->records;

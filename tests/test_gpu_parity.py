@@ -603,3 +603,60 @@ def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_p
     p = s2.run_strain_detect(["-r", "strain.fa", "-a", "inf.txt", "-b", "a_R1.fastq.gz", "-c", "e_R2.fastq.gz", "-t", "PE", "-o", os.path.join(tmp, "x.gz")], cwd=tmp)
     assert o.returncode == 1 and p.returncode == 1
     assert p.stderr == o.stderr
+
+
+def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_path):
+    """multi-line FASTA (BGZF and plain) through the GPU ingest: sequence lines joined on the device, headers become
+    separators, chunk boundaries inside long contigs; irregular FASTA goes back to the host reader"""
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    rng = synth.rng_for(9, 0)
+    strain = synth.genome(rng, 400_000, 3, n_runs=3)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    # ~130 MB of FASTA text: one 60 Mb contig (crosses ingest chunks) + relatives of the strain + short contigs
+    big = [synth.random_bases(rng, 60_000_000)] + [synth.mutate(c, 0.01, rng) for c in strain] * 20 + [synth.random_bases(rng, n) for n in (5, 30, 31, 200)]
+    big[0][1_000_000:1_400_000] = strain[0][:400_000] if strain[0].size >= 400_000 else big[0][1_000_000:1_400_000]
+    import io
+    def fasta_text(recs, wrap):
+        out = io.BytesIO()
+        for i, r in enumerate(recs):
+            b = r.tobytes()
+            out.write(b">c%d some description\n" % i)
+            for j in range(0, len(b), wrap):
+                out.write(b[j:j + wrap] + b"\n")
+            if i % 7 == 3:
+                out.write(b"\n")                                # empty lines inside / between records are legal
+        return out.getvalue()
+    text = fasta_text(big, 70)
+    synth.write_bgzf(os.path.join(tmp, "g.fa.gz"), text)
+    open(os.path.join(tmp, "g.fa"), "wb").write(text[:-1])           # plain, unterminated last line
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    want = ctx.scan_count(t, s2.load_flat(os.path.join(tmp, "g.fa.gz")), 1)
+    assert want.hits > 100_000
+    for col, name in ((2, "g.fa.gz"), (3, "g.fa")):
+        rc, bases, lookups = ctx.ingest_count_file(t, os.path.join(tmp, name), col)
+        st = ctx.sync()
+        assert rc == 0
+        assert bases == sum(r.size for r in big)
+        assert st.hits == want.hits and st.valid_windows == want.valid_windows
+        assert np.array_equal(t.counts(col), t.counts(1))
+    t.clear_counts(2)
+    for name, bad in {"junk": b"junk\n" + text[:5000], "crlf": text[:5000].replace(b"\n", b"\r\n"),
+                      "fastq_inside": text[:5000] + b"@r\nACGT\n+\nIIII\n", "plus_line": text[:5000] + b"+\n"}.items():
+        synth.write_bgzf(os.path.join(tmp, name + ".fa.gz"), bad)
+        assert ctx.ingest_count_file(t, os.path.join(tmp, name + ".fa.gz"), 2)[0] == 1, name
+        assert int(t.counts(2).sum()) == 0
+    t.free()
+    # the executable on the golden count case with every input re-packed as BGZF: bytes equal the reference's
+    d = os.path.join(golden_dir, "count_edge")
+    for lst in ("listA.txt", "listB.txt", "listC.txt"):
+        names = [l.strip() for l in open(os.path.join(d, lst)) if l.strip()]
+        new = []
+        for n in names:
+            raw = ou.gunzip(os.path.join(d, n)) if n.endswith(".gz") else open(os.path.join(d, n), "rb").read()
+            synth.write_bgzf(os.path.join(tmp, n.replace("/", "_") + ".bgz"), raw)
+            new.append(os.path.join(tmp, n.replace("/", "_") + ".bgz"))
+        open(os.path.join(tmp, lst), "w").write("".join(x + "\n" for x in new))
+    p = s2.run_kmer_scrub_count(["-r", os.path.join(d, "ref.fa.gz"), "-A", os.path.join(tmp, "listA.txt"), "-B", os.path.join(tmp, "listB.txt")], cwd=tmp)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout == open(os.path.join(d, "expected_AB.tsv"), "rb").read()
