@@ -642,7 +642,7 @@ def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_pat
         assert np.array_equal(t.counts(col), t.counts(1))
     t.clear_counts(2)
     for name, bad in {"junk": b"junk\n" + text[:5000], "crlf": text[:5000].replace(b"\n", b"\r\n"),
-                      "fastq_inside": text[:5000] + b"@r\nACGT\n+\nIIII\n", "plus_line": text[:5000] + b"+\n"}.items():
+                      "fastq_inside": text[:5000] + b"\n@r\nACGT\n+\nIIII\n", "plus_line": text[:5000] + b"\n+\n"}.items():
         synth.write_bgzf(os.path.join(tmp, name + ".fa.gz"), bad)
         assert ctx.ingest_count_file(t, os.path.join(tmp, name + ".fa.gz"), 2)[0] == 1, name
         assert int(t.counts(2).sum()) == 0
