@@ -20,7 +20,15 @@ def _gen_genome(a):
     from strainer2_b200 import synth
     path, index, gz = a
     strain = bench.make_strain()
-    synth.write_fasta(path, bench.make_genome(strain, index), gz=gz)
+    if path.endswith(".bgz"):
+        import io
+        buf = io.BytesIO()
+        for i, c in enumerate(bench.make_genome(strain, index)):
+            b = c.tobytes()
+            buf.write(b">seq%d\n" % i + b"\n".join(b[j:j + 80] for j in range(0, len(b), 80)) + b"\n")
+        synth.write_bgzf(path, buf.getvalue())
+    else:
+        synth.write_fasta(path, bench.make_genome(strain, index), gz=gz)
     return path
 
 
@@ -60,12 +68,19 @@ def main():
     strain = bench.make_strain()
     synth.write_fasta(os.path.join(tmp, "strain.fa"), strain, gz=False)
     jobs = [(os.path.join(tmp, f"g{i}.fa" + (".gz" if i < args.gz_genomes else "")), i, i < args.gz_genomes) for i in range(args.genomes)]
+    jobs += [(os.path.join(tmp, f"g{i}.fa.bgz"), i, False) for i in range(args.genomes)]
+    jobs += [(os.path.join(tmp, f"z{i}.fa.gz"), i, True) for i in range(args.genomes)]
     mjobs = [(os.path.join(tmp, f"m{i}.fastq.gz"), i, args.reads) for i in range(args.metas)]
     mjobs += [(os.path.join(tmp, f"m{i}.fastq.bgz"), i, args.reads) for i in range(args.metas)]
     with mp.Pool(min(24, os.cpu_count() or 1)) as pool:
         A = pool.map(_gen_genome, jobs)
         B = pool.map(_gen_meta, mjobs)
+    Az = [a for a in A if a.endswith(".bgz")]
+    Ag = [a for a in A if os.path.basename(a).startswith("z")]
+    A = [a for a in A if a not in Az and a not in Ag]
     open(os.path.join(tmp, "A.txt"), "w").write("".join(a + "\n" for a in A))
+    open(os.path.join(tmp, "Az.txt"), "w").write("".join(a + "\n" for a in Az))
+    open(os.path.join(tmp, "Ag.txt"), "w").write("".join(a + "\n" for a in Ag))
     Bz = [b for b in B if b.endswith(".bgz")]
     B = [b for b in B if not b.endswith(".bgz")]
     open(os.path.join(tmp, "B.txt"), "w").write("".join(b + "\n" for b in B))
@@ -76,6 +91,8 @@ def main():
     exe = os.path.join(ROOT, "strainer2_b200", "bin", "kmer_scrub_count")
     env = dict(os.environ, S2_STATS="1")
     runs = [("genomes_only", ["-r", "strain.fa", "-A", "A.txt", "-B", "empty.txt"]),
+            ("genomes_all_gz_host_inflate", ["-r", "strain.fa", "-A", "Ag.txt", "-B", "empty.txt"]),
+            ("genomes_all_bgzf_gpu_ingest", ["-r", "strain.fa", "-A", "Az.txt", "-B", "empty.txt"]),
             ("metagenomes_only", ["-r", "strain.fa", "-A", "empty.txt", "-B", "B.txt"]),
             ("metagenomes_bgzf_gpu_ingest", ["-r", "strain.fa", "-A", "empty.txt", "-B", "Bz.txt"])]
     for th in ([t for t in args.threads.split(",") if t] or [""]):
