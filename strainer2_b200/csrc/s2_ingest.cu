@@ -475,7 +475,7 @@ static int ingest_chunk(s2_ingest *g, s2_table *t, int col, int mode, bool bgzf,
     const bool fasta = g->fasta;
     s2_ctx *c = g->ctx;
     cudaStream_t st = g->stream;
-    const unsigned text_blocks = (unsigned)(((size_t)ING_MAXCARRY + ING_TEXT_CAP) / 4096 + 1);
+    const unsigned text_blocks = (unsigned)(((size_t)ING_MAXCARRY + ch.text_len) / 4096 + 1);      // covers [0, t1] of the text buffer
     ing_begin_chunk<<<1, 1, 0, st>>>(g->d_state, ch.text_len, ch.eof ? 1u : 0u, first ? 1u : 0u);
     if (bgzf) {
         if (!ch.params.empty()) {
@@ -646,6 +646,8 @@ static int ingest_open(s2_ctx *c, const char *path, int *fd_out, bool *bgzf_out,
     const bool bgzf = is_bgzf_header(head, hn);
     const int first = bgzf ? bgzf_first_text_byte(fd) : (hn >= 1 ? head[0] : -1);
     if (first != '@' && first != '>') { close(fd); return 1; }            // neither FASTQ nor FASTA (or an ordinary .gz): host reader
+    // uncompressed text gains nothing but PCIe from this path (the host parser does GB/s per thread): opt-in only
+    if (!bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 0)) { close(fd); return 1; }
     if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
     if (!tl_ingest) {
         tl_ingest = new s2_ingest();

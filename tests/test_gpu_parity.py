@@ -476,8 +476,9 @@ def _ingest_fixture(s2, tmp, n_reads=60_000, seed=0):
     return strain, reads
 
 
-def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path):
+def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path, monkeypatch):
     from strainer2_b200 import synth
+    monkeypatch.setenv("S2_GPU_INGEST_PLAIN", "1")
     tmp = str(tmp_path)
     strain, reads = _ingest_fixture(s2, tmp, 340_000)                  # ~100 MB of text: several ingest chunks
     data = synth.fastq_bytes(reads)
@@ -545,7 +546,7 @@ def test_executable_with_bgzf_inputs_matches_oracle(s2, golden_dir, tmp_path):
     args = ["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"]
     o = ou.oracle_cli(["count"] + args, cwd=tmp)
     assert o.returncode == 0
-    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1"}):
+    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1", "S2_GPU_INGEST_PLAIN": "1"}):
         p = s2.run_kmer_scrub_count(args, cwd=tmp, env=env)
         assert p.returncode == 0, p.stderr
         assert p.stdout == o.stdout, env
@@ -591,7 +592,7 @@ def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_p
     o = ou.oracle_cli(["detect"] + args + ["-m", os.path.join(tmp, "msg")], cwd=tmp)
     assert o.returncode == 0, o.stderr
     assert o.stdout.count(b"\n") > 500
-    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1"}):
+    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1", "S2_GPU_INGEST_PLAIN": "1"}):
         out = os.path.join(tmp, "hits.gz")
         p = s2.run_strain_detect(args + ["-o", out], cwd=tmp, env=env)
         assert p.returncode == 0, p.stderr
@@ -605,7 +606,8 @@ def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_p
     assert p.stderr == o.stderr
 
 
-def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_path):
+def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_path, monkeypatch):
+    monkeypatch.setenv("S2_GPU_INGEST_PLAIN", "1")
     """multi-line FASTA (BGZF and plain) through the GPU ingest: sequence lines joined on the device, headers become
     separators, chunk boundaries inside long contigs; irregular FASTA goes back to the host reader"""
     from strainer2_b200 import synth
