@@ -123,6 +123,10 @@ int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
  * s2_batch_submit_count), -1 = error.  Thread safe (one ingest pipeline per calling thread; call
  * s2_ingest_thread_cleanup() before the thread exits). */
 int         s2_ingest_count_file(s2_ctx *ctx, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups);
+/* the same for a file IMAGE in host memory (the bytes of a BGZF or plain FASTA / FASTQ file; pinned memory from
+ * s2_pinned_alloc gives the full PCIe rate): only the compressed bytes cross PCIe.  The image must stay valid
+ * until the call returns. */
+int         s2_ingest_count_mem(s2_ctx *ctx, s2_table *t, const void *image, uint64_t n_bytes, int col, uint64_t *bases, uint64_t *lookups);
 /* the detect form: pass 1 of quantify_hits_PE for every read of one file.  len / hits / inf are per record in
  * file order (ALL records, also those shorter than 31, which the pairing loop needs); inf_* list the informative
  * windows sorted by (record, offset) with their canonical k-mer.  Arrays are malloc()ed by the call. */

@@ -116,6 +116,19 @@ class Context:
             raise S2Error("s2_ingest_count_file: " + _lib.last_error())
         return rc, b.value, l.value
 
+    def ingest_count_mem(self, table, image, col):
+        """the same for a file image in host memory (bytes / numpy uint8 / (pointer, length)) -> (rc, bases, lookups)"""
+        if isinstance(image, tuple):
+            ptr, n, keep = image[0], image[1], None
+        else:
+            keep = np.frombuffer(image, dtype=np.uint8) if not isinstance(image, np.ndarray) else np.ascontiguousarray(image, dtype=np.uint8)
+            ptr, n = keep.ctypes.data, keep.size
+        b, l = C.c_uint64(), C.c_uint64()
+        rc = lib.s2_ingest_count_mem(self.h, table.h, ptr, n, col, C.byref(b), C.byref(l))
+        if rc < 0:
+            raise S2Error("s2_ingest_count_mem: " + _lib.last_error())
+        return rc, b.value, l.value
+
     def kernel_time(self, reset=False):
         ms, n = C.c_double(), C.c_uint64()
         check(lib.s2_kernel_time(self.h, C.byref(ms), C.byref(n), 1 if reset else 0), "s2_kernel_time")

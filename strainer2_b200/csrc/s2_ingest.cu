@@ -464,6 +464,23 @@ static bool is_bgzf_header(const uint8_t *p, ssize_t n)
            p[12] == 'B' && p[13] == 'C' && p[14] == 2 && p[15] == 0;
 }
 
+// where the compressed (or plain) bytes come from: a file read chunk by chunk into pinned staging buffers, or a
+// caller's host buffer (pinned for full PCIe rate) that is copied to the device directly
+struct IngSource {
+    int fd = -1;
+    const uint8_t *mem = nullptr;
+    size_t mem_len = 0;
+    ssize_t size() const { if (mem) return (ssize_t)mem_len; struct stat sb; return fstat(fd, &sb) == 0 ? (ssize_t)sb.st_size : -1; }
+    ssize_t peek(void *dst, size_t len, off_t off) const
+    {
+        if (!mem) return pread(fd, dst, len, off);
+        if ((size_t)off >= mem_len) return 0;
+        const size_t n = std::min(len, mem_len - (size_t)off);
+        memcpy(dst, mem + off, n);
+        return (ssize_t)n;
+    }
+};
+
 // device work for one chunk whose bytes are already on the device: inflate (or copy), index, validate,
 // and - when scan is set - copy the sequence lines out and count them
 #define ING_CAP_C (8ull << 20)        /* informative windows one chunk may report */
@@ -536,7 +553,7 @@ static int ingest_chunk(s2_ingest *g, s2_table *t, int col, int mode, bool bgzf,
 // Pass over the file FROM THE HOST: read() chunks of whole BGZF blocks (or of raw text) into two alternating
 // pinned buffers, copy them to the device (into the file cache when the file fits, so that the second pass
 // needs no I/O), and run the device stage.  Returns 0 ok, 1 irregular / unsupported, -1 error.
-static int ingest_pass_host(s2_ingest *g, s2_table *t, int fd, bool bgzf, int col, int mode, bool cache)
+static int ingest_pass_host(s2_ingest *g, s2_table *t, const IngSource &src, bool bgzf, int col, int mode, bool cache)
 {
     cudaStream_t st = g->stream;
     CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), st));
@@ -545,10 +562,16 @@ static int ingest_pass_host(s2_ingest *g, s2_table *t, int fd, bool bgzf, int co
     bool first = true, eof = false;
     int buf = 0;
     while (!eof) {
-        uint8_t *h = g->h_comp[buf];
-        CK(cudaEventSynchronize(g->h_free[buf]));                                // its previous H2D copy is done
-        const ssize_t got = pread(fd, h, ING_COMP_CHUNK, file_off);
-        if (got < 0) { s2_set_error("read failed"); return -1; }
+        const uint8_t *h = g->h_comp[buf];
+        ssize_t got;
+        if (src.mem) {                                                           // caller's buffer: no staging copy
+            h = src.mem + file_off;
+            got = (size_t)file_off < src.mem_len ? (ssize_t)std::min<size_t>(ING_COMP_CHUNK, src.mem_len - (size_t)file_off) : 0;
+        } else {
+            CK(cudaEventSynchronize(g->h_free[buf]));                            // its previous H2D copy is done
+            got = pread(src.fd, g->h_comp[buf], ING_COMP_CHUNK, file_off);
+            if (got < 0) { s2_set_error("read failed"); return -1; }
+        }
         uint8_t *d_dst = cache ? g->d_file + file_off : g->d_comp;
         s2_ingest::Chunk local, &ch = cache ? (g->chunks.emplace_back(), g->chunks.back()) : local;
         size_t used = 0, text_len = 0;
@@ -611,10 +634,10 @@ static int ingest_pass_cached(s2_ingest *g, s2_table *t, bool bgzf, int col, int
 static thread_local s2_ingest *tl_ingest = nullptr;
 
 // first byte of the text inside a BGZF file ('@' FASTQ, '>' FASTA): inflate the first non-empty block on the host
-static int bgzf_first_text_byte(int fd)
+static int bgzf_first_text_byte(const IngSource &src)
 {
     std::vector<uint8_t> buf(1 << 17);
-    const ssize_t got = pread(fd, buf.data(), buf.size(), 0);
+    const ssize_t got = src.peek(buf.data(), buf.size(), 0);
     size_t used = 0;
     while (got > 0 && used < (size_t)got) {
         size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
@@ -635,38 +658,59 @@ static int bgzf_first_text_byte(int fd)
     return -1;
 }
 
-// open + classify a file for the GPU path and make sure this thread's pipeline (and its file cache) exists.
+// classify a source for the GPU path and make sure this thread's pipeline (and its file cache) exists.
 // Returns 0 ready, 1 not eligible, -1 error.
-static int ingest_open(s2_ctx *c, const char *path, int *fd_out, bool *bgzf_out, bool *cache_out, s2_ingest **g_out)
+static int ingest_prepare(s2_ctx *c, const IngSource &src, bool *bgzf_out, bool *cache_out, s2_ingest **g_out)
 {
-    const int fd = open(path, O_RDONLY);
-    if (fd < 0) return 1;
     uint8_t head[32];
-    const ssize_t hn = pread(fd, head, sizeof head, 0);
+    const ssize_t hn = src.peek(head, sizeof head, 0);
     const bool bgzf = is_bgzf_header(head, hn);
-    const int first = bgzf ? bgzf_first_text_byte(fd) : (hn >= 1 ? head[0] : -1);
-    if (first != '@' && first != '>') { close(fd); return 1; }            // neither FASTQ nor FASTA (or an ordinary .gz): host reader
+    const int first = bgzf ? bgzf_first_text_byte(src) : (hn >= 1 ? head[0] : -1);
+    if (first != '@' && first != '>') return 1;                           // neither FASTQ nor FASTA (or an ordinary .gz): host reader
     // uncompressed text gains nothing but PCIe from this path (the host parser does GB/s per thread): opt-in only
-    if (!bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 0)) { close(fd); return 1; }
+    if (!bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 0)) return 1;
     if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
     if (!tl_ingest) {
         tl_ingest = new s2_ingest();
-        if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; close(fd); return -1; }
+        if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return -1; }
     }
     s2_ingest *g = tl_ingest;
-    if (bgzf && !g->hw_deflate) { close(fd); return 1; }
+    if (bgzf && !g->hw_deflate) return 1;
     // keep the compressed file on the device between the two passes when it fits (S2_INGEST_CACHE_MB, default 2048)
-    struct stat sb;
-    bool cache = fstat(fd, &sb) == 0 && (uint64_t)sb.st_size <= (s2_env_u64("S2_INGEST_CACHE_MB", 2048) << 20);
-    if (cache && (size_t)sb.st_size + ING_COMP_CHUNK > g->d_file_cap) {
+    const ssize_t size = src.size();
+    bool cache = size >= 0 && (uint64_t)size <= (s2_env_u64("S2_INGEST_CACHE_MB", 2048) << 20);
+    if (cache && (size_t)size + ING_COMP_CHUNK > g->d_file_cap) {
         cudaStreamSynchronize(g->stream);
         cudaFree(g->d_file); g->d_file = nullptr; g->d_file_cap = 0;
-        const size_t want = (size_t)sb.st_size + ING_COMP_CHUNK + ((size_t)sb.st_size >> 2);
+        const size_t want = (size_t)size + ING_COMP_CHUNK + ((size_t)size >> 2);
         if (cudaMalloc((void **)&g->d_file, want) == cudaSuccess) g->d_file_cap = want; else { cudaGetLastError(); cache = false; }
     }
     g->fasta = first == '>';
-    *fd_out = fd; *bgzf_out = bgzf; *cache_out = cache; *g_out = g;
+    *bgzf_out = bgzf; *cache_out = cache; *g_out = g;
     return 0;
+}
+
+static int ingest_open(s2_ctx *c, const char *path, IngSource *src, bool *bgzf_out, bool *cache_out, s2_ingest **g_out)
+{
+    src->fd = open(path, O_RDONLY);
+    if (src->fd < 0) return 1;
+    const int rc = ingest_prepare(c, *src, bgzf_out, cache_out, g_out);
+    if (rc) { close(src->fd); src->fd = -1; }
+    return rc;
+}
+
+static int ingest_count_source(s2_ingest *g, s2_table *t, const IngSource &src, bool bgzf, bool cache, int col, uint64_t *bases, uint64_t *lookups)
+{
+    int rc = ingest_pass_host(g, t, src, bgzf, col, ING_VALIDATE, cache);         // pass 1: prove the text is strict FASTQ / FASTA
+    if (rc == 0) rc = cache ? ingest_pass_cached(g, t, bgzf, col, ING_COUNT)      // pass 2: count
+                            : ingest_pass_host(g, t, src, bgzf, col, ING_COUNT, false);
+    if (rc == 0) {
+        if (bases) *bases = g->h_state->bases;
+        // FASTA records are not measured one by one on the device: every record is assumed to have at least one window
+        if (lookups) *lookups = g->fasta ? (g->h_state->bases > 30 * g->h_state->records ? g->h_state->bases - 30 * g->h_state->records : 0)
+                                         : g->h_state->lookups;
+    }
+    return rc;
 }
 
 // GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed or plain strict
@@ -676,20 +720,25 @@ extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, in
 {
     if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
     if (t->partitioned) return 1;                                    // union tables keep the host reader + two-phase scan
-    int fd; bool bgzf, cache; s2_ingest *g;
-    int rc = ingest_open(c, path, &fd, &bgzf, &cache, &g);
+    IngSource src; bool bgzf, cache; s2_ingest *g;
+    int rc = ingest_open(c, path, &src, &bgzf, &cache, &g);
     if (rc) return rc;
-    rc = ingest_pass_host(g, t, fd, bgzf, col, ING_VALIDATE, cache);             // pass 1: prove the file is strict FASTQ
-    if (rc == 0) rc = cache ? ingest_pass_cached(g, t, bgzf, col, ING_COUNT)      // pass 2: count
-                            : ingest_pass_host(g, t, fd, bgzf, col, ING_COUNT, false);
-    close(fd);
-    if (rc == 0) {
-        if (bases) *bases = g->h_state->bases;
-        // FASTA records are not measured one by one on the device: every record is assumed to have at least one window
-        if (lookups) *lookups = g->fasta ? (g->h_state->bases > 30 * g->h_state->records ? g->h_state->bases - 30 * g->h_state->records : 0)
-                                         : g->h_state->lookups;
-    }
+    rc = ingest_count_source(g, t, src, bgzf, cache, col, bases, lookups);
+    close(src.fd);
     return rc;
+}
+
+// The same for a file image that is already in host memory (the bytes of a BGZF or plain FASTA/FASTQ file; pinned
+// memory gives the full PCIe rate).  Only the compressed bytes cross PCIe.
+extern "C" int s2_ingest_count_mem(s2_ctx *c, s2_table *t, const void *image, uint64_t n_bytes, int col, uint64_t *bases, uint64_t *lookups)
+{
+    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
+    if (t->partitioned) return 1;
+    IngSource src; src.mem = (const uint8_t *)image; src.mem_len = (size_t)n_bytes;
+    bool bgzf, cache; s2_ingest *g;
+    const int rc = ingest_prepare(c, src, &bgzf, &cache, &g);
+    if (rc) return rc;
+    return ingest_count_source(g, t, src, bgzf, cache, col, bases, lookups);
 }
 
 // Pass 1 of quantify_hits_PE (src/strain_detect.c:465-491) for every read of one file, inflated and split on the
@@ -700,11 +749,12 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
 {
     memset(out, 0, sizeof *out);
     if (t->partitioned) return 1;
-    int fd; bool bgzf, cache; s2_ingest *g;
-    int rc = ingest_open(c, path, &fd, &bgzf, &cache, &g);
+    IngSource src; bool bgzf, cache; s2_ingest *g;
+    int rc = ingest_open(c, path, &src, &bgzf, &cache, &g);
     if (rc) return rc;
+    const int fd = src.fd;
     if (g->fasta) { close(fd); return 1; }                            // per-read results are a FASTQ feature here
-    rc = ingest_pass_host(g, t, fd, bgzf, 0, ING_VALIDATE, cache);
+    rc = ingest_pass_host(g, t, src, bgzf, 0, ING_VALIDATE, cache);
     if (rc) { close(fd); return rc; }
     const unsigned long long n_rec = g->h_state->records;
     const size_t max_rec = (size_t)ING_MAX_LINES / 4 + 4;
@@ -727,7 +777,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
                 cudaMalloc((void **)&g->d_fkmer, g->f_cap * 8)) { s2_set_error("out of device memory"); close(fd); return -1; }
         }
         CK(cudaMemsetAsync(g->d_fcnt, 0, 8, g->stream));
-        rc = cache ? ingest_pass_cached(g, t, bgzf, 0, ING_DETECT) : ingest_pass_host(g, t, fd, bgzf, 0, ING_DETECT, false);
+        rc = cache ? ingest_pass_cached(g, t, bgzf, 0, ING_DETECT) : ingest_pass_host(g, t, src, bgzf, 0, ING_DETECT, false);
         if (rc) break;
         CK(cudaMemcpy(&n_inf, g->d_fcnt, 8, cudaMemcpyDeviceToHost));
         if (g->h_state->inf_overflow) { rc = 1; break; }                         // absurdly dense chunk: host path

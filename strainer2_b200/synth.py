@@ -135,20 +135,38 @@ def write_reads_fastq(path, reads: np.ndarray, gz=None):
             f.write(b"".join(b"@r%d\n%s\n+\n%s\n" % (s + i, chunk[i].tobytes(), qual) for i in range(chunk.shape[0])))
 
 
-def write_bgzf(path, data: bytes, block: int = 65280, level: int = 6):
+def bgzf_bytes(data: bytes, block: int = 65280, level: int = 6) -> bytes:
     """BGZF (bgzip) container: independent gzip members of <= 64 KB of text each, sizes in the 'BC' extra
     field, empty EOF member at the end.  A valid multi-member .gz for zlib (what the reference uses); the
     block structure is what lets the hardware decompression engine inflate it in parallel."""
     import struct
     import zlib
+    out = []
+    for off in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if off is None else data[off:off + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        bsize = len(comp) + 25                                   # total member size - 1
+        out.append(b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize))
+        out.append(comp + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return b"".join(out)
+
+
+def write_bgzf(path, data: bytes, block: int = 65280, level: int = 6):
     with open(path, "wb") as f:
-        for off in list(range(0, len(data), block)) + [None]:
-            chunk = b"" if off is None else data[off:off + block]
-            co = zlib.compressobj(level, zlib.DEFLATED, -15)
-            comp = co.compress(chunk) + co.flush()
-            bsize = len(comp) + 25                                   # total member size - 1
-            f.write(b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize))
-            f.write(comp + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        f.write(bgzf_bytes(data, block, level))
+
+
+def fasta_bytes(records, wrap=80) -> bytes:
+    out = []
+    for i, r in enumerate(records):
+        b = bytes(r) if not isinstance(r, np.ndarray) else r.tobytes()
+        out.append(b">seq%d\n" % i)
+        if wrap:
+            out.extend(b[j:j + wrap] + b"\n" for j in range(0, len(b), wrap))
+        else:
+            out.append(b + b"\n")
+    return b"".join(out)
 
 
 def fastq_bytes(reads: np.ndarray) -> bytes:

@@ -496,6 +496,15 @@ def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path, mo
         assert bases == n_bases and lookups == len(reads) * 120 + 50
         assert st.hits == want.hits and st.valid_windows == want.valid_windows
         assert np.array_equal(t.counts(col), t.counts(1))
+    # the same files as images in host memory (s2_ingest_count_mem): only the compressed bytes cross PCIe
+    for name in ("m.fastq.gz", "m.fastq"):
+        t.clear_counts(2)
+        image = np.fromfile(os.path.join(tmp, name), dtype=np.uint8)
+        rc, bases, lookups = ctx.ingest_count_mem(t, image, 2)
+        st = ctx.sync()
+        assert rc == 0 and bases == n_bases and lookups == len(reads) * 120 + 50
+        assert st.hits == want.hits and np.array_equal(t.counts(2), t.counts(1))
+    assert ctx.ingest_count_mem(t, np.frombuffer(b"junk\n" + data[:5000], dtype=np.uint8), 3)[0] == 1
     t.free()
 
 
