@@ -117,16 +117,25 @@ int         s2_batch_release(s2_ctx *ctx, uint8_t *batch);               /* give
 int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
 
 /* GPU-side ingest: GEN_calculate_kmer_count() for one FILE without the host inflating or
- * parsing it.  BGZF-compressed (bgzip) and uncompressed strict 4-line FASTQ are inflated by the Blackwell
- * hardware decompression engine and split into records by kernels; the file is first proven regular in a
- * pass that counts nothing.  Returns 0 = done, 1 = not handled (nothing was counted; use the reader +
- * s2_batch_submit_count), -1 = error.  Thread safe (one ingest pipeline per calling thread; call
- * s2_ingest_thread_cleanup() before the thread exits). */
+ * parsing it.  BGZF-compressed (bgzip) strict 4-line FASTQ / strict FASTA (and, with S2_GPU_INGEST_PLAIN=1, the same
+ * uncompressed) is inflated by the Blackwell hardware decompression engine and split into records by kernels; every
+ * chunk is proven regular on the device before its scan starts, so an irregular file is never counted.
+ * Returns 0 = done, 1 = not handled (nothing was counted; use the reader + s2_batch_submit_count), -1 = error.
+ * Thread safe (one ingest pipeline per calling thread; call s2_ingest_thread_cleanup() before the thread exits).
+ * Knobs: S2_INGEST_CHUNK_MB (compressed bytes per chunk, 64), S2_INGEST_TEXT_MB (text per chunk, 256). */
 int         s2_ingest_count_file(s2_ctx *ctx, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups);
 /* the same for a file IMAGE in host memory (the bytes of a BGZF or plain FASTA / FASTQ file; pinned memory from
  * s2_pinned_alloc gives the full PCIe rate): only the compressed bytes cross PCIe.  The image must stay valid
  * until the call returns. */
 int         s2_ingest_count_mem(s2_ctx *ctx, s2_table *t, const void *image, uint64_t n_bytes, int col, uint64_t *bases, uint64_t *lookups);
+/* many files per call (the list loop of GEN_all_kmer_counts, src/genome_compare.c:149-177, minus the progress lines):
+ * files that fit one chunk travel in groups - their texts back to back, one launch sequence per group - and the
+ * verdicts are collected once at the end.  rc_each[i] = 0 done / 1 not handled (nothing of file i was counted);
+ * bases / lookups = totals of the handled files.  Returns 0, or -1 on error. */
+int         s2_ingest_count_mem_batch(s2_ctx *ctx, s2_table *t, const void *const *images, const uint64_t *n_bytes, int n, int col,
+                                      int *rc_each, uint64_t *bases, uint64_t *lookups);
+int         s2_ingest_count_files(s2_ctx *ctx, s2_table *t, const char *const *paths, int n, int col,
+                                  int *rc_each, uint64_t *bases, uint64_t *lookups);
 /* the detect form: pass 1 of quantify_hits_PE for every read of one file.  len / hits / inf are per record in
  * file order (ALL records, also those shorter than 31, which the pairing loop needs); inf_* list the informative
  * windows sorted by (record, offset) with their canonical k-mer.  Arrays are malloc()ed by the call. */

@@ -65,6 +65,10 @@ SIGNATURES = {
     "s2_sync": (C.c_int, [C.c_void_p, C.POINTER(ScanStatsStruct)]),
     "s2_ingest_count_file": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, c_u64p, c_u64p]),
     "s2_ingest_count_mem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, c_u64p, c_u64p]),
+    "s2_ingest_count_mem_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), c_u64p, C.c_int, C.c_int,
+                                            C.POINTER(C.c_int), c_u64p, c_u64p]),
+    "s2_ingest_count_files": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int,
+                                        C.POINTER(C.c_int), c_u64p, c_u64p]),
     "s2_ingest_detect_file": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]),
     "s2_ingest_detect_free": (None, [C.c_void_p]),
     "s2_ingest_thread_cleanup": (None, []),

@@ -129,6 +129,32 @@ class Context:
             raise S2Error("s2_ingest_count_mem: " + _lib.last_error())
         return rc, b.value, l.value
 
+    def ingest_count_mem_batch(self, table, ptrs, sizes, col):
+        """many file images (host pointers + lengths) in one call, small files grouped -> (rc_each, bases, lookups)"""
+        n = len(ptrs)
+        P = (C.c_void_p * n)(*ptrs)
+        S = (C.c_uint64 * n)(*sizes)
+        R = (C.c_int * n)()
+        b, l = C.c_uint64(), C.c_uint64()
+        if lib.s2_ingest_count_mem_batch(self.h, table.h, P, S, n, col, R, C.byref(b), C.byref(l)) < 0:
+            raise S2Error("s2_ingest_count_mem_batch: " + _lib.last_error())
+        return list(R), b.value, l.value
+
+    def ingest_count_files(self, table, paths, col):
+        """many files in one call, small files grouped -> (rc_each, bases, lookups)"""
+        n = len(paths)
+        P = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        R = (C.c_int * n)()
+        b, l = C.c_uint64(), C.c_uint64()
+        if lib.s2_ingest_count_files(self.h, table.h, P, n, col, R, C.byref(b), C.byref(l)) < 0:
+            raise S2Error("s2_ingest_count_files: " + _lib.last_error())
+        return list(R), b.value, l.value
+
+    @staticmethod
+    def ingest_reset():
+        """drop the calling thread's ingest pipeline (the next call re-reads S2_INGEST_CHUNK_MB / S2_INGEST_TEXT_MB)"""
+        lib.s2_ingest_thread_cleanup()
+
     def kernel_time(self, reset=False):
         ms, n = C.c_double(), C.c_uint64()
         check(lib.s2_kernel_time(self.h, C.byref(ms), C.byref(n), 1 if reset else 0), "s2_kernel_time")

@@ -759,7 +759,7 @@ extern "C" int s2_scan_detect(s2_ctx *c, s2_table *t, const void *bases, uint64_
     CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
 
     S2DetectOut out;
-    out.rec_off = d_off; out.n_rec = n_rec; out.n_rec_dev = nullptr; out.n_bytes_dev = nullptr; out.read_hits = d_hits; out.read_inf = d_inf;
+    out.rec_off = d_off; out.n_rec = n_rec; out.n_rec_dev = nullptr; out.read_hits = d_hits; out.read_inf = d_inf;
     out.inf_pos = d_pos; out.inf_count = d_cnt; out.inf_cap = inf_cap;
     CK(cudaEventRecord(l.k0, st));
     s2_launch_scan_detect(d_bases, n_bytes, t->v, out, c->d_stats, c->grid_detect, st);

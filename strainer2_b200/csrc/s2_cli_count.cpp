@@ -24,6 +24,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <sys/stat.h>
 #include <vector>
 
 static void count_usage()
@@ -148,60 +149,75 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
     std::atomic<bool> stop(false);
     std::atomic<uint64_t> total_bases(0), total_lookups(0);
 
+    // GPU ingest takes runs of files (same counter column, S2_INGEST_BATCH files / S2_INGEST_BATCH_MB compressed bytes
+    // at most) so that small files share a chunk; everything it does not handle goes through the host reader below
+    const size_t max_run = gpu_ingest && !exotic ? (size_t)std::max(1, s2_env_int("S2_INGEST_BATCH", 16)) : 1;
+    const uint64_t run_bytes = s2_env_u64("S2_INGEST_BATCH_MB", 32) << 20;
+    struct Taken { std::string path; s2_reader *r; };
+
     auto reader = [&](int tid) {
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
         for (;;) {
-            s2_reader *r = nullptr; int col = 0;
-            std::string path;
+            std::vector<Taken> run;
+            int col = 0;
             {
                 std::lock_guard<std::mutex> g(mu);
-                while (path.empty()) {
+                uint64_t bytes = 0;
+                while (run.size() < max_run && bytes < run_bytes) {
                     if (stop.load() || next >= work.size()) break;
+                    if (!run.empty() && work[next].col != col) break;
                     S2WorkItem &it = work[next++];
                     if (progress) {
                         time_t now = time(nullptr);
                         fprintf(progress, "%s\t%s", it.path.c_str(), asctime(localtime(&now)));   // src/genome_compare.c:167-170
                     }
                     if (it.skip) { fprintf(stderr, "skipping %s (identical match)\n", it.path.c_str()); continue; }   // :141
-                    r = s2_reader_open(it.path.c_str());
+                    s2_reader *r = s2_reader_open(it.path.c_str());
                     if (!r) {
                         open_error = "could not read file " + it.path + " in GEN_calculate_kmer_count()";   // :196
                         stop.store(true);
                         break;
                     }
                     col = it.col;
-                    path = it.path;
+                    run.push_back({ it.path, r });
+                    struct stat sb;
+                    bytes += stat(it.path.c_str(), &sb) == 0 ? (uint64_t)sb.st_size : run_bytes;
                 }
             }
-            if (!r) break;
-            // BGZF / plain strict FASTQ: hardware inflate + record splitting on the GPU, nothing parsed here
+            if (run.empty()) break;
+            // BGZF / plain strict FASTQ + FASTA: hardware inflate + record splitting on the GPU, nothing parsed here
+            std::vector<int> handled(run.size(), 1);
             if (gpu_ingest && !exotic) {
+                std::vector<const char *> paths;
+                for (auto &x : run) paths.push_back(x.path.c_str());
                 uint64_t gb = 0, gl = 0;
-                const int irc = s2_ingest_count_file(w.ctx, w.table, path.c_str(), col, &gb, &gl);
-                if (irc == 0) { s2_reader_close(r); total_bases += gb; total_lookups += gl; continue; }
-                if (irc < 0) {
+                if (s2_ingest_count_files(w.ctx, w.table, paths.data(), (int)paths.size(), col, handled.data(), &gb, &gl) < 0) {
                     std::lock_guard<std::mutex> g(mu);
                     if (open_error.empty()) open_error = s2_last_error();
                     stop.store(true);
-                    s2_reader_close(r);
+                    for (auto &x : run) s2_reader_close(x.r);
                     break;
                 }
+                total_bases += gb; total_lookups += gl;
             }
-            if (!r) break;
-            const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
-            while ((l = s2_reader_next(r, &seq)) >= 0) {
-                bases += (uint64_t)l;
-                if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
-                if (!w.append(seq, (uint64_t)l, col)) {
-                    std::lock_guard<std::mutex> g(mu);
-                    if (open_error.empty()) open_error = s2_last_error();
-                    stop.store(true);
-                    break;
+            for (size_t k = 0; k < run.size(); ++k) {
+                s2_reader *r = run[k].r;
+                if (handled[k] == 0 || w.failed) { s2_reader_close(r); continue; }
+                const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
+                while ((l = s2_reader_next(r, &seq)) >= 0) {
+                    bases += (uint64_t)l;
+                    if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
+                    if (!w.append(seq, (uint64_t)l, col)) {
+                        std::lock_guard<std::mutex> g(mu);
+                        if (open_error.empty()) open_error = s2_last_error();
+                        stop.store(true);
+                        break;
+                    }
+                    if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
                 }
-                if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
+                s2_reader_close(r);
+                total_bases += bases; total_lookups += lookups;
             }
-            s2_reader_close(r);
-            total_bases += bases; total_lookups += lookups;
             if (w.failed) break;
         }
         if (!w.flush()) {

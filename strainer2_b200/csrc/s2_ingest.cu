@@ -1,4 +1,4 @@
-// s2_ingest.cu - GPU-side ingest of FASTQ files: hardware DEFLATE + record splitting on the device.
+// s2_ingest.cu - GPU-side ingest of FASTA / FASTQ files: hardware DEFLATE + record splitting on the device.
 //
 // SURVEY 8(f) rank 1.  The reference inflates and parses every input on one CPU thread (zlib gzread +
 // the vendored line parser, /root/reference/src/genome_compare.c:194-203, src/kseq.h:171-211); zlib gives
@@ -7,21 +7,29 @@
 // independent raw-DEFLATE streams of up to 4 MiB each (measured here: 240-320 GB/s of text for batches of
 // 64 KB blocks).  A plain .gz file is ONE long stream and cannot be split, but BGZF (bgzip, the block-
 // gzip flavour htslib writes; still a valid multi-member gzip file for the reference's zlib) is a sequence
-// of independent <= 64 KB members whose sizes are in their headers.  For BGZF FASTQ - and for uncompressed
-// FASTQ - this file does on the GPU what the reader threads do for everything else:
+// of independent <= 64 KB members whose sizes are in their headers.  For BGZF files - and, opt-in, for
+// uncompressed text - this file does on the GPU what the reader threads do for everything else:
 //
-//   host   : read() the compressed bytes into pinned memory, walk the BGZF headers (no inflate)
+//   host   : hand the compressed bytes to the copy engine (from the caller's memory, or read() into pinned
+//            staging), walk the BGZF headers (no inflate)
 //   engine : inflate all blocks of a chunk into one contiguous text buffer
-//   kernels: index the newlines, check that the text is strict 4-line FASTQ, copy the sequence lines into
-//            the flat batch format (sequence bytes + '\n'), carry the partial last record to the next chunk
-//   scan   : the normal count kernel, with the batch length read from device memory
+//   kernels: index the newlines (per 16 KB text block: count -> scan over blocks -> scatter), check that the text is
+//            strict 4-line FASTQ / strict FASTA and measure it, copy the sequence lines into the flat batch format
+//            (sequence bytes + '\n'; output offsets = scan over blocks + a scan inside each block), carry the partial
+//            last record to the next chunk
+//   scan   : the normal count / detect kernel; batch length, veto and increment are read from device memory
+//
+// A chunk is either a slice of one big file (streamed through a two-slot ring: the copy of chunk i+1 overlaps the
+// kernels of chunk i) or a GROUP of whole small files whose texts lie back to back (2,000 genomes of 5 Mb are 2,000
+// x 1.5 MB of BGZF: one launch sequence per file would be all latency).
 //
 // Parity: the parser the reference vendors accepts many irregular layouts (multi-line FASTQ, CR LF, '>'
-// records mixed in, truncated last record ...).  The kernels do not emulate those; they PROVE that a file is
-// regular (every record is '@' line, sequence line, '+' line, quality line of the same length, no CR, no
-// sequence starting with '>', '+' or '@', nothing left over at the end) in a first pass that scans nothing,
-// and only then run the pass that counts.  Anything else is handed back to the host reader untouched
-// (return value 1), so the counters are identical either way.
+// records mixed in, truncated last record ...).  The kernels do not emulate those; they PROVE that a chunk is
+// regular before its scan kernel starts (the scan reads the verdict from device memory and counts nothing after
+// the first irregular chunk).  A file that fits one chunk is therefore either counted completely or not at all;
+// a streamed file that turns irregular after some chunks were counted is replayed once with increment -1
+// (uint32 wrap-around add: the counters return to their exact previous values).  Irregular files are handed back
+// to the host reader (return value 1) with the counters untouched.
 #include "s2_private.h"
 #include "s2_kmer.cuh"
 
@@ -32,54 +40,54 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 
 #define ING_THREADS 256
-#define ING_MAXCARRY (1u << 20)          /* longest partial record carried between chunks */
-#define ING_COMP_CHUNK (8u << 20)        /* compressed bytes read per chunk */
-#define ING_TEXT_CAP (96u << 20)         /* inflated text per chunk (BGZF: <= 64 KB per block) */
-#define ING_MAX_LINES (ING_TEXT_CAP / 8) /* shorter average lines than 8 bytes: not a read file */
+#define ING_TILE 4096u                          /* bytes one pass of a CTA covers: 256 threads x 16 B */
+#define ING_TILES 4u
+#define ING_BLOCK (ING_TILE * ING_TILES)        /* text bytes per CTA of the indexing kernels */
+#define ING_MAXCARRY (1u << 20)                 /* longest partial record carried between chunks (multiple of ING_BLOCK) */
+#define ING_MAX_DBLOCKS 32768u                  /* DEFLATE blocks per chunk */
+#define ING_MAX_FILES 4096u                     /* whole files grouped into one chunk */
+#define ING_MAX_RESULTS 4096u                   /* chunks-with-a-verdict in flight between two host syncs */
+#define ING_DECOMP_CALL 4096u                   /* blocks per driver call */
+#define ING_CAP_C (8ull << 20)                  /* informative windows one chunk may report */
 
-struct IngState {                 // lives in device memory, one per ingest object
-    unsigned long long t0, t1;    // current text range inside the text buffer
-    unsigned long long flat_len;  // bytes of the flat batch produced from this chunk
-    unsigned long long carry_len; // bytes after the last complete record
-    unsigned long long bases, lookups, records;   // totals over the file (pass 2)
+typedef unsigned long long ull;
+
+struct IngState {                 // lives in device memory, one per ingest pipeline
+    ull t0, t1;                   // current text range inside the text buffer
+    ull flat_len;                 // \  S2DevBatch: bytes of the flat batch produced from this chunk,
+    unsigned int skip;            //  | veto (the text seen so far is irregular),
+    unsigned int inc;             // /  increment (1 or -1)
+    ull carry_from, carry_len;    // bytes after the last complete record
+    ull bases, lookups, records;  // totals over the file / group
     unsigned int n_lines, n_rec;
-    unsigned int irregular;       // sticky: the file is not strict FASTQ
-    unsigned int inf_overflow;    // a chunk produced more informative windows than the chunk list holds
+    unsigned int irregular;       // sticky: not strict FASTQ / FASTA
+    unsigned int inf_overflow;    // a chunk produced more informative windows / records than the lists hold
     unsigned int last_chunk, first_chunk;
     unsigned int tail_len;        // FASTA: last bytes of the previous chunk's flat stream, re-scanned in front of this one
+    unsigned int pad;
     unsigned char tail[32];
 };
 
-// ------------------------------------------------------------------------------------------------
-// newline index
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned nl_mask16(const uint8_t *text, unsigned long long base, unsigned long long t0,
-                                              unsigned long long t1, unsigned *cr)
-{
-    // bit i set <=> text[base+i] == '\n' and t0 <= base+i < t1   (base is 16-byte aligned)
-    unsigned m = 0;
-    *cr = 0;
-    if (base + 16 <= t0 || base >= t1) return 0;
-    const uint4 v = *reinterpret_cast<const uint4 *>(text + base);
-    const unsigned w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const unsigned c = (w[k] >> (8 * b)) & 0xFFu;
-            const unsigned long long pos = base + 4 * k + b;
-            const bool in = pos >= t0 && pos < t1;
-            if (in && c == '\n') m |= 1u << (4 * k + b);
-            if (in && c == '\r') *cr = 1;
-        }
-    return m;
-}
+struct IngResult { ull bases, lookups, records; unsigned int irregular, inf_overflow; };
 
+struct IngChunkArgs {             // by value to the kernels of one chunk
+    ull new_bytes;                // text bytes that arrived behind the carry
+    unsigned int first_chunk, last_chunk, inc, fasta;
+    unsigned int n_files, n_dblocks;
+    const ull *file_end;          // group: text offset (relative to the chunk's new bytes) where file i ends
+    const unsigned int *isz;      // expected inflated size per DEFLATE block
+    const unsigned int *act;      // what the engine reported
+};
+
+// ------------------------------------------------------------------------------------------------
+// block-level helpers
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ing_block_scan(unsigned v, unsigned &total)
 {
     __shared__ unsigned warp_sums[ING_THREADS / 32];
@@ -97,23 +105,78 @@ __device__ __forceinline__ unsigned ing_block_scan(unsigned v, unsigned &total)
     return base + inc - v;
 }
 
-// one CTA covers 4096 bytes of the text buffer (absolute, aligned); CTAs outside [t0, t1) do nothing
-__global__ void __launch_bounds__(ING_THREADS) ing_nl_count(const uint8_t *__restrict__ text, IngState *st, unsigned *__restrict__ block_nl)
+__device__ __forceinline__ ull ing_block_sum(ull v)
 {
-    const unsigned long long t0 = st->t0, t1 = st->t1;
-    const unsigned long long base = (unsigned long long)blockIdx.x * 4096 + threadIdx.x * 16;
-    unsigned cr;
-    const unsigned m = nl_mask16(text, base, t0, t1, &cr);
-    if (cr) atomicOr(&st->irregular, 1u);
-    unsigned total;
-    ing_block_scan(__popc(m), total);
-    if (threadIdx.x == 0) block_nl[blockIdx.x] = total;
+    __shared__ ull warp_sums64[ING_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) warp_sums64[wid] = v;
+    __syncthreads();
+    ull tot = 0;
+#pragma unroll
+    for (int i = 0; i < ING_THREADS / 32; ++i) tot += warp_sums64[i];
+    __syncthreads();
+    return tot;
 }
 
-// single CTA: exclusive scan of n counters in place, total to *total_out (n may come from device memory)
-__global__ void __launch_bounds__(ING_THREADS) ing_scan_u32(unsigned *__restrict__ v, unsigned n_host, const unsigned *n_dev, unsigned *total_out)
+// 4 bits: which bytes of w equal c
+__device__ __forceinline__ unsigned eq_bytes4(unsigned w, unsigned c)
 {
-    const unsigned n = n_dev ? *n_dev : n_host;
+    const unsigned x = w ^ (c * 0x01010101u);
+    const unsigned y = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);      // 0x80 in every zero byte of x, exact
+    return ((((y >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+}
+
+// bit i set <=> text[base+i] == '\n' and t0 <= base+i < t1   (base is 16-byte aligned); *cr: a '\r' in that range
+__device__ __forceinline__ unsigned nl_mask16(const uint8_t *text, ull base, ull t0, ull t1, unsigned *cr)
+{
+    *cr = 0;
+    if (base + 16 <= t0 || base >= t1) return 0;
+    const uint4 v = *reinterpret_cast<const uint4 *>(text + base);
+    const unsigned lo = t0 > base ? (unsigned)(t0 - base) : 0u;                  // < 16 here
+    const unsigned hi = t1 - base >= 16 ? 16u : (unsigned)(t1 - base);
+    const unsigned range = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+    const unsigned nl = eq_bytes4(v.x, '\n') | (eq_bytes4(v.y, '\n') << 4) | (eq_bytes4(v.z, '\n') << 8) | (eq_bytes4(v.w, '\n') << 12);
+    const unsigned r = eq_bytes4(v.x, '\r') | (eq_bytes4(v.y, '\r') << 4) | (eq_bytes4(v.z, '\r') << 8) | (eq_bytes4(v.w, '\r') << 12);
+    *cr = (r & range) ? 1u : 0u;
+    return nl & range;
+}
+
+// ------------------------------------------------------------------------------------------------
+// newline index: count per 16 KB block -> scan over blocks -> scatter
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, IngState *st, unsigned *__restrict__ block_nl, IngChunkArgs a)
+{
+    const ull carry = a.first_chunk ? 0ull : st->carry_len;
+    const ull t0 = ING_MAXCARRY - carry, t1 = ING_MAXCARRY + a.new_bytes;
+    // a final line without '\n' is completed (the parser the reference uses accepts that; the buffer has room past t1)
+    const bool term = a.last_chunk && t1 > t0 && text[t1 - 1] != '\n';
+    unsigned n = 0, any_cr = 0;
+#pragma unroll
+    for (unsigned k = 0; k < ING_TILES; ++k) {
+        const ull base = (ull)blockIdx.x * ING_BLOCK + k * ING_TILE + threadIdx.x * 16;
+        unsigned cr;
+        unsigned m = nl_mask16(text, base, t0, t1, &cr);
+        if (term && t1 >= base && t1 < base + 16) { m |= 1u << (unsigned)(t1 - base); text[t1] = '\n'; }
+        n += __popc(m);
+        any_cr |= cr;
+    }
+    if (any_cr) atomicOr(&st->irregular, 1u);
+    unsigned total;
+    ing_block_scan(n, total);
+    if (threadIdx.x == 0) block_nl[blockIdx.x] = total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->t0 = t0; st->t1 = t1 + (term ? 1 : 0);
+        st->first_chunk = a.first_chunk; st->last_chunk = a.last_chunk;
+        st->inc = a.inc; st->flat_len = 0;
+        if (a.first_chunk) st->tail_len = 0;
+    }
+}
+
+// single CTA: exclusive scan of v[0..n) in place, v[n] = total -> returned to every thread
+__device__ __forceinline__ unsigned ing_scan_array(unsigned *__restrict__ v, unsigned n)
+{
     __shared__ unsigned carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -129,206 +192,255 @@ __global__ void __launch_bounds__(ING_THREADS) ing_scan_u32(unsigned *__restrict
         if (threadIdx.x == 0) carry_s += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+    if (threadIdx.x == 0) v[n] = carry_s;
+    return carry_s;
 }
 
-__global__ void __launch_bounds__(ING_THREADS) ing_nl_scatter(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ block_off,
-                                                               unsigned *__restrict__ line_end)
+// the total becomes the line count of the chunk
+__global__ void __launch_bounds__(ING_THREADS) ing_scan_lines(unsigned *__restrict__ v, unsigned n, IngState *st, unsigned max_lines, unsigned fasta)
 {
-    const unsigned long long t0 = st->t0, t1 = st->t1;
-    const unsigned long long base = (unsigned long long)blockIdx.x * 4096 + threadIdx.x * 16;
-    unsigned cr;
-    unsigned m = nl_mask16(text, base, t0, t1, &cr);
-    unsigned total;
-    unsigned r = block_off[blockIdx.x] + ing_block_scan(__popc(m), total);
-    while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        if (r < ING_MAX_LINES) line_end[r] = (unsigned)(base + b);     // the text buffer is < 4 GiB
-        ++r;
+    unsigned lines = ing_scan_array(v, n);
+    if (threadIdx.x == 0) {
+        if (lines > max_lines) { st->irregular = 1; lines = 0; }       // shorter average lines than 8 bytes: not a sequence file
+        st->n_lines = lines;
+        st->n_rec = fasta ? 0u : lines / 4;
+    }
+}
+
+__global__ void __launch_bounds__(ING_THREADS) ing_index_scatter(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ block_off,
+                                                                  unsigned *__restrict__ line_end, unsigned max_lines)
+{
+    const ull t0 = st->t0, t1 = st->t1;
+    unsigned r = block_off[blockIdx.x];
+    for (unsigned k = 0; k < ING_TILES; ++k) {
+        const ull base = (ull)blockIdx.x * ING_BLOCK + k * ING_TILE + threadIdx.x * 16;
+        unsigned cr;
+        unsigned m = nl_mask16(text, base, t0, t1, &cr);
+        unsigned total;
+        unsigned at = r + ing_block_scan(__popc(m), total);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (at < max_lines) line_end[at] = (unsigned)(base + b);       // the text buffer is < 4 GiB
+            ++at;
+        }
+        r += total;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// strict FASTQ: validate, measure, copy
+// checks that do not belong to one record: what the engine inflated, where the files of a group meet
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ING_THREADS) ing_fastq_prepare(IngState *st)
+__device__ __forceinline__ void ing_check_chunk(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ line_end, const IngChunkArgs &a)
 {
-    // on the last chunk a final line without '\n' is completed (the buffer has room past t1)
-    if (st->n_lines > ING_MAX_LINES) { st->irregular = 1; st->n_lines = 0; }
-    st->n_rec = st->n_lines / 4;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    for (unsigned i = gtid; i < a.n_dblocks; i += n_threads)
+        if (a.act[i] != a.isz[i]) atomicOr(&st->irregular, 1u);                       // damaged DEFLATE block
+    // every file of a group but the last must end with '\n' (only the chunk's last line can be completed), and in
+    // FASTQ on a record boundary; that the next file starts with '>' / '@' was checked by the host
+    const unsigned n_lines = st->n_lines;
+    for (unsigned i = gtid; i + 1 < a.n_files; i += n_threads) {
+        const unsigned p = (unsigned)(ING_MAXCARRY + a.file_end[i] - 1);
+        bool ok = text[p] == '\n';
+        if (ok && !a.fasta) {
+            unsigned lo = 0, hi = n_lines;                                            // first line_end >= p
+            while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (line_end[mid] < p) lo = mid + 1; else hi = mid; }
+            ok = lo < n_lines && line_end[lo] == p && ((lo + 1) & 3u) == 0;
+        }
+        if (!ok) atomicOr(&st->irregular, 1u);
+    }
 }
 
-__global__ void __launch_bounds__(ING_THREADS) ing_fastq_len(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ line_end,
-                                                              unsigned *__restrict__ out_len, int count_stats)
+// ------------------------------------------------------------------------------------------------
+// strict FASTQ: validate + measure per block, copy
+// ------------------------------------------------------------------------------------------------
+// The records of block b are those whose LAST line ends in it: lines [off[b], off[b+1]) -> records [off[b]/4, off[b+1]/4).
+__global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ block_off,
+                                                                  const unsigned *__restrict__ line_end, unsigned *__restrict__ block_out, IngChunkArgs a)
 {
-    const unsigned n_rec = st->n_rec;
-    unsigned long long bases = 0, lookups = 0;
-    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
-        const unsigned long long h0 = r ? (unsigned long long)line_end[4 * r - 1] + 1 : st->t0;   // '@' line
-        const unsigned long long s0 = (unsigned long long)line_end[4 * r] + 1;                     // sequence line
-        const unsigned long long p0 = (unsigned long long)line_end[4 * r + 1] + 1;                 // '+' line
-        const unsigned long long q0 = (unsigned long long)line_end[4 * r + 2] + 1;                 // quality line
-        const unsigned long long e0 = (unsigned long long)line_end[4 * r + 3];
-        const unsigned long long len = p0 - 1 - s0, qlen = e0 - q0;
+    ing_check_chunk(text, st, line_end, a);
+    const unsigned n_lines = st->n_lines;
+    const unsigned r_lo = min(block_off[blockIdx.x], n_lines) / 4, r_hi = min(block_off[blockIdx.x + 1], n_lines) / 4;
+    const ull t0 = st->t0;
+    ull bases = 0, lookups = 0, out = 0;
+    bool bad = false;
+    for (unsigned r = r_lo + threadIdx.x; r < r_hi; r += ING_THREADS) {
+        const ull h0 = r ? (ull)line_end[4 * r - 1] + 1 : t0;      // '@' line
+        const ull s0 = (ull)line_end[4 * r] + 1;                    // sequence line
+        const ull p0 = (ull)line_end[4 * r + 1] + 1;                // '+' line
+        const ull q0 = (ull)line_end[4 * r + 2] + 1;                // quality line
+        const ull e0 = (ull)line_end[4 * r + 3];
+        const ull len = p0 - 1 - s0, qlen = e0 - q0;
         bool ok = text[h0] == '@' && text[p0] == '+' && len == qlen;
         if (len) { const uint8_t c = text[s0]; ok = ok && c != '>' && c != '+' && c != '@'; }
-        if (!ok) atomicOr(&st->irregular, 1u);
-        out_len[r] = len >= S2_K ? (unsigned)len + 1 : 0;       // records without a window are not copied (genome_compare.c:204)
+        bad |= !ok;
         bases += len;
-        if (len >= S2_K) lookups += len - (S2_K - 1);
+        if (len >= S2_K) { lookups += len - (S2_K - 1); out += len + 1; }      // records without a window are not copied (genome_compare.c:204)
     }
-    if (count_stats) {
+    if (bad) atomicOr(&st->irregular, 1u);
+    bases = ing_block_sum(bases); lookups = ing_block_sum(lookups); out = ing_block_sum(out);
+    if (threadIdx.x == 0) {
+        block_out[blockIdx.x] = (unsigned)out;
         if (bases) atomicAdd(&st->bases, bases);
         if (lookups) atomicAdd(&st->lookups, lookups);
     }
 }
 
-__global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ line_end,
-                                                               const unsigned *__restrict__ out_off, uint8_t *__restrict__ flat)
+// single CTA: exclusive scan of the blocks' output sizes; then the chunk's verdict (everything that can veto the
+// scan is known here), the carry, and the batch length the scan kernel will read
+__global__ void __launch_bounds__(ING_THREADS) ing_scan_out(unsigned *__restrict__ v, unsigned n, IngState *st, const unsigned *__restrict__ line_end,
+                                                             unsigned fasta, ull *__restrict__ rec_off)
 {
-    const unsigned n_rec = st->n_rec;
-    const int lane = threadIdx.x & 31;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned r = warp; r < n_rec; r += n_warps) {
-        const unsigned long long s0 = (unsigned long long)line_end[4 * r] + 1;
-        const unsigned len = line_end[4 * r + 1] - (unsigned)s0;
-        if (len < S2_K) continue;
-        uint8_t *dst = flat + out_off[r];
-        for (unsigned i = lane; i <= len; i += 32) dst[i] = text[s0 + i];       // includes the line's own '\n' = the separator
-    }
-}
-
-// end of chunk: totals, carry of the partial last record to the front of the buffer for the next chunk
-__global__ void __launch_bounds__(ING_THREADS) ing_fastq_finish(uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ line_end,
-                                                                 uint8_t *__restrict__ carry_tmp, int phase)
-{
-    __shared__ unsigned long long c_from, c_len;
+    const unsigned total = ing_scan_array(v, n);
     if (threadIdx.x == 0) {
-        const unsigned n_rec = st->n_rec;
-        c_from = n_rec ? (unsigned long long)line_end[4 * n_rec - 1] + 1 : st->t0;
-        c_len = st->t1 - c_from;
+        const unsigned n_done = fasta ? st->n_lines : 4 * st->n_rec;         // lines that belong to complete records
+        const ull c_from = n_done ? (ull)line_end[n_done - 1] + 1 : st->t0;
+        ull c_len = st->t1 - c_from;
         if (c_len > ING_MAXCARRY) { st->irregular = 1; c_len = 0; }
-        if (st->last_chunk && c_len) { st->irregular = 1; c_len = 0; }     // truncated last record: the host parser's business
+        if (st->last_chunk && c_len) { st->irregular = 1; c_len = 0; }       // truncated last record: the host parser's business
+        st->carry_from = c_from; st->carry_len = c_len;
+        st->flat_len = (fasta ? st->tail_len : 0u) + (ull)total;
+        st->skip = st->irregular;
+        if (rec_off) rec_off[st->n_rec] = st->flat_len;
     }
-    __syncthreads();
-    if (phase == 0) {
-        for (unsigned long long i = threadIdx.x; i < c_len; i += blockDim.x) carry_tmp[i] = text[c_from + i];
-    } else {
-        for (unsigned long long i = threadIdx.x; i < c_len; i += blockDim.x) text[ING_MAXCARRY - c_len + i] = carry_tmp[i];
+}
+
+// copy `n` bytes with one warp
+__device__ __forceinline__ void ing_warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, unsigned n, int lane)
+{
+    for (unsigned i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ block_off,
+                                                               const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
+                                                               uint8_t *__restrict__ flat, ull *__restrict__ rec_off)
+{
+    if (st->skip) return;
+    __shared__ unsigned s_src[ING_THREADS], s_len[ING_THREADS], s_dst[ING_THREADS];
+    const unsigned n_lines = st->n_lines;
+    const unsigned r_lo = min(block_off[blockIdx.x], n_lines) / 4, r_hi = min(block_off[blockIdx.x + 1], n_lines) / 4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned run = block_out[blockIdx.x];
+    for (unsigned r0 = r_lo; r0 < r_hi; r0 += ING_THREADS) {
+        const unsigned r = r0 + threadIdx.x;
+        unsigned s0 = 0, olen = 0;
+        if (r < r_hi) {
+            s0 = line_end[4 * r] + 1;
+            const unsigned len = line_end[4 * r + 1] - s0;
+            olen = len >= S2_K ? len + 1 : 0;                       // includes the line's own '\n' = the separator
+        }
+        unsigned total;
+        const unsigned at = run + ing_block_scan(olen, total);
+        s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
+        if (rec_off && r < r_hi) rec_off[r] = at;
         __syncthreads();
-        if (threadIdx.x == 0) { st->carry_len = c_len; st->records += st->n_rec; }
+        const unsigned cnt = min((unsigned)ING_THREADS, r_hi - r0);
+        for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) ing_warp_copy(flat + s_dst[e], text + s_src[e], s_len[e], lane);
+        __syncthreads();
+        run += total;
     }
 }
-
-__global__ void ing_begin_chunk(IngState *st, unsigned long long new_bytes, unsigned last_chunk, unsigned first_chunk)
-{
-    if (first_chunk) { st->carry_len = 0; st->tail_len = 0; }
-    st->first_chunk = first_chunk;
-    st->t0 = ING_MAXCARRY - st->carry_len;
-    st->t1 = ING_MAXCARRY + new_bytes;
-    st->last_chunk = last_chunk;
-    st->flat_len = 0;
-}
-
-// terminate a final line that lacks its '\n' (the parser the reference uses accepts that)
-__global__ void ing_terminate_last_line(uint8_t *text, IngState *st)
-{
-    if (st->last_chunk && st->t1 > st->t0 && text[st->t1 - 1] != '\n') { text[st->t1] = '\n'; st->t1 += 1; }
-}
-
-__global__ void ing_set_flat_len(IngState *st, const unsigned *total) { st->flat_len = *total; }
 
 // ------------------------------------------------------------------------------------------------
 // strict FASTA: '>' lines are headers, every other line is sequence (joined), nothing else
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ING_THREADS) ing_fasta_len(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ line_end,
-                                                              unsigned *__restrict__ out_len, int count_stats)
+__global__ void __launch_bounds__(ING_THREADS) ing_fasta_measure(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ block_off,
+                                                                  const unsigned *__restrict__ line_end, unsigned *__restrict__ block_out, IngChunkArgs a)
 {
+    ing_check_chunk(text, st, line_end, a);
     const unsigned n_lines = st->n_lines;
-    unsigned long long bases = 0, recs = 0;
-    for (unsigned L = blockIdx.x * blockDim.x + threadIdx.x; L < n_lines; L += gridDim.x * blockDim.x) {
-        const unsigned long long s0 = L ? (unsigned long long)line_end[L - 1] + 1 : st->t0;
+    const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
+    const ull t0 = st->t0;
+    ull bases = 0, recs = 0, out = 0;
+    bool bad = false;
+    for (unsigned L = l_lo + threadIdx.x; L < l_hi; L += ING_THREADS) {
+        const ull s0 = L ? (ull)line_end[L - 1] + 1 : t0;
         const unsigned len = line_end[L] - (unsigned)s0;
         const uint8_t first = len ? text[s0] : 0;
         const bool header = first == '>';
-        if (first == '@' || first == '+') atomicOr(&st->irregular, 1u);              // the reference's parser would switch to FASTQ rules
-        if (L == 0 && st->first_chunk && !header) atomicOr(&st->irregular, 1u);       // text before the first record
-        out_len[L] = header ? 1u : len;                                               // a header becomes the record separator
+        if (first == '@' || first == '+') bad = true;                              // the reference's parser would switch to FASTQ rules
+        if (L == 0 && a.first_chunk && !header) bad = true;                        // text before the first record
+        out += header ? 1u : len;                                                  // a header becomes the record separator
         if (header) ++recs; else bases += len;
     }
-    if (count_stats) {
+    if (bad) atomicOr(&st->irregular, 1u);
+    bases = ing_block_sum(bases); recs = ing_block_sum(recs); out = ing_block_sum(out);
+    if (threadIdx.x == 0) {
+        block_out[blockIdx.x] = (unsigned)out;
         if (bases) atomicAdd(&st->bases, bases);
         if (recs) atomicAdd(&st->records, recs);
     }
 }
 
-__global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ line_end,
-                                                               const unsigned *__restrict__ out_off, uint8_t *__restrict__ flat)
+__global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ block_off,
+                                                               const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
+                                                               uint8_t *__restrict__ flat)
 {
+    if (st->skip) return;
+    __shared__ unsigned s_src[ING_THREADS], s_len[ING_THREADS], s_dst[ING_THREADS];
     const unsigned n_lines = st->n_lines, tail = st->tail_len;
-    const int lane = threadIdx.x & 31;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    if (warp == 0) for (unsigned i = lane; i < tail; i += 32) flat[i] = st->tail[i];
-    for (unsigned L = warp; L < n_lines; L += n_warps) {
-        const unsigned long long s0 = L ? (unsigned long long)line_end[L - 1] + 1 : st->t0;
-        const unsigned len = line_end[L] - (unsigned)s0;
-        uint8_t *dst = flat + tail + out_off[L];
-        if (len && text[s0] == '>') { if (lane == 0) dst[0] = '\n'; continue; }
-        for (unsigned i = lane; i < len; i += 32) dst[i] = text[s0 + i];
+    const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const ull t0 = st->t0;
+    if (blockIdx.x == 0 && wid == 0) for (unsigned i = lane; i < tail; i += 32) flat[i] = st->tail[i];
+    unsigned run = tail + block_out[blockIdx.x];
+    for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
+        const unsigned L = l0 + threadIdx.x;
+        unsigned s0 = 0, olen = 0;
+        if (L < l_hi) {
+            s0 = L ? line_end[L - 1] + 1 : (unsigned)t0;
+            olen = line_end[L] - s0;
+            if (olen && text[s0] == '>') { olen = 1; s0 = 0xFFFFFFFFu; }            // header: one separator byte
+        }
+        unsigned total;
+        const unsigned at = run + ing_block_scan(olen, total);
+        s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
+        __syncthreads();
+        const unsigned cnt = min((unsigned)ING_THREADS, l_hi - l0);
+        for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) {
+            if (s_src[e] == 0xFFFFFFFFu) { if (lane == 0) flat[s_dst[e]] = '\n'; }
+            else ing_warp_copy(flat + s_dst[e], text + s_src[e], s_len[e], lane);
+        }
+        __syncthreads();
+        run += total;
     }
 }
 
-__global__ void ing_fasta_set_flat_len(IngState *st, const unsigned *total) { st->flat_len = (unsigned long long)st->tail_len + *total; }
-
-// end of a FASTA chunk: carry the partial last line, remember the last 30 bytes of the flat stream
-__global__ void __launch_bounds__(ING_THREADS) ing_fasta_finish(uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ line_end,
-                                                                 uint8_t *__restrict__ carry_tmp, const uint8_t *__restrict__ flat, int phase, int scan)
+// ------------------------------------------------------------------------------------------------
+// end of chunk: copy the partial last record in front of where the next chunk's text lands, FASTA tail, record
+// count, and the verdict of a finished file / group
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ING_THREADS) ing_finish(const uint8_t *__restrict__ text, uint8_t *__restrict__ text_next, IngState *st,
+                                                           const uint8_t *__restrict__ flat, unsigned fasta, IngResult *__restrict__ res)
 {
-    __shared__ unsigned long long c_from, c_len;
+    // the next chunk of a streamed file is inflated into ANOTHER buffer of the ring (perhaps already, behind its carry region)
+    const ull c_from = st->carry_from, c_len = st->carry_len, dst = ING_MAXCARRY - c_len;
+    for (ull i = threadIdx.x; i < c_len; i += ING_THREADS) text_next[dst + i] = text[c_from + i];
     if (threadIdx.x == 0) {
-        const unsigned n_lines = st->n_lines;
-        c_from = n_lines ? (unsigned long long)line_end[n_lines - 1] + 1 : st->t0;
-        c_len = st->t1 - c_from;
-        if (c_len > ING_MAXCARRY) { st->irregular = 1; c_len = 0; }
-    }
-    __syncthreads();
-    if (phase == 0) {
-        for (unsigned long long i = threadIdx.x; i < c_len; i += blockDim.x) carry_tmp[i] = text[c_from + i];
-    } else {
-        for (unsigned long long i = threadIdx.x; i < c_len; i += blockDim.x) text[ING_MAXCARRY - c_len + i] = carry_tmp[i];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            st->carry_len = c_len;
-            if (scan) {
-                const unsigned long long fl = st->flat_len;
-                const unsigned keep = fl < (S2_K - 1) ? (unsigned)fl : (S2_K - 1);
-                unsigned char tmp[32];
-                for (unsigned i = 0; i < keep; ++i) tmp[i] = flat[fl - keep + i];
-                for (unsigned i = 0; i < keep; ++i) st->tail[i] = tmp[i];
-                st->tail_len = keep;
-            }
+        if (!fasta) st->records += st->n_rec;
+        if (fasta && !st->skip) {
+            const ull fl = st->flat_len;
+            const unsigned keep = fl < (S2_K - 1) ? (unsigned)fl : (S2_K - 1);
+            unsigned char tmp[32];
+            for (unsigned i = 0; i < keep; ++i) tmp[i] = flat[fl - keep + i];
+            for (unsigned i = 0; i < keep; ++i) st->tail[i] = tmp[i];
+            st->tail_len = keep;
         }
+        if (res) { res->bases = st->bases; res->lookups = st->lookups; res->records = st->records; res->irregular = st->irregular; res->inf_overflow = st->inf_overflow; }
     }
 }
 
 // ---- detect mode (strain_detect pass 1 on ingested reads) ------------------------------------------
-__global__ void __launch_bounds__(ING_THREADS) ing_make_rec_off(const IngState *st, const unsigned *__restrict__ out_off, unsigned long long *__restrict__ rec_off)
-{
-    const unsigned n_rec = st->n_rec;
-    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_rec; r += gridDim.x * blockDim.x)
-        rec_off[r] = r < n_rec ? out_off[r] : st->flat_len;
-}
-
 // per-record results of this chunk -> the file-level arrays (record numbering continues across chunks)
-__global__ void __launch_bounds__(ING_THREADS) ing_store_records(const IngState *st, const unsigned *__restrict__ line_end, const unsigned *__restrict__ hits_c,
+__global__ void __launch_bounds__(ING_THREADS) ing_store_records(IngState *st, const unsigned *__restrict__ line_end, const unsigned *__restrict__ hits_c,
                                                                   const unsigned *__restrict__ inf_c, unsigned *__restrict__ len_all,
-                                                                  unsigned *__restrict__ hits_all, unsigned *__restrict__ inf_all, unsigned long long cap)
+                                                                  unsigned *__restrict__ hits_all, unsigned *__restrict__ inf_all, ull cap)
 {
+    if (st->skip) return;
     const unsigned n_rec = st->n_rec;
-    const unsigned long long base = st->records;
+    const ull base = st->records;
+    if (base + n_rec > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) st->inf_overflow = 1; return; }
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
-        if (base + r >= cap) break;
         len_all[base + r] = line_end[4 * r + 1] - (line_end[4 * r] + 1);
         hits_all[base + r] = hits_c[r];
         inf_all[base + r] = inf_c[r];
@@ -336,26 +448,27 @@ __global__ void __launch_bounds__(ING_THREADS) ing_store_records(const IngState 
 }
 
 // informative windows of this chunk (byte offsets in the flat batch) -> (record number, offset, canonical k-mer)
-__global__ void __launch_bounds__(ING_THREADS) ing_collect_inf(IngState *st, const uint8_t *__restrict__ flat, const unsigned long long *__restrict__ rec_off,
-                                                                const unsigned long long *__restrict__ pos_c, const unsigned long long *__restrict__ cnt_c,
-                                                                unsigned long long cap_c, unsigned *__restrict__ f_rec, unsigned *__restrict__ f_off,
-                                                                unsigned long long *__restrict__ f_kmer, unsigned long long *__restrict__ f_cnt, unsigned long long cap_f)
+__global__ void __launch_bounds__(ING_THREADS) ing_collect_inf(IngState *st, const uint8_t *__restrict__ flat, const ull *__restrict__ rec_off,
+                                                                const ull *__restrict__ pos_c, const ull *__restrict__ cnt_c,
+                                                                ull cap_c, unsigned *__restrict__ f_rec, unsigned *__restrict__ f_off,
+                                                                ull *__restrict__ f_kmer, ull *__restrict__ f_cnt, ull cap_f)
 {
-    const unsigned long long n = *cnt_c;
+    if (st->skip) return;
+    const ull n = *cnt_c;
     if (n > cap_c) { if (blockIdx.x == 0 && threadIdx.x == 0) st->inf_overflow = 1; }
     const unsigned n_rec = st->n_rec;
-    const unsigned long long base = st->records;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap_c; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long pos = pos_c[i];
+    const ull base = st->records;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap_c; i += (ull)gridDim.x * blockDim.x) {
+        const ull pos = pos_c[i];
         unsigned lo = 0, hi = n_rec;
         while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (rec_off[mid] <= pos) lo = mid; else hi = mid; }
-        unsigned long long fwd = 0;
+        ull fwd = 0;
         for (int b = 0; b < S2_K; ++b) {
             const unsigned c = flat[pos + b];
             const unsigned x = (c >> 1) & 3u;
             fwd = (fwd << 2) | (x ^ (x >> 1));
         }
-        const unsigned long long at = atomicAdd(f_cnt, 1ull);
+        const ull at = atomicAdd(f_cnt, 1ull);
         if (at < cap_f) { f_rec[at] = (unsigned)(base + lo); f_off[at] = (unsigned)(pos - rec_off[lo]); f_kmer[at] = s2_canonical(fwd, s2_revcomp31(fwd)); }
     }
 }
@@ -366,61 +479,95 @@ __global__ void __launch_bounds__(ING_THREADS) ing_collect_inf(IngState *st, con
 typedef CUresult (*decompress_fn)(CUmemDecompressParams *, size_t, unsigned int, size_t *, CUstream);
 typedef CUresult (*devattr_fn)(int *, CUdevice_attribute, CUdevice);
 
+enum { ING_COUNT = 1, ING_DETECT = 2 };
+
+#define ING_SLOTS 3
+struct IngSlot {                       // a chunk travels through one slot of the ring: copy engine -> decompression engine -> kernels
+    uint8_t *h_comp = nullptr;         // pinned staging for file sources (allocated on first use)
+    uint8_t *d_comp = nullptr;         // compressed bytes on the device
+    uint8_t *d_text = nullptr;         // [carry region: ING_MAXCARRY][inflated text: text_cap]
+    uint8_t *h_meta = nullptr, *d_meta = nullptr;      // [file_end: ull x ING_MAX_FILES][isz: u32 x ING_MAX_DBLOCKS]
+    unsigned *d_act = nullptr;         // bytes the engine produced per DEFLATE block
+    std::vector<CUmemDecompressParams> params;
+    cudaEvent_t h2d_done = nullptr;    // copy stream: the chunk's bytes are on the device
+    cudaEvent_t inflated = nullptr;    // inflate stream: the text is in d_text
+    cudaEvent_t consumed = nullptr;    // kernel stream: the chunk's kernels are through with this slot
+};
+
 struct s2_ingest {
     s2_ctx *ctx = nullptr;
-    cudaStream_t stream = nullptr;
-    uint8_t *h_comp[2] = { nullptr, nullptr }, *d_comp = nullptr, *d_text = nullptr, *d_flat = nullptr, *d_carry = nullptr;
-    cudaEvent_t h_free[2] = { nullptr, nullptr };      // pinned buffer b may be overwritten once its H2D copy is done
-    uint8_t *d_file = nullptr; size_t d_file_cap = 0;  // the whole compressed file, kept on the device between the two passes
-    unsigned *d_block_nl = nullptr, *d_line_end = nullptr, *d_out = nullptr, *d_total = nullptr, *d_act = nullptr;
-    IngState *d_state = nullptr, *h_state = nullptr;
+    // three streams, one per engine, so that the copy of chunk i+2, the inflate of chunk i+1 and the kernels of chunk i overlap
+    cudaStream_t stream = nullptr, copy_stream = nullptr, inflate_stream = nullptr;
+    size_t comp_chunk = 0, text_cap = 0; unsigned max_lines = 0;
+    IngSlot slot[ING_SLOTS];
+    uint64_t n_chunks = 0;             // chunks enqueued so far (slot = n_chunks % ING_SLOTS)
+    uint8_t *d_flat = nullptr;
+    unsigned *d_block_nl = nullptr, *d_block_out = nullptr, *d_line_end = nullptr;
+    IngState *d_state = nullptr;
+    IngResult *d_results = nullptr, *h_results = nullptr; unsigned n_results = 0;
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
-    bool fasta = false;                // format of the file being ingested (strict FASTA instead of strict FASTQ)
     // detect mode: chunk-local and file-level result arrays
     unsigned *d_hits_c = nullptr, *d_inf_c = nullptr;
-    unsigned long long *d_rec_off = nullptr, *d_pos_c = nullptr, *d_cnt_c = nullptr, *d_fcnt = nullptr;
-    unsigned *d_len_all = nullptr, *d_hits_all = nullptr, *d_inf_all = nullptr; unsigned long long rec_cap = 0;
-    unsigned *d_frec = nullptr, *d_foff = nullptr; unsigned long long *d_fkmer = nullptr; unsigned long long f_cap = 0;
-    struct Chunk { std::vector<CUmemDecompressParams> params; size_t src_off = 0, src_len = 0, text_len = 0; bool eof = false; };
-    std::vector<Chunk> chunks;                         // pass 1 records them, pass 2 replays them without touching the host
+    ull *d_rec_off = nullptr, *d_pos_c = nullptr, *d_cnt_c = nullptr, *d_fcnt = nullptr;
+    unsigned *d_len_all = nullptr, *d_hits_all = nullptr, *d_inf_all = nullptr; ull rec_cap = 0;
+    unsigned *d_frec = nullptr, *d_foff = nullptr; ull *d_fkmer = nullptr; ull f_cap = 0;
 };
 
 static void ingest_free(s2_ingest *g)
 {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
-    if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
-    for (int b = 0; b < 2; ++b) { cudaFreeHost(g->h_comp[b]); if (g->h_free[b]) cudaEventDestroy(g->h_free[b]); }
-    cudaFree(g->d_file); cudaFree(g->d_comp); cudaFree(g->d_text); cudaFree(g->d_flat); cudaFree(g->d_carry);
-    cudaFree(g->d_block_nl); cudaFree(g->d_line_end); cudaFree(g->d_out); cudaFree(g->d_total); cudaFree(g->d_act);
-    cudaFree(g->d_state); cudaFreeHost(g->h_state);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+    if (g->inflate_stream) { cudaStreamSynchronize(g->inflate_stream); cudaStreamDestroy(g->inflate_stream); }
+    if (g->stream) cudaStreamDestroy(g->stream);
+    for (auto &s : g->slot) {
+        cudaFreeHost(s.h_comp); cudaFree(s.d_comp); cudaFree(s.d_text); cudaFreeHost(s.h_meta); cudaFree(s.d_meta); cudaFree(s.d_act);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.inflated) cudaEventDestroy(s.inflated);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+    }
+    cudaFree(g->d_flat);
+    cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end);
+    cudaFree(g->d_state); cudaFree(g->d_results); cudaFreeHost(g->h_results);
     cudaFree(g->d_hits_c); cudaFree(g->d_inf_c); cudaFree(g->d_rec_off); cudaFree(g->d_pos_c); cudaFree(g->d_cnt_c); cudaFree(g->d_fcnt);
     cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all); cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);
+    cudaGetLastError();
     delete g;
 }
+
+#define ING_META_BYTES ((size_t)ING_MAX_FILES * 8 + (size_t)ING_MAX_DBLOCKS * 4)
 
 static int ingest_init(s2_ingest *g, s2_ctx *c)
 {
     g->ctx = c;
+    // S2_INGEST_CHUNK_MB: compressed bytes per chunk; S2_INGEST_TEXT_MB: inflated text per chunk (BGZF: <= 64 KB per block)
+    g->comp_chunk = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_CHUNK_MB", 16), 1), 1024) << 20;
+    g->text_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_TEXT_MB", 64), 4), 2048) << 20;
+    g->max_lines = (unsigned)(g->text_cap / 8);
     CK(cudaSetDevice(c->device));
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
-        CK(cudaHostAlloc((void **)&g->h_comp[b], ING_COMP_CHUNK, cudaHostAllocDefault));
-        CK(cudaEventCreateWithFlags(&g->h_free[b], cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g->inflate_stream, cudaStreamNonBlocking));
+    for (auto &s : g->slot) {
+        CK(cudaMalloc((void **)&s.d_comp, g->comp_chunk + 256));
+        CK(cudaMalloc((void **)&s.d_text, (size_t)ING_MAXCARRY + g->text_cap + ING_BLOCK));
+        CK(cudaHostAlloc((void **)&s.h_meta, ING_META_BYTES, cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&s.d_meta, ING_META_BYTES));
+        CK(cudaMalloc((void **)&s.d_act, (size_t)ING_MAX_DBLOCKS * sizeof(unsigned)));
+        CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.inflated, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
     }
-    CK(cudaMalloc((void **)&g->d_comp, ING_COMP_CHUNK + 256));
-    CK(cudaMalloc((void **)&g->d_text, (size_t)ING_MAXCARRY + ING_TEXT_CAP + 4096));
-    CK(cudaMalloc((void **)&g->d_flat, (size_t)ING_TEXT_CAP + ING_MAXCARRY + 4096));
-    CK(cudaMalloc((void **)&g->d_carry, ING_MAXCARRY));
-    const size_t n_blocks = ((size_t)ING_MAXCARRY + ING_TEXT_CAP) / 4096 + 2;
+    CK(cudaMalloc((void **)&g->d_flat, g->text_cap + ING_MAXCARRY + 4096));
+    const size_t n_blocks = ((size_t)ING_MAXCARRY + g->text_cap) / ING_BLOCK + 4;
     CK(cudaMalloc((void **)&g->d_block_nl, n_blocks * sizeof(unsigned)));
-    CK(cudaMalloc((void **)&g->d_line_end, (size_t)ING_MAX_LINES * sizeof(unsigned)));
-    CK(cudaMalloc((void **)&g->d_out, ((size_t)ING_MAX_LINES + 4) * sizeof(unsigned)));     // per record (FASTQ) or per line (FASTA)
-    CK(cudaMalloc((void **)&g->d_total, 4 * sizeof(unsigned)));
-    CK(cudaMalloc((void **)&g->d_act, (ING_TEXT_CAP / 256) * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&g->d_block_out, n_blocks * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&g->d_line_end, (size_t)g->max_lines * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_state, sizeof(IngState)));
-    CK(cudaHostAlloc((void **)&g->h_state, sizeof(IngState), cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&g->d_results, ING_MAX_RESULTS * sizeof(IngResult)));
+    CK(cudaHostAlloc((void **)&g->h_results, ING_MAX_RESULTS * sizeof(IngResult), cudaHostAllocDefault));
     // the decompression engine is reached through the driver; no link-time dependency on libcuda
     cudaDriverEntryPointQueryResult q;
     void *fn = nullptr, *fa = nullptr;
@@ -470,6 +617,7 @@ struct IngSource {
     int fd = -1;
     const uint8_t *mem = nullptr;
     size_t mem_len = 0;
+    bool eligible = false, bgzf = false, fasta = false;      // classification
     ssize_t size() const { if (mem) return (ssize_t)mem_len; struct stat sb; return fstat(fd, &sb) == 0 ? (ssize_t)sb.st_size : -1; }
     ssize_t peek(void *dst, size_t len, off_t off) const
     {
@@ -481,251 +629,426 @@ struct IngSource {
     }
 };
 
-// device work for one chunk whose bytes are already on the device: inflate (or copy), index, validate,
-// and - when scan is set - copy the sequence lines out and count them
-#define ING_CAP_C (8ull << 20)        /* informative windows one chunk may report */
-enum { ING_VALIDATE = 0, ING_COUNT = 1, ING_DETECT = 2 };
-
-static int ingest_chunk(s2_ingest *g, s2_table *t, int col, int mode, bool bgzf, const s2_ingest::Chunk &ch, const uint8_t *d_src, bool first)
+// first byte of the text inside a BGZF file ('@' FASTQ, '>' FASTA): inflate the start of the first non-empty member on
+// the host (a few microseconds: one z_stream per thread, only the member's own bytes are looked at)
+static int bgzf_first_text_byte(const IngSource &src)
 {
-    const bool scan = mode != ING_VALIDATE;
-    const bool fasta = g->fasta;
+    static thread_local z_stream z;
+    static thread_local bool z_ready = false;
+    static thread_local std::vector<uint8_t> buf;
+    off_t off = 0;
+    for (int guard = 0; guard < 64; ++guard) {                 // leading empty members
+        uint8_t head[32];
+        const uint8_t *p = head;
+        ssize_t hn;
+        if (src.mem) { hn = (size_t)off < src.mem_len ? (ssize_t)std::min<size_t>(src.mem_len - (size_t)off, 65536) : 0; p = src.mem + off; }
+        else hn = src.peek(head, sizeof head, off);
+        size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
+        if (hn <= 0 || !bgzf_block(p, (size_t)hn, &bs, &doff, &dlen, &isz)) return -1;
+        if (dlen == (size_t)-1) {                              // the header was readable, the member is not (yet)
+            if (src.mem || bs > 65536) return -1;
+            buf.resize(bs);
+            if (src.peek(buf.data(), bs, off) != (ssize_t)bs) return -1;
+            p = buf.data();
+            if (!bgzf_block(p, bs, &bs, &doff, &dlen, &isz) || dlen == (size_t)-1) return -1;
+        }
+        if (isz) {
+            if (!z_ready) { memset(&z, 0, sizeof z); if (inflateInit2(&z, -15) != Z_OK) return -1; z_ready = true; }
+            else if (inflateReset(&z) != Z_OK) return -1;
+            uint8_t out[16];
+            z.next_in = const_cast<uint8_t *>(p) + doff; z.avail_in = (uInt)dlen;
+            z.next_out = out; z.avail_out = sizeof out;
+            inflate(&z, Z_SYNC_FLUSH);
+            return z.total_out ? out[0] : -1;
+        }
+        off += (off_t)bs;
+    }
+    return -1;
+}
+
+static void ingest_classify(IngSource &src)
+{
+    uint8_t head[32];
+    const ssize_t hn = src.peek(head, sizeof head, 0);
+    src.bgzf = is_bgzf_header(head, hn);
+    const int first = src.bgzf ? bgzf_first_text_byte(src) : (hn >= 1 ? head[0] : -1);
+    src.fasta = first == '>';
+    src.eligible = first == '@' || first == '>';             // neither FASTQ nor FASTA (or an ordinary .gz): host reader
+    // uncompressed text gains nothing but PCIe from this path (the host parser does GB/s per thread): opt-in only
+    if (!src.bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 0)) src.eligible = false;
+}
+
+static thread_local s2_ingest *tl_ingest = nullptr;
+
+static s2_ingest *ingest_pipeline(s2_ctx *c)
+{
+    if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
+    if (!tl_ingest) {
+        tl_ingest = new s2_ingest();
+        if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return nullptr; }
+    }
+    return tl_ingest;
+}
+
+// ---- one chunk ------------------------------------------------------------------------------------------
+struct IngChunk {
+    size_t comp_len = 0;          // bytes staged in the slot's d_comp
+    size_t text_len = 0;
+    bool first = true, last = true;
+    unsigned n_files = 0;         // > 0: a group of whole files (their ends are in the slot's meta)
+};
+
+// wait until the slot's previous chunk has left d_comp / params / meta, and return the slot
+static int ingest_slot_begin(s2_ingest *g, IngSlot **out)
+{
+    IngSlot &s = g->slot[g->n_chunks % ING_SLOTS];
+    CK(cudaEventSynchronize(s.consumed));
+    s.params.clear();
+    *out = &s;
+    return 0;
+}
+
+static int ingest_staging(IngSlot &s, size_t bytes)
+{
+    if (!s.h_comp) CK(cudaHostAlloc((void **)&s.h_comp, bytes, cudaHostAllocDefault));
+    return 0;
+}
+
+// walk the BGZF members in h[0..avail) and append their DEFLATE streams to the slot's decompress list; the bytes will
+// sit at d_comp + comp_off, the text goes to text offset *text_len.  Stops at a partial member or when a cap would be
+// exceeded (then *full is set).  Returns the bytes consumed, or (size_t)-1 if this is not BGZF.
+static size_t ingest_walk_bgzf(s2_ingest *g, IngSlot &s, const uint8_t *h, size_t avail, size_t comp_off, size_t *text_len, bool *full)
+{
+    size_t used = 0;
+    unsigned *isz_list = (unsigned *)(s.h_meta + (size_t)ING_MAX_FILES * 8);
+    *full = false;
+    while (used < avail) {
+        size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
+        if (!bgzf_block(h + used, avail - used, &bs, &doff, &dlen, &isz)) return (size_t)-1;
+        if (dlen == (size_t)-1) break;                                   // partial block: the next chunk starts here
+        if (isz > 65536) return (size_t)-1;
+        if (*text_len + isz > g->text_cap || s.params.size() >= ING_MAX_DBLOCKS) { *full = true; break; }
+        if (isz) {
+            CUmemDecompressParams p; memset(&p, 0, sizeof p);
+            p.srcNumBytes = dlen; p.dstNumBytes = isz;
+            p.dstActBytes = (cuuint32_t *)(s.d_act + s.params.size());
+            p.src = s.d_comp + comp_off + used + doff;
+            p.dst = s.d_text + ING_MAXCARRY + *text_len;
+            p.algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
+            isz_list[s.params.size()] = isz;
+            s.params.push_back(p);
+            *text_len += isz;
+        }
+        used += bs;
+    }
+    return used;
+}
+
+// the device work of one chunk whose compressed bytes are being copied into the slot by the copy stream
+static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk &ch, bool bgzf, bool fasta, int mode, int col, unsigned inc,
+                          bool want_result)
+{
     s2_ctx *c = g->ctx;
     cudaStream_t st = g->stream;
-    const unsigned text_blocks = (unsigned)(((size_t)ING_MAXCARRY + ch.text_len) / 4096 + 1);      // covers [0, t1] of the text buffer
-    ing_begin_chunk<<<1, 1, 0, st>>>(g->d_state, ch.text_len, ch.eof ? 1u : 0u, first ? 1u : 0u);
+    // meta (group file ends, expected block sizes) travels with the chunk
+    const size_t n_db = bgzf ? s.params.size() : 0;
+    if (ch.n_files) CK(cudaMemcpyAsync(s.d_meta, s.h_meta, (size_t)ch.n_files * 8, cudaMemcpyHostToDevice, g->copy_stream));
+    if (n_db) CK(cudaMemcpyAsync(s.d_meta + (size_t)ING_MAX_FILES * 8, s.h_meta + (size_t)ING_MAX_FILES * 8, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
+    CK(cudaEventRecord(s.h2d_done, g->copy_stream));
+    CK(cudaStreamWaitEvent(g->inflate_stream, s.h2d_done, 0));
     if (bgzf) {
-        if (!ch.params.empty()) {
+        for (size_t i = 0; i < s.params.size(); i += ING_DECOMP_CALL) {
             size_t err_index = 0;
-            const CUresult r = g->decompress(const_cast<CUmemDecompressParams *>(ch.params.data()), ch.params.size(), 0, &err_index, (CUstream)st);
-            if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, err_index); return -1; }
+            const size_t n = std::min<size_t>(ING_DECOMP_CALL, s.params.size() - i);
+            const CUresult r = g->decompress(s.params.data() + i, n, 0, &err_index, (CUstream)g->inflate_stream);
+            if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, i + err_index); return -1; }
         }
-    } else if (ch.src_len) {
-        CK(cudaMemcpyAsync(g->d_text + ING_MAXCARRY, d_src, ch.src_len, cudaMemcpyDeviceToDevice, st));
+    } else if (ch.comp_len) {
+        CK(cudaMemcpyAsync(s.d_text + ING_MAXCARRY, s.d_comp, ch.comp_len, cudaMemcpyDeviceToDevice, g->inflate_stream));
     }
-    ing_terminate_last_line<<<1, 1, 0, st>>>(g->d_text, g->d_state);
-    ing_nl_count<<<text_blocks, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_block_nl);
-    ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_block_nl, text_blocks, nullptr, &g->d_state->n_lines);
-    ing_nl_scatter<<<text_blocks, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_block_nl, g->d_line_end);
-    ing_fastq_prepare<<<1, 1, 0, st>>>(g->d_state);
+    CK(cudaEventRecord(s.inflated, g->inflate_stream));
+    CK(cudaStreamWaitEvent(st, s.inflated, 0));
+    uint8_t *d_text = s.d_text;
+    uint8_t *d_text_next = g->slot[(g->n_chunks + 1) % ING_SLOTS].d_text;      // where a streamed file's next chunk will be inflated
+    IngChunkArgs a;
+    a.new_bytes = ch.text_len; a.first_chunk = ch.first ? 1u : 0u; a.last_chunk = ch.last ? 1u : 0u; a.inc = inc; a.fasta = fasta ? 1u : 0u;
+    a.n_files = ch.n_files; a.n_dblocks = (unsigned)n_db;
+    a.file_end = (const ull *)s.d_meta; a.isz = (const unsigned *)(s.d_meta + (size_t)ING_MAX_FILES * 8); a.act = s.d_act;
+    const unsigned n_blocks = (unsigned)(((size_t)ING_MAXCARRY + ch.text_len) / ING_BLOCK + 1);      // covers [0, t1] of the text buffer
+    const bool detect = mode == ING_DETECT;
+    ing_index_count<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, a);
+    ing_scan_lines<<<1, ING_THREADS, 0, st>>>(g->d_block_nl, n_blocks, g->d_state, g->max_lines, a.fasta);
+    ing_index_scatter<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->max_lines);
+    if (fasta) ing_fasta_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a);
+    else       ing_fastq_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a);
+    ing_scan_out<<<1, ING_THREADS, 0, st>>>(g->d_block_out, n_blocks, g->d_state, g->d_line_end, a.fasta, detect ? g->d_rec_off : nullptr);
+    const S2DevBatch *dev = reinterpret_cast<const S2DevBatch *>(&g->d_state->flat_len);
     if (fasta) {
-        ing_fasta_len<<<c->n_sm * 4, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, scan ? 1 : 0);
-        if (scan) {
-            ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_out, 0, &g->d_state->n_lines, g->d_total);
-            ing_fasta_set_flat_len<<<1, 1, 0, st>>>(g->d_state, g->d_total);
-            ing_fasta_copy<<<c->n_sm * 8, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, g->d_flat);
-            s2_launch_scan_count_devlen(g->d_flat, &g->d_state->flat_len, t->v, col, c->d_stats, c->grid_count, st);
-        }
-        ing_fasta_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, g->d_flat, 0, scan ? 1 : 0);
-        ing_fasta_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, g->d_flat, 1, scan ? 1 : 0);
-        CK(cudaGetLastError());
-        return 0;
-    }
-    ing_fastq_len<<<c->n_sm * 4, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, scan ? 1 : 0);
-    if (scan) {
-        ing_scan_u32<<<1, ING_THREADS, 0, st>>>(g->d_out, 0, &g->d_state->n_rec, g->d_total);
-        ing_set_flat_len<<<1, 1, 0, st>>>(g->d_state, g->d_total);
-        ing_fastq_copy<<<c->n_sm * 8, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_out, g->d_flat);
-        if (mode == ING_COUNT) {
-            s2_launch_scan_count_devlen(g->d_flat, &g->d_state->flat_len, t->v, col, c->d_stats, c->grid_count, st);
+        ing_fasta_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat);
+        s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, st);
+    } else {
+        ing_fastq_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat,
+                                                          detect ? g->d_rec_off : nullptr);
+        if (!detect) {
+            s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, st);
         } else {
-            const size_t max_rec = (size_t)ING_MAX_LINES / 4 + 4;
-            ing_make_rec_off<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_out, g->d_rec_off);
+            const size_t max_rec = (size_t)g->max_lines / 4 + 4;
             CK(cudaMemsetAsync(g->d_hits_c, 0, max_rec * sizeof(unsigned), st));
             CK(cudaMemsetAsync(g->d_inf_c, 0, max_rec * sizeof(unsigned), st));
-            CK(cudaMemsetAsync(g->d_cnt_c, 0, sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(g->d_cnt_c, 0, sizeof(ull), st));
             S2DetectOut out;
-            out.rec_off = (const uint64_t *)g->d_rec_off; out.n_rec = 0; out.n_rec_dev = &g->d_state->n_rec; out.n_bytes_dev = &g->d_state->flat_len;
+            out.rec_off = (const uint64_t *)g->d_rec_off; out.n_rec = 0; out.n_rec_dev = &g->d_state->n_rec;
             out.read_hits = g->d_hits_c; out.read_inf = g->d_inf_c; out.inf_pos = (uint64_t *)g->d_pos_c; out.inf_count = g->d_cnt_c; out.inf_cap = ING_CAP_C;
-            s2_launch_scan_detect_dev(g->d_flat, t->v, out, c->d_stats, c->grid_detect, st);
+            s2_launch_scan_detect_dev(g->d_flat, dev, t->v, out, c->d_stats, c->grid_detect, st);
             ing_collect_inf<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_flat, g->d_rec_off, g->d_pos_c, g->d_cnt_c, ING_CAP_C,
                                                                   g->d_frec, g->d_foff, g->d_fkmer, g->d_fcnt, g->f_cap);
             ing_store_records<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_line_end, g->d_hits_c, g->d_inf_c, g->d_len_all, g->d_hits_all,
                                                                     g->d_inf_all, g->rec_cap);
         }
     }
-    ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 0);
-    ing_fastq_finish<<<1, ING_THREADS, 0, st>>>(g->d_text, g->d_state, g->d_line_end, g->d_carry, 1);
+    ing_finish<<<1, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_flat, a.fasta, want_result ? g->d_results + g->n_results : nullptr);
+    CK(cudaEventRecord(s.consumed, st));                   // the slot (compressed bytes, decompress list, meta, text) may be reused
+    if (want_result) ++g->n_results;
     CK(cudaGetLastError());
+    ++g->n_chunks;
     return 0;
 }
 
-// Pass over the file FROM THE HOST: read() chunks of whole BGZF blocks (or of raw text) into two alternating
-// pinned buffers, copy them to the device (into the file cache when the file fits, so that the second pass
-// needs no I/O), and run the device stage.  Returns 0 ok, 1 irregular / unsupported, -1 error.
-static int ingest_pass_host(s2_ingest *g, s2_table *t, const IngSource &src, bool bgzf, int col, int mode, bool cache)
+// all verdicts enqueued so far -> h_results[0 .. n_results); the pipeline is idle afterwards
+static int ingest_collect(s2_ingest *g)
 {
-    cudaStream_t st = g->stream;
-    CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), st));
-    g->chunks.clear();
+    if (g->n_results) CK(cudaMemcpyAsync(g->h_results, g->d_results, g->n_results * sizeof(IngResult), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+
+// ---- a file too big for one chunk: streamed through the ring ----------------------------------------------
+// Returns 0 ok (verdict in *res), 1 not BGZF after all (nothing enqueued for the offending chunk; the verdict then
+// says irregular), -1 error.  Synchronous at the end.  *chunks_done: chunks that went to the device.
+static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mode, int col, unsigned inc, IngResult *res, uint64_t *chunks_done)
+{
+    CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), g->stream));
+    g->n_results = 0;
     off_t file_off = 0;
-    bool first = true, eof = false;
-    int buf = 0;
+    bool first = true, eof = false, broken = false;
+    uint64_t n = 0;
+    ull text_total = 0;
     while (!eof) {
-        const uint8_t *h = g->h_comp[buf];
+        IngSlot *sp;
+        if (ingest_slot_begin(g, &sp)) return -1;
+        IngSlot &s = *sp;
+        const uint8_t *h;
         ssize_t got;
         if (src.mem) {                                                           // caller's buffer: no staging copy
             h = src.mem + file_off;
-            got = (size_t)file_off < src.mem_len ? (ssize_t)std::min<size_t>(ING_COMP_CHUNK, src.mem_len - (size_t)file_off) : 0;
+            got = (size_t)file_off < src.mem_len ? (ssize_t)std::min<size_t>(g->comp_chunk, src.mem_len - (size_t)file_off) : 0;
         } else {
-            CK(cudaEventSynchronize(g->h_free[buf]));                            // its previous H2D copy is done
-            got = pread(src.fd, g->h_comp[buf], ING_COMP_CHUNK, file_off);
+            if (ingest_staging(s, g->comp_chunk)) return -1;
+            got = pread(src.fd, s.h_comp, g->comp_chunk, file_off);
             if (got < 0) { s2_set_error("read failed"); return -1; }
+            h = s.h_comp;
         }
-        uint8_t *d_dst = cache ? g->d_file + file_off : g->d_comp;
-        s2_ingest::Chunk local, &ch = cache ? (g->chunks.emplace_back(), g->chunks.back()) : local;
-        size_t used = 0, text_len = 0;
-        if (bgzf) {
-            while (used < (size_t)got) {
-                size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
-                if (!bgzf_block(h + used, (size_t)got - used, &bs, &doff, &dlen, &isz)) return 1;        // not BGZF after all
-                if (dlen == (size_t)-1) break;                                   // partial block: the next chunk starts here
-                if (isz > 65536) return 1;
-                if (text_len + isz > ING_TEXT_CAP) break;
-                if (isz) {
-                    CUmemDecompressParams p; memset(&p, 0, sizeof p);
-                    p.srcNumBytes = dlen; p.dstNumBytes = isz;
-                    p.dstActBytes = (cuuint32_t *)(g->d_act + ch.params.size());
-                    p.src = d_dst + used + doff;
-                    p.dst = g->d_text + ING_MAXCARRY + text_len;
-                    p.algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
-                    ch.params.push_back(p);
-                    text_len += isz;
-                }
-                used += bs;
-            }
-            if (used == 0 && got > 0) return 1;                                  // a block larger than the chunk: not bgzip output
+        IngChunk ch;
+        size_t used;
+        bool full = false;
+        if (src.bgzf) {
+            used = ingest_walk_bgzf(g, s, h, (size_t)got, 0, &ch.text_len, &full);
+            if (used == (size_t)-1 || (used == 0 && got > 0)) { broken = true; break; }       // not BGZF after all / a member larger than a chunk
         } else {
-            used = (size_t)got;
-            text_len = used;
+            used = std::min<size_t>((size_t)got, g->text_cap);
+            full = used < (size_t)got;
+            ch.text_len = used;
         }
-        eof = (size_t)got < ING_COMP_CHUNK && used == (size_t)got;              // short read and everything consumed
-        ch.src_off = (size_t)file_off; ch.src_len = used; ch.text_len = text_len; ch.eof = eof;
+        eof = (size_t)got < g->comp_chunk && used == (size_t)got && !full;      // short read and everything consumed
+        ch.comp_len = used; ch.first = first; ch.last = eof; ch.n_files = 0;
         file_off += (off_t)used;
-        if (!cache) CK(cudaStreamSynchronize(st));                               // ch.params (a local) and d_comp are reused
-        if (used) CK(cudaMemcpyAsync(d_dst, h, used, cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(g->h_free[buf], st));
-        if (ingest_chunk(g, t, col, mode, bgzf, ch, d_dst, first)) return -1;
-        if (!cache) CK(cudaStreamSynchronize(st));
+        text_total += ch.text_len;
+        if (mode == ING_DETECT && text_total / 64 + 1024 > g->rec_cap) {        // records shorter than 64 bytes of text on average overflow the lists (-> host path)
+            const ull want = std::max<ull>(text_total / 32 + 4096, g->rec_cap * 2);
+            unsigned *nl = nullptr, *nh = nullptr, *ni = nullptr;
+            if (cudaMalloc((void **)&nl, want * 4) || cudaMalloc((void **)&nh, want * 4) || cudaMalloc((void **)&ni, want * 4)) { s2_set_error("out of device memory"); return -1; }
+            CK(cudaStreamSynchronize(g->stream));
+            if (g->rec_cap) {
+                CK(cudaMemcpy(nl, g->d_len_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
+                CK(cudaMemcpy(nh, g->d_hits_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
+                CK(cudaMemcpy(ni, g->d_inf_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
+            }
+            cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all);
+            g->d_len_all = nl; g->d_hits_all = nh; g->d_inf_all = ni; g->rec_cap = want;
+        }
+        if (used) CK(cudaMemcpyAsync(s.d_comp, h, used, cudaMemcpyHostToDevice, g->copy_stream));
+        if (ingest_enqueue(g, t, s, ch, src.bgzf, src.fasta, mode, col, inc, eof)) return -1;
         first = false;
-        buf ^= 1;
+        ++n;
         if (got == 0) break;
     }
-    CK(cudaMemcpyAsync(g->h_state, g->d_state, sizeof(IngState), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return g->h_state->irregular ? 1 : 0;
-}
-
-// second pass when the compressed file is resident on the device: replay the recorded chunks, no host I/O
-static int ingest_pass_cached(s2_ingest *g, s2_table *t, bool bgzf, int col, int mode)
-{
-    cudaStream_t st = g->stream;
-    CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), st));
-    bool first = true;
-    for (const auto &ch : g->chunks) {
-        if (ingest_chunk(g, t, col, mode, bgzf, ch, g->d_file + ch.src_off, first)) return -1;
-        first = false;
+    if (chunks_done) *chunks_done = n;
+    if (broken) {
+        CK(cudaStreamSynchronize(g->stream));
+        g->n_results = 0;
+        memset(res, 0, sizeof *res);
+        res->irregular = 1;
+        return 1;
     }
-    CK(cudaMemcpyAsync(g->h_state, g->d_state, sizeof(IngState), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return g->h_state->irregular ? 1 : 0;
-}
-
-static thread_local s2_ingest *tl_ingest = nullptr;
-
-// first byte of the text inside a BGZF file ('@' FASTQ, '>' FASTA): inflate the first non-empty block on the host
-static int bgzf_first_text_byte(const IngSource &src)
-{
-    std::vector<uint8_t> buf(1 << 17);
-    const ssize_t got = src.peek(buf.data(), buf.size(), 0);
-    size_t used = 0;
-    while (got > 0 && used < (size_t)got) {
-        size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
-        if (!bgzf_block(buf.data() + used, (size_t)got - used, &bs, &doff, &dlen, &isz) || dlen == (size_t)-1) return -1;
-        if (isz) {
-            z_stream z; memset(&z, 0, sizeof z);
-            if (inflateInit2(&z, -15) != Z_OK) return -1;
-            uint8_t out[16];
-            z.next_in = buf.data() + used + doff; z.avail_in = (uInt)dlen;
-            z.next_out = out; z.avail_out = sizeof out;
-            inflate(&z, Z_SYNC_FLUSH);
-            const int first = z.total_out ? out[0] : -1;
-            inflateEnd(&z);
-            return first;
-        }
-        used += bs;
-    }
-    return -1;
-}
-
-// classify a source for the GPU path and make sure this thread's pipeline (and its file cache) exists.
-// Returns 0 ready, 1 not eligible, -1 error.
-static int ingest_prepare(s2_ctx *c, const IngSource &src, bool *bgzf_out, bool *cache_out, s2_ingest **g_out)
-{
-    uint8_t head[32];
-    const ssize_t hn = src.peek(head, sizeof head, 0);
-    const bool bgzf = is_bgzf_header(head, hn);
-    const int first = bgzf ? bgzf_first_text_byte(src) : (hn >= 1 ? head[0] : -1);
-    if (first != '@' && first != '>') return 1;                           // neither FASTQ nor FASTA (or an ordinary .gz): host reader
-    // uncompressed text gains nothing but PCIe from this path (the host parser does GB/s per thread): opt-in only
-    if (!bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 0)) return 1;
-    if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
-    if (!tl_ingest) {
-        tl_ingest = new s2_ingest();
-        if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return -1; }
-    }
-    s2_ingest *g = tl_ingest;
-    if (bgzf && !g->hw_deflate) return 1;
-    // keep the compressed file on the device between the two passes when it fits (S2_INGEST_CACHE_MB, default 2048)
-    const ssize_t size = src.size();
-    bool cache = size >= 0 && (uint64_t)size <= (s2_env_u64("S2_INGEST_CACHE_MB", 2048) << 20);
-    if (cache && (size_t)size + ING_COMP_CHUNK > g->d_file_cap) {
-        cudaStreamSynchronize(g->stream);
-        cudaFree(g->d_file); g->d_file = nullptr; g->d_file_cap = 0;
-        const size_t want = (size_t)size + ING_COMP_CHUNK + ((size_t)size >> 2);
-        if (cudaMalloc((void **)&g->d_file, want) == cudaSuccess) g->d_file_cap = want; else { cudaGetLastError(); cache = false; }
-    }
-    g->fasta = first == '>';
-    *bgzf_out = bgzf; *cache_out = cache; *g_out = g;
+    if (ingest_collect(g)) return -1;
+    *res = g->h_results[0];
+    g->n_results = 0;
     return 0;
 }
 
-static int ingest_open(s2_ctx *c, const char *path, IngSource *src, bool *bgzf_out, bool *cache_out, s2_ingest **g_out)
-{
-    src->fd = open(path, O_RDONLY);
-    if (src->fd < 0) return 1;
-    const int rc = ingest_prepare(c, *src, bgzf_out, cache_out, g_out);
-    if (rc) { close(src->fd); src->fd = -1; }
-    return rc;
-}
+// ---- count: any number of sources, small ones grouped ------------------------------------------------------
+struct IngGroup { std::vector<int> members; int result = -1; };
 
-static int ingest_count_source(s2_ingest *g, s2_table *t, const IngSource &src, bool bgzf, bool cache, int col, uint64_t *bases, uint64_t *lookups)
+static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &srcs, int col, int *rc_each, uint64_t *bases, uint64_t *lookups)
 {
-    int rc = ingest_pass_host(g, t, src, bgzf, col, ING_VALIDATE, cache);         // pass 1: prove the text is strict FASTQ / FASTA
-    if (rc == 0) rc = cache ? ingest_pass_cached(g, t, bgzf, col, ING_COUNT)      // pass 2: count
-                            : ingest_pass_host(g, t, src, bgzf, col, ING_COUNT, false);
-    if (rc == 0) {
-        if (bases) *bases = g->h_state->bases;
-        // FASTA records are not measured one by one on the device: every record is assumed to have at least one window
-        if (lookups) *lookups = g->fasta ? (g->h_state->bases > 30 * g->h_state->records ? g->h_state->bases - 30 * g->h_state->records : 0)
-                                         : g->h_state->lookups;
+    s2_ingest *g = ingest_pipeline(c);
+    if (!g) return -1;
+    uint64_t tot_bases = 0, tot_lookups = 0;
+    const int n = (int)srcs.size();
+    std::vector<IngGroup> groups;
+    std::vector<int> streamed;                       // too big for one chunk
+    std::vector<int> retry;                          // members of an irregular group: run alone
+    g->n_results = 0;
+
+    // the group being assembled in the current slot
+    IngSlot *s = nullptr;
+    IngGroup cur;
+    IngChunk ch;
+    bool cur_fasta = false, cur_bgzf = false;
+    auto flush = [&]() -> int {
+        if (!s || cur.members.empty()) return 0;
+        ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size();
+        CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), g->stream));
+        cur.result = (int)g->n_results;
+        if (ingest_enqueue(g, t, *s, ch, cur_bgzf, cur_fasta, ING_COUNT, col, 1u, true)) return -1;
+        groups.push_back(cur);
+        cur = IngGroup(); ch = IngChunk(); s = nullptr;
+        return 0;
+    };
+    auto harvest = [&]() -> int {                    // verdicts of everything enqueued so far
+        if (flush()) return -1;
+        if (ingest_collect(g)) return -1;
+        for (auto &gr : groups) {
+            const IngResult &r = g->h_results[gr.result];
+            if (!r.irregular) { tot_bases += r.bases; tot_lookups += srcs[gr.members[0]].fasta ? (r.bases > 30 * r.records ? r.bases - 30 * r.records : 0) : r.lookups; }
+            else if (gr.members.size() == 1) rc_each[gr.members[0]] = 1;
+            else retry.insert(retry.end(), gr.members.begin(), gr.members.end());
+        }
+        groups.clear();
+        g->n_results = 0;
+        return 0;
+    };
+    auto add_to_group = [&](int i, bool alone) -> int {       // 0 added, 1 does not fit one chunk (stream it), 2 not BGZF after all, -1 error
+        IngSource &src = srcs[i];
+        const ssize_t size = src.size();
+        if (size < 0) return 2;
+        const size_t cap = src.bgzf ? g->comp_chunk : std::min(g->comp_chunk, g->text_cap);
+        if ((size_t)size > cap) return 1;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
+            if (!s) { if (ingest_slot_begin(g, &s)) return -1; cur_fasta = src.fasta; cur_bgzf = src.bgzf; }
+            const uint8_t *h = src.mem;
+            if (!src.mem) {
+                if (ingest_staging(*s, g->comp_chunk)) return -1;
+                if (pread(src.fd, s->h_comp + ch.comp_len, (size_t)size, 0) != size) { s2_set_error("read failed"); return -1; }
+                h = s->h_comp + ch.comp_len;
+            }
+            size_t text_len = ch.text_len;
+            const size_t n_params = s->params.size();
+            if (src.bgzf) {
+                bool full = false;
+                const size_t used = ingest_walk_bgzf(g, *s, h, (size_t)size, ch.comp_len, &text_len, &full);
+                if (full) {                                      // the group's text or block list is full: close it and retry in a fresh one
+                    s->params.resize(n_params);
+                    if (cur.members.empty()) { s = nullptr; return 1; }          // does not fit a chunk on its own (nothing was enqueued on this slot)
+                    if (flush()) return -1;
+                    continue;
+                }
+                if (used != (size_t)size) { s->params.resize(n_params); if (cur.members.empty()) s = nullptr; return 2; }      // trailing garbage / truncated member
+            } else {
+                if (text_len + (size_t)size > g->text_cap) { if (cur.members.empty()) { s = nullptr; return 1; } if (flush()) return -1; continue; }
+                text_len += (size_t)size;
+            }
+            if (size) CK(cudaMemcpyAsync(s->d_comp + ch.comp_len, h, (size_t)size, cudaMemcpyHostToDevice, g->copy_stream));
+            ch.comp_len += (size_t)size;
+            ch.text_len = text_len;
+            ((ull *)s->h_meta)[cur.members.size()] = text_len;
+            cur.members.push_back(i);
+            if (alone && flush()) return -1;
+            return 0;
+        }
+        return 1;
+    };
+
+    const bool trace = s2_env_int("S2_INGEST_TRACE", 0) != 0;
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double us_classify = 0, us_group = 0;
+    const double t_begin = now();
+    for (int i = 0; i < n; ++i) {
+        const double ta = now();
+        ingest_classify(srcs[i]);                    // one file at a time, so that the first group is on its way while the rest is looked at
+        if (srcs[i].bgzf && !g->hw_deflate) srcs[i].eligible = false;
+        rc_each[i] = srcs[i].eligible ? 0 : 1;
+        const double tb = now();
+        us_classify += tb - ta;
+        if (!srcs[i].eligible) continue;
+        const int rc = add_to_group(i, false);
+        us_group += now() - tb;
+        if (rc < 0) return -1;
+        if (rc == 1) streamed.push_back(i);
+        if (rc == 2) rc_each[i] = 1;
+        if (g->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
     }
-    return rc;
+    const double t_enq = now();
+    if (harvest()) return -1;
+    if (trace) fprintf(stderr, "[s2 ingest] %d sources: classify %.0f us, group+enqueue %.0f us, enqueue done at %.0f us, verdicts at %.0f us, chunks so far %llu\n",
+                       n, us_classify, us_group, t_enq - t_begin, now() - t_begin, (unsigned long long)g->n_chunks);
+    // members of irregular groups, one by one (a group's verdict precedes its scan: nothing of it was counted)
+    std::vector<int> again;
+    again.swap(retry);
+    for (int i : again) {
+        const int rc = add_to_group(i, true);
+        if (rc < 0) return -1;
+        if (rc) rc_each[i] = 1;
+        if (g->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
+    }
+    if (harvest()) return -1;
+    // big files
+    for (int i : streamed) {
+        IngResult r; uint64_t done = 0;
+        const int rc = ingest_stream(g, t, srcs[i], ING_COUNT, col, 1u, &r, &done);
+        if (rc < 0) return -1;
+        if (r.irregular) {
+            // chunks before the first irregular one were counted: replay with increment -1 (same verdicts, same chunks)
+            if (done > 1 || (rc == 1 && done > 0)) {
+                IngResult r2; uint64_t d2 = 0;
+                if (ingest_stream(g, t, srcs[i], ING_COUNT, col, 0xFFFFFFFFu, &r2, &d2) < 0) return -1;
+            }
+            rc_each[i] = 1;
+        } else {
+            tot_bases += r.bases;
+            tot_lookups += srcs[i].fasta ? (r.bases > 30 * r.records ? r.bases - 30 * r.records : 0) : r.lookups;
+        }
+    }
+    if (bases) *bases = tot_bases;
+    if (lookups) *lookups = tot_lookups;
+    return 0;
 }
 
-// GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed or plain strict
-// FASTQ.  Returns 0 = done (counters updated, *bases / *lookups set), 1 = not handled (nothing was counted: use
-// the host reader), -1 = error.
+// GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed (or, opt-in, plain)
+// strict FASTQ / FASTA.  Returns 0 = done (counters updated, *bases / *lookups set), 1 = not handled (nothing was
+// counted: use the host reader), -1 = error.
 extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups)
 {
     if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
     if (t->partitioned) return 1;                                    // union tables keep the host reader + two-phase scan
-    IngSource src; bool bgzf, cache; s2_ingest *g;
-    int rc = ingest_open(c, path, &src, &bgzf, &cache, &g);
-    if (rc) return rc;
-    rc = ingest_count_source(g, t, src, bgzf, cache, col, bases, lookups);
-    close(src.fd);
-    return rc;
+    std::vector<IngSource> srcs(1);
+    srcs[0].fd = open(path, O_RDONLY);
+    if (srcs[0].fd < 0) return 1;
+    int rc_each = 1;
+    const int rc = ingest_count_sources(c, t, srcs, col, &rc_each, bases, lookups);
+    close(srcs[0].fd);
+    return rc < 0 ? rc : rc_each;
 }
 
 // The same for a file image that is already in host memory (the bytes of a BGZF or plain FASTA/FASTQ file; pinned
@@ -734,11 +1057,47 @@ extern "C" int s2_ingest_count_mem(s2_ctx *c, s2_table *t, const void *image, ui
 {
     if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
     if (t->partitioned) return 1;
-    IngSource src; src.mem = (const uint8_t *)image; src.mem_len = (size_t)n_bytes;
-    bool bgzf, cache; s2_ingest *g;
-    const int rc = ingest_prepare(c, src, &bgzf, &cache, &g);
-    if (rc) return rc;
-    return ingest_count_source(g, t, src, bgzf, cache, col, bases, lookups);
+    std::vector<IngSource> srcs(1);
+    srcs[0].mem = (const uint8_t *)image; srcs[0].mem_len = (size_t)n_bytes;
+    int rc_each = 1;
+    const int rc = ingest_count_sources(c, t, srcs, col, &rc_each, bases, lookups);
+    return rc < 0 ? rc : rc_each;
+}
+
+// Many files in one call: small files travel in groups (one launch sequence per group), verdicts are collected at
+// the end.  rc_each[i] = 0 done / 1 not handled (nothing of file i was counted).  *bases / *lookups: totals of the
+// files that were handled.  Returns 0, or -1 on error (then the counters are undefined).
+extern "C" int s2_ingest_count_mem_batch(s2_ctx *c, s2_table *t, const void *const *images, const uint64_t *n_bytes, int n, int col,
+                                         int *rc_each, uint64_t *bases, uint64_t *lookups)
+{
+    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
+    for (int i = 0; i < n; ++i) rc_each[i] = 1;
+    if (bases) *bases = 0;
+    if (lookups) *lookups = 0;
+    if (t->partitioned || n <= 0) return 0;
+    std::vector<IngSource> srcs((size_t)n);
+    for (int i = 0; i < n; ++i) { srcs[i].mem = (const uint8_t *)images[i]; srcs[i].mem_len = (size_t)n_bytes[i]; }
+    return ingest_count_sources(c, t, srcs, col, rc_each, bases, lookups);
+}
+
+extern "C" int s2_ingest_count_files(s2_ctx *c, s2_table *t, const char *const *paths, int n, int col, int *rc_each, uint64_t *bases, uint64_t *lookups)
+{
+    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
+    for (int i = 0; i < n; ++i) rc_each[i] = 1;
+    if (bases) *bases = 0;
+    if (lookups) *lookups = 0;
+    if (t->partitioned || n <= 0) return 0;
+    std::vector<IngSource> srcs;
+    std::vector<int> index;
+    for (int i = 0; i < n; ++i) {
+        const int fd = open(paths[i], O_RDONLY);
+        if (fd < 0) continue;
+        srcs.emplace_back(); srcs.back().fd = fd; index.push_back(i);
+    }
+    std::vector<int> rcs(srcs.size(), 1);
+    const int rc = srcs.empty() ? 0 : ingest_count_sources(c, t, srcs, col, rcs.data(), bases, lookups);
+    for (size_t k = 0; k < srcs.size(); ++k) { close(srcs[k].fd); rc_each[index[k]] = rcs[k]; }
+    return rc;
 }
 
 // Pass 1 of quantify_hits_PE (src/strain_detect.c:465-491) for every read of one file, inflated and split on the
@@ -749,27 +1108,23 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
 {
     memset(out, 0, sizeof *out);
     if (t->partitioned) return 1;
-    IngSource src; bool bgzf, cache; s2_ingest *g;
-    int rc = ingest_open(c, path, &src, &bgzf, &cache, &g);
-    if (rc) return rc;
+    s2_ingest *g = ingest_pipeline(c);
+    if (!g) return -1;
+    IngSource src;
+    src.fd = open(path, O_RDONLY);
+    if (src.fd < 0) return 1;
+    ingest_classify(src);
+    if (!src.eligible || src.fasta || (src.bgzf && !g->hw_deflate)) { close(src.fd); return 1; }      // per-read results are a FASTQ feature here
     const int fd = src.fd;
-    if (g->fasta) { close(fd); return 1; }                            // per-read results are a FASTQ feature here
-    rc = ingest_pass_host(g, t, src, bgzf, 0, ING_VALIDATE, cache);
-    if (rc) { close(fd); return rc; }
-    const unsigned long long n_rec = g->h_state->records;
-    const size_t max_rec = (size_t)ING_MAX_LINES / 4 + 4;
+    const size_t max_rec = (size_t)g->max_lines / 4 + 4;
     auto dev_alloc = [](void **p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
     if (dev_alloc((void **)&g->d_hits_c, max_rec * 4) || dev_alloc((void **)&g->d_inf_c, max_rec * 4) ||
         dev_alloc((void **)&g->d_rec_off, (max_rec + 1) * 8) || dev_alloc((void **)&g->d_pos_c, (ING_CAP_C + 1) * 8) ||
         dev_alloc((void **)&g->d_cnt_c, 8) || dev_alloc((void **)&g->d_fcnt, 8)) { s2_set_error("out of device memory"); close(fd); return -1; }
-    if (n_rec + 1 > g->rec_cap) {
-        cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all);
-        g->d_len_all = g->d_hits_all = g->d_inf_all = nullptr;
-        g->rec_cap = n_rec + n_rec / 8 + 1024;
-        if (cudaMalloc((void **)&g->d_len_all, g->rec_cap * 4) || cudaMalloc((void **)&g->d_hits_all, g->rec_cap * 4) ||
-            cudaMalloc((void **)&g->d_inf_all, g->rec_cap * 4)) { s2_set_error("out of device memory"); g->rec_cap = 0; close(fd); return -1; }
-    }
-    unsigned long long n_inf = 0;
+    ull n_inf = 0;
+    IngResult r;
+    memset(&r, 0, sizeof r);
+    int rc = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!g->d_frec) {
             if (!g->f_cap) g->f_cap = 1ull << 20;
@@ -777,10 +1132,10 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
                 cudaMalloc((void **)&g->d_fkmer, g->f_cap * 8)) { s2_set_error("out of device memory"); close(fd); return -1; }
         }
         CK(cudaMemsetAsync(g->d_fcnt, 0, 8, g->stream));
-        rc = cache ? ingest_pass_cached(g, t, bgzf, 0, ING_DETECT) : ingest_pass_host(g, t, src, bgzf, 0, ING_DETECT, false);
-        if (rc) break;
+        rc = ingest_stream(g, t, src, ING_DETECT, 0, 1u, &r, nullptr);
+        if (rc < 0) break;
+        if (rc || r.irregular || r.inf_overflow) { rc = 1; break; }              // irregular text / absurdly dense chunk: host path
         CK(cudaMemcpy(&n_inf, g->d_fcnt, 8, cudaMemcpyDeviceToHost));
-        if (g->h_state->inf_overflow) { rc = 1; break; }                         // absurdly dense chunk: host path
         if (n_inf <= g->f_cap) break;
         cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);          // list too small: grow and run the pass again
         g->d_frec = g->d_foff = nullptr; g->d_fkmer = nullptr;
@@ -789,7 +1144,8 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     }
     close(fd);
     if (rc) return rc == 2 ? -1 : rc;
-    out->n_records = n_rec; out->n_inf = n_inf; out->bases = g->h_state->bases;
+    const ull n_rec = r.records;
+    out->n_records = n_rec; out->n_inf = n_inf; out->bases = r.bases;
     out->len = (uint32_t *)malloc((n_rec + 1) * 4); out->hits = (uint32_t *)malloc((n_rec + 1) * 4); out->inf = (uint32_t *)malloc((n_rec + 1) * 4);
     out->inf_rec = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_off = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_kmer = (uint64_t *)malloc((n_inf + 1) * 8);
     CK(cudaMemcpy(out->len, g->d_len_all, n_rec * 4, cudaMemcpyDeviceToHost));

@@ -189,7 +189,7 @@ __device__ __forceinline__ void consume_group(uint32_t vmask, int g, const uint3
 template <int MODE>
 __device__ __forceinline__ void drain_queue(const S2TableView &t, const uint64_t *q_canon, const uint32_t *q_slot,
                                             const uint64_t *q_pos, uint32_t &qlen, uint32_t count, int lane,
-                                            uint32_t *__restrict__ counts_col, const S2DetectOut &dout, uint32_t &n_hits)
+                                            uint32_t *__restrict__ counts_col, const S2DetectOut &dout, uint32_t &n_hits, uint32_t inc)
 {
     const uint32_t base = qlen - count;
     if ((uint32_t)lane < count) {
@@ -202,7 +202,7 @@ __device__ __forceinline__ void drain_queue(const S2TableView &t, const uint64_t
         if (hit) {
             ++n_hits;
             if (MODE == S2_MODE_COUNT) {
-                atomicAdd(&counts_col[slot], 1u);                     // count[vec_column] += 1
+                atomicAdd(&counts_col[slot], inc);                    // count[vec_column] += 1
             } else {
                 uint32_t lo = 0, hi = dout.n_rec;                     // record r: rec_off[r] <= pos < rec_off[r+1]
                 while (hi - lo > 1) {
@@ -226,12 +226,17 @@ template <int MODE, int G, int MINB, bool PIPE>
 __global__ void __launch_bounds__(S2_THREADS, MINB)
 s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView t,
                uint32_t *__restrict__ counts_col, S2DetectOut dout, unsigned long long *__restrict__ stats,
-               const uint32_t *__restrict__ run_if, const unsigned long long *__restrict__ n_bytes_dev)
+               const uint32_t *__restrict__ run_if, const S2DevBatch *__restrict__ dev)
 {
     constexpr int NG = 16 / G;
     if (run_if && *run_if == 0) return;            // fallback launch after a partition overflow: normally a no-op
-    if (n_bytes_dev) n_bytes = *n_bytes_dev;       // batch produced on the device (GPU ingest): its length lives there
-    if (MODE == S2_MODE_DETECT && dout.n_rec_dev) { dout.n_rec = *dout.n_rec_dev; n_bytes = *dout.n_bytes_dev; }
+    uint32_t inc = 1u;
+    if (dev) {                                     // batch produced on the device (GPU ingest): length, veto and sign live there
+        if (dev->skip) return;
+        n_bytes = dev->n_bytes;
+        inc = dev->inc;
+    }
+    if (MODE == S2_MODE_DETECT && dout.n_rec_dev) dout.n_rec = *dout.n_rec_dev;
     __shared__ uint64_t q_canon_s[S2_WARPS][S2_QCAP];
     __shared__ uint32_t q_slot_s[S2_WARPS][S2_QCAP];
     __shared__ uint64_t q_pos_s[MODE == S2_MODE_DETECT ? S2_WARPS : 1][MODE == S2_MODE_DETECT ? S2_QCAP : 1];
@@ -329,7 +334,7 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
             }
             qlen += __popc(bal);
             __syncwarp();
-            if (qlen >= 32) drain_queue<MODE>(t, q_canon, q_slot, q_pos, qlen, 32, lane, counts_col, dout, n_hits);
+            if (qlen >= 32) drain_queue<MODE>(t, q_canon, q_slot, q_pos, qlen, 32, lane, counts_col, dout, n_hits, inc);
         }
         if (!PIPE) {
             const uint64_t nt = tile + n_warps;
@@ -340,19 +345,20 @@ s2_scan_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2TableView 
             }
         }
     }
-    if (qlen) drain_queue<MODE>(t, q_canon, q_slot, q_pos, qlen, qlen, lane, counts_col, dout, n_hits);
+    if (qlen) drain_queue<MODE>(t, q_canon, q_slot, q_pos, qlen, qlen, lane, counts_col, dout, n_hits, inc);
 
     n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
     n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
     if (lane == 0 && stats) {
-        if (n_hits) atomicAdd(&stats[0], (unsigned long long)n_hits);
-        if (n_valid && !run_if) atomicAdd(&stats[1], (unsigned long long)n_valid);   // fallback run: phase A counted them
+        const long long sign = (int)inc;                                              // +1, or -1 for a take-back replay
+        if (n_hits) atomicAdd(&stats[0], (unsigned long long)(sign * (long long)n_hits));
+        if (n_valid && !run_if) atomicAdd(&stats[1], (unsigned long long)(sign * (long long)n_valid));   // fallback run: phase A counted them
     }
 }
 
 // ---- variants -------------------------------------------------------------------------------------
 typedef void (*s2_scan_fn)(const uint8_t *, uint64_t, S2TableView, uint32_t *, S2DetectOut, unsigned long long *, const uint32_t *,
-                           const unsigned long long *);
+                           const S2DevBatch *);
 struct S2ScanVariant { const char *name; s2_scan_fn count_fn, detect_fn; };
 
 #define S2_VARIANT(G, MINB, PIPE) \
@@ -399,13 +405,13 @@ void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableV
         bases, n_bytes, t, t.counts + (uint64_t)col * t.n_slots, none, stats, nullptr, nullptr);
 }
 
-// same, but the batch length is read from device memory (the batch was produced by the GPU ingest kernels)
-void s2_launch_scan_count_devlen(const uint8_t *bases, const unsigned long long *n_bytes_dev, const S2TableView &t, int col,
-                                 unsigned long long *stats, int grid_blocks, cudaStream_t stream)
+// same, but the batch was produced by the GPU ingest kernels: length, veto and increment are read from device memory
+void s2_launch_scan_count_dev(const uint8_t *bases, const S2DevBatch *dev, const S2TableView &t, int col,
+                              unsigned long long *stats, int grid_blocks, cudaStream_t stream)
 {
     S2DetectOut none = {};
     g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(
-        bases, 0, t, t.counts + (uint64_t)col * t.n_slots, none, stats, nullptr, n_bytes_dev);
+        bases, 0, t, t.counts + (uint64_t)col * t.n_slots, none, stats, nullptr, dev);
 }
 
 void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
@@ -418,10 +424,10 @@ void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2Table
 
 
 // detect scan of a batch that was produced on the device (GPU ingest): lengths are in device memory
-void s2_launch_scan_detect_dev(const uint8_t *bases, const S2TableView &t, const S2DetectOut &out, unsigned long long *stats,
-                               int grid_blocks, cudaStream_t stream)
+void s2_launch_scan_detect_dev(const uint8_t *bases, const S2DevBatch *dev, const S2TableView &t, const S2DetectOut &out,
+                               unsigned long long *stats, int grid_blocks, cudaStream_t stream)
 {
-    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, 0, t, nullptr, out, stats, nullptr, nullptr);
+    g_variants[g_variant].detect_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, 0, t, nullptr, out, stats, nullptr, dev);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,11 +16,19 @@ struct S2TableView {
     int n_cols;
 };
 
+// a batch that was produced on the device (GPU ingest): its length lives there, together with a veto (the ingest
+// kernels found the text irregular: count nothing) and the increment (1, or 0xFFFFFFFF = -1 when a file that turned
+// out irregular after some of its chunks were counted is replayed to take its contribution back out)
+struct S2DevBatch {
+    unsigned long long n_bytes;
+    unsigned int skip;
+    unsigned int inc;
+};
+
 struct S2DetectOut {
     const uint64_t *rec_off;     // n_rec + 1 ascending byte offsets of the records inside the batch
     uint32_t n_rec;
-    const uint32_t *n_rec_dev;   // when set, the record count (and the batch length) are read from device memory
-    const unsigned long long *n_bytes_dev;
+    const uint32_t *n_rec_dev;   // when set, the record count is read from device memory (the batch is an S2DevBatch)
     uint32_t *read_hits;         // per record: table hits                 (src/strain_detect.c:481)
     uint32_t *read_inf;          // per record: informative hits           (src/strain_detect.c:482-483)
     uint64_t *inf_pos;           // batch byte offsets of informative windows (unordered)
@@ -36,10 +44,10 @@ void s2_launch_scan_count(const uint8_t *bases, uint64_t n_bytes, const S2TableV
 void s2_launch_scan_detect(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t,
                            const S2DetectOut &out, unsigned long long *stats, int grid_blocks,
                            cudaStream_t stream);
-void s2_launch_scan_count_devlen(const uint8_t *bases, const unsigned long long *n_bytes_dev, const S2TableView &t, int col,
-                                 unsigned long long *stats, int grid_blocks, cudaStream_t stream);
-void s2_launch_scan_detect_dev(const uint8_t *bases, const S2TableView &t, const S2DetectOut &out, unsigned long long *stats,
-                               int grid_blocks, cudaStream_t stream);
+void s2_launch_scan_count_dev(const uint8_t *bases, const S2DevBatch *dev, const S2TableView &t, int col,
+                              unsigned long long *stats, int grid_blocks, cudaStream_t stream);
+void s2_launch_scan_detect_dev(const uint8_t *bases, const S2DevBatch *dev, const S2TableView &t, const S2DetectOut &out,
+                               unsigned long long *stats, int grid_blocks, cudaStream_t stream);
 int  s2_scan_blocks_per_sm(int mode);
 // two-phase (radix partition, then per-partition probe) count scan for tables larger than L2
 #define S2_NPART 32

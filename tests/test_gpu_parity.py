@@ -476,9 +476,19 @@ def _ingest_fixture(s2, tmp, n_reads=60_000, seed=0):
     return strain, reads
 
 
-def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path, monkeypatch):
+def _ingest_chunks(ctx, monkeypatch, chunk_mb):
+    """small chunks stream a file through the two-slot ring in many pieces; the defaults take it as one chunk"""
+    if chunk_mb:
+        monkeypatch.setenv("S2_INGEST_CHUNK_MB", str(chunk_mb[0]))
+        monkeypatch.setenv("S2_INGEST_TEXT_MB", str(chunk_mb[1]))
+    ctx.ingest_reset()
+
+
+@pytest.mark.parametrize("chunk_mb", [(2, 8), None], ids=["streamed", "one_chunk"])
+def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path, monkeypatch, chunk_mb):
     from strainer2_b200 import synth
     monkeypatch.setenv("S2_GPU_INGEST_PLAIN", "1")
+    _ingest_chunks(ctx, monkeypatch, chunk_mb)
     tmp = str(tmp_path)
     strain, reads = _ingest_fixture(s2, tmp, 340_000)                  # ~100 MB of text: several ingest chunks
     data = synth.fastq_bytes(reads)
@@ -506,12 +516,17 @@ def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path, mo
         assert st.hits == want.hits and np.array_equal(t.counts(2), t.counts(1))
     assert ctx.ingest_count_mem(t, np.frombuffer(b"junk\n" + data[:5000], dtype=np.uint8), 3)[0] == 1
     t.free()
+    ctx.ingest_reset()
 
 
-def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path):
+@pytest.mark.parametrize("chunk_mb", [(1, 4), None], ids=["streamed", "one_chunk"])
+def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path, monkeypatch, chunk_mb):
+    """irregular text is never counted: in one chunk the verdict precedes the scan; in a streamed file the chunks
+    that were counted before the irregular one are taken back out (replay with increment -1)"""
     from strainer2_b200 import synth
+    _ingest_chunks(ctx, monkeypatch, chunk_mb)
     tmp = str(tmp_path)
-    strain, reads = _ingest_fixture(s2, tmp, 3000, seed=1)
+    strain, reads = _ingest_fixture(s2, tmp, 60_000 if chunk_mb else 3000, seed=1)       # streamed: ~20 MB of text, 5+ chunks
     good = synth.fastq_bytes(reads)
     r0 = reads[0].tobytes()
     cases = {
@@ -521,18 +536,93 @@ def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path):
         "qual_len": good + b"@q\n" + r0 + b"\n+\n" + b"I" * 149 + b"\n",
         "fasta_inside": good + b">fa\n" + r0 + b"\n",
         "junk_first": b"junk\n" + good,
+        "middle": good[:len(good) // 2] + b"@x\nACGT\n+\nII\n" + good[len(good) // 2:],
     }
     t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    want = ctx.scan_count(t, synth.reads_to_flat(reads), 2)
+    assert want.hits > 1000
+    ctx.sync()
     for name, data in cases.items():
         p = os.path.join(tmp, name + ".fastq.gz")
         synth.write_bgzf(p, data)
         rc, _, _ = ctx.ingest_count_file(t, p, 1)
+        st = ctx.sync()
         assert rc == 1, name
-        assert int(t.counts(1).sum()) == 0, name                     # the validation pass counted nothing
+        assert int(t.counts(1).sum()) == 0, name                     # nothing counted, or everything taken back
+        assert st.hits == 0, name
+    # a BGZF file cut in the middle of a member (streamed: the earlier chunks are taken back)
+    whole = synth.bgzf_bytes(good)
+    open(os.path.join(tmp, "cut.fastq.gz"), "wb").write(whole[:len(whole) * 3 // 4])
+    assert ctx.ingest_count_file(t, os.path.join(tmp, "cut.fastq.gz"), 1)[0] == 1
+    assert int(t.counts(1).sum()) == 0 and ctx.sync().hits == 0
     # a plain single-member gzip is not BGZF: host reader
-    synth.write_reads_fastq(os.path.join(tmp, "plain.fastq.gz"), reads)
+    synth.write_reads_fastq(os.path.join(tmp, "plain.fastq.gz"), reads[:3000])
     assert ctx.ingest_count_file(t, os.path.join(tmp, "plain.fastq.gz"), 1)[0] == 1
+    # and the regular file itself is counted
+    synth.write_bgzf(os.path.join(tmp, "good.fastq.gz"), good)
+    assert ctx.ingest_count_file(t, os.path.join(tmp, "good.fastq.gz"), 1)[0] == 0
+    assert ctx.sync().hits == want.hits and np.array_equal(t.counts(1), t.counts(2))
     t.free()
+    ctx.ingest_reset()
+
+
+def test_gpu_ingest_groups_of_small_files(s2, ctx, tmp_path, monkeypatch):
+    """many files per call: small files share a chunk (texts back to back); an irregular member sends its group back
+    to be run file by file; rc_each tells which files were not handled; counters = sum over the handled files"""
+    from strainer2_b200 import synth
+    monkeypatch.setenv("S2_INGEST_CHUNK_MB", "2")
+    monkeypatch.setenv("S2_INGEST_TEXT_MB", "8")
+    ctx.ingest_reset()
+    tmp = str(tmp_path)
+    rng = synth.rng_for(11, 0)
+    strain = synth.genome(rng, 300_000, 4, n_runs=2)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for c in strain]
+    files, handled = [], []
+    # 30 FASTA genomes of 0.2 - 1.2 Mb (several groups of 8 MB text), relatives of the strain among them
+    for i in range(30):
+        contigs = [synth.mutate(c, 0.01 * (1 + i % 3), rng) for c in strain[: 1 + i % 4]] + [synth.random_bases(rng, 50_000 * (1 + i % 5))]
+        text = synth.fasta_bytes(contigs, 60 + i)
+        if i == 7:
+            text = text[:-1]                                  # no final newline inside a group: irregular there, fine alone
+        if i == 12:
+            text = text.replace(b"\n", b"\r\n", 5)             # irregular wherever it is
+        files.append(("g%d.fa.gz" % i, synth.bgzf_bytes(text)))
+        handled.append(i != 12)
+    # FASTQ files (a group of their own), one truncated, one with a record count that is not a multiple of 4 lines
+    for i in range(6):
+        reads = synth.sample_reads(rng, clean, 4000 + 500 * i, 100 + 10 * i, sub_rate=0.01, n_rate=1e-4)
+        text = synth.fastq_bytes(reads)
+        if i == 2:
+            text = text[:-40]
+        if i == 4:
+            text += b"@half\nACGT\n"
+        files.append(("r%d.fq.gz" % i, synth.bgzf_bytes(text)))
+        handled.append(i not in (2, 4))
+    files.append(("ordinary.fa.gz", __import__("gzip").compress(synth.fasta_bytes(strain))))
+    handled.append(False)
+    files.append(("big.fa.gz", synth.bgzf_bytes(synth.fasta_bytes([synth.mutate(np.concatenate(clean), 0.02, rng)] * 30, 80))))    # 9 MB of text: streamed
+    handled.append(True)
+    for name, data in files:
+        open(os.path.join(tmp, name), "wb").write(data)
+    # expected: the host reader on the handled files
+    want_hits = 0
+    for (name, _), h in zip(files, handled):
+        if h:
+            want_hits += ctx.scan_count(t, s2.load_flat(os.path.join(tmp, name)), 1).hits
+    assert want_hits > 100_000
+    images = [np.frombuffer(d, dtype=np.uint8) for _, d in files]
+    rcs, bases, lookups = ctx.ingest_count_mem_batch(t, [a.ctypes.data for a in images], [a.size for a in images], 2)
+    st = ctx.sync()
+    assert [rc == 0 for rc in rcs] == handled
+    assert st.hits == want_hits and np.array_equal(t.counts(2), t.counts(1))
+    rcs, bases2, lookups2 = ctx.ingest_count_files(t, [os.path.join(tmp, n) for n, _ in files], 3)
+    st = ctx.sync()
+    assert [rc == 0 for rc in rcs] == handled and bases2 == bases
+    assert st.hits == want_hits and np.array_equal(t.counts(3), t.counts(1))
+    t.free()
+    ctx.ingest_reset()
 
 
 def test_executable_with_bgzf_inputs_matches_oracle(s2, golden_dir, tmp_path):
@@ -615,8 +705,10 @@ def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_p
     assert p.stderr == o.stderr
 
 
-def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_path, monkeypatch):
+@pytest.mark.parametrize("chunk_mb", [(2, 8), None], ids=["streamed", "one_chunk"])
+def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_path, monkeypatch, chunk_mb):
     monkeypatch.setenv("S2_GPU_INGEST_PLAIN", "1")
+    _ingest_chunks(ctx, monkeypatch, chunk_mb)
     """multi-line FASTA (BGZF and plain) through the GPU ingest: sequence lines joined on the device, headers become
     separators, chunk boundaries inside long contigs; irregular FASTA goes back to the host reader"""
     from strainer2_b200 import synth
@@ -624,8 +716,8 @@ def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_pat
     rng = synth.rng_for(9, 0)
     strain = synth.genome(rng, 400_000, 3, n_runs=3)
     synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
-    # ~130 MB of FASTA text: one 60 Mb contig (crosses ingest chunks) + relatives of the strain + short contigs
-    big = [synth.random_bases(rng, 60_000_000)] + [synth.mutate(c, 0.01, rng) for c in strain] * 20 + [synth.random_bases(rng, n) for n in (5, 30, 31, 200)]
+    # ~35 MB of FASTA text: one 24 Mb contig (crosses ingest chunks) + relatives of the strain + short contigs
+    big = [synth.random_bases(rng, 24_000_000)] + [synth.mutate(c, 0.01, rng) for c in strain] * 20 + [synth.random_bases(rng, n) for n in (5, 30, 31, 200)]
     big[0][1_000_000:1_400_000] = strain[0][:400_000] if strain[0].size >= 400_000 else big[0][1_000_000:1_400_000]
     import io
     def fasta_text(recs, wrap):
@@ -658,6 +750,9 @@ def test_gpu_ingest_fasta_genomes_equal_host_reader(s2, ctx, golden_dir, tmp_pat
         assert ctx.ingest_count_file(t, os.path.join(tmp, name + ".fa.gz"), 2)[0] == 1, name
         assert int(t.counts(2).sum()) == 0
     t.free()
+    ctx.ingest_reset()
+    if chunk_mb:
+        return
     # the executable on the golden count case with every input re-packed as BGZF: bytes equal the reference's
     d = os.path.join(golden_dir, "count_edge")
     for lst in ("listA.txt", "listB.txt", "listC.txt"):

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--genomes", type=int, default=16)
+    ap.add_argument("--genomes", type=int, default=64)
     ap.add_argument("--distinct", type=int, default=4, help="distinct genome images (cycled)")
     ap.add_argument("--reads", type=int, default=400_000)
     ap.add_argument("--reps", type=int, default=3)
