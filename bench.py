@@ -325,12 +325,13 @@ def main():
     # the genomes of batch 0 once more, as the files the reference would read: BGZF-compressed FASTA images
     first0 = 1000 * rank + 10_000 * (world > 1)
     imgs = make_file_images(strain, first0, G)
-    img_bufs = []
+    arena = s2.PinnedBuffer(sum(len(z) for z in imgs))     # the images back to back, like files read into one buffer
+    ptrs, sizes, at = [], [], 0
     for z in imgs:
-        pb = s2.PinnedBuffer(len(z))
-        pb.array[:] = np.frombuffer(z, dtype=np.uint8)
-        img_bufs.append(pb)
-    ptrs, sizes = [pb.ptr for pb in img_bufs], [pb.n for pb in img_bufs]
+        arena.array[at:at + len(z)] = np.frombuffer(z, dtype=np.uint8)
+        ptrs.append(arena.ptr + at); sizes.append(len(z))
+        at += len(z)
+    img_bufs = [arena]
     del imgs
     step_bases = [b for _, b, _ in batches]
     step_lookups = [l for _, _, l in batches]

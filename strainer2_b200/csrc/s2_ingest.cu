@@ -143,10 +143,52 @@ __device__ __forceinline__ unsigned nl_mask16(const uint8_t *text, ull base, ull
     return nl & range;
 }
 
+// The per-block kernels end with a step that needs every block's result (the scan over the blocks' counts, the
+// carry and verdict of the chunk): the block that finishes LAST does it (fence, then a ticket), which saves a
+// kernel boundary per step - a chunk is a chain of dependent launches, so each boundary is pure latency.
+__device__ __forceinline__ bool ing_last_block(unsigned *ticket)
+{
+    __shared__ bool last;
+    __threadfence();                       // this thread's results before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        last = t == gridDim.x - 1;
+        if (last) *ticket = 0;             // ready for the next launch
+    }
+    __syncthreads();
+    if (last) __threadfence();
+    return last;
+}
+
+// single CTA: exclusive scan of v[0..n) in place, v[n] = total -> returned to every thread (reads bypass L1: the
+// values were written by other blocks of the same launch)
+__device__ __forceinline__ unsigned ing_scan_array(unsigned *v, unsigned n)
+{
+    __shared__ unsigned carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (unsigned b0 = 0; b0 < n; b0 += ING_THREADS * 4) {
+        unsigned x[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const unsigned i = b0 + threadIdx.x * 4 + k; x[k] = i < n ? __ldcg(v + i) : 0; sum += x[k]; }
+        unsigned total;
+        unsigned ex = ing_block_scan(sum, total) + carry_s;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const unsigned i = b0 + threadIdx.x * 4 + k; if (i < n) v[i] = ex; ex += x[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) v[n] = carry_s;
+    return carry_s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // newline index: count per 16 KB block -> scan over blocks -> scatter
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, IngState *st, unsigned *__restrict__ block_nl, IngChunkArgs a)
+__global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, IngState *st, unsigned *block_nl,
+                                                                unsigned short *__restrict__ masks, IngChunkArgs a, unsigned max_lines, unsigned *ticket)
 {
     const ull carry = a.first_chunk ? 0ull : st->carry_len;
     const ull t0 = ING_MAXCARRY - carry, t1 = ING_MAXCARRY + a.new_bytes;
@@ -159,6 +201,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, In
         unsigned cr;
         unsigned m = nl_mask16(text, base, t0, t1, &cr);
         if (term && t1 >= base && t1 < base + 16) { m |= 1u << (unsigned)(t1 - base); text[t1] = '\n'; }
+        masks[base >> 4] = (unsigned short)m;                      // the scatter pass reads these 2 bytes instead of the 16 of text
         n += __popc(m);
         any_cr |= cr;
     }
@@ -172,55 +215,32 @@ __global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, In
         st->inc = a.inc; st->flat_len = 0;
         if (a.first_chunk) st->tail_len = 0;
     }
-}
-
-// single CTA: exclusive scan of v[0..n) in place, v[n] = total -> returned to every thread
-__device__ __forceinline__ unsigned ing_scan_array(unsigned *__restrict__ v, unsigned n)
-{
-    __shared__ unsigned carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (unsigned b0 = 0; b0 < n; b0 += ING_THREADS * 4) {
-        unsigned x[4], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const unsigned i = b0 + threadIdx.x * 4 + k; x[k] = i < n ? v[i] : 0; sum += x[k]; }
-        unsigned total;
-        unsigned ex = ing_block_scan(sum, total) + carry_s;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const unsigned i = b0 + threadIdx.x * 4 + k; if (i < n) v[i] = ex; ex += x[k]; }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) v[n] = carry_s;
-    return carry_s;
-}
-
-// the total becomes the line count of the chunk
-__global__ void __launch_bounds__(ING_THREADS) ing_scan_lines(unsigned *__restrict__ v, unsigned n, IngState *st, unsigned max_lines, unsigned fasta)
-{
-    unsigned lines = ing_scan_array(v, n);
+    if (!ing_last_block(ticket)) return;
+    // the last block: counts -> offsets; the total is the line count of the chunk
+    unsigned lines = ing_scan_array(block_nl, gridDim.x);
     if (threadIdx.x == 0) {
-        if (lines > max_lines) { st->irregular = 1; lines = 0; }       // shorter average lines than 8 bytes: not a sequence file
+        if (lines > max_lines) { atomicOr(&st->irregular, 1u); lines = 0; }       // shorter average lines than 8 bytes: not a sequence file
         st->n_lines = lines;
-        st->n_rec = fasta ? 0u : lines / 4;
+        st->n_rec = a.fasta ? 0u : lines / 4;
     }
 }
 
-__global__ void __launch_bounds__(ING_THREADS) ing_index_scatter(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ block_off,
+__global__ void __launch_bounds__(ING_THREADS) ing_index_scatter(const unsigned short *__restrict__ masks, const unsigned *__restrict__ block_off,
                                                                   unsigned *__restrict__ line_end, unsigned max_lines)
 {
-    const ull t0 = st->t0, t1 = st->t1;
     unsigned r = block_off[blockIdx.x];
+    unsigned m[ING_TILES];
+#pragma unroll
+    for (unsigned k = 0; k < ING_TILES; ++k) m[k] = masks[((ull)blockIdx.x * ING_BLOCK + k * ING_TILE) / 16 + threadIdx.x];
+#pragma unroll
     for (unsigned k = 0; k < ING_TILES; ++k) {
         const ull base = (ull)blockIdx.x * ING_BLOCK + k * ING_TILE + threadIdx.x * 16;
-        unsigned cr;
-        unsigned m = nl_mask16(text, base, t0, t1, &cr);
         unsigned total;
-        unsigned at = r + ing_block_scan(__popc(m), total);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
+        unsigned at = r + ing_block_scan(__popc(m[k]), total);
+        unsigned mm = m[k];
+        while (mm) {
+            const int b = __ffs(mm) - 1;
+            mm &= mm - 1;
             if (at < max_lines) line_end[at] = (unsigned)(base + b);       // the text buffer is < 4 GiB
             ++at;
         }
@@ -251,12 +271,32 @@ __device__ __forceinline__ void ing_check_chunk(const uint8_t *__restrict__ text
     }
 }
 
+// the chunk's verdict (everything that can veto the scan is known once all blocks are measured), the carry, and the
+// batch length the scan kernel will read.  Runs in the last block of the measure kernels, after the scan over the
+// blocks' output sizes.
+__device__ __forceinline__ void ing_chunk_verdict(IngState *st, const unsigned *line_end, unsigned total, unsigned fasta, ull *rec_off)
+{
+    const unsigned irregular = atomicOr(&st->irregular, 0u);                 // what every block reported (L2)
+    const unsigned n_done = fasta ? st->n_lines : 4 * st->n_rec;             // lines that belong to complete records
+    const ull c_from = n_done ? (ull)__ldcg(line_end + n_done - 1) + 1 : st->t0;
+    ull c_len = st->t1 - c_from;
+    unsigned bad = irregular;
+    if (c_len > ING_MAXCARRY) { bad = 1; c_len = 0; }
+    if (st->last_chunk && c_len) { bad = 1; c_len = 0; }                     // truncated last record: the host parser's business
+    if (bad) st->irregular = 1;
+    st->carry_from = c_from; st->carry_len = c_len;
+    st->flat_len = (fasta ? st->tail_len : 0u) + (ull)total;
+    st->skip = bad;
+    if (rec_off) rec_off[st->n_rec] = st->flat_len;
+}
+
 // ------------------------------------------------------------------------------------------------
 // strict FASTQ: validate + measure per block, copy
 // ------------------------------------------------------------------------------------------------
 // The records of block b are those whose LAST line ends in it: lines [off[b], off[b+1]) -> records [off[b]/4, off[b+1]/4).
 __global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ block_off,
-                                                                  const unsigned *__restrict__ line_end, unsigned *__restrict__ block_out, IngChunkArgs a)
+                                                                  const unsigned *__restrict__ line_end, unsigned *block_out, IngChunkArgs a,
+                                                                  ull *rec_off, unsigned *ticket)
 {
     ing_check_chunk(text, st, line_end, a);
     const unsigned n_lines = st->n_lines;
@@ -284,68 +324,107 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *
         if (bases) atomicAdd(&st->bases, bases);
         if (lookups) atomicAdd(&st->lookups, lookups);
     }
+    if (!ing_last_block(ticket)) return;
+    const unsigned total = ing_scan_array(block_out, gridDim.x);
+    if (threadIdx.x == 0) ing_chunk_verdict(st, line_end, total, 0u, rec_off);
 }
 
-// single CTA: exclusive scan of the blocks' output sizes; then the chunk's verdict (everything that can veto the
-// scan is known here), the carry, and the batch length the scan kernel will read
-__global__ void __launch_bounds__(ING_THREADS) ing_scan_out(unsigned *__restrict__ v, unsigned n, IngState *st, const unsigned *__restrict__ line_end,
-                                                             unsigned fasta, ull *__restrict__ rec_off)
+// ------------------------------------------------------------------------------------------------
+// end of chunk (one block): copy the partial last record in front of where the next chunk's text lands (the next chunk
+// of a streamed file is inflated into ANOTHER buffer of the ring, perhaps already, behind its carry region), FASTA
+// tail, record count, the verdict of a finished file / group, and a clean state for the next one
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ing_finish_body(const uint8_t *text, uint8_t *text_next, IngState *st, const uint8_t *flat, unsigned fasta, IngResult *res)
 {
-    const unsigned total = ing_scan_array(v, n);
+    const ull c_from = st->carry_from, c_len = st->carry_len, dst = ING_MAXCARRY - c_len;
+    for (ull i = threadIdx.x; i < c_len; i += ING_THREADS) text_next[dst + i] = text[c_from + i];
     if (threadIdx.x == 0) {
-        const unsigned n_done = fasta ? st->n_lines : 4 * st->n_rec;         // lines that belong to complete records
-        const ull c_from = n_done ? (ull)line_end[n_done - 1] + 1 : st->t0;
-        ull c_len = st->t1 - c_from;
-        if (c_len > ING_MAXCARRY) { st->irregular = 1; c_len = 0; }
-        if (st->last_chunk && c_len) { st->irregular = 1; c_len = 0; }       // truncated last record: the host parser's business
-        st->carry_from = c_from; st->carry_len = c_len;
-        st->flat_len = (fasta ? st->tail_len : 0u) + (ull)total;
-        st->skip = st->irregular;
-        if (rec_off) rec_off[st->n_rec] = st->flat_len;
+        if (!fasta) st->records += st->n_rec;
+        if (fasta && !st->skip) {
+            const ull fl = st->flat_len;
+            const unsigned keep = fl < (S2_K - 1) ? (unsigned)fl : (S2_K - 1);
+            unsigned char tmp[32];
+            for (unsigned i = 0; i < keep; ++i) tmp[i] = __ldcg(flat + fl - keep + i);
+            for (unsigned i = 0; i < keep; ++i) st->tail[i] = tmp[i];
+            st->tail_len = keep;
+        }
+        if (res) { res->bases = st->bases; res->lookups = st->lookups; res->records = st->records; res->irregular = st->irregular; res->inf_overflow = st->inf_overflow; }
+        if (st->last_chunk) { st->bases = 0; st->lookups = 0; st->records = 0; st->irregular = 0; st->inf_overflow = 0; }      // (skip stays: the scan reads it)
     }
 }
 
-// copy `n` bytes with one warp
-__device__ __forceinline__ void ing_warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, unsigned n, int lane)
+// The copy kernels stage the text their block's lines come from in shared memory with 128-bit loads (the 16 KB of the
+// block plus the 8 KB in front of it, where a line that ends in this block normally starts); the lines then go from
+// shared memory to the flat stream with byte stores, which do not wait for anything.  (Copying line by line straight
+// from global memory is latency bound: every 32-byte piece is a dependent load -> store round trip.)
+#define ING_STAGE_BACK 8192u
+__device__ __forceinline__ ull ing_stage(const uint8_t *__restrict__ text, uint8_t *stage)
 {
-    for (unsigned i = lane; i < n; i += 32) dst[i] = src[i];
+    const ull b0 = (ull)blockIdx.x * ING_BLOCK;
+    const ull w0 = b0 >= ING_STAGE_BACK ? b0 - ING_STAGE_BACK : 0;
+    for (ull off = w0 + threadIdx.x * 16; off < b0 + ING_BLOCK; off += ING_THREADS * 16)
+        *reinterpret_cast<uint4 *>(stage + (off - w0)) = *reinterpret_cast<const uint4 *>(text + off);
+    __syncthreads();
+    return w0;
 }
 
-__global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ block_off,
-                                                               const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
-                                                               uint8_t *__restrict__ flat, ull *__restrict__ rec_off)
+__device__ __forceinline__ uint8_t stage_or_text(const uint8_t *text, const uint8_t *stage, ull w0, unsigned pos)
 {
-    if (st->skip) return;
+    return pos >= w0 ? stage[pos - w0] : text[pos];
+}
+
+// copy `n` bytes starting at text position `src` with one warp; what lies at or behind w0 comes from the stage
+__device__ __forceinline__ void ing_warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ text, const uint8_t *stage, ull w0,
+                                              unsigned src, unsigned n, int lane)
+{
+    unsigned i = lane;
+    if (src < w0) {                                          // a long line: its head is still in global memory
+        const unsigned n0 = min(n, (unsigned)(w0 - src));
+        for (; i < n0; i += 32) dst[i] = text[src + i];
+    }
+    for (; i < n; i += 32) dst[i] = stage[(ull)src + i - w0];
+}
+
+__global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *text, uint8_t *text_next, IngState *st, const unsigned *__restrict__ block_off,
+                                                               const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
+                                                               uint8_t *flat, ull *__restrict__ rec_off, unsigned do_finish, IngResult *res, unsigned *ticket)
+{
     __shared__ unsigned s_src[ING_THREADS], s_len[ING_THREADS], s_dst[ING_THREADS];
+    __shared__ __align__(16) uint8_t stage[ING_STAGE_BACK + ING_BLOCK];
     const unsigned n_lines = st->n_lines;
     const unsigned r_lo = min(block_off[blockIdx.x], n_lines) / 4, r_hi = min(block_off[blockIdx.x + 1], n_lines) / 4;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned run = block_out[blockIdx.x];
-    for (unsigned r0 = r_lo; r0 < r_hi; r0 += ING_THREADS) {
-        const unsigned r = r0 + threadIdx.x;
-        unsigned s0 = 0, olen = 0;
-        if (r < r_hi) {
-            s0 = line_end[4 * r] + 1;
-            const unsigned len = line_end[4 * r + 1] - s0;
-            olen = len >= S2_K ? len + 1 : 0;                       // includes the line's own '\n' = the separator
+    if (!st->skip && r_lo < r_hi) {
+        const ull w0 = ing_stage(text, stage);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        unsigned run = block_out[blockIdx.x];
+        for (unsigned r0 = r_lo; r0 < r_hi; r0 += ING_THREADS) {
+            const unsigned r = r0 + threadIdx.x;
+            unsigned s0 = 0, olen = 0;
+            if (r < r_hi) {
+                s0 = line_end[4 * r] + 1;
+                const unsigned len = line_end[4 * r + 1] - s0;
+                olen = len >= S2_K ? len + 1 : 0;                       // includes the line's own '\n' = the separator
+            }
+            unsigned total;
+            const unsigned at = run + ing_block_scan(olen, total);
+            s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
+            if (rec_off && r < r_hi) rec_off[r] = at;
+            __syncthreads();
+            const unsigned cnt = min((unsigned)ING_THREADS, r_hi - r0);
+            for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) ing_warp_copy(flat + s_dst[e], text, stage, w0, s_src[e], s_len[e], lane);
+            __syncthreads();
+            run += total;
         }
-        unsigned total;
-        const unsigned at = run + ing_block_scan(olen, total);
-        s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
-        if (rec_off && r < r_hi) rec_off[r] = at;
-        __syncthreads();
-        const unsigned cnt = min((unsigned)ING_THREADS, r_hi - r0);
-        for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) ing_warp_copy(flat + s_dst[e], text + s_src[e], s_len[e], lane);
-        __syncthreads();
-        run += total;
     }
+    if (!do_finish || !ing_last_block(ticket)) return;
+    ing_finish_body(text, text_next, st, flat, 0u, res);
 }
 
 // ------------------------------------------------------------------------------------------------
 // strict FASTA: '>' lines are headers, every other line is sequence (joined), nothing else
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ING_THREADS) ing_fasta_measure(const uint8_t *__restrict__ text, IngState *st, const unsigned *__restrict__ block_off,
-                                                                  const unsigned *__restrict__ line_end, unsigned *__restrict__ block_out, IngChunkArgs a)
+                                                                  const unsigned *__restrict__ line_end, unsigned *block_out, IngChunkArgs a, unsigned *ticket)
 {
     ing_check_chunk(text, st, line_end, a);
     const unsigned n_lines = st->n_lines;
@@ -370,64 +449,55 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fasta_measure(const uint8_t *
         if (bases) atomicAdd(&st->bases, bases);
         if (recs) atomicAdd(&st->records, recs);
     }
+    if (!ing_last_block(ticket)) return;
+    const unsigned total = ing_scan_array(block_out, gridDim.x);
+    if (threadIdx.x == 0) ing_chunk_verdict(st, line_end, total, 1u, nullptr);
 }
 
-__global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *__restrict__ text, const IngState *st, const unsigned *__restrict__ block_off,
+__global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *text, uint8_t *text_next, IngState *st, const unsigned *__restrict__ block_off,
                                                                const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
-                                                               uint8_t *__restrict__ flat)
+                                                               uint8_t *flat, IngResult *res, unsigned *ticket)
 {
-    if (st->skip) return;
     __shared__ unsigned s_src[ING_THREADS], s_len[ING_THREADS], s_dst[ING_THREADS];
+    __shared__ __align__(16) uint8_t stage[ING_STAGE_BACK + ING_BLOCK];
     const unsigned n_lines = st->n_lines, tail = st->tail_len;
     const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const ull t0 = st->t0;
-    if (blockIdx.x == 0 && wid == 0) for (unsigned i = lane; i < tail; i += 32) flat[i] = st->tail[i];
-    unsigned run = tail + block_out[blockIdx.x];
-    for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
-        const unsigned L = l0 + threadIdx.x;
-        unsigned s0 = 0, olen = 0;
-        if (L < l_hi) {
-            s0 = L ? line_end[L - 1] + 1 : (unsigned)t0;
-            olen = line_end[L] - s0;
-            if (olen && text[s0] == '>') { olen = 1; s0 = 0xFFFFFFFFu; }            // header: one separator byte
+    const bool skip = st->skip != 0;
+    if (!skip && blockIdx.x == 0 && wid == 0) for (unsigned i = lane; i < tail; i += 32) flat[i] = st->tail[i];
+    if (!skip && l_lo < l_hi) {
+        const ull t0 = st->t0;
+        const ull w0 = ing_stage(text, stage);
+        unsigned run = tail + block_out[blockIdx.x];
+        for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
+            const unsigned L = l0 + threadIdx.x;
+            unsigned s0 = 0, olen = 0;
+            if (L < l_hi) {
+                s0 = L ? line_end[L - 1] + 1 : (unsigned)t0;
+                olen = line_end[L] - s0;
+                if (olen && stage_or_text(text, stage, w0, s0) == '>') { olen = 1; s0 = 0xFFFFFFFFu; }      // header: one separator byte
+            }
+            unsigned total;
+            const unsigned at = run + ing_block_scan(olen, total);
+            s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
+            __syncthreads();
+            const unsigned cnt = min((unsigned)ING_THREADS, l_hi - l0);
+            for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) {
+                if (s_src[e] == 0xFFFFFFFFu) { if (lane == 0) flat[s_dst[e]] = '\n'; }
+                else ing_warp_copy(flat + s_dst[e], text, stage, w0, s_src[e], s_len[e], lane);
+            }
+            __syncthreads();
+            run += total;
         }
-        unsigned total;
-        const unsigned at = run + ing_block_scan(olen, total);
-        s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
-        __syncthreads();
-        const unsigned cnt = min((unsigned)ING_THREADS, l_hi - l0);
-        for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) {
-            if (s_src[e] == 0xFFFFFFFFu) { if (lane == 0) flat[s_dst[e]] = '\n'; }
-            else ing_warp_copy(flat + s_dst[e], text + s_src[e], s_len[e], lane);
-        }
-        __syncthreads();
-        run += total;
     }
+    if (!ing_last_block(ticket)) return;
+    ing_finish_body(text, text_next, st, flat, 1u, res);
 }
 
-// ------------------------------------------------------------------------------------------------
-// end of chunk: copy the partial last record in front of where the next chunk's text lands, FASTA tail, record
-// count, and the verdict of a finished file / group
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ING_THREADS) ing_finish(const uint8_t *__restrict__ text, uint8_t *__restrict__ text_next, IngState *st,
-                                                           const uint8_t *__restrict__ flat, unsigned fasta, IngResult *__restrict__ res)
+// detect mode: the per-record results are stored after the scan, so the end-of-chunk step is a launch of its own
+__global__ void __launch_bounds__(ING_THREADS) ing_finish(const uint8_t *text, uint8_t *text_next, IngState *st, const uint8_t *flat, unsigned fasta, IngResult *res)
 {
-    // the next chunk of a streamed file is inflated into ANOTHER buffer of the ring (perhaps already, behind its carry region)
-    const ull c_from = st->carry_from, c_len = st->carry_len, dst = ING_MAXCARRY - c_len;
-    for (ull i = threadIdx.x; i < c_len; i += ING_THREADS) text_next[dst + i] = text[c_from + i];
-    if (threadIdx.x == 0) {
-        if (!fasta) st->records += st->n_rec;
-        if (fasta && !st->skip) {
-            const ull fl = st->flat_len;
-            const unsigned keep = fl < (S2_K - 1) ? (unsigned)fl : (S2_K - 1);
-            unsigned char tmp[32];
-            for (unsigned i = 0; i < keep; ++i) tmp[i] = flat[fl - keep + i];
-            for (unsigned i = 0; i < keep; ++i) st->tail[i] = tmp[i];
-            st->tail_len = keep;
-        }
-        if (res) { res->bases = st->bases; res->lookups = st->lookups; res->records = st->records; res->irregular = st->irregular; res->inf_overflow = st->inf_overflow; }
-    }
+    ing_finish_body(text, text_next, st, flat, fasta, res);
 }
 
 // ---- detect mode (strain_detect pass 1 on ingested reads) ------------------------------------------
@@ -501,8 +571,12 @@ struct s2_ingest {
     size_t comp_chunk = 0, text_cap = 0; unsigned max_lines = 0;
     IngSlot slot[ING_SLOTS];
     uint64_t n_chunks = 0;             // chunks enqueued so far (slot = n_chunks % ING_SLOTS)
+    uint64_t call_chunk0 = 0;          // n_chunks at the start of the current call: the first chunks of a call are small
+                                       // (2, 4, 8 ... MB) so that the inflate engine and the kernels start early
     uint8_t *d_flat = nullptr;
     unsigned *d_block_nl = nullptr, *d_block_out = nullptr, *d_line_end = nullptr;
+    unsigned short *d_masks = nullptr;   // newline mask of every 16 text bytes
+    unsigned *d_tickets = nullptr;       // last-block election of the three fused kernels
     IngState *d_state = nullptr;
     IngResult *d_results = nullptr, *h_results = nullptr; unsigned n_results = 0;
     decompress_fn decompress = nullptr;
@@ -529,7 +603,7 @@ static void ingest_free(s2_ingest *g)
         if (s.consumed) cudaEventDestroy(s.consumed);
     }
     cudaFree(g->d_flat);
-    cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end);
+    cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end); cudaFree(g->d_masks); cudaFree(g->d_tickets);
     cudaFree(g->d_state); cudaFree(g->d_results); cudaFreeHost(g->h_results);
     cudaFree(g->d_hits_c); cudaFree(g->d_inf_c); cudaFree(g->d_rec_off); cudaFree(g->d_pos_c); cudaFree(g->d_cnt_c); cudaFree(g->d_fcnt);
     cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all); cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);
@@ -564,8 +638,12 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     const size_t n_blocks = ((size_t)ING_MAXCARRY + g->text_cap) / ING_BLOCK + 4;
     CK(cudaMalloc((void **)&g->d_block_nl, n_blocks * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_block_out, n_blocks * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&g->d_masks, n_blocks * (ING_BLOCK / 16) * sizeof(unsigned short)));
     CK(cudaMalloc((void **)&g->d_line_end, (size_t)g->max_lines * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_state, sizeof(IngState)));
+    CK(cudaMemset(g->d_state, 0, sizeof(IngState)));                   // afterwards every finished file leaves a clean state behind
+    CK(cudaMalloc((void **)&g->d_tickets, 4 * sizeof(unsigned)));
+    CK(cudaMemset(g->d_tickets, 0, 4 * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_results, ING_MAX_RESULTS * sizeof(IngResult)));
     CK(cudaHostAlloc((void **)&g->h_results, ING_MAX_RESULTS * sizeof(IngResult), cudaHostAllocDefault));
     // the decompression engine is reached through the driver; no link-time dependency on libcuda
@@ -679,6 +757,13 @@ static void ingest_classify(IngSource &src)
 }
 
 static thread_local s2_ingest *tl_ingest = nullptr;
+// host-side time accounting (S2_INGEST_TRACE=1): where the submitting thread spends its time
+static thread_local double tr_wait = 0, tr_h2d = 0, tr_decomp = 0, tr_launch = 0;
+struct IngTraceEv { cudaEvent_t e[6]; size_t comp = 0, text = 0; };     // copy begin/end, inflate begin/end, kernels begin/end
+static thread_local std::vector<IngTraceEv> tr_events;
+static thread_local bool tr_on = false;
+static void tr_record(int which, cudaStream_t st) { if (tr_on && !tr_events.empty()) cudaEventRecord(tr_events.back().e[which], st); }
+static inline double ing_now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static s2_ingest *ingest_pipeline(s2_ctx *c)
 {
@@ -688,6 +773,13 @@ static s2_ingest *ingest_pipeline(s2_ctx *c)
         if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return nullptr; }
     }
     return tl_ingest;
+}
+
+// compressed bytes the next chunk may hold: ramps up over the first chunks of a call
+static size_t ingest_chunk_cap(const s2_ingest *g)
+{
+    const uint64_t k = g->n_chunks - g->call_chunk0;
+    return k >= 6 ? g->comp_chunk : std::min<size_t>(g->comp_chunk, (size_t)(2u << 20) << k);
 }
 
 // ---- one chunk ------------------------------------------------------------------------------------------
@@ -702,7 +794,14 @@ struct IngChunk {
 static int ingest_slot_begin(s2_ingest *g, IngSlot **out)
 {
     IngSlot &s = g->slot[g->n_chunks % ING_SLOTS];
+    const double t0 = ing_now();
     CK(cudaEventSynchronize(s.consumed));
+    tr_wait += ing_now() - t0;
+    if (tr_on) {
+        tr_events.emplace_back();
+        for (auto &e : tr_events.back().e) cudaEventCreate(&e);
+        tr_record(0, g->copy_stream);
+    }
     s.params.clear();
     *out = &s;
     return 0;
@@ -754,8 +853,12 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     const size_t n_db = bgzf ? s.params.size() : 0;
     if (ch.n_files) CK(cudaMemcpyAsync(s.d_meta, s.h_meta, (size_t)ch.n_files * 8, cudaMemcpyHostToDevice, g->copy_stream));
     if (n_db) CK(cudaMemcpyAsync(s.d_meta + (size_t)ING_MAX_FILES * 8, s.h_meta + (size_t)ING_MAX_FILES * 8, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
+    tr_record(1, g->copy_stream);
+    if (tr_on && !tr_events.empty()) { tr_events.back().comp = ch.comp_len; tr_events.back().text = ch.text_len; }
     CK(cudaEventRecord(s.h2d_done, g->copy_stream));
     CK(cudaStreamWaitEvent(g->inflate_stream, s.h2d_done, 0));
+    tr_record(2, g->inflate_stream);
+    const double t_dec = ing_now();
     if (bgzf) {
         for (size_t i = 0; i < s.params.size(); i += ING_DECOMP_CALL) {
             size_t err_index = 0;
@@ -766,8 +869,12 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     } else if (ch.comp_len) {
         CK(cudaMemcpyAsync(s.d_text + ING_MAXCARRY, s.d_comp, ch.comp_len, cudaMemcpyDeviceToDevice, g->inflate_stream));
     }
+    tr_record(3, g->inflate_stream);
     CK(cudaEventRecord(s.inflated, g->inflate_stream));
     CK(cudaStreamWaitEvent(st, s.inflated, 0));
+    tr_record(4, st);
+    const double t_launch = ing_now();
+    tr_decomp += t_launch - t_dec;
     uint8_t *d_text = s.d_text;
     uint8_t *d_text_next = g->slot[(g->n_chunks + 1) % ING_SLOTS].d_text;      // where a streamed file's next chunk will be inflated
     IngChunkArgs a;
@@ -776,19 +883,19 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     a.file_end = (const ull *)s.d_meta; a.isz = (const unsigned *)(s.d_meta + (size_t)ING_MAX_FILES * 8); a.act = s.d_act;
     const unsigned n_blocks = (unsigned)(((size_t)ING_MAXCARRY + ch.text_len) / ING_BLOCK + 1);      // covers [0, t1] of the text buffer
     const bool detect = mode == ING_DETECT;
-    ing_index_count<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, a);
-    ing_scan_lines<<<1, ING_THREADS, 0, st>>>(g->d_block_nl, n_blocks, g->d_state, g->max_lines, a.fasta);
-    ing_index_scatter<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->max_lines);
-    if (fasta) ing_fasta_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a);
-    else       ing_fastq_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a);
-    ing_scan_out<<<1, ING_THREADS, 0, st>>>(g->d_block_out, n_blocks, g->d_state, g->d_line_end, a.fasta, detect ? g->d_rec_off : nullptr);
+    ing_index_count<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_masks, a, g->max_lines, g->d_tickets + 0);
+    ing_index_scatter<<<n_blocks, ING_THREADS, 0, st>>>(g->d_masks, g->d_block_nl, g->d_line_end, g->max_lines);
+    IngResult *res = want_result ? g->d_results + g->n_results : nullptr;
     const S2DevBatch *dev = reinterpret_cast<const S2DevBatch *>(&g->d_state->flat_len);
     if (fasta) {
-        ing_fasta_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat);
+        ing_fasta_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a, g->d_tickets + 1);
+        ing_fasta_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat, res, g->d_tickets + 2);
         s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, st);
     } else {
-        ing_fastq_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat,
-                                                          detect ? g->d_rec_off : nullptr);
+        ing_fastq_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a,
+                                                             detect ? g->d_rec_off : nullptr, g->d_tickets + 1);
+        ing_fastq_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat,
+                                                          detect ? g->d_rec_off : nullptr, detect ? 0u : 1u, res, g->d_tickets + 2);
         if (!detect) {
             s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, st);
         } else {
@@ -804,12 +911,14 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
                                                                   g->d_frec, g->d_foff, g->d_fkmer, g->d_fcnt, g->f_cap);
             ing_store_records<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_line_end, g->d_hits_c, g->d_inf_c, g->d_len_all, g->d_hits_all,
                                                                     g->d_inf_all, g->rec_cap);
+            ing_finish<<<1, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_flat, 0u, res);
         }
     }
-    ing_finish<<<1, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_flat, a.fasta, want_result ? g->d_results + g->n_results : nullptr);
+    tr_record(5, st);
     CK(cudaEventRecord(s.consumed, st));                   // the slot (compressed bytes, decompress list, meta, text) may be reused
     if (want_result) ++g->n_results;
     CK(cudaGetLastError());
+    tr_launch += ing_now() - t_launch;
     ++g->n_chunks;
     return 0;
 }
@@ -827,8 +936,8 @@ static int ingest_collect(s2_ingest *g)
 // says irregular), -1 error.  Synchronous at the end.  *chunks_done: chunks that went to the device.
 static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mode, int col, unsigned inc, IngResult *res, uint64_t *chunks_done)
 {
-    CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), g->stream));
     g->n_results = 0;
+    g->call_chunk0 = g->n_chunks;
     off_t file_off = 0;
     bool first = true, eof = false, broken = false;
     uint64_t n = 0;
@@ -839,12 +948,13 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
         IngSlot &s = *sp;
         const uint8_t *h;
         ssize_t got;
+        const size_t want_bytes = ingest_chunk_cap(g);
         if (src.mem) {                                                           // caller's buffer: no staging copy
             h = src.mem + file_off;
-            got = (size_t)file_off < src.mem_len ? (ssize_t)std::min<size_t>(g->comp_chunk, src.mem_len - (size_t)file_off) : 0;
+            got = (size_t)file_off < src.mem_len ? (ssize_t)std::min<size_t>(want_bytes, src.mem_len - (size_t)file_off) : 0;
         } else {
             if (ingest_staging(s, g->comp_chunk)) return -1;
-            got = pread(src.fd, s.h_comp, g->comp_chunk, file_off);
+            got = pread(src.fd, s.h_comp, want_bytes, file_off);
             if (got < 0) { s2_set_error("read failed"); return -1; }
             h = s.h_comp;
         }
@@ -859,7 +969,7 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
             full = used < (size_t)got;
             ch.text_len = used;
         }
-        eof = (size_t)got < g->comp_chunk && used == (size_t)got && !full;      // short read and everything consumed
+        eof = (size_t)got < want_bytes && used == (size_t)got && !full;        // short read and everything consumed
         ch.comp_len = used; ch.first = first; ch.last = eof; ch.n_files = 0;
         file_off += (off_t)used;
         text_total += ch.text_len;
@@ -884,6 +994,7 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
     }
     if (chunks_done) *chunks_done = n;
     if (broken) {
+        CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), g->stream));        // no last chunk came to tidy up
         CK(cudaStreamSynchronize(g->stream));
         g->n_results = 0;
         memset(res, 0, sizeof *res);
@@ -909,16 +1020,28 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
     std::vector<int> streamed;                       // too big for one chunk
     std::vector<int> retry;                          // members of an irregular group: run alone
     g->n_results = 0;
+    g->call_chunk0 = g->n_chunks;
 
     // the group being assembled in the current slot
     IngSlot *s = nullptr;
     IngGroup cur;
     IngChunk ch;
     bool cur_fasta = false, cur_bgzf = false;
+    // host -> device copies of neighbouring sources (consecutive in memory, as in the staging buffer or a caller's arena) are merged
+    struct { const uint8_t *h = nullptr; size_t d_off = 0, len = 0; } pend;
+    auto push_copy = [&]() -> int {
+        if (pend.len) {
+            const double t_cp = ing_now();
+            CK(cudaMemcpyAsync(s->d_comp + pend.d_off, pend.h, pend.len, cudaMemcpyHostToDevice, g->copy_stream));
+            tr_h2d += ing_now() - t_cp;
+        }
+        pend.len = 0;
+        return 0;
+    };
     auto flush = [&]() -> int {
         if (!s || cur.members.empty()) return 0;
+        if (push_copy()) return -1;
         ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size();
-        CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), g->stream));
         cur.result = (int)g->n_results;
         if (ingest_enqueue(g, t, *s, ch, cur_bgzf, cur_fasta, ING_COUNT, col, 1u, true)) return -1;
         groups.push_back(cur);
@@ -942,9 +1065,11 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
         IngSource &src = srcs[i];
         const ssize_t size = src.size();
         if (size < 0) return 2;
-        const size_t cap = src.bgzf ? g->comp_chunk : std::min(g->comp_chunk, g->text_cap);
-        if ((size_t)size > cap) return 1;
+        const size_t cap_max = src.bgzf ? g->comp_chunk : std::min(g->comp_chunk, g->text_cap);
+        if ((size_t)size > cap_max) return 1;
         for (int attempt = 0; attempt < 2; ++attempt) {
+            // a group closes when the next file would push it over the (ramping) chunk size; a single file may exceed the ramp
+            const size_t cap = std::min(cap_max, std::max(ingest_chunk_cap(g), (size_t)size));
             if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
             if (!s) { if (ingest_slot_begin(g, &s)) return -1; cur_fasta = src.fasta; cur_bgzf = src.bgzf; }
             const uint8_t *h = src.mem;
@@ -969,7 +1094,8 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
                 if (text_len + (size_t)size > g->text_cap) { if (cur.members.empty()) { s = nullptr; return 1; } if (flush()) return -1; continue; }
                 text_len += (size_t)size;
             }
-            if (size) CK(cudaMemcpyAsync(s->d_comp + ch.comp_len, h, (size_t)size, cudaMemcpyHostToDevice, g->copy_stream));
+            if (pend.len && pend.h + pend.len == h && pend.d_off + pend.len == ch.comp_len && pend.len < (8u << 20)) pend.len += (size_t)size;
+            else { if (push_copy()) return -1; pend.h = h; pend.d_off = ch.comp_len; pend.len = (size_t)size; }
             ch.comp_len += (size_t)size;
             ch.text_len = text_len;
             ((ull *)s->h_meta)[cur.members.size()] = text_len;
@@ -981,7 +1107,9 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
     };
 
     const bool trace = s2_env_int("S2_INGEST_TRACE", 0) != 0;
-    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    auto now = []() { return ing_now(); };
+    tr_wait = tr_h2d = tr_decomp = tr_launch = 0;
+    tr_on = trace && s2_env_int("S2_INGEST_TRACE", 0) >= 2;
     double us_classify = 0, us_group = 0;
     const double t_begin = now();
     for (int i = 0; i < n; ++i) {
@@ -1001,8 +1129,24 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
     }
     const double t_enq = now();
     if (harvest()) return -1;
-    if (trace) fprintf(stderr, "[s2 ingest] %d sources: classify %.0f us, group+enqueue %.0f us, enqueue done at %.0f us, verdicts at %.0f us, chunks so far %llu\n",
-                       n, us_classify, us_group, t_enq - t_begin, now() - t_begin, (unsigned long long)g->n_chunks);
+    if (trace) fprintf(stderr, "[s2 ingest] %d sources: classify %.0f us, group+enqueue %.0f us (ring wait %.0f, H2D calls %.0f, inflate calls %.0f, launches %.0f), "
+                       "enqueue done at %.0f us, verdicts at %.0f us, chunks so far %llu\n",
+                       n, us_classify, us_group, tr_wait, tr_h2d, tr_decomp, tr_launch, t_enq - t_begin, now() - t_begin, (unsigned long long)g->n_chunks);
+    if (tr_on) {                                     // device timeline of every chunk, relative to the first copy
+        for (size_t k = 0; k < tr_events.size(); ++k) {
+            float t[6] = { 0, 0, 0, 0, 0, 0 };
+            for (int j = 0; j < 6; ++j) {
+                const cudaError_t e = cudaEventElapsedTime(&t[j], tr_events[0].e[0], tr_events[k].e[j]);
+                if (e != cudaSuccess) { fprintf(stderr, "[s2 ingest]   chunk %zu event %d: %s\n", k, j, cudaGetErrorName(e)); cudaGetLastError(); }
+            }
+            fprintf(stderr, "[s2 ingest]   chunk %zu (%5.1f MB -> %5.1f MB): copy %7.0f..%7.0f  inflate %7.0f..%7.0f  kernels %7.0f..%7.0f us\n", k,
+                            tr_events[k].comp / 1e6, tr_events[k].text / 1e6, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+        }
+        for (auto &ev : tr_events) for (auto &e : ev.e) cudaEventDestroy(e);
+        cudaGetLastError();
+        tr_events.clear();
+        tr_on = false;
+    }
     // members of irregular groups, one by one (a group's verdict precedes its scan: nothing of it was counted)
     std::vector<int> again;
     again.swap(retry);

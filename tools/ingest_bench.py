@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reads", type=int, default=400_000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--bench-mix", type=int, default=0, help="also time one step of bench.py's file-image batch (64 genomes, 5 %% relatives)")
     args = ap.parse_args()
     import strainer2_b200 as s2
     from strainer2_b200 import synth
@@ -97,6 +98,26 @@ def main():
             dt = time.perf_counter() - t
             assert not any(rcs), rcs
             print(f"genomes batch rep {rep}: {args.genomes} files, {b / 1e6:.0f} Mbases in {dt * 1e3:.2f} ms = {b / dt / 1e9:.2f} Gbases/s", flush=True)
+    if args.bench_mix:
+        bench_mix(ctx, table, strain, args.reps)
+
+
+def bench_mix(ctx, table, strain, reps):
+    import strainer2_b200 as s2
+    import bench
+    imgs = bench.make_file_images(strain, 0, 64)
+    arena = s2.PinnedBuffer(sum(len(z) for z in imgs))
+    ptrs, sizes, at = [], [], 0
+    for z in imgs:
+        arena.array[at:at + len(z)] = np.frombuffer(z, dtype=np.uint8)
+        ptrs.append(arena.ptr + at); sizes.append(len(z))
+        at += len(z)
+    for rep in range(reps):
+        t = time.perf_counter()
+        rcs, b, l = ctx.ingest_count_mem_batch(table, ptrs, sizes, 2)
+        dt = time.perf_counter() - t
+        assert not any(rcs)
+        print(f"bench-mix batch rep {rep}: 64 files, {b / 1e6:.0f} Mbases, {sum(sizes) / 1e6:.1f} MB compressed in {dt * 1e3:.2f} ms = {b / dt / 1e9:.2f} Gbases/s", flush=True)
 
 
 if __name__ == "__main__":
