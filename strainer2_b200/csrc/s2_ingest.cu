@@ -362,8 +362,16 @@ __device__ __forceinline__ ull ing_stage(const uint8_t *__restrict__ text, uint8
 {
     const ull b0 = (ull)blockIdx.x * ING_BLOCK;
     const ull w0 = b0 >= ING_STAGE_BACK ? b0 - ING_STAGE_BACK : 0;
-    for (ull off = w0 + threadIdx.x * 16; off < b0 + ING_BLOCK; off += ING_THREADS * 16)
-        *reinterpret_cast<uint4 *>(stage + (off - w0)) = *reinterpret_cast<const uint4 *>(text + off);
+    constexpr int N = (ING_STAGE_BACK + ING_BLOCK) / (ING_THREADS * 16);        // 6 loads in flight per thread
+    uint4 v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const ull off = w0 + (ull)k * ING_THREADS * 16 + threadIdx.x * 16;
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (off < b0 + ING_BLOCK) v[k] = __ldg(reinterpret_cast<const uint4 *>(text + off));
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) *reinterpret_cast<uint4 *>(stage + (ull)k * ING_THREADS * 16 + threadIdx.x * 16) = v[k];
     __syncthreads();
     return w0;
 }
