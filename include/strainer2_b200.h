@@ -149,6 +149,21 @@ int         s2_ingest_detect_file(s2_ctx *ctx, s2_table *t, const char *path, s2
 void        s2_ingest_detect_free(s2_ingest_detect_result *r);
 void        s2_ingest_thread_cleanup(void);
 
+/* ---------------------------------------------------------------- scrub filter -------------- */
+/* The selection steps of scripts/kmer_scrub_filter.py on table columns.
+ * joint scrub (:88-143): rows are ranked by max(pan / pan_sum, meta / meta_sum) (IEEE doubles, as the script computes
+ * them), descending, ties in table order; the top n_scrub ALIVE rows go.  keep_out[i] = 1 for the survivors (dead
+ * rows - those the drug scrub removed, alive[i] = 0 - are never kept).  0 <= n_scrub <= number of alive rows. */
+int         s2_scrub_joint(s2_ctx *ctx, const uint64_t *pan, const uint64_t *meta, const uint8_t *alive, uint64_t n,
+                           uint64_t pan_sum, uint64_t meta_sum, uint64_t n_scrub, uint8_t *keep_out);
+/* independent scrub (:31-58): hist[v] = entries equal to v for v < 65536, hist[65536] = entries >= 65536;
+ * count_above = entries > t (for thresholds beyond the histogram) */
+int         s2_scrub_histogram(s2_ctx *ctx, const uint64_t *vals, uint64_t n, uint64_t *hist65537);
+int         s2_scrub_count_above(s2_ctx *ctx, const uint64_t *vals, uint64_t n, uint64_t t, uint64_t *count);
+/* str(float) of Python 3 (shortest round-trip digits, exponent notation below 1e-4 and from 1e16): the script prints
+ * such numbers on stdout / stderr.  out must hold 32 bytes. */
+void        s2_py_float_repr(double x, char *out);
+
 /* ---------------------------------------------------------------- detect scan --------------- */
 /* Pass 1 of quantify_hits_PE() (src/strain_detect.c:465-491, :514-539) for every record of a batch,
  * plus the positions pass 2 (:554-623) will print.  rec_off[n_rec+1] are the ascending byte offsets of
@@ -216,6 +231,7 @@ void        s2_reader_close(s2_reader *r);
 
 /* whole programs, argv-compatible with the reference executables */
 int         s2_kmer_scrub_count_main(int argc, char **argv);   /* src/kmer_scrub_count.c:29-123 */
+int         s2_kmer_scrub_filter_main(int argc, char **argv);  /* scripts/kmer_scrub_filter.py:146-229 */
 int         s2_strain_detect_main(int argc, char **argv);      /* src/strain_detect.c:61-158    */
 /* many strains against the same -A/-B/-C lists in ONE pass over the inputs (union table); every output
  * table is byte-identical to kmer_scrub_count run on that strain alone.  No reference counterpart:

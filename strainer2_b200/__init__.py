@@ -10,5 +10,5 @@ from .api import (                                  # noqa: F401
     K, Context, StrainTable, Reader, ScanStats, PinnedBuffer,
     encode_2bit, decode_2bit, kmer_from_ascii, kmer_to_ascii,
     roworder_emulate, format_count_table, load_flat, flatten_records,
-    run_kmer_scrub_count, run_strain_detect, run_kmer_scrub_count_batch, BIN_DIR,
+    run_kmer_scrub_count, run_strain_detect, run_kmer_scrub_count_batch, run_kmer_scrub_filter, py_float_repr, BIN_DIR,
 )

@@ -72,6 +72,12 @@ SIGNATURES = {
     "s2_ingest_detect_file": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]),
     "s2_ingest_detect_free": (None, [C.c_void_p]),
     "s2_ingest_thread_cleanup": (None, []),
+    "s2_scrub_joint": (C.c_int, [C.c_void_p, c_u64p, c_u64p, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                 C.POINTER(C.c_uint8)]),
+    "s2_scrub_histogram": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u64p]),
+    "s2_scrub_count_above": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, C.c_uint64, c_u64p]),
+    "s2_py_float_repr": (None, [C.c_double, C.c_char_p]),
+    "s2_kmer_scrub_filter_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "s2_scan_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, c_u64p, C.c_uint32, c_u32p,
                                  c_u32p, c_u64p, C.c_uint64, c_u64p, C.c_int, C.POINTER(ScanStatsStruct)]),
     "s2_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), c_u64p, C.c_int]),

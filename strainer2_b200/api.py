@@ -413,6 +413,17 @@ def run_strain_detect(args, cwd=None, env=None, timeout=None):
     return _run("strain_detect", args, cwd, env, timeout)
 
 
+def run_kmer_scrub_filter(args, cwd=None, env=None, timeout=None):
+    """Run strainer2_b200/bin/kmer_scrub_filter with the argv of scripts/kmer_scrub_filter.py; -> CompletedProcess."""
+    return _run("kmer_scrub_filter", args, cwd, env, timeout)
+
+
+def py_float_repr(x: float) -> str:
+    buf = C.create_string_buffer(40)
+    lib.s2_py_float_repr(float(x), buf)
+    return buf.value.decode()
+
+
 def run_kmer_scrub_count_batch(args, cwd=None, env=None, timeout=None):
     """many strains against the same lists in one pass (-R strains.txt -A -B [-C] -O outdir)"""
     return _run("kmer_scrub_count_batch", args, cwd, env, timeout)
