@@ -270,7 +270,7 @@ static int replay_ingested(Detect &d, Job &job, const s2_ingest_detect_result &A
 }
 
 // quantify_hits_PE (src/strain_detect.c:387-663).  Returns 0 or EXIT_FAILURE (message already printed).
-static int quantify_hits(Detect &d, Job &job)
+static int quantify_hits(Detect &d, Job &job, s2_ctx *ctx, s2_table *table)
 {
     const char *pe1 = job.f1.c_str();
     const char *pe2 = job.has_f2 ? job.f2.c_str() : nullptr;
@@ -282,8 +282,8 @@ static int quantify_hits(Detect &d, Job &job)
         const auto tI = std::chrono::steady_clock::now();
         s2_ingest_detect_result A, B;
         memset(&A, 0, sizeof A); memset(&B, 0, sizeof B);
-        int ra = s2_ingest_detect_file(d.ctx, d.table, pe1, &A), rb = 0;
-        if (ra == 0 && is_pe == IS_PAIRED_END) rb = s2_ingest_detect_file(d.ctx, d.table, pe2, &B);
+        int ra = s2_ingest_detect_file(ctx, table, pe1, &A), rb = 0;
+        if (ra == 0 && is_pe == IS_PAIRED_END) rb = s2_ingest_detect_file(ctx, table, pe2, &B);
         if (ra < 0 || rb < 0) { job.err = std::string(s2_last_error()) + "\n"; s2_ingest_detect_free(&A); s2_ingest_detect_free(&B); return EXIT_FAILURE; }
         if (ra == 0 && rb == 0) {
             const auto tJ = std::chrono::steady_clock::now();
@@ -370,7 +370,7 @@ static int quantify_hits(Detect &d, Job &job)
             uint64_t cap = std::max<uint64_t>(4096, batch.size() / 32);
             for (;;) {
                 pos.resize(cap);
-                if (s2_scan_detect(d.ctx, d.table, batch.data(), batch.size(), rec_off.data(), n_rec, hits.data(), inf.data(),
+                if (s2_scan_detect(ctx, table, batch.data(), batch.size(), rec_off.data(), n_rec, hits.data(), inf.data(),
                                    pos.data(), cap, &n_inf, 0, nullptr)) {
                     job.err = std::string(s2_last_error()) + "\n";
                     rc = EXIT_FAILURE;
@@ -536,7 +536,6 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     d.table = s2_table_build(d.ctx, flat.data(), flat.size(), 6, 0.0, 0);
     if (!d.table) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
     d.exotic = s2_exotic_build(flat.data(), flat.size(), 6);
-    std::vector<uint8_t>().swap(flat);
     d.genome_kmers = (unsigned)(s2_table_n_keys(d.table) + s2_exotic_n_keys(d.exotic));
     unsigned n_found = 0;
     const int lrc = label_informative(d, a_file, &n_found);                                // :140
@@ -588,25 +587,48 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     }
     fflush(stdout);
 
+    // S2_GPUS=n: the path shards by batch line - every GPU holds a replica of the labelled table, worker
+    // thread w feeds GPU w % n, the finished blocks are still written in batch order; no collective
+    const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(jobs.size(), (size_t)s2_default_reader_threads()));
+    std::vector<s2_ctx *> ctxs(1, d.ctx);
+    std::vector<s2_table *> tables(1, d.table);
+    {
+        const int dev0 = s2_env_int("S2_DEVICE", 0);
+        int n_gpus = std::min(std::min(s2_env_int("S2_GPUS", 1), s2_device_count() - dev0), n_workers);
+        std::vector<uint64_t> labelled(d.informative.begin(), d.informative.end());
+        for (int g = 1; g < n_gpus; ++g) {
+            s2_ctx *c = s2_init(dev0 + g, 8u << 20, 2);
+            s2_table *t = c ? s2_table_build(c, flat.data(), flat.size(), 6, 0.0, 0) : nullptr;
+            std::vector<uint8_t> found(labelled.size() + 1);
+            if (!t || s2_table_flag(t, labelled.data(), labelled.size(), found.data())) {
+                fprintf(stderr, "%s\n", s2_last_error());
+                return EXIT_FAILURE;
+            }
+            ctxs.push_back(c); tables.push_back(t);
+        }
+    }
+    std::vector<uint8_t>().swap(flat);
+
     // worker threads read + scan files concurrently; this thread writes the finished blocks in order
     int rc = 0;
     {
         std::mutex mu; std::condition_variable cv;
         std::atomic<size_t> next(0);
         std::atomic<bool> stop(false);
-        auto worker = [&]() {
+        auto worker = [&](int w) {
+            s2_ctx *ctx = ctxs[(size_t)w % ctxs.size()];
+            s2_table *table = tables[(size_t)w % tables.size()];
             for (;;) {
                 const size_t i = next.fetch_add(1);
                 if (i >= jobs.size() || stop.load()) break;
-                jobs[i].rc = quantify_hits(d, jobs[i]);
+                jobs[i].rc = quantify_hits(d, jobs[i], ctx, table);
                 { std::lock_guard<std::mutex> g(mu); jobs[i].done = true; }
                 cv.notify_all();
             }
             s2_ingest_thread_cleanup();
         };
-        const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(jobs.size(), (size_t)s2_default_reader_threads()));
         std::vector<std::thread> pool;
-        for (int w = 0; w < n_workers; ++w) pool.emplace_back(worker);
+        for (int w = 0; w < n_workers; ++w) pool.emplace_back(worker, w);
         for (size_t i = 0; i < jobs.size(); ++i) {
             { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&]() { return jobs[i].done; }); }
             d.write_out(jobs[i].out);
@@ -625,12 +647,11 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     fflush(stdout);
     if (s2_env_int("S2_STATS", 0)) {
         double kms = 0; uint64_t kl = 0;
-        s2_kernel_time(d.ctx, &kms, &kl, 0);
-        fprintf(stderr, "[s2 detect] keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu\n",
-                d.genome_kmers, d.genome_informative, (unsigned long long)d.n_bases, d.t_read, d.t_gpu, d.t_emit, kms, (unsigned long long)kl);
+        for (s2_ctx *c : ctxs) { double k1 = 0; uint64_t l1 = 0; s2_kernel_time(c, &k1, &l1, 0); kms += k1; kl += l1; }
+        fprintf(stderr, "[s2 detect] gpus=%zu keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu\n",
+                ctxs.size(), d.genome_kmers, d.genome_informative, (unsigned long long)d.n_bases, d.t_read, d.t_gpu, d.t_emit, kms, (unsigned long long)kl);
     }
     s2_exotic_free(d.exotic);
-    s2_table_free(d.table);
-    s2_shutdown(d.ctx);
+    for (size_t g = 0; g < ctxs.size(); ++g) { s2_table_free(tables[g]); s2_shutdown(ctxs[g]); }
     return rc;
 }
