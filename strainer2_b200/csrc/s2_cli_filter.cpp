@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <charconv>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,46 +60,49 @@ std::string py_repr(double x)
 
 // ---- keys -> dense ids ---------------------------------------------------------------------------------------------
 struct KeyIndex {
-    std::vector<uint64_t> slots_key;       // 62-bit code + 1 (0 = empty)
-    std::vector<uint32_t> slots_id;
+    struct Slot { uint64_t key; uint32_t id, pad; };       // 62-bit code + 1 (0 = empty); one cache line touch per probe
+    std::vector<Slot> slots;
     uint64_t mask = 0, used = 0;
     std::unordered_map<std::string, uint32_t> odd;
     uint32_t next_id = 0;
 
-    void grow()
+    static uint64_t slot_of(uint64_t code, uint64_t mask) { return ((code * 0x9E3779B97F4A7C15ull) >> 20) & mask; }
+    void grow(uint64_t want = 0)
     {
-        const uint64_t cap = slots_key.empty() ? (1u << 16) : slots_key.size() * 2;
-        std::vector<uint64_t> k(cap, 0); std::vector<uint32_t> v(cap, 0);
-        for (size_t i = 0; i < slots_key.size(); ++i)
-            if (slots_key[i]) {
-                uint64_t h = (slots_key[i] * 0x9E3779B97F4A7C15ull) >> 17 & (cap - 1);
-                while (k[h]) h = (h + 1) & (cap - 1);
-                k[h] = slots_key[i]; v[h] = slots_id[i];
+        uint64_t cap = slots.empty() ? (1u << 16) : slots.size() * 2;
+        while (cap < want) cap *= 2;
+        std::vector<Slot> k(cap, Slot{ 0, 0, 0 });
+        for (const Slot &x : slots)
+            if (x.key) {
+                uint64_t h = slot_of(x.key, cap - 1);
+                while (k[h].key) h = (h + 1) & (cap - 1);
+                k[h] = x;
             }
-        slots_key.swap(k); slots_id.swap(v); mask = cap - 1;
+        slots.swap(k); mask = cap - 1;
     }
-    static bool encode(const char *s, size_t len, uint64_t *code)
+    void reserve(uint64_t n_keys)                   // room for n_keys plain keys without another rehash
     {
-        if (len != 31) return false;
-        uint64_t c = 0;
-        for (size_t i = 0; i < 31; ++i) {
-            unsigned x;
-            switch (s[i]) { case 'A': x = 0; break; case 'C': x = 1; break; case 'G': x = 2; break; case 'T': x = 3; break; default: return false; }
-            c = (c << 2) | x;
-        }
-        *code = c + 1;
-        return true;
+        if (slots.size() < (n_keys + 64) * 2) grow((n_keys + 64) * 2);
     }
-    // id of the key, new ids are handed out in order of first appearance; *is_new tells
-    uint32_t get(const char *s, size_t len, bool *is_new)
+    // 62-bit code + 1 of an ACGT 31-mer, 0 for anything else (branch-free: the letters are as good as random)
+    static uint64_t encode(const char *s, size_t len)
     {
-        uint64_t code;
-        if (encode(s, len, &code)) {
-            if ((used + 1) * 2 > slots_key.size()) grow();
-            uint64_t h = (code * 0x9E3779B97F4A7C15ull) >> 17 & mask;
-            while (slots_key[h] && slots_key[h] != code) h = (h + 1) & mask;
-            if (slots_key[h]) { *is_new = false; return slots_id[h]; }
-            slots_key[h] = code; slots_id[h] = next_id; ++used;
+        static const struct Lut { uint8_t v[256]; Lut() { memset(v, 4, sizeof v); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } lut;
+        if (len != 31) return 0;
+        uint64_t c = 0; unsigned bad = 0;
+        for (size_t i = 0; i < 31; ++i) { const unsigned x = lut.v[(uint8_t)s[i]]; bad |= x; c = (c << 2) | (x & 3u); }
+        return (bad & 4u) ? 0 : c + 1;
+    }
+    void prefetch(uint64_t code) const { if (code) __builtin_prefetch(&slots[slot_of(code, mask)]); }
+    // id of the key (code = encode(s, len)), new ids are handed out in order of first appearance; *is_new tells
+    uint32_t get(uint64_t code, const char *s, size_t len, bool *is_new)
+    {
+        if (code) {
+            if ((used + 1) * 2 > slots.size()) grow();
+            uint64_t h = slot_of(code, mask);
+            while (slots[h].key && slots[h].key != code) h = (h + 1) & mask;
+            if (slots[h].key) { *is_new = false; return slots[h].id; }
+            slots[h].key = code; slots[h].id = next_id; ++used;
             *is_new = true;
             return next_id++;
         }
@@ -234,10 +238,15 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
         fclose(lf);
     }
 
+    const bool stats = s2_env_int("S2_STATS", 0) != 0;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    double t_inflate = 0, t_parse = 0, t_gpu = 0;
     KeyIndex index;
     std::vector<uint64_t> pan_sum, meta_sum;            // over ids; membership flags beside them
     std::vector<uint8_t> in_pan, in_meta, in_drug;
-    std::vector<std::string> names;                     // id -> key
+    std::string name_pool;                              // id -> key: bytes [name_off[id], name_off[id + 1])
+    std::vector<uint64_t> name_off(1, 0);
     bool drug_filter = false;
     // the strain dict of the current and of the previous file: distinct ids in first-occurrence order + reference count by id
     std::vector<uint32_t> strain_ids, prev_ids;
@@ -249,48 +258,77 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
         if (fi > 1) { prev_ids = strain_ids; prev_ref_of = ref_of; }              // :163 (sic): only from the third file on
         strain_ids.clear();
         all_kmers = 0;
+        const double t_a = now();
         if (!read_gz(files[fi], text)) return fail_traceback("FileNotFoundError: [Errno 2] No such file or directory: '" + files[fi] + "'");
+        const double t_b = now();
+        t_inflate += t_b - t_a;
         const char *p = text.data(), *end = p + text.size();
-        while (p < end) {
-            const char *nl = p;
-            while (nl < end && *nl != '\n' && *nl != '\r') ++nl;
-            const char *line_end = nl;
-            const char *next = nl < end ? nl + ((*nl == '\r' && nl + 1 < end && nl[1] == '\n') ? 2 : 1) : end;
-            if (line_end > p && *p == '#') { p = next; continue; }
-            // split on tabs
-            const char *f[6]; int nf = 0;
-            const char *q = p;
-            f[nf++] = q;
-            for (; q < line_end; ++q) if (*q == '\t') { if (nf < 6) f[nf] = q + 1; ++nf; }
-            const int n_fields = nf;
-            if (n_fields < 4) return fail_traceback("IndexError: list index out of range");
-            auto field_end = [&](int k) { return k + 1 < n_fields && k + 1 < 6 ? f[k + 1] - 1 : line_end; };
-            long long c1, c2, c3, c4 = 0;
-            if (!parse_int(f[1], field_end(1), &c1) || !parse_int(f[2], field_end(2), &c2) || !parse_int(f[3], field_end(3), &c3))
-                return fail_traceback("ValueError: invalid literal for int() with base 10");
-            bool is_new;
-            const uint32_t id = index.get(f[0], (size_t)(field_end(0) - f[0]), &is_new);
-            if (is_new) {
-                names.emplace_back(f[0], (size_t)(field_end(0) - f[0]));
-                pan_sum.push_back(0); meta_sum.push_back(0); in_pan.push_back(0); in_meta.push_back(0); in_drug.push_back(0);
-                ref_of.push_back(0); stamp.push_back(0);
-            }
-            ++all_kmers;
-            if (stamp[id] != fi + 1) { stamp[id] = (uint32_t)fi + 1; strain_ids.push_back(id); }
-            ref_of[id] = c1;
-            if (c2 > 0) { pan_sum[id] += (uint64_t)c2; in_pan[id] = 1; }
-            if (c3 > 0) { meta_sum[id] += (uint64_t)c3; in_meta[id] = 1; }
-            if (n_fields == 5) {
-                drug_filter = true;
-                if (!parse_int(f[4], field_end(4), &c4)) return fail_traceback("ValueError: invalid literal for int() with base 10");
-                if (c4 > 0) in_drug[id] = 1;                                     // :194 adds content[3]: only membership is used
-            }
-            p = next;
+        {                                                                         // sizes are known roughly: no reallocation / rehash while parsing
+            const uint64_t est = text.size() / 36 + 1024;
+            index.reserve(index.used + est);
+            for (auto *v : { &pan_sum, &meta_sum }) v->reserve(v->size() + est);
+            for (auto *v : { &in_pan, &in_meta, &in_drug }) v->reserve(v->size() + est);
+            ref_of.reserve(ref_of.size() + est); stamp.reserve(stamp.size() + est); name_off.reserve(name_off.size() + est);
+            name_pool.reserve(name_pool.size() + est * 31);
+            strain_ids.reserve(est);
         }
+        const bool has_cr = memchr(p, '\r', text.size()) != nullptr;             // universal newlines only cost something when there is a CR
+        struct Line { const char *b, *e; uint64_t code; };
+        Line block[64];
+        while (p < end) {
+            // the next 64 data lines; their keys' hash slots are prefetched before the lines are parsed
+            int n_lines = 0;
+            while (p < end && n_lines < 64) {
+                const char *nl;
+                if (!has_cr) { nl = (const char *)memchr(p, '\n', (size_t)(end - p)); if (!nl) nl = end; }
+                else { nl = p; while (nl < end && *nl != '\n' && *nl != '\r') ++nl; }
+                const char *next = nl < end ? nl + ((*nl == '\r' && nl + 1 < end && nl[1] == '\n') ? 2 : 1) : end;
+                if (!(nl > p && *p == '#')) {
+                    const char *tab = (const char *)memchr(p, '\t', (size_t)(nl - p));
+                    const uint64_t code = tab ? KeyIndex::encode(p, (size_t)(tab - p)) : 0;
+                    index.prefetch(code);
+                    block[n_lines++] = { p, nl, code };
+                }
+                p = next;
+            }
+            for (int li = 0; li < n_lines; ++li) {
+                const char *lb = block[li].b, *line_end = block[li].e;
+                // split on tabs
+                const char *f[6]; int nf = 0;
+                const char *q = lb;
+                f[nf++] = q;
+                for (; q < line_end; ++q) if (*q == '\t') { if (nf < 6) f[nf] = q + 1; ++nf; }
+                const int n_fields = nf;
+                if (n_fields < 4) return fail_traceback("IndexError: list index out of range");
+                auto field_end = [&](int k) { return k + 1 < n_fields && k + 1 < 6 ? f[k + 1] - 1 : line_end; };
+                long long c1, c2, c3, c4 = 0;
+                if (!parse_int(f[1], field_end(1), &c1) || !parse_int(f[2], field_end(2), &c2) || !parse_int(f[3], field_end(3), &c3))
+                    return fail_traceback("ValueError: invalid literal for int() with base 10");
+                bool is_new;
+                const size_t klen = (size_t)(field_end(0) - f[0]);
+                const uint32_t id = index.get(block[li].code, f[0], klen, &is_new);
+                if (is_new) {
+                    name_pool.append(f[0], klen); name_off.push_back(name_pool.size());
+                    pan_sum.push_back(0); meta_sum.push_back(0); in_pan.push_back(0); in_meta.push_back(0); in_drug.push_back(0);
+                    ref_of.push_back(0); stamp.push_back(0);
+                }
+                ++all_kmers;
+                if (stamp[id] != fi + 1) { stamp[id] = (uint32_t)fi + 1; strain_ids.push_back(id); }
+                ref_of[id] = c1;
+                if (c2 > 0) { pan_sum[id] += (uint64_t)c2; in_pan[id] = 1; }
+                if (c3 > 0) { meta_sum[id] += (uint64_t)c3; in_meta[id] = 1; }
+                if (n_fields == 5) {
+                    drug_filter = true;
+                    if (!parse_int(f[4], field_end(4), &c4)) return fail_traceback("ValueError: invalid literal for int() with base 10");
+                    if (c4 > 0) in_drug[id] = 1;                                 // :194 adds content[3]: only membership is used
+                }
+            }
+        }
+        t_parse += now() - t_b;
         if (fi > 1) {                                                             // dict equality with the previous file's strain dict
             bool same = prev_ids.size() == strain_ids.size();
             if (same) {
-                std::vector<uint8_t> in_prev(names.size(), 0);
+                std::vector<uint8_t> in_prev(name_off.size(), 0);
                 for (uint32_t id : prev_ids) in_prev[id] = 1;
                 for (uint32_t id : strain_ids) if (!in_prev[id] || (id < prev_ref_of.size() ? prev_ref_of[id] : 0) != ref_of[id]) { same = false; break; }
             }
@@ -299,7 +337,7 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
     }
     text.clear(); text.shrink_to_fit();
 
-    const uint64_t n_ids = names.size(), n_strain = strain_ids.size();
+    const uint64_t n_ids = name_off.size() - 1, n_strain = strain_ids.size();
     uint64_t n_pan = 0, n_meta = 0, n_drug = 0;
     for (uint64_t i = 0; i < n_ids; ++i) { n_pan += in_pan[i]; n_meta += in_meta[i]; n_drug += in_drug[i]; }
     char hb[256];
@@ -327,6 +365,7 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
     }
 
     s2_ctx *ctx = nullptr;
+    const double t_gpu0 = now();
     auto need_gpu = [&]() -> bool {
         if (!ctx) ctx = s2_init(s2_env_int("S2_DEVICE", 0), 1 << 20, 1);
         if (!ctx) fprintf(stderr, "kmer_scrub_filter: %s\n", s2_last_error());
@@ -379,7 +418,11 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
             if (!need_gpu() || s2_scrub_joint(ctx, pan.data(), meta.data(), alive.data(), n_strain, psum, msum, n_scrub, keep.data())) rc = 1;
         }
     }
+    const double t_sel = now();
     if (ctx) s2_shutdown(ctx);
+    t_gpu = now() - t_gpu0;
+    if (stats) fprintf(stderr, "[s2 filter] rows=%llu inflate=%.3fs parse=%.3fs gpu(init+select+shutdown)=%.3fs (select done after %.3fs) total=%.3fs\n",
+                       (unsigned long long)all_kmers, t_inflate, t_parse, t_gpu, t_sel - t_gpu0, now() - t_start);
     if (rc) { if (rc == 1 && s2_last_error()[0]) fprintf(stderr, "kmer_scrub_filter: %s\n", s2_last_error()); return rc; }
 
     uint64_t n_keep = 0;
@@ -390,7 +433,7 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
     std::string body;
     body.reserve((size_t)n_keep * 33);
     for (uint64_t j = 0; j < n_strain; ++j)
-        if (keep[j]) { body += names[strain_ids[j]]; body += '\n'; }
+        if (keep[j]) { const uint32_t id = strain_ids[j]; body.append(name_pool, name_off[id], name_off[id + 1] - name_off[id]); body += '\n'; }
     fwrite(body.data(), 1, body.size(), stdout);
     fflush(stdout);
     return 0;

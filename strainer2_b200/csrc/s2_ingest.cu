@@ -585,6 +585,7 @@ struct s2_ingest {
     unsigned *d_block_nl = nullptr, *d_block_out = nullptr, *d_line_end = nullptr;
     unsigned short *d_masks = nullptr;   // newline mask of every 16 text bytes
     unsigned *d_tickets = nullptr;       // last-block election of the three fused kernels
+    uint64_t *part_pool = nullptr; unsigned long long *part_cursor = nullptr; uint32_t *part_overflow = nullptr;     // two-phase scan scratch
     IngState *d_state = nullptr;
     IngResult *d_results = nullptr, *h_results = nullptr; unsigned n_results = 0;
     decompress_fn decompress = nullptr;
@@ -612,6 +613,7 @@ static void ingest_free(s2_ingest *g)
     }
     cudaFree(g->d_flat);
     cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end); cudaFree(g->d_masks); cudaFree(g->d_tickets);
+    cudaFree(g->part_pool); cudaFree(g->part_cursor); cudaFree(g->part_overflow);
     cudaFree(g->d_state); cudaFree(g->d_results); cudaFreeHost(g->h_results);
     cudaFree(g->d_hits_c); cudaFree(g->d_inf_c); cudaFree(g->d_rec_off); cudaFree(g->d_pos_c); cudaFree(g->d_cnt_c); cudaFree(g->d_fcnt);
     cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all); cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);
@@ -851,6 +853,26 @@ static size_t ingest_walk_bgzf(s2_ingest *g, IngSlot &s, const uint8_t *h, size_
     return used;
 }
 
+// the count scan of the chunk's flat batch: direct kernel, or the two-phase scan for tables larger than L2
+static int ingest_launch_count(s2_ingest *g, s2_table *t, const S2DevBatch *dev, int col)
+{
+    s2_ctx *c = g->ctx;
+    if (!t->partitioned) {
+        s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, g->stream);
+        return 0;
+    }
+    const uint64_t n_max = g->text_cap + ING_MAXCARRY;                                     // the flat batch cannot be longer
+    const uint64_t region_cap = n_max / S2_NPART + n_max / (2 * S2_NPART) + 8192;          // 1.5x the even share
+    if (!g->part_pool) {
+        CK(cudaMalloc((void **)&g->part_pool, region_cap * S2_NPART * sizeof(uint64_t)));
+        CK(cudaMalloc((void **)&g->part_cursor, (S2_NPART + 1) * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&g->part_overflow, 2 * sizeof(uint32_t)));
+    }
+    s2_launch_scan_count_partitioned(g->d_flat, 0, t->v, col, c->d_stats, g->part_pool, region_cap, g->part_cursor, g->part_overflow,
+                                     c->n_sm, c->grid_count, g->stream, dev);
+    return 0;
+}
+
 // the device work of one chunk whose compressed bytes are being copied into the slot by the copy stream
 static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk &ch, bool bgzf, bool fasta, int mode, int col, unsigned inc,
                           bool want_result)
@@ -898,14 +920,14 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     if (fasta) {
         ing_fasta_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a, g->d_tickets + 1);
         ing_fasta_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat, res, g->d_tickets + 2);
-        s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, st);
+        if (ingest_launch_count(g, t, dev, col)) return -1;
     } else {
         ing_fastq_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a,
                                                              detect ? g->d_rec_off : nullptr, g->d_tickets + 1);
         ing_fastq_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat,
                                                           detect ? g->d_rec_off : nullptr, detect ? 0u : 1u, res, g->d_tickets + 2);
         if (!detect) {
-            s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, st);
+            if (ingest_launch_count(g, t, dev, col)) return -1;
         } else {
             const size_t max_rec = (size_t)g->max_lines / 4 + 4;
             CK(cudaMemsetAsync(g->d_hits_c, 0, max_rec * sizeof(unsigned), st));
@@ -1193,7 +1215,6 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
 extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups)
 {
     if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
-    if (t->partitioned) return 1;                                    // union tables keep the host reader + two-phase scan
     std::vector<IngSource> srcs(1);
     srcs[0].fd = open(path, O_RDONLY);
     if (srcs[0].fd < 0) return 1;
@@ -1208,7 +1229,6 @@ extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, in
 extern "C" int s2_ingest_count_mem(s2_ctx *c, s2_table *t, const void *image, uint64_t n_bytes, int col, uint64_t *bases, uint64_t *lookups)
 {
     if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
-    if (t->partitioned) return 1;
     std::vector<IngSource> srcs(1);
     srcs[0].mem = (const uint8_t *)image; srcs[0].mem_len = (size_t)n_bytes;
     int rc_each = 1;
@@ -1226,7 +1246,7 @@ extern "C" int s2_ingest_count_mem_batch(s2_ctx *c, s2_table *t, const void *con
     for (int i = 0; i < n; ++i) rc_each[i] = 1;
     if (bases) *bases = 0;
     if (lookups) *lookups = 0;
-    if (t->partitioned || n <= 0) return 0;
+    if (n <= 0) return 0;
     std::vector<IngSource> srcs((size_t)n);
     for (int i = 0; i < n; ++i) { srcs[i].mem = (const uint8_t *)images[i]; srcs[i].mem_len = (size_t)n_bytes[i]; }
     return ingest_count_sources(c, t, srcs, col, rc_each, bases, lookups);
@@ -1238,7 +1258,7 @@ extern "C" int s2_ingest_count_files(s2_ctx *c, s2_table *t, const char *const *
     for (int i = 0; i < n; ++i) rc_each[i] = 1;
     if (bases) *bases = 0;
     if (lookups) *lookups = 0;
-    if (t->partitioned || n <= 0) return 0;
+    if (n <= 0) return 0;
     std::vector<IngSource> srcs;
     std::vector<int> index;
     for (int i = 0; i < n; ++i) {

@@ -452,8 +452,15 @@ struct S2PartView {
 // in each partition's global region with ONE global atomic per partition and round and copies the stage
 // out in coalesced runs (about 1 KB each).  Skewed rounds that overflow a stage append straight to global.
 __global__ void __launch_bounds__(S2_THREADS, 2)
-s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartView pv, unsigned long long *__restrict__ stats)
+s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartView pv, unsigned long long *__restrict__ stats,
+                    const S2DevBatch *__restrict__ dev)
 {
+    long long sign = 1;
+    if (dev) {                                                    // batch produced on the device (GPU ingest)
+        if (dev->skip) return;
+        n_bytes = dev->n_bytes;
+        sign = (int)dev->inc;
+    }
     extern __shared__ uint64_t stage[];                           // [S2_NPART][S2_PSTAGE]
     __shared__ uint32_t cnt[S2_NPART];
     __shared__ unsigned long long gbase[S2_NPART];
@@ -504,7 +511,7 @@ s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartV
         __syncthreads();
     }
     n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
-    if (lane == 0 && stats && n_valid) atomicAdd(&stats[1], (unsigned long long)n_valid);
+    if (lane == 0 && stats && n_valid) atomicAdd(&stats[1], (unsigned long long)(sign * (long long)n_valid));
 }
 
 // phase B, all partitions in ONE launch: CTAs draw work items (4096 entries of one partition) from a global
@@ -514,9 +521,11 @@ s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartV
 #define S2_PITEM 4096
 __global__ void __launch_bounds__(S2_THREADS, 4)
 s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_col,
-                    unsigned long long *__restrict__ stats, unsigned long long *__restrict__ work_counter)
+                    unsigned long long *__restrict__ stats, unsigned long long *__restrict__ work_counter, const S2DevBatch *__restrict__ dev)
 {
     if (*pv.overflow) return;
+    uint32_t inc = 1u;
+    if (dev) { if (dev->skip) return; inc = dev->inc; }
     __shared__ unsigned long long pre[S2_NPART + 1];
     __shared__ unsigned long long item_s;
     if (threadIdx.x == 0) {
@@ -574,13 +583,13 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
                     uint64_t key = t.keys[slot];
                     bool hit = (key & S2_KMER_MASK) == canon[u] && key != S2_EMPTY_KEY;
                     if (!hit) hit = probe_exact(t, canon[u], slot, key);
-                    if (hit) { atomicAdd(&counts_col[slot], 1u); ++n_hits; }
+                    if (hit) { atomicAdd(&counts_col[slot], inc); ++n_hits; }
                 }
             }
         }
     }
     n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
-    if ((threadIdx.x & 31) == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)n_hits);
+    if ((threadIdx.x & 31) == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)((long long)(int)inc * (long long)n_hits));
     if (sink == 0x12345679u) atomicOr(pv.overflow + 1, sink);     // never true; keeps the prefetch loads alive
 }
 
@@ -606,9 +615,9 @@ size_t s2_partition_smem_bytes(void) { return (size_t)S2_NPART * S2_PSTAGE * siz
 void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t, int col,
                                       unsigned long long *stats, uint64_t *part_pool, uint64_t region_cap,
                                       unsigned long long *cursor, uint32_t *overflow, int n_sm, int grid_blocks,
-                                      cudaStream_t stream)
+                                      cudaStream_t stream, const S2DevBatch *dev)
 {
-    if (n_bytes == 0) return;
+    if (n_bytes == 0 && !dev) return;
     unsigned long long *work_counter = cursor + S2_NPART;        // cursor[] has one spare slot for the item counter
     static bool attr_set = false;
     if (!attr_set) {
@@ -618,16 +627,16 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     cudaMemsetAsync(cursor, 0, S2_NPART * sizeof(unsigned long long), stream);
     cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
     S2PartView pv = { part_pool, region_cap, cursor, overflow };
-    s2_partition_kernel<<<n_sm * 2, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats);
+    s2_partition_kernel<<<n_sm * 2, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
     uint32_t *counts_col = t.counts + (uint64_t)col * t.n_slots;
     // buckets whose hash has top bits == p: [ceil(p * nb / 32), ceil((p+1) * nb / 32)); slice 0 is prefetched
     // by its own small kernel, every later slice by the items of the partition before it
     const uint32_t hi0 = (uint32_t)(((uint64_t)t.n_buckets + S2_NPART - 1) / S2_NPART);
     s2_prefetch_slice_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(t.fp, 0, hi0, overflow + 1);
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
-    s2_probe_all_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter);
+    s2_probe_all_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter, dev);
     S2DetectOut none = {};
-    g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow, nullptr);
+    g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow, dev);
 }
 
 // ------------------------------------------------------------------------------------------------

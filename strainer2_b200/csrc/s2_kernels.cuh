@@ -54,7 +54,7 @@ int  s2_scan_blocks_per_sm(int mode);
 void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t, int col,
                                       unsigned long long *stats, uint64_t *part_pool, uint64_t region_cap,
                                       unsigned long long *cursor, uint32_t *overflow, int n_sm, int grid_blocks,
-                                      cudaStream_t stream);
+                                      cudaStream_t stream, const S2DevBatch *dev = nullptr);
 // kernel shape selection (sweep tool / S2_SCAN_VARIANT); see s2_kernels.cu
 int  s2_scan_variant_count(void);
 const char *s2_scan_variant_name(int v);

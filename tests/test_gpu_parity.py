@@ -387,26 +387,35 @@ def test_multi_strain_batch_equals_one_reference_run_per_strain(s2, tmp_path):
     B = []
     for i in range(2):
         p = os.path.join(tmp, f"m{i}.fastq.gz")
-        synth.write_reads_fastq(p, synth.sample_reads(rng, clean + synth.genome(rng, 400_000, 2), 20_000, 150, sub_rate=0.004, n_rate=1e-4))
+        rd = synth.sample_reads(rng, clean + synth.genome(rng, 400_000, 2), 20_000, 150, sub_rate=0.004, n_rate=1e-4)
+        if i == 0:
+            synth.write_reads_fastq(p, rd)                               # ordinary gzip: host inflate
+        else:
+            synth.write_bgzf(p, synth.fastq_bytes(rd))                  # BGZF: GPU ingest into the union table
         B.append(p)
     open(os.path.join(tmp, "R.txt"), "w").write("".join(p + "\n" for p, _ in strains))
     open(os.path.join(tmp, "A.txt"), "w").write("".join(p + "\n" for p in A))
     open(os.path.join(tmp, "B.txt"), "w").write("".join(p + "\n" for p in B))
     open(os.path.join(tmp, "C.txt"), "w").write("".join(p + "\n" for p, _ in strains) + A[0] + "\n" + strains[3][0] + "\n")
-    out = os.path.join(tmp, "out")
-    p = s2.run_kmer_scrub_count_batch(["-R", os.path.join(tmp, "R.txt"), "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"),
-                                       "-C", os.path.join(tmp, "C.txt"), "-O", out], env={"S2_BATCH_MB": "2"})
-    assert p.returncode == 0, p.stderr
-    drug_sums = []
+    args = ["-R", os.path.join(tmp, "R.txt"), "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"), "-C", os.path.join(tmp, "C.txt")]
+    want = {}
     for path, _ in strains:
         o = ou.oracle_cli(["count", "-r", path, "-A", os.path.join(tmp, "A.txt"), "-B", os.path.join(tmp, "B.txt"), "-C", os.path.join(tmp, "C.txt")])
         assert o.returncode == 0
-        got = open(os.path.join(out, os.path.basename(path) + ".scrub_kmer_counts"), "rb").read()
-        assert got == o.stdout, path
-        k, v = ou.parse_table(got)
-        assert v[:, 2].sum() > 0
-        drug_sums.append(int(v[:, 3].sum()))
-    assert sum(1 for d in drug_sums if d > 0) >= 3          # the strains that share sequence see each other in -C
+        want[path] = o.stdout
+    # second run: the union table is forced through the two-phase (partitioned) scan, host batches and GPU ingest alike
+    for k_run, env in enumerate(({"S2_BATCH_MB": "2"}, {"S2_BATCH_MB": "2", "S2_PARTITION_MIN_MB": "0", "S2_PARTITION_MIN_BATCH_KB": "0"})):
+        out = os.path.join(tmp, "out%d" % k_run)
+        p = s2.run_kmer_scrub_count_batch(args + ["-O", out], env=env)
+        assert p.returncode == 0, p.stderr
+        drug_sums = []
+        for path, _ in strains:
+            got = open(os.path.join(out, os.path.basename(path) + ".scrub_kmer_counts"), "rb").read()
+            assert got == want[path], (path, env)
+            k, v = ou.parse_table(got)
+            assert v[:, 2].sum() > 0
+            drug_sums.append(int(v[:, 3].sum()))
+        assert sum(1 for d in drug_sums if d > 0) >= 3          # the strains that share sequence see each other in -C
 
 
 def test_two_phase_partitioned_scan_equals_direct_scan(s2, tmp_path, monkeypatch):
@@ -434,10 +443,28 @@ def test_two_phase_partitioned_scan_equals_direct_scan(s2, tmp_path, monkeypatch
             b = ctx.scan_count(part, torch.from_numpy(data).cuda(), col)
             assert (a.hits, a.valid_windows) == (b.hits, b.valid_windows) and a.hits > 0
             assert np.array_equal(direct.counts(col), part.counts(col))
+            if col == 1:
+                a_hits_reads = a.hits
         # host batches through the lanes use the same two-phase path
         c = ctx.scan_count(part, batch, 3)
         assert c.hits == int(direct.counts(1).sum())
         assert np.array_equal(part.counts(3), direct.counts(1))
+        # and so does the GPU ingest (batch length, veto and increment come from device memory): a BGZF image of the
+        # reads, streamed in several chunks; then an irregular one whose counted chunks are taken back out
+        monkeypatch.setenv("S2_INGEST_CHUNK_MB", "1")
+        monkeypatch.setenv("S2_INGEST_TEXT_MB", "4")
+        ctx.ingest_reset()
+        ctx.sync()
+        part.clear_counts(3)
+        text = synth.fastq_bytes(reads)
+        rc, n_bases, _ = ctx.ingest_count_mem(part, np.frombuffer(synth.bgzf_bytes(text), dtype=np.uint8), 3)
+        st = ctx.sync()
+        assert rc == 0 and n_bases == reads.size and st.hits == a_hits_reads
+        assert np.array_equal(part.counts(3), direct.counts(1))
+        bad = text + b"@x\nACGT\n+\nII\n"
+        assert ctx.ingest_count_mem(part, np.frombuffer(synth.bgzf_bytes(bad), dtype=np.uint8), 3)[0] == 1
+        assert ctx.sync().hits == 0 and np.array_equal(part.counts(3), direct.counts(1))
+        ctx.ingest_reset()
         direct.free(); part.free()
 
 
