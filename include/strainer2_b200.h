@@ -149,6 +149,16 @@ int         s2_ingest_detect_file(s2_ctx *ctx, s2_table *t, const char *path, s2
 void        s2_ingest_detect_free(s2_ingest_detect_result *r);
 void        s2_ingest_thread_cleanup(void);
 
+/* ---------------------------------------------------------------- gzip output --------------- */
+/* The kmer_hits stream of strain_detect (gzopen(outfile, "wb9") + gzprintf, src/strain_detect.c:299,567,608).
+ * threads == 0: one zlib stream at level 9 - the file is byte-identical to the reference's.  threads > 0 (SURVEY 8f
+ * rank 2): 256 KB blocks deflated independently at level 9 on that many threads (each primed with the 32 KB before
+ * it) and concatenated into one gzip member, as pigz does: the same text for any gunzip, different compressed bytes. */
+typedef struct s2_gz_writer s2_gz_writer;
+s2_gz_writer *s2_gz_writer_open(const char *path, int threads);
+int         s2_gz_writer_write(s2_gz_writer *w, const void *data, uint64_t n);
+int         s2_gz_writer_close(s2_gz_writer *w);
+
 /* ---------------------------------------------------------------- scrub filter -------------- */
 /* The selection steps of scripts/kmer_scrub_filter.py on table columns.
  * joint scrub (:88-143): rows are ranked by max(pan / pan_sum, meta / meta_sum) (IEEE doubles, as the script computes

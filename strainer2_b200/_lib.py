@@ -72,6 +72,9 @@ SIGNATURES = {
     "s2_ingest_detect_file": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]),
     "s2_ingest_detect_free": (None, [C.c_void_p]),
     "s2_ingest_thread_cleanup": (None, []),
+    "s2_gz_writer_open": (C.c_void_p, [C.c_char_p, C.c_int]),
+    "s2_gz_writer_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "s2_gz_writer_close": (C.c_int, [C.c_void_p]),
     "s2_scrub_joint": (C.c_int, [C.c_void_p, c_u64p, c_u64p, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                  C.POINTER(C.c_uint8)]),
     "s2_scrub_histogram": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, c_u64p]),

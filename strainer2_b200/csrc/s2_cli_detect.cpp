@@ -58,7 +58,7 @@ struct Detect {
     s2_ctx *ctx = nullptr;
     s2_table *table = nullptr;
     s2_exotic *exotic = nullptr;        // string keys for -r windows with bytes outside ACGTN (normally nullptr)
-    gzFile gzout = nullptr;
+    s2_gz_writer *gzout = nullptr;      // one zlib stream (byte-identical to the reference) or, S2_GZ_THREADS=n, the parallel writer
     unsigned genome_kmers = 0, genome_informative = 0;
     uint64_t batch_bytes = 32ull << 20;
     std::unordered_set<uint64_t> informative;   // device keys currently labelled INFORMATIVE
@@ -69,12 +69,7 @@ struct Detect {
 
     void write_out(const std::string &out)
     {
-        size_t off = 0;
-        while (off < out.size()) {
-            const unsigned n = (unsigned)std::min<size_t>(out.size() - off, 1u << 30);
-            gzwrite(gzout, out.data() + off, n);
-            off += n;
-        }
+        s2_gz_writer_write(gzout, out.data(), out.size());
     }
 };
 
@@ -547,7 +542,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     }
 
     // quantify_hits_all_files                                                             :263-384
-    d.gzout = gzopen(kmer_outfile, "wb9");
+    d.gzout = s2_gz_writer_open(kmer_outfile, s2_env_int("S2_GZ_THREADS", 0));                 // gzopen(outfile, "wb9") :299
     if (!d.gzout) {
         fprintf(stderr, "could not open *gzout file outfile %s in quantify_hits_all_files()\n", kmer_outfile);
         return EXIT_FAILURE;
@@ -643,7 +638,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
         for (auto &t : pool) t.join();
     }
     // on a fatal error the reference exit()s with the gz stream unfinished; we close it either way
-    gzclose(d.gzout);
+    s2_gz_writer_close(d.gzout);
     fflush(stdout);
     if (s2_env_int("S2_STATS", 0)) {
         double kms = 0; uint64_t kl = 0;

@@ -295,3 +295,41 @@ def test_hash_spreads_real_kmers(sim):
             cnt2[sim.sim_bucket(h.value, nb)] += 1
     lam2 = cnt2.sum() / nb
     assert cnt2.var() < 1.3 * lam2 and cnt2.max() <= 12
+
+
+def test_gz_writer_single_stream_and_parallel_blocks(tmp_path):
+    """s2_gz_writer: threads=0 is gzopen("wb9") + gzwrite (the reference's stream, src/strain_detect.c:299); threads>0
+    deflates 256 KB blocks in parallel into ONE gzip member - any gunzip must give back the identical text"""
+    import ctypes as C
+    import gzip
+    import random
+    import zlib
+    from strainer2_b200 import lib
+    r = random.Random(3)
+    line = lambda: b"sample_%d.fastq.gz\t%d\t%d\t%d\t%d\t%s\n" % (r.randint(0, 9), r.randint(0, 120), r.randint(0, 9), r.randint(0, 120), r.randint(0, 9),
+                                                                   bytes(r.choice(b"ACGT") for _ in range(31)))
+    big = b"".join(line() for _ in range(40_000))                     # ~2.7 MB: several rounds of blocks
+    cases = {"empty": b"", "one_byte": b"x", "block_edge": big[:262144], "block_edge_plus": big[:262145], "big": big}
+    for name, text in cases.items():
+        for threads in (0, 1, 3, 8):
+            path = str(tmp_path / f"{name}_{threads}.gz").encode()
+            w = lib.s2_gz_writer_open(path, threads)
+            assert w
+            pos, step = 0, 1
+            while pos < len(text):                                    # ragged writes: a few bytes up to hundreds of KB
+                n = min(len(text) - pos, step)
+                buf = text[pos:pos + n]
+                assert lib.s2_gz_writer_write(w, buf, n) == 0
+                pos += n
+                step = min(step * 3 + 1, 400_000)
+            assert lib.s2_gz_writer_close(w) == 0
+            raw = open(path, "rb").read()
+            assert gzip.decompress(raw) == text, (name, threads)
+            d = zlib.decompressobj(31)                                # exactly one gzip member, nothing after it
+            assert d.decompress(raw) == text and d.eof and d.unused_data == b""
+            if threads == 0:                                          # the single stream is what zlib's gzwrite gives at level 9
+                ref = str(tmp_path / "ref.gz")
+                with open(ref, "wb") as f:
+                    pass
+                g = zlib.compressobj(9, zlib.DEFLATED, 31)
+                assert len(raw) == len(g.compress(text) + g.flush())
