@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -241,6 +242,14 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
     const bool stats = s2_env_int("S2_STATS", 0) != 0;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
+    // the CUDA context comes up (hundreds of milliseconds) while the table is inflated and parsed
+    struct EarlyCtx {
+        s2_ctx *ctx = nullptr; std::string error; std::thread th; bool started = false;
+        void start() { started = true; th = std::thread([this]() { ctx = s2_init(s2_env_int("S2_DEVICE", 0), 1 << 20, 1); if (!ctx) error = s2_last_error(); }); }
+        s2_ctx *get() { if (th.joinable()) th.join(); return ctx; }
+        ~EarlyCtx() { if (th.joinable()) th.join(); if (ctx) s2_shutdown(ctx); }
+    } early;
+    if (!files.empty()) early.start();
     double t_inflate = 0, t_parse = 0, t_gpu = 0;
     KeyIndex index;
     std::vector<uint64_t> pan_sum, meta_sum;            // over ids; membership flags beside them
@@ -367,8 +376,8 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
     s2_ctx *ctx = nullptr;
     const double t_gpu0 = now();
     auto need_gpu = [&]() -> bool {
-        if (!ctx) ctx = s2_init(s2_env_int("S2_DEVICE", 0), 1 << 20, 1);
-        if (!ctx) fprintf(stderr, "kmer_scrub_filter: %s\n", s2_last_error());
+        if (!ctx) { if (!early.started) early.start(); ctx = early.get(); }
+        if (!ctx) fprintf(stderr, "kmer_scrub_filter: %s\n", early.error.c_str());
         return ctx != nullptr;
     };
     int rc = 0;
@@ -418,12 +427,10 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
             if (!need_gpu() || s2_scrub_joint(ctx, pan.data(), meta.data(), alive.data(), n_strain, psum, msum, n_scrub, keep.data())) rc = 1;
         }
     }
-    const double t_sel = now();
-    if (ctx) s2_shutdown(ctx);
     t_gpu = now() - t_gpu0;
-    if (stats) fprintf(stderr, "[s2 filter] rows=%llu inflate=%.3fs parse=%.3fs gpu(init+select+shutdown)=%.3fs (select done after %.3fs) total=%.3fs\n",
-                       (unsigned long long)all_kmers, t_inflate, t_parse, t_gpu, t_sel - t_gpu0, now() - t_start);
-    if (rc) { if (rc == 1 && s2_last_error()[0]) fprintf(stderr, "kmer_scrub_filter: %s\n", s2_last_error()); return rc; }
+    if (stats) fprintf(stderr, "[s2 filter] rows=%llu inflate=%.3fs parse=%.3fs wait for context + select=%.3fs total so far=%.3fs\n",
+                       (unsigned long long)all_kmers, t_inflate, t_parse, t_gpu, now() - t_start);
+    if (rc) { if (rc == 1 && ctx && s2_last_error()[0]) fprintf(stderr, "kmer_scrub_filter: %s\n", s2_last_error()); return rc; }
 
     uint64_t n_keep = 0;
     for (uint64_t j = 0; j < n_strain; ++j) n_keep += keep[j] ? 1 : 0;

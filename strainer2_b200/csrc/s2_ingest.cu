@@ -19,9 +19,12 @@
 //            last record to the next chunk
 //   scan   : the normal count / detect kernel; batch length, veto and increment are read from device memory
 //
-// A chunk is either a slice of one big file (streamed through a two-slot ring: the copy of chunk i+1 overlaps the
-// kernels of chunk i) or a GROUP of whole small files whose texts lie back to back (2,000 genomes of 5 Mb are 2,000
-// x 1.5 MB of BGZF: one launch sequence per file would be all latency).
+// A chunk is either a slice of one big file or a GROUP of whole small files whose texts lie back to back (2,000
+// genomes of 5 Mb are 2,000 x 1.5 MB of BGZF: one launch sequence per file would be all latency).  Chunks travel
+// through a three-slot ring on three streams, one per engine: the host -> device copy of chunk i+2, the inflate of
+// chunk i+1 and the kernels of chunk i run at the same time.  Steps that need every block's result (the scans over
+// the blocks, the chunk's verdict and carry) run in the last block to finish of the preceding kernel, so a chunk
+// is five launches.
 //
 // Parity: the parser the reference vendors accepts many irregular layouts (multi-line FASTQ, CR LF, '>'
 // records mixed in, truncated last record ...).  The kernels do not emulate those; they PROVE that a chunk is

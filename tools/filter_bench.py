@@ -50,6 +50,8 @@ def main():
         t1 = time.time()
         p = subprocess.run([exe] + argv, cwd=tmp, capture_output=True)
         t_ours = time.time() - t1
+        q = subprocess.run([exe] + argv, cwd=tmp, capture_output=True, env=dict(os.environ, S2_STATS="1"))      # once more for the phase times
+        print("  " + "".join(l for l in q.stderr.decode().splitlines(True) if l.startswith("[s2 filter]")).strip(), flush=True)
         line = f"kmer_scrub_filter {' '.join(argv)}: rc={p.returncode} {t_ours:.2f}s, {len(p.stdout)} bytes out"
         if args.oracle:
             from oracle import scrub_filter_oracle as fo
