@@ -1,3 +1,11 @@
-/* drop-in for scripts/kmer_scrub_filter.py: everything lives in libstrainer2_b200.so */
+/* drop-in executable: everything lives in libstrainer2_b200.so.  The process ends with _exit() after flushing its
+ * streams: tearing the CUDA context down at exit costs up to seconds and frees nothing the OS does not free anyway. */
+#include <stdio.h>
+#include <unistd.h>
 int s2_kmer_scrub_filter_main(int argc, char **argv);
-int main(int argc, char **argv) { return s2_kmer_scrub_filter_main(argc, argv); }
+int main(int argc, char **argv)
+{
+    const int rc = s2_kmer_scrub_filter_main(argc, argv);
+    fflush(NULL);
+    _exit(rc);
+}

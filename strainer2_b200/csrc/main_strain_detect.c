@@ -1,3 +1,11 @@
-/* strain_detect - drop-in executable (replaces /root/reference/src/strain_detect.c). */
-#include "../../include/strainer2_b200.h"
-int main(int argc, char **argv) { return s2_strain_detect_main(argc, argv); }
+/* drop-in executable: everything lives in libstrainer2_b200.so.  The process ends with _exit() after flushing its
+ * streams: tearing the CUDA context down at exit costs up to seconds and frees nothing the OS does not free anyway. */
+#include <stdio.h>
+#include <unistd.h>
+int s2_strain_detect_main(int argc, char **argv);
+int main(int argc, char **argv)
+{
+    const int rc = s2_strain_detect_main(argc, argv);
+    fflush(NULL);
+    _exit(rc);
+}

@@ -152,6 +152,18 @@ def bgzf_bytes(data: bytes, block: int = 65280, level: int = 6) -> bytes:
     return b"".join(out)
 
 
+def bgzf_bytes_parallel(data: bytes, block: int = 65280, level: int = 6, threads: int = 16) -> bytes:
+    """bgzf_bytes() on a thread pool (zlib releases the GIL): members are independent, so pieces cut at multiples of the
+    block size compress separately and concatenate; the empty EOF member comes once, at the end"""
+    from concurrent.futures import ThreadPoolExecutor
+    piece = block * 256
+    eof = bgzf_bytes(b"", block, level)
+    parts = [data[o:o + piece] for o in range(0, len(data), piece)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        out = list(ex.map(lambda d: bgzf_bytes(d, block, level)[:-len(eof)], parts))
+    return b"".join(out) + eof
+
+
 def write_bgzf(path, data: bytes, block: int = 65280, level: int = 6):
     with open(path, "wb") as f:
         f.write(bgzf_bytes(data, block, level))

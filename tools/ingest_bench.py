@@ -46,7 +46,7 @@ def main():
     clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for c in strain]
     reads = synth.sample_reads(rng, clean + synth.genome(rng, 5_000_000, 4), args.reads, 150, sub_rate=0.005, n_rate=1e-5)
     rtext = synth.fastq_bytes(reads)
-    rz = synth.bgzf_bytes(rtext)
+    rz = synth.bgzf_bytes_parallel(rtext)
     rpb = s2.PinnedBuffer(len(rz))
     rpb.array[:] = np.frombuffer(rz, dtype=np.uint8)
     print(f"# inputs ready in {time.time() - t0:.1f}s: genome image {images[0][1] / 1e6:.2f} MB for {images[0][2] / 1e6:.2f} MB of FASTA; "
