@@ -73,7 +73,8 @@ struct IngState {                 // lives in device memory, one per ingest pipe
     unsigned int inf_overflow;    // a chunk produced more informative windows / records than the lists hold
     unsigned int last_chunk, first_chunk;
     unsigned int tail_len;        // FASTA: last bytes of the previous chunk's flat stream, re-scanned in front of this one
-    unsigned int pad;
+    unsigned int open_kind;       // FASTA, streamed: what this chunk ends in - 0 a line start, 1 inside a sequence line, 2 inside a header
+    unsigned int open_kind_in;    // ... and what the previous chunk ended in (= what this chunk's first line continues)
     unsigned char tail[32];
 };
 
@@ -195,8 +196,11 @@ __global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, In
 {
     const ull carry = a.first_chunk ? 0ull : st->carry_len;
     const ull t0 = ING_MAXCARRY - carry, t1 = ING_MAXCARRY + a.new_bytes;
-    // a final line without '\n' is completed (the parser the reference uses accepts that; the buffer has room past t1)
-    const bool term = a.last_chunk && t1 > t0 && text[t1 - 1] != '\n';
+    // a final line without '\n' is completed (the parser the reference uses accepts that; the buffer has room past t1).
+    // FASTA carries no bytes between chunks: a chunk of a streamed file always ends its last line here - the line's
+    // bytes are emitted with this chunk and st->open_kind tells the next chunk what its first line continues - so
+    // lines may be as long as they like.
+    const bool term = a.last_chunk ? (t1 > t0 && text[t1 - 1] != '\n') : (a.fasta != 0);
     unsigned n = 0, any_cr = 0;
 #pragma unroll
     for (unsigned k = 0; k < ING_TILES; ++k) {
@@ -216,7 +220,8 @@ __global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, In
         st->t0 = t0; st->t1 = t1 + (term ? 1 : 0);
         st->first_chunk = a.first_chunk; st->last_chunk = a.last_chunk;
         st->inc = a.inc; st->flat_len = 0;
-        if (a.first_chunk) st->tail_len = 0;
+        if (a.first_chunk) { st->tail_len = 0; st->open_kind = 0; }
+        st->open_kind_in = a.first_chunk ? 0u : st->open_kind;
     }
     if (!ing_last_block(ticket)) return;
     // the last block: counts -> offsets; the total is the line count of the chunk
@@ -277,8 +282,28 @@ __device__ __forceinline__ void ing_check_chunk(const uint8_t *__restrict__ text
 // the chunk's verdict (everything that can veto the scan is known once all blocks are measured), the carry, and the
 // batch length the scan kernel will read.  Runs in the last block of the measure kernels, after the scan over the
 // blocks' output sizes.
-__device__ __forceinline__ void ing_chunk_verdict(IngState *st, const unsigned *line_end, unsigned total, unsigned fasta, ull *rec_off)
+// kind of FASTA line L: 1 sequence, 2 header (3 = a header that begins here: counts as a record and emits the separator)
+__device__ __forceinline__ unsigned ing_fasta_kind(unsigned L, unsigned len, uint8_t first, unsigned open_prev)
 {
+    if (L == 0 && open_prev) return open_prev;                               // continues the previous chunk's last line
+    return len && first == '>' ? 3u : 1u;
+}
+
+__device__ __forceinline__ void ing_chunk_verdict(const uint8_t *text, IngState *st, const unsigned *line_end, unsigned total, unsigned fasta, ull *rec_off)
+{
+    if (fasta && !st->last_chunk) {                                          // what does the next chunk's first line continue?
+        const ull t1 = st->t1 - 1;                                           // (the chunk's text without the line end added at its end)
+        const unsigned n_lines = st->n_lines;
+        if (t1 > st->t0 && n_lines) {
+            if (text[t1 - 1] == '\n') st->open_kind = 0;
+            else {
+                const unsigned L = n_lines - 1;
+                const ull s0 = L ? (ull)__ldcg(line_end + L - 1) + 1 : st->t0;
+                const unsigned k = ing_fasta_kind(L, (unsigned)(t1 - s0), text[s0], st->open_kind_in);
+                st->open_kind = k == 1 ? 1u : 2u;
+            }
+        }
+    }
     const unsigned irregular = atomicOr(&st->irregular, 0u);                 // what every block reported (L2)
     const unsigned n_done = fasta ? st->n_lines : 4 * st->n_rec;             // lines that belong to complete records
     const ull c_from = n_done ? (ull)__ldcg(line_end + n_done - 1) + 1 : st->t0;
@@ -318,7 +343,16 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *
         if (len) { const uint8_t c = text[s0]; ok = ok && c != '>' && c != '+' && c != '@'; }
         bad |= !ok;
         bases += len;
-        if (len >= S2_K) { lookups += len - (S2_K - 1); out += len + 1; }      // records without a window are not copied (genome_compare.c:204)
+        if (len >= S2_K) lookups += len - (S2_K - 1);
+    }
+    // output bytes are accounted to the block in which the SEQUENCE line ends (the copy kernel's ownership rule)
+    {
+        const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines), n_rec = st->n_rec;
+        for (unsigned L = l_lo + threadIdx.x; L < l_hi; L += ING_THREADS)
+            if ((L & 3u) == 1u && (L >> 2) < n_rec) {
+                const unsigned len = line_end[L] - (line_end[L - 1] + 1);
+                if (len >= S2_K) out += len + 1;                    // records without a window are not copied (genome_compare.c:204)
+            }
     }
     if (bad) atomicOr(&st->irregular, 1u);
     bases = ing_block_sum(bases); lookups = ing_block_sum(lookups); out = ing_block_sum(out);
@@ -329,7 +363,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *
     }
     if (!ing_last_block(ticket)) return;
     const unsigned total = ing_scan_array(block_out, gridDim.x);
-    if (threadIdx.x == 0) ing_chunk_verdict(st, line_end, total, 0u, rec_off);
+    if (threadIdx.x == 0) ing_chunk_verdict(text, st, line_end, total, 0u, rec_off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,76 +390,112 @@ __device__ __forceinline__ void ing_finish_body(const uint8_t *text, uint8_t *te
     }
 }
 
-// The copy kernels stage the text their block's lines come from in shared memory with 128-bit loads (the 16 KB of the
-// block plus the 8 KB in front of it, where a line that ends in this block normally starts); the lines then go from
-// shared memory to the flat stream with byte stores, which do not wait for anything.  (Copying line by line straight
-// from global memory is latency bound: every 32-byte piece is a dependent load -> store round trip.)
-#define ING_STAGE_BACK 8192u
-__device__ __forceinline__ ull ing_stage(const uint8_t *__restrict__ text, uint8_t *stage)
+// The copy kernels work by BYTE OWNERSHIP: a block copies the sequence bytes that lie in its own 16 KB of text,
+// whichever line they belong to - lines that end in the block (output offset = the block's offset + a scan inside
+// the block), the head part of a line that started in an earlier block, and the part of a line that is still open at
+// the block's end (such a line is the first one to end in its last block, so its output offset is that block's
+// offset).  Long lines - unwrapped genomes, long reads - are thereby spread over as many blocks as they span.  The
+// block's text is staged in shared memory with 128-bit loads; pieces up to 512 bytes are copied by one warp each,
+// longer ones by the whole block.
+#define ING_BIG_PIECE 512u
+#define ING_MAX_BIG 40
+struct IngPieces {                      // shared-memory work list of one block
+    unsigned src[ING_THREADS], len[ING_THREADS], dst[ING_THREADS];     // this round's small pieces (stage index, bytes, flat offset)
+    unsigned big_src[ING_MAX_BIG], big_len[ING_MAX_BIG], big_dst[ING_MAX_BIG];
+    unsigned n_big;
+};
+
+__device__ __forceinline__ void ing_stage_block(const uint8_t *__restrict__ text, uint8_t *stage)
 {
     const ull b0 = (ull)blockIdx.x * ING_BLOCK;
-    const ull w0 = b0 >= ING_STAGE_BACK ? b0 - ING_STAGE_BACK : 0;
-    constexpr int N = (ING_STAGE_BACK + ING_BLOCK) / (ING_THREADS * 16);        // 6 loads in flight per thread
+    constexpr int N = ING_BLOCK / (ING_THREADS * 16);        // 4 loads in flight per thread
     uint4 v[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const ull off = w0 + (ull)k * ING_THREADS * 16 + threadIdx.x * 16;
-        v[k] = make_uint4(0, 0, 0, 0);
-        if (off < b0 + ING_BLOCK) v[k] = __ldg(reinterpret_cast<const uint4 *>(text + off));
-    }
+    for (int k = 0; k < N; ++k) v[k] = __ldg(reinterpret_cast<const uint4 *>(text + b0 + (ull)k * ING_THREADS * 16 + threadIdx.x * 16));
 #pragma unroll
     for (int k = 0; k < N; ++k) *reinterpret_cast<uint4 *>(stage + (ull)k * ING_THREADS * 16 + threadIdx.x * 16) = v[k];
-    __syncthreads();
-    return w0;
 }
 
-__device__ __forceinline__ uint8_t stage_or_text(const uint8_t *text, const uint8_t *stage, ull w0, unsigned pos)
+// a piece [lo, hi) of text (inside this block) that goes to flat + dst: small ones into this thread's slot of the round,
+// big ones onto the block's list
+__device__ __forceinline__ void ing_add_piece(IngPieces &w, unsigned lo, unsigned hi, unsigned dst, bool to_slot)
 {
-    return pos >= w0 ? stage[pos - w0] : text[pos];
-}
-
-// copy `n` bytes starting at text position `src` with one warp; what lies at or behind w0 comes from the stage
-__device__ __forceinline__ void ing_warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ text, const uint8_t *stage, ull w0,
-                                              unsigned src, unsigned n, int lane)
-{
-    unsigned i = lane;
-    if (src < w0) {                                          // a long line: its head is still in global memory
-        const unsigned n0 = min(n, (unsigned)(w0 - src));
-        for (; i < n0; i += 32) dst[i] = text[src + i];
+    const unsigned b0 = blockIdx.x * ING_BLOCK;
+    unsigned n = hi > lo ? hi - lo : 0u;
+    if (n > ING_BIG_PIECE || (!to_slot && n)) {
+        const unsigned at = atomicAdd(&w.n_big, 1u);
+        if (at < ING_MAX_BIG) { w.big_src[at] = lo - b0; w.big_len[at] = n; w.big_dst[at] = dst; }
+        n = 0;
     }
-    for (; i < n; i += 32) dst[i] = stage[(ull)src + i - w0];
+    if (to_slot) { w.src[threadIdx.x] = lo - b0; w.len[threadIdx.x] = n; w.dst[threadIdx.x] = dst; }
+}
+
+__device__ __forceinline__ void ing_copy_small(const IngPieces &w, const uint8_t *stage, uint8_t *__restrict__ flat, unsigned cnt)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) {
+        const unsigned n = w.len[e];
+        const uint8_t *sp = stage + w.src[e];
+        uint8_t *dp = flat + w.dst[e];
+        for (unsigned i = lane; i < n; i += 32) dp[i] = sp[i];
+    }
+}
+
+__device__ __forceinline__ void ing_copy_big(const IngPieces &w, const uint8_t *stage, uint8_t *__restrict__ flat)
+{
+    const unsigned nb = min(w.n_big, (unsigned)ING_MAX_BIG);
+    for (unsigned e = 0; e < nb; ++e) {
+        const unsigned n = w.big_len[e];
+        const uint8_t *sp = stage + w.big_src[e];
+        uint8_t *dp = flat + w.big_dst[e];
+        for (unsigned i = threadIdx.x; i < n; i += ING_THREADS) dp[i] = sp[i];
+    }
 }
 
 __global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *text, uint8_t *text_next, IngState *st, const unsigned *__restrict__ block_off,
                                                                const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
                                                                uint8_t *flat, ull *__restrict__ rec_off, unsigned do_finish, IngResult *res, unsigned *ticket)
 {
-    __shared__ unsigned s_src[ING_THREADS], s_len[ING_THREADS], s_dst[ING_THREADS];
-    __shared__ __align__(16) uint8_t stage[ING_STAGE_BACK + ING_BLOCK];
-    const unsigned n_lines = st->n_lines;
-    const unsigned r_lo = min(block_off[blockIdx.x], n_lines) / 4, r_hi = min(block_off[blockIdx.x + 1], n_lines) / 4;
-    if (!st->skip && r_lo < r_hi) {
-        const ull w0 = ing_stage(text, stage);
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ IngPieces w;
+    __shared__ __align__(16) uint8_t stage[ING_BLOCK];
+    const unsigned n_lines = st->n_lines, n_rec = st->n_rec;
+    const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
+    const unsigned b0 = blockIdx.x * ING_BLOCK, b1 = b0 + ING_BLOCK;
+    // is a sequence line of a complete record still open at the end of this block?
+    const bool open_seq = l_hi < n_lines && (l_hi & 3u) == 1u && (l_hi >> 2) < n_rec;
+    if (!st->skip && (l_lo < l_hi || open_seq)) {
+        if (threadIdx.x == 0) w.n_big = 0;
+        ing_stage_block(text, stage);
+        __syncthreads();
         unsigned run = block_out[blockIdx.x];
-        for (unsigned r0 = r_lo; r0 < r_hi; r0 += ING_THREADS) {
-            const unsigned r = r0 + threadIdx.x;
-            unsigned s0 = 0, olen = 0;
-            if (r < r_hi) {
-                s0 = line_end[4 * r] + 1;
-                const unsigned len = line_end[4 * r + 1] - s0;
-                olen = len >= S2_K ? len + 1 : 0;                       // includes the line's own '\n' = the separator
+        for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
+            const unsigned L = l0 + threadIdx.x;
+            unsigned s0 = 0, e1 = 0, olen = 0;
+            const bool seq = L < l_hi && (L & 3u) == 1u && (L >> 2) < n_rec;
+            if (seq) {
+                s0 = line_end[L - 1] + 1;
+                e1 = line_end[L] + 1;                                // one past the line's own '\n' = the separator
+                olen = e1 - 1 - s0 >= S2_K ? e1 - s0 : 0;           // records without a window are not copied
             }
             unsigned total;
             const unsigned at = run + ing_block_scan(olen, total);
-            s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
-            if (rec_off && r < r_hi) rec_off[r] = at;
+            if (seq && rec_off) rec_off[L >> 2] = at;
+            const unsigned lo = max(s0, b0);                         // the line may have started in an earlier block
+            ing_add_piece(w, lo, olen ? e1 : lo, at + (lo - s0), true);
             __syncthreads();
-            const unsigned cnt = min((unsigned)ING_THREADS, r_hi - r0);
-            for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) ing_warp_copy(flat + s_dst[e], text, stage, w0, s_src[e], s_len[e], lane);
+            ing_copy_small(w, stage, flat, min((unsigned)ING_THREADS, l_hi - l0));
             __syncthreads();
             run += total;
         }
+        if (open_seq && threadIdx.x == 0) {
+            const unsigned s0 = line_end[l_hi - 1] + 1, len = line_end[l_hi] - s0;
+            if (s0 < b1 && len >= S2_K) {
+                const unsigned lo = max(s0, b0);
+                ing_add_piece(w, lo, b1, block_out[line_end[l_hi] / ING_BLOCK] + (lo - s0), false);
+            }
+        }
+        __syncthreads();
+        ing_copy_big(w, stage, flat);
     }
     if (!do_finish || !ing_last_block(ticket)) return;
     ing_finish_body(text, text_next, st, flat, 0u, res);
@@ -441,17 +511,19 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fasta_measure(const uint8_t *
     const unsigned n_lines = st->n_lines;
     const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
     const ull t0 = st->t0;
+    const unsigned open_prev = st->open_kind_in;
     ull bases = 0, recs = 0, out = 0;
     bool bad = false;
     for (unsigned L = l_lo + threadIdx.x; L < l_hi; L += ING_THREADS) {
         const ull s0 = L ? (ull)line_end[L - 1] + 1 : t0;
         const unsigned len = line_end[L] - (unsigned)s0;
         const uint8_t first = len ? text[s0] : 0;
-        const bool header = first == '>';
-        if (first == '@' || first == '+') bad = true;                              // the reference's parser would switch to FASTQ rules
-        if (L == 0 && a.first_chunk && !header) bad = true;                        // text before the first record
-        out += header ? 1u : len;                                                  // a header becomes the record separator
-        if (header) ++recs; else bases += len;
+        const unsigned kind = ing_fasta_kind(L, len, first, open_prev);
+        const bool line_start = !(L == 0 && open_prev);
+        if (line_start && (first == '@' || first == '+')) bad = true;              // the reference's parser would switch to FASTQ rules
+        if (L == 0 && a.first_chunk && kind != 3) bad = true;                      // text before the first record
+        out += kind == 3 ? 1u : kind == 1 ? len : 0u;                              // a header becomes the record separator
+        if (kind == 3) ++recs; else if (kind == 1) bases += len;
     }
     if (bad) atomicOr(&st->irregular, 1u);
     bases = ing_block_sum(bases); recs = ing_block_sum(recs); out = ing_block_sum(out);
@@ -462,44 +534,58 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fasta_measure(const uint8_t *
     }
     if (!ing_last_block(ticket)) return;
     const unsigned total = ing_scan_array(block_out, gridDim.x);
-    if (threadIdx.x == 0) ing_chunk_verdict(st, line_end, total, 1u, nullptr);
+    if (threadIdx.x == 0) ing_chunk_verdict(text, st, line_end, total, 1u, nullptr);
 }
 
 __global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *text, uint8_t *text_next, IngState *st, const unsigned *__restrict__ block_off,
                                                                const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
                                                                uint8_t *flat, IngResult *res, unsigned *ticket)
 {
-    __shared__ unsigned s_src[ING_THREADS], s_len[ING_THREADS], s_dst[ING_THREADS];
-    __shared__ __align__(16) uint8_t stage[ING_STAGE_BACK + ING_BLOCK];
+    __shared__ IngPieces w;
+    __shared__ __align__(16) uint8_t stage[ING_BLOCK];
     const unsigned n_lines = st->n_lines, tail = st->tail_len;
     const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned b0 = blockIdx.x * ING_BLOCK, b1 = b0 + ING_BLOCK;
     const bool skip = st->skip != 0;
-    if (!skip && blockIdx.x == 0 && wid == 0) for (unsigned i = lane; i < tail; i += 32) flat[i] = st->tail[i];
-    if (!skip && l_lo < l_hi) {
-        const ull t0 = st->t0;
-        const ull w0 = ing_stage(text, stage);
+    if (!skip && blockIdx.x == 0 && threadIdx.x < tail) flat[threadIdx.x] = st->tail[threadIdx.x];
+    if (!skip && (l_lo < l_hi || l_hi < n_lines)) {
+        const unsigned t0 = (unsigned)st->t0;
+        const unsigned open_prev = st->open_kind_in;
+        if (threadIdx.x == 0) w.n_big = 0;
+        ing_stage_block(text, stage);
+        __syncthreads();
         unsigned run = tail + block_out[blockIdx.x];
         for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
             const unsigned L = l0 + threadIdx.x;
-            unsigned s0 = 0, olen = 0;
+            unsigned s0 = 0, e = 0, olen = 0;
+            bool header = false;
             if (L < l_hi) {
-                s0 = L ? line_end[L - 1] + 1 : (unsigned)t0;
-                olen = line_end[L] - s0;
-                if (olen && stage_or_text(text, stage, w0, s0) == '>') { olen = 1; s0 = 0xFFFFFFFFu; }      // header: one separator byte
+                s0 = L ? line_end[L - 1] + 1 : t0;
+                e = line_end[L];
+                olen = e - s0;
+                const unsigned kind = ing_fasta_kind(L, olen, olen ? (s0 >= b0 ? stage[s0 - b0] : text[s0]) : 0, open_prev);
+                header = kind != 1;
+                if (header) olen = kind == 3 ? 1u : 0u;              // a header becomes the record separator, once
             }
             unsigned total;
             const unsigned at = run + ing_block_scan(olen, total);
-            s_src[threadIdx.x] = s0; s_len[threadIdx.x] = olen; s_dst[threadIdx.x] = at;
+            if (header && olen) flat[at] = '\n';
+            const unsigned lo = max(s0, b0);                         // the line may have started in an earlier block
+            ing_add_piece(w, lo, header ? lo : e, at + (lo - s0), true);
             __syncthreads();
-            const unsigned cnt = min((unsigned)ING_THREADS, l_hi - l0);
-            for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) {
-                if (s_src[e] == 0xFFFFFFFFu) { if (lane == 0) flat[s_dst[e]] = '\n'; }
-                else ing_warp_copy(flat + s_dst[e], text, stage, w0, s_src[e], s_len[e], lane);
-            }
+            ing_copy_small(w, stage, flat, min((unsigned)ING_THREADS, l_hi - l0));
             __syncthreads();
             run += total;
         }
+        if (l_hi < n_lines && threadIdx.x == 0) {                   // the line that is still open at the end of this block
+            const unsigned s0 = l_hi ? line_end[l_hi - 1] + 1 : t0;
+            if (s0 < b1 && line_end[l_hi] > s0 && ing_fasta_kind(l_hi, 1u, s0 >= b0 ? stage[s0 - b0] : text[s0], open_prev) == 1) {
+                const unsigned lo = max(s0, b0);
+                ing_add_piece(w, lo, b1, tail + block_out[line_end[l_hi] / ING_BLOCK] + (lo - s0), false);
+            }
+        }
+        __syncthreads();
+        ing_copy_big(w, stage, flat);
     }
     if (!ing_last_block(ticket)) return;
     ing_finish_body(text, text_next, st, flat, 1u, res);

@@ -593,6 +593,60 @@ def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path, monk
     ctx.ingest_reset()
 
 
+@pytest.mark.parametrize("chunk_mb", [(1, 4), None], ids=["streamed", "one_chunk"])
+def test_gpu_ingest_long_lines_are_spread_over_blocks(s2, ctx, tmp_path, monkeypatch, chunk_mb):
+    """unwrapped genomes and long reads: a line of hundreds of KB spans many 16 KB text blocks, each of which copies the
+    part that lies in it; FASTA lines may be longer than a chunk (no bytes are carried between chunks, only what kind of
+    line is open), FASTQ records must fit the 1 MB carry"""
+    from strainer2_b200 import synth
+    _ingest_chunks(ctx, monkeypatch, chunk_mb)
+    tmp = str(tmp_path)
+    rng = synth.rng_for(12, 0)
+    strain = synth.genome(rng, 300_000, 3, n_runs=2)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    rel = [synth.mutate(c, 0.01, rng) for c in strain]
+    # FASTA: one line per contig (100 kb each), a 900 kb line, short and empty-ish records in between, a wrapped record
+    contigs = rel + [synth.random_bases(rng, 900_000)] + [synth.random_bases(rng, n) for n in (31, 30, 1, 16_384, 16_383, 16_385, 512, 513)] + rel[:1]
+    text = b"".join(b">c%d\n%s\n" % (i, c.tobytes()) for i, c in enumerate(contigs)) + synth.fasta_bytes(rel[1:2], 80)
+    open(os.path.join(tmp, "u.fa.gz"), "wb").write(synth.bgzf_bytes(text))
+    want = ctx.scan_count(t, s2.load_flat(os.path.join(tmp, "u.fa.gz")), 1)
+    assert want.hits > 300_000
+    rc, bases, _ = ctx.ingest_count_file(t, os.path.join(tmp, "u.fa.gz"), 2)
+    st = ctx.sync()
+    assert rc == 0 and bases == sum(c.size for c in contigs) + rel[1].size
+    assert st.hits == want.hits and st.valid_windows == want.valid_windows and np.array_equal(t.counts(2), t.counts(1))
+    # lines longer than a chunk (streamed: 4 MB of text per chunk): a 9 Mb chromosome on one line that holds the strain
+    # twice, a header of 5 MB, and the file from above behind them
+    chrom = synth.random_bases(rng, 9_000_000)
+    chrom[2_000_000:2_100_000] = rel[0][:100_000]
+    chrom[8_388_600:8_388_600 + rel[1].size] = rel[1]
+    big = b">chromosome\n" + chrom.tobytes() + b"\n>" + b"h" * 5_000_000 + b"\n" + text
+    open(os.path.join(tmp, "big.fa.gz"), "wb").write(synth.bgzf_bytes_parallel(big, threads=8))
+    t.clear_counts(1); t.clear_counts(2)
+    want = ctx.scan_count(t, s2.load_flat(os.path.join(tmp, "big.fa.gz")), 1)
+    rc, bases, _ = ctx.ingest_count_file(t, os.path.join(tmp, "big.fa.gz"), 2)
+    st = ctx.sync()
+    assert rc == 0 and bases == chrom.size + sum(c.size for c in contigs) + rel[1].size
+    assert st.hits == want.hits and st.valid_windows == want.valid_windows and np.array_equal(t.counts(2), t.counts(1))
+    # FASTQ with long reads (quality lines just as long) between short ones
+    reads = []
+    for i, n in enumerate((150, 40_000, 150, 31, 30, 100_000, 16_384, 20, 250_000, 150, 16_385, 400_000, 151)):      # records stay below the 1 MB carry limit
+        src = np.concatenate([rel[i % 3], synth.random_bases(rng, max(0, n - rel[i % 3].size))])[:n]
+        reads.append(src)
+    fq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r.tobytes(), b"I" * r.size) for i, r in enumerate(reads)) * 2
+    open(os.path.join(tmp, "long.fastq.gz"), "wb").write(synth.bgzf_bytes(fq))
+    t.clear_counts(1); t.clear_counts(2)
+    want = ctx.scan_count(t, s2.load_flat(os.path.join(tmp, "long.fastq.gz")), 1)
+    assert want.hits > 100_000
+    rc, bases, lookups = ctx.ingest_count_file(t, os.path.join(tmp, "long.fastq.gz"), 2)
+    st = ctx.sync()
+    assert rc == 0 and bases == 2 * sum(r.size for r in reads) and lookups == 2 * sum(r.size - 30 for r in reads if r.size >= 31)
+    assert st.hits == want.hits and st.valid_windows == want.valid_windows and np.array_equal(t.counts(2), t.counts(1))
+    t.free()
+    ctx.ingest_reset()
+
+
 def test_gpu_ingest_groups_of_small_files(s2, ctx, tmp_path, monkeypatch):
     """many files per call: small files share a chunk (texts back to back); an irregular member sends its group back
     to be run file by file; rc_each tells which files were not handled; counters = sum over the handled files"""
