@@ -679,6 +679,7 @@ struct s2_ingest {
     IngResult *d_results = nullptr, *h_results = nullptr; unsigned n_results = 0;
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
+    int grid_scan = 0;                   // CTAs of the count scan launched from this pipeline
     // detect mode: chunk-local and file-level result arrays
     unsigned *d_hits_c = nullptr, *d_inf_c = nullptr;
     ull *d_rec_off = nullptr, *d_pos_c = nullptr, *d_cnt_c = nullptr, *d_fcnt = nullptr;
@@ -719,6 +720,11 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     g->comp_chunk = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_CHUNK_MB", 16), 1), 1024) << 20;
     g->text_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_TEXT_MB", 64), 4), 2048) << 20;
     g->max_lines = (unsigned)(g->text_cap / 8);
+    {   // S2_INGEST_SCAN_CTAS: scan CTAs per SM (default: as many as fit)
+        const int fit = std::max(1, c->grid_count / std::max(1, c->n_sm));
+        const int want = s2_env_int("S2_INGEST_SCAN_CTAS", fit);
+        g->grid_scan = c->n_sm * std::min(fit, std::max(1, want));
+    }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
@@ -855,7 +861,13 @@ static void ingest_classify(IngSource &src)
     if (!src.bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 0)) src.eligible = false;
 }
 
-static thread_local s2_ingest *tl_ingest = nullptr;
+// Up to two pipelines per calling thread (S2_INGEST_PIPELINES=2; default 1): groups of small files are independent of
+// each other and can alternate between two pipelines, so that the kernels of one group run beside the scan of the
+// previous one (S2_INGEST_SCAN_CTAS leaves them room).  Measured on the bench workload (profiles/r1n_*): no gain - copy
+// engine (46 GB/s of BGZF), inflate engine (140-160 GB/s of text) and the kernels are equally loaded at about 2.2-2.6 ms
+// per 324 MB of FASTA, so overlapping more of the third stage moves nothing.  A streamed file is a chain of dependent
+// chunks and always stays on pipeline 0.
+static thread_local s2_ingest *tl_ingest_p[2] = { nullptr, nullptr };
 // host-side time accounting (S2_INGEST_TRACE=1): where the submitting thread spends its time
 static thread_local double tr_wait = 0, tr_h2d = 0, tr_decomp = 0, tr_launch = 0;
 struct IngTraceEv { cudaEvent_t e[6]; size_t comp = 0, text = 0; };     // copy begin/end, inflate begin/end, kernels begin/end
@@ -864,14 +876,15 @@ static thread_local bool tr_on = false;
 static void tr_record(int which, cudaStream_t st) { if (tr_on && !tr_events.empty()) cudaEventRecord(tr_events.back().e[which], st); }
 static inline double ing_now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-static s2_ingest *ingest_pipeline(s2_ctx *c)
+static s2_ingest *ingest_pipeline(s2_ctx *c, int which = 0)
 {
-    if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
-    if (!tl_ingest) {
-        tl_ingest = new s2_ingest();
-        if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return nullptr; }
+    s2_ingest *&p = tl_ingest_p[which];
+    if (p && p->ctx != c) { ingest_free(p); p = nullptr; }
+    if (!p) {
+        p = new s2_ingest();
+        if (ingest_init(p, c)) { ingest_free(p); p = nullptr; return nullptr; }
     }
-    return tl_ingest;
+    return p;
 }
 
 // compressed bytes the next chunk may hold: ramps up over the first chunks of a call
@@ -947,7 +960,7 @@ static int ingest_launch_count(s2_ingest *g, s2_table *t, const S2DevBatch *dev,
 {
     s2_ctx *c = g->ctx;
     if (!t->partitioned) {
-        s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, c->grid_count, g->stream);
+        s2_launch_scan_count_dev(g->d_flat, dev, t->v, col, c->d_stats, g->grid_scan, g->stream);
         return 0;
     }
     const uint64_t n_max = g->text_cap + ING_MAXCARRY;                                     // the flat batch cannot be longer
@@ -958,7 +971,7 @@ static int ingest_launch_count(s2_ingest *g, s2_table *t, const S2DevBatch *dev,
         CK(cudaMalloc((void **)&g->part_overflow, 2 * sizeof(uint32_t)));
     }
     s2_launch_scan_count_partitioned(g->d_flat, 0, t->v, col, c->d_stats, g->part_pool, region_cap, g->part_cursor, g->part_overflow,
-                                     c->n_sm, c->grid_count, g->stream, dev);
+                                     c->n_sm, g->grid_scan, g->stream, dev);
     return 0;
 }
 
@@ -1127,12 +1140,15 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
 }
 
 // ---- count: any number of sources, small ones grouped ------------------------------------------------------
-struct IngGroup { std::vector<int> members; int result = -1; };
+struct IngGroup { std::vector<int> members; int result = -1; int pipe = 0; };
 
 static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &srcs, int col, int *rc_each, uint64_t *bases, uint64_t *lookups)
 {
-    s2_ingest *g = ingest_pipeline(c);
-    if (!g) return -1;
+    s2_ingest *P[2] = { ingest_pipeline(c, 0), nullptr };
+    if (!P[0]) return -1;
+    s2_ingest *g = P[0];                             // the pipeline of the group being assembled
+    int next_pipe = 0;
+    const bool two_pipes = s2_env_int("S2_INGEST_PIPELINES", 1) >= 2;
     uint64_t tot_bases = 0, tot_lookups = 0;
     const int n = (int)srcs.size();
     std::vector<IngGroup> groups;
@@ -1140,6 +1156,17 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
     std::vector<int> retry;                          // members of an irregular group: run alone
     g->n_results = 0;
     g->call_chunk0 = g->n_chunks;
+    auto pick_pipeline = [&]() -> int {              // a new group starts: take the pipelines in turn
+        if (two_pipes && next_pipe == 1 && !P[1]) {
+            P[1] = ingest_pipeline(c, 1);
+            if (!P[1]) return -1;
+            P[1]->n_results = 0;
+            P[1]->call_chunk0 = P[1]->n_chunks;
+        }
+        g = P[next_pipe];
+        if (two_pipes) next_pipe ^= 1;
+        return 0;
+    };
 
     // the group being assembled in the current slot
     IngSlot *s = nullptr;
@@ -1162,6 +1189,7 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
         if (push_copy()) return -1;
         ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size();
         cur.result = (int)g->n_results;
+        cur.pipe = g == P[1] ? 1 : 0;
         if (ingest_enqueue(g, t, *s, ch, cur_bgzf, cur_fasta, ING_COUNT, col, 1u, true)) return -1;
         groups.push_back(cur);
         cur = IngGroup(); ch = IngChunk(); s = nullptr;
@@ -1169,15 +1197,15 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
     };
     auto harvest = [&]() -> int {                    // verdicts of everything enqueued so far
         if (flush()) return -1;
-        if (ingest_collect(g)) return -1;
+        for (s2_ingest *q : P) if (q && ingest_collect(q)) return -1;
         for (auto &gr : groups) {
-            const IngResult &r = g->h_results[gr.result];
+            const IngResult &r = P[gr.pipe]->h_results[gr.result];
             if (!r.irregular) { tot_bases += r.bases; tot_lookups += srcs[gr.members[0]].fasta ? (r.bases > 30 * r.records ? r.bases - 30 * r.records : 0) : r.lookups; }
             else if (gr.members.size() == 1) rc_each[gr.members[0]] = 1;
             else retry.insert(retry.end(), gr.members.begin(), gr.members.end());
         }
         groups.clear();
-        g->n_results = 0;
+        for (s2_ingest *q : P) if (q) q->n_results = 0;
         return 0;
     };
     auto add_to_group = [&](int i, bool alone) -> int {       // 0 added, 1 does not fit one chunk (stream it), 2 not BGZF after all, -1 error
@@ -1190,7 +1218,7 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
             // a group closes when the next file would push it over the (ramping) chunk size; a single file may exceed the ramp
             const size_t cap = std::min(cap_max, std::max(ingest_chunk_cap(g), (size_t)size));
             if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
-            if (!s) { if (ingest_slot_begin(g, &s)) return -1; cur_fasta = src.fasta; cur_bgzf = src.bgzf; }
+            if (!s) { if (pick_pipeline() || ingest_slot_begin(g, &s)) return -1; cur_fasta = src.fasta; cur_bgzf = src.bgzf; }
             const uint8_t *h = src.mem;
             if (!src.mem) {
                 if (ingest_staging(*s, g->comp_chunk)) return -1;
@@ -1244,7 +1272,7 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
         if (rc < 0) return -1;
         if (rc == 1) streamed.push_back(i);
         if (rc == 2) rc_each[i] = 1;
-        if (g->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
+        if (P[0]->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
     }
     const double t_enq = now();
     if (harvest()) return -1;
@@ -1273,19 +1301,19 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
         const int rc = add_to_group(i, true);
         if (rc < 0) return -1;
         if (rc) rc_each[i] = 1;
-        if (g->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
+        if (P[0]->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
     }
     if (harvest()) return -1;
     // big files
     for (int i : streamed) {
         IngResult r; uint64_t done = 0;
-        const int rc = ingest_stream(g, t, srcs[i], ING_COUNT, col, 1u, &r, &done);
+        const int rc = ingest_stream(P[0], t, srcs[i], ING_COUNT, col, 1u, &r, &done);
         if (rc < 0) return -1;
         if (r.irregular) {
             // chunks before the first irregular one were counted: replay with increment -1 (same verdicts, same chunks)
             if (done > 1 || (rc == 1 && done > 0)) {
                 IngResult r2; uint64_t d2 = 0;
-                if (ingest_stream(g, t, srcs[i], ING_COUNT, col, 0xFFFFFFFFu, &r2, &d2) < 0) return -1;
+                if (ingest_stream(P[0], t, srcs[i], ING_COUNT, col, 0xFFFFFFFFu, &r2, &d2) < 0) return -1;
             }
             rc_each[i] = 1;
         } else {
@@ -1436,5 +1464,5 @@ extern "C" void s2_ingest_detect_free(s2_ingest_detect_result *r)
 
 extern "C" void s2_ingest_thread_cleanup(void)
 {
-    if (tl_ingest) { ingest_free(tl_ingest); tl_ingest = nullptr; }
+    for (auto &p : tl_ingest_p) if (p) { ingest_free(p); p = nullptr; }
 }
