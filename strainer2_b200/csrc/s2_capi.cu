@@ -518,8 +518,17 @@ extern "C" int s2_tables_allreduce(s2_table **tabs, int n, int col)
     }
     if (n_keys == 0) return 0;
     for (int i = 0; i < n; ++i) if (s2_table_counts_gather_dev(tabs[i], col, tabs[i]->scratch)) return -1;
-    std::vector<ncclComm_t> comms(n);
-    {
+    // communicators are created once per set of devices (creating them costs seconds) and kept for the life of the
+    // process: the executables call this once per counter column
+    static std::mutex comm_mu;
+    static std::vector<int> comm_devs;
+    static std::vector<ncclComm_t> comm_cache;
+    std::lock_guard<std::mutex> comm_lock(comm_mu);
+    std::vector<ncclComm_t> &comms = comm_cache;
+    if (comm_devs != devs) {
+        for (ncclComm_t cm : comm_cache) g_nccl.CommDestroy(cm);
+        comm_cache.assign(n, nullptr);
+        comm_devs.clear();
         // NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/WARN; stdout is the count table
         // of the drop-in executables, so it is parked on /dev/null while the communicators are created
         fflush(stdout);
@@ -529,7 +538,9 @@ extern "C" int s2_tables_allreduce(s2_table **tabs, int n, int col)
         fflush(stdout);
         if (saved >= 0) { dup2(saved, 1); close(saved); }
         if (nul >= 0) close(nul);
+        if (r != ncclSuccess) comm_cache.clear();
         CKNCCL(r);
+        comm_devs = devs;
     }
     CKNCCL(g_nccl.GroupStart());
     for (int i = 0; i < n; ++i) {
@@ -541,7 +552,6 @@ extern "C" int s2_tables_allreduce(s2_table **tabs, int n, int col)
         CK(cudaSetDevice(devs[i]));
         CK(cudaStreamSynchronize(tabs[i]->ctx->lanes[0].stream));
     }
-    for (int i = 0; i < n; ++i) g_nccl.CommDestroy(comms[i]);
     for (int i = 0; i < n; ++i) if (s2_table_counts_scatter_dev(tabs[i], col, tabs[i]->scratch)) return -1;
     return 0;
 }

@@ -111,6 +111,19 @@ extern "C" int s2_kmer_scrub_count_batch_main(int argc, char **argv)
     s2_table *U = s2_table_build(ctx, union_flat.data(), union_flat.size(), 4, 0.0, 0);
     if (!U) return die(s2_last_error());
     const uint64_t union_keys = s2_table_n_keys(U);
+    // S2_GPUS > 1: a replica of the union table per GPU, the input files sharded over them, one all-reduce
+    // per counter column at the end; every strain's counters are then read from replica 0 as before
+    int n_gpus = s2_env_int("S2_GPUS", 1);
+    if (n_gpus < 1) n_gpus = 1;
+    if (n_gpus > 1 && n_gpus > s2_device_count() - s2_env_int("S2_DEVICE", 0)) return die("S2_GPUS exceeds the number of visible GPUs");
+    std::vector<s2_ctx *> ctxs(1, ctx);
+    std::vector<s2_table *> tables(1, U);
+    for (int g = 1; g < n_gpus; ++g) {
+        s2_ctx *cg = s2_init(s2_env_int("S2_DEVICE", 0) + g, s2_env_u64("S2_BATCH_MB", 16) << 20, n_threads / n_gpus + 2);
+        s2_table *tg = cg ? s2_table_build(cg, union_flat.data(), union_flat.size(), 4, 0.0, 0) : nullptr;
+        if (!tg) return die(s2_last_error());
+        ctxs.push_back(cg); tables.push_back(tg);
+    }
     std::vector<uint8_t>().swap(union_flat);
     const auto t1 = std::chrono::steady_clock::now();
 
@@ -132,9 +145,15 @@ extern "C" int s2_kmer_scrub_count_batch_main(int argc, char **argv)
     }
     std::string open_error;
     uint64_t bases = 0, lookups = 0;
-    const bool ok = s2_scan_work_items(ctx, U, nullptr, work, n_threads, progress, open_error, &bases, &lookups);
+    const bool ok = s2_scan_work_items_multi(ctxs, tables, nullptr, work, std::max(n_threads, n_gpus), progress, open_error, &bases, &lookups);
     s2_scan_stats stats = {};
-    if (s2_sync(ctx, &stats)) return die(s2_last_error());
+    for (s2_ctx *cg : ctxs) {
+        s2_scan_stats sg = {};
+        if (s2_sync(cg, &sg)) return die(s2_last_error());
+        stats.hits += sg.hits; stats.valid_windows += sg.valid_windows;
+    }
+    for (int k = 1; k < 4 && n_gpus > 1 && ok && open_error.empty(); ++k)
+        if (s2_tables_allreduce(tables.data(), n_gpus, k)) return die(s2_last_error());
     if (progress) fclose(progress);
     if (!open_error.empty()) return die(open_error.c_str());
     if (!ok) return die(s2_last_error());
@@ -190,7 +209,6 @@ extern "C" int s2_kmer_scrub_count_batch_main(int argc, char **argv)
                         "kernel_ms=%.3f launches=%llu\n", strains.size(), (unsigned long long)union_keys, sec(t0, t1), sec(t1, t2), sec(t2, t3),
                 (unsigned long long)bases, (unsigned long long)lookups, (unsigned long long)stats.hits, kms, (unsigned long long)kl);
     }
-    s2_table_free(U);
-    s2_shutdown(ctx);
+    for (size_t g = 0; g < ctxs.size(); ++g) { s2_table_free(tables[g]); s2_shutdown(ctxs[g]); }
     return 0;
 }

@@ -276,9 +276,16 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     const int n_threads = std::max(s2_default_reader_threads(), n_gpus);
     std::vector<s2_ctx *> ctxs(n_gpus, nullptr);
     std::vector<s2_table *> tables(n_gpus, nullptr);
-    for (int g = 0; g < n_gpus; ++g) {
-        ctxs[g] = s2_init(s2_env_int("S2_DEVICE", 0) + g, s2_env_u64("S2_BATCH_MB", 16) << 20, (n_threads + n_gpus - 1) / n_gpus + 2);
-        if (!ctxs[g]) return fail(s2_last_error());
+    {   // the CUDA contexts come up side by side (each takes the better part of a second)
+        std::vector<std::thread> starters;
+        std::vector<std::string> errs(n_gpus);
+        for (int g = 0; g < n_gpus; ++g)
+            starters.emplace_back([&, g]() {
+                ctxs[g] = s2_init(s2_env_int("S2_DEVICE", 0) + g, s2_env_u64("S2_BATCH_MB", 16) << 20, (n_threads + n_gpus - 1) / n_gpus + 2);
+                if (!ctxs[g]) errs[g] = s2_last_error();
+            });
+        for (auto &t : starters) t.join();
+        for (int g = 0; g < n_gpus; ++g) if (!ctxs[g]) return fail(errs[g].c_str());
     }
 
     // ---- table from -r (GEN_hash_sequences_set_count_vec, default 1 / increment 1 / column 0 / 4 wide)

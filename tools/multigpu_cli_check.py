@@ -49,6 +49,12 @@ def main():
         for i in range(0, len(c0) - 31, 100):
             f.write(c0[i:i + 31] + b"\n")
     open(os.path.join(tmp, "batch.txt"), "w").write("".join("SE\t%s\n" % m for m in metas[:4]) + "PE\t%s\t%s\n" % (metas[4], metas[5]))
+    # the batch tool: three strains in one pass through a union table
+    strains = ["strain.fa"]
+    for i in (1, 2):
+        synth.write_fasta(os.path.join(tmp, "strain%d.fa" % i), synth.genome(synth.rng_for(5, i), 2_000_000, 8, n_runs=2), gz=False)
+        strains.append("strain%d.fa" % i)
+    open(os.path.join(tmp, "R.txt"), "w").write("".join(s + "\n" for s in strains))
     bin_dir = os.path.join(ROOT, "strainer2_b200", "bin")
     results = {}
     for n in sorted({1, args.gpus}):
@@ -60,9 +66,17 @@ def main():
         q = subprocess.run([os.path.join(bin_dir, "strain_detect"), "-r", "strain.fa", "-a", "inf.txt", "-B", "batch.txt", "-o", "hits%d.gz" % n], cwd=tmp, env=env,
                            capture_output=True)
         print(f"strain_detect    S2_GPUS={n}: rc={q.returncode} wall={time.time() - t:.2f}s {q.stderr.decode().strip()[-300:]}", flush=True)
-        results[n] = (p.returncode, p.stdout, q.returncode, q.stdout, gzip.open(os.path.join(tmp, "hits%d.gz" % n)).read())
+        t = time.time()
+        out_dir = os.path.join(tmp, "batch%d" % n)
+        os.makedirs(out_dir)
+        b = subprocess.run([os.path.join(bin_dir, "kmer_scrub_count_batch"), "-R", "R.txt", "-A", "A.txt", "-B", "B.txt", "-C", "R.txt", "-O", out_dir], cwd=tmp,
+                           env=env, capture_output=True)
+        print(f"kmer_scrub_count_batch S2_GPUS={n}: rc={b.returncode} wall={time.time() - t:.2f}s {b.stderr.decode().strip()[-300:]}", flush=True)
+        tables = tuple(open(os.path.join(out_dir, f), "rb").read() for f in sorted(os.listdir(out_dir)))
+        results[n] = (p.returncode, p.stdout, q.returncode, q.stdout, gzip.open(os.path.join(tmp, "hits%d.gz" % n)).read(), b.returncode, tables)
     a, b = results[1], results[args.gpus]
-    print("count tables identical:", a[:2] == b[:2], len(a[1]), "bytes; kmer_hits identical:", a[2:] == b[2:], len(a[4]), "bytes", flush=True)
+    print("count tables identical:", a[:2] == b[:2], len(a[1]), "bytes; kmer_hits identical:", a[2:5] == b[2:5], len(a[4]), "bytes;",
+          "batch tables identical:", a[5:] == b[5:], [len(x) for x in a[6]], "bytes", flush=True)
     subprocess.run(["rm", "-rf", tmp])
     return 0 if a == b else 1
 
