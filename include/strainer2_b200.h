@@ -117,8 +117,8 @@ int         s2_batch_release(s2_ctx *ctx, uint8_t *batch);               /* give
 int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
 
 /* GPU-side ingest: GEN_calculate_kmer_count() for one FILE without the host inflating or
- * parsing it.  BGZF-compressed (bgzip) strict 4-line FASTQ / strict FASTA (and, with S2_GPU_INGEST_PLAIN=1, the same
- * uncompressed) is inflated by the Blackwell hardware decompression engine and split into records by kernels; every
+ * parsing it.  BGZF-compressed (bgzip) strict 4-line FASTQ / strict FASTA (and the same uncompressed, unless
+ * S2_GPU_INGEST_PLAIN=0) is inflated by the Blackwell hardware decompression engine and split into records by kernels; every
  * chunk is proven regular on the device before its scan starts, so an irregular file is never counted.
  * Returns 0 = done, 1 = not handled (nothing was counted; use the reader + s2_batch_submit_count), -1 = error.
  * Thread safe (one ingest pipeline per calling thread; call s2_ingest_thread_cleanup() before the thread exits).

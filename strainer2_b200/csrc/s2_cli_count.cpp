@@ -6,7 +6,7 @@
 // Extra controls come from the environment so argv stays drop-in:
 //   S2_GPUS (1: GPUs to shard the input files over)  S2_DEVICE (0)  S2_THREADS (min(nproc,16) reader threads)  S2_BATCH_MB (16)  S2_LOAD (0.5)
 //   S2_GPU_INGEST (1: BGZF-compressed strict FASTQ / FASTA are inflated by the hardware engine and split into
-//                  records on the GPU; S2_GPU_INGEST_PLAIN=1 sends uncompressed files that way too)
+//                  records on the GPU, uncompressed files too unless S2_GPU_INGEST_PLAIN=0)
 //   S2_STATS=1 prints a one-line throughput summary on stderr.
 #include "../../include/strainer2_b200.h"
 #include "s2_internal.h"

@@ -7,8 +7,8 @@
 // independent raw-DEFLATE streams of up to 4 MiB each (measured here: 240-320 GB/s of text for batches of
 // 64 KB blocks).  A plain .gz file is ONE long stream and cannot be split, but BGZF (bgzip, the block-
 // gzip flavour htslib writes; still a valid multi-member gzip file for the reference's zlib) is a sequence
-// of independent <= 64 KB members whose sizes are in their headers.  For BGZF files - and, opt-in, for
-// uncompressed text - this file does on the GPU what the reader threads do for everything else:
+// of independent <= 64 KB members whose sizes are in their headers.  For BGZF files - and for uncompressed
+// text - this file does on the GPU what the reader threads do for everything else:
 //
 //   host   : hand the compressed bytes to the copy engine (from the caller's memory, or read() into pinned
 //            staging), walk the BGZF headers (no inflate)
@@ -44,6 +44,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -77,6 +78,10 @@ struct IngState {                 // lives in device memory, one per ingest pipe
     unsigned int open_kind_in;    // ... and what the previous chunk ended in (= what this chunk's first line continues)
     unsigned char tail[32];
 };
+
+static_assert(offsetof(IngState, skip) - offsetof(IngState, flat_len) == offsetof(S2DevBatch, skip) &&
+              offsetof(IngState, inc) - offsetof(IngState, flat_len) == offsetof(S2DevBatch, inc) && offsetof(S2DevBatch, n_bytes) == 0,
+              "the scan kernels read IngState::flat_len / skip / inc as an S2DevBatch");
 
 struct IngResult { ull bases, lookups, records; unsigned int irregular, inf_overflow; };
 
@@ -857,8 +862,9 @@ static void ingest_classify(IngSource &src)
     const int first = src.bgzf ? bgzf_first_text_byte(src) : (hn >= 1 ? head[0] : -1);
     src.fasta = first == '>';
     src.eligible = first == '@' || first == '>';             // neither FASTQ nor FASTA (or an ordinary .gz): host reader
-    // uncompressed text gains nothing but PCIe from this path (the host parser does GB/s per thread): opt-in only
-    if (!src.bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 0)) src.eligible = false;
+    // uncompressed text takes this path too (read() + PCIe against a host parser at about 1 GB/s per thread);
+    // S2_GPU_INGEST_PLAIN=0 keeps it on the host
+    if (!src.bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 1)) src.eligible = false;
 }
 
 // Up to two pipelines per calling thread (S2_INGEST_PIPELINES=2; default 1): groups of small files are independent of
@@ -1146,6 +1152,11 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
 {
     s2_ingest *P[2] = { ingest_pipeline(c, 0), nullptr };
     if (!P[0]) return -1;
+    // whatever way this function is left, nothing it enqueued still reads the caller's memory afterwards
+    struct Quiesce {
+        s2_ingest **P;
+        ~Quiesce() { for (int k = 0; k < 2; ++k) if (P[k]) { cudaStreamSynchronize(P[k]->copy_stream); cudaStreamSynchronize(P[k]->inflate_stream); cudaStreamSynchronize(P[k]->stream); } }
+    } quiesce{ P };
     s2_ingest *g = P[0];                             // the pipeline of the group being assembled
     int next_pipe = 0;
     const bool two_pipes = s2_env_int("S2_INGEST_PIPELINES", 1) >= 2;
@@ -1326,7 +1337,7 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
     return 0;
 }
 
-// GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed (or, opt-in, plain)
+// GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed (or uncompressed)
 // strict FASTQ / FASTA.  Returns 0 = done (counters updated, *bases / *lookups set), 1 = not handled (nothing was
 // counted: use the host reader), -1 = error.
 extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups)

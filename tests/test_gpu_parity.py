@@ -726,7 +726,7 @@ def test_executable_with_bgzf_inputs_matches_oracle(s2, golden_dir, tmp_path):
     args = ["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"]
     o = ou.oracle_cli(["count"] + args, cwd=tmp)
     assert o.returncode == 0
-    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1", "S2_GPU_INGEST_PLAIN": "1"}):
+    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1", "S2_GPU_INGEST_PLAIN": "0"}):
         p = s2.run_kmer_scrub_count(args, cwd=tmp, env=env)
         assert p.returncode == 0, p.stderr
         assert p.stdout == o.stdout, env
@@ -773,7 +773,7 @@ def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_p
     assert o.returncode == 0, o.stderr
     assert o.stdout.count(b"\n") > 500
     # S2_GPUS: batch lines are sharded over table replicas (as many as there are GPUs; one here on a single-GPU box)
-    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1", "S2_GPU_INGEST_PLAIN": "1"}, {"S2_GPUS": "4"}, {"S2_GPUS": "2", "S2_GPU_INGEST": "0"},
+    for env in ({}, {"S2_GPU_INGEST": "0"}, {"S2_THREADS": "1", "S2_GPU_INGEST_PLAIN": "0"}, {"S2_GPUS": "4"}, {"S2_GPUS": "2", "S2_GPU_INGEST": "0"},
                 {"S2_GZ_THREADS": "4"}):                                 # parallel gzip writer: same text, other compressed bytes
         out = os.path.join(tmp, "hits.gz")
         p = s2.run_strain_detect(args + ["-o", out], cwd=tmp, env=env)
