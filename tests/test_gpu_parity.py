@@ -329,6 +329,77 @@ def test_strain_detect_synthetic_matches_oracle(s2, tmp_path):
     assert p.stdout == open(os.path.join(tmp, "msg"), "rb").read()
 
 
+def test_example_pipeline_count_filter_detect_chained(s2, tmp_path):
+    """the three steps of test/example.sh chained, every step fed by the previous step's own output:
+    kmer_scrub_count | gzip --best  ->  kmer_scrub_filter -m  ->  strain_detect -B; against the same chain of the oracle
+    (C restatement for steps 1 and 3, the restated script for step 2).  Inputs mix BGZF, ordinary gzip and plain files."""
+    import gzip
+    from oracle import scrub_filter_oracle as fo
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    rng = synth.rng_for(1, 7)
+    strain = synth.genome(rng, 400_000, 5, n_runs=3)
+    synth.write_fasta(os.path.join(tmp, "strain.fna.gz"), strain)
+    clean = [np.where(c == ord("N"), ord("G"), c).astype(np.uint8) for c in strain]
+    others = synth.genome(rng, 800_000, 4)
+    # step-1 inputs: genomes (relatives of the strain among them) and metagenomes
+    A, B = [], []
+    for i in range(6):
+        g = [synth.mutate(c, 0.02 * (i + 1), rng) for c in strain[: 1 + i % 3]] + synth.genome(rng, 200_000, 2) if i < 4 else synth.genome(rng, 400_000, 3)
+        name = "g%d.fa" % i + ("" if i % 3 == 0 else ".gz")
+        if i % 3 == 1:
+            synth.write_bgzf(os.path.join(tmp, name), synth.fasta_bytes(g, 70))
+        else:
+            synth.write_fasta(os.path.join(tmp, name), g)
+        A.append(name)
+    for i in range(3):
+        reads = synth.sample_reads(rng, clean[: 1 + i] + others, 30_000, 150, sub_rate=0.01, n_rate=1e-4)
+        name = "scrub_m%d.fastq.gz" % i
+        if i == 1:
+            synth.write_reads_fastq(os.path.join(tmp, name), reads)
+        else:
+            synth.write_bgzf(os.path.join(tmp, name), synth.fastq_bytes(reads))
+        B.append(name)
+    open(os.path.join(tmp, "genomes_to_scrub.txt"), "w").write("".join(a + "\n" for a in A))
+    open(os.path.join(tmp, "metagenomes_to_scrub.txt"), "w").write("".join(b + "\n" for b in B))
+    # step-3 inputs: target metagenomes that contain the strain
+    r1 = synth.sample_reads(rng, clean + others, 40_000, 150, sub_rate=0.003, n_rate=1e-4)
+    r2 = synth.sample_reads(rng, clean + others, 40_000, 150, sub_rate=0.003, n_rate=1e-4)
+    synth.write_bgzf(os.path.join(tmp, "t_R1.fastq.gz"), synth.fastq_bytes(r1))
+    synth.write_bgzf(os.path.join(tmp, "t_R2.fastq.gz"), synth.fastq_bytes(r2))
+    synth.write_reads_fastq(os.path.join(tmp, "t_se.fastq.gz"), r1[:10_000])
+    open(os.path.join(tmp, "target_metagenomes.txt"), "w").write("PE\tt_R1.fastq.gz\tt_R2.fastq.gz\nSE\tt_se.fastq.gz\n")
+
+    step1 = ["-r", "strain.fna.gz", "-A", "genomes_to_scrub.txt", "-B", "metagenomes_to_scrub.txt"]
+    # ---- the oracle's chain
+    o1 = ou.oracle_cli(["count"] + step1, cwd=tmp)
+    assert o1.returncode == 0
+    with gzip.GzipFile(os.path.join(tmp, "o.scrub_kmer_counts.gz"), "wb", compresslevel=9) as f:
+        f.write(o1.stdout)
+    rc, o2, _ = fo.run(["-s", "o.scrub_kmer_counts.gz", "-m", "0.02"], cwd=tmp)
+    assert rc == 0
+    with gzip.GzipFile(os.path.join(tmp, "o.scrubbed_kmers.gz"), "wb", compresslevel=9) as f:
+        f.write(o2)
+    o3 = ou.oracle_cli(["detect", "-r", "strain.fna.gz", "-a", "o.scrubbed_kmers.gz", "-B", "target_metagenomes.txt", "-m", os.path.join(tmp, "o.msg")], cwd=tmp)
+    assert o3.returncode == 0
+    # ---- the drop-ins' chain
+    p1 = s2.run_kmer_scrub_count(step1 + ["-p", "strain.progress"], cwd=tmp)
+    assert p1.returncode == 0, p1.stderr
+    assert p1.stdout == o1.stdout
+    with gzip.GzipFile(os.path.join(tmp, "p.scrub_kmer_counts.gz"), "wb", compresslevel=9) as f:
+        f.write(p1.stdout)
+    p2 = s2.run_kmer_scrub_filter(["-s", "p.scrub_kmer_counts.gz", "-m", "0.02"], cwd=tmp)
+    assert p2.returncode == 0, p2.stderr
+    assert p2.stdout == o2 and p2.stdout.count(b"\n") > 5000
+    with gzip.GzipFile(os.path.join(tmp, "p.scrubbed_kmers.gz"), "wb", compresslevel=9) as f:
+        f.write(p2.stdout)
+    p3 = s2.run_strain_detect(["-r", "strain.fna.gz", "-a", "p.scrubbed_kmers.gz", "-B", "target_metagenomes.txt", "-o", "p.kmer_hits.gz"], cwd=tmp)
+    assert p3.returncode == 0, p3.stderr
+    hits = ou.gunzip(os.path.join(tmp, "p.kmer_hits.gz"))
+    assert hits == o3.stdout and hits.count(b"\n") > 2000
+    assert p3.stdout == open(os.path.join(tmp, "o.msg"), "rb").read()
+
+
 def test_iupac_bytes_are_hashed_as_strings_like_the_reference(s2, golden_dir, tmp_path):
     """windows with bytes outside ACGTN go through the host string path; output bytes equal the
     reference's (rows containing R/Y/K/M/-/E ..., merged into the replayed row order)"""
