@@ -13,11 +13,15 @@
 #include "../../include/strainer2_b200.h"
 #include "s2_internal.h"
 
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <charconv>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -169,20 +173,51 @@ int parse_args(int argc, char **argv, Options &o)
     return 0;
 }
 
-// whole (gzip) file -> text; universal newlines like Python's text mode
-bool read_gz(const std::string &path, std::string &text)
-{
-    gzFile f = gzopen(path.c_str(), "rb");
-    if (!f) return false;
-    gzbuffer(f, 1 << 20);
-    text.clear();
-    std::vector<char> buf(4 << 20);
-    int got;
-    while ((got = gzread(f, buf.data(), (unsigned)buf.size())) > 0) text.append(buf.data(), (size_t)got);
-    const bool ok = got == 0;
-    gzclose(f);
-    return ok;
-}
+// the (gzip) file arrives in pieces from a thread of its own: zlib inflates the next 8 MB while the previous ones are parsed
+struct GzPieces {
+    gzFile f = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::string> q;
+    bool done = false, ok = true, quit = false;
+    bool open(const std::string &path)
+    {
+        f = gzopen(path.c_str(), "rb");
+        if (!f) return false;
+        gzbuffer(f, 1 << 20);
+        th = std::thread([this]() {
+            for (;;) {
+                std::string buf;
+                buf.resize(8u << 20);
+                const int got = gzread(f, &buf[0], (unsigned)buf.size());
+                std::unique_lock<std::mutex> g(mu);
+                if (got <= 0) { ok = got == 0; done = true; cv.notify_all(); return; }
+                buf.resize((size_t)got);
+                cv.wait(g, [this]() { return q.size() < 3 || quit; });
+                if (quit) { done = true; cv.notify_all(); return; }
+                q.push_back(std::move(buf));
+                cv.notify_all();
+            }
+        });
+        return true;
+    }
+    bool next(std::string &out)                        // false at the end of the file
+    {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [this]() { return !q.empty() || done; });
+        if (q.empty()) return false;
+        out = std::move(q.front());
+        q.pop_front();
+        cv.notify_all();
+        return true;
+    }
+    ~GzPieces()
+    {
+        if (th.joinable()) { { std::lock_guard<std::mutex> g(mu); quit = true; } cv.notify_all(); th.join(); }
+        if (f) gzclose(f);
+    }
+};
 
 bool parse_int(const char *s, const char *e, long long *out)
 {
@@ -267,13 +302,11 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
         if (fi > 1) { prev_ids = strain_ids; prev_ref_of = ref_of; }              // :163 (sic): only from the third file on
         strain_ids.clear();
         all_kmers = 0;
-        const double t_a = now();
-        if (!read_gz(files[fi], text)) return fail_traceback("FileNotFoundError: [Errno 2] No such file or directory: '" + files[fi] + "'");
-        const double t_b = now();
-        t_inflate += t_b - t_a;
-        const char *p = text.data(), *end = p + text.size();
-        {                                                                         // sizes are known roughly: no reallocation / rehash while parsing
-            const uint64_t est = text.size() / 36 + 1024;
+        GzPieces pieces;
+        if (!pieces.open(files[fi])) return fail_traceback("FileNotFoundError: [Errno 2] No such file or directory: '" + files[fi] + "'");
+        {                                                                         // sizes are known roughly: few reallocations / rehashes while parsing
+            struct stat sb;
+            const uint64_t est = (stat(files[fi].c_str(), &sb) == 0 ? (uint64_t)sb.st_size * 3 : (64u << 20)) / 36 + 1024;     // count tables compress about 3 : 1
             index.reserve(index.used + est);
             for (auto *v : { &pan_sum, &meta_sum }) v->reserve(v->size() + est);
             for (auto *v : { &in_pan, &in_meta, &in_drug }) v->reserve(v->size() + est);
@@ -281,7 +314,9 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
             name_pool.reserve(name_pool.size() + est * 31);
             strain_ids.reserve(est);
         }
-        const bool has_cr = memchr(p, '\r', text.size()) != nullptr;             // universal newlines only cost something when there is a CR
+        // complete lines [p, end) -> the dicts; returns the last line of a Python traceback, or nothing
+        auto parse_lines = [&](const char *p, const char *end) -> std::string {
+        const bool has_cr = memchr(p, '\r', (size_t)(end - p)) != nullptr;             // universal newlines only cost something when there is a CR
         struct Line { const char *b, *e; uint64_t code; };
         Line block[64];
         while (p < end) {
@@ -308,11 +343,11 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
                 f[nf++] = q;
                 for (; q < line_end; ++q) if (*q == '\t') { if (nf < 6) f[nf] = q + 1; ++nf; }
                 const int n_fields = nf;
-                if (n_fields < 4) return fail_traceback("IndexError: list index out of range");
+                if (n_fields < 4) return std::string("IndexError: list index out of range");
                 auto field_end = [&](int k) { return k + 1 < n_fields && k + 1 < 6 ? f[k + 1] - 1 : line_end; };
                 long long c1, c2, c3, c4 = 0;
                 if (!parse_int(f[1], field_end(1), &c1) || !parse_int(f[2], field_end(2), &c2) || !parse_int(f[3], field_end(3), &c3))
-                    return fail_traceback("ValueError: invalid literal for int() with base 10");
+                    return std::string("ValueError: invalid literal for int() with base 10");
                 bool is_new;
                 const size_t klen = (size_t)(field_end(0) - f[0]);
                 const uint32_t id = index.get(block[li].code, f[0], klen, &is_new);
@@ -328,11 +363,34 @@ extern "C" int s2_kmer_scrub_filter_main(int argc, char **argv)
                 if (c3 > 0) { meta_sum[id] += (uint64_t)c3; in_meta[id] = 1; }
                 if (n_fields == 5) {
                     drug_filter = true;
-                    if (!parse_int(f[4], field_end(4), &c4)) return fail_traceback("ValueError: invalid literal for int() with base 10");
+                    if (!parse_int(f[4], field_end(4), &c4)) return std::string("ValueError: invalid literal for int() with base 10");
                     if (c4 > 0) in_drug[id] = 1;                                 // :194 adds content[3]: only membership is used
                 }
             }
         }
+            return std::string();
+        };
+        // a piece is parsed up to its last line break; the rest waits for the next piece (a CR at the very end may be half of a CR LF)
+        std::string piece;
+        text.clear();
+        for (;;) {
+            const double t_a = now();
+            const bool more = pieces.next(piece);
+            const double t_b = now();
+            t_inflate += t_b - t_a;                                               // time spent WAITING for the inflating thread
+            if (more) text += piece;
+            size_t cut = text.size();
+            if (more) {
+                while (cut > 0 && text[cut - 1] != '\n' && !(text[cut - 1] == '\r' && cut < text.size())) --cut;
+            }
+            const std::string err = parse_lines(text.data(), text.data() + cut);
+            if (!err.empty()) return fail_traceback(err);
+            text.erase(0, cut);
+            t_parse += now() - t_b;
+            if (!more) break;
+        }
+        if (!pieces.ok) return fail_traceback("EOFError: Compressed file ended before the end-of-stream marker was reached");
+        const double t_b = now();
         t_parse += now() - t_b;
         if (fi > 1) {                                                             // dict equality with the previous file's strain dict
             bool same = prev_ids.size() == strain_ids.size();

@@ -84,6 +84,10 @@ def main():
     # keys that are not plain ACGT 31-mers (IUPAC rows of SURVEY D6, odd lengths): still just dict keys
     odd = [k[:10] + "R" + k[11:] for k in keys[:40]] + [k[:20] for k in keys[40:60]] + keys[60:400]
     write_gz("t_odd_keys.tsv.gz", table(r, odd))
+    # DOS and old-Mac line ends: the script reads in text mode (universal newlines)
+    small = table(r, keys[:600])
+    write_gz("t_crlf.tsv.gz", small.replace("\n", "\r\n"))
+    write_gz("t_cr.tsv.gz", small.replace("\n", "\r"))
 
     cases = {
         "plain_default": ["-s", "t_plain.tsv.gz"],
@@ -112,6 +116,9 @@ def main():
         "multi_reordered": ["-l", "list_reordered.txt", "-m", "0.1"],
         "dups": ["-s", "t_dups.tsv.gz", "-m", "0.1"],
         "odd_keys": ["-s", "t_odd_keys.tsv.gz", "-m", "0.1"],
+        "crlf": ["-s", "t_crlf.tsv.gz", "-m", "0.1"],
+        "cr_only": ["-s", "t_cr.tsv.gz", "-m", "0.1"],
+        "crlf_independent": ["-s", "t_crlf.tsv.gz", "-m", "0.5", "-i"],
         "no_input": [],
         "both_inputs": ["-s", "t_tiny.tsv.gz", "-l", "list2.txt", "-m", "0.3"],
     }
