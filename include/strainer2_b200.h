@@ -136,6 +136,15 @@ int         s2_ingest_count_mem_batch(s2_ctx *ctx, s2_table *t, const void *cons
                                       int *rc_each, uint64_t *bases, uint64_t *lookups);
 int         s2_ingest_count_files(s2_ctx *ctx, s2_table *t, const char *const *paths, int n, int col,
                                   int *rc_each, uint64_t *bases, uint64_t *lookups);
+/* asynchronous form of the two calls above: submit returns as soon as every file that fits a chunk is enqueued (file
+ * images must stay valid until the wait), wait blocks until the job's files are counted or handed back, fills rc_each /
+ * bases / lookups as above and releases the job.  Submitting the next job before waiting for the previous one hides the
+ * fill and drain of the copy -> inflate -> kernels pipeline.  A job is waited for on the thread that submitted it, jobs
+ * of one thread in the order they were submitted.  submit returns NULL on error. */
+typedef struct s2_ingest_job s2_ingest_job;
+s2_ingest_job *s2_ingest_submit_mem_batch(s2_ctx *ctx, s2_table *t, const void *const *images, const uint64_t *n_bytes, int n, int col);
+s2_ingest_job *s2_ingest_submit_files(s2_ctx *ctx, s2_table *t, const char *const *paths, int n, int col);
+int         s2_ingest_wait(s2_ingest_job *job, int *rc_each, uint64_t *bases, uint64_t *lookups);
 /* the detect form: pass 1 of quantify_hits_PE for every read of one file.  len / hits / inf are per record in
  * file order (ALL records, also those shorter than 31, which the pairing loop needs); inf_* list the informative
  * windows sorted by (record, offset) with their canonical k-mer.  Arrays are malloc()ed by the call. */

@@ -69,6 +69,9 @@ SIGNATURES = {
                                             C.POINTER(C.c_int), c_u64p, c_u64p]),
     "s2_ingest_count_files": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int,
                                         C.POINTER(C.c_int), c_u64p, c_u64p]),
+    "s2_ingest_submit_mem_batch": (C.c_void_p, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), c_u64p, C.c_int, C.c_int]),
+    "s2_ingest_submit_files": (C.c_void_p, [C.c_void_p, C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int]),
+    "s2_ingest_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), c_u64p, c_u64p]),
     "s2_ingest_detect_file": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]),
     "s2_ingest_detect_free": (None, [C.c_void_p]),
     "s2_ingest_thread_cleanup": (None, []),

@@ -140,6 +140,25 @@ class Context:
             raise S2Error("s2_ingest_count_mem_batch: " + _lib.last_error())
         return list(R), b.value, l.value
 
+    def ingest_submit_mem_batch(self, table, ptrs, sizes, col):
+        """asynchronous form: -> job handle for ingest_wait(); the images must stay valid until then"""
+        n = len(ptrs)
+        P = (C.c_void_p * n)(*ptrs)
+        S = (C.c_uint64 * n)(*sizes)
+        h = lib.s2_ingest_submit_mem_batch(self.h, table.h, P, S, n, col)
+        if not h:
+            raise S2Error("s2_ingest_submit_mem_batch: " + _lib.last_error())
+        return (h, n)
+
+    def ingest_wait(self, job):
+        """-> (rc_each, bases, lookups) of a submitted job"""
+        h, n = job
+        R = (C.c_int * n)()
+        b, l = C.c_uint64(), C.c_uint64()
+        if lib.s2_ingest_wait(h, R, C.byref(b), C.byref(l)) < 0:
+            raise S2Error("s2_ingest_wait: " + _lib.last_error())
+        return list(R), b.value, l.value
+
     def ingest_count_files(self, table, paths, col):
         """many files in one call, small files grouped -> (rc_each, bases, lookups)"""
         n = len(paths)

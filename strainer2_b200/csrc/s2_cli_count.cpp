@@ -157,6 +157,49 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
 
     auto reader = [&](int tid) {
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
+        // a run handed to the GPU ingest stays pending while the next one is taken and submitted (the ingest pipeline never
+        // drains between runs); whatever the ingest hands back is then read by the host parser below
+        struct Pending { std::vector<Taken> run; int col = 0; s2_ingest_job *job = nullptr; };
+        Pending pending;
+        auto host_read = [&](std::vector<Taken> &run, const std::vector<int> &handled, int col) {
+            for (size_t k = 0; k < run.size(); ++k) {
+                s2_reader *r = run[k].r;
+                if (handled[k] == 0 || w.failed) { s2_reader_close(r); continue; }
+                const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
+                while ((l = s2_reader_next(r, &seq)) >= 0) {
+                    bases += (uint64_t)l;
+                    if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
+                    if (!w.append(seq, (uint64_t)l, col)) {
+                        std::lock_guard<std::mutex> g(mu);
+                        if (open_error.empty()) open_error = s2_last_error();
+                        stop.store(true);
+                        break;
+                    }
+                    if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
+                }
+                s2_reader_close(r);
+                total_bases += bases; total_lookups += lookups;
+            }
+        };
+        auto finish_pending = [&]() -> bool {
+            if (!pending.job) return true;
+            std::vector<int> handled(pending.run.size(), 1);
+            uint64_t gb = 0, gl = 0;
+            const int rc = s2_ingest_wait(pending.job, handled.data(), &gb, &gl);
+            pending.job = nullptr;
+            if (rc < 0) {
+                std::lock_guard<std::mutex> g(mu);
+                if (open_error.empty()) open_error = s2_last_error();
+                stop.store(true);
+                for (auto &x : pending.run) s2_reader_close(x.r);
+                pending.run.clear();
+                return false;
+            }
+            total_bases += gb; total_lookups += gl;
+            host_read(pending.run, handled, pending.col);
+            pending.run.clear();
+            return !w.failed;
+        };
         for (;;) {
             std::vector<Taken> run;
             int col = 0;
@@ -185,41 +228,26 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                 }
             }
             if (run.empty()) break;
-            // BGZF / plain strict FASTQ + FASTA: hardware inflate + record splitting on the GPU, nothing parsed here
-            std::vector<int> handled(run.size(), 1);
             if (gpu_ingest && !exotic) {
+                // BGZF / plain strict FASTQ + FASTA: hardware inflate + record splitting on the GPU, nothing parsed here
                 std::vector<const char *> paths;
                 for (auto &x : run) paths.push_back(x.path.c_str());
-                uint64_t gb = 0, gl = 0;
-                if (s2_ingest_count_files(w.ctx, w.table, paths.data(), (int)paths.size(), col, handled.data(), &gb, &gl) < 0) {
+                s2_ingest_job *job = s2_ingest_submit_files(w.ctx, w.table, paths.data(), (int)paths.size(), col);
+                if (!job) {
                     std::lock_guard<std::mutex> g(mu);
                     if (open_error.empty()) open_error = s2_last_error();
                     stop.store(true);
                     for (auto &x : run) s2_reader_close(x.r);
                     break;
                 }
-                total_bases += gb; total_lookups += gl;
-            }
-            for (size_t k = 0; k < run.size(); ++k) {
-                s2_reader *r = run[k].r;
-                if (handled[k] == 0 || w.failed) { s2_reader_close(r); continue; }
-                const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
-                while ((l = s2_reader_next(r, &seq)) >= 0) {
-                    bases += (uint64_t)l;
-                    if (l >= S2_K) lookups += (uint64_t)l - (S2_K - 1);
-                    if (!w.append(seq, (uint64_t)l, col)) {
-                        std::lock_guard<std::mutex> g(mu);
-                        if (open_error.empty()) open_error = s2_last_error();
-                        stop.store(true);
-                        break;
-                    }
-                    if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
-                }
-                s2_reader_close(r);
-                total_bases += bases; total_lookups += lookups;
+                if (!finish_pending()) { pending.run.swap(run); pending.col = col; pending.job = job; break; }
+                pending.run.swap(run); pending.col = col; pending.job = job;
+            } else {
+                host_read(run, std::vector<int>(run.size(), 1), col);
             }
             if (w.failed) break;
         }
+        finish_pending();
         if (!w.flush()) {
             std::lock_guard<std::mutex> g(mu);
             if (open_error.empty()) open_error = s2_last_error();

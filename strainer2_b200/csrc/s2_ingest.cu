@@ -681,7 +681,8 @@ struct s2_ingest {
     unsigned *d_tickets = nullptr;       // last-block election of the three fused kernels
     uint64_t *part_pool = nullptr; unsigned long long *part_cursor = nullptr; uint32_t *part_overflow = nullptr;     // two-phase scan scratch
     IngState *d_state = nullptr;
-    IngResult *d_results = nullptr, *h_results = nullptr; unsigned n_results = 0;
+    IngResult *h_results = nullptr, *d_results = nullptr;      // ring of verdicts in mapped pinned memory (host pointer, device alias)
+    uint64_t res_seq = 0;                // verdicts handed out so far; slot = res_seq % ING_MAX_RESULTS
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
     int grid_scan = 0;                   // CTAs of the count scan launched from this pipeline
@@ -709,7 +710,7 @@ static void ingest_free(s2_ingest *g)
     cudaFree(g->d_flat);
     cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end); cudaFree(g->d_masks); cudaFree(g->d_tickets);
     cudaFree(g->part_pool); cudaFree(g->part_cursor); cudaFree(g->part_overflow);
-    cudaFree(g->d_state); cudaFree(g->d_results); cudaFreeHost(g->h_results);
+    cudaFree(g->d_state); cudaFreeHost(g->h_results);
     cudaFree(g->d_hits_c); cudaFree(g->d_inf_c); cudaFree(g->d_rec_off); cudaFree(g->d_pos_c); cudaFree(g->d_cnt_c); cudaFree(g->d_fcnt);
     cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all); cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);
     cudaGetLastError();
@@ -754,8 +755,8 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     CK(cudaMemset(g->d_state, 0, sizeof(IngState)));                   // afterwards every finished file leaves a clean state behind
     CK(cudaMalloc((void **)&g->d_tickets, 4 * sizeof(unsigned)));
     CK(cudaMemset(g->d_tickets, 0, 4 * sizeof(unsigned)));
-    CK(cudaMalloc((void **)&g->d_results, ING_MAX_RESULTS * sizeof(IngResult)));
-    CK(cudaHostAlloc((void **)&g->h_results, ING_MAX_RESULTS * sizeof(IngResult), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&g->h_results, ING_MAX_RESULTS * sizeof(IngResult), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&g->d_results, g->h_results, 0));          // the end-of-chunk kernel writes the verdict straight to the host
     // the decompression engine is reached through the driver; no link-time dependency on libcuda
     cudaDriverEntryPointQueryResult q;
     void *fn = nullptr, *fa = nullptr;
@@ -867,13 +868,11 @@ static void ingest_classify(IngSource &src)
     if (!src.bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 1)) src.eligible = false;
 }
 
-// Up to two pipelines per calling thread (S2_INGEST_PIPELINES=2; default 1): groups of small files are independent of
-// each other and can alternate between two pipelines, so that the kernels of one group run beside the scan of the
-// previous one (S2_INGEST_SCAN_CTAS leaves them room).  Measured on the bench workload (profiles/r1n_*): no gain - copy
-// engine (46 GB/s of BGZF), inflate engine (140-160 GB/s of text) and the kernels are equally loaded at about 2.2-2.6 ms
-// per 324 MB of FASTA, so overlapping more of the third stage moves nothing.  A streamed file is a chain of dependent
-// chunks and always stays on pipeline 0.
-static thread_local s2_ingest *tl_ingest_p[2] = { nullptr, nullptr };
+// One pipeline per calling thread.  (A second pipeline per thread, groups alternating between the two so that the kernels
+// of one group run beside the scan of the previous one, was measured on the bench workload - profiles/r1n_ingest_two_
+// pipelines.txt - and gains nothing: copy engine (46 GB/s of BGZF), inflate engine (140-160 GB/s of text) and the kernels
+// are equally loaded at about 2.2-2.6 ms per 324 MB of FASTA, so overlapping more of the third stage moves nothing.)
+static thread_local s2_ingest *tl_ingest_p[1] = { nullptr };
 // host-side time accounting (S2_INGEST_TRACE=1): where the submitting thread spends its time
 static thread_local double tr_wait = 0, tr_h2d = 0, tr_decomp = 0, tr_launch = 0;
 struct IngTraceEv { cudaEvent_t e[6]; size_t comp = 0, text = 0; };     // copy begin/end, inflate begin/end, kernels begin/end
@@ -1023,7 +1022,7 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     const bool detect = mode == ING_DETECT;
     ing_index_count<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_masks, a, g->max_lines, g->d_tickets + 0);
     ing_index_scatter<<<n_blocks, ING_THREADS, 0, st>>>(g->d_masks, g->d_block_nl, g->d_line_end, g->max_lines);
-    IngResult *res = want_result ? g->d_results + g->n_results : nullptr;
+    IngResult *res = want_result ? g->d_results + g->res_seq % ING_MAX_RESULTS : nullptr;
     const S2DevBatch *dev = reinterpret_cast<const S2DevBatch *>(&g->d_state->flat_len);
     if (fasta) {
         ing_fasta_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a, g->d_tickets + 1);
@@ -1054,18 +1053,10 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     }
     tr_record(5, st);
     CK(cudaEventRecord(s.consumed, st));                   // the slot (compressed bytes, decompress list, meta, text) may be reused
-    if (want_result) ++g->n_results;
+    if (want_result) ++g->res_seq;
     CK(cudaGetLastError());
     tr_launch += ing_now() - t_launch;
     ++g->n_chunks;
-    return 0;
-}
-
-// all verdicts enqueued so far -> h_results[0 .. n_results); the pipeline is idle afterwards
-static int ingest_collect(s2_ingest *g)
-{
-    if (g->n_results) CK(cudaMemcpyAsync(g->h_results, g->d_results, g->n_results * sizeof(IngResult), cudaMemcpyDeviceToHost, g->stream));
-    CK(cudaStreamSynchronize(g->stream));
     return 0;
 }
 
@@ -1074,7 +1065,6 @@ static int ingest_collect(s2_ingest *g)
 // says irregular), -1 error.  Synchronous at the end.  *chunks_done: chunks that went to the device.
 static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mode, int col, unsigned inc, IngResult *res, uint64_t *chunks_done)
 {
-    g->n_results = 0;
     g->call_chunk0 = g->n_chunks;
     off_t file_off = 0;
     bool first = true, eof = false, broken = false;
@@ -1134,59 +1124,53 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
     if (broken) {
         CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), g->stream));        // no last chunk came to tidy up
         CK(cudaStreamSynchronize(g->stream));
-        g->n_results = 0;
         memset(res, 0, sizeof *res);
         res->irregular = 1;
         return 1;
     }
-    if (ingest_collect(g)) return -1;
-    *res = g->h_results[0];
-    g->n_results = 0;
+    CK(cudaStreamSynchronize(g->stream));
+    *res = g->h_results[(g->res_seq - 1) % ING_MAX_RESULTS];        // the last chunk's verdict
     return 0;
 }
 
 // ---- count: any number of sources, small ones grouped ------------------------------------------------------
-struct IngGroup { std::vector<int> members; int result = -1; int pipe = 0; };
+// A job is one call's worth of sources.  submit() classifies them, packs the small ones into groups and enqueues the
+// groups (asynchronous: it returns while the device works); finish() waits for the job's last group, reads the
+// verdicts, runs the members of irregular groups one by one and streams the files that are too big for a chunk.
+// Several jobs of one thread may be in flight: the next one is submitted before the previous one is finished, which
+// hides the pipeline's fill and drain.
+struct IngGroup { std::vector<int> members; uint64_t result = 0; };
 
-static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &srcs, int col, int *rc_each, uint64_t *bases, uint64_t *lookups)
-{
-    s2_ingest *P[2] = { ingest_pipeline(c, 0), nullptr };
-    if (!P[0]) return -1;
-    // whatever way this function is left, nothing it enqueued still reads the caller's memory afterwards
-    struct Quiesce {
-        s2_ingest **P;
-        ~Quiesce() { for (int k = 0; k < 2; ++k) if (P[k]) { cudaStreamSynchronize(P[k]->copy_stream); cudaStreamSynchronize(P[k]->inflate_stream); cudaStreamSynchronize(P[k]->stream); } }
-    } quiesce{ P };
-    s2_ingest *g = P[0];                             // the pipeline of the group being assembled
-    int next_pipe = 0;
-    const bool two_pipes = s2_env_int("S2_INGEST_PIPELINES", 1) >= 2;
+struct s2_ingest_job {
+    s2_ctx *c = nullptr; s2_table *t = nullptr; s2_ingest *g = nullptr;
+    int col = 0;
+    std::vector<IngSource> srcs;
+    std::vector<int> own_fds;                       // opened by the job (file form): closed when the job ends
+    std::vector<int> rc;                            // per source: 0 handled / 1 not handled
+    std::vector<IngGroup> groups;                   // enqueued, verdict not read yet
+    std::vector<int> streamed, retry;
     uint64_t tot_bases = 0, tot_lookups = 0;
-    const int n = (int)srcs.size();
-    std::vector<IngGroup> groups;
-    std::vector<int> streamed;                       // too big for one chunk
-    std::vector<int> retry;                          // members of an irregular group: run alone
-    g->n_results = 0;
-    g->call_chunk0 = g->n_chunks;
-    auto pick_pipeline = [&]() -> int {              // a new group starts: take the pipelines in turn
-        if (two_pipes && next_pipe == 1 && !P[1]) {
-            P[1] = ingest_pipeline(c, 1);
-            if (!P[1]) return -1;
-            P[1]->n_results = 0;
-            P[1]->call_chunk0 = P[1]->n_chunks;
-        }
-        g = P[next_pipe];
-        if (two_pipes) next_pipe ^= 1;
-        return 0;
-    };
-
+    cudaEvent_t done = nullptr;                     // after the last chunk submit() enqueued
     // the group being assembled in the current slot
     IngSlot *s = nullptr;
     IngGroup cur;
     IngChunk ch;
     bool cur_fasta = false, cur_bgzf = false;
-    // host -> device copies of neighbouring sources (consecutive in memory, as in the staging buffer or a caller's arena) are merged
-    struct { const uint8_t *h = nullptr; size_t d_off = 0, len = 0; } pend;
-    auto push_copy = [&]() -> int {
+    struct { const uint8_t *h = nullptr; size_t d_off = 0, len = 0; } pend;     // host -> device copies of neighbouring sources are merged
+
+    ~s2_ingest_job()
+    {
+        if (done) cudaEventDestroy(done);
+        for (int fd : own_fds) close(fd);
+    }
+    void add_totals(const IngResult &r, bool fasta)
+    {
+        tot_bases += r.bases;
+        // FASTA records are not measured one by one on the device: every record is assumed to have at least one window
+        tot_lookups += fasta ? (r.bases > 30 * r.records ? r.bases - 30 * r.records : 0) : r.lookups;
+    }
+    int push_copy()
+    {
         if (pend.len) {
             const double t_cp = ing_now();
             CK(cudaMemcpyAsync(s->d_comp + pend.d_off, pend.h, pend.len, cudaMemcpyHostToDevice, g->copy_stream));
@@ -1194,32 +1178,39 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
         }
         pend.len = 0;
         return 0;
-    };
-    auto flush = [&]() -> int {
+    }
+    int flush()
+    {
         if (!s || cur.members.empty()) return 0;
         if (push_copy()) return -1;
         ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size();
-        cur.result = (int)g->n_results;
-        cur.pipe = g == P[1] ? 1 : 0;
+        cur.result = g->res_seq;
         if (ingest_enqueue(g, t, *s, ch, cur_bgzf, cur_fasta, ING_COUNT, col, 1u, true)) return -1;
         groups.push_back(cur);
         cur = IngGroup(); ch = IngChunk(); s = nullptr;
         return 0;
-    };
-    auto harvest = [&]() -> int {                    // verdicts of everything enqueued so far
+    }
+    // verdicts of everything enqueued so far (the whole pipeline is idle afterwards)
+    int harvest()
+    {
         if (flush()) return -1;
-        for (s2_ingest *q : P) if (q && ingest_collect(q)) return -1;
+        CK(cudaStreamSynchronize(g->stream));
+        return read_verdicts();
+    }
+    int read_verdicts()
+    {
         for (auto &gr : groups) {
-            const IngResult &r = P[gr.pipe]->h_results[gr.result];
-            if (!r.irregular) { tot_bases += r.bases; tot_lookups += srcs[gr.members[0]].fasta ? (r.bases > 30 * r.records ? r.bases - 30 * r.records : 0) : r.lookups; }
-            else if (gr.members.size() == 1) rc_each[gr.members[0]] = 1;
+            const IngResult r = g->h_results[gr.result % ING_MAX_RESULTS];
+            if (!r.irregular) add_totals(r, srcs[gr.members[0]].fasta);
+            else if (gr.members.size() == 1) rc[gr.members[0]] = 1;
             else retry.insert(retry.end(), gr.members.begin(), gr.members.end());
         }
         groups.clear();
-        for (s2_ingest *q : P) if (q) q->n_results = 0;
         return 0;
-    };
-    auto add_to_group = [&](int i, bool alone) -> int {       // 0 added, 1 does not fit one chunk (stream it), 2 not BGZF after all, -1 error
+    }
+    // 0 added, 1 does not fit one chunk (stream it), 2 not BGZF after all, -1 error
+    int add_to_group(int i, bool alone)
+    {
         IngSource &src = srcs[i];
         const ssize_t size = src.size();
         if (size < 0) return 2;
@@ -1229,7 +1220,12 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
             // a group closes when the next file would push it over the (ramping) chunk size; a single file may exceed the ramp
             const size_t cap = std::min(cap_max, std::max(ingest_chunk_cap(g), (size_t)size));
             if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
-            if (!s) { if (pick_pipeline() || ingest_slot_begin(g, &s)) return -1; cur_fasta = src.fasta; cur_bgzf = src.bgzf; }
+            if (!s) {
+                // the verdict ring must not wrap onto verdicts this job has not read yet
+                if (!groups.empty() && g->res_seq - groups.front().result + 4 >= ING_MAX_RESULTS && harvest()) return -1;
+                if (ingest_slot_begin(g, &s)) return -1;
+                cur_fasta = src.fasta; cur_bgzf = src.bgzf;
+            }
             const uint8_t *h = src.mem;
             if (!src.mem) {
                 if (ingest_staging(*s, g->comp_chunk)) return -1;
@@ -1262,79 +1258,153 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
             return 0;
         }
         return 1;
-    };
+    }
+};
 
+// whatever way a job fails, nothing it enqueued may still read the caller's memory afterwards
+static void ingest_quiesce(s2_ingest *g)
+{
+    if (!g) return;
+    cudaStreamSynchronize(g->copy_stream); cudaStreamSynchronize(g->inflate_stream); cudaStreamSynchronize(g->stream);
+    cudaGetLastError();
+}
+
+static int ingest_job_submit(s2_ingest_job *job)
+{
+    s2_ingest *g = job->g;
+    const int n = (int)job->srcs.size();
+    // small first chunks only when the pipeline is idle: behind a job that is still running there is nothing to start early
+    const bool idle = cudaStreamQuery(g->stream) == cudaSuccess;
+    cudaGetLastError();
+    g->call_chunk0 = idle || g->n_chunks < 6 ? g->n_chunks : g->n_chunks - 6;
     const bool trace = s2_env_int("S2_INGEST_TRACE", 0) != 0;
-    auto now = []() { return ing_now(); };
     tr_wait = tr_h2d = tr_decomp = tr_launch = 0;
     tr_on = trace && s2_env_int("S2_INGEST_TRACE", 0) >= 2;
     double us_classify = 0, us_group = 0;
-    const double t_begin = now();
+    const double t_begin = ing_now();
     for (int i = 0; i < n; ++i) {
-        const double ta = now();
-        ingest_classify(srcs[i]);                    // one file at a time, so that the first group is on its way while the rest is looked at
-        if (srcs[i].bgzf && !g->hw_deflate) srcs[i].eligible = false;
-        rc_each[i] = srcs[i].eligible ? 0 : 1;
-        const double tb = now();
+        const double ta = ing_now();
+        ingest_classify(job->srcs[i]);               // one file at a time, so that the first group is on its way while the rest is looked at
+        if (job->srcs[i].bgzf && !g->hw_deflate) job->srcs[i].eligible = false;
+        job->rc[i] = job->srcs[i].eligible ? 0 : 1;
+        const double tb = ing_now();
         us_classify += tb - ta;
-        if (!srcs[i].eligible) continue;
-        const int rc = add_to_group(i, false);
-        us_group += now() - tb;
+        if (!job->srcs[i].eligible) continue;
+        const int rc = job->add_to_group(i, false);
+        us_group += ing_now() - tb;
         if (rc < 0) return -1;
-        if (rc == 1) streamed.push_back(i);
-        if (rc == 2) rc_each[i] = 1;
-        if (P[0]->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
+        if (rc == 1) job->streamed.push_back(i);
+        if (rc == 2) job->rc[i] = 1;
     }
-    const double t_enq = now();
-    if (harvest()) return -1;
-    if (trace) fprintf(stderr, "[s2 ingest] %d sources: classify %.0f us, group+enqueue %.0f us (ring wait %.0f, H2D calls %.0f, inflate calls %.0f, launches %.0f), "
-                       "enqueue done at %.0f us, verdicts at %.0f us, chunks so far %llu\n",
-                       n, us_classify, us_group, tr_wait, tr_h2d, tr_decomp, tr_launch, t_enq - t_begin, now() - t_begin, (unsigned long long)g->n_chunks);
-    if (tr_on) {                                     // device timeline of every chunk, relative to the first copy
-        for (size_t k = 0; k < tr_events.size(); ++k) {
-            float t[6] = { 0, 0, 0, 0, 0, 0 };
-            for (int j = 0; j < 6; ++j) {
-                const cudaError_t e = cudaEventElapsedTime(&t[j], tr_events[0].e[0], tr_events[k].e[j]);
-                if (e != cudaSuccess) { fprintf(stderr, "[s2 ingest]   chunk %zu event %d: %s\n", k, j, cudaGetErrorName(e)); cudaGetLastError(); }
-            }
-            fprintf(stderr, "[s2 ingest]   chunk %zu (%5.1f MB -> %5.1f MB): copy %7.0f..%7.0f  inflate %7.0f..%7.0f  kernels %7.0f..%7.0f us\n", k,
-                            tr_events[k].comp / 1e6, tr_events[k].text / 1e6, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+    if (job->flush()) return -1;
+    CK(cudaEventRecord(job->done, g->stream));
+    if (trace) fprintf(stderr, "[s2 ingest] %d sources submitted: classify %.0f us, group+enqueue %.0f us (ring wait %.0f, H2D calls %.0f, inflate calls %.0f, launches %.0f), "
+                       "enqueue done at %.0f us, chunks so far %llu\n",
+                       n, us_classify, us_group, tr_wait, tr_h2d, tr_decomp, tr_launch, ing_now() - t_begin, (unsigned long long)g->n_chunks);
+    return 0;
+}
+
+static void ingest_trace_timeline(void)
+{
+    if (!tr_on) return;                              // device timeline of every chunk, relative to the first copy
+    for (size_t k = 0; k < tr_events.size(); ++k) {
+        float t[6] = { 0, 0, 0, 0, 0, 0 };
+        for (int j = 0; j < 6; ++j) {
+            const cudaError_t e = cudaEventElapsedTime(&t[j], tr_events[0].e[0], tr_events[k].e[j]);
+            if (e != cudaSuccess) { fprintf(stderr, "[s2 ingest]   chunk %zu event %d: %s\n", k, j, cudaGetErrorName(e)); cudaGetLastError(); }
         }
-        for (auto &ev : tr_events) for (auto &e : ev.e) cudaEventDestroy(e);
-        cudaGetLastError();
-        tr_events.clear();
-        tr_on = false;
+        fprintf(stderr, "[s2 ingest]   chunk %zu (%5.1f MB -> %5.1f MB): copy %7.0f..%7.0f  inflate %7.0f..%7.0f  kernels %7.0f..%7.0f us\n", k,
+                        tr_events[k].comp / 1e6, tr_events[k].text / 1e6, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
     }
+    for (auto &ev : tr_events) for (auto &e : ev.e) cudaEventDestroy(e);
+    cudaGetLastError();
+    tr_events.clear();
+    tr_on = false;
+}
+
+static int ingest_job_finish(s2_ingest_job *job)
+{
+    s2_ingest *g = job->g;
+    s2_table *t = job->t;
+    const double t0 = ing_now();
+    CK(cudaEventSynchronize(job->done));             // the job's last group is through (later jobs may still be running)
+    if (job->read_verdicts()) return -1;
+    if (s2_env_int("S2_INGEST_TRACE", 0)) fprintf(stderr, "[s2 ingest] verdicts after another %.0f us of waiting\n", ing_now() - t0);
+    ingest_trace_timeline();
     // members of irregular groups, one by one (a group's verdict precedes its scan: nothing of it was counted)
     std::vector<int> again;
-    again.swap(retry);
+    again.swap(job->retry);
     for (int i : again) {
-        const int rc = add_to_group(i, true);
+        const int rc = job->add_to_group(i, true);
         if (rc < 0) return -1;
-        if (rc) rc_each[i] = 1;
-        if (P[0]->n_results + 2 >= ING_MAX_RESULTS && harvest()) return -1;
+        if (rc) job->rc[i] = 1;
     }
-    if (harvest()) return -1;
+    if (!again.empty() && job->harvest()) return -1;
     // big files
-    for (int i : streamed) {
+    for (int i : job->streamed) {
         IngResult r; uint64_t done = 0;
-        const int rc = ingest_stream(P[0], t, srcs[i], ING_COUNT, col, 1u, &r, &done);
+        const int rc = ingest_stream(g, t, job->srcs[i], ING_COUNT, job->col, 1u, &r, &done);
         if (rc < 0) return -1;
         if (r.irregular) {
             // chunks before the first irregular one were counted: replay with increment -1 (same verdicts, same chunks)
             if (done > 1 || (rc == 1 && done > 0)) {
                 IngResult r2; uint64_t d2 = 0;
-                if (ingest_stream(P[0], t, srcs[i], ING_COUNT, col, 0xFFFFFFFFu, &r2, &d2) < 0) return -1;
+                if (ingest_stream(g, t, job->srcs[i], ING_COUNT, job->col, 0xFFFFFFFFu, &r2, &d2) < 0) return -1;
             }
-            rc_each[i] = 1;
+            job->rc[i] = 1;
         } else {
-            tot_bases += r.bases;
-            tot_lookups += srcs[i].fasta ? (r.bases > 30 * r.records ? r.bases - 30 * r.records : 0) : r.lookups;
+            job->add_totals(r, job->srcs[i].fasta);
         }
     }
-    if (bases) *bases = tot_bases;
-    if (lookups) *lookups = tot_lookups;
     return 0;
+}
+
+static s2_ingest_job *ingest_job_new(s2_ctx *c, s2_table *t, int col, size_t n)
+{
+    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return nullptr; }
+    s2_ingest *g = ingest_pipeline(c);
+    if (!g) return nullptr;
+    s2_ingest_job *job = new s2_ingest_job();
+    job->c = c; job->t = t; job->g = g; job->col = col;
+    job->srcs.resize(n); job->rc.assign(n, 1);
+    if (cudaEventCreateWithFlags(&job->done, cudaEventDisableTiming) != cudaSuccess) { s2_set_error("cannot create an event"); delete job; return nullptr; }
+    return job;
+}
+
+// Asynchronous form: submit returns as soon as everything that fits a chunk is enqueued (the images must stay valid
+// until the job has been waited for); wait blocks until the job's files are counted (or handed back) and frees the job.
+extern "C" s2_ingest_job *s2_ingest_submit_mem_batch(s2_ctx *c, s2_table *t, const void *const *images, const uint64_t *n_bytes, int n, int col)
+{
+    s2_ingest_job *job = ingest_job_new(c, t, col, (size_t)std::max(n, 0));
+    if (!job) return nullptr;
+    for (int i = 0; i < n; ++i) { job->srcs[i].mem = (const uint8_t *)images[i]; job->srcs[i].mem_len = (size_t)n_bytes[i]; }
+    if (ingest_job_submit(job)) { ingest_quiesce(job->g); delete job; return nullptr; }
+    return job;
+}
+
+extern "C" s2_ingest_job *s2_ingest_submit_files(s2_ctx *c, s2_table *t, const char *const *paths, int n, int col)
+{
+    s2_ingest_job *job = ingest_job_new(c, t, col, (size_t)std::max(n, 0));
+    if (!job) return nullptr;
+    for (int i = 0; i < n; ++i) {
+        const int fd = open(paths[i], O_RDONLY);
+        job->srcs[i].fd = fd;                        // -1: not eligible (classification reads nothing)
+        if (fd >= 0) job->own_fds.push_back(fd);
+    }
+    if (ingest_job_submit(job)) { ingest_quiesce(job->g); delete job; return nullptr; }
+    return job;
+}
+
+extern "C" int s2_ingest_wait(s2_ingest_job *job, int *rc_each, uint64_t *bases, uint64_t *lookups)
+{
+    if (!job) { s2_set_error("no job"); return -1; }
+    const int rc = ingest_job_finish(job);
+    if (rc) ingest_quiesce(job->g);
+    for (size_t i = 0; i < job->rc.size(); ++i) if (rc_each) rc_each[i] = rc ? 1 : job->rc[i];
+    if (bases) *bases = job->tot_bases;
+    if (lookups) *lookups = job->tot_lookups;
+    delete job;
+    return rc;
 }
 
 // GEN_calculate_kmer_count for one file, entirely on the GPU when the file is BGZF-compressed (or uncompressed)
@@ -1342,13 +1412,8 @@ static int ingest_count_sources(s2_ctx *c, s2_table *t, std::vector<IngSource> &
 // counted: use the host reader), -1 = error.
 extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups)
 {
-    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
-    std::vector<IngSource> srcs(1);
-    srcs[0].fd = open(path, O_RDONLY);
-    if (srcs[0].fd < 0) return 1;
     int rc_each = 1;
-    const int rc = ingest_count_sources(c, t, srcs, col, &rc_each, bases, lookups);
-    close(srcs[0].fd);
+    const int rc = s2_ingest_count_files(c, t, &path, 1, col, &rc_each, bases, lookups);
     return rc < 0 ? rc : rc_each;
 }
 
@@ -1356,11 +1421,8 @@ extern "C" int s2_ingest_count_file(s2_ctx *c, s2_table *t, const char *path, in
 // memory gives the full PCIe rate).  Only the compressed bytes cross PCIe.
 extern "C" int s2_ingest_count_mem(s2_ctx *c, s2_table *t, const void *image, uint64_t n_bytes, int col, uint64_t *bases, uint64_t *lookups)
 {
-    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
-    std::vector<IngSource> srcs(1);
-    srcs[0].mem = (const uint8_t *)image; srcs[0].mem_len = (size_t)n_bytes;
     int rc_each = 1;
-    const int rc = ingest_count_sources(c, t, srcs, col, &rc_each, bases, lookups);
+    const int rc = s2_ingest_count_mem_batch(c, t, &image, &n_bytes, 1, col, &rc_each, bases, lookups);
     return rc < 0 ? rc : rc_each;
 }
 
@@ -1370,34 +1432,22 @@ extern "C" int s2_ingest_count_mem(s2_ctx *c, s2_table *t, const void *image, ui
 extern "C" int s2_ingest_count_mem_batch(s2_ctx *c, s2_table *t, const void *const *images, const uint64_t *n_bytes, int n, int col,
                                          int *rc_each, uint64_t *bases, uint64_t *lookups)
 {
-    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
     for (int i = 0; i < n; ++i) rc_each[i] = 1;
     if (bases) *bases = 0;
     if (lookups) *lookups = 0;
-    if (n <= 0) return 0;
-    std::vector<IngSource> srcs((size_t)n);
-    for (int i = 0; i < n; ++i) { srcs[i].mem = (const uint8_t *)images[i]; srcs[i].mem_len = (size_t)n_bytes[i]; }
-    return ingest_count_sources(c, t, srcs, col, rc_each, bases, lookups);
+    if (n <= 0) return col < 0 || col >= t->v.n_cols ? -1 : 0;
+    s2_ingest_job *job = s2_ingest_submit_mem_batch(c, t, images, n_bytes, n, col);
+    return job ? s2_ingest_wait(job, rc_each, bases, lookups) : -1;
 }
 
 extern "C" int s2_ingest_count_files(s2_ctx *c, s2_table *t, const char *const *paths, int n, int col, int *rc_each, uint64_t *bases, uint64_t *lookups)
 {
-    if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return -1; }
     for (int i = 0; i < n; ++i) rc_each[i] = 1;
     if (bases) *bases = 0;
     if (lookups) *lookups = 0;
-    if (n <= 0) return 0;
-    std::vector<IngSource> srcs;
-    std::vector<int> index;
-    for (int i = 0; i < n; ++i) {
-        const int fd = open(paths[i], O_RDONLY);
-        if (fd < 0) continue;
-        srcs.emplace_back(); srcs.back().fd = fd; index.push_back(i);
-    }
-    std::vector<int> rcs(srcs.size(), 1);
-    const int rc = srcs.empty() ? 0 : ingest_count_sources(c, t, srcs, col, rcs.data(), bases, lookups);
-    for (size_t k = 0; k < srcs.size(); ++k) { close(srcs[k].fd); rc_each[index[k]] = rcs[k]; }
-    return rc;
+    if (n <= 0) return col < 0 || col >= t->v.n_cols ? -1 : 0;
+    s2_ingest_job *job = s2_ingest_submit_files(c, t, paths, n, col);
+    return job ? s2_ingest_wait(job, rc_each, bases, lookups) : -1;
 }
 
 // Pass 1 of quantify_hits_PE (src/strain_detect.c:465-491) for every read of one file, inflated and split on the
