@@ -773,6 +773,15 @@ def test_gpu_ingest_groups_of_small_files(s2, ctx, tmp_path, monkeypatch):
     st = ctx.sync()
     assert [rc == 0 for rc in rcs] == handled and bases2 == bases
     assert st.hits == want_hits and np.array_equal(t.counts(3), t.counts(1))
+    # asynchronous jobs: three in flight (the same files into two columns, and once more), waited for in order
+    t.clear_counts(2); t.clear_counts(3)
+    ptrs, sizes = [a.ctypes.data for a in images], [a.size for a in images]
+    jobs = [ctx.ingest_submit_mem_batch(t, ptrs, sizes, 2), ctx.ingest_submit_mem_batch(t, ptrs, sizes, 3), ctx.ingest_submit_mem_batch(t, ptrs, sizes, 3)]
+    for j in jobs:
+        rcs, b3, _ = ctx.ingest_wait(j)
+        assert [rc == 0 for rc in rcs] == handled and b3 == bases
+    st = ctx.sync()
+    assert st.hits == 3 * want_hits and np.array_equal(t.counts(2), t.counts(1)) and np.array_equal(t.counts(3), 2 * t.counts(1))
     t.free()
     ctx.ingest_reset()
 
