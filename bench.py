@@ -96,6 +96,39 @@ def make_batch(strain, first_index, n_genomes):
 
 
 # ------------------------------------------------------------------------------------------------
+# NUMA: a rank's pinned host buffers should live next to its GPU
+# ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(device):
+    """run this process on the CPUs of the NUMA node the GPU hangs off, so that the pinned buffers allocated afterwards
+    (first touch) are local to the GPU's PCIe root; returns the node number or None.  Best effort: any failure is ignored."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        if hasattr(pr, "pci_bus_id"):                             # CUDA's own numbering of the device
+            bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, getattr(pr, "pci_device_id", 0))
+        else:
+            out = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            if not out:
+                return None
+            bus = out[-12:] if len(out) >= 12 else out            # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks sampling (recipe: B200_PROFILING.md)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -302,6 +335,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
 
     # ---- strain table replica on this rank's GPU -------------------------------------------------
     from strainer2_b200 import synth
@@ -461,7 +495,8 @@ def main():
                        "genomes_per_step": G, "bases_per_step": step_bases[0], "strain_keys": int(table.n_keys),
                        "table_probe_bytes": int(table.probe_bytes), "table_hbm_bytes": int(table.hbm_bytes),
                        "l2": "inputs larger than L2 (320 MB per step, two alternating batches; the file images come from host memory every step)",
-                       "parallelism": f"file-shard x{world}, replicated table, 1 NCCL all-reduce at the end"},
+                       "parallelism": f"file-shard x{world}, replicated table, 1 NCCL all-reduce at the end",
+                       "numa": "ranks bound to their GPU's NUMA node" if numa_node is not None else "unbound"},
             "kmer_lookups_per_s": all_lookups / (total_ms * 1e-3),
             "hits": int(stats.hits), "hit_rate": stats.hits / max(1, stats.valid_windows),
             "table_build_s": build_s,
