@@ -726,11 +726,7 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     g->comp_chunk = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_CHUNK_MB", 16), 1), 1024) << 20;
     g->text_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_TEXT_MB", 64), 4), 2048) << 20;
     g->max_lines = (unsigned)(g->text_cap / 8);
-    {   // S2_INGEST_SCAN_CTAS: scan CTAs per SM (default: as many as fit)
-        const int fit = std::max(1, c->grid_count / std::max(1, c->n_sm));
-        const int want = s2_env_int("S2_INGEST_SCAN_CTAS", fit);
-        g->grid_scan = c->n_sm * std::min(fit, std::max(1, want));
-    }
+    g->grid_scan = c->grid_count;
     CK(cudaSetDevice(c->device));
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
@@ -872,7 +868,7 @@ static void ingest_classify(IngSource &src)
 // of one group run beside the scan of the previous one, was measured on the bench workload - profiles/r1n_ingest_two_
 // pipelines.txt - and gains nothing: copy engine (46 GB/s of BGZF), inflate engine (140-160 GB/s of text) and the kernels
 // are equally loaded at about 2.2-2.6 ms per 324 MB of FASTA, so overlapping more of the third stage moves nothing.)
-static thread_local s2_ingest *tl_ingest_p[1] = { nullptr };
+static thread_local s2_ingest *tl_ingest = nullptr;
 // host-side time accounting (S2_INGEST_TRACE=1): where the submitting thread spends its time
 static thread_local double tr_wait = 0, tr_h2d = 0, tr_decomp = 0, tr_launch = 0;
 struct IngTraceEv { cudaEvent_t e[6]; size_t comp = 0, text = 0; };     // copy begin/end, inflate begin/end, kernels begin/end
@@ -881,15 +877,14 @@ static thread_local bool tr_on = false;
 static void tr_record(int which, cudaStream_t st) { if (tr_on && !tr_events.empty()) cudaEventRecord(tr_events.back().e[which], st); }
 static inline double ing_now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-static s2_ingest *ingest_pipeline(s2_ctx *c, int which = 0)
+static s2_ingest *ingest_pipeline(s2_ctx *c)
 {
-    s2_ingest *&p = tl_ingest_p[which];
-    if (p && p->ctx != c) { ingest_free(p); p = nullptr; }
-    if (!p) {
-        p = new s2_ingest();
-        if (ingest_init(p, c)) { ingest_free(p); p = nullptr; return nullptr; }
+    if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
+    if (!tl_ingest) {
+        tl_ingest = new s2_ingest();
+        if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return nullptr; }
     }
-    return p;
+    return tl_ingest;
 }
 
 // compressed bytes the next chunk may hold: ramps up over the first chunks of a call
@@ -1525,5 +1520,5 @@ extern "C" void s2_ingest_detect_free(s2_ingest_detect_result *r)
 
 extern "C" void s2_ingest_thread_cleanup(void)
 {
-    for (auto &p : tl_ingest_p) if (p) { ingest_free(p); p = nullptr; }
+    if (tl_ingest) { ingest_free(tl_ingest); tl_ingest = nullptr; }
 }
