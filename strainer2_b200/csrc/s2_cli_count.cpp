@@ -148,6 +148,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
     size_t next = 0;
     std::atomic<bool> stop(false);
     std::atomic<uint64_t> total_bases(0), total_lookups(0);
+    std::atomic<uint64_t> n_gpu_files(0), n_host_files(0);        // S2_STATS: which way the files went
 
     // GPU ingest takes runs of files (same counter column, S2_INGEST_BATCH files / S2_INGEST_BATCH_MB compressed bytes
     // at most) so that small files share a chunk; everything it does not handle goes through the host reader below
@@ -164,6 +165,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
         auto host_read = [&](std::vector<Taken> &run, const std::vector<int> &handled, int col) {
             for (size_t k = 0; k < run.size(); ++k) {
                 s2_reader *r = run[k].r;
+                if (handled[k] == 0) ++n_gpu_files; else ++n_host_files;
                 if (handled[k] == 0 || w.failed) { s2_reader_close(r); continue; }
                 const char *seq; int64_t l; uint64_t bases = 0, lookups = 0;
                 while ((l = s2_reader_next(r, &seq)) >= 0) {
@@ -262,6 +264,9 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
 
     if (bases_out) *bases_out = total_bases.load();
     if (lookups_out) *lookups_out = total_lookups.load();
+    if (s2_env_int("S2_STATS", 0))
+        fprintf(stderr, "[s2] files: %llu inflated + split on the GPU (BGZF / uncompressed), %llu through host zlib + parser (ordinary .gz, irregular text)\n",
+                (unsigned long long)n_gpu_files.load(), (unsigned long long)n_host_files.load());
     return !stop.load() || !open_error.empty();
 }
 
