@@ -451,21 +451,31 @@ def main():
     files_s = time.perf_counter() - t0
     files_stats = ctx.sync()
     barrier()
+    # the same with ONE synchronous call per step (the pipeline fills and drains every step): reported beside it
+    t0 = time.perf_counter()
+    sync_bases = 0
+    for i in range(args.steps):
+        rcs, b, _ = ctx.ingest_count_mem_batch(table, img_ptrs[i % 2], img_sizes[i % 2], 3)
+        sync_bases += b
+    torch.cuda.synchronize()
+    files_sync_s = time.perf_counter() - t0
+    barrier()
     clocks = sampler.stop()                                # sampled through all timed regions
     parity_ok = bool(np.array_equal(table.counts(2), table.counts(1))) if dist is None else None
-    # the file-image path saw the same genomes in the same alternation as the flat path: the two counter columns are equal
-    files_parity_ok = bool(np.array_equal(table.counts(2), table.counts(3))) and files_bases == my_bases
+    # the file-image path saw the same genomes in the same alternation as the flat path, twice (double buffered, then one
+    # synchronous call per step): its counter column is exactly twice the flat path's
+    files_parity_ok = bool(np.array_equal(2 * table.counts(2).astype(np.uint64), table.counts(3).astype(np.uint64))) and files_bases == my_bases == sync_bases
 
     # ---- reduce over ranks ----------------------------------------------------------------------
     vals = torch.tensor([total_ms, e2e_s * 1e3, float(my_bases), float(my_lookups), kernel_ms, float(launches),
-                         files_s * 1e3, float(files_bases)], dtype=torch.float64, device=dev)
+                         files_s * 1e3, float(files_bases), files_sync_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms, files_ms = float(mx[0]), float(mx[1]), float(mx[6])
+        total_ms, e2e_ms, files_ms, files_sync_ms = float(mx[0]), float(mx[1]), float(mx[6]), float(mx[8])
         all_bases, all_lookups, all_files_bases = float(sm[2]), float(sm[3]), float(sm[7])
     else:
-        e2e_ms, files_ms = e2e_s * 1e3, files_s * 1e3
+        e2e_ms, files_ms, files_sync_ms = e2e_s * 1e3, files_s * 1e3, files_sync_s * 1e3
         all_bases, all_lookups, all_files_bases = float(my_bases), float(my_lookups), float(files_bases)
 
     if rank == 0:
@@ -482,6 +492,8 @@ def main():
                               "inflate + record splitting + validation + scan kernel + D2H of the verdicts",
                       "text_bytes_per_step": int(step_bases[0] + step_bases[0] // 80 + 50 * G),
                       "counts_equal_flat_path": files_parity_ok},
+            "files_one_synchronous_call_per_step": {"value": all_files_bases / 1e9 / (files_sync_ms * 1e-3), "unit": "Gbases/s",
+                                                    "what": "the same through s2_ingest_count_mem_batch(): the copy -> inflate -> kernels pipeline fills and drains every step"},
             "flat": {"value": all_bases / 1e9 / (e2e_ms * 1e-3), "unit": "Gbases/s",
                      "h2d_bytes_per_step": int(pinned[0].n), "d2h_bytes_per_step": 16,
                      "what": "s2_scan_count() on pinned host batches: H2D + scan kernel + D2H of the step's hit statistics"},
