@@ -718,6 +718,34 @@ def test_gpu_ingest_long_lines_are_spread_over_blocks(s2, ctx, tmp_path, monkeyp
     ctx.ingest_reset()
 
 
+def test_gpu_ingest_many_short_lines_per_block(s2, ctx, tmp_path):
+    """more lines than threads in one 16 KB text block (the per-block loops run in several rounds): FASTA wrapped at 12
+    columns and at 3 (4,096 lines per block), FASTQ reads of 31-40 bases"""
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    ctx.ingest_reset()
+    rng = synth.rng_for(13, 0)
+    strain = synth.genome(rng, 200_000, 3, n_runs=2)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    rel = [synth.mutate(c, 0.01, rng) for c in strain] + synth.genome(rng, 300_000, 2)
+    clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for c in rel]
+    reads = [synth.sample_reads(rng, clean, 30_000, n, sub_rate=0.005) for n in (31, 33, 40)]
+    fq = b"".join(b"@%d\n%s\n+\n%s\n" % (i, r.tobytes(), b"I" * r.size) for rr in reads for i, r in enumerate(rr))
+    for name, text, ok in (("w12.fa.gz", synth.fasta_bytes(rel, 12), True), ("w3.fa.gz", synth.fasta_bytes(rel[:1], 3), True), ("short.fq.gz", fq, True)):
+        open(os.path.join(tmp, name), "wb").write(synth.bgzf_bytes(text))
+        t.clear_counts(1); t.clear_counts(2)
+        want = ctx.scan_count(t, s2.load_flat(os.path.join(tmp, name)), 1)
+        rc, _, _ = ctx.ingest_count_file(t, os.path.join(tmp, name), 2)
+        st = ctx.sync()
+        if ok:
+            assert rc == 0 and st.hits == want.hits > 10_000 and st.valid_windows == want.valid_windows, name
+            assert np.array_equal(t.counts(2), t.counts(1)), name
+        else:
+            assert rc == 1 and st.hits == 0 and int(t.counts(2).sum()) == 0, name
+    t.free()
+
+
 def test_gpu_ingest_groups_of_small_files(s2, ctx, tmp_path, monkeypatch):
     """many files per call: small files share a chunk (texts back to back); an irregular member sends its group back
     to be run file by file; rc_each tells which files were not handled; counters = sum over the handled files"""
