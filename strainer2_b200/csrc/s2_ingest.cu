@@ -1097,7 +1097,10 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
         file_off += (off_t)used;
         text_total += ch.text_len;
         if (mode == ING_DETECT && text_total / 64 + 1024 > g->rec_cap) {        // records shorter than 64 bytes of text on average overflow the lists (-> host path)
-            const ull want = std::max<ull>(text_total / 32 + 4096, g->rec_cap * 2);
+            // sized once from the file's size where possible (FASTQ deflates about 5 : 1) instead of growing step by step
+            const ssize_t fsize = src.size();
+            const ull guess = fsize > 0 ? (ull)fsize * (src.bgzf ? 6 : 1) / 64 + 4096 : 0;
+            const ull want = std::max<ull>(std::max<ull>(text_total / 32 + 4096, g->rec_cap * 2), std::min<ull>(guess, 1ull << 28));
             unsigned *nl = nullptr, *nh = nullptr, *ni = nullptr;
             if (cudaMalloc((void **)&nl, want * 4) || cudaMalloc((void **)&nh, want * 4) || cudaMalloc((void **)&ni, want * 4)) { s2_set_error("out of device memory"); return -1; }
             CK(cudaStreamSynchronize(g->stream));
