@@ -137,16 +137,27 @@ __device__ __forceinline__ unsigned eq_bytes4(unsigned w, unsigned c)
     return ((((y >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
 }
 
+// nonzero iff some byte of w equals c (no positions: the borrow trick is exact for "any")
+__device__ __forceinline__ unsigned any_byte4(unsigned w, unsigned c)
+{
+    const unsigned x = w ^ (c * 0x01010101u);
+    return (x - 0x01010101u) & ~x & 0x80808080u;
+}
+
 // bit i set <=> text[base+i] == '\n' and t0 <= base+i < t1   (base is 16-byte aligned); *cr: a '\r' in that range
 __device__ __forceinline__ unsigned nl_mask16(const uint8_t *text, ull base, ull t0, ull t1, unsigned *cr)
 {
     *cr = 0;
     if (base + 16 <= t0 || base >= t1) return 0;
     const uint4 v = *reinterpret_cast<const uint4 *>(text + base);
+    const unsigned nl = eq_bytes4(v.x, '\n') | (eq_bytes4(v.y, '\n') << 4) | (eq_bytes4(v.z, '\n') << 8) | (eq_bytes4(v.w, '\n') << 12);
+    if (base >= t0 && base + 16 <= t1) {                                          // the common case: all 16 bytes are text
+        *cr = (any_byte4(v.x, '\r') | any_byte4(v.y, '\r') | any_byte4(v.z, '\r') | any_byte4(v.w, '\r')) ? 1u : 0u;
+        return nl;
+    }
     const unsigned lo = t0 > base ? (unsigned)(t0 - base) : 0u;                  // < 16 here
     const unsigned hi = t1 - base >= 16 ? 16u : (unsigned)(t1 - base);
     const unsigned range = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-    const unsigned nl = eq_bytes4(v.x, '\n') | (eq_bytes4(v.y, '\n') << 4) | (eq_bytes4(v.z, '\n') << 8) | (eq_bytes4(v.w, '\n') << 12);
     const unsigned r = eq_bytes4(v.x, '\r') | (eq_bytes4(v.y, '\r') << 4) | (eq_bytes4(v.z, '\r') << 8) | (eq_bytes4(v.w, '\r') << 12);
     *cr = (r & range) ? 1u : 0u;
     return nl & range;
@@ -437,12 +448,23 @@ __device__ __forceinline__ void ing_add_piece(IngPieces &w, unsigned lo, unsigne
 
 __device__ __forceinline__ void ing_copy_small(const IngPieces &w, const uint8_t *stage, uint8_t *__restrict__ flat, unsigned cnt)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (unsigned e = wid; e < cnt; e += ING_THREADS / 32) {
         const unsigned n = w.len[e];
-        const uint8_t *sp = stage + w.src[e];
-        uint8_t *dp = flat + w.dst[e];
-        for (unsigned i = lane; i < n; i += 32) dp[i] = sp[i];
+        const uint8_t *sp = stage + w.src[e] + lane;                 // one address pair per piece; the passes use immediate offsets
+        uint8_t *dp = flat + w.dst[e] + lane;
+        for (unsigned off = 0; off < n; off += 128, sp += 128, dp += 128) {
+            const unsigned r = n - off;
+            uint8_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            if (lane < r) b0 = sp[0];
+            if (lane + 32 < r) b1 = sp[32];
+            if (lane + 64 < r) b2 = sp[64];
+            if (lane + 96 < r) b3 = sp[96];
+            if (lane < r) dp[0] = b0;
+            if (lane + 32 < r) dp[32] = b1;
+            if (lane + 64 < r) dp[64] = b2;
+            if (lane + 96 < r) dp[96] = b3;
+        }
     }
 }
 
