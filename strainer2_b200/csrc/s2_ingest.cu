@@ -618,167 +618,6 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *tex
     ing_finish_body(text, text_next, st, flat, 1u, res);
 }
 
-// The same copy, organised by TEXT BYTES instead of by lines: a thread takes 16 text bytes (registers), finds the line
-// they lie in by a search in the block's line table (shared memory) and drops them into a shared-memory image of the
-// block's output run - which is contiguous in the flat stream - at (line's flat offset + position in the line); the image
-// is then flushed with 128-bit stores.  A line costs nothing per se (the warp-per-line copy above spends its
-// instructions on per-line bookkeeping: 0.9 warp instructions per text byte), 16 bytes inside one line cost about 35.
-#define ING_TAB 1024                         /* lines per block the table holds; blocks with more copy line by line */
-#define ING_NONE 0xFFFFFFFFu
-struct IngLineTab {
-    unsigned start[ING_TAB + 1], end[ING_TAB + 1], dst[ING_TAB + 1];     // text range [start, end) of a line, flat offset of its first byte (ING_NONE: header)
-    unsigned n, d0, d1;                                                  // entries; flat range [d0, d1) this block produces
-};
-
-__global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy_image(const uint8_t *text, uint8_t *text_next, IngState *st, const unsigned *__restrict__ block_off,
-                                                                     const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
-                                                                     uint8_t *flat, IngResult *res, unsigned *ticket)
-{
-    __shared__ IngLineTab T;
-    // the image is padded by 4 bytes per 16: neighbouring threads store 16-byte runs, which would otherwise hit every bank
-    // four times per store instruction; with the padding consecutive runs start 5 banks apart
-#define ING_IMG(p) ((p) + (((p) >> 4) << 2))
-    __shared__ __align__(16) uint8_t img[(ING_BLOCK + 32) / 16 * 20 + 32];
-    const unsigned n_lines = st->n_lines, tail = st->tail_len;
-    const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
-    const unsigned b0 = blockIdx.x * ING_BLOCK, b1 = b0 + ING_BLOCK;
-    const bool skip = st->skip != 0;
-    if (!skip && blockIdx.x == 0 && threadIdx.x < tail) flat[threadIdx.x] = st->tail[threadIdx.x];
-    if (!skip && (l_lo < l_hi || l_hi < n_lines)) {
-        const unsigned t0 = (unsigned)st->t0;
-        const unsigned open_prev = st->open_kind_in;
-        const unsigned n_end = l_hi - l_lo;
-        const unsigned dst_first = tail + block_out[blockIdx.x];          // flat offset of line l_lo's first byte (see ing_fasta_copy)
-        if (n_end + 1 > ING_TAB) {
-            // thousands of tiny lines in 16 KB: line by line, straight from global memory (rare, slow, simple)
-            const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-            unsigned run = dst_first;
-            for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
-                const unsigned L = l0 + threadIdx.x;
-                unsigned s0 = 0, e = 0, olen = 0, kind = 0;
-                if (L < l_hi) {
-                    s0 = L ? line_end[L - 1] + 1 : t0;
-                    e = line_end[L];
-                    kind = ing_fasta_kind(L, e - s0, e > s0 ? text[s0] : 0, open_prev);
-                    olen = kind == 1 ? e - s0 : kind == 3 ? 1u : 0u;
-                }
-                unsigned total;
-                const unsigned at = run + ing_block_scan(olen, total);
-                const unsigned from = max(s0, b0);                          // what lies before b0 belongs to earlier blocks
-                T.start[threadIdx.x] = from; T.end[threadIdx.x] = kind == 1 ? e - from : 0u; T.dst[threadIdx.x] = at + (from - s0);
-                if (kind == 3) flat[at] = '\n';
-                __syncthreads();
-                const unsigned cnt = min((unsigned)ING_THREADS, l_hi - l0);
-                for (unsigned e = wid; e < cnt; e += ING_THREADS / 32)
-                    for (unsigned i = lane; i < T.end[e]; i += 32) flat[T.dst[e] + i] = text[T.start[e] + i];
-                __syncthreads();
-                run += total;
-            }
-            if (l_hi < n_lines && threadIdx.x < 32) {                      // the open line's part in this block
-                const unsigned s0 = l_hi ? line_end[l_hi - 1] + 1 : t0;
-                if (s0 < b1 && line_end[l_hi] > s0 && ing_fasta_kind(l_hi, 1u, text[s0], open_prev) == 1) {
-                    const unsigned lo = max(s0, b0);
-                    for (unsigned i = lo + lane; i < b1; i += 32) flat[run + (i - s0)] = text[i];
-                }
-            }
-        } else {
-            // ---- the block's first line fixes where its output starts --------------------------------------------
-            if (threadIdx.x == 0) {
-                const unsigned s0 = l_lo ? line_end[l_lo - 1] + 1 : t0;
-                const unsigned len = line_end[l_lo] - s0;
-                const unsigned kind = ing_fasta_kind(l_lo, len, len ? text[s0] : 0, open_prev);
-                T.d0 = dst_first + (kind == 1 && s0 < b0 ? b0 - s0 : 0u);
-                T.d1 = T.d0;
-                T.n = n_end;
-            }
-            __syncthreads();
-            const unsigned a0 = T.d0 & ~15u;                               // the image starts at a 16-byte boundary of the flat stream
-            // ---- line table: the lines that end in this block ... -----------------------------------------------
-            unsigned run = dst_first;
-            for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
-                const unsigned L = l0 + threadIdx.x;
-                unsigned s0 = 0, e = 0, olen = 0, kind = 0;
-                if (L < l_hi) {
-                    s0 = L ? line_end[L - 1] + 1 : t0;
-                    e = line_end[L];
-                    kind = ing_fasta_kind(L, e - s0, e > s0 ? text[s0] : 0, open_prev);
-                    olen = kind == 1 ? e - s0 : kind == 3 ? 1u : 0u;      // a header becomes the record separator, once
-                }
-                unsigned total;
-                const unsigned at = run + ing_block_scan(olen, total);
-                if (L < l_hi) {
-                    const unsigned j = L - l_lo;
-                    T.start[j] = s0; T.end[j] = e; T.dst[j] = kind == 1 ? at : ING_NONE;
-                    if (kind == 3) img[ING_IMG(at - a0)] = '\n';
-                    atomicMax(&T.d1, at + olen);
-                }
-                run += total;
-            }
-            // ---- ... and the one that is still open at its end ---------------------------------------------------
-            if (threadIdx.x == 0 && l_hi < n_lines) {
-                const unsigned s0 = l_hi ? line_end[l_hi - 1] + 1 : t0;
-                if (s0 < b1) {
-                    const unsigned e = line_end[l_hi];
-                    const unsigned kind = ing_fasta_kind(l_hi, e - s0, e > s0 ? text[s0] : 0, open_prev);
-                    T.start[n_end] = s0; T.end[n_end] = b1; T.dst[n_end] = kind == 1 ? run : ING_NONE;
-                    if (kind == 1) atomicMax(&T.d1, run + (b1 - s0));
-                    T.n = n_end + 1;
-                }
-            }
-            __syncthreads();
-            // ---- 16 text bytes per thread and pass -> image -------------------------------------------------------
-            const unsigned n = T.n;
-            uint4 v[ING_TILES];
-#pragma unroll
-            for (unsigned k = 0; k < ING_TILES; ++k) v[k] = __ldg(reinterpret_cast<const uint4 *>(text + b0 + k * ING_TILE + threadIdx.x * 16));
-#pragma unroll
-            for (unsigned k = 0; k < ING_TILES; ++k) {
-                const unsigned x = b0 + k * ING_TILE + threadIdx.x * 16;
-                unsigned lo = 0, hi = n;                                   // first entry with start > x
-                while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (T.start[mid] <= x) lo = mid + 1; else hi = mid; }
-                int j = (int)lo - 1;                                       // the line x lies in (or behind), -1: before the first line
-                const unsigned wv[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
-                if (j >= 0 && x + 16 <= T.end[j]) {                        // all 16 bytes inside one line
-                    const unsigned d = T.dst[j];
-                    if (d != ING_NONE) {
-                        const unsigned o = d + (x - T.start[j]) - a0;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) img[ING_IMG(o + i)] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
-                    }
-                } else {                                                   // a line ends (or the text begins / ends) inside
-                    unsigned cs = 0, ce = 0, cd = ING_NONE;                // current line; empty until the walk reaches one
-                    if (j >= 0) { cs = T.start[j]; ce = T.end[j]; cd = T.dst[j]; }
-                    unsigned nxt = (unsigned)(j + 1);
-                    unsigned ns = nxt < n ? T.start[nxt] : ING_NONE;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const unsigned pos = x + i;
-                        if (pos >= ns) {                                   // the next line begins here
-                            cs = ns; ce = T.end[nxt]; cd = T.dst[nxt];
-                            ++nxt;
-                            ns = nxt < n ? T.start[nxt] : ING_NONE;
-                        }
-                        if (pos < ce && pos >= cs && cd != ING_NONE) img[ING_IMG(cd + (pos - cs) - a0)] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- image -> flat: whole 16-byte words where the block owns all of them, bytes at the two ends ----------
-            const unsigned d0 = T.d0, d1 = T.d1;
-            for (unsigned wd = threadIdx.x; a0 + wd * 16 < d1; wd += ING_THREADS) {
-                const unsigned p = a0 + wd * 16;
-                if (p >= d0 && p + 16 <= d1) {
-                    const unsigned *w4 = reinterpret_cast<const unsigned *>(img + wd * 20);      // ING_IMG(16 * wd): 4-byte aligned
-                    *reinterpret_cast<uint4 *>(flat + p) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                } else for (unsigned q = max(p, d0); q < min(p + 16, d1); ++q) flat[q] = img[ING_IMG(q - a0)];
-            }
-        }
-    }
-#undef ING_IMG
-    if (!ing_last_block(ticket)) return;
-    ing_finish_body(text, text_next, st, flat, 1u, res);
-}
-
 // detect mode: the per-record results are stored after the scan, so the end-of-chunk step is a launch of its own
 __global__ void __launch_bounds__(ING_THREADS) ing_finish(const uint8_t *text, uint8_t *text_next, IngState *st, const uint8_t *flat, unsigned fasta, IngResult *res)
 {
@@ -869,7 +708,6 @@ struct s2_ingest {
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
     int grid_scan = 0;                   // CTAs of the count scan launched from this pipeline
-    bool copy_by_lines = false;          // S2_INGEST_COPY=lines: the warp-per-line FASTA copy instead of the text-byte one
     // detect mode: chunk-local and file-level result arrays
     unsigned *d_hits_c = nullptr, *d_inf_c = nullptr;
     ull *d_rec_off = nullptr, *d_pos_c = nullptr, *d_cnt_c = nullptr, *d_fcnt = nullptr;
@@ -911,10 +749,6 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     g->text_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_TEXT_MB", 64), 4), 2048) << 20;
     g->max_lines = (unsigned)(g->text_cap / 8);
     g->grid_scan = c->grid_count;
-    {
-        const char *e = getenv("S2_INGEST_COPY");
-        g->copy_by_lines = e && strcmp(e, "lines") == 0;
-    }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
@@ -1209,8 +1043,7 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     const S2DevBatch *dev = reinterpret_cast<const S2DevBatch *>(&g->d_state->flat_len);
     if (fasta) {
         ing_fasta_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a, g->d_tickets + 1);
-        if (g->copy_by_lines) ing_fasta_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat, res, g->d_tickets + 2);
-        else ing_fasta_copy_image<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat, res, g->d_tickets + 2);
+        ing_fasta_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat, res, g->d_tickets + 2);
         if (ingest_launch_count(g, t, dev, col)) return -1;
     } else {
         ing_fastq_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a,
