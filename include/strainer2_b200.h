@@ -121,8 +121,10 @@ int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
  * S2_GPU_INGEST_PLAIN=0) is inflated by the Blackwell hardware decompression engine and split into records by kernels; every
  * chunk is proven regular on the device before its scan starts, so an irregular file is never counted.
  * Returns 0 = done, 1 = not handled (nothing was counted; use the reader + s2_batch_submit_count), -1 = error.
- * Thread safe (one ingest pipeline per calling thread; call s2_ingest_thread_cleanup() before the thread exits).
- * Knobs: S2_INGEST_CHUNK_MB (compressed bytes per chunk, 64), S2_INGEST_TEXT_MB (text per chunk, 256). */
+ * Thread safe: one ingest pipeline per calling thread and context.  s2_shutdown() drops the pipeline the calling
+ * thread holds for that context; any other thread calls s2_ingest_thread_cleanup() before it exits (or before the
+ * context it used is shut down).
+ * Knobs: S2_INGEST_CHUNK_MB (compressed bytes per chunk, 16), S2_INGEST_TEXT_MB (text per chunk, 64). */
 int         s2_ingest_count_file(s2_ctx *ctx, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups);
 /* the same for a file IMAGE in host memory (the bytes of a BGZF or plain FASTA / FASTQ file; pinned memory from
  * s2_pinned_alloc gives the full PCIe rate): only the compressed bytes cross PCIe.  The image must stay valid

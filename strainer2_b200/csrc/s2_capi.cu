@@ -58,8 +58,10 @@ extern "C" s2_ctx *s2_init(int device, uint64_t batch_bytes, int n_lanes)
         return nullptr;
     }
     CKN(cudaSetDevice(device));
+    static std::atomic<uint64_t> next_serial{1};
     s2_ctx *c = new s2_ctx();
     c->device = device;
+    c->serial = next_serial.fetch_add(1);
     c->n_sm = prop.multiProcessorCount;
     c->batch_bytes = batch_bytes ? batch_bytes : (64ull << 20);
     c->batch_bytes = (c->batch_bytes + 511) & ~511ull;
@@ -86,6 +88,7 @@ extern "C" s2_ctx *s2_init(int device, uint64_t batch_bytes, int n_lanes)
 extern "C" void s2_shutdown(s2_ctx *c)
 {
     if (!c) return;
+    s2_ingest_ctx_closing(c);
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &l : c->lanes) {

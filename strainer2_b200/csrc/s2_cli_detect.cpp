@@ -592,14 +592,14 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
         int n_gpus = std::min(std::min(s2_env_int("S2_GPUS", 1), s2_device_count() - dev0), n_workers);
         std::vector<uint64_t> labelled(d.informative.begin(), d.informative.end());
         for (int g = 1; g < n_gpus; ++g) {
-            s2_ctx *c = s2_init(dev0 + g, 8u << 20, 2);
-            s2_table *t = c ? s2_table_build(c, flat.data(), flat.size(), 6, 0.0, 0) : nullptr;
+            s2_ctx *gc = s2_init(dev0 + g, 8u << 20, 2);
+            s2_table *t = gc ? s2_table_build(gc, flat.data(), flat.size(), 6, 0.0, 0) : nullptr;
             std::vector<uint8_t> found(labelled.size() + 1);
             if (!t || s2_table_flag(t, labelled.data(), labelled.size(), found.data())) {
                 fprintf(stderr, "%s\n", s2_last_error());
                 return EXIT_FAILURE;
             }
-            ctxs.push_back(c); tables.push_back(t);
+            ctxs.push_back(gc); tables.push_back(t);
         }
     }
     std::vector<uint8_t>().swap(flat);
@@ -642,7 +642,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     fflush(stdout);
     if (s2_env_int("S2_STATS", 0)) {
         double kms = 0; uint64_t kl = 0;
-        for (s2_ctx *c : ctxs) { double k1 = 0; uint64_t l1 = 0; s2_kernel_time(c, &k1, &l1, 0); kms += k1; kl += l1; }
+        for (s2_ctx *gc : ctxs) { double k1 = 0; uint64_t l1 = 0; s2_kernel_time(gc, &k1, &l1, 0); kms += k1; kl += l1; }
         fprintf(stderr, "[s2 detect] gpus=%zu keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu\n",
                 ctxs.size(), d.genome_kmers, d.genome_informative, (unsigned long long)d.n_bases, d.t_read, d.t_gpu, d.t_emit, kms, (unsigned long long)kl);
     }

@@ -690,6 +690,7 @@ struct IngSlot {                       // a chunk travels through one slot of th
 
 struct s2_ingest {
     s2_ctx *ctx = nullptr;
+    uint64_t ctx_serial = 0; int device = 0;      // of ctx when the pipeline was made (ctx itself may be gone by the time it is freed)
     // three streams, one per engine, so that the copy of chunk i+2, the inflate of chunk i+1 and the kernels of chunk i overlap
     cudaStream_t stream = nullptr, copy_stream = nullptr, inflate_stream = nullptr;
     size_t comp_chunk = 0, text_cap = 0; unsigned max_lines = 0;
@@ -718,7 +719,7 @@ struct s2_ingest {
 static void ingest_free(s2_ingest *g)
 {
     if (!g) return;
-    cudaSetDevice(g->ctx->device);
+    cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
     if (g->inflate_stream) { cudaStreamSynchronize(g->inflate_stream); cudaStreamDestroy(g->inflate_stream); }
@@ -743,7 +744,7 @@ static void ingest_free(s2_ingest *g)
 
 static int ingest_init(s2_ingest *g, s2_ctx *c)
 {
-    g->ctx = c;
+    g->ctx = c; g->ctx_serial = c->serial; g->device = c->device;
     // S2_INGEST_CHUNK_MB: compressed bytes per chunk; S2_INGEST_TEXT_MB: inflated text per chunk (BGZF: <= 64 KB per block)
     g->comp_chunk = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_CHUNK_MB", 16), 1), 1024) << 20;
     g->text_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_TEXT_MB", 64), 4), 2048) << 20;
@@ -901,7 +902,8 @@ static inline double ing_now() { return std::chrono::duration<double, std::micro
 
 static s2_ingest *ingest_pipeline(s2_ctx *c)
 {
-    if (tl_ingest && tl_ingest->ctx != c) { ingest_free(tl_ingest); tl_ingest = nullptr; }
+    // another context, or a new one at the address of one that was shut down: start over
+    if (tl_ingest && (tl_ingest->ctx != c || tl_ingest->ctx_serial != c->serial)) { ingest_free(tl_ingest); tl_ingest = nullptr; }
     if (!tl_ingest) {
         tl_ingest = new s2_ingest();
         if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return nullptr; }
@@ -1483,14 +1485,14 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     IngSource src;
     src.fd = open(path, O_RDONLY);
     if (src.fd < 0) return 1;
+    struct FdGuard { int fd; ~FdGuard() { close(fd); } } guard{ src.fd };          // closed on every way out
     ingest_classify(src);
-    if (!src.eligible || src.fasta || (src.bgzf && !g->hw_deflate)) { close(src.fd); return 1; }      // per-read results are a FASTQ feature here
-    const int fd = src.fd;
+    if (!src.eligible || src.fasta || (src.bgzf && !g->hw_deflate)) return 1;      // per-read results are a FASTQ feature here
     const size_t max_rec = (size_t)g->max_lines / 4 + 4;
     auto dev_alloc = [](void **p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
     if (dev_alloc((void **)&g->d_hits_c, max_rec * 4) || dev_alloc((void **)&g->d_inf_c, max_rec * 4) ||
         dev_alloc((void **)&g->d_rec_off, (max_rec + 1) * 8) || dev_alloc((void **)&g->d_pos_c, (ING_CAP_C + 1) * 8) ||
-        dev_alloc((void **)&g->d_cnt_c, 8) || dev_alloc((void **)&g->d_fcnt, 8)) { s2_set_error("out of device memory"); close(fd); return -1; }
+        dev_alloc((void **)&g->d_cnt_c, 8) || dev_alloc((void **)&g->d_fcnt, 8)) { s2_set_error("out of device memory"); return -1; }
     ull n_inf = 0;
     IngResult r;
     memset(&r, 0, sizeof r);
@@ -1499,7 +1501,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
         if (!g->d_frec) {
             if (!g->f_cap) g->f_cap = 1ull << 20;
             if (cudaMalloc((void **)&g->d_frec, g->f_cap * 4) || cudaMalloc((void **)&g->d_foff, g->f_cap * 4) ||
-                cudaMalloc((void **)&g->d_fkmer, g->f_cap * 8)) { s2_set_error("out of device memory"); close(fd); return -1; }
+                cudaMalloc((void **)&g->d_fkmer, g->f_cap * 8)) { s2_set_error("out of device memory"); return -1; }
         }
         CK(cudaMemsetAsync(g->d_fcnt, 0, 8, g->stream));
         rc = ingest_stream(g, t, src, ING_DETECT, 0, 1u, &r, nullptr);
@@ -1512,18 +1514,24 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
         g->f_cap = n_inf + n_inf / 8 + 1024;
         rc = 2;
     }
-    close(fd);
+    if (rc == 2) s2_set_error("the list of informative windows kept growing");
     if (rc) return rc == 2 ? -1 : rc;
     const ull n_rec = r.records;
     out->n_records = n_rec; out->n_inf = n_inf; out->bases = r.bases;
     out->len = (uint32_t *)malloc((n_rec + 1) * 4); out->hits = (uint32_t *)malloc((n_rec + 1) * 4); out->inf = (uint32_t *)malloc((n_rec + 1) * 4);
     out->inf_rec = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_off = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_kmer = (uint64_t *)malloc((n_inf + 1) * 8);
-    CK(cudaMemcpy(out->len, g->d_len_all, n_rec * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->hits, g->d_hits_all, n_rec * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->inf, g->d_inf_all, n_rec * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->inf_rec, g->d_frec, n_inf * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->inf_off, g->d_foff, n_inf * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->inf_kmer, g->d_fkmer, n_inf * 8, cudaMemcpyDeviceToHost));
+    if (!out->len || !out->hits || !out->inf || !out->inf_rec || !out->inf_off || !out->inf_kmer) {
+        s2_set_error("out of host memory");
+        s2_ingest_detect_free(out);
+        return -1;
+    }
+    auto d2h = [](void *dst, const void *from, size_t bytes) { return !bytes || cudaMemcpy(dst, from, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
+    if (!d2h(out->len, g->d_len_all, n_rec * 4) || !d2h(out->hits, g->d_hits_all, n_rec * 4) || !d2h(out->inf, g->d_inf_all, n_rec * 4) ||
+        !d2h(out->inf_rec, g->d_frec, n_inf * 4) || !d2h(out->inf_off, g->d_foff, n_inf * 4) || !d2h(out->inf_kmer, g->d_fkmer, n_inf * 8)) {
+        s2_set_error("reading the per-read results back failed: %s", cudaGetErrorString(cudaGetLastError()));
+        s2_ingest_detect_free(out);
+        return -1;
+    }
     // the kernels append in arbitrary order: sort by (record, offset) = the order pass 2 prints them
     std::vector<uint32_t> perm(n_inf);
     for (uint32_t i = 0; i < n_inf; ++i) perm[i] = i;
@@ -1546,4 +1554,9 @@ extern "C" void s2_ingest_detect_free(s2_ingest_detect_result *r)
 extern "C" void s2_ingest_thread_cleanup(void)
 {
     if (tl_ingest) { ingest_free(tl_ingest); tl_ingest = nullptr; }
+}
+
+void s2_ingest_ctx_closing(s2_ctx *c)
+{
+    if (tl_ingest && tl_ingest->ctx == c) s2_ingest_thread_cleanup();
 }

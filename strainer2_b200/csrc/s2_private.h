@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -50,6 +51,7 @@ struct Lane {
 
 struct s2_ctx {
     int device = 0, n_sm = 0;
+    uint64_t serial = 0;               // unique per s2_init: a thread's ingest pipeline recognises a context that is gone
     uint64_t batch_bytes = 0;
     int n_lanes = 0;
     std::vector<Lane> lanes;
@@ -89,6 +91,9 @@ struct s2_table {
     bool partitioned = false;          // fingerprints do not fit L2: count scans go through the two-phase kernels
 };
 
+
+// s2_shutdown: the calling thread's ingest pipeline goes with its context (s2_ingest.cu)
+void s2_ingest_ctx_closing(s2_ctx *c);
 
 // the count scan of one batch on one lane's stream (direct or two-phase), caller holds c->mu
 int s2_launch_count_on_lane(s2_ctx *c, Lane &l, const uint8_t *d_bases, uint64_t n_bytes, s2_table *t, int col);

@@ -617,6 +617,37 @@ def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path, mo
     ctx.ingest_reset()
 
 
+def test_gpu_ingest_pipeline_follows_its_context(s2, ctx, tmp_path):
+    """the calling thread's ingest pipeline belongs to one context: closing that context drops it, and a context
+    made afterwards (possibly at the same address) gets a pipeline of its own with the same results"""
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    strain, reads = _ingest_fixture(s2, tmp, 20_000, seed=5)
+    synth.write_bgzf(os.path.join(tmp, "m.fastq.gz"), synth.fastq_bytes(reads))
+    flat = s2.load_flat(os.path.join(tmp, "strain.fa"))
+    ctx.ingest_reset()
+    seen = []
+    for _ in range(3):
+        c2 = s2.Context(0, batch_bytes=8 << 20, n_lanes=2)
+        t = s2.StrainTable(c2, flat, n_cols=3)
+        want = c2.scan_count(t, synth.reads_to_flat(reads), 1)
+        rc, bases, _ = c2.ingest_count_file(t, os.path.join(tmp, "m.fastq.gz"), 2)
+        st = c2.sync()
+        assert rc == 0 and bases == reads.size and st.hits == want.hits > 1000
+        assert np.array_equal(t.counts(1), t.counts(2))
+        seen.append(t.counts(2).copy())
+        t.free()
+        c2.close()                                   # takes this thread's pipeline with it
+    assert all(np.array_equal(seen[0], x) for x in seen[1:])
+    # the module's context still works afterwards (its pipeline is rebuilt on demand)
+    t = s2.StrainTable(ctx, flat, n_cols=3)
+    assert ctx.ingest_count_file(t, os.path.join(tmp, "m.fastq.gz"), 2)[0] == 0
+    ctx.sync()
+    assert np.array_equal(t.counts(2), seen[0])
+    t.free()
+    ctx.ingest_reset()
+
+
 @pytest.mark.parametrize("chunk_mb", [(1, 4), None], ids=["streamed", "one_chunk"])
 def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path, monkeypatch, chunk_mb):
     """irregular text is never counted: in one chunk the verdict precedes the scan; in a streamed file the chunks

@@ -79,7 +79,7 @@ def main():
         ctx.sync()
         dt = time.perf_counter() - t
         print(f"genomes  rep {rep}: {args.genomes} files, {tot / 1e6:.0f} Mbases in {dt * 1e3:.2f} ms = {tot / dt / 1e9:.2f} Gbases/s "
-              f"({dt / args.genomes * 1e6:.0f} us per file)", flush=True)
+              f"({dt / max(1, args.genomes) * 1e6:.0f} us per file)", flush=True)
     for rep in range(args.reps):
         t = time.perf_counter()
         rc, b, l = ctx.ingest_count_mem(table, (rpb.ptr, len(rz)), 2)
