@@ -575,7 +575,7 @@ def _ingest_fixture(s2, tmp, n_reads=60_000, seed=0):
 
 
 def _ingest_chunks(ctx, monkeypatch, chunk_mb):
-    """small chunks stream a file through the two-slot ring in many pieces; the defaults take it as one chunk"""
+    """small chunks stream a file through the three-slot ring in many pieces; the defaults take it as one chunk"""
     if chunk_mb:
         monkeypatch.setenv("S2_INGEST_CHUNK_MB", str(chunk_mb[0]))
         monkeypatch.setenv("S2_INGEST_TEXT_MB", str(chunk_mb[1]))
