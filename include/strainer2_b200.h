@@ -159,6 +159,11 @@ typedef struct s2_ingest_detect_result {
 int         s2_ingest_detect_file(s2_ctx *ctx, s2_table *t, const char *path, s2_ingest_detect_result *out);
 void        s2_ingest_detect_free(s2_ingest_detect_result *r);
 void        s2_ingest_thread_cleanup(void);
+/* 1 after the hardware decompression engine met a DEFLATE block it cannot decode (a damaged BGZF member): the engine
+ * reports that as a sticky launch failure (measured, profiles/r1s_hw_decompression_error_probe.txt), the CUDA context
+ * of the process is lost and every later call fails.  The executables exit with an error that says so - as they do
+ * when zlib finds the damage on the host path (s2_reader_damaged); the reference hangs on such a file. */
+int         s2_ingest_engine_failed(void);
 
 /* ---------------------------------------------------------------- gzip output --------------- */
 /* The kmer_hits stream of strain_detect (gzopen(outfile, "wb9") + gzprintf, src/strain_detect.c:299,567,608).
@@ -248,6 +253,10 @@ typedef struct s2_reader s2_reader;
 s2_reader  *s2_reader_open(const char *path);
 int64_t     s2_reader_next(s2_reader *r, const char **seq);
 uint64_t    s2_reader_len(const s2_reader *r);      /* kseq's seq.l, stale after EOF like the original */
+/* 1 once gzread has reported damaged data (corrupt DEFLATE payload, CRC mismatch).  The reference never returns from
+ * such a file: kseq (src/kseq.h:72,:99) takes only a 0 from gzread for the end and re-reads the error for ever
+ * (measured: 100 % CPU until killed).  Here the stream ends at the damage and the executables exit with an error. */
+int         s2_reader_damaged(const s2_reader *r);
 void        s2_reader_close(s2_reader *r);
 
 /* whole programs, argv-compatible with the reference executables */

@@ -123,6 +123,9 @@ static int rd_getc(s2o_reader *r)
     if (r->begin >= r->end) {
         r->begin = 0;
         r->end = gzread(r->f, r->buf, sizeof r->buf);
+        /* gzread < 0 (damaged DEFLATE data, CRC mismatch): the reference tests only `== 0` (src/kseq.h:72,:99) and
+         * re-reads the error for ever - measured, it never returns from such a file.  No behaviour to restate: the
+         * oracle ends the stream; the product ends the run with an error (DESIGN.md 4.4 "Damaged data"). */
         if (r->end <= 0) { r->end = 0; r->is_eof = 1; return -1; }
     }
     return r->buf[r->begin++];

@@ -75,6 +75,7 @@ SIGNATURES = {
     "s2_ingest_detect_file": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]),
     "s2_ingest_detect_free": (None, [C.c_void_p]),
     "s2_ingest_thread_cleanup": (None, []),
+    "s2_ingest_engine_failed": (C.c_int, []),
     "s2_gz_writer_open": (C.c_void_p, [C.c_char_p, C.c_int]),
     "s2_gz_writer_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "s2_gz_writer_close": (C.c_int, [C.c_void_p]),
@@ -100,6 +101,7 @@ SIGNATURES = {
     "s2_reader_open": (C.c_void_p, [C.c_char_p]),
     "s2_reader_next": (C.c_int64, [C.c_void_p, C.POINTER(C.c_char_p)]),
     "s2_reader_len": (C.c_uint64, [C.c_void_p]),
+    "s2_reader_damaged": (C.c_int, [C.c_void_p]),
     "s2_reader_close": (None, [C.c_void_p]),
     "s2_kmer_scrub_count_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "s2_strain_detect_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),

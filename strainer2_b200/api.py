@@ -310,6 +310,11 @@ class Reader:
         seq = C.string_at(s, n) if s else b""
         return ret, seq
 
+    @property
+    def damaged(self):
+        """True once zlib has reported corrupt gzip data (the reference never returns from such a file)"""
+        return bool(lib.s2_reader_damaged(self.h))
+
     def close(self):
         if self.h:
             lib.s2_reader_close(self.h)
@@ -325,7 +330,10 @@ def load_flat(path):
         if ret < 0:
             break
         parts.append(seq)
+    damaged = r.damaged
     r.close()
+    if damaged:
+        raise S2Error("damaged gzip data in %s" % path)
     return flatten_records(parts)[0]
 
 

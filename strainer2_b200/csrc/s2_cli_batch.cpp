@@ -149,7 +149,7 @@ extern "C" int s2_kmer_scrub_count_batch_main(int argc, char **argv)
     s2_scan_stats stats = {};
     for (s2_ctx *cg : ctxs) {
         s2_scan_stats sg = {};
-        if (s2_sync(cg, &sg)) return die(s2_last_error());
+        if (s2_sync(cg, &sg)) return die(open_error.empty() ? s2_last_error() : open_error.c_str());
         stats.hits += sg.hits; stats.valid_windows += sg.valid_windows;
     }
     for (int k = 1; k < 4 && n_gpus > 1 && ok && open_error.empty(); ++k)

@@ -35,7 +35,7 @@ static void count_usage()
 }
 
 // One flat byte stream for s2_table_build: sequence bytes of every record, '\n' between records.
-// Returns -1 if the file cannot be opened.
+// Returns -1 if the file cannot be opened or its gzip data is damaged (the reference never returns from such a file).
 int s2_load_flat(const char *path, std::vector<uint8_t> &flat)
 {
     s2_reader *r = s2_reader_open(path);
@@ -46,7 +46,9 @@ int s2_load_flat(const char *path, std::vector<uint8_t> &flat)
         flat.insert(flat.end(), (const uint8_t *)seq, (const uint8_t *)seq + l);
         flat.push_back('\n');
     }
+    const bool damaged = s2_reader_damaged(r) != 0;
     s2_reader_close(r);
+    if (damaged) { s2_set_error("damaged gzip data in %s", path); return -1; }
     return 0;
 }
 
@@ -179,6 +181,13 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                     }
                     if (exotic) s2_exotic_count_record(exotic, seq, (uint64_t)l, col);
                 }
+                if (s2_reader_damaged(r)) {
+                    // zlib met corrupt DEFLATE data or a CRC mismatch.  The reference spins for ever on this (s2_reader_damaged in
+                    // include/strainer2_b200.h); counting the part before the damage without a word would be worse than either
+                    std::lock_guard<std::mutex> g(mu);
+                    if (open_error.empty()) open_error = "damaged gzip data in " + run[k].path + " (gzread error); nothing is printed";
+                    stop.store(true);
+                }
                 s2_reader_close(r);
                 total_bases += bases; total_lookups += lookups;
             }
@@ -264,6 +273,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
 
     if (bases_out) *bases_out = total_bases.load();
     if (lookups_out) *lookups_out = total_lookups.load();
+    if (s2_ingest_engine_failed()) { open_error = s2_last_error(); stop.store(true); }      // the cause, not whichever thread noticed first
     if (s2_env_int("S2_STATS", 0))
         fprintf(stderr, "[s2] files: %llu inflated + split on the GPU (BGZF / uncompressed), %llu through host zlib + parser (ordinary .gz, irregular text)\n",
                 (unsigned long long)n_gpu_files.load(), (unsigned long long)n_host_files.load());
@@ -360,7 +370,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     s2_scan_stats st = {};
     for (int g = 0; g < n_gpus; ++g) {
         s2_scan_stats sg = {};
-        if (s2_sync(ctxs[g], &sg)) return fail(s2_last_error());
+        if (s2_sync(ctxs[g], &sg)) return fail(open_error.empty() ? s2_last_error() : open_error.c_str());
         st.hits += sg.hits; st.valid_windows += sg.valid_windows;
     }
     if (!open_error.empty()) return fail(open_error.c_str());

@@ -143,7 +143,7 @@ static int background_filter(Detect &d, const char *background_file, unsigned nu
     if (s2_read_list(background_file, 5, nullptr, work)) return EXIT_FAILURE;               // GEN_all_kmer_counts(..., 5, NULL)
     std::string open_error;
     const bool ok = s2_scan_work_items(d.ctx, d.table, d.exotic, work, n_threads, nullptr, open_error, nullptr, nullptr);
-    if (s2_sync(d.ctx, nullptr)) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+    if (s2_sync(d.ctx, nullptr)) { fprintf(stderr, "%s\n", open_error.empty() ? s2_last_error() : open_error.c_str()); return EXIT_FAILURE; }
     if (!open_error.empty()) { fprintf(stderr, "%s\n", open_error.c_str()); return EXIT_FAILURE; }
     if (!ok) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
 
@@ -453,6 +453,12 @@ static int quantify_hits(Detect &d, Job &job, s2_ctx *ctx, s2_table *table)
         }
         t_emit += secs(tC, now());
     }
+    if (rc == 0 && (s2_reader_damaged(r1) || (r2 && s2_reader_damaged(r2)))) {
+        // corrupt DEFLATE data / CRC mismatch: the reference never returns from such a file (include/strainer2_b200.h)
+        snprintf(msg, sizeof msg, "damaged gzip data in %s (gzread error)\n", s2_reader_damaged(r1) ? pe1 : pe2);
+        job.err = msg;
+        rc = EXIT_FAILURE;
+    }
     if (rc == 0) {
         char foot[4][512];
         snprintf(foot[0], sizeof foot[0], "#%s\ttotal_kmer_evaluated\t%lld\n", pe1, (long long)evaluated);          // :633-636
@@ -629,7 +635,8 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
             d.write_out(jobs[i].out);
             std::string().swap(jobs[i].out);
             if (jobs[i].rc) {                       // the reference exit()s here: later lines are never processed
-                fputs(jobs[i].err.c_str(), stderr);
+                if (s2_ingest_engine_failed()) fprintf(stderr, "%s\n", s2_last_error());      // the cause; other lines fail with bare CUDA errors
+                else fputs(jobs[i].err.c_str(), stderr);
                 rc = jobs[i].rc;
                 stop.store(true);
                 break;

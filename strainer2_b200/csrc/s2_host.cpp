@@ -180,6 +180,7 @@ struct s2_reader {
     std::vector<unsigned char> buf;
     size_t begin = 0, end = 0;
     bool eof = false;
+    bool damaged = false;          // gzread reported an error (Z_DATA_ERROR: corrupt DEFLATE data or a CRC mismatch)
     int last_char = 0;
     std::vector<char> seq, qual;
     size_t seq_len = 0, qual_len = 0;
@@ -189,6 +190,10 @@ struct s2_reader {
         if (eof) return 0;
         begin = 0;
         int got = gzread(f, buf.data(), (unsigned)buf.size());
+        // 0 = end of file, also for a file cut short (zlib reports that as Z_BUF_ERROR and returns what it has, so the
+        // reference ends there too).  < 0 = damaged data: the reference's kseq never returns from that (kseq.h:72,99
+        // take only 0 for the end, so it re-reads the error for ever); here the stream ends and the callers fail loudly
+        if (got < 0) damaged = true;
         if (got <= 0) { end = 0; eof = true; return 0; }
         end = (size_t)got;
         return 1;
@@ -249,6 +254,8 @@ extern "C" void s2_reader_close(s2_reader *r)
 }
 
 extern "C" uint64_t s2_reader_len(const s2_reader *r) { return r->seq_len; }
+
+extern "C" int s2_reader_damaged(const s2_reader *r) { return r && r->damaged ? 1 : 0; }
 
 extern "C" int64_t s2_reader_next(s2_reader *r, const char **seq_out)
 {

@@ -43,6 +43,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstddef>
 #include <cstdlib>
@@ -1291,6 +1292,33 @@ static void ingest_quiesce(s2_ingest *g)
     cudaGetLastError();
 }
 
+// Measured (profiles/r1s_hw_decompression_error_probe.txt): a DEFLATE stream the engine cannot decode - not DEFLATE at
+// all, cut short, or followed by other bytes inside the stated length - is not reported per stream: it surfaces as a
+// sticky cudaErrorLaunchFailure and the CUDA context is lost.  The host walk only hands over complete BGZF members,
+// so this takes a member whose payload is damaged.  Say so (the callers' generic message would be a bare CUDA error)
+// and remember it: the executables start over with host inflate (main_kmer_scrub_count.c).
+static std::atomic<int> g_engine_failed{0};
+static void ingest_engine_failed_message(void)
+{
+    s2_set_error("the hardware decompression engine met a DEFLATE block it cannot decode (damaged data inside a BGZF member) and the CUDA "
+                 "context is lost; S2_GPU_INGEST=0 inflates with zlib on the host instead, which names the damaged file");
+}
+static void ingest_explain_failure(void)
+{
+    if (cudaDeviceSynchronize() != cudaErrorLaunchFailure) { cudaGetLastError(); return; }
+    g_engine_failed.store(1);
+    ingest_engine_failed_message();
+}
+
+// also puts the explanation back into the calling thread's error string (other threads fail with bare CUDA errors once
+// the context is gone; the executables report this cause instead of whichever error came first)
+extern "C" int s2_ingest_engine_failed(void)
+{
+    if (!g_engine_failed.load()) return 0;
+    ingest_engine_failed_message();
+    return 1;
+}
+
 static int ingest_job_submit(s2_ingest_job *job)
 {
     s2_ingest *g = job->g;
@@ -1400,7 +1428,7 @@ extern "C" s2_ingest_job *s2_ingest_submit_mem_batch(s2_ctx *c, s2_table *t, con
     s2_ingest_job *job = ingest_job_new(c, t, col, (size_t)std::max(n, 0));
     if (!job) return nullptr;
     for (int i = 0; i < n; ++i) { job->srcs[i].mem = (const uint8_t *)images[i]; job->srcs[i].mem_len = (size_t)n_bytes[i]; }
-    if (ingest_job_submit(job)) { ingest_quiesce(job->g); delete job; return nullptr; }
+    if (ingest_job_submit(job)) { ingest_quiesce(job->g); ingest_explain_failure(); delete job; return nullptr; }
     return job;
 }
 
@@ -1413,7 +1441,7 @@ extern "C" s2_ingest_job *s2_ingest_submit_files(s2_ctx *c, s2_table *t, const c
         job->srcs[i].fd = fd;                        // -1: not eligible (classification reads nothing)
         if (fd >= 0) job->own_fds.push_back(fd);
     }
-    if (ingest_job_submit(job)) { ingest_quiesce(job->g); delete job; return nullptr; }
+    if (ingest_job_submit(job)) { ingest_quiesce(job->g); ingest_explain_failure(); delete job; return nullptr; }
     return job;
 }
 
@@ -1421,7 +1449,7 @@ extern "C" int s2_ingest_wait(s2_ingest_job *job, int *rc_each, uint64_t *bases,
 {
     if (!job) { s2_set_error("no job"); return -1; }
     const int rc = ingest_job_finish(job);
-    if (rc) ingest_quiesce(job->g);
+    if (rc) { ingest_quiesce(job->g); ingest_explain_failure(); }
     for (size_t i = 0; i < job->rc.size(); ++i) if (rc_each) rc_each[i] = rc ? 1 : job->rc[i];
     if (bases) *bases = job->tot_bases;
     if (lookups) *lookups = job->tot_lookups;
@@ -1505,7 +1533,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
         }
         CK(cudaMemsetAsync(g->d_fcnt, 0, 8, g->stream));
         rc = ingest_stream(g, t, src, ING_DETECT, 0, 1u, &r, nullptr);
-        if (rc < 0) break;
+        if (rc < 0) { ingest_quiesce(g); ingest_explain_failure(); break; }
         if (rc || r.irregular || r.inf_overflow) { rc = 1; break; }              // irregular text / absurdly dense chunk: host path
         CK(cudaMemcpy(&n_inf, g->d_fcnt, 8, cudaMemcpyDeviceToHost));
         if (n_inf <= g->f_cap) break;

@@ -107,6 +107,60 @@ def test_reader_randomised_against_oracle_reader(tmp_path):
         assert b"".join(out) == o, text
 
 
+def test_reader_flags_damaged_gzip_data(tmp_path):
+    """Corrupt DEFLATE data makes gzread return -1.  The reference never returns from such a file (kseq takes only a
+    0 from gzread for the end, src/kseq.h:72,:99, and re-reads the error for ever: measured, 100 % CPU until killed),
+    so there is nothing to match: the reader ends the stream there and says so, load_flat raises, the executables exit
+    with an error.  A file that is merely cut short is an ordinary end of file for zlib, the reference and the reader."""
+    import gzip
+    import strainer2_b200 as s2
+    from strainer2_b200 import synth
+    rng = synth.rng_for(9, 0)
+    reads = synth.sample_reads(rng, synth.genome(rng, 100_000, 2), 6000, 100)
+    text = synth.fastq_bytes(reads)
+    good = synth.bgzf_bytes(text)
+    members, off = [], 0
+    while off < len(good):
+        bsize = int.from_bytes(good[off + 16:off + 18], "little") + 1
+        members.append((off, bsize))
+        off += bsize
+    assert len(members) > 4
+    o, b = members[len(members) // 2]
+    junk = bytes((((i * 2654435761) & 0xFFFFFFFF) >> 13) & 0xFF for i in range(b - 26))
+    z = bytearray(gzip.compress(text, 6))
+    for i in range(len(z) // 2, len(z) // 2 + 64):
+        z[i] ^= 0x5A
+    crc = bytearray(gzip.compress(text, 6))
+    crc[-6] ^= 1                                                  # only the CRC-32 in the trailer is wrong
+    cases = {"bgzf_junk_member.gz": (good[:o + 18] + junk + good[o + b - 8:], True),
+             "gzip_flipped_bytes.gz": (bytes(z), True),
+             "gzip_bad_crc.gz": (bytes(crc), True),
+             "gzip_cut_short.gz": (gzip.compress(text, 6)[:-5000], False),
+             "good.gz": (good, False)}
+    first = reads[0].tobytes()
+    for name, (data, damaged) in cases.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        rd = s2.Reader(str(p))
+        n = 0
+        while True:
+            ret, seq = rd.next()
+            if ret == -1:
+                break
+            if ret == -2:                                          # garbage text in front of the damage may parse as a broken record
+                continue
+            assert n > 0 or seq == first, name
+            n += 1
+        assert rd.damaged == damaged, name                         # read to the end: the damage has been met
+        rd.close()
+        assert (n == len(reads)) == (name == "good.gz"), (name, n)
+    with pytest.raises(s2.S2Error):
+        s2.load_flat(str(tmp_path / "bgzf_junk_member.gz"))
+    with pytest.raises(s2.S2Error):
+        s2.load_flat(str(tmp_path / "gzip_bad_crc.gz"))
+    assert len(s2.load_flat(str(tmp_path / "gzip_cut_short.gz"))) < len(s2.load_flat(str(tmp_path / "good.gz"))) == reads.size + len(reads)
+
+
 def _djb2_str(s: bytes) -> int:
     h = 5381
     for c in s:
