@@ -161,6 +161,100 @@ def test_reader_flags_damaged_gzip_data(tmp_path):
     assert len(s2.load_flat(str(tmp_path / "gzip_cut_short.gz"))) < len(s2.load_flat(str(tmp_path / "good.gz"))) == reads.size + len(reads)
 
 
+# ---- the DEFLATE / gzip decoder written for host and device (groundwork, not on the product path) ----------
+@pytest.fixture(scope="module")
+def infl(tmp_path_factory):
+    so = tmp_path_factory.mktemp("infl") / "libinfl.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                           os.path.join(ROOT, "tests", "sim", "inflate_harness.cpp"), "-o", str(so)])
+    L = C.CDLL(str(so))
+    L.sim_gunzip.restype = C.c_int
+    L.sim_inflate_raw.restype = C.c_int
+
+    class Infl:
+        @staticmethod
+        def gunzip(data, cap):
+            dst = (C.c_ubyte * (cap + 64))()
+            C.memset(dst, 0xAB, cap + 64)
+            out = C.c_ulonglong()
+            rc = L.sim_gunzip(data, C.c_ulonglong(len(data)), dst, C.c_ulonglong(cap), C.byref(out))
+            raw = bytes(dst)
+            assert raw[cap:] == b"\xAB" * 64, "wrote past the destination"
+            return rc, raw[:out.value]
+
+        @staticmethod
+        def raw(data, cap):
+            dst = (C.c_ubyte * (cap + 64))()
+            C.memset(dst, 0xAB, cap + 64)
+            out, used = C.c_ulonglong(), C.c_ulonglong()
+            rc = L.sim_inflate_raw(data, C.c_ulonglong(len(data)), dst, C.c_ulonglong(cap), C.byref(out), C.byref(used))
+            raw = bytes(dst)
+            assert raw[cap:] == b"\xAB" * 64, "wrote past the destination"
+            return rc, raw[:out.value], used.value
+    return Infl
+
+
+def _inflate_texts():
+    r = random.Random(1)
+    fasta = b">c1 test\n" + b"\n".join(bytes(r.choice(b"ACGT") for _ in range(80)) for _ in range(1500)) + b"\n"
+    fastq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(r.choice(b"ACGT") for _ in range(150)), b"I" * 150) for i in range(700))
+    return {"empty": b"", "one": b"A", "runs": b"A" * 100000 + b"CG" * 5000, "fasta": fasta, "fastq": fastq,
+            "random": bytes(r.getrandbits(8) for _ in range(70000)), "prose": open(os.path.join(ROOT, "DESIGN.md"), "rb").read()}
+
+
+def test_inflate_matches_zlib_on_every_block_type(infl):
+    """stored / fixed / dynamic blocks, every zlib strategy and level, long overlapping matches, several members, a
+    header with a file name, sync-flush pieces: the decoder yields zlib's bytes and knows where the stream ended"""
+    import gzip
+    import io
+    import zlib
+    texts = _inflate_texts()
+    for name, t in texts.items():
+        for lvl in (0, 1, 6, 9):
+            rc, o = infl.gunzip(gzip.compress(t, lvl), len(t))
+            assert rc == 0 and o == t, (name, lvl, rc)
+        for strat in (zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+            co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, strat)
+            z = co.compress(t) + co.flush()
+            rc, o, used = infl.raw(z + b"TRAILING", len(t))
+            assert rc == 0 and o == t and used == len(z), (name, strat, rc, used, len(z))
+        if len(t) > 1:                                            # a destination one byte too small
+            rc, o = infl.gunzip(gzip.compress(t, 6), len(t) - 1)
+            assert rc == -7 and o == t[:len(o)], (name, rc)
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="some_name.fa", mode="wb", fileobj=buf, compresslevel=6) as f:
+        f.write(texts["fasta"])
+    z = buf.getvalue() + gzip.compress(texts["fastq"], 9) + gzip.compress(b"") + b"\0\0\0\0"
+    rc, o = infl.gunzip(z, len(texts["fasta"]) + len(texts["fastq"]))
+    assert rc == 0 and o == texts["fasta"] + texts["fastq"]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    fq = texts["fastq"]
+    z = b"".join(co.compress(fq[i:i + 5000]) + co.flush(zlib.Z_SYNC_FLUSH) for i in range(0, len(fq), 5000)) + co.flush()
+    rc, o, used = infl.raw(z, len(fq))
+    assert rc == 0 and o == fq and used == len(z)
+    assert infl.gunzip(b"not a gzip file at all, just text\n", 100)[0] == -8
+
+
+def test_inflate_survives_damaged_input(infl):
+    """every truncation is an error; random bit flips end in an error or in the bytes zlib also produces; nothing is
+    ever written past the destination (the harness checks a canary behind it on every call)"""
+    import gzip
+    import zlib
+    r = random.Random(2)
+    t = _inflate_texts()["fastq"][:20000]
+    z = gzip.compress(t, 6)
+    for cut in range(0, len(z), 5):
+        assert infl.gunzip(z[:cut], len(t))[0] < 0, cut
+    for _ in range(1500):
+        zz = bytearray(z)
+        for _ in range(r.randint(1, 4)):
+            zz[r.randrange(len(zz))] ^= 1 << r.randrange(8)
+        rc, o = infl.gunzip(bytes(zz), len(t))
+        if rc == 0:                                               # the CRC-32 is not checked here: compare with zlib's raw inflate
+            d = zlib.decompressobj(-15).decompress(bytes(zz)[10:])
+            assert d == o
+
+
 def _djb2_str(s: bytes) -> int:
     h = 5381
     for c in s:
