@@ -871,52 +871,6 @@ def test_executable_with_bgzf_inputs_matches_oracle(s2, golden_dir, tmp_path):
         assert p.stdout == o.stdout, env
 
 
-def test_executables_fail_loudly_on_damaged_gzip_data(s2, tmp_path, capsys):
-    """Corrupt DEFLATE data inside an intact container.  The reference never returns from such a file (kseq re-reads
-    the gzread error for ever, src/kseq.h:72,:99), so there is no output to match; what must not happen is a table
-    that silently misses part of a file.  GPU ingest path: the hardware engine either reports a wrong length (verdict
-    irregular -> host reader -> zlib finds the damage) or takes the CUDA context down (sticky launch failure); host
-    path (ordinary .gz): zlib finds it.  Every way ends in exit code 1, a message that names the cause, no table."""
-    import gzip
-    from strainer2_b200 import synth
-    tmp = str(tmp_path)
-    strain, reads = _ingest_fixture(s2, tmp, 30_000, seed=6)
-    text = synth.fastq_bytes(reads)
-    good = synth.bgzf_bytes(text)
-    members, off = [], 0
-    while off < len(good):
-        bsize = int.from_bytes(good[off + 16:off + 18], "little") + 1
-        members.append((off, bsize))
-        off += bsize
-    o, b = members[len(members) // 2]
-    junk = bytes((((i * 2654435761) & 0xFFFFFFFF) >> 13) & 0xFF for i in range(b - 26))
-    open(os.path.join(tmp, "bad_bgzf.fastq.gz"), "wb").write(good[:o + 18] + junk + good[o + b - 8:])
-    z = bytearray(gzip.compress(text, 6))
-    z[-6] ^= 1                                                    # ordinary gzip, wrong CRC-32
-    open(os.path.join(tmp, "bad_gzip.fastq.gz"), "wb").write(bytes(z))
-    open(os.path.join(tmp, "good.fastq.gz"), "wb").write(good)
-    open(os.path.join(tmp, "A.txt"), "w").write("")
-    with open(os.path.join(tmp, "inf.txt"), "wb") as f:
-        c0 = bytes(strain[0]).replace(b"N", b"A")
-        for i in range(0, len(c0) - 31, 500):
-            f.write(c0[i:i + 31] + b"\n")
-    for bad in ("bad_bgzf.fastq.gz", "bad_gzip.fastq.gz"):
-        open(os.path.join(tmp, "B.txt"), "w").write("good.fastq.gz\n%s\ngood.fastq.gz\n" % bad)
-        for env in ({}, {"S2_GPU_INGEST": "0"}):
-            p = s2.run_kmer_scrub_count(["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"], cwd=tmp, env=env, timeout=120)
-            with capsys.disabled():
-                print("\n[%s %s] kmer_scrub_count rc=%d: %s" % (bad, env, p.returncode, p.stderr.decode(errors="replace").strip()[-300:]))
-            assert p.returncode == 1 and p.stdout == b"", (bad, env)
-            assert b"damaged" in p.stderr, (bad, env)
-            q = s2.run_strain_detect(["-r", "strain.fa", "-a", "inf.txt", "-b", bad, "-t", "SE", "-o", "hits.gz"], cwd=tmp, env=env, timeout=120)
-            with capsys.disabled():
-                print("[%s %s] strain_detect rc=%d: %s" % (bad, env, q.returncode, q.stderr.decode(errors="replace").strip()[-300:]))
-            assert q.returncode == 1 and b"damaged" in q.stderr, (bad, env)
-    # the same lists without the damaged file still work afterwards (a fresh process has a fresh context)
-    open(os.path.join(tmp, "B.txt"), "w").write("good.fastq.gz\n")
-    assert s2.run_kmer_scrub_count(["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"], cwd=tmp).returncode == 0
-
-
 def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_path):
     """strain_detect on BGZF / plain FASTQ (GPU ingest) with reads shorter than 31 sprinkled in (the reference's
     stale-state behaviour), SE + PE + PEI lines, a PE2 that ends early on a short read (silent) and one that
