@@ -3,7 +3,10 @@
 // STATUS: groundwork for SURVEY 8(f) rank 1, second half - NOT on the product path yet.  The decoder is unit-tested on
 // the host against zlib (tests/test_host.py::test_inflate_*, through tests/sim/inflate_harness.cpp); the probe kernels
 // that wrap it (tools/gunzip_probe.cu) decoded 2,048 .gz images correctly on a B200 at 8.5 - 14.3 GB/s of text
-// (profiles/r1s_gunzip_kernel_v0_probe.txt); nothing in libstrainer2_b200.so calls it yet.
+// (profiles/r1s_gunzip_kernel_v0_probe.txt); nothing in libstrainer2_b200.so calls it yet.  After those runs the match copy,
+// the input refill and the length / distance tables were rewritten for the device (no load that waits for the thread's own
+// store, loads issued in groups, no tables on the thread's stack): same results on the host tests, effect on the GPU not
+// measured yet.
 //
 // Why it exists.  The reference reads every input through zlib's gzread (/root/reference/src/genome_compare.c:194,
 // src/strain_detect.c:417-433), and the inputs it ships and documents are ORDINARY single-member .gz files
@@ -14,7 +17,7 @@
 // files, and a decoder instance needs about 3.4 KB of tables, so thousands run side by side.  A single multi-GB FASTQ
 // stream has no such parallelism and stays on host zlib (or becomes BGZF).
 //
-// Design of the decoder: a 64-bit bit buffer refilled bytewise; canonical Huffman codes decoded through a first-level
+// Design of the decoder: a 64-bit bit buffer refilled eight loads at a time; canonical Huffman codes decoded through a first-level
 // table (10 bits for literal/length codes, 8 bits for distance codes: one load for nearly every symbol of real data)
 // with the canonical count/symbol arrays as the slow path for longer codes; every read and every write is bounds-
 // checked, damaged input ends in an error code, never in an out-of-bounds access.
@@ -53,9 +56,26 @@ struct S2InfBits {
     int overrun;                   // bits were consumed that the input does not have
 };
 
+// top the bit buffer up to at least 57 bits (or to the end of the input).  All loads first, then the shifts: a device
+// thread issues in order, so a load -> shift -> or chain per byte would wait out one cache latency per byte
 S2I_HD inline void s2i_refill(S2InfBits &b)
 {
-    while (b.cnt <= 56 && b.pos < b.n) { b.buf |= (uint64_t)b.p[b.pos++] << b.cnt; b.cnt += 8; }
+    const unsigned want = (64u - b.cnt) >> 3;                       // whole bytes that fit
+    const uint64_t avail = b.n - b.pos;
+    const unsigned take = avail < want ? (unsigned)avail : want;
+    uint8_t r[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (unsigned k = 0; k < 8; ++k) r[k] = k < take ? b.p[b.pos + k] : (uint8_t)0;
+    uint64_t w = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (unsigned k = 0; k < 8; ++k) w |= (uint64_t)r[k] << (8 * k);
+    if (take) b.buf |= w << b.cnt;                                  // cnt <= 56 whenever take > 0
+    b.pos += take;
+    b.cnt += 8 * take;
 }
 // the next k <= 32 bits without consuming them (missing bits read as 0; consuming them sets overrun)
 S2I_HD inline uint32_t s2i_peek(S2InfBits &b, unsigned k)
@@ -139,23 +159,89 @@ S2I_HD inline int s2i_decode(S2InfBits &b, const S2InfCode<TBITS, NSYM> &h)
     return S2I_ERR_BAD_SYMBOL;
 }
 
+// The match copy dst[i] = dst[i - dist], i in [0, len).  Written so that a thread never has to read back a byte it has
+// just stored: on the device such a load goes to L2 (the stores write through L1) and costs some 300 cycles, and the
+// naive byte loop pays that for EVERY byte - which is what the first kernel measurements showed (270 cycles per byte
+// of FASTA, whose gzip -6 stream is mostly 6-8 byte matches).  dist >= 8: groups of 8 loads, then 8 stores (the source
+// group lies wholly before the destination group, so the loads are independent and overlap).  dist < 8 (runs, e.g. a
+// FASTQ quality line of one letter): the dist-byte pattern is loaded once into a register and replicated from there.
+S2I_HD inline void s2i_copy_match(uint8_t *dst, uint64_t dist, uint32_t len)
+{
+    const uint8_t *src = dst - dist;
+    if (dist >= 8) {
+        uint32_t i = 0;
+        for (; i + 8 <= len; i += 8) {
+            uint8_t r[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 8; ++k) r[k] = src[i + k];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 8; ++k) dst[i + k] = r[k];
+        }
+        uint8_t r[8];
+        const uint32_t tail = len - i;                              // < 8 <= dist: still no overlap inside the group
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t k = 0; k < 8; ++k) if (k < tail) r[k] = src[i + k];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t k = 0; k < 8; ++k) if (k < tail) dst[i + k] = r[k];
+        return;
+    }
+    uint64_t pattern = 0;
+    for (uint64_t k = 0; k < dist; ++k) pattern |= (uint64_t)src[k] << (8 * k);
+    uint64_t word = pattern;
+    uint32_t left = (uint32_t)dist;                                 // bytes of the pattern still in `word`
+    for (uint32_t i = 0; i < len; ++i) {
+        dst[i] = (uint8_t)word;
+        word >>= 8;
+        if (--left == 0) { word = pattern; left = (uint32_t)dist; }
+    }
+}
+
 struct S2InfTables {
     S2InfCode<S2I_LIT_BITS, 288> lit;
     S2InfCode<S2I_DIST_BITS, 32> dist;
 };
+
+// RFC 1951 3.2.5 / 3.2.7 as arithmetic instead of tables: a table on a device thread's stack is local memory, which is
+// interleaved over the lanes of the warp - with one decoding lane every entry sits in a cache line of its own
+// length symbol s = 0..28 (codes 257..285): base length and number of extra bits
+S2I_HD inline void s2i_len_code(int s, uint32_t *base, unsigned *extra)
+{
+    if (s < 8) { *base = 3u + (uint32_t)s; *extra = 0; return; }
+    if (s == 28) { *base = 258; *extra = 0; return; }
+    const unsigned e = (unsigned)(s - 4) >> 2;
+    *base = 3u + ((4u + ((unsigned)s & 3u)) << e);
+    *extra = e;
+}
+// distance symbol d = 0..29
+S2I_HD inline void s2i_dist_code(int d, uint32_t *base, unsigned *extra)
+{
+    if (d < 4) { *base = 1u + (uint32_t)d; *extra = 0; return; }
+    const unsigned e = ((unsigned)d >> 1) - 1u;
+    *base = 1u + ((2u + ((unsigned)d & 1u)) << e);
+    *extra = e;
+}
+// order in which the code lengths of the code-length code are sent: 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15, 5 bits each
+S2I_HD inline int s2i_clen_order(int i)
+{
+    const uint64_t lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45 |
+                        11ull << 50 | 4ull << 55;
+    const uint64_t hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+    return (int)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31u);
+}
 
 // One raw DEFLATE stream src[0..src_len) -> dst[0..dst_cap).  *out_len = bytes written (also on error: what was
 // produced before it), *consumed = input bytes the stream occupied (rounded up to a whole byte).  `t` is scratch.
 S2I_HD inline int s2_inflate_raw(const uint8_t *src, uint64_t src_len, uint8_t *dst, uint64_t dst_cap, uint64_t *out_len,
                                  uint64_t *consumed, S2InfTables &t)
 {
-    const uint16_t len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
-    const uint8_t len_extra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
-    const uint16_t dist_base[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145,
-                                     8193, 12289, 16385, 24577 };
-    const uint8_t dist_extra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
-    const uint8_t clen_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
-
     S2InfBits b = { src, src_len, 0, 0, 0, 0 };
     uint64_t out = 0;
     int rc = S2I_OK, last = 0;
@@ -199,8 +285,8 @@ S2I_HD inline int s2_inflate_raw(const uint8_t *src, uint64_t src_len, uint8_t *
             if (b.overrun) { rc = S2I_ERR_TRUNCATED; break; }
             if (nlen > 286 || ndist > 30) { rc = S2I_ERR_CODE_LENGTHS; break; }
             int i = 0;
-            for (; i < ncode; ++i) lengths[clen_order[i]] = (uint8_t)s2i_bits(b, 3);
-            for (; i < 19; ++i) lengths[clen_order[i]] = 0;
+            for (; i < ncode; ++i) lengths[s2i_clen_order(i)] = (uint8_t)s2i_bits(b, 3);
+            for (; i < 19; ++i) lengths[s2i_clen_order(i)] = 0;
             // the code-length code is decoded with the distance table's storage (8-bit first level, <= 7-bit codes)
             if (s2i_build(t.dist, lengths, 19)) { rc = S2I_ERR_CODE_LENGTHS; break; }
             i = 0;
@@ -237,15 +323,18 @@ S2I_HD inline int s2_inflate_raw(const uint8_t *src, uint64_t src_len, uint8_t *
             if (sym == 256) break;
             sym -= 257;
             if (sym >= 29) { rc = S2I_ERR_BAD_SYMBOL; break; }
-            const uint32_t len = len_base[sym] + s2i_bits(b, len_extra[sym]);
+            uint32_t base; unsigned extra;
+            s2i_len_code(sym, &base, &extra);
+            const uint32_t len = base + s2i_bits(b, extra);
             const int ds = s2i_decode(b, t.dist);
             if (ds < 0) { rc = ds; break; }
             if (ds >= 30) { rc = S2I_ERR_BAD_SYMBOL; break; }
-            const uint64_t dist = dist_base[ds] + s2i_bits(b, dist_extra[ds]);
+            s2i_dist_code(ds, &base, &extra);
+            const uint64_t dist = (uint64_t)base + s2i_bits(b, extra);
             if (b.overrun) { rc = S2I_ERR_TRUNCATED; break; }
             if (dist > out) { rc = S2I_ERR_DISTANCE; break; }
             if (dst_cap - out < len) { rc = S2I_ERR_OUTPUT_FULL; break; }
-            for (uint32_t i = 0; i < len; ++i) dst[out + i] = dst[out + i - dist];     // overlapping by design
+            s2i_copy_match(dst + out, dist, len);
             out += len;
         }
         if (rc == S2I_OK && b.overrun) rc = S2I_ERR_TRUNCATED;
