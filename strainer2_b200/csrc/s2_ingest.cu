@@ -35,6 +35,7 @@
 // to the host reader (return value 1) with the counters untouched.
 #include "s2_private.h"
 #include "s2_kmer.cuh"
+#include "s2_inflate.cuh"
 
 #include <cuda.h>
 #include <fcntl.h>
@@ -677,6 +678,27 @@ typedef CUresult (*devattr_fn)(int *, CUdevice_attribute, CUdevice);
 enum { ING_COUNT = 1, ING_DETECT = 2 };
 
 #define ING_SLOTS 3
+// ---- ordinary .gz: software gunzip of the files of a group (S2_GPU_GUNZIP=1; UNVALIDATED ON A GPU IN THIS FORM) --------
+// The hardware engine cannot take ordinary single-member .gz (DESIGN 4.4 "Damaged data"), so those files are decoded by
+// s2_inflate.cuh: one warp per file, lane 0 decodes, the tables of the warp's decoder in shared memory.  To the rest of the
+// pipeline a gz group looks like a BGZF chunk whose "blocks" are whole files: isz[f] = the file's ISIZE, act[f] = the bytes
+// the decoder produced (all ones on any error), so ing_check_chunk's act == isz test vetoes the scan exactly as it does
+// for a damaged BGZF member.  Off by default until it has been through the GPU tests.
+#define ING_GZ_WARPS 4
+__global__ void __launch_bounds__(ING_GZ_WARPS * 32) ing_gunzip_files(const uint8_t *__restrict__ comp, const ull *__restrict__ comp_off,
+                                                                      uint8_t *text, const ull *__restrict__ file_end,
+                                                                      const unsigned *__restrict__ isz, unsigned *act, unsigned n_files)
+{
+    __shared__ S2InfTables tables[ING_GZ_WARPS];
+    const unsigned warp = threadIdx.x >> 5;
+    const unsigned f = blockIdx.x * ING_GZ_WARPS + warp;
+    if (f >= n_files || (threadIdx.x & 31u)) return;
+    const ull t_begin = f ? file_end[f - 1] : 0;
+    uint64_t got = 0;
+    const int rc = s2_gunzip(comp + comp_off[f], comp_off[f + 1] - comp_off[f], text + ING_MAXCARRY + t_begin, isz[f], &got, tables[warp]);
+    act[f] = rc == S2I_OK ? (unsigned)got : 0xFFFFFFFFu;
+}
+
 struct IngSlot {                       // a chunk travels through one slot of the ring: copy engine -> decompression engine -> kernels
     uint8_t *h_comp = nullptr;         // pinned staging for file sources (allocated on first use)
     uint8_t *d_comp = nullptr;         // compressed bytes on the device
@@ -742,6 +764,9 @@ static void ingest_free(s2_ingest *g)
 }
 
 #define ING_META_BYTES ((size_t)ING_MAX_FILES * 8 + (size_t)ING_MAX_DBLOCKS * 4)
+// a gz group uses isz[0..n_files) only; the files' offsets into d_comp (ull x (n_files + 1)) sit in the second half of that area
+#define ING_META_GZ_OFF ((size_t)ING_MAX_FILES * 8 + (size_t)ING_MAX_DBLOCKS * 2)
+static_assert((size_t)ING_MAX_FILES * 4 <= (size_t)ING_MAX_DBLOCKS * 2 && ((size_t)ING_MAX_FILES + 1) * 8 <= (size_t)ING_MAX_DBLOCKS * 2, "gz meta fits");
 
 static int ingest_init(s2_ingest *g, s2_ctx *c)
 {
@@ -827,6 +852,7 @@ struct IngSource {
     const uint8_t *mem = nullptr;
     size_t mem_len = 0;
     bool eligible = false, bgzf = false, fasta = false;      // classification
+    bool gz = false; uint32_t gz_isize = 0;                  // ordinary .gz (S2_GPU_GUNZIP=1): ISIZE of the trailer
     ssize_t size() const { if (mem) return (ssize_t)mem_len; struct stat sb; return fstat(fd, &sb) == 0 ? (ssize_t)sb.st_size : -1; }
     ssize_t peek(void *dst, size_t len, off_t off) const
     {
@@ -875,17 +901,44 @@ static int bgzf_first_text_byte(const IngSource &src)
     return -1;
 }
 
+// first byte of the text of an ordinary .gz file (its header may carry a name: up to 4 KB are looked at), -1 if unknown
+static int gz_first_text_byte(const IngSource &src)
+{
+    static thread_local std::vector<uint8_t> buf;
+    buf.resize(4096);
+    const ssize_t hn = src.peek(buf.data(), buf.size(), 0);
+    if (hn < 20) return -1;
+    const uint64_t hl = s2_gzip_header_len(buf.data(), (uint64_t)hn);
+    if (!hl) return -1;
+    z_stream z; memset(&z, 0, sizeof z);
+    if (inflateInit2(&z, -15) != Z_OK) return -1;
+    uint8_t out[16];
+    z.next_in = buf.data() + hl; z.avail_in = (uInt)((size_t)hn - hl);
+    z.next_out = out; z.avail_out = sizeof out;
+    inflate(&z, Z_SYNC_FLUSH);
+    const int first = z.total_out ? out[0] : -1;
+    inflateEnd(&z);
+    return first;
+}
+
 static void ingest_classify(IngSource &src)
 {
     uint8_t head[32];
     const ssize_t hn = src.peek(head, sizeof head, 0);
     src.bgzf = is_bgzf_header(head, hn);
-    const int first = src.bgzf ? bgzf_first_text_byte(src) : (hn >= 1 ? head[0] : -1);
+    src.gz = !src.bgzf && hn >= 18 && head[0] == 0x1f && head[1] == 0x8b && head[2] == 8 && s2_env_int("S2_GPU_GUNZIP", 0) != 0;
+    if (src.gz) {
+        uint8_t tail[4];
+        const ssize_t size = src.size();
+        if (size < 18 || src.peek(tail, 4, (off_t)size - 4) != 4) src.gz = false;
+        else src.gz_isize = (uint32_t)tail[0] | ((uint32_t)tail[1] << 8) | ((uint32_t)tail[2] << 16) | ((uint32_t)tail[3] << 24);
+    }
+    const int first = src.bgzf ? bgzf_first_text_byte(src) : src.gz ? gz_first_text_byte(src) : (hn >= 1 ? head[0] : -1);
     src.fasta = first == '>';
     src.eligible = first == '@' || first == '>';             // neither FASTQ nor FASTA (or an ordinary .gz): host reader
     // uncompressed text takes this path too (read() + PCIe against a host parser at about 1 GB/s per thread);
     // S2_GPU_INGEST_PLAIN=0 keeps it on the host
-    if (!src.bgzf && !s2_env_int("S2_GPU_INGEST_PLAIN", 1)) src.eligible = false;
+    if (!src.bgzf && !src.gz && !s2_env_int("S2_GPU_INGEST_PLAIN", 1)) src.eligible = false;
 }
 
 // One pipeline per calling thread.  (A second pipeline per thread, groups alternating between the two so that the kernels
@@ -925,6 +978,7 @@ struct IngChunk {
     size_t text_len = 0;
     bool first = true, last = true;
     unsigned n_files = 0;         // > 0: a group of whole files (their ends are in the slot's meta)
+    bool gz = false;              // the group's files are ordinary .gz: decoded by ing_gunzip_files
 };
 
 // wait until the slot's previous chunk has left d_comp / params / meta, and return the slot
@@ -1007,9 +1061,10 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     s2_ctx *c = g->ctx;
     cudaStream_t st = g->stream;
     // meta (group file ends, expected block sizes) travels with the chunk
-    const size_t n_db = bgzf ? s.params.size() : 0;
+    const size_t n_db = bgzf ? s.params.size() : ch.gz ? (size_t)ch.n_files : 0;
     if (ch.n_files) CK(cudaMemcpyAsync(s.d_meta, s.h_meta, (size_t)ch.n_files * 8, cudaMemcpyHostToDevice, g->copy_stream));
     if (n_db) CK(cudaMemcpyAsync(s.d_meta + (size_t)ING_MAX_FILES * 8, s.h_meta + (size_t)ING_MAX_FILES * 8, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
+    if (ch.gz) CK(cudaMemcpyAsync(s.d_meta + ING_META_GZ_OFF, s.h_meta + ING_META_GZ_OFF, ((size_t)ch.n_files + 1) * 8, cudaMemcpyHostToDevice, g->copy_stream));
     tr_record(1, g->copy_stream);
     if (tr_on && !tr_events.empty()) { tr_events.back().comp = ch.comp_len; tr_events.back().text = ch.text_len; }
     CK(cudaEventRecord(s.h2d_done, g->copy_stream));
@@ -1023,6 +1078,10 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
             const CUresult r = g->decompress(s.params.data() + i, n, 0, &err_index, (CUstream)g->inflate_stream);
             if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, i + err_index); return -1; }
         }
+    } else if (ch.gz) {
+        ing_gunzip_files<<<(ch.n_files + ING_GZ_WARPS - 1) / ING_GZ_WARPS, ING_GZ_WARPS * 32, 0, g->inflate_stream>>>(
+            s.d_comp, (const ull *)(s.d_meta + ING_META_GZ_OFF), s.d_text, (const ull *)s.d_meta, (const unsigned *)(s.d_meta + (size_t)ING_MAX_FILES * 8), s.d_act,
+            ch.n_files);
     } else if (ch.comp_len) {
         CK(cudaMemcpyAsync(s.d_text + ING_MAXCARRY, s.d_comp, ch.comp_len, cudaMemcpyDeviceToDevice, g->inflate_stream));
     }
@@ -1178,7 +1237,7 @@ struct s2_ingest_job {
     IngSlot *s = nullptr;
     IngGroup cur;
     IngChunk ch;
-    bool cur_fasta = false, cur_bgzf = false;
+    bool cur_fasta = false, cur_bgzf = false, cur_gz = false;
     struct { const uint8_t *h = nullptr; size_t d_off = 0, len = 0; } pend;     // host -> device copies of neighbouring sources are merged
 
     ~s2_ingest_job()
@@ -1206,7 +1265,7 @@ struct s2_ingest_job {
     {
         if (!s || cur.members.empty()) return 0;
         if (push_copy()) return -1;
-        ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size();
+        ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size(); ch.gz = cur_gz;
         cur.result = g->res_seq;
         if (ingest_enqueue(g, t, *s, ch, cur_bgzf, cur_fasta, ING_COUNT, col, 1u, true)) return -1;
         groups.push_back(cur);
@@ -1237,17 +1296,18 @@ struct s2_ingest_job {
         IngSource &src = srcs[i];
         const ssize_t size = src.size();
         if (size < 0) return 2;
-        const size_t cap_max = src.bgzf ? g->comp_chunk : std::min(g->comp_chunk, g->text_cap);
+        const size_t cap_max = src.bgzf || src.gz ? g->comp_chunk : std::min(g->comp_chunk, g->text_cap);
+        if (src.gz && ((size_t)size > cap_max || (size_t)src.gz_isize > g->text_cap)) return 2;       // one DEFLATE stream cannot be streamed in chunks: host
         if ((size_t)size > cap_max) return 1;
         for (int attempt = 0; attempt < 2; ++attempt) {
             // a group closes when the next file would push it over the (ramping) chunk size; a single file may exceed the ramp
             const size_t cap = std::min(cap_max, std::max(ingest_chunk_cap(g), (size_t)size));
-            if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
+            if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || cur_gz != src.gz || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
             if (!s) {
                 // the verdict ring must not wrap onto verdicts this job has not read yet
                 if (!groups.empty() && g->res_seq - groups.front().result + 4 >= ING_MAX_RESULTS && harvest()) return -1;
                 if (ingest_slot_begin(g, &s)) return -1;
-                cur_fasta = src.fasta; cur_bgzf = src.bgzf;
+                cur_fasta = src.fasta; cur_bgzf = src.bgzf; cur_gz = src.gz;
             }
             const uint8_t *h = src.mem;
             if (!src.mem) {
@@ -1267,6 +1327,12 @@ struct s2_ingest_job {
                     continue;
                 }
                 if (used != (size_t)size) { s->params.resize(n_params); if (cur.members.empty()) s = nullptr; return 2; }      // trailing garbage / truncated member
+            } else if (src.gz) {
+                if (text_len + (size_t)src.gz_isize > g->text_cap) { if (cur.members.empty()) { s = nullptr; return 2; } if (flush()) return -1; continue; }
+                ((unsigned *)(s->h_meta + (size_t)ING_MAX_FILES * 8))[cur.members.size()] = src.gz_isize;
+                ((ull *)(s->h_meta + ING_META_GZ_OFF))[cur.members.size()] = ch.comp_len;
+                ((ull *)(s->h_meta + ING_META_GZ_OFF))[cur.members.size() + 1] = ch.comp_len + (size_t)size;
+                text_len += (size_t)src.gz_isize;
             } else {
                 if (text_len + (size_t)size > g->text_cap) { if (cur.members.empty()) { s = nullptr; return 1; } if (flush()) return -1; continue; }
                 text_len += (size_t)size;
@@ -1515,7 +1581,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     if (src.fd < 0) return 1;
     struct FdGuard { int fd; ~FdGuard() { close(fd); } } guard{ src.fd };          // closed on every way out
     ingest_classify(src);
-    if (!src.eligible || src.fasta || (src.bgzf && !g->hw_deflate)) return 1;      // per-read results are a FASTQ feature here
+    if (!src.eligible || src.fasta || src.gz || (src.bgzf && !g->hw_deflate)) return 1;      // per-read results are a FASTQ feature here
     const size_t max_rec = (size_t)g->max_lines / 4 + 4;
     auto dev_alloc = [](void **p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
     if (dev_alloc((void **)&g->d_hits_c, max_rec * 4) || dev_alloc((void **)&g->d_inf_c, max_rec * 4) ||

@@ -64,3 +64,53 @@ def test_executables_fail_loudly_on_damaged_gzip_data(s2, tmp_path, capsys):
     # the same lists without the damaged file still work afterwards (a fresh process has a fresh context)
     open(os.path.join(tmp, "B.txt"), "w").write("good.fastq.gz\n")
     assert s2.run_kmer_scrub_count(["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"], cwd=tmp).returncode == 0
+
+
+@pytest.mark.skipif(not os.environ.get("S2_TEST_GPU_GUNZIP"),
+                    reason="software gunzip route (S2_GPU_GUNZIP=1) is wired but has not been through a GPU run yet; set S2_TEST_GPU_GUNZIP=1 to try it")
+def test_gpu_gunzip_of_ordinary_gz_groups_equals_host_reader(s2, tmp_path, monkeypatch):
+    """ordinary single-member .gz files (FASTA genomes, a FASTQ file) decoded by ing_gunzip_files inside the ingest
+    pipeline: counters equal the host reader's; files the decoder cannot vouch for (two members behind one ISIZE, a
+    wrong ISIZE, damaged data) are handed back untouched"""
+    import gzip
+    from strainer2_b200 import synth
+    monkeypatch.setenv("S2_GPU_GUNZIP", "1")
+    tmp = str(tmp_path)
+    rng = synth.rng_for(7, 11)
+    strain = synth.genome(rng, 300_000, 4, n_runs=2)
+    clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for c in strain]
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    ctx = s2.Context(0, batch_bytes=8 << 20, n_lanes=2)
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    paths = []
+    for i in range(24):                                           # relatives and strangers, 0.3 - 0.6 Mb each
+        g = [c.copy() for c in clean] if i % 3 == 0 else synth.genome(rng, 300_000 + 10_000 * i, 3)
+        p = os.path.join(tmp, "g%d.fa.gz" % i)
+        open(p, "wb").write(gzip.compress(synth.fasta_bytes(g, 80), 6))
+        paths.append(p)
+    reads = synth.sample_reads(rng, clean + synth.genome(rng, 600_000, 2), 20_000, 150, sub_rate=0.005, n_rate=1e-4)
+    fq = os.path.join(tmp, "m.fastq.gz")
+    open(fq, "wb").write(gzip.compress(synth.fastq_bytes(reads), 6))
+    want_hits = 0
+    for p in paths:
+        want_hits += ctx.scan_count(t, s2.load_flat(p), 1).hits
+    rc, bases, lookups = ctx.ingest_count_files(t, paths, 2)
+    st = ctx.sync()
+    assert rc == [0] * len(paths)
+    assert st.hits == want_hits > 1000 and np.array_equal(t.counts(1), t.counts(2))
+    t.clear_counts(1); t.clear_counts(2)
+    want = ctx.scan_count(t, s2.load_flat(fq), 1)
+    rc, bases, lookups = ctx.ingest_count_files(t, [fq], 2)
+    st = ctx.sync()
+    assert rc == [0] and bases == reads.size and st.hits == want.hits and np.array_equal(t.counts(1), t.counts(2))
+    # not vouched for: nothing counted, rc 1
+    t.clear_counts(2)
+    z = gzip.compress(synth.fasta_bytes(clean, 80), 6)
+    bad = {"two_members.fa.gz": z + z, "wrong_isize.fa.gz": z[:-4] + b"\x01\x00\x00\x00", "flipped.fa.gz": z[:len(z) // 2] + bytes([z[len(z) // 2] ^ 0x10]) + z[len(z) // 2 + 1:]}
+    for name, data in bad.items():
+        open(os.path.join(tmp, name), "wb").write(data)
+    rc, _, _ = ctx.ingest_count_files(t, [os.path.join(tmp, n) for n in bad] + paths[:2], 2)
+    ctx.sync()
+    assert rc[:2] == [1, 1] and rc[3:] == [0, 0], rc              # (a single flipped bit may still decode to text of the right length)
+    t.free()
+    ctx.close()
