@@ -255,6 +255,19 @@ def test_inflate_survives_damaged_input(infl):
             assert d == o
 
 
+def test_inflate_fuzz_under_sanitizers(tmp_path):
+    """the decoder on damaged / truncated streams and short destinations, built with -fsanitize=address,undefined and run
+    on exact-size heap buffers: every access stays inside its buffer and intact streams decode to their text"""
+    exe = tmp_path / "inflate_fuzz"
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                         os.path.join(ROOT, "tests", "sim", "inflate_fuzz.cpp"), "-o", str(exe), "-lz"], capture_output=True)
+    if cc.returncode != 0:
+        pytest.skip("no sanitizer runtime for this g++: " + cc.stderr.decode()[-200:])
+    p = subprocess.run([str(exe), "300"], capture_output=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr).decode()[-2000:]
+    assert b"fuzz done" in p.stdout
+
+
 def _djb2_str(s: bytes) -> int:
     h = 5381
     for c in s:
