@@ -400,6 +400,58 @@ def test_example_pipeline_count_filter_detect_chained(s2, tmp_path):
     assert p3.stdout == open(os.path.join(tmp, "o.msg"), "rb").read()
 
 
+def test_config1_reference_example_sh_has_the_reference_digests(s2, tmp_path):
+    """BASELINE config #1 = the reference's own test/example.sh (steps 1-3: test/example.sh:4,11,18) through the three
+    drop-in executables on the reference's own inputs (single-member .gz FASTA), against the digests of the unmodified
+    reference.  The inputs are a copy of /root/reference/test made by oracle/Makefile under oracle/_ref/test
+    (git-ignored data that travels to the GPU box like the compiled reference)."""
+    import gzip
+    import hashlib
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "test")
+    strain = "strains/Bacteroides_ovatus_1001283st1_B8_1001283B150210_160208"
+    if not os.path.exists(os.path.join(d, strain + ".fna.gz")):
+        pytest.skip("oracle/_ref/test (copy of the reference's example inputs, `make -C oracle`) is not present")
+    tmp = str(tmp_path)
+    md5 = lambda b: hashlib.md5(b).hexdigest()
+    p1 = s2.run_kmer_scrub_count(["-r", strain + ".fna.gz", "-A", "genomes_to_scrub.txt", "-B", "metagenomes_to_scrub.txt",
+                                  "-p", os.path.join(tmp, "progress")], cwd=d)
+    assert p1.returncode == 0, p1.stderr
+    assert p1.stdout.count(b"\n") == 6_698_541
+    assert md5(p1.stdout) == "75989a9bc31ef0b6f53a5112a60920bd"
+    prog = open(os.path.join(tmp, "progress"), "rb").read().split(b"\n")
+    assert prog[0] == b"adding kmer counts for:" and [l.split(b"\t")[0] for l in prog[1:3]] == [
+        b"strains/Bacteroides_ovatus_1001302st1_D4_1001302B_160321.fna.gz", b"metagenomes/1001099B_150804_B6_s09_tiny_PE1.fasta.gz"]
+    with gzip.GzipFile(os.path.join(tmp, "counts.gz"), "wb", compresslevel=6) as f:
+        f.write(p1.stdout)
+    p2 = s2.run_kmer_scrub_filter(["-s", os.path.join(tmp, "counts.gz"), "-m", "0.01"], cwd=d)
+    assert p2.returncode == 0, p2.stderr
+    lines = p2.stdout.split(b"\n")
+    assert sum(1 for l in lines if l and not l.startswith(b"#")) == 66_986
+    assert md5(p2.stdout) == "fe981fa571be70e602875ac3463ecdac"          # unmodified scripts/kmer_scrub_filter.py, recorded in the dev container
+    with gzip.GzipFile(os.path.join(tmp, "scrubbed.gz"), "wb", compresslevel=9) as f:
+        f.write(p2.stdout)
+    p3 = s2.run_strain_detect(["-r", strain + ".fna.gz", "-a", os.path.join(tmp, "scrubbed.gz"), "-B", "target_metagenomes.txt",
+                               "-o", os.path.join(tmp, "kmer_hits.gz")], cwd=d)
+    assert p3.returncode == 0, p3.stderr
+    raw = open(os.path.join(tmp, "kmer_hits.gz"), "rb").read()
+    text = gzip.decompress(raw)
+    assert text.count(b"\n") == 1_130
+    assert md5(text) == "e1799e705d4f693240573da32540efcc"
+    assert md5(raw) == "997c3e1b8c1272a736168909c6be359b"                # same zlib, level 9, same byte stream
+    # -C = {the strain itself, the other strain}: the self entry is skipped with the reference's note, the drug column
+    # then equals the pangenome column (same file)
+    open(os.path.join(tmp, "listC.txt"), "w").write(strain + ".fna.gz\nstrains/Bacteroides_ovatus_1001302st1_D4_1001302B_160321.fna.gz\n")
+    p4 = s2.run_kmer_scrub_count(["-r", strain + ".fna.gz", "-A", "genomes_to_scrub.txt", "-B", "metagenomes_to_scrub.txt",
+                                  "-C", os.path.join(tmp, "listC.txt")], cwd=d)
+    assert p4.returncode == 0, p4.stderr
+    assert p4.stderr == ("skipping %s.fna.gz (identical match)\n" % strain).encode()
+    import io
+    import pandas as pd
+    v = pd.read_csv(io.BytesIO(p4.stdout), sep="\t", header=0, usecols=[1, 2, 3, 4]).to_numpy()
+    assert v.shape[0] == 6_698_540
+    assert v[:, 0].sum() == 6_721_161 and v[:, 1].sum() == 1_376_122 and v[:, 2].sum() == 50_506 and v[:, 3].sum() == 1_376_122
+
+
 def test_iupac_bytes_are_hashed_as_strings_like_the_reference(s2, golden_dir, tmp_path):
     """windows with bytes outside ACGTN go through the host string path; output bytes equal the
     reference's (rows containing R/Y/K/M/-/E ..., merged into the replayed row order)"""
