@@ -121,9 +121,9 @@ int         s2_sync(s2_ctx *ctx, s2_scan_stats *totals);
  * S2_GPU_INGEST_PLAIN=0) is inflated by the Blackwell hardware decompression engine and split into records by kernels; every
  * chunk is proven regular on the device before its scan starts, so an irregular file is never counted.
  * Returns 0 = done, 1 = not handled (nothing was counted; use the reader + s2_batch_submit_count), -1 = error.
- * Thread safe: one ingest pipeline per calling thread and context.  s2_shutdown() drops the pipeline the calling
- * thread holds for that context; any other thread calls s2_ingest_thread_cleanup() before it exits (or before the
- * context it used is shut down).
+ * Thread safe: a context owns a small pool of ingest pipelines (S2_INGEST_PIPES, default 3) that all calling threads
+ * share - a call takes a free pipeline for as long as it enqueues work; s2_shutdown() releases them.  s2_ingest_warm()
+ * creates n of them ahead of the first call (device buffers + pinned staging: tens of milliseconds each).
  * Knobs: S2_INGEST_CHUNK_MB (compressed bytes per chunk, 16), S2_INGEST_TEXT_MB (text per chunk, 64). */
 int         s2_ingest_count_file(s2_ctx *ctx, s2_table *t, const char *path, int col, uint64_t *bases, uint64_t *lookups);
 /* the same for a file IMAGE in host memory (the bytes of a BGZF or plain FASTA / FASTQ file; pinned memory from
@@ -158,7 +158,9 @@ typedef struct s2_ingest_detect_result {
 } s2_ingest_detect_result;
 int         s2_ingest_detect_file(s2_ctx *ctx, s2_table *t, const char *path, s2_ingest_detect_result *out);
 void        s2_ingest_detect_free(s2_ingest_detect_result *r);
-void        s2_ingest_thread_cleanup(void);
+void        s2_ingest_thread_cleanup(void);               /* no-op since the pipelines belong to the context */
+int         s2_ingest_warm(s2_ctx *ctx, int n_pipes);
+void        s2_ingest_reset(s2_ctx *ctx);                 /* releases the context's pipelines (no job may be in flight); the next call makes new ones */
 /* 1 after the hardware decompression engine met a DEFLATE block it cannot decode (a damaged BGZF member): the engine
  * reports that as a sticky launch failure (measured, profiles/r1s_hw_decompression_error_probe.txt), the CUDA context
  * of the process is lost and every later call fails.  The executables exit with an error that says so - as they do

@@ -169,10 +169,9 @@ class Context:
             raise S2Error("s2_ingest_count_files: " + _lib.last_error())
         return list(R), b.value, l.value
 
-    @staticmethod
-    def ingest_reset():
-        """drop the calling thread's ingest pipeline (the next call re-reads S2_INGEST_CHUNK_MB / S2_INGEST_TEXT_MB)"""
-        lib.s2_ingest_thread_cleanup()
+    def ingest_reset(self):
+        """drop the context's ingest pipelines (the next call re-reads S2_INGEST_CHUNK_MB / S2_INGEST_TEXT_MB / S2_INGEST_PIPES)"""
+        lib.s2_ingest_reset(self.h)
 
     def kernel_time(self, reset=False):
         ms, n = C.c_double(), C.c_uint64()

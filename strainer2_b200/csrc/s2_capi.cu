@@ -521,6 +521,41 @@ extern "C" int s2_tables_allreduce(s2_table **tabs, int n, int col)
     }
     if (n_keys == 0) return 0;
     for (int i = 0; i < n; ++i) if (s2_table_counts_gather_dev(tabs[i], col, tabs[i]->scratch)) return -1;
+    // One process, n GPUs: the sum is taken straight out of peer memory over NVLink by one kernel per GPU that also
+    // scatters it (s2_peer_sum_scatter_kernel) - no communicator to create (ncclCommInitAll cost 12 s of a 16 s run in
+    // round 1, profiles/r1n_multigpu_cli_check.txt).  S2_ALLREDUCE=nccl, or GPUs without peer access, take ncclAllReduce.
+    const char *how = getenv("S2_ALLREDUCE");
+    bool p2p = n <= S2_MAX_PEERS && !(how && !strcmp(how, "nccl"));
+    for (int i = 0; i < n && p2p; ++i)
+        for (int j = 0; j < n && p2p; ++j) {
+            int can = 0;
+            if (i != j && (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess || !can)) p2p = false;
+        }
+    if (p2p) {
+        S2PeerVecs pv;
+        pv.n = n;
+        for (int i = 0; i < n; ++i) pv.v[i] = tabs[i]->scratch;
+        for (int i = 0; i < n; ++i) {                        // every gather is done before any GPU starts reading
+            CK(cudaSetDevice(devs[i]));
+            CK(cudaStreamSynchronize(tabs[i]->ctx->lanes[0].stream));
+            for (int j = 0; j < n; ++j)
+                if (i != j) {
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                    cudaGetLastError();
+                }
+        }
+        for (int i = 0; i < n; ++i) {
+            CK(cudaSetDevice(devs[i]));
+            s2_launch_peer_sum_scatter(tabs[i]->v, col, tabs[i]->rank_slot, n_keys, pv, tabs[i]->ctx->lanes[0].stream);
+            CK(cudaGetLastError());
+        }
+        for (int i = 0; i < n; ++i) {                        // nobody's vector is reused before everybody has read it
+            CK(cudaSetDevice(devs[i]));
+            CK(cudaStreamSynchronize(tabs[i]->ctx->lanes[0].stream));
+        }
+        return 0;
+    }
     // communicators are created once per set of devices (creating them costs seconds) and kept for the life of the
     // process: the executables call this once per counter column
     static std::mutex comm_mu;

@@ -319,24 +319,30 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     const int n_threads = std::max(s2_default_reader_threads(), n_gpus);
     std::vector<s2_ctx *> ctxs(n_gpus, nullptr);
     std::vector<s2_table *> tables(n_gpus, nullptr);
-    {   // the CUDA contexts come up side by side (each takes the better part of a second)
-        std::vector<std::thread> starters;
-        std::vector<std::string> errs(n_gpus);
-        for (int g = 0; g < n_gpus; ++g)
-            starters.emplace_back([&, g]() {
-                ctxs[g] = s2_init(s2_env_int("S2_DEVICE", 0) + g, s2_env_u64("S2_BATCH_MB", 16) << 20, (n_threads + n_gpus - 1) / n_gpus + 2);
-                if (!ctxs[g]) errs[g] = s2_last_error();
-            });
-        for (auto &t : starters) t.join();
-        for (int g = 0; g < n_gpus; ++g) if (!ctxs[g]) return fail(errs[g].c_str());
-    }
+    // The CUDA contexts come up side by side (each takes the better part of a second) while this thread inflates and
+    // parses the -r genome; each starter then creates its context's ingest pipelines, which goes on beside the table build.
+    const bool gpu_ingest_on = s2_env_int("S2_GPU_INGEST", 1) != 0;
+    const int warm_pipes = gpu_ingest_on ? std::min((n_threads + n_gpus - 1) / n_gpus, std::max(1, s2_env_int("S2_INGEST_PIPES", 3))) : 0;
+    std::vector<std::thread> starters, warmers;
+    std::vector<std::string> start_errs(n_gpus);
+    for (int g = 0; g < n_gpus; ++g)
+        starters.emplace_back([&, g]() {
+            ctxs[g] = s2_init(s2_env_int("S2_DEVICE", 0) + g, s2_env_u64("S2_BATCH_MB", 16) << 20, (n_threads + n_gpus - 1) / n_gpus + 2);
+            if (!ctxs[g]) start_errs[g] = s2_last_error();
+        });
+    auto join_all = [](std::vector<std::thread> &v) { for (auto &t : v) if (t.joinable()) t.join(); };
 
     // ---- table from -r (GEN_hash_sequences_set_count_vec, default 1 / increment 1 / column 0 / 4 wide)
     std::vector<uint8_t> flat;
-    if (s2_load_flat(r_file, flat) != 0) {
+    const int load_rc = s2_load_flat(r_file, flat);
+    join_all(starters);
+    for (int g = 0; g < n_gpus; ++g) if (!ctxs[g]) return fail(start_errs[g].c_str());
+    if (load_rc != 0) {
         fprintf(stderr, "could not read file %s GEN_hash_sequences_set_count_vec()\n", r_file);   // src/genome_compare.c:986
         return fail(nullptr);
     }
+    for (int g = 0; g < n_gpus && warm_pipes; ++g) warmers.emplace_back([&, g]() { s2_ingest_warm(ctxs[g], warm_pipes); });
+    struct JoinGuard { std::vector<std::thread> &v; ~JoinGuard() { for (auto &t : v) if (t.joinable()) t.join(); } } warm_guard{ warmers };
     // windows of the -r genome with a byte outside ACGTN become string keys on the host;
     // nullptr (the normal case) means no such window exists and the host never looks at a window again
     s2_exotic *exotic = s2_exotic_build(flat.data(), flat.size(), 4);
@@ -366,6 +372,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
 
     std::string open_error;
     uint64_t total_bases = 0, total_lookups = 0;
+    join_all(warmers);
     const bool pool_ok = s2_scan_work_items_multi(ctxs, tables, exotic, work, n_threads, progress, open_error, &total_bases, &total_lookups);
     s2_scan_stats st = {};
     for (int g = 0; g < n_gpus; ++g) {

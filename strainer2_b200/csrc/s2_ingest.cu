@@ -49,6 +49,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <string>
 
 #define ING_THREADS 256
@@ -713,7 +714,11 @@ struct IngSlot {                       // a chunk travels through one slot of th
 
 struct s2_ingest {
     s2_ctx *ctx = nullptr;
-    uint64_t ctx_serial = 0; int device = 0;      // of ctx when the pipeline was made (ctx itself may be gone by the time it is freed)
+    int device = 0;
+    // A pipeline belongs to its context's pool and is used by one thread at a time: whoever enqueues chunks (a job's
+    // submit, its retries / streamed files, a detect call) holds `mu`; verdicts are read without it.
+    std::mutex mu;
+    std::mutex res_mu; std::set<uint64_t> res_live;      // verdict-ring entries handed out and not read yet
     // three streams, one per engine, so that the copy of chunk i+2, the inflate of chunk i+1 and the kernels of chunk i overlap
     cudaStream_t stream = nullptr, copy_stream = nullptr, inflate_stream = nullptr;
     size_t comp_chunk = 0, text_cap = 0; unsigned max_lines = 0;
@@ -770,7 +775,7 @@ static_assert((size_t)ING_MAX_FILES * 4 <= (size_t)ING_MAX_DBLOCKS * 2 && ((size
 
 static int ingest_init(s2_ingest *g, s2_ctx *c)
 {
-    g->ctx = c; g->ctx_serial = c->serial; g->device = c->device;
+    g->ctx = c; g->device = c->device;
     // S2_INGEST_CHUNK_MB: compressed bytes per chunk; S2_INGEST_TEXT_MB: inflated text per chunk (BGZF: <= 64 KB per block)
     g->comp_chunk = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_CHUNK_MB", 16), 1), 1024) << 20;
     g->text_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_INGEST_TEXT_MB", 64), 4), 2048) << 20;
@@ -818,11 +823,18 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
 }
 
 // a BGZF member header at p (RFC 1952 + the 'BC' extra subfield): total block size, offset/length of its deflate data, ISIZE
+// A buffer that ends inside the member - even inside its header - is reported as "incomplete" (true, *data_len =
+// (size_t)-1, *block_size = the member's size where the header already tells it, else 0) as long as the bytes that are
+// there fit a BGZF header: a streamed file's chunk may end anywhere (round 1 called a chunk that ended within the first
+// 18 bytes of a header "not BGZF" and sent the whole file back to host zlib after un-counting it).
 static bool bgzf_block(const uint8_t *p, size_t avail, size_t *block_size, size_t *data_off, size_t *data_len, uint32_t *isize)
 {
-    if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return false;
+    static const uint8_t magic[3] = { 0x1f, 0x8b, 8 };
+    for (size_t i = 0; i < 3 && i < avail; ++i) if (p[i] != magic[i]) return false;
+    if (avail > 3 && !(p[3] & 4)) return false;
+    if (avail < 18) { *block_size = 0; *data_len = (size_t)-1; return avail > 0; }
     const size_t xlen = p[10] | (p[11] << 8);
-    if (avail < 12 + xlen) return false;
+    if (avail < 12 + xlen) { *block_size = 0; *data_len = (size_t)-1; return true; }
     size_t bsize = 0;
     for (size_t o = 12; o + 4 <= 12 + xlen;) {
         const size_t slen = p[o + 2] | (p[o + 3] << 8);
@@ -881,7 +893,7 @@ static int bgzf_first_text_byte(const IngSource &src)
         size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
         if (hn <= 0 || !bgzf_block(p, (size_t)hn, &bs, &doff, &dlen, &isz)) return -1;
         if (dlen == (size_t)-1) {                              // the header was readable, the member is not (yet)
-            if (src.mem || bs > 65536) return -1;
+            if (src.mem || bs > 65536 || bs == 0) return -1;
             buf.resize(bs);
             if (src.peek(buf.data(), bs, off) != (ssize_t)bs) return -1;
             p = buf.data();
@@ -941,11 +953,30 @@ static void ingest_classify(IngSource &src)
     if (!src.bgzf && !src.gz && !s2_env_int("S2_GPU_INGEST_PLAIN", 1)) src.eligible = false;
 }
 
-// One pipeline per calling thread.  (A second pipeline per thread, groups alternating between the two so that the kernels
-// of one group run beside the scan of the previous one, was measured on the bench workload - profiles/r1n_ingest_two_
-// pipelines.txt - and gains nothing: copy engine (46 GB/s of BGZF), inflate engine (140-160 GB/s of text) and the kernels
-// are equally loaded at about 2.2-2.6 ms per 324 MB of FASTA, so overlapping more of the third stage moves nothing.)
-static thread_local s2_ingest *tl_ingest = nullptr;
+// The pipelines of a context: a small pool (S2_INGEST_PIPES, default 3) shared by every thread that calls in.  One
+// pipeline already overlaps copy engine, inflate engine and kernels; the others exist so that several reader threads can
+// read files into pinned staging and build launch lists at the same time.  (Round 1 had one pipeline per calling thread:
+// 16 reader threads allocated 16 rings - 5 GB of HBM, 0.8 GB of pinned staging - and the allocation alone made the
+// executables 18x slower than with one thread, profiles/r1n_e2e_cli.txt.)
+struct IngPool {
+    std::mutex mu;                       // guards `pipes` growing
+    std::vector<s2_ingest *> pipes;
+    std::atomic<unsigned> rr{0};
+    unsigned max_pipes = 3;
+};
+static std::mutex g_pool_mu;             // guards c->ingest_pool coming into being
+
+static IngPool *ingest_pool(s2_ctx *c)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!c->ingest_pool) {
+        IngPool *p = new IngPool();
+        p->max_pipes = (unsigned)std::min(std::max(s2_env_int("S2_INGEST_PIPES", 3), 1), 16);
+        c->ingest_pool = p;
+    }
+    return (IngPool *)c->ingest_pool;
+}
+
 // host-side time accounting (S2_INGEST_TRACE=1): where the submitting thread spends its time
 static thread_local double tr_wait = 0, tr_h2d = 0, tr_decomp = 0, tr_launch = 0;
 struct IngTraceEv { cudaEvent_t e[6]; size_t comp = 0, text = 0; };     // copy begin/end, inflate begin/end, kernels begin/end
@@ -954,15 +985,63 @@ static thread_local bool tr_on = false;
 static void tr_record(int which, cudaStream_t st) { if (tr_on && !tr_events.empty()) cudaEventRecord(tr_events.back().e[which], st); }
 static inline double ing_now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-static s2_ingest *ingest_pipeline(s2_ctx *c)
+// a pipeline of the context, LOCKED (release with g->mu.unlock()): a free one, else a new one while the pool may grow,
+// else wait for one
+static s2_ingest *ingest_acquire(s2_ctx *c)
 {
-    // another context, or a new one at the address of one that was shut down: start over
-    if (tl_ingest && (tl_ingest->ctx != c || tl_ingest->ctx_serial != c->serial)) { ingest_free(tl_ingest); tl_ingest = nullptr; }
-    if (!tl_ingest) {
-        tl_ingest = new s2_ingest();
-        if (ingest_init(tl_ingest, c)) { ingest_free(tl_ingest); tl_ingest = nullptr; return nullptr; }
+    IngPool *pool = ingest_pool(c);
+    for (int round = 0; round < 2; ++round) {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        for (s2_ingest *g : pool->pipes) if (g->mu.try_lock()) return g;
+        if (pool->pipes.size() < pool->max_pipes) {
+            s2_ingest *g = new s2_ingest();
+            if (ingest_init(g, c)) { ingest_free(g); return nullptr; }
+            g->mu.lock();
+            pool->pipes.push_back(g);
+            return g;
+        }
     }
-    return tl_ingest;
+    s2_ingest *g;
+    { std::lock_guard<std::mutex> lk(pool->mu); g = pool->pipes[pool->rr.fetch_add(1) % pool->pipes.size()]; }
+    g->mu.lock();
+    return g;
+}
+
+// creates the context's pipelines ahead of their first use (the executables do this beside the table build: a
+// pipeline is 350 MB of device memory and, for file sources, 48 MB of pinned staging - tens of milliseconds each)
+extern "C" int s2_ingest_warm(s2_ctx *c, int n_pipes)
+{
+    IngPool *pool = ingest_pool(c);
+    std::lock_guard<std::mutex> lk(pool->mu);
+    while (pool->pipes.size() < std::min<size_t>((size_t)std::max(n_pipes, 0), pool->max_pipes)) {
+        s2_ingest *g = new s2_ingest();
+        if (ingest_init(g, c)) { ingest_free(g); return -1; }
+        for (auto &sl : g->slot) if (!sl.h_comp && cudaHostAlloc((void **)&sl.h_comp, g->comp_chunk, cudaHostAllocDefault) != cudaSuccess) {
+            s2_set_error("out of pinned memory"); ingest_free(g); return -1;
+        }
+        pool->pipes.push_back(g);
+    }
+    return 0;
+}
+
+// a verdict-ring entry for the chunk about to be enqueued (caller holds g->mu); fails instead of overwriting a verdict
+// that nobody has read yet (thousands of jobs submitted and never waited for)
+static int ingest_result_claim(s2_ingest *g)
+{
+    std::lock_guard<std::mutex> lk(g->res_mu);
+    if (!g->res_live.empty() && g->res_seq - *g->res_live.begin() + 2 >= ING_MAX_RESULTS) {
+        s2_set_error("too many ingest jobs in flight on one pipeline: wait for earlier jobs first");
+        return -1;
+    }
+    g->res_live.insert(g->res_seq);
+    return 0;
+}
+static IngResult ingest_result_take(s2_ingest *g, uint64_t seq)
+{
+    const IngResult r = g->h_results[seq % ING_MAX_RESULTS];
+    std::lock_guard<std::mutex> lk(g->res_mu);
+    g->res_live.erase(seq);
+    return r;
 }
 
 // compressed bytes the next chunk may hold: ramps up over the first chunks of a call
@@ -1101,6 +1180,7 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     const bool detect = mode == ING_DETECT;
     ing_index_count<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_masks, a, g->max_lines, g->d_tickets + 0);
     ing_index_scatter<<<n_blocks, ING_THREADS, 0, st>>>(g->d_masks, g->d_block_nl, g->d_line_end, g->max_lines);
+    if (want_result && ingest_result_claim(g)) return -1;
     IngResult *res = want_result ? g->d_results + g->res_seq % ING_MAX_RESULTS : nullptr;
     const S2DevBatch *dev = reinterpret_cast<const S2DevBatch *>(&g->d_state->flat_len);
     if (fasta) {
@@ -1211,7 +1291,7 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
         return 1;
     }
     CK(cudaStreamSynchronize(g->stream));
-    *res = g->h_results[(g->res_seq - 1) % ING_MAX_RESULTS];        // the last chunk's verdict
+    *res = ingest_result_take(g, g->res_seq - 1);                   // the last chunk's verdict
     return 0;
 }
 
@@ -1282,7 +1362,7 @@ struct s2_ingest_job {
     int read_verdicts()
     {
         for (auto &gr : groups) {
-            const IngResult r = g->h_results[gr.result % ING_MAX_RESULTS];
+            const IngResult r = ingest_result_take(g, gr.result);
             if (!r.irregular) add_totals(r, srcs[gr.members[0]].fasta);
             else if (gr.members.size() == 1) rc[gr.members[0]] = 1;
             else retry.insert(retry.end(), gr.members.begin(), gr.members.end());
@@ -1450,6 +1530,8 @@ static int ingest_job_finish(s2_ingest_job *job)
     // members of irregular groups, one by one (a group's verdict precedes its scan: nothing of it was counted)
     std::vector<int> again;
     again.swap(job->retry);
+    if (again.empty() && job->streamed.empty()) return 0;
+    std::lock_guard<std::mutex> pipeline_lock(g->mu);              // more chunks to enqueue: the pipeline is ours again
     for (int i : again) {
         const int rc = job->add_to_group(i, true);
         if (rc < 0) return -1;
@@ -1478,12 +1560,12 @@ static int ingest_job_finish(s2_ingest_job *job)
 static s2_ingest_job *ingest_job_new(s2_ctx *c, s2_table *t, int col, size_t n)
 {
     if (col < 0 || col >= t->v.n_cols) { s2_set_error("column out of range"); return nullptr; }
-    s2_ingest *g = ingest_pipeline(c);
+    s2_ingest *g = ingest_acquire(c);                   // locked; the submit calls unlock it when everything is enqueued
     if (!g) return nullptr;
     s2_ingest_job *job = new s2_ingest_job();
     job->c = c; job->t = t; job->g = g; job->col = col;
     job->srcs.resize(n); job->rc.assign(n, 1);
-    if (cudaEventCreateWithFlags(&job->done, cudaEventDisableTiming) != cudaSuccess) { s2_set_error("cannot create an event"); delete job; return nullptr; }
+    if (cudaEventCreateWithFlags(&job->done, cudaEventDisableTiming) != cudaSuccess) { s2_set_error("cannot create an event"); g->mu.unlock(); delete job; return nullptr; }
     return job;
 }
 
@@ -1494,7 +1576,8 @@ extern "C" s2_ingest_job *s2_ingest_submit_mem_batch(s2_ctx *c, s2_table *t, con
     s2_ingest_job *job = ingest_job_new(c, t, col, (size_t)std::max(n, 0));
     if (!job) return nullptr;
     for (int i = 0; i < n; ++i) { job->srcs[i].mem = (const uint8_t *)images[i]; job->srcs[i].mem_len = (size_t)n_bytes[i]; }
-    if (ingest_job_submit(job)) { ingest_quiesce(job->g); ingest_explain_failure(); delete job; return nullptr; }
+    if (ingest_job_submit(job)) { ingest_quiesce(job->g); job->g->mu.unlock(); ingest_explain_failure(); delete job; return nullptr; }
+    job->g->mu.unlock();
     return job;
 }
 
@@ -1507,7 +1590,8 @@ extern "C" s2_ingest_job *s2_ingest_submit_files(s2_ctx *c, s2_table *t, const c
         job->srcs[i].fd = fd;                        // -1: not eligible (classification reads nothing)
         if (fd >= 0) job->own_fds.push_back(fd);
     }
-    if (ingest_job_submit(job)) { ingest_quiesce(job->g); ingest_explain_failure(); delete job; return nullptr; }
+    if (ingest_job_submit(job)) { ingest_quiesce(job->g); job->g->mu.unlock(); ingest_explain_failure(); delete job; return nullptr; }
+    job->g->mu.unlock();
     return job;
 }
 
@@ -1574,8 +1658,9 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
 {
     memset(out, 0, sizeof *out);
     if (t->partitioned) return 1;
-    s2_ingest *g = ingest_pipeline(c);
+    s2_ingest *g = ingest_acquire(c);
     if (!g) return -1;
+    std::lock_guard<std::mutex> pipeline_lock(g->mu, std::adopt_lock);     // ours for the whole call
     IngSource src;
     src.fd = open(path, O_RDONLY);
     if (src.fd < 0) return 1;
@@ -1645,12 +1730,16 @@ extern "C" void s2_ingest_detect_free(s2_ingest_detect_result *r)
     memset(r, 0, sizeof *r);
 }
 
-extern "C" void s2_ingest_thread_cleanup(void)
-{
-    if (tl_ingest) { ingest_free(tl_ingest); tl_ingest = nullptr; }
-}
+// kept for callers written against round 1's one-pipeline-per-thread design: the pipelines now belong to the context
+extern "C" void s2_ingest_thread_cleanup(void) {}
+
+extern "C" void s2_ingest_reset(s2_ctx *c) { if (c) s2_ingest_ctx_closing(c); }
 
 void s2_ingest_ctx_closing(s2_ctx *c)
 {
-    if (tl_ingest && tl_ingest->ctx == c) s2_ingest_thread_cleanup();
+    IngPool *pool;
+    { std::lock_guard<std::mutex> lk(g_pool_mu); pool = (IngPool *)c->ingest_pool; c->ingest_pool = nullptr; }
+    if (!pool) return;
+    for (s2_ingest *g : pool->pipes) ingest_free(g);
+    delete pool;
 }

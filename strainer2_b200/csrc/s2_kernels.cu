@@ -434,11 +434,14 @@ void s2_launch_scan_detect_dev(const uint8_t *bases, const S2DevBatch *dev, cons
 // two-phase count scan for tables whose fingerprints do not fit L2 (multi-strain union tables)
 // ------------------------------------------------------------------------------------------------
 // Probing a 1.3 GB fingerprint array at random is DRAM row/latency bound (36 G lookups/s measured).
-// Phase A radix-partitions the canonical k-mers of a batch by the top 5 bits of their hash into 32
+// Phase A radix-partitions the canonical k-mers of a batch by the top 7 bits of their hash into 128
 // streams (8 bytes written + 8 read per lookup, fully coalesced); phase B probes one partition at a
-// time, whose 1/32 slice of the table (40 MB for 64 strains) stays L2 resident.
+// time, whose 1/128 slice of the table (10 MB for 64 strains) stays L2 resident.  (Round 1 used 32
+// partitions: ncu showed 84 % of the probes missing L2 - profiles/r2a_two_phase_ncu.txt - because the grid
+// straddles two partitions while it prefetches a third, and three 40 MB slices plus the entry streams
+// do not fit the part of the 126 MB L2 that data shared by both dies can use.)
 
-#define S2_PSTAGE 384          /* staged entries per (CTA, partition) and round: 3x the even share of 4096 windows */
+#define S2_PSTAGE 64           /* staged entries per (CTA, partition) and round: 2x the even share of 4096 windows (64 KB: 3 CTAs per SM) */
 
 struct S2PartView {
     uint64_t *pool;            // S2_NPART regions of region_cap entries
@@ -451,7 +454,7 @@ struct S2PartView {
 // the shared-memory stage of its partition (one shared atomic for the slot), then the CTA reserves room
 // in each partition's global region with ONE global atomic per partition and round and copies the stage
 // out in coalesced runs (about 1 KB each).  Skewed rounds that overflow a stage append straight to global.
-__global__ void __launch_bounds__(S2_THREADS, 2)
+__global__ void __launch_bounds__(S2_THREADS, 3)
 s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartView pv, unsigned long long *__restrict__ stats,
                     const S2DevBatch *__restrict__ dev)
 {
@@ -480,7 +483,7 @@ s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartV
             for (unsigned j = 0; j < 16; ++j) {
                 if (s2_window_valid(m0, m1, m2, j)) {
                     const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
-                    const uint32_t p = s2_hash(canon).h >> 27;
+                    const uint32_t p = s2_hash(canon).h >> (32 - S2_NPART_LOG2);
                     const uint32_t at = atomicAdd(&cnt[p], 1u);
                     ++n_valid;
                     if (at < S2_PSTAGE) {
@@ -499,7 +502,7 @@ s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartV
             gbase[threadIdx.x] = c ? atomicAdd(&pv.cursor[threadIdx.x], (unsigned long long)c) : 0ull;
         }
         __syncthreads();
-        for (int p = wid; p < S2_NPART; p += S2_WARPS) {          // each warp copies out four partitions
+        for (int p = wid; p < S2_NPART; p += S2_WARPS) {          // each warp copies out its share of the partitions
             const uint32_t c = min(cnt[p], (uint32_t)S2_PSTAGE);
             const unsigned long long g = gbase[p];
             if (g + c > pv.region_cap) { if (lane == 0 && c) atomicOr(pv.overflow, 1u); continue; }
@@ -542,8 +545,9 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
         const unsigned long long item = item_s;
         __syncthreads();
         if (item >= total) break;
-        int part = 0;
-        while (pre[part + 1] <= item) ++part;
+        int part = 0;                                             // largest part with pre[part] <= item < pre[part + 1]
+#pragma unroll
+        for (int step = S2_NPART / 2; step > 0; step >>= 1) if (pre[part + step] <= item) part += step;
         const uint64_t n = pv.cursor[part];
         const uint64_t off = (item - pre[part]) * S2_PITEM;
         const uint64_t *__restrict__ src = pv.pool + (uint64_t)part * pv.region_cap;
@@ -627,7 +631,7 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     cudaMemsetAsync(cursor, 0, S2_NPART * sizeof(unsigned long long), stream);
     cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
     S2PartView pv = { part_pool, region_cap, cursor, overflow };
-    s2_partition_kernel<<<n_sm * 2, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
+    s2_partition_kernel<<<n_sm * 3, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
     uint32_t *counts_col = t.counts + (uint64_t)col * t.n_slots;
     // buckets whose hash has top bits == p: [ceil(p * nb / 32), ceil((p+1) * nb / 32)); slice 0 is prefetched
     // by its own small kernel, every later slice by the items of the partition before it
@@ -980,6 +984,36 @@ void s2_launch_scatter_counts(const S2TableView &t, int col, const uint32_t *ran
                               const uint32_t *in, cudaStream_t stream)
 {
     if (n_keys) s2_scatter_kernel<<<blocks_for(n_keys, 256), 256, 0, stream>>>(t.counts + (uint64_t)col * t.n_slots, rank_slot, n_keys, in);
+}
+
+// The all-reduce of a counter column when ONE process drives all the GPUs (the executables): every GPU has gathered its
+// column into a dense first-occurrence-order vector (identical order on all replicas); this kernel, run on every GPU,
+// reads ALL replicas' vectors straight out of peer memory over NVLink (coalesced 128-bit loads), adds them with uint32
+// wrap-around and scatters the sums into its own column - collective and scatter in one pass, no communicator, no staging.
+__global__ void __launch_bounds__(256)
+s2_peer_sum_scatter_kernel(S2PeerVecs pv, uint32_t *__restrict__ counts_col, const uint32_t *__restrict__ rank_slot, uint64_t n_keys)
+{
+    const uint64_t n4 = n_keys / 4;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (int p = 0; p < pv.n; ++p) {
+            const uint4 v = __ldcv(reinterpret_cast<const uint4 *>(pv.v[p]) + i);       // peer memory: never from a stale cache line
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const uint4 s = *(reinterpret_cast<const uint4 *>(rank_slot) + i);
+        counts_col[s.x] = acc.x; counts_col[s.y] = acc.y; counts_col[s.z] = acc.z; counts_col[s.w] = acc.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n_keys & 3)) {
+        const uint64_t r = n4 * 4 + threadIdx.x;
+        uint32_t acc = 0;
+        for (int p = 0; p < pv.n; ++p) acc += __ldcv(pv.v[p] + r);
+        counts_col[rank_slot[r]] = acc;
+    }
+}
+
+void s2_launch_peer_sum_scatter(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys, const S2PeerVecs &pv, cudaStream_t stream)
+{
+    if (n_keys) s2_peer_sum_scatter_kernel<<<148 * 8, 256, 0, stream>>>(pv, t.counts + (uint64_t)col * t.n_slots, rank_slot, n_keys);
 }
 
 void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found, int set, cudaStream_t stream)

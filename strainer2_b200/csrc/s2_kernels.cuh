@@ -50,7 +50,8 @@ void s2_launch_scan_detect_dev(const uint8_t *bases, const S2DevBatch *dev, cons
                                unsigned long long *stats, int grid_blocks, cudaStream_t stream);
 int  s2_scan_blocks_per_sm(int mode);
 // two-phase (radix partition, then per-partition probe) count scan for tables larger than L2
-#define S2_NPART 32
+#define S2_NPART_LOG2 7
+#define S2_NPART (1 << S2_NPART_LOG2)
 void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, const S2TableView &t, int col,
                                       unsigned long long *stats, uint64_t *part_pool, uint64_t region_cap,
                                       unsigned long long *cursor, uint32_t *overflow, int n_sm, int grid_blocks,
@@ -74,6 +75,11 @@ void s2_launch_gather_counts(const S2TableView &t, int col, const uint32_t *rank
                              uint32_t *out, cudaStream_t stream);
 void s2_launch_scatter_counts(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys,
                               const uint32_t *in, cudaStream_t stream);
+// all-reduce over peer memory for a process that drives several GPUs: dense vectors of all replicas -> sum -> own column
+#define S2_MAX_PEERS 16
+struct S2PeerVecs { const uint32_t *v[S2_MAX_PEERS]; int n; };
+void s2_launch_peer_sum_scatter(const S2TableView &t, int col, const uint32_t *rank_slot, uint64_t n_keys, const S2PeerVecs &pv,
+                                cudaStream_t stream);
 void s2_launch_flag(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint8_t *found, int set,
                     cudaStream_t stream);
 void s2_launch_lookup(const S2TableView &t, const uint64_t *kmers, uint64_t n, uint32_t *slot_out,

@@ -67,6 +67,8 @@ struct s2_ctx {
     cudaEvent_t user_ev[4] = { nullptr, nullptr, nullptr, nullptr };
     // grow-only scratch of s2_scan_detect (no cudaMalloc per call)
     struct Scratch { void *p = nullptr; size_t cap = 0; } det[6];
+    // GPU ingest pipelines of this context (s2_ingest.cu): a small pool shared by all calling threads
+    void *ingest_pool = nullptr;
 };
 
 static inline int scratch_reserve(s2_ctx::Scratch &s, size_t bytes)
@@ -92,7 +94,7 @@ struct s2_table {
 };
 
 
-// s2_shutdown: the calling thread's ingest pipeline goes with its context (s2_ingest.cu)
+// s2_shutdown: the context's ingest pipelines go with it (s2_ingest.cu)
 void s2_ingest_ctx_closing(s2_ctx *c);
 
 // the count scan of one batch on one lane's stream (direct or two-phase), caller holds c->mu

@@ -669,6 +669,64 @@ def test_gpu_ingest_bgzf_and_plain_fastq_equal_host_reader(s2, ctx, tmp_path, mo
     ctx.ingest_reset()
 
 
+def test_gpu_ingest_streamed_bgzf_chunk_may_end_inside_a_member_header(s2, ctx, tmp_path, monkeypatch):
+    """a streamed BGZF file whose 1 MiB chunk ends 1..17 bytes into the next member's header (empty members are used as
+    padding to put a header exactly there): the walk must take that as an incomplete member and start the next chunk at
+    it, not hand the file back as "not BGZF" """
+    import struct
+    from strainer2_b200 import synth
+    _ingest_chunks(ctx, monkeypatch, (1, 8))
+    tmp = str(tmp_path)
+    strain, reads = _ingest_fixture(s2, tmp, 60_000)
+    data = synth.fastq_bytes(reads)
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    eof = synth.bgzf_bytes(b"")
+    assert len(eof) == 28
+    tested = 0
+    for k in (1, 5, 11, 17):                                            # bytes of the straddling header inside chunk 0
+        members, size, pos = [], 0, 0
+        while pos < len(data):
+            m = synth.bgzf_bytes(data[pos:pos + 65280])[:-28]
+            if size + len(m) > (1 << 20) - k and size <= (1 << 20) - k:
+                gap = (1 << 20) - k - size                              # pad with empty members up to 2^20 - k
+                if gap % 28:
+                    # shrink the previous member's text so that the gap becomes a multiple of 28 (try a few cuts)
+                    prev_pos = pos - 65280
+                    for cut in range(1, 4000):
+                        pm = synth.bgzf_bytes(data[prev_pos:pos - cut])[:-28]
+                        if ((1 << 20) - k - (size - len(members[-1]) + len(pm))) % 28 == 0:
+                            size += len(pm) - len(members[-1]); members[-1] = pm; pos -= cut
+                            break
+                    else:
+                        break
+                    gap = (1 << 20) - k - size
+                    m = synth.bgzf_bytes(data[pos:pos + 65280])[:-28]
+                members.extend([eof] * (gap // 28)); size += gap
+            members.append(m); size += len(m); pos += 65280
+        image = b"".join(members) + eof
+        import gzip
+        assert gzip.decompress(image) == data
+        # a member header really starts k bytes before the 1 MiB mark
+        off, starts = 0, set()
+        while off < len(image):
+            starts.add(off); off += struct.unpack_from("<H", image, off + 16)[0] + 1
+        if (1 << 20) - k not in starts:
+            continue
+        tested += 1
+        path = os.path.join(tmp, "straddle%d.fastq.gz" % k)
+        open(path, "wb").write(image)
+        t.clear_counts(1); t.clear_counts(2)
+        want = ctx.scan_count(t, s2.load_flat(path), 1)
+        rc, bases, lookups = ctx.ingest_count_file(t, path, 2)
+        st = ctx.sync()
+        assert rc == 0, "the file was handed back to the host reader"
+        assert bases == len(reads) * 150 and st.hits == want.hits
+        assert np.array_equal(t.counts(2), t.counts(1))
+    assert tested >= 2
+    t.free()
+    ctx.ingest_reset()
+
+
 def test_gpu_ingest_pipeline_follows_its_context(s2, ctx, tmp_path):
     """the calling thread's ingest pipeline belongs to one context: closing that context drops it, and a context
     made afterwards (possibly at the same address) gets a pipeline of its own with the same results"""
