@@ -335,7 +335,9 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     // ---- table from -r (GEN_hash_sequences_set_count_vec, default 1 / increment 1 / column 0 / 4 wide)
     std::vector<uint8_t> flat;
     const int load_rc = s2_load_flat(r_file, flat);
+    const auto t_loaded = std::chrono::steady_clock::now();
     join_all(starters);
+    const auto t_ctx = std::chrono::steady_clock::now();
     for (int g = 0; g < n_gpus; ++g) if (!ctxs[g]) return fail(start_errs[g].c_str());
     if (load_rc != 0) {
         fprintf(stderr, "could not read file %s GEN_hash_sequences_set_count_vec()\n", r_file);   // src/genome_compare.c:986
@@ -382,6 +384,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     }
     if (!open_error.empty()) return fail(open_error.c_str());
     if (!pool_ok) return fail(s2_last_error());
+    const auto t_scan_end = std::chrono::steady_clock::now();
     for (int k = 1; k < 4 && n_gpus > 1; ++k)                          // sum the replicas' counters over NVLink
         if (s2_tables_allreduce(tables.data(), n_gpus, k)) return fail(s2_last_error());
     const auto t_scanned = std::chrono::steady_clock::now();
@@ -444,6 +447,8 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         double kms = 0; uint64_t kl = 0;
         for (int g = 0; g < n_gpus; ++g) { double m = 0; uint64_t l = 0; s2_kernel_time(ctxs[g], &m, &l, 0); kms += m; kl += l; }
+        fprintf(stderr, "[s2] phases: read -r %.3fs | CUDA contexts up after %.3fs | table build %.3fs | scan %.3fs | all-reduce %.3fs | row order + format + write %.3fs\n",
+                sec(t_start, t_loaded), sec(t_start, t_ctx), sec(t_ctx, t_built), sec(t_built, t_scan_end), sec(t_scan_end, t_scanned), sec(t_scanned, t_done));
         fprintf(stderr, "[s2] gpus=%d keys=%llu build=%.3fs scan=%.3fs print=%.3fs bases=%llu lookups=%llu hits=%llu "
                         "kernel_ms=%.3f launches=%llu scan_Gbases_per_s=%.3f\n",
                 n_gpus, (unsigned long long)n, sec(t_start, t_built), sec(t_built, t_scanned), sec(t_scanned, t_done),

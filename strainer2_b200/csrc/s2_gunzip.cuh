@@ -1,0 +1,515 @@
+// s2_gunzip.cuh - chunk-parallel gunzip: ONE ordinary .gz stream decoded by many warps at once.
+//
+// What it replaces: zlib's gzread under the reference's parser (/root/reference/src/genome_compare.c:194-203,
+// src/strain_detect.c:417-433, src/kseq.h:68-101).  Every input the reference ships is an ordinary single-member .gz;
+// one DEFLATE stream is sequential, zlib inflates it at 0.3 GB/s of text per core, and the Blackwell decompression
+// engine cannot take it.  The scheme here is the published one of pugz / rapidgzip, laid out for warps:
+//
+//   1. the compressed bytes are cut into sub-chunks of fixed size.  The warp of sub-chunk i FINDS the first DEFLATE
+//      block that starts at or after its cut (32 lanes test 32 bit offsets at a time: block type, code counts, a
+//      complete code-length code; survivors get the whole header parsed and both Huffman codes checked for completeness)
+//      and DECODES from there to the first block boundary at or after the next cut.  It does not know the 32 KB of text
+//      before its start, so it writes 16-bit symbols: a byte, or 256 + the position inside that unknown window.
+//   2. a chain pass per file checks that every sub-chunk ended exactly where the next one started (a false block start -
+//      or a missed one - breaks the chain: the file is then NOT handled and goes to the host reader, nothing is guessed)
+//      and resolves the windows in order: window i = last 32 KB of text up to the end of sub-chunk i.
+//   3. a translate pass turns the 16-bit symbols into text with window i-1, all sub-chunks in parallel.
+//
+// The decoder itself is written for a warp: all 32 lanes run the same bit reader and the same table lookups (shared
+// memory broadcasts, no divergence), lane 0 stores literals, and a match is copied by all lanes at once (coalesced),
+// which is where a one-lane decoder spends most of its time.  Host code (lane 0 of 1) compiles from the same source:
+// tests/sim/gunzip_harness.cpp checks the whole scheme against zlib on the CPU.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define GZ_HD __host__ __device__
+#else
+#define GZ_HD
+#endif
+#if defined(__CUDA_ARCH__)
+#define GZ_SYNC() __syncwarp()
+#define GZ_UNROLL _Pragma("unroll")
+#else
+#define GZ_SYNC() do { } while (0)
+#define GZ_UNROLL
+#endif
+
+#define GZ_WINDOW 32768u
+#define GZ_LIT_ROOT 9
+#define GZ_DIST_ROOT 6
+#define GZ_PRE_ROOT 7
+#define GZ_LIT_ENTRIES 864u        /* zlib's bound for 286 symbols, 15 bits, root 9 is 852 */
+#define GZ_DIST_ENTRIES 608u       /* ... for 30 symbols, 15 bits, root 6: 592 */
+
+// table entry: value << 16 | flags | extra_bits << 4 | bits_to_consume
+#define GZ_F_LIT 0x100u            /* value = the byte */
+#define GZ_F_BASE 0x200u           /* value = base length / distance, extra_bits follow in the stream */
+#define GZ_F_EOB 0x400u
+#define GZ_F_SUB 0x800u            /* value = offset of a second-level table indexed by the next extra_bits bits */
+
+enum {
+    GZ_OK = 0,
+    GZ_FINAL = 1,                  // decoding ended with the stream's last block
+    GZ_ERR_INPUT = -1,             // ran past the end of the input
+    GZ_ERR_HEADER = -2,            // block type 3, stored LEN/NLEN mismatch, impossible code lengths
+    GZ_ERR_SYMBOL = -3,            // a bit pattern that is no code
+    GZ_ERR_DISTANCE = -4,          // a match reaches back further than the window (or before the start of the member)
+    GZ_ERR_OUTPUT = -5,            // the sub-chunk's symbol region is full
+    GZ_ERR_NOT_FOUND = -6,         // no block start within the search limit
+    GZ_ERR_TABLE = -7              // second-level tables do not fit (never for codes a DEFLATE stream can carry)
+};
+
+struct GzTables {                  // one per decoding warp (shared memory on the device)
+    uint32_t lit[GZ_LIT_ENTRIES];
+    uint32_t dist[GZ_DIST_ENTRIES];    // also: the code-length code's table, and scratch while `lit` is built
+    uint8_t lens[320];
+    uint8_t scratch[192];              // scratch while `dist` is built
+};
+
+// ------------------------------------------------------------------------------------------------
+// bit reader over 32-bit words (the input buffer is 4-byte aligned and padded with >= 8 zero bytes)
+// ------------------------------------------------------------------------------------------------
+struct GzBits {
+    const uint32_t *w;
+    uint64_t n_words;              // words that may be read
+    uint64_t wi;                   // words merged into buf so far; nextw = w[wi]
+    uint64_t buf;
+    uint32_t cnt;
+    uint32_t nextw;
+};
+
+GZ_HD inline uint32_t gz_word(const GzBits &b, uint64_t i) { return i < b.n_words ? b.w[i] : 0u; }
+
+GZ_HD inline void gz_bits_seek(GzBits &b, uint64_t bitpos)
+{
+    b.wi = bitpos >> 5;
+    b.buf = (uint64_t)gz_word(b, b.wi) >> (bitpos & 31u);
+    b.cnt = 32u - (uint32_t)(bitpos & 31u);
+    ++b.wi;
+    b.nextw = gz_word(b, b.wi);
+}
+GZ_HD inline uint64_t gz_bits_pos(const GzBits &b) { return b.wi * 32u - b.cnt; }
+// at least 32 valid bits afterwards
+GZ_HD inline void gz_refill(GzBits &b)
+{
+    if (b.cnt < 32u) {
+        b.buf |= (uint64_t)b.nextw << b.cnt;
+        b.cnt += 32u;
+        ++b.wi;
+        b.nextw = gz_word(b, b.wi);
+    }
+}
+GZ_HD inline uint32_t gz_take(GzBits &b, uint32_t k)          // k <= 32 bits, the caller has refilled
+{
+    const uint32_t v = (uint32_t)b.buf & (k >= 32u ? 0xFFFFFFFFu : ((1u << k) - 1u));
+    b.buf >>= k; b.cnt -= k;
+    return v;
+}
+
+GZ_HD inline uint32_t gz_bitrev(uint32_t v, int n)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32 - n);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+#endif
+}
+
+// RFC 1951 3.2.5: base value and extra bits of length symbol s (257..285 -> 0..28) / distance symbol d (0..29)
+GZ_HD inline uint32_t gz_len_entry(int s)
+{
+    if (s < 8) return (uint32_t)(3 + s) << 16 | GZ_F_BASE;
+    if (s == 28) return 258u << 16 | GZ_F_BASE;
+    const uint32_t e = (uint32_t)(s - 4) >> 2;
+    return (3u + ((4u + ((uint32_t)s & 3u)) << e)) << 16 | GZ_F_BASE | e << 4;
+}
+GZ_HD inline uint32_t gz_dist_entry(int d)
+{
+    if (d < 4) return (uint32_t)(1 + d) << 16 | GZ_F_BASE;
+    const uint32_t e = ((uint32_t)d >> 1) - 1u;
+    return (1u + ((2u + ((uint32_t)d & 1u)) << e)) << 16 | GZ_F_BASE | e << 4;
+}
+GZ_HD inline int gz_clen_order(int i)
+{
+    const uint64_t lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45 |
+                        11ull << 50 | 4ull << 55;
+    const uint64_t hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+    return (int)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// canonical Huffman code -> decoding table (root-bit first level + second-level tables for longer codes)
+// ------------------------------------------------------------------------------------------------
+// kind 0: literal/length alphabet, 1: distance alphabet, 2: code-length alphabet (value = symbol, flagged LIT).
+// Kraft sum of lens[0..n): returns 0 complete, 1 incomplete, -1 over-subscribed; *max_len = longest code
+GZ_HD inline int gz_kraft(const uint8_t *lens, int n, int *max_len, int *n_codes)
+{
+    uint32_t sum = 0;                      // in units of 2^-15
+    int mx = 0, nc = 0;
+    for (int s = 0; s < n; ++s) {
+        const int l = lens[s];
+        if (l) { sum += 32768u >> l; ++nc; if (l > mx) mx = l; }
+    }
+    *max_len = mx; *n_codes = nc;
+    return sum == 32768u ? 0 : sum < 32768u ? 1 : -1;
+}
+
+GZ_HD inline uint32_t gz_symbol_entry(int kind, int s)
+{
+    if (kind == 2) return (uint32_t)s << 16 | GZ_F_LIT;
+    if (kind == 1) return s < 30 ? gz_dist_entry(s) : 0u;
+    if (s < 256) return (uint32_t)s << 16 | GZ_F_LIT;
+    if (s == 256) return GZ_F_EOB;
+    return s < 286 ? gz_len_entry(s - 257) : 0u;          // 286 / 287 may have codes (fixed blocks) but may not occur
+}
+
+// tab[0..cap): built from lens[0..n).  scratch: (1 << root) + 2 * n bytes.  Returns 0, GZ_ERR_HEADER (over-subscribed),
+// GZ_ERR_TABLE.  Unused patterns of an incomplete code decode to an entry without flags (an error when met).
+GZ_HD inline int gz_build(uint32_t *tab, uint32_t cap, int root, int kind, const uint8_t *lens, int n, uint8_t *scratch, int lane, int nl)
+{
+    uint8_t *submax = scratch;                                      // per first-level prefix: longest code below it, minus root
+    uint16_t *code = reinterpret_cast<uint16_t *>(scratch + (1u << root));
+    const uint32_t rsize = 1u << root;
+    for (uint32_t i = (uint32_t)lane; i < cap; i += (uint32_t)nl) tab[i] = 0u;
+    for (uint32_t i = (uint32_t)lane; i < rsize; i += (uint32_t)nl) submax[i] = 0;
+    GZ_SYNC();
+    int rc = 0;
+    if (lane == 0) {
+        uint32_t count[16], next[16];
+        GZ_UNROLL
+        for (int l = 0; l < 16; ++l) count[l] = 0;
+        for (int s = 0; s < n; ++s) count[lens[s]]++;
+        uint32_t c = 0;
+        int left = 1;
+        count[0] = 0;
+        for (int l = 1; l < 16; ++l) {
+            c = (c + count[l - 1]) << 1;
+            next[l] = c;
+            left = (left << 1) - (int)count[l];
+            if (left < 0) rc = GZ_ERR_HEADER;
+        }
+        if (rc == 0)
+            for (int s = 0; s < n; ++s) {
+                const int l = lens[s];
+                if (!l) continue;
+                const uint32_t cd = next[l]++;
+                code[s] = (uint16_t)gz_bitrev(cd, l);
+                if (l > root) {
+                    const uint32_t prefix = code[s] & (rsize - 1u);
+                    if (submax[prefix] < l - root) submax[prefix] = (uint8_t)(l - root);
+                }
+            }
+        // second-level tables, in prefix order
+        uint32_t at = rsize;
+        for (uint32_t p = 0; p < rsize && rc == 0; ++p)
+            if (submax[p]) {
+                if (at + (1u << submax[p]) > cap) { rc = GZ_ERR_TABLE; break; }
+                tab[p] = at << 16 | GZ_F_SUB | (uint32_t)submax[p] << 4 | (uint32_t)root;
+                at += 1u << submax[p];
+            }
+    }
+    GZ_SYNC();
+#if defined(__CUDA_ARCH__)
+    rc = __shfl_sync(0xFFFFFFFFu, rc, 0);
+#endif
+    if (rc) return rc;
+    for (int s = lane; s < n; s += nl) {
+        const int l = lens[s];
+        if (!l) continue;
+        const uint32_t e = gz_symbol_entry(kind, s);
+        const uint32_t rev = code[s];
+        if (l <= root) {
+            for (uint32_t idx = rev; idx < rsize; idx += 1u << l) tab[idx] = e | (uint32_t)l;
+        } else {
+            const uint32_t sub = tab[rev & (rsize - 1u)];
+            const uint32_t off = sub >> 16, sb = (sub >> 4) & 15u;
+            for (uint32_t idx = rev >> root; idx < (1u << sb); idx += 1u << (l - root)) tab[off + idx] = e | (uint32_t)(l - root);
+        }
+    }
+    GZ_SYNC();
+    return 0;
+}
+
+// one symbol of a code: the entry, with its bits consumed (second-level lookup included).  At most 15 bits.
+GZ_HD inline uint32_t gz_decode_sym(GzBits &b, const uint32_t *tab, int root)
+{
+    uint32_t e = tab[(uint32_t)b.buf & ((1u << root) - 1u)];
+    if (e & GZ_F_SUB) {
+        b.buf >>= root; b.cnt -= (uint32_t)root;
+        e = tab[(e >> 16) + ((uint32_t)b.buf & ((1u << ((e >> 4) & 15u)) - 1u))];
+    }
+    const uint32_t nb = e & 15u;
+    b.buf >>= nb; b.cnt -= nb;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block header (the bit reader stands behind BFINAL / BTYPE) -> tables.  check_only: code lengths are read and
+// judged, no literal/length or distance table is built (the block finder).  strict: both codes must be complete
+// (what every zlib-family compressor writes); otherwise zlib's own rule (incomplete only as a single 1-bit code).
+// ------------------------------------------------------------------------------------------------
+GZ_HD inline int gz_dynamic_header(GzBits &b, GzTables &t, bool check_only, bool strict, int lane, int nl)
+{
+    gz_refill(b);
+    const int nlen = (int)gz_take(b, 5) + 257, ndist = (int)gz_take(b, 5) + 1, ncode = (int)gz_take(b, 4) + 4;
+    if (nlen > 286 || ndist > 30) return GZ_ERR_HEADER;
+    GZ_SYNC();
+    if (lane == 0) {
+        for (int i = 0; i < 19; ++i) t.lens[i] = 0;
+    }
+    GZ_SYNC();
+    for (int i = 0; i < ncode; ++i) {
+        gz_refill(b);
+        const uint32_t v = gz_take(b, 3);
+        if (lane == 0) t.lens[gz_clen_order(i)] = (uint8_t)v;
+    }
+    GZ_SYNC();
+    {
+        int mx, nc;
+        const int k = gz_kraft(t.lens, 19, &mx, &nc);
+        if (k < 0 || (k > 0 && (strict || mx != 1))) return GZ_ERR_HEADER;
+    }
+    // the code-length code lives in the distance table's storage (the build is done with lens[] before they are overwritten)
+    int rc = gz_build(t.dist, 1u << GZ_PRE_ROOT, GZ_PRE_ROOT, 2, t.lens, 19, reinterpret_cast<uint8_t *>(t.dist + 256), lane, nl);
+    if (rc) return rc;
+    int i = 0, prev = 0;
+    const int total = nlen + ndist;
+    while (i < total) {
+        gz_refill(b);
+        const uint32_t e = gz_decode_sym(b, t.dist, GZ_PRE_ROOT);
+        if (!(e & GZ_F_LIT)) return GZ_ERR_HEADER;
+        const int sym = (int)(e >> 16);
+        if (sym < 16) { if (lane == 0) t.lens[i] = (uint8_t)sym; prev = sym; ++i; continue; }
+        int rep, val = 0;
+        if (sym == 16) { if (i == 0) return GZ_ERR_HEADER; val = prev; rep = 3 + (int)gz_take(b, 2); }
+        else if (sym == 17) rep = 3 + (int)gz_take(b, 3);
+        else rep = 11 + (int)gz_take(b, 7);
+        if (i + rep > total) return GZ_ERR_HEADER;
+        for (int k = lane; k < rep; k += nl) t.lens[i + k] = (uint8_t)val;
+        i += rep; prev = val;
+    }
+    GZ_SYNC();
+    if (gz_bits_pos(b) > b.n_words * 32u) return GZ_ERR_INPUT;
+    if (t.lens[256] == 0) return GZ_ERR_HEADER;                         // no end-of-block code
+    int mx, nc;
+    int k = gz_kraft(t.lens, nlen, &mx, &nc);
+    if (k < 0 || (k > 0 && (strict || mx != 1))) return GZ_ERR_HEADER;
+    k = gz_kraft(t.lens + nlen, ndist, &mx, &nc);
+    if (k < 0 || (k > 0 && (strict || mx > 1))) return GZ_ERR_HEADER;   // zlib's rule: incomplete only as no code at all or a single 1-bit code
+    if (check_only) return 0;
+    // distance lengths move out of the way (lit's build uses dist[] as scratch), then lit, then dist
+    uint8_t *dl = t.scratch + 128;
+    GZ_SYNC();
+    for (int s = lane; s < ndist; s += nl) dl[s] = t.lens[nlen + s];
+    GZ_SYNC();
+    rc = gz_build(t.lit, GZ_LIT_ENTRIES, GZ_LIT_ROOT, 0, t.lens, nlen, reinterpret_cast<uint8_t *>(t.dist), lane, nl);
+    if (rc) return rc;
+    return gz_build(t.dist, GZ_DIST_ENTRIES, GZ_DIST_ROOT, 1, dl, ndist, t.scratch, lane, nl);
+}
+
+GZ_HD inline int gz_fixed_header(GzTables &t, int lane, int nl)
+{
+    GZ_SYNC();
+    for (int s = lane; s < 288; s += nl) t.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
+    uint8_t *dl = t.scratch + 128;
+    for (int s = lane; s < 30; s += nl) dl[s] = 5;
+    GZ_SYNC();
+    const int rc = gz_build(t.lit, GZ_LIT_ENTRIES, GZ_LIT_ROOT, 0, t.lens, 288, reinterpret_cast<uint8_t *>(t.dist), lane, nl);
+    if (rc) return rc;
+    return gz_build(t.dist, GZ_DIST_ENTRIES, GZ_DIST_ROOT, 1, dl, 30, t.scratch, lane, nl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode from a block start to the first block boundary at or after stop_bit (or the end of the stream)
+// ------------------------------------------------------------------------------------------------
+// out[0..cap): 16-bit symbols; window: how many bytes before out[0] a match may reach (32768 for a sub-chunk in the
+// middle of a stream, 0 at the start of a member).  Returns GZ_OK (stopped at a boundary: *end_bit), GZ_FINAL (the last
+// block ended at *end_bit) or an error.  *n_out = symbols written.
+GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_t cap, uint32_t window, uint64_t stop_bit,
+                                  uint32_t *n_out, uint64_t *end_bit, int lane, int nl)
+{
+    uint32_t o = 0;
+    int rc = GZ_OK;
+    for (;;) {
+        gz_refill(b);
+        // a sub-chunk ends at the first boundary at or after the next cut whose block is one the finder can see (not
+        // final, dynamic codes): final, stored and fixed-code blocks are decoded by whoever arrives at them
+        if (gz_bits_pos(b) >= stop_bit && ((uint32_t)b.buf & 7u) == 4u) break;
+        const uint32_t last = gz_take(b, 1), type = gz_take(b, 2);
+        if (type == 3) { rc = GZ_ERR_HEADER; break; }
+        if (type == 0) {
+            uint64_t pos = (gz_bits_pos(b) + 7u) & ~7ull;                 // stored: byte aligned LEN, ~LEN, bytes
+            gz_bits_seek(b, pos);
+            gz_refill(b);
+            const uint32_t len = gz_take(b, 16), nlen = gz_take(b, 16);
+            if ((len ^ 0xFFFFu) != nlen) { rc = GZ_ERR_HEADER; break; }
+            pos += 32;
+            if (pos + 8ull * len > b.n_words * 32u) { rc = GZ_ERR_INPUT; break; }
+            if (o + len > cap) { rc = GZ_ERR_OUTPUT; break; }
+            const uint8_t *bytes = reinterpret_cast<const uint8_t *>(b.w) + (pos >> 3);
+            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) out[o + i] = bytes[i];
+            o += len;
+            gz_bits_seek(b, pos + 8ull * len);
+        } else {
+            rc = type == 1 ? gz_fixed_header(t, lane, nl) : gz_dynamic_header(b, t, false, false, lane, nl);
+            if (rc) break;
+            for (;;) {
+                gz_refill(b);
+                const uint32_t e = gz_decode_sym(b, t.lit, GZ_LIT_ROOT);
+                if (e & GZ_F_LIT) {
+                    if (o >= cap) { rc = GZ_ERR_OUTPUT; break; }
+                    if (lane == 0) out[o] = (uint16_t)(e >> 16);
+                    ++o;
+                    continue;
+                }
+                if (!(e & GZ_F_BASE)) { if (!(e & GZ_F_EOB)) rc = GZ_ERR_SYMBOL; break; }
+                const uint32_t len = (e >> 16) + gz_take(b, (e >> 4) & 15u);
+                gz_refill(b);
+                const uint32_t d = gz_decode_sym(b, t.dist, GZ_DIST_ROOT);
+                if (!(d & GZ_F_BASE)) { rc = GZ_ERR_SYMBOL; break; }
+                const uint32_t dist = (d >> 16) + gz_take(b, (d >> 4) & 15u);
+                if (dist > o + window) { rc = GZ_ERR_DISTANCE; break; }
+                if (o + len > cap) { rc = GZ_ERR_OUTPUT; break; }
+                GZ_SYNC();                                               // the lanes' earlier stores, before anybody reads them
+                if (dist >= len) {
+                    for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) {
+                        const int64_t src = (int64_t)o - (int64_t)dist + (int64_t)i;
+                        out[o + i] = src >= 0 ? out[src] : (uint16_t)(256 + (int64_t)GZ_WINDOW + src);
+                    }
+                } else {                                                 // the match overlaps itself: a repeating pattern of `dist` symbols
+                    for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) {
+                        const int64_t src = (int64_t)o - (int64_t)dist + (int64_t)(i % dist);
+                        out[o + i] = src >= 0 ? out[src] : (uint16_t)(256 + (int64_t)GZ_WINDOW + src);
+                    }
+                }
+                o += len;
+            }
+            if (rc) break;
+            if (gz_bits_pos(b) > b.n_words * 32u) { rc = GZ_ERR_INPUT; break; }
+        }
+        if (last) { rc = GZ_FINAL; break; }
+    }
+    GZ_SYNC();
+    *n_out = o;
+    *end_bit = gz_bits_pos(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block finder: the first bit position >= from_bit (and < limit_bit) where a dynamic-code block plausibly starts
+// ------------------------------------------------------------------------------------------------
+// 96 bits of the stream starting at bit p
+GZ_HD inline void gz_peek96(const GzBits &b, uint64_t p, uint64_t *lo, uint32_t *hi)
+{
+    const uint64_t i = p >> 5;
+    const uint32_t s = (uint32_t)(p & 31u);
+    const uint64_t w0 = gz_word(b, i), w1 = gz_word(b, i + 1), w2 = gz_word(b, i + 2), w3 = gz_word(b, i + 3);
+    const uint64_t a = w0 | w1 << 32, c = w2 | w3 << 32;
+    *lo = s ? (a >> s) | (c << (64 - s)) : a;
+    *hi = (uint32_t)(c >> s);
+}
+
+// cheap test of one position: not-final dynamic block, sane code counts, complete code-length code
+GZ_HD inline bool gz_candidate(const GzBits &b, uint64_t p)
+{
+    uint64_t lo; uint32_t hi;
+    gz_peek96(b, p, &lo, &hi);
+    const uint32_t h = (uint32_t)lo;
+    if ((h & 7u) != 4u) return false;                                   // BFINAL = 0, BTYPE = 2
+    if (((h >> 3) & 31u) > 29u || ((h >> 8) & 31u) > 29u) return false;
+    const uint32_t ncode = ((h >> 13) & 15u) + 4u;
+    uint64_t bits = lo >> 17 | (uint64_t)hi << 47;                      // 3 bits per code length
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < ncode; ++i) {
+        const uint32_t l = (uint32_t)bits & 7u;
+        bits >>= 3;
+        sum += l ? 128u >> l : 0u;                                       // (19 x 3 = 57 bits: all inside `bits`)
+    }
+    return sum == 128u;
+}
+
+GZ_HD inline int gz_find_block(GzBits &b, GzTables &t, uint64_t from_bit, uint64_t limit_bit, uint64_t *found, int lane, int nl)
+{
+    for (uint64_t base = from_bit; base < limit_bit; base += (uint64_t)nl) {
+        const uint64_t p = base + (uint64_t)lane;
+        const bool cand = p < limit_bit && gz_candidate(b, p);
+#if defined(__CUDA_ARCH__)
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, cand);
+#else
+        uint32_t m = cand ? 1u : 0u;
+#endif
+        while (m) {                                                      // survivors in order, the whole warp on each
+#if defined(__CUDA_ARCH__)
+            const int k = __ffs(m) - 1;
+#else
+            const int k = 0;
+#endif
+            m &= m - 1u;
+            gz_bits_seek(b, base + (uint64_t)k + 3u);
+            if (gz_dynamic_header(b, t, true, true, lane, nl) == 0) { *found = base + (uint64_t)k; return 0; }
+        }
+    }
+    return GZ_ERR_NOT_FOUND;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one sub-chunk: find (unless the start is known) + decode
+// ------------------------------------------------------------------------------------------------
+struct GzSubResult {
+    uint64_t start_bit, end_bit;       // where decoding started / ended (bit offsets inside the file's bytes)
+    uint32_t n_out;
+    int32_t status;                    // GZ_OK / GZ_FINAL / error
+};
+
+// words/n_words: the FILE's compressed bytes (4-byte aligned, zero padded).  known_start: bit offset of the member's
+// first block for the sub-chunk that begins a member, else ~0.  cut_bit / next_cut_bit: this sub-chunk's and the next
+// one's cut.  search_limit_bits: how far past the cut the finder looks.
+GZ_HD inline void gz_subchunk(const uint32_t *words, uint64_t n_words, uint64_t known_start, uint64_t cut_bit, uint64_t next_cut_bit,
+                              uint64_t search_limit_bits, uint16_t *out, uint32_t cap, GzTables &t, GzSubResult *res, int lane, int nl)
+{
+    GzBits b;
+    b.w = words; b.n_words = n_words;
+    uint64_t start = known_start;
+    int rc = 0;
+    if (known_start == ~0ull) {
+        const uint64_t end_bits = n_words * 32u;
+        uint64_t limit = cut_bit + search_limit_bits;
+        if (limit > end_bits) limit = end_bits;
+        rc = gz_find_block(b, t, cut_bit, limit, &start, lane, nl);
+    }
+    uint32_t n_out = 0;
+    uint64_t end_bit = start;
+    if (rc == 0) {
+        gz_bits_seek(b, start);
+        rc = gz_decode_blocks(b, t, out, cap, known_start == ~0ull ? GZ_WINDOW : 0u, next_cut_bit, &n_out, &end_bit, lane, nl);
+    }
+    if (lane == 0) { res->start_bit = rc == GZ_ERR_NOT_FOUND ? ~0ull : start; res->end_bit = end_bit; res->n_out = n_out; res->status = rc; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain pass and translate pass (shared by the kernels and the host harness)
+// ------------------------------------------------------------------------------------------------
+// window after a sub-chunk = the last 32 KB of text up to its end: from its own symbols (markers resolved through the
+// previous window) and, where it produced fewer than 32 K symbols, the tail of the previous window
+GZ_HD inline void gz_next_window(const uint8_t *prev_win, const uint16_t *out, uint32_t n_out, uint8_t *next_win, uint32_t tid, uint32_t n_threads)
+{
+    for (uint32_t j = tid; j < GZ_WINDOW; j += n_threads) {
+        const int64_t k = (int64_t)n_out - (int64_t)GZ_WINDOW + (int64_t)j;
+        uint8_t v;
+        if (k >= 0) { const uint16_t sym = out[k]; v = sym < 256 ? (uint8_t)sym : prev_win[sym - 256]; }
+        else v = prev_win[(int64_t)GZ_WINDOW + k];
+        next_win[j] = v;
+    }
+}
+
+GZ_HD inline void gz_translate(const uint8_t *prev_win, const uint16_t *out, uint32_t n_out, uint8_t *text, uint32_t tid, uint32_t n_threads)
+{
+    for (uint32_t j = tid; j < n_out; j += n_threads) {
+        const uint16_t sym = out[j];
+        text[j] = sym < 256 ? (uint8_t)sym : prev_win[sym - 256];
+    }
+}
