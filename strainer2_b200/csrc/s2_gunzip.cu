@@ -1,0 +1,229 @@
+// s2_gunzip.cu - kernels around s2_gunzip.cuh: ordinary .gz files decoded on the GPU, many warps per stream.
+//
+// Replaces zlib's gzread under the reference's reader (/root/reference/src/genome_compare.c:194-203, src/kseq.h:68-101)
+// for single-member .gz inputs - the format of every file the reference ships (test/genomes_to_scrub.txt,
+// metagenomes_to_scrub.txt, target_metagenomes.txt) and of BASELINE config #3.  Three launches per batch of files:
+//
+//   gz_decode_kernel     one warp per sub-chunk of compressed bytes: find the first block start behind the cut, decode
+//                        to the first block start behind the next cut into 16-bit symbols (byte, or marker into the
+//                        unknown 32 KB window before the sub-chunk)
+//   gz_chain_kernel      one CTA per file, sub-chunks in order: every sub-chunk must start where its predecessor ended
+//                        (else the file is NOT handled: host reader), window i = last 32 KB of text up to sub-chunk i,
+//                        text offsets, the member's end (trailer, ISIZE, nothing behind it)
+//   gz_translate_kernel  symbols -> text through window i-1, all sub-chunks in parallel, straight into the ingest
+//                        pipeline's text buffer
+//   gz_crc_kernel        CRC-32 of every file's text against its trailer (slices in parallel, combined by
+//                        multiplication with x^(8 n) in GF(2)[x] / P)
+//
+// This is byte/bit work bounded by instruction issue (a Huffman symbol is a dependent chain of a shared-memory lookup,
+// shifts and a branch) - no tensor cores, little HBM traffic (5 bytes per byte of text).
+#include "s2_gunzip.h"
+#include "s2_gunzip.cuh"
+
+#define GZ_WARPS 4                       /* decoding warps per CTA: 4 x 6.4 KB of tables */
+#define GZ_CHAIN_THREADS 1024
+
+__global__ void __launch_bounds__(GZ_WARPS * 32)
+gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const uint32_t *__restrict__ sub_file, uint32_t n_sub,
+                 uint32_t sub_bytes, uint16_t *sym, uint32_t sub_cap, GzSubResult *res, uint64_t search_limit_bits)
+{
+    __shared__ GzTables tables[GZ_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t sub = blockIdx.x * GZ_WARPS + warp;
+    if (sub >= n_sub) return;
+    const GzFileDesc f = files[sub_file[sub]];
+    const uint32_t j = sub - f.sub0;                                            // sub-chunk j of its file
+    const uint64_t n_words = (f.comp_len + 3) / 4;
+    gz_subchunk(reinterpret_cast<const uint32_t *>(comp + f.comp_off), n_words, j == 0 ? f.first_bit : ~0ull, (uint64_t)j * sub_bytes * 8ull,
+                (uint64_t)(j + 1) * sub_bytes * 8ull, search_limit_bits, sym + (uint64_t)sub * sub_cap, sub_cap, tables[warp], res + sub, (int)lane, 32);
+}
+
+// one CTA per file
+__global__ void __launch_bounds__(GZ_CHAIN_THREADS)
+gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const uint16_t *__restrict__ sym, uint32_t sub_cap,
+                const GzSubResult *__restrict__ res, uint8_t *win, uint64_t *__restrict__ sub_off, GzFileResult *__restrict__ out)
+{
+    const GzFileDesc f = files[blockIdx.x];
+    __shared__ int s_state;                 // 0 going on, 1 the stream ended, < 0 error
+    __shared__ uint64_t s_cur, s_total;
+    __shared__ uint32_t s_len;
+    if (threadIdx.x == 0) { s_state = 0; s_cur = f.first_bit; s_total = 0; }
+    __syncthreads();
+    uint8_t *w0 = win + ((uint64_t)f.sub0 + blockIdx.x) * GZ_WINDOW;          // n_sub + 1 windows of this file
+    for (uint32_t j = 0; j < f.n_sub; ++j) {
+        const uint32_t sub = f.sub0 + j;
+        if (threadIdx.x == 0) {
+            s_len = 0;
+            sub_off[sub] = s_total;
+            if (s_state == 0) {
+                const GzSubResult r = res[sub];
+                if (r.start_bit != s_cur) s_state = GZ_CHAIN_BROKEN;
+                else if (r.status < 0) s_state = r.status;
+                else {
+                    s_len = r.n_out; s_total += r.n_out; s_cur = r.end_bit;
+                    if (r.status == GZ_FINAL) s_state = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_state < 0) break;
+        const uint32_t len = s_len;
+        // (after the end of the stream nothing more is decoded: later sub-chunks keep length 0 and need no window)
+        if (len || s_state == 0) gz_next_window(w0 + (uint64_t)j * GZ_WINDOW, sym + (uint64_t)sub * sub_cap, len, w0 + (uint64_t)(j + 1) * GZ_WINDOW, threadIdx.x, GZ_CHAIN_THREADS);
+        __threadfence_block();
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        GzFileResult r;
+        r.text_len = s_total; r.status = s_state == 1 ? 0 : (s_state == 0 ? GZ_STREAM_OPEN : s_state); r.crc = 0; r.crc_ok = 0;
+        if (s_state == 1) {                                                     // trailer: CRC-32, ISIZE; nothing but zeros behind it
+            const uint64_t tr = (s_cur + 7) / 8;
+            const uint8_t *p = comp + f.comp_off;
+            if (tr + 8 > f.comp_len) r.status = GZ_ERR_INPUT;
+            else {
+                const uint32_t isize = (uint32_t)p[tr + 4] | (uint32_t)p[tr + 5] << 8 | (uint32_t)p[tr + 6] << 16 | (uint32_t)p[tr + 7] << 24;
+                r.crc = (uint32_t)p[tr] | (uint32_t)p[tr + 1] << 8 | (uint32_t)p[tr + 2] << 16 | (uint32_t)p[tr + 3] << 24;
+                if (isize != (uint32_t)s_total || s_total != f.text_len) r.status = GZ_SIZE_MISMATCH;
+                for (uint64_t i = tr + 8; i < f.comp_len && r.status == 0; ++i) if (p[i]) r.status = GZ_TRAILING_BYTES;     // another member, or junk: host reader
+            }
+        }
+        out[blockIdx.x] = r;
+    }
+}
+
+// symbols -> text.  One CTA per sub-chunk; files whose chain failed are skipped (their text area stays unwritten and the
+// pipeline's act != isz check vetoes the chunk).
+__global__ void __launch_bounds__(256)
+gz_translate_kernel(const GzFileDesc *__restrict__ files, const uint32_t *__restrict__ sub_file, uint32_t sub_lo,
+                    const uint16_t *__restrict__ sym, uint32_t sub_cap, const uint8_t *__restrict__ win,
+                    const uint64_t *__restrict__ sub_off, const GzFileResult *__restrict__ fres, uint8_t *text)
+{
+    const uint32_t sub = sub_lo + blockIdx.x;
+    const uint32_t fi = sub_file[sub];
+    const GzFileDesc f = files[fi];
+    const GzFileResult fr = fres[fi];
+    if (fr.status != 0) return;
+    const uint32_t j = sub - f.sub0;
+    const uint64_t off = sub_off[sub];
+    const uint64_t next = j + 1 < f.n_sub ? sub_off[sub + 1] : fr.text_len;
+    const uint32_t n = (uint32_t)(next - off);                                  // 0 behind the end of the stream
+    gz_translate(win + ((uint64_t)sub + fi) * GZ_WINDOW, sym + (uint64_t)sub * sub_cap, n, text + f.text_off + off, threadIdx.x, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CRC-32 (the gzip trailer's, reflected polynomial 0xEDB88320) of every file's text, in parallel
+// ------------------------------------------------------------------------------------------------
+// In the reflected representation bit 31 of a register is the coefficient of x^0.  a * b mod P:
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+        if (a & 0x80000000u) r ^= b;                    // coefficient of x^i in a
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);   // b *= x
+    }
+    return r;
+}
+// x^(8 n) mod P by square and multiply
+__device__ __forceinline__ uint32_t crc_xpow8(uint64_t n)
+{
+    uint32_t r = 0x80000000u;                           // 1
+    uint32_t sq = 0x00800000u;                          // x^8
+    while (n) {
+        if (n & 1u) r = crc_mulmod(r, sq);
+        sq = crc_mulmod(sq, sq);
+        n >>= 1;
+    }
+    return r;
+}
+
+#define GZ_CRC_SLICE 4096u
+// one warp per 4 KB slice of a file's text, 128 bytes per lane: the remainder of each piece (byte-wise table), moved to its
+// place by a multiplication with x^(8 x bytes behind it), XORed into the file's accumulator (the CRC is linear)
+__global__ void __launch_bounds__(256)
+gz_crc_kernel(const GzFileDesc *__restrict__ files, uint32_t file0, uint32_t n_files, const uint32_t *__restrict__ file_slice0, uint32_t n_slices,
+              const uint8_t *__restrict__ text, const GzFileResult *__restrict__ fres, uint32_t *crc_acc)
+{
+    __shared__ uint32_t table[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+        table[i] = c;
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slice >= n_slices) return;                                             // (whole warps)
+    uint32_t lo = 0, hi = n_files;                                             // file of this slice: last f with file_slice0[f] <= slice
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (file_slice0[mid] <= slice) lo = mid; else hi = mid; }
+    const GzFileDesc f = files[file0 + lo];
+    const GzFileResult fr = fres[file0 + lo];
+    if (fr.status != 0) return;                                                // (the same for every lane of the warp)
+    const uint64_t len = fr.text_len;
+    const uint64_t s0 = (uint64_t)(slice - file_slice0[lo]) * GZ_CRC_SLICE + (uint64_t)lane * (GZ_CRC_SLICE / 32);
+    uint32_t c = 0;
+    if (s0 < len) {
+        const uint64_t s1 = s0 + GZ_CRC_SLICE / 32 < len ? s0 + GZ_CRC_SLICE / 32 : len;
+        const uint8_t *p = text + f.text_off;
+        for (uint64_t i = s0; i < s1; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+        c = crc_mulmod(c, crc_xpow8(len - s1));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if (lane == 0 && c) atomicXor(&crc_acc[file0 + lo], c);
+}
+
+// the conditioning (initial value ~0, final complement) as one more term, the comparison with the trailer, and what the
+// ingest pipeline's act == isz check will see for the file
+__global__ void gz_crc_finish_kernel(uint32_t file0, uint32_t n_files, GzFileResult *fres, uint32_t *crc_acc, unsigned *act)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_files) return;
+    GzFileResult r = fres[file0 + i];
+    if (r.status == 0) {
+        // crc(M) = rem(M) ^ rem(0xFFFFFFFF . x^(8 len)) ^ 0xFFFFFFFF
+        const uint32_t got = crc_acc[file0 + i] ^ crc_mulmod(0xFFFFFFFFu, crc_xpow8(r.text_len)) ^ 0xFFFFFFFFu;
+        r.crc_ok = got == r.crc ? 1u : 0u;
+        if (!r.crc_ok) r.status = GZ_CRC_MISMATCH;
+        fres[file0 + i] = r;
+    }
+    crc_acc[file0 + i] = 0;
+    act[i] = r.status == 0 ? (unsigned)r.text_len : 0xFFFFFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+size_t gz_tables_bytes(void) { return sizeof(GzTables); }
+
+void gz_launch_decode(const uint8_t *comp, const GzFileDesc *files, const uint32_t *sub_file, uint32_t n_sub, uint32_t sub_bytes, uint16_t *sym,
+                      uint32_t sub_cap, GzSubResult *res, cudaStream_t st)
+{
+    if (!n_sub) return;
+    gz_decode_kernel<<<(n_sub + GZ_WARPS - 1) / GZ_WARPS, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
+}
+
+void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint16_t *sym, uint32_t sub_cap, const GzSubResult *res,
+                     uint8_t *win, uint64_t *sub_off, GzFileResult *fres, cudaStream_t st)
+{
+    if (!n_files) return;
+    gz_chain_kernel<<<n_files, GZ_CHAIN_THREADS, 0, st>>>(comp, files, sym, sub_cap, res, win, sub_off, fres);
+}
+
+size_t gz_sub_result_bytes(void) { return sizeof(GzSubResult); }
+
+void gz_launch_translate(const GzFileDesc *files, const uint32_t *sub_file, uint32_t sub_lo, uint32_t sub_hi, const uint16_t *sym, uint32_t sub_cap,
+                         const uint8_t *win, const uint64_t *sub_off, const GzFileResult *fres, uint8_t *text, cudaStream_t st)
+{
+    if (sub_hi <= sub_lo) return;
+    gz_translate_kernel<<<sub_hi - sub_lo, 256, 0, st>>>(files, sub_file, sub_lo, sym, sub_cap, win, sub_off, fres, text);
+}
+
+void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, const uint32_t *file_slice0, uint32_t n_slices, const uint8_t *text,
+                   GzFileResult *fres, uint32_t *crc_acc, unsigned *act, cudaStream_t st)
+{
+    if (!n_files) return;
+    if (n_slices) gz_crc_kernel<<<(n_slices + 7) / 8, 256, 0, st>>>(files, file0, n_files, file_slice0, n_slices, text, fres, crc_acc);
+    gz_crc_finish_kernel<<<(n_files + 127) / 128, 128, 0, st>>>(file0, n_files, fres, crc_acc, act);
+}

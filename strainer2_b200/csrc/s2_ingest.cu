@@ -36,6 +36,7 @@
 #include "s2_private.h"
 #include "s2_kmer.cuh"
 #include "s2_inflate.cuh"
+#include "s2_gunzip.h"
 
 #include <cuda.h>
 #include <fcntl.h>
@@ -679,26 +680,29 @@ typedef CUresult (*devattr_fn)(int *, CUdevice_attribute, CUdevice);
 enum { ING_COUNT = 1, ING_DETECT = 2 };
 
 #define ING_SLOTS 3
-// ---- ordinary .gz: software gunzip of the files of a group (S2_GPU_GUNZIP=1; UNVALIDATED ON A GPU IN THIS FORM) --------
-// The hardware engine cannot take ordinary single-member .gz (DESIGN 4.4 "Damaged data"), so those files are decoded by
-// s2_inflate.cuh: one warp per file, lane 0 decodes, the tables of the warp's decoder in shared memory.  To the rest of the
-// pipeline a gz group looks like a BGZF chunk whose "blocks" are whole files: isz[f] = the file's ISIZE, act[f] = the bytes
-// the decoder produced (all ones on any error), so ing_check_chunk's act == isz test vetoes the scan exactly as it does
-// for a damaged BGZF member.  Off by default until it has been through the GPU tests.
-#define ING_GZ_WARPS 4
-__global__ void __launch_bounds__(ING_GZ_WARPS * 32) ing_gunzip_files(const uint8_t *__restrict__ comp, const ull *__restrict__ comp_off,
-                                                                      uint8_t *text, const ull *__restrict__ file_end,
-                                                                      const unsigned *__restrict__ isz, unsigned *act, unsigned n_files)
-{
-    __shared__ S2InfTables tables[ING_GZ_WARPS];
-    const unsigned warp = threadIdx.x >> 5;
-    const unsigned f = blockIdx.x * ING_GZ_WARPS + warp;
-    if (f >= n_files || (threadIdx.x & 31u)) return;
-    const ull t_begin = f ? file_end[f - 1] : 0;
-    uint64_t got = 0;
-    const int rc = s2_gunzip(comp + comp_off[f], comp_off[f + 1] - comp_off[f], text + ING_MAXCARRY + t_begin, isz[f], &got, tables[warp]);
-    act[f] = rc == S2I_OK ? (unsigned)got : 0xFFFFFFFFu;
-}
+// ---- ordinary .gz (single-member gzip: what the reference's own inputs are) -------------------------------------------
+// The hardware engine cannot take it (DESIGN 4.4 "Damaged data"), so those files go through the chunk-parallel software
+// gunzip of s2_gunzip.cu: a BATCH of whole files (up to S2_GZ_BATCH_MB of compressed bytes) is copied to the device and
+// decoded by one launch - one warp per S2_GZ_SUB_KB of compressed bytes, thousands of warps - then chained per file; the
+// files' texts are then translated straight into the text buffers of ordinary pipeline chunks (groups of whole files),
+// CRC-checked, and from there on a gz group is a BGZF group whose "blocks" are whole files: isz[f] = ISIZE as the host read
+// it, act[f] = what the file inflated to (all ones on any doubt: chain broken, size or CRC-32 mismatch, a second member),
+// so ing_check_chunk's act == isz test vetoes the scan exactly as it does for a damaged BGZF member.
+struct GzStage {
+    size_t comp_cap = 0;
+    uint32_t sub_bytes = 0, sub_cap = 0, max_sub = 0, max_files = 0;
+    uint8_t *h_comp = nullptr, *d_comp = nullptr;
+    uint16_t *d_sym = nullptr;
+    GzSubResult *d_res = nullptr;
+    uint8_t *d_win = nullptr;
+    uint64_t *d_sub_off = nullptr;
+    GzFileDesc *h_files = nullptr, *d_files = nullptr;
+    uint32_t *h_sub_file = nullptr, *d_sub_file = nullptr, *h_slice0 = nullptr, *d_slice0 = nullptr;
+    GzFileResult *d_fres = nullptr;
+    uint32_t *d_crc_acc = nullptr;
+    cudaEvent_t idle = nullptr;          // inflate stream: the last chunk of the previous batch has been translated
+    bool used = false;
+};
 
 struct IngSlot {                       // a chunk travels through one slot of the ring: copy engine -> decompression engine -> kernels
     uint8_t *h_comp = nullptr;         // pinned staging for file sources (allocated on first use)
@@ -737,6 +741,7 @@ struct s2_ingest {
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
     int grid_scan = 0;                   // CTAs of the count scan launched from this pipeline
+    GzStage gz;                          // ordinary .gz batches (allocated on first use)
     // detect mode: chunk-local and file-level result arrays
     unsigned *d_hits_c = nullptr, *d_inf_c = nullptr;
     ull *d_rec_off = nullptr, *d_pos_c = nullptr, *d_cnt_c = nullptr, *d_fcnt = nullptr;
@@ -758,6 +763,13 @@ static void ingest_free(s2_ingest *g)
         if (s.inflated) cudaEventDestroy(s.inflated);
         if (s.consumed) cudaEventDestroy(s.consumed);
     }
+    {
+        GzStage &z = g->gz;
+        cudaFreeHost(z.h_comp); cudaFree(z.d_comp); cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_sub_off);
+        cudaFreeHost(z.h_files); cudaFree(z.d_files); cudaFreeHost(z.h_sub_file); cudaFree(z.d_sub_file); cudaFreeHost(z.h_slice0); cudaFree(z.d_slice0);
+        cudaFree(z.d_fres); cudaFree(z.d_crc_acc);
+        if (z.idle) cudaEventDestroy(z.idle);
+    }
     cudaFree(g->d_flat);
     cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end); cudaFree(g->d_masks); cudaFree(g->d_tickets);
     cudaFree(g->part_pool); cudaFree(g->part_cursor); cudaFree(g->part_overflow);
@@ -769,10 +781,6 @@ static void ingest_free(s2_ingest *g)
 }
 
 #define ING_META_BYTES ((size_t)ING_MAX_FILES * 8 + (size_t)ING_MAX_DBLOCKS * 4)
-// a gz group uses isz[0..n_files) only; the files' offsets into d_comp (ull x (n_files + 1)) sit in the second half of that area
-#define ING_META_GZ_OFF ((size_t)ING_MAX_FILES * 8 + (size_t)ING_MAX_DBLOCKS * 2)
-static_assert((size_t)ING_MAX_FILES * 4 <= (size_t)ING_MAX_DBLOCKS * 2 && ((size_t)ING_MAX_FILES + 1) * 8 <= (size_t)ING_MAX_DBLOCKS * 2, "gz meta fits");
-
 static int ingest_init(s2_ingest *g, s2_ctx *c)
 {
     g->ctx = c; g->device = c->device;
@@ -938,7 +946,7 @@ static void ingest_classify(IngSource &src)
     uint8_t head[32];
     const ssize_t hn = src.peek(head, sizeof head, 0);
     src.bgzf = is_bgzf_header(head, hn);
-    src.gz = !src.bgzf && hn >= 18 && head[0] == 0x1f && head[1] == 0x8b && head[2] == 8 && s2_env_int("S2_GPU_GUNZIP", 0) != 0;
+    src.gz = !src.bgzf && hn >= 18 && head[0] == 0x1f && head[1] == 0x8b && head[2] == 8 && s2_env_int("S2_GPU_GUNZIP", 1) != 0;
     if (src.gz) {
         uint8_t tail[4];
         const ssize_t size = src.size();
@@ -989,6 +997,8 @@ static inline double ing_now() { return std::chrono::duration<double, std::micro
 // else wait for one
 static s2_ingest *ingest_acquire(s2_ctx *c)
 {
+    // pipelines are shared by threads: the calling thread's current device may be another context's
+    if (cudaSetDevice(c->device) != cudaSuccess) { s2_set_error("cannot select device %d", c->device); return nullptr; }
     IngPool *pool = ingest_pool(c);
     for (int round = 0; round < 2; ++round) {
         std::lock_guard<std::mutex> lk(pool->mu);
@@ -1011,6 +1021,7 @@ static s2_ingest *ingest_acquire(s2_ctx *c)
 // pipeline is 350 MB of device memory and, for file sources, 48 MB of pinned staging - tens of milliseconds each)
 extern "C" int s2_ingest_warm(s2_ctx *c, int n_pipes)
 {
+    CK(cudaSetDevice(c->device));
     IngPool *pool = ingest_pool(c);
     std::lock_guard<std::mutex> lk(pool->mu);
     while (pool->pipes.size() < std::min<size_t>((size_t)std::max(n_pipes, 0), pool->max_pipes)) {
@@ -1057,7 +1068,8 @@ struct IngChunk {
     size_t text_len = 0;
     bool first = true, last = true;
     unsigned n_files = 0;         // > 0: a group of whole files (their ends are in the slot's meta)
-    bool gz = false;              // the group's files are ordinary .gz: decoded by ing_gunzip_files
+    bool gz = false;              // the group's files are ordinary .gz, decoded by the pipeline's gz stage: its files [gz_file0, +n_files)
+    uint32_t gz_file0 = 0, gz_sub_lo = 0, gz_sub_hi = 0, gz_slice0 = 0, gz_slices = 0;      // and their sub-chunks / CRC slices
 };
 
 // wait until the slot's previous chunk has left d_comp / params / meta, and return the slot
@@ -1143,7 +1155,6 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     const size_t n_db = bgzf ? s.params.size() : ch.gz ? (size_t)ch.n_files : 0;
     if (ch.n_files) CK(cudaMemcpyAsync(s.d_meta, s.h_meta, (size_t)ch.n_files * 8, cudaMemcpyHostToDevice, g->copy_stream));
     if (n_db) CK(cudaMemcpyAsync(s.d_meta + (size_t)ING_MAX_FILES * 8, s.h_meta + (size_t)ING_MAX_FILES * 8, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
-    if (ch.gz) CK(cudaMemcpyAsync(s.d_meta + ING_META_GZ_OFF, s.h_meta + ING_META_GZ_OFF, ((size_t)ch.n_files + 1) * 8, cudaMemcpyHostToDevice, g->copy_stream));
     tr_record(1, g->copy_stream);
     if (tr_on && !tr_events.empty()) { tr_events.back().comp = ch.comp_len; tr_events.back().text = ch.text_len; }
     CK(cudaEventRecord(s.h2d_done, g->copy_stream));
@@ -1158,9 +1169,12 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
             if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, i + err_index); return -1; }
         }
     } else if (ch.gz) {
-        ing_gunzip_files<<<(ch.n_files + ING_GZ_WARPS - 1) / ING_GZ_WARPS, ING_GZ_WARPS * 32, 0, g->inflate_stream>>>(
-            s.d_comp, (const ull *)(s.d_meta + ING_META_GZ_OFF), s.d_text, (const ull *)s.d_meta, (const unsigned *)(s.d_meta + (size_t)ING_MAX_FILES * 8), s.d_act,
-            ch.n_files);
+        // the batch was decoded and chained on this stream already: symbols -> text of this chunk's files, then their CRC-32
+        GzStage &z = g->gz;
+        gz_launch_translate(z.d_files, z.d_sub_file, ch.gz_sub_lo, ch.gz_sub_hi, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres,
+                            s.d_text + ING_MAXCARRY, g->inflate_stream);
+        gz_launch_crc(z.d_files, ch.gz_file0, ch.n_files, z.d_slice0 + ch.gz_slice0, ch.gz_slices, s.d_text + ING_MAXCARRY, z.d_fres, z.d_crc_acc, s.d_act,
+                      g->inflate_stream);
     } else if (ch.comp_len) {
         CK(cudaMemcpyAsync(s.d_text + ING_MAXCARRY, s.d_comp, ch.comp_len, cudaMemcpyDeviceToDevice, g->inflate_stream));
     }
@@ -1317,7 +1331,8 @@ struct s2_ingest_job {
     IngSlot *s = nullptr;
     IngGroup cur;
     IngChunk ch;
-    bool cur_fasta = false, cur_bgzf = false, cur_gz = false;
+    bool cur_fasta = false, cur_bgzf = false;
+    std::vector<int> gz_list;                       // ordinary .gz sources: decoded in batches by the pipeline's gz stage (gz_run)
     struct { const uint8_t *h = nullptr; size_t d_off = 0, len = 0; } pend;     // host -> device copies of neighbouring sources are merged
 
     ~s2_ingest_job()
@@ -1345,7 +1360,7 @@ struct s2_ingest_job {
     {
         if (!s || cur.members.empty()) return 0;
         if (push_copy()) return -1;
-        ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size(); ch.gz = cur_gz;
+        ch.first = true; ch.last = true; ch.n_files = (unsigned)cur.members.size(); ch.gz = false;
         cur.result = g->res_seq;
         if (ingest_enqueue(g, t, *s, ch, cur_bgzf, cur_fasta, ING_COUNT, col, 1u, true)) return -1;
         groups.push_back(cur);
@@ -1370,24 +1385,159 @@ struct s2_ingest_job {
         groups.clear();
         return 0;
     }
+    // ---- ordinary .gz sources: batches through the gz stage, then ordinary groups of whole files ---------------------
+    int gz_stage_init()
+    {
+        GzStage &z = g->gz;
+        if (z.d_comp) return 0;
+        z.comp_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_BATCH_MB", 128), 1), 2048) << 20;
+        z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 32), 4), 4096) << 10;
+        // symbols one sub-chunk may produce: S2_GZ_RATIO x its compressed bytes (FASTQ deflates 4-6 : 1, FASTA 3.5 : 1) plus the
+        // run-on to the first block boundary behind the next cut; a sub-chunk that needs more makes its file the host reader's
+        z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 10), 2), 64) + (192u << 10);
+        z.max_files = ING_MAX_FILES;
+        z.max_sub = (uint32_t)(z.comp_cap / z.sub_bytes) + z.max_files;
+        CK(cudaMalloc((void **)&z.d_comp, z.comp_cap + (size_t)z.max_files * 32 + 256));
+        CK(cudaMalloc((void **)&z.d_sym, (size_t)z.max_sub * z.sub_cap * sizeof(uint16_t)));
+        CK(cudaMalloc((void **)&z.d_res, (size_t)z.max_sub * gz_sub_result_bytes()));
+        CK(cudaMalloc((void **)&z.d_win, ((size_t)z.max_sub + z.max_files + 1) * 32768));
+        CK(cudaMemset(z.d_win, 0, ((size_t)z.max_sub + z.max_files + 1) * 32768));
+        CK(cudaMalloc((void **)&z.d_sub_off, (size_t)z.max_sub * sizeof(uint64_t)));
+        CK(cudaHostAlloc((void **)&z.h_files, (size_t)z.max_files * sizeof(GzFileDesc), cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&z.d_files, (size_t)z.max_files * sizeof(GzFileDesc)));
+        CK(cudaHostAlloc((void **)&z.h_sub_file, (size_t)z.max_sub * sizeof(uint32_t), cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&z.d_sub_file, (size_t)z.max_sub * sizeof(uint32_t)));
+        CK(cudaHostAlloc((void **)&z.h_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t), cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&z.d_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&z.d_fres, (size_t)z.max_files * sizeof(GzFileResult)));
+        CK(cudaMalloc((void **)&z.d_crc_acc, (size_t)z.max_files * sizeof(uint32_t)));
+        CK(cudaMemset(z.d_crc_acc, 0, (size_t)z.max_files * sizeof(uint32_t)));
+        CK(cudaEventCreateWithFlags(&z.idle, cudaEventDisableTiming));
+        return 0;
+    }
+    // the listed sources (all ordinary .gz, classified).  Files that cannot go this way (larger than a batch or than a
+    // chunk's text, no readable gzip header) are left to the host reader (rc stays 1).  Returns 0 / -1.
+    int gz_run(const std::vector<int> &list)
+    {
+        if (flush()) return -1;                                     // the group being assembled goes first
+        if (gz_stage_init()) return -1;
+        GzStage &z = g->gz;
+        size_t at = 0;
+        while (at < list.size()) {
+            // ---- plan one batch: files [at, end) ------------------------------------------------------------------------
+            size_t comp_used = 0, end = at;
+            uint32_t n_sub = 0, n_files = 0;
+            std::vector<int> members;
+            for (; end < list.size(); ++end) {
+                IngSource &src = srcs[list[end]];
+                const ssize_t size = src.size();
+                const uint32_t subs = size > 0 ? (uint32_t)(((size_t)size + z.sub_bytes - 1) / z.sub_bytes) : 0;
+                if (size < 18 || (size_t)size > z.comp_cap || (size_t)src.gz_isize > g->text_cap) { rc[list[end]] = 1; continue; }     // host reader
+                const size_t need = ((size_t)size + 15) / 16 * 16 + 16;
+                if (n_files && (comp_used + need > z.comp_cap || n_sub + subs > z.max_sub || n_files + 1 > z.max_files)) break;
+                comp_used += need; n_sub += subs; ++n_files;
+                members.push_back(list[end]);
+            }
+            at = end;
+            if (members.empty()) continue;
+            // ---- bytes: caller's memory goes straight to the device, files through the stage's pinned buffer ----------
+            CK(cudaEventSynchronize(z.idle));                       // the previous batch is out of the stage's buffers
+            if (!srcs[members[0]].mem && !z.h_comp) CK(cudaHostAlloc((void **)&z.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
+            CK(cudaMemsetAsync(z.d_comp, 0, comp_used + 64, g->copy_stream));              // zero padding behind every file
+            size_t off = 0;
+            uint32_t sub0 = 0, nf = 0;
+            std::vector<int> good;
+            for (int i : members) {
+                IngSource &src = srcs[i];
+                const size_t size = (size_t)src.size();
+                const uint8_t *h = src.mem;
+                if (!src.mem) {
+                    if (pread(src.fd, z.h_comp + off, size, 0) != (ssize_t)size) { s2_set_error("read failed"); return -1; }
+                    memset(z.h_comp + off + size, 0, (size + 15) / 16 * 16 + 16 - size);
+                    h = z.h_comp + off;
+                }
+                const uint64_t hl = s2_gzip_header_len(h, size);
+                if (!hl) { rc[i] = 1; continue; }                   // not a gzip member after all
+                const uint32_t subs = (uint32_t)((size + z.sub_bytes - 1) / z.sub_bytes);
+                GzFileDesc &d = z.h_files[nf];
+                d.comp_off = off; d.comp_len = size; d.first_bit = hl * 8; d.text_off = 0; d.text_len = src.gz_isize; d.sub0 = sub0; d.n_sub = subs;
+                for (uint32_t k = 0; k < subs; ++k) z.h_sub_file[sub0 + k] = nf;
+                if (src.mem) CK(cudaMemcpyAsync(z.d_comp + off, h, size, cudaMemcpyHostToDevice, g->copy_stream));
+                off += (size + 15) / 16 * 16 + 16;
+                sub0 += subs; ++nf;
+                good.push_back(i);
+            }
+            if (good.empty()) continue;
+            if (!srcs[good[0]].mem) CK(cudaMemcpyAsync(z.d_comp, z.h_comp, off, cudaMemcpyHostToDevice, g->copy_stream));
+            // ---- plan the pipeline chunks: groups of whole files of one kind whose texts fit a chunk --------------------
+            struct Plan { uint32_t f0, f1, sub_lo, sub_hi, slice0, slices; size_t text; bool fasta; };
+            std::vector<Plan> plans;
+            uint32_t slice_at = 0;
+            for (uint32_t f = 0; f < nf;) {
+                Plan p; p.f0 = f; p.sub_lo = z.h_files[f].sub0; p.text = 0; p.fasta = srcs[good[f]].fasta; p.slice0 = slice_at + (uint32_t)plans.size();
+                uint32_t local = 0;
+                while (f < nf && srcs[good[f]].fasta == p.fasta && p.text + z.h_files[f].text_len <= g->text_cap && f - p.f0 < ING_MAX_FILES) {
+                    z.h_files[f].text_off = p.text;
+                    z.h_slice0[p.slice0 + (f - p.f0)] = local;
+                    local += (uint32_t)((z.h_files[f].text_len + 4095) / 4096);
+                    p.text += z.h_files[f].text_len;
+                    ++f;
+                }
+                z.h_slice0[p.slice0 + (f - p.f0)] = local;
+                p.f1 = f; p.sub_hi = f < nf ? z.h_files[f].sub0 : sub0; p.slices = local;
+                slice_at += f - p.f0;
+                plans.push_back(p);
+            }
+            CK(cudaMemcpyAsync(z.d_files, z.h_files, (size_t)nf * sizeof(GzFileDesc), cudaMemcpyHostToDevice, g->copy_stream));
+            CK(cudaMemcpyAsync(z.d_sub_file, z.h_sub_file, (size_t)sub0 * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+            CK(cudaMemcpyAsync(z.d_slice0, z.h_slice0, ((size_t)nf + plans.size()) * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+            // ---- decode + chain of the whole batch, on the inflate stream -------------------------------------------------
+            cudaEvent_t up = g->slot[0].h2d_done;                   // (any event will do: recorded and waited for right here)
+            CK(cudaEventRecord(up, g->copy_stream));
+            CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
+            gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, sub0, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
+            gz_launch_chain(z.d_comp, z.d_files, nf, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
+            CK(cudaGetLastError());
+            // ---- one ordinary group per plan ------------------------------------------------------------------------------
+            for (const Plan &p : plans) {
+                if (!groups.empty() && g->res_seq - groups.front().result + 4 >= ING_MAX_RESULTS && harvest()) return -1;
+                IngSlot *sl;
+                if (ingest_slot_begin(g, &sl)) return -1;
+                IngChunk c2;
+                c2.comp_len = 0; c2.text_len = p.text; c2.first = true; c2.last = true; c2.n_files = p.f1 - p.f0; c2.gz = true;
+                c2.gz_file0 = p.f0; c2.gz_sub_lo = p.sub_lo; c2.gz_sub_hi = p.sub_hi; c2.gz_slice0 = p.slice0; c2.gz_slices = p.slices;
+                IngGroup gr;
+                for (uint32_t f = p.f0; f < p.f1; ++f) {
+                    ((ull *)sl->h_meta)[f - p.f0] = z.h_files[f].text_off + z.h_files[f].text_len;                    // where file f's text ends
+                    ((unsigned *)(sl->h_meta + (size_t)ING_MAX_FILES * 8))[f - p.f0] = (unsigned)z.h_files[f].text_len;       // isz
+                    gr.members.push_back(good[f]);
+                }
+                gr.result = g->res_seq;
+                if (ingest_enqueue(g, t, *sl, c2, false, p.fasta, ING_COUNT, col, 1u, true)) return -1;
+                groups.push_back(gr);
+            }
+            CK(cudaEventRecord(z.idle, g->inflate_stream));
+        }
+        return 0;
+    }
     // 0 added, 1 does not fit one chunk (stream it), 2 not BGZF after all, -1 error
     int add_to_group(int i, bool alone)
     {
         IngSource &src = srcs[i];
         const ssize_t size = src.size();
         if (size < 0) return 2;
-        const size_t cap_max = src.bgzf || src.gz ? g->comp_chunk : std::min(g->comp_chunk, g->text_cap);
-        if (src.gz && ((size_t)size > cap_max || (size_t)src.gz_isize > g->text_cap)) return 2;       // one DEFLATE stream cannot be streamed in chunks: host
+        if (src.gz) return gz_run(std::vector<int>(1, i));                                            // (a retry of one member of an irregular gz group)
+        const size_t cap_max = src.bgzf ? g->comp_chunk : std::min(g->comp_chunk, g->text_cap);
         if ((size_t)size > cap_max) return 1;
         for (int attempt = 0; attempt < 2; ++attempt) {
             // a group closes when the next file would push it over the (ramping) chunk size; a single file may exceed the ramp
             const size_t cap = std::min(cap_max, std::max(ingest_chunk_cap(g), (size_t)size));
-            if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || cur_gz != src.gz || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
+            if (s && (alone || cur_fasta != src.fasta || cur_bgzf != src.bgzf || ch.comp_len + (size_t)size > cap || cur.members.size() >= ING_MAX_FILES)) { if (flush()) return -1; }
             if (!s) {
                 // the verdict ring must not wrap onto verdicts this job has not read yet
                 if (!groups.empty() && g->res_seq - groups.front().result + 4 >= ING_MAX_RESULTS && harvest()) return -1;
                 if (ingest_slot_begin(g, &s)) return -1;
-                cur_fasta = src.fasta; cur_bgzf = src.bgzf; cur_gz = src.gz;
+                cur_fasta = src.fasta; cur_bgzf = src.bgzf;
             }
             const uint8_t *h = src.mem;
             if (!src.mem) {
@@ -1407,12 +1557,6 @@ struct s2_ingest_job {
                     continue;
                 }
                 if (used != (size_t)size) { s->params.resize(n_params); if (cur.members.empty()) s = nullptr; return 2; }      // trailing garbage / truncated member
-            } else if (src.gz) {
-                if (text_len + (size_t)src.gz_isize > g->text_cap) { if (cur.members.empty()) { s = nullptr; return 2; } if (flush()) return -1; continue; }
-                ((unsigned *)(s->h_meta + (size_t)ING_MAX_FILES * 8))[cur.members.size()] = src.gz_isize;
-                ((ull *)(s->h_meta + ING_META_GZ_OFF))[cur.members.size()] = ch.comp_len;
-                ((ull *)(s->h_meta + ING_META_GZ_OFF))[cur.members.size() + 1] = ch.comp_len + (size_t)size;
-                text_len += (size_t)src.gz_isize;
             } else {
                 if (text_len + (size_t)size > g->text_cap) { if (cur.members.empty()) { s = nullptr; return 1; } if (flush()) return -1; continue; }
                 text_len += (size_t)size;
@@ -1486,6 +1630,7 @@ static int ingest_job_submit(s2_ingest_job *job)
         const double tb = ing_now();
         us_classify += tb - ta;
         if (!job->srcs[i].eligible) continue;
+        if (job->srcs[i].gz) { job->gz_list.push_back(i); continue; }
         const int rc = job->add_to_group(i, false);
         us_group += ing_now() - tb;
         if (rc < 0) return -1;
@@ -1493,6 +1638,7 @@ static int ingest_job_submit(s2_ingest_job *job)
         if (rc == 2) job->rc[i] = 1;
     }
     if (job->flush()) return -1;
+    if (!job->gz_list.empty() && job->gz_run(job->gz_list)) return -1;
     CK(cudaEventRecord(job->done, g->stream));
     if (trace) fprintf(stderr, "[s2 ingest] %d sources submitted: classify %.0f us, group+enqueue %.0f us (ring wait %.0f, H2D calls %.0f, inflate calls %.0f, launches %.0f), "
                        "enqueue done at %.0f us, chunks so far %llu\n",
@@ -1523,6 +1669,7 @@ static int ingest_job_finish(s2_ingest_job *job)
     s2_ingest *g = job->g;
     s2_table *t = job->t;
     const double t0 = ing_now();
+    CK(cudaSetDevice(g->device));
     CK(cudaEventSynchronize(job->done));             // the job's last group is through (later jobs may still be running)
     if (job->read_verdicts()) return -1;
     if (s2_env_int("S2_INGEST_TRACE", 0)) fprintf(stderr, "[s2 ingest] verdicts after another %.0f us of waiting\n", ing_now() - t0);

@@ -16,6 +16,7 @@
 #include "s2_kernels.cuh"
 #include "s2_kmer.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #define S2_THREADS 256
 #define S2_NONE 0xFFFFFFFFu
@@ -28,6 +29,15 @@ __device__ __forceinline__ void ld_bucket256(const uint16_t *fp, uint32_t bucket
     const uint16_t *p = fp + (uint64_t)bucket * S2_BUCKET_SLOTS;
     // one 32-byte sector, read-only path, do not allocate in L1 (the table never fits, the input does)
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "l"(p));
+}
+
+// the same without an L2 policy (tables that are swept once per batch, slice by slice: nothing should stay behind)
+__device__ __forceinline__ void ld_bucket256_plain(const uint16_t *fp, uint32_t bucket, uint32_t (&x)[8])
+{
+    const uint16_t *p = fp + (uint64_t)bucket * S2_BUCKET_SLOTS;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
                  : "l"(p));
 }
@@ -524,7 +534,7 @@ s2_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartV
 #define S2_PITEM 4096
 __global__ void __launch_bounds__(S2_THREADS, 4)
 s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_col,
-                    unsigned long long *__restrict__ stats, unsigned long long *__restrict__ work_counter, const S2DevBatch *__restrict__ dev)
+                    unsigned long long *__restrict__ stats, unsigned long long *__restrict__ work_counter, const S2DevBatch *__restrict__ dev, uint32_t flags)
 {
     if (*pv.overflow) return;
     uint32_t inc = 1u;
@@ -552,7 +562,7 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
         const uint64_t off = (item - pre[part]) * S2_PITEM;
         const uint64_t *__restrict__ src = pv.pool + (uint64_t)part * pv.region_cap;
         // this item's share of the next partition's slice -> L2
-        if (part + 1 < S2_NPART) {
+        if (part + 1 < S2_NPART && !(flags & 1u)) {
             const uint64_t items_here = pre[part + 1] - pre[part];
             const uint64_t lo = ((uint64_t)(part + 1) * t.n_buckets + S2_NPART - 1) / S2_NPART;
             const uint64_t hi = ((uint64_t)(part + 2) * t.n_buckets + S2_NPART - 1) / S2_NPART;
@@ -560,7 +570,7 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
             const uint64_t b0 = lo + (item - pre[part]) * share;
             for (uint64_t b = b0 + threadIdx.x; b < b0 + share && b < hi; b += S2_THREADS) {
                 uint32_t x[8];
-                ld_bucket256(t.fp, (uint32_t)b, x);
+                if (flags & 4u) ld_bucket256_plain(t.fp, (uint32_t)b, x); else ld_bucket256(t.fp, (uint32_t)b, x);
                 sink |= x[0] ^ x[7];
             }
         }
@@ -575,7 +585,7 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
                 const s2_hash_t hh = s2_hash(canon[u]);
                 fp2[u] = hh.fp * 0x00010001u;
                 bucket[u] = s2_bucket_of(hh.h, t.n_buckets);
-                ld_bucket256(t.fp, bucket[u], x[u]);
+                if (flags & 2u) ld_bucket256_plain(t.fp, bucket[u], x[u]); else ld_bucket256(t.fp, bucket[u], x[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -638,7 +648,8 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     const uint32_t hi0 = (uint32_t)(((uint64_t)t.n_buckets + S2_NPART - 1) / S2_NPART);
     s2_prefetch_slice_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(t.fp, 0, hi0, overflow + 1);
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
-    s2_probe_all_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter, dev);
+    static const uint32_t probe_flags = getenv("S2_PROBE_FLAGS") ? (uint32_t)atoi(getenv("S2_PROBE_FLAGS")) : 0u;
+    s2_probe_all_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter, dev, probe_flags);
     S2DetectOut none = {};
     g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow, dev);
 }

@@ -494,3 +494,76 @@ def test_gz_writer_single_stream_and_parallel_blocks(tmp_path):
                     pass
                 g = zlib.compressobj(9, zlib.DEFLATED, 31)
                 assert len(raw) == len(g.compress(text) + g.flush())
+
+
+# ---- chunk-parallel gunzip (strainer2_b200/csrc/s2_gunzip.cuh), host build of the device source ----------------------
+@pytest.fixture(scope="module")
+def pgz(tmp_path_factory):
+    so = tmp_path_factory.mktemp("pgz") / "libpgz.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                           os.path.join(ROOT, "tests", "sim", "gunzip_harness.cpp"), "-o", str(so)])
+    L = C.CDLL(str(so))
+    L.sim_pgunzip.restype = C.c_int
+
+    cap = 1 << 23
+    dst = (C.c_ubyte * cap)()
+
+    def run(z, sub_bytes, ratio=64):
+        out, stats = C.c_ulonglong(), (C.c_ulonglong * 4)()
+        rc = L.sim_pgunzip(z, C.c_ulonglong(len(z)), C.c_uint(sub_bytes), C.c_uint(ratio), dst, C.c_ulonglong(cap), C.byref(out), stats)
+        return rc, C.string_at(dst, out.value) if rc == 0 else b"", list(stats)
+    return run
+
+
+def test_parallel_gunzip_matches_zlib(pgz):
+    """one .gz stream cut into sub-chunks that are found, decoded with window markers, chained and translated
+    independently: the text is zlib's, for every level, block type and sub-chunk size (cuts inside blocks, blocks larger
+    than a sub-chunk, streams smaller than one)"""
+    import gzip
+    import zlib
+    texts = _inflate_texts()
+    r = random.Random(5)
+    texts["fastq_big"] = b"".join(b"@read%d/1\n%s\n+\n%s\n" % (i, bytes(r.choice(b"ACGTN") for _ in range(150)),
+                                                                  bytes(r.choice(b"FFFFF:,#") for _ in range(150))) for i in range(9000))
+    n_multi = 0
+    for name, t in texts.items():
+        for lvl in (0, 1, 6, 9):
+            z = gzip.compress(t, lvl)
+            for sub in ((4096, 16384, 65536, 1 << 20) if lvl == 6 else (16384,)):
+                rc, o, st = pgz(z, sub)
+                if lvl == 0:                                      # stored blocks only: invisible to the block finder, so the first sub-chunk
+                    assert (rc == 0 and o == t) or rc in (-5, -101), (name, sub, rc)       # decodes it all, or its symbol area overflows
+                    continue
+                assert rc == 0 and o == t, (name, lvl, sub, rc)
+                n_multi += st[1] > 1
+        for strat in (zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+            co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, strat)
+            z = co.compress(t) + co.flush()
+            rc, o, st = pgz(z, 16384)
+            # fixed-code and stored blocks are invisible to the block finder: such a stream either decodes (one sub-chunk
+            # runs through them) or breaks the chain (-101: handed to the host reader) - never a wrong text
+            assert (rc == 0 and o == t) or rc in (-5, -101), (name, strat, rc)
+    assert n_multi >= 4                                           # streams really were decoded in several pieces
+
+
+def test_parallel_gunzip_rejects_what_it_cannot_vouch_for(pgz):
+    """truncations and random bit flips end in an error or in the text zlib also produces - the chain check, ISIZE and
+    the bounds checks; the CRC-32 pass (device only) closes the rest"""
+    import gzip
+    import zlib
+    r = random.Random(3)
+    t = _inflate_texts()["fastq"]
+    z = gzip.compress(t, 6)
+    for cut in range(20, len(z), 211):
+        assert pgz(z[:cut], 8192)[0] != 0, cut
+    assert pgz(z + z, 8192)[0] == -104                            # a second member: not ours
+    for _ in range(300):
+        zz = bytearray(z)
+        for _ in range(r.randint(1, 3)):
+            zz[r.randrange(10, len(zz))] ^= 1 << r.randrange(8)
+        rc, o, _ = pgz(bytes(zz), 8192)
+        if rc == 0:
+            try:
+                assert o == zlib.decompress(bytes(zz), 47)
+            except zlib.error:
+                assert len(o) == len(t)                           # only the CRC-32 differs: the device pass compares it

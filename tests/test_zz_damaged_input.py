@@ -66,15 +66,15 @@ def test_executables_fail_loudly_on_damaged_gzip_data(s2, tmp_path, capsys):
     assert s2.run_kmer_scrub_count(["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"], cwd=tmp).returncode == 0
 
 
-@pytest.mark.skipif(not os.environ.get("S2_TEST_GPU_GUNZIP"),
-                    reason="software gunzip route (S2_GPU_GUNZIP=1) is wired but has not been through a GPU run yet; set S2_TEST_GPU_GUNZIP=1 to try it")
-def test_gpu_gunzip_of_ordinary_gz_groups_equals_host_reader(s2, tmp_path, monkeypatch):
-    """ordinary single-member .gz files (FASTA genomes, a FASTQ file) decoded by ing_gunzip_files inside the ingest
-    pipeline: counters equal the host reader's; files the decoder cannot vouch for (two members behind one ISIZE, a
-    wrong ISIZE, damaged data) are handed back untouched"""
+@pytest.mark.parametrize("sub_kb", [8, 32, 256])
+def test_gpu_gunzip_of_ordinary_gz_files_equals_host_reader(s2, tmp_path, monkeypatch, sub_kb):
+    """ordinary single-member .gz files (FASTA genomes at several compression levels, FASTQ files of several MB) decoded by
+    the chunk-parallel gunzip (s2_gunzip.cu: block finder, speculative decode, chain, translate, CRC-32) inside the ingest
+    pipeline: counters equal the host reader's (zlib); files the decoder cannot vouch for (a second member, a wrong ISIZE, a
+    wrong CRC-32, a flipped bit, a truncated stream) are handed back untouched"""
     import gzip
     from strainer2_b200 import synth
-    monkeypatch.setenv("S2_GPU_GUNZIP", "1")
+    monkeypatch.setenv("S2_GZ_SUB_KB", str(sub_kb))
     tmp = str(tmp_path)
     rng = synth.rng_for(7, 11)
     strain = synth.genome(rng, 300_000, 4, n_runs=2)
@@ -86,11 +86,15 @@ def test_gpu_gunzip_of_ordinary_gz_groups_equals_host_reader(s2, tmp_path, monke
     for i in range(24):                                           # relatives and strangers, 0.3 - 0.6 Mb each
         g = [c.copy() for c in clean] if i % 3 == 0 else synth.genome(rng, 300_000 + 10_000 * i, 3)
         p = os.path.join(tmp, "g%d.fa.gz" % i)
-        open(p, "wb").write(gzip.compress(synth.fasta_bytes(g, 80), 6))
+        open(p, "wb").write(gzip.compress(synth.fasta_bytes(g, 80), (1, 6, 9)[i % 3]))
         paths.append(p)
-    reads = synth.sample_reads(rng, clean + synth.genome(rng, 600_000, 2), 20_000, 150, sub_rate=0.005, n_rate=1e-4)
-    fq = os.path.join(tmp, "m.fastq.gz")
-    open(fq, "wb").write(gzip.compress(synth.fastq_bytes(reads), 6))
+    open(os.path.join(tmp, "empty.fa.gz"), "wb").write(gzip.compress(b"", 6))
+    fqs = []
+    for k, n_reads in enumerate((20_000, 150_000)):                # 6 MB and 47 MB of FASTQ text
+        reads = synth.sample_reads(rng, clean + synth.genome(rng, 600_000, 2), n_reads, 150, sub_rate=0.005, n_rate=1e-4)
+        fq = os.path.join(tmp, "m%d.fastq.gz" % k)
+        open(fq, "wb").write(gzip.compress(synth.fastq_bytes(reads), 6 if k else 1))
+        fqs.append((fq, reads.size))
     want_hits = 0
     for p in paths:
         want_hits += ctx.scan_count(t, s2.load_flat(p), 1).hits
@@ -98,19 +102,31 @@ def test_gpu_gunzip_of_ordinary_gz_groups_equals_host_reader(s2, tmp_path, monke
     st = ctx.sync()
     assert rc == [0] * len(paths)
     assert st.hits == want_hits > 1000 and np.array_equal(t.counts(1), t.counts(2))
+    for fq, n_bases in fqs:
+        t.clear_counts(1); t.clear_counts(2)
+        want = ctx.scan_count(t, s2.load_flat(fq), 1)
+        rc, bases, lookups = ctx.ingest_count_files(t, [fq], 2)
+        st = ctx.sync()
+        assert rc == [0] and bases == n_bases and st.hits == want.hits and np.array_equal(t.counts(1), t.counts(2))
+    # the same as file images in host memory, genomes and reads in one call
     t.clear_counts(1); t.clear_counts(2)
-    want = ctx.scan_count(t, s2.load_flat(fq), 1)
-    rc, bases, lookups = ctx.ingest_count_files(t, [fq], 2)
+    want_hits = sum(ctx.scan_count(t, s2.load_flat(p), 1).hits for p in paths[:6] + [fqs[0][0]])
+    images = [np.fromfile(p, dtype=np.uint8) for p in paths[:6] + [fqs[0][0], os.path.join(tmp, "empty.fa.gz")]]
+    rc, bases, lookups = ctx.ingest_count_mem_batch(t, [im.ctypes.data for im in images], [im.size for im in images], 2)
     st = ctx.sync()
-    assert rc == [0] and bases == reads.size and st.hits == want.hits and np.array_equal(t.counts(1), t.counts(2))
+    assert list(rc)[:7] == [0] * 7 and st.hits == want_hits and np.array_equal(t.counts(1), t.counts(2))
     # not vouched for: nothing counted, rc 1
     t.clear_counts(2)
     z = gzip.compress(synth.fasta_bytes(clean, 80), 6)
-    bad = {"two_members.fa.gz": z + z, "wrong_isize.fa.gz": z[:-4] + b"\x01\x00\x00\x00", "flipped.fa.gz": z[:len(z) // 2] + bytes([z[len(z) // 2] ^ 0x10]) + z[len(z) // 2 + 1:]}
+    mid = len(z) // 2
+    bad = {"two_members.fa.gz": z + z, "wrong_isize.fa.gz": z[:-4] + b"\x01\x00\x00\x00", "wrong_crc.fa.gz": z[:-8] + bytes([z[-8] ^ 1]) + z[-7:],
+           "flipped.fa.gz": z[:mid] + bytes([z[mid] ^ 0x10]) + z[mid + 1:], "cut.fa.gz": z[:mid] + z[-8:]}
     for name, data in bad.items():
         open(os.path.join(tmp, name), "wb").write(data)
     rc, _, _ = ctx.ingest_count_files(t, [os.path.join(tmp, n) for n in bad] + paths[:2], 2)
-    ctx.sync()
-    assert rc[:2] == [1, 1] and rc[3:] == [0, 0], rc              # (a single flipped bit may still decode to text of the right length)
+    st = ctx.sync()
+    assert rc[:len(bad)] == [1] * len(bad) and rc[len(bad):] == [0, 0], rc
+    want_two = sum(ctx.scan_count(t, s2.load_flat(p), 3).hits for p in paths[:2])
+    assert st.hits == want_two and np.array_equal(t.counts(2), t.counts(3))
     t.free()
     ctx.close()
