@@ -149,12 +149,17 @@ s2_ingest_job *s2_ingest_submit_files(s2_ctx *ctx, s2_table *t, const char *cons
 int         s2_ingest_wait(s2_ingest_job *job, int *rc_each, uint64_t *bases, uint64_t *lookups);
 /* the detect form: pass 1 of quantify_hits_PE for every read of one file.  len / hits / inf are per record in
  * file order (ALL records, also those shorter than 31, which the pairing loop needs); inf_* list the informative
- * windows sorted by (record, offset) with their canonical k-mer.  Arrays are malloc()ed by the call. */
+ * windows sorted by (record, offset) with their canonical k-mer.  Arrays are malloc()ed by the call.  FASTQ (four lines
+ * per record) and FASTA reads (two lines per record: test/target_metagenomes.txt), uncompressed, BGZF or ordinary .gz. */
 typedef struct s2_ingest_detect_result {
     uint64_t n_records, n_inf, bases;
     uint32_t *len, *hits, *inf;
     uint32_t *inf_rec, *inf_off;
     uint64_t *inf_kmer;
+    /* 1: two-line FASTA reads, 0: FASTQ.  The pairing loop needs it: after the last record of a FASTQ file the parser's
+     * sequence length keeps its last value (src/kseq.h:174-177 returns before the reset), after a FASTA file it is 0
+     * (last_char stays '>', so the reset at :179 runs first) - src/strain_detect.c:497 tests that length */
+    uint32_t fasta, pad_;
 } s2_ingest_detect_result;
 int         s2_ingest_detect_file(s2_ctx *ctx, s2_table *t, const char *path, s2_ingest_detect_result *out);
 void        s2_ingest_detect_free(s2_ingest_detect_result *r);

@@ -66,6 +66,7 @@ struct Detect {
     std::mutex stat_mu;
     double t_read = 0, t_gpu = 0, t_emit = 0;   // S2_STATS (summed over worker threads)
     uint64_t n_bases = 0;
+    uint64_t files_gpu = 0, files_host = 0;     // input files inflated + split on the GPU / read by the host parser
 
     void write_out(const std::string &out)
     {
@@ -215,7 +216,7 @@ static int replay_ingested(Detect &d, Job &job, const s2_ingest_detect_result &A
     while (a < A.n_records) {                                                        // :443
         const uint64_t rec1 = a++;
         const uint32_t len1 = A.len[rec1];
-        stale_a = len1;
+        stale_a = len1;                                                              // (an interleaved FASTA file that ends on PE1: reset by the failed PE2 read below)
         if (len1 >= S2_K) {                                                          // :444-449
             ++reads; h1 = (int)A.hits[rec1]; i1 = (int)A.inf[rec1];
             evaluated += len1 - (S2_K - 1);
@@ -230,6 +231,7 @@ static int replay_ingested(Detect &d, Job &job, const s2_ingest_detect_result &A
             uint32_t &stale = shared ? stale_a : stale_b;
             int64_t l2 = -1;
             if (cur < S.n_records) { rec2 = cur++; stale = S.len[rec2]; l2 = stale; }
+            else if (S.fasta) stale = 0;                                             // kseq.h:179 resets the length before it meets the end of a FASTA file
             if (stale >= S2_K) {                                                     // :497
                 if (l2 < 0) {                                                        // :501-504
                     char msg[1024];
@@ -288,6 +290,7 @@ static int quantify_hits(Detect &d, Job &job, s2_ctx *ctx, s2_table *table)
                 d.t_gpu += std::chrono::duration<double>(tJ - tI).count();
                 d.t_emit += std::chrono::duration<double>(std::chrono::steady_clock::now() - tJ).count();
                 d.n_bases += A.bases + B.bases;
+                d.files_gpu += is_pe == IS_PAIRED_END ? 2 : 1;
             }
             s2_ingest_detect_free(&A); s2_ingest_detect_free(&B);
             return rc;
@@ -470,6 +473,7 @@ static int quantify_hits(Detect &d, Job &job, s2_ctx *ctx, s2_table *table)
     {
         std::lock_guard<std::mutex> g(d.stat_mu);
         d.t_read += t_read; d.t_gpu += t_gpu; d.t_emit += t_emit; d.n_bases += n_bases;
+        d.files_host += r2 && r2 != r1 ? 2 : 1;
     }
     if (r2 && r2 != r1) s2_reader_close(r2);
     s2_reader_close(r1);
@@ -650,8 +654,9 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     if (s2_env_int("S2_STATS", 0)) {
         double kms = 0; uint64_t kl = 0;
         for (s2_ctx *gc : ctxs) { double k1 = 0; uint64_t l1 = 0; s2_kernel_time(gc, &k1, &l1, 0); kms += k1; kl += l1; }
-        fprintf(stderr, "[s2 detect] gpus=%zu keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu\n",
-                ctxs.size(), d.genome_kmers, d.genome_informative, (unsigned long long)d.n_bases, d.t_read, d.t_gpu, d.t_emit, kms, (unsigned long long)kl);
+        fprintf(stderr, "[s2 detect] gpus=%zu keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu files_gpu_ingest=%llu files_host_reader=%llu\n",
+                ctxs.size(), d.genome_kmers, d.genome_informative, (unsigned long long)d.n_bases, d.t_read, d.t_gpu, d.t_emit, kms, (unsigned long long)kl,
+                (unsigned long long)d.files_gpu, (unsigned long long)d.files_host);
     }
     s2_exotic_free(d.exotic);
     for (size_t g = 0; g < ctxs.size(); ++g) { s2_table_free(tables[g]); s2_shutdown(ctxs[g]); }

@@ -23,7 +23,9 @@
 #define GZ_WARPS 4                       /* decoding warps per CTA: 4 x 6.4 KB of tables */
 #define GZ_CHAIN_THREADS 1024
 
-__global__ void __launch_bounds__(GZ_WARPS * 32)
+// (the symbol loop is a dependent chain of about 100 cycles for 40-100 instructions: four warps per scheduler already
+// fill the issue slots, so the kernel takes the registers - no re-computed addresses in the loop - rather than the occupancy)
+__global__ void __launch_bounds__(GZ_WARPS * 32, 4)
 gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const uint32_t *__restrict__ sub_file, uint32_t n_sub,
                  uint32_t sub_bytes, uint16_t *sym, uint32_t sub_cap, GzSubResult *res, uint64_t search_limit_bits)
 {
@@ -47,7 +49,7 @@ gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__
     __shared__ int s_state;                 // 0 going on, 1 the stream ended, < 0 error
     __shared__ uint64_t s_cur, s_total;
     __shared__ uint32_t s_len;
-    if (threadIdx.x == 0) { s_state = 0; s_cur = f.first_bit; s_total = 0; }
+    if (threadIdx.x == 0) { s_state = 0; s_cur = f.chain_bit; s_total = 0; }
     __syncthreads();
     uint8_t *w0 = win + ((uint64_t)f.sub0 + blockIdx.x) * GZ_WINDOW;          // n_sub + 1 windows of this file
     for (uint32_t j = 0; j < f.n_sub; ++j) {
@@ -75,15 +77,18 @@ gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__
     }
     if (threadIdx.x == 0) {
         GzFileResult r;
-        r.text_len = s_total; r.status = s_state == 1 ? 0 : (s_state == 0 ? GZ_STREAM_OPEN : s_state); r.crc = 0; r.crc_ok = 0;
-        if (s_state == 1) {                                                     // trailer: CRC-32, ISIZE; nothing but zeros behind it
+        r.text_len = s_total; r.end_bit = s_cur; r.crc = 0; r.crc_ok = 0; r.crc_raw = 0;
+        r.status = s_state == 1 ? 0 : (s_state == 0 ? (f.piece == 1 ? 0 : GZ_STREAM_OPEN) : s_state);
+        if (s_state == 1 && f.piece == 1) r.status = GZ_TRAILING_BYTES;        // the stream ended inside a piece that is not the last: more members, or junk
+        if (f.piece && s_total > f.text_len) r.status = GZ_SIZE_MISMATCH;       // more text than the piece buffer holds (text_len = its capacity): nothing is translated
+        if (s_state == 1 && f.piece != 1) {                                                     // trailer: CRC-32, ISIZE; nothing but zeros behind it
             const uint64_t tr = (s_cur + 7) / 8;
             const uint8_t *p = comp + f.comp_off;
             if (tr + 8 > f.comp_len) r.status = GZ_ERR_INPUT;
             else {
                 const uint32_t isize = (uint32_t)p[tr + 4] | (uint32_t)p[tr + 5] << 8 | (uint32_t)p[tr + 6] << 16 | (uint32_t)p[tr + 7] << 24;
                 r.crc = (uint32_t)p[tr] | (uint32_t)p[tr + 1] << 8 | (uint32_t)p[tr + 2] << 16 | (uint32_t)p[tr + 3] << 24;
-                if (isize != (uint32_t)s_total || s_total != f.text_len) r.status = GZ_SIZE_MISMATCH;
+                if (isize != (uint32_t)(f.text_before + s_total) || (f.piece == 0 && s_total != f.text_len)) r.status = GZ_SIZE_MISMATCH;
                 for (uint64_t i = tr + 8; i < f.comp_len && r.status == 0; ++i) if (p[i]) r.status = GZ_TRAILING_BYTES;     // another member, or junk: host reader
             }
         }
@@ -176,11 +181,18 @@ gz_crc_kernel(const GzFileDesc *__restrict__ files, uint32_t file0, uint32_t n_f
 
 // the conditioning (initial value ~0, final complement) as one more term, the comparison with the trailer, and what the
 // ingest pipeline's act == isz check will see for the file
-__global__ void gz_crc_finish_kernel(uint32_t file0, uint32_t n_files, GzFileResult *fres, uint32_t *crc_acc, unsigned *act)
+__global__ void gz_crc_finish_kernel(const GzFileDesc *__restrict__ files, uint32_t file0, uint32_t n_files, GzFileResult *fres, uint32_t *crc_acc, unsigned *act)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_files) return;
     GzFileResult r = fres[file0 + i];
+    if (files[file0 + i].piece) {                        // a piece of a streamed file: the host combines the pieces' remainders
+        r.crc_raw = crc_acc[file0 + i];
+        fres[file0 + i] = r;
+        crc_acc[file0 + i] = 0;
+        if (act) act[i] = r.status == 0 ? (unsigned)r.text_len : 0xFFFFFFFFu;
+        return;
+    }
     if (r.status == 0) {
         // crc(M) = rem(M) ^ rem(0xFFFFFFFF . x^(8 len)) ^ 0xFFFFFFFF
         const uint32_t got = crc_acc[file0 + i] ^ crc_mulmod(0xFFFFFFFFu, crc_xpow8(r.text_len)) ^ 0xFFFFFFFFu;
@@ -189,7 +201,7 @@ __global__ void gz_crc_finish_kernel(uint32_t file0, uint32_t n_files, GzFileRes
         fres[file0 + i] = r;
     }
     crc_acc[file0 + i] = 0;
-    act[i] = r.status == 0 ? (unsigned)r.text_len : 0xFFFFFFFFu;
+    if (act) act[i] = r.status == 0 ? (unsigned)r.text_len : 0xFFFFFFFFu;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -225,5 +237,5 @@ void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, co
 {
     if (!n_files) return;
     if (n_slices) gz_crc_kernel<<<(n_slices + 7) / 8, 256, 0, st>>>(files, file0, n_files, file_slice0, n_slices, text, fres, crc_acc);
-    gz_crc_finish_kernel<<<(n_files + 127) / 128, 128, 0, st>>>(file0, n_files, fres, crc_acc, act);
+    gz_crc_finish_kernel<<<(n_files + 127) / 128, 128, 0, st>>>(files, file0, n_files, fres, crc_acc, act);
 }

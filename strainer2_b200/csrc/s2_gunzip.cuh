@@ -31,9 +31,21 @@
 #if defined(__CUDA_ARCH__)
 #define GZ_SYNC() __syncwarp()
 #define GZ_UNROLL _Pragma("unroll")
+#define GZ_NOUNROLL _Pragma("unroll 1")
+// The symbol loop addresses its tables and buffers through values the compiler must keep in registers: left to itself it
+// re-derives them from the kernel parameters, block and thread ids inside the loop (a dozen instructions per symbol).
+#define GZ_KEEP64(p) asm volatile("" : "+l"(p))
+typedef uint32_t gz_tab_t;                                                  // shared-memory address of a table
+__device__ __forceinline__ gz_tab_t gz_tab(const uint32_t *t) { uint32_t a = (uint32_t)__cvta_generic_to_shared(t); asm volatile("" : "+r"(a)); return a; }
+__device__ __forceinline__ uint32_t gz_tab_at(gz_tab_t t, uint32_t i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(t + (i << 2))); return v; }
 #else
 #define GZ_SYNC() do { } while (0)
 #define GZ_UNROLL
+#define GZ_NOUNROLL
+#define GZ_KEEP64(p) do { } while (0)
+typedef const uint32_t *gz_tab_t;
+inline gz_tab_t gz_tab(const uint32_t *t) { return t; }
+inline uint32_t gz_tab_at(gz_tab_t t, uint32_t i) { return t[i]; }
 #endif
 
 #define GZ_WINDOW 32768u
@@ -71,40 +83,45 @@ struct GzTables {                  // one per decoding warp (shared memory on th
 // ------------------------------------------------------------------------------------------------
 // bit reader over 32-bit words (the input buffer is 4-byte aligned and padded with >= 8 zero bytes)
 // ------------------------------------------------------------------------------------------------
+// Two words of the stream in registers and the bit position inside the first: 32 valid bits at any time through ONE
+// funnel shift, no 64-bit arithmetic in the symbol loop (round 2's first version kept a 64-bit buffer: a variable
+// 64-bit shift is half a dozen instructions, and the decoder is bound by instruction issue - profiles/r2d_gz_decode_ncu.txt).
 struct GzBits {
     const uint32_t *w;
-    uint64_t n_words;              // words that may be read
-    uint64_t wi;                   // words merged into buf so far; nextw = w[wi]
-    uint64_t buf;
-    uint32_t cnt;
-    uint32_t nextw;
+    uint32_t n_words;              // words that may be read (files below 16 GiB)
+    uint32_t wi;                   // index of `lo`
+    uint32_t lo, hi, nxt;          // w[wi], w[wi + 1], w[wi + 2] (zeros behind the end)
+    uint32_t pos;                  // bits of `lo` already consumed, < 32
 };
 
-GZ_HD inline uint32_t gz_word(const GzBits &b, uint64_t i) { return i < b.n_words ? b.w[i] : 0u; }
+GZ_HD inline uint32_t gz_word(const GzBits &b, uint32_t i) { return i < b.n_words ? b.w[i] : 0u; }
 
 GZ_HD inline void gz_bits_seek(GzBits &b, uint64_t bitpos)
 {
-    b.wi = bitpos >> 5;
-    b.buf = (uint64_t)gz_word(b, b.wi) >> (bitpos & 31u);
-    b.cnt = 32u - (uint32_t)(bitpos & 31u);
-    ++b.wi;
-    b.nextw = gz_word(b, b.wi);
+    b.wi = (uint32_t)(bitpos >> 5);
+    b.pos = (uint32_t)(bitpos & 31u);
+    b.lo = gz_word(b, b.wi); b.hi = gz_word(b, b.wi + 1u); b.nxt = gz_word(b, b.wi + 2u);
 }
-GZ_HD inline uint64_t gz_bits_pos(const GzBits &b) { return b.wi * 32u - b.cnt; }
-// at least 32 valid bits afterwards
-GZ_HD inline void gz_refill(GzBits &b)
+GZ_HD inline uint64_t gz_bits_pos(const GzBits &b) { return (uint64_t)b.wi * 32u + b.pos; }
+// the next 32 bits of the stream
+GZ_HD inline uint32_t gz_peek(const GzBits &b)
 {
-    if (b.cnt < 32u) {
-        b.buf |= (uint64_t)b.nextw << b.cnt;
-        b.cnt += 32u;
-        ++b.wi;
-        b.nextw = gz_word(b, b.wi);
-    }
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(b.lo, b.hi, b.pos);
+#else
+    return b.pos ? (b.lo >> b.pos) | (b.hi << (32u - b.pos)) : b.lo;
+#endif
 }
-GZ_HD inline uint32_t gz_take(GzBits &b, uint32_t k)          // k <= 32 bits, the caller has refilled
+GZ_HD inline void gz_skip(GzBits &b, uint32_t k)              // k <= 32
 {
-    const uint32_t v = (uint32_t)b.buf & (k >= 32u ? 0xFFFFFFFFu : ((1u << k) - 1u));
-    b.buf >>= k; b.cnt -= k;
+    b.pos += k;
+    if (b.pos >= 32u) { b.pos -= 32u; b.lo = b.hi; b.hi = b.nxt; ++b.wi; b.nxt = gz_word(b, b.wi + 2u); }
+}
+GZ_HD inline void gz_refill(GzBits &) {}                      // (32 bits are always there)
+GZ_HD inline uint32_t gz_take(GzBits &b, uint32_t k)          // k <= 32 bits
+{
+    const uint32_t v = gz_peek(b) & (k >= 32u ? 0xFFFFFFFFu : ((1u << k) - 1u));
+    gz_skip(b, k);
     return v;
 }
 
@@ -237,13 +254,13 @@ GZ_HD inline int gz_build(uint32_t *tab, uint32_t cap, int root, int kind, const
 // one symbol of a code: the entry, with its bits consumed (second-level lookup included).  At most 15 bits.
 GZ_HD inline uint32_t gz_decode_sym(GzBits &b, const uint32_t *tab, int root)
 {
-    uint32_t e = tab[(uint32_t)b.buf & ((1u << root) - 1u)];
+    const uint32_t bits = gz_peek(b);
+    uint32_t e = tab[bits & ((1u << root) - 1u)], used = 0;
     if (e & GZ_F_SUB) {
-        b.buf >>= root; b.cnt -= (uint32_t)root;
-        e = tab[(e >> 16) + ((uint32_t)b.buf & ((1u << ((e >> 4) & 15u)) - 1u))];
+        used = (uint32_t)root;
+        e = tab[(e >> 16) + ((bits >> root) & ((1u << ((e >> 4) & 15u)) - 1u))];
     }
-    const uint32_t nb = e & 15u;
-    b.buf >>= nb; b.cnt -= nb;
+    gz_skip(b, used + (e & 15u));
     return e;
 }
 
@@ -293,7 +310,7 @@ GZ_HD inline int gz_dynamic_header(GzBits &b, GzTables &t, bool check_only, bool
         i += rep; prev = val;
     }
     GZ_SYNC();
-    if (gz_bits_pos(b) > b.n_words * 32u) return GZ_ERR_INPUT;
+    if (gz_bits_pos(b) > (uint64_t)b.n_words * 32u) return GZ_ERR_INPUT;
     if (t.lens[256] == 0) return GZ_ERR_HEADER;                         // no end-of-block code
     int mx, nc;
     int k = gz_kraft(t.lens, nlen, &mx, &nc);
@@ -334,11 +351,13 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
 {
     uint32_t o = 0;
     int rc = GZ_OK;
+    GZ_KEEP64(out);
+    GZ_KEEP64(b.w);
     for (;;) {
         gz_refill(b);
         // a sub-chunk ends at the first boundary at or after the next cut whose block is one the finder can see (not
         // final, dynamic codes): final, stored and fixed-code blocks are decoded by whoever arrives at them
-        if (gz_bits_pos(b) >= stop_bit && ((uint32_t)b.buf & 7u) == 4u) break;
+        if (gz_bits_pos(b) >= stop_bit && (gz_peek(b) & 7u) == 4u) break;
         const uint32_t last = gz_take(b, 1), type = gz_take(b, 2);
         if (type == 3) { rc = GZ_ERR_HEADER; break; }
         if (type == 0) {
@@ -348,7 +367,7 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
             const uint32_t len = gz_take(b, 16), nlen = gz_take(b, 16);
             if ((len ^ 0xFFFFu) != nlen) { rc = GZ_ERR_HEADER; break; }
             pos += 32;
-            if (pos + 8ull * len > b.n_words * 32u) { rc = GZ_ERR_INPUT; break; }
+            if (pos + 8ull * len > (uint64_t)b.n_words * 32u) { rc = GZ_ERR_INPUT; break; }
             if (o + len > cap) { rc = GZ_ERR_OUTPUT; break; }
             const uint8_t *bytes = reinterpret_cast<const uint8_t *>(b.w) + (pos >> 3);
             for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) out[o + i] = bytes[i];
@@ -357,39 +376,69 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
         } else {
             rc = type == 1 ? gz_fixed_header(t, lane, nl) : gz_dynamic_header(b, t, false, false, lane, nl);
             if (rc) break;
+            // The symbol loop.  One peek holds a literal/length code and its extra bits (15 + 5), a second one the distance
+            // code and its extra bits (15 + 13); everything is 32-bit arithmetic.
+            const gz_tab_t lit = gz_tab(t.lit), dtab = gz_tab(t.dist);
             for (;;) {
-                gz_refill(b);
-                const uint32_t e = gz_decode_sym(b, t.lit, GZ_LIT_ROOT);
+                uint32_t bits = gz_peek(b);
+                uint32_t e = gz_tab_at(lit, bits & ((1u << GZ_LIT_ROOT) - 1u)), used = 0;
+                if (e & GZ_F_SUB) {
+                    used = GZ_LIT_ROOT;
+                    e = gz_tab_at(lit, (e >> 16) + ((bits >> GZ_LIT_ROOT) & ((1u << ((e >> 4) & 15u)) - 1u)));
+                }
+                used += e & 15u;
                 if (e & GZ_F_LIT) {
-                    if (o >= cap) { rc = GZ_ERR_OUTPUT; break; }
-                    if (lane == 0) out[o] = (uint16_t)(e >> 16);
-                    ++o;
+                    // every lane stores the same value to the same place (one transaction, no branch around it); a full
+                    // region stops `o` at cap - reported when the block ends or the next match arrives
+                    gz_skip(b, used);
+                    const bool room = o < cap;
+                    if (room) out[o] = (uint16_t)(e >> 16);
+                    o += room ? 1u : 0u;
                     continue;
                 }
-                if (!(e & GZ_F_BASE)) { if (!(e & GZ_F_EOB)) rc = GZ_ERR_SYMBOL; break; }
-                const uint32_t len = (e >> 16) + gz_take(b, (e >> 4) & 15u);
-                gz_refill(b);
-                const uint32_t d = gz_decode_sym(b, t.dist, GZ_DIST_ROOT);
+                if (!(e & GZ_F_BASE)) {
+                    gz_skip(b, used);
+                    if (!(e & GZ_F_EOB)) rc = GZ_ERR_SYMBOL;
+                    else if (o >= cap) rc = GZ_ERR_OUTPUT;              // (a region filled to the last symbol counts as overflowed)
+                    break;
+                }
+                const uint32_t xl = (e >> 4) & 15u;
+                const uint32_t len = (e >> 16) + ((bits >> used) & ((1u << xl) - 1u));
+                gz_skip(b, used + xl);
+                bits = gz_peek(b);
+                uint32_t d = gz_tab_at(dtab, bits & ((1u << GZ_DIST_ROOT) - 1u));
+                used = 0;
+                if (d & GZ_F_SUB) {
+                    used = GZ_DIST_ROOT;
+                    d = gz_tab_at(dtab, (d >> 16) + ((bits >> GZ_DIST_ROOT) & ((1u << ((d >> 4) & 15u)) - 1u)));
+                }
+                used += d & 15u;
                 if (!(d & GZ_F_BASE)) { rc = GZ_ERR_SYMBOL; break; }
-                const uint32_t dist = (d >> 16) + gz_take(b, (d >> 4) & 15u);
+                const uint32_t xd = (d >> 4) & 15u;
+                const uint32_t dist = (d >> 16) + ((bits >> used) & ((1u << xd) - 1u));
+                gz_skip(b, used + xd);
                 if (dist > o + window) { rc = GZ_ERR_DISTANCE; break; }
-                if (o + len > cap) { rc = GZ_ERR_OUTPUT; break; }
+                if (o + len >= cap) { rc = GZ_ERR_OUTPUT; break; }
                 GZ_SYNC();                                               // the lanes' earlier stores, before anybody reads them
+                const int32_t s0 = (int32_t)o - (int32_t)dist;           // >= -32768: before out[0] lies the unknown window
+                uint16_t *dst = out + o;
                 if (dist >= len) {
+                    GZ_NOUNROLL
                     for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) {
-                        const int64_t src = (int64_t)o - (int64_t)dist + (int64_t)i;
-                        out[o + i] = src >= 0 ? out[src] : (uint16_t)(256 + (int64_t)GZ_WINDOW + src);
+                        const int32_t src = s0 + (int32_t)i;
+                        dst[i] = src >= 0 ? out[src] : (uint16_t)(256 + (int32_t)GZ_WINDOW + src);
                     }
                 } else {                                                 // the match overlaps itself: a repeating pattern of `dist` symbols
+                    GZ_NOUNROLL
                     for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) {
-                        const int64_t src = (int64_t)o - (int64_t)dist + (int64_t)(i % dist);
-                        out[o + i] = src >= 0 ? out[src] : (uint16_t)(256 + (int64_t)GZ_WINDOW + src);
+                        const int32_t src = s0 + (int32_t)(i % dist);
+                        dst[i] = src >= 0 ? out[src] : (uint16_t)(256 + (int32_t)GZ_WINDOW + src);
                     }
                 }
                 o += len;
             }
             if (rc) break;
-            if (gz_bits_pos(b) > b.n_words * 32u) { rc = GZ_ERR_INPUT; break; }
+            if (gz_bits_pos(b) > (uint64_t)b.n_words * 32u) { rc = GZ_ERR_INPUT; break; }
         }
         if (last) { rc = GZ_FINAL; break; }
     }
@@ -405,7 +454,7 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
 // 96 bits of the stream starting at bit p
 GZ_HD inline void gz_peek96(const GzBits &b, uint64_t p, uint64_t *lo, uint32_t *hi)
 {
-    const uint64_t i = p >> 5;
+    const uint32_t i = (uint32_t)(p >> 5);
     const uint32_t s = (uint32_t)(p & 31u);
     const uint64_t w0 = gz_word(b, i), w1 = gz_word(b, i + 1), w2 = gz_word(b, i + 2), w3 = gz_word(b, i + 3);
     const uint64_t a = w0 | w1 << 32, c = w2 | w3 << 32;
@@ -472,11 +521,11 @@ GZ_HD inline void gz_subchunk(const uint32_t *words, uint64_t n_words, uint64_t 
                               uint64_t search_limit_bits, uint16_t *out, uint32_t cap, GzTables &t, GzSubResult *res, int lane, int nl)
 {
     GzBits b;
-    b.w = words; b.n_words = n_words;
+    b.w = words; b.n_words = (uint32_t)n_words;
     uint64_t start = known_start;
     int rc = 0;
     if (known_start == ~0ull) {
-        const uint64_t end_bits = n_words * 32u;
+        const uint64_t end_bits = (uint64_t)n_words * 32u;
         uint64_t limit = cut_bit + search_limit_bits;
         if (limit > end_bits) limit = end_bits;
         rc = gz_find_block(b, t, cut_bit, limit, &start, lane, nl);

@@ -3,14 +3,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-// one .gz file of a batch; built by the host
+// one .gz file of a batch - or one PIECE of a big file that is streamed through the stage in several batches; built by the host
 struct GzFileDesc {
     uint64_t comp_off;     // where its bytes start in the batch's compressed buffer (multiple of 4; zero padded behind)
-    uint64_t comp_len;
-    uint64_t first_bit;    // bit offset of the member's first DEFLATE block (8 x length of the gzip header)
+    uint64_t comp_len;     // bytes present (a piece: its own bytes plus a tail of the next piece's, for the last sub-chunk to run on)
+    uint64_t first_bit;    // bit offset of the member's first DEFLATE block (8 x length of the gzip header); ~0: a later piece (block finder)
+    uint64_t chain_bit;    // where the chain starts: first_bit, or (a later piece) where the previous piece ended, relative to this piece
     uint64_t text_off;     // where its text goes, relative to the text base handed to the translate launch
-    uint64_t text_len;     // ISIZE of the trailer as the host read it (files below 4 GiB of text)
+    uint64_t text_len;     // whole file: ISIZE of the trailer as the host read it (files below 4 GiB of text); piece: capacity of the text buffer
+    uint64_t text_before;  // piece: bytes of text the earlier pieces produced
     uint32_t sub0, n_sub;  // its sub-chunks
+    uint32_t piece;        // 0 whole file, 1 a piece that is not the last (the stream stays open), 2 the last piece
+    uint32_t pad_;
 };
 
 struct GzSubResult;        // s2_gunzip.cuh
@@ -18,11 +22,13 @@ struct GzSubResult;        // s2_gunzip.cuh
 enum { GZ_CHAIN_BROKEN = -20, GZ_STREAM_OPEN = -21, GZ_SIZE_MISMATCH = -22, GZ_TRAILING_BYTES = -23, GZ_CRC_MISMATCH = -24 };
 
 struct GzFileResult {
-    uint64_t text_len;     // bytes the stream inflated to
-    int32_t status;        // 0 = a complete single member whose size and CRC-32 match its trailer; else why not (host reader)
-    uint32_t crc;          // CRC-32 of the trailer
+    uint64_t text_len;     // bytes the stream (piece) inflated to
+    uint64_t end_bit;      // where decoding ended, relative to the file's (piece's) first byte
+    int32_t status;        // 0 = whole file / last piece: a complete single member whose size (and, whole file, CRC-32) match the trailer;
+                           //     piece: chain intact so far; else why not (host reader)
+    uint32_t crc;          // CRC-32 of the trailer (whole file / last piece)
     uint32_t crc_ok;
-    uint32_t pad_;
+    uint32_t crc_raw;      // piece: remainder of its text (no conditioning), for the host to combine
 };
 
 size_t gz_tables_bytes(void);
@@ -39,3 +45,26 @@ void gz_launch_translate(const GzFileDesc *files, const uint32_t *sub_file, uint
 // file_slice0: n + 1 ascending slice numbers (4 KB slices of each file's text), built by the host from the ISIZEs.
 void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, const uint32_t *file_slice0, uint32_t n_slices, const uint8_t *text,
                    GzFileResult *fres, uint32_t *crc_acc, unsigned *act, cudaStream_t st);
+
+// CRC-32 arithmetic for combining the pieces of a streamed file on the host (the same operations as the kernels':
+// reflected polynomial 0xEDB88320, bit 31 = coefficient of x^0)
+static inline uint32_t gz_crc_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) {
+        if (a & 0x80000000u) r ^= b;
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+    }
+    return r;
+}
+static inline uint32_t gz_crc_xpow8(uint64_t n)
+{
+    uint32_t r = 0x80000000u, sq = 0x00800000u;
+    while (n) { if (n & 1u) r = gz_crc_mulmod(r, sq); sq = gz_crc_mulmod(sq, sq); n >>= 1; }
+    return r;
+}
+// remainder of A || B from the remainders of A and B
+static inline uint32_t gz_crc_append(uint32_t raw_a, uint32_t raw_b, uint64_t len_b) { return gz_crc_mulmod(raw_a, gz_crc_xpow8(len_b)) ^ raw_b; }
+// the gzip trailer's CRC-32 from the remainder of the whole text
+static inline uint32_t gz_crc_finish(uint32_t raw, uint64_t len) { return raw ^ gz_crc_mulmod(0xFFFFFFFFu, gz_crc_xpow8(len)) ^ 0xFFFFFFFFu; }

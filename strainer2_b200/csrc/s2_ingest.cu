@@ -92,6 +92,7 @@ struct IngResult { ull bases, lookups, records; unsigned int irregular, inf_over
 struct IngChunkArgs {             // by value to the kernels of one chunk
     ull new_bytes;                // text bytes that arrived behind the carry
     unsigned int first_chunk, last_chunk, inc, fasta;
+    unsigned int lsh;             // record formats: log2 of the lines per record - 2 strict FASTQ, 1 two-line FASTA reads (strain_detect)
     unsigned int n_files, n_dblocks;
     const ull *file_end;          // group: text offset (relative to the chunk's new bytes) where file i ends
     const unsigned int *isz;      // expected inflated size per DEFLATE block
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_index_count(uint8_t *text, In
     if (threadIdx.x == 0) {
         if (lines > max_lines) { atomicOr(&st->irregular, 1u); lines = 0; }       // shorter average lines than 8 bytes: not a sequence file
         st->n_lines = lines;
-        st->n_rec = a.fasta ? 0u : lines / 4;
+        st->n_rec = a.fasta ? 0u : lines >> a.lsh;
     }
 }
 
@@ -293,7 +294,7 @@ __device__ __forceinline__ void ing_check_chunk(const uint8_t *__restrict__ text
         if (ok && !a.fasta) {
             unsigned lo = 0, hi = n_lines;                                            // first line_end >= p
             while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (line_end[mid] < p) lo = mid + 1; else hi = mid; }
-            ok = lo < n_lines && line_end[lo] == p && ((lo + 1) & 3u) == 0;
+            ok = lo < n_lines && line_end[lo] == p && ((lo + 1) & ((1u << a.lsh) - 1u)) == 0;
         }
         if (!ok) atomicOr(&st->irregular, 1u);
     }
@@ -309,7 +310,7 @@ __device__ __forceinline__ unsigned ing_fasta_kind(unsigned L, unsigned len, uin
     return len && first == '>' ? 3u : 1u;
 }
 
-__device__ __forceinline__ void ing_chunk_verdict(const uint8_t *text, IngState *st, const unsigned *line_end, unsigned total, unsigned fasta, ull *rec_off)
+__device__ __forceinline__ void ing_chunk_verdict(const uint8_t *text, IngState *st, const unsigned *line_end, unsigned total, unsigned fasta, unsigned lsh, ull *rec_off)
 {
     if (fasta && !st->last_chunk) {                                          // what does the next chunk's first line continue?
         const ull t1 = st->t1 - 1;                                           // (the chunk's text without the line end added at its end)
@@ -325,7 +326,7 @@ __device__ __forceinline__ void ing_chunk_verdict(const uint8_t *text, IngState 
         }
     }
     const unsigned irregular = atomicOr(&st->irregular, 0u);                 // what every block reported (L2)
-    const unsigned n_done = fasta ? st->n_lines : 4 * st->n_rec;             // lines that belong to complete records
+    const unsigned n_done = fasta ? st->n_lines : st->n_rec << lsh;          // lines that belong to complete records
     const ull c_from = n_done ? (ull)__ldcg(line_end + n_done - 1) + 1 : st->t0;
     ull c_len = st->t1 - c_from;
     unsigned bad = irregular;
@@ -348,18 +349,26 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *
 {
     ing_check_chunk(text, st, line_end, a);
     const unsigned n_lines = st->n_lines;
-    const unsigned r_lo = min(block_off[blockIdx.x], n_lines) / 4, r_hi = min(block_off[blockIdx.x + 1], n_lines) / 4;
+    const unsigned lsh = a.lsh, lmask = (1u << lsh) - 1u;
+    const unsigned r_lo = min(block_off[blockIdx.x], n_lines) >> lsh, r_hi = min(block_off[blockIdx.x + 1], n_lines) >> lsh;
     const ull t0 = st->t0;
     ull bases = 0, lookups = 0, out = 0;
     bool bad = false;
     for (unsigned r = r_lo + threadIdx.x; r < r_hi; r += ING_THREADS) {
-        const ull h0 = r ? (ull)line_end[4 * r - 1] + 1 : t0;      // '@' line
-        const ull s0 = (ull)line_end[4 * r] + 1;                    // sequence line
-        const ull p0 = (ull)line_end[4 * r + 1] + 1;                // '+' line
-        const ull q0 = (ull)line_end[4 * r + 2] + 1;                // quality line
-        const ull e0 = (ull)line_end[4 * r + 3];
-        const ull len = p0 - 1 - s0, qlen = e0 - q0;
-        bool ok = text[h0] == '@' && text[p0] == '+' && len == qlen;
+        const unsigned L0 = r << lsh;
+        const ull h0 = r ? (ull)line_end[L0 - 1] + 1 : t0;         // '@' / '>' line
+        const ull s0 = (ull)line_end[L0] + 1;                       // sequence line
+        const ull p0 = (ull)line_end[L0 + 1] + 1;                   // FASTQ: '+' line; two-line FASTA: the next record
+        const ull len = p0 - 1 - s0;
+        bool ok;
+        if (lsh == 2) {
+            const ull q0 = (ull)line_end[L0 + 2] + 1;               // quality line
+            const ull e0 = (ull)line_end[L0 + 3];
+            ok = text[h0] == '@' && text[p0] == '+' && len == e0 - q0;
+        } else {
+            ok = text[h0] == '>';                                   // (that the NEXT line is a header again is the next record's check)
+        }
+        // a sequence line that begins with one of these would make the reference's parser see another record / the quality part
         if (len) { const uint8_t c = text[s0]; ok = ok && c != '>' && c != '+' && c != '@'; }
         bad |= !ok;
         bases += len;
@@ -369,7 +378,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *
     {
         const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines), n_rec = st->n_rec;
         for (unsigned L = l_lo + threadIdx.x; L < l_hi; L += ING_THREADS)
-            if ((L & 3u) == 1u && (L >> 2) < n_rec) {
+            if ((L & lmask) == 1u && (L >> lsh) < n_rec) {
                 const unsigned len = line_end[L] - (line_end[L - 1] + 1);
                 if (len >= S2_K) out += len + 1;                    // records without a window are not copied (genome_compare.c:204)
             }
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_measure(const uint8_t *
     }
     if (!ing_last_block(ticket)) return;
     const unsigned total = ing_scan_array(block_out, gridDim.x);
-    if (threadIdx.x == 0) ing_chunk_verdict(text, st, line_end, total, 0u, rec_off);
+    if (threadIdx.x == 0) ing_chunk_verdict(text, st, line_end, total, 0u, a.lsh, rec_off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -485,7 +494,7 @@ __device__ __forceinline__ void ing_copy_big(const IngPieces &w, const uint8_t *
 
 __global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *text, uint8_t *text_next, IngState *st, const unsigned *__restrict__ block_off,
                                                                const unsigned *__restrict__ block_out, const unsigned *__restrict__ line_end,
-                                                               uint8_t *flat, ull *__restrict__ rec_off, unsigned do_finish, IngResult *res, unsigned *ticket)
+                                                               uint8_t *flat, ull *__restrict__ rec_off, unsigned do_finish, unsigned lsh, IngResult *res, unsigned *ticket)
 {
     __shared__ IngPieces w;
     __shared__ __align__(16) uint8_t stage[ING_BLOCK];
@@ -493,7 +502,8 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *tex
     const unsigned l_lo = min(block_off[blockIdx.x], n_lines), l_hi = min(block_off[blockIdx.x + 1], n_lines);
     const unsigned b0 = blockIdx.x * ING_BLOCK, b1 = b0 + ING_BLOCK;
     // is a sequence line of a complete record still open at the end of this block?
-    const bool open_seq = l_hi < n_lines && (l_hi & 3u) == 1u && (l_hi >> 2) < n_rec;
+    const unsigned lmask = (1u << lsh) - 1u;
+    const bool open_seq = l_hi < n_lines && (l_hi & lmask) == 1u && (l_hi >> lsh) < n_rec;
     if (!st->skip && (l_lo < l_hi || open_seq)) {
         if (threadIdx.x == 0) w.n_big = 0;
         ing_stage_block(text, stage);
@@ -502,7 +512,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *tex
         for (unsigned l0 = l_lo; l0 < l_hi; l0 += ING_THREADS) {
             const unsigned L = l0 + threadIdx.x;
             unsigned s0 = 0, e1 = 0, olen = 0;
-            const bool seq = L < l_hi && (L & 3u) == 1u && (L >> 2) < n_rec;
+            const bool seq = L < l_hi && (L & lmask) == 1u && (L >> lsh) < n_rec;
             if (seq) {
                 s0 = line_end[L - 1] + 1;
                 e1 = line_end[L] + 1;                                // one past the line's own '\n' = the separator
@@ -510,7 +520,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fastq_copy(const uint8_t *tex
             }
             unsigned total;
             const unsigned at = run + ing_block_scan(olen, total);
-            if (seq && rec_off) rec_off[L >> 2] = at;
+            if (seq && rec_off) rec_off[L >> lsh] = at;
             const unsigned lo = max(s0, b0);                         // the line may have started in an earlier block
             ing_add_piece(w, lo, olen ? e1 : lo, at + (lo - s0), true);
             __syncthreads();
@@ -565,7 +575,7 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fasta_measure(const uint8_t *
     }
     if (!ing_last_block(ticket)) return;
     const unsigned total = ing_scan_array(block_out, gridDim.x);
-    if (threadIdx.x == 0) ing_chunk_verdict(text, st, line_end, total, 1u, nullptr);
+    if (threadIdx.x == 0) ing_chunk_verdict(text, st, line_end, total, 1u, 0u, nullptr);
 }
 
 __global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *text, uint8_t *text_next, IngState *st, const unsigned *__restrict__ block_off,
@@ -632,14 +642,14 @@ __global__ void __launch_bounds__(ING_THREADS) ing_finish(const uint8_t *text, u
 // per-record results of this chunk -> the file-level arrays (record numbering continues across chunks)
 __global__ void __launch_bounds__(ING_THREADS) ing_store_records(IngState *st, const unsigned *__restrict__ line_end, const unsigned *__restrict__ hits_c,
                                                                   const unsigned *__restrict__ inf_c, unsigned *__restrict__ len_all,
-                                                                  unsigned *__restrict__ hits_all, unsigned *__restrict__ inf_all, ull cap)
+                                                                  unsigned *__restrict__ hits_all, unsigned *__restrict__ inf_all, ull cap, unsigned lsh)
 {
     if (st->skip) return;
     const unsigned n_rec = st->n_rec;
     const ull base = st->records;
     if (base + n_rec > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) st->inf_overflow = 1; return; }
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
-        len_all[base + r] = line_end[4 * r + 1] - (line_end[4 * r] + 1);
+        len_all[base + r] = line_end[(r << lsh) + 1] - (line_end[r << lsh] + 1);
         hits_all[base + r] = hits_c[r];
         inf_all[base + r] = inf_c[r];
     }
@@ -701,6 +711,8 @@ struct GzStage {
     GzFileResult *d_fres = nullptr;
     uint32_t *d_crc_acc = nullptr;
     cudaEvent_t idle = nullptr;          // inflate stream: the last chunk of the previous batch has been translated
+    uint8_t *d_piece_text = nullptr; size_t piece_text_cap = 0;      // streamed files: the text of one piece
+    GzFileResult *h_fres = nullptr;      // pinned: a piece's result
     bool used = false;
 };
 
@@ -767,7 +779,7 @@ static void ingest_free(s2_ingest *g)
         GzStage &z = g->gz;
         cudaFreeHost(z.h_comp); cudaFree(z.d_comp); cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_sub_off);
         cudaFreeHost(z.h_files); cudaFree(z.d_files); cudaFreeHost(z.h_sub_file); cudaFree(z.d_sub_file); cudaFreeHost(z.h_slice0); cudaFree(z.d_slice0);
-        cudaFree(z.d_fres); cudaFree(z.d_crc_acc);
+        cudaFree(z.d_fres); cudaFree(z.d_crc_acc); cudaFree(z.d_piece_text); cudaFreeHost(z.h_fres);
         if (z.idle) cudaEventDestroy(z.idle);
     }
     cudaFree(g->d_flat);
@@ -1070,6 +1082,7 @@ struct IngChunk {
     unsigned n_files = 0;         // > 0: a group of whole files (their ends are in the slot's meta)
     bool gz = false;              // the group's files are ordinary .gz, decoded by the pipeline's gz stage: its files [gz_file0, +n_files)
     uint32_t gz_file0 = 0, gz_sub_lo = 0, gz_sub_hi = 0, gz_slice0 = 0, gz_slices = 0;      // and their sub-chunks / CRC slices
+    const uint8_t *dev_src = nullptr;   // the chunk's text is already on the device (a slice of a streamed .gz piece's text)
 };
 
 // wait until the slot's previous chunk has left d_comp / params / meta, and return the slot
@@ -1175,6 +1188,8 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
                             s.d_text + ING_MAXCARRY, g->inflate_stream);
         gz_launch_crc(z.d_files, ch.gz_file0, ch.n_files, z.d_slice0 + ch.gz_slice0, ch.gz_slices, s.d_text + ING_MAXCARRY, z.d_fres, z.d_crc_acc, s.d_act,
                       g->inflate_stream);
+    } else if (ch.dev_src) {
+        if (ch.text_len) CK(cudaMemcpyAsync(s.d_text + ING_MAXCARRY, ch.dev_src, ch.text_len, cudaMemcpyDeviceToDevice, g->inflate_stream));
     } else if (ch.comp_len) {
         CK(cudaMemcpyAsync(s.d_text + ING_MAXCARRY, s.d_comp, ch.comp_len, cudaMemcpyDeviceToDevice, g->inflate_stream));
     }
@@ -1186,12 +1201,18 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     tr_decomp += t_launch - t_dec;
     uint8_t *d_text = s.d_text;
     uint8_t *d_text_next = g->slot[(g->n_chunks + 1) % ING_SLOTS].d_text;      // where a streamed file's next chunk will be inflated
+    const bool detect = mode == ING_DETECT;
+    // strain_detect wants per-read results: FASTA there means READS, two lines per record (what the reference's own target
+    // metagenomes are, test/target_metagenomes.txt) and goes through the record kernels; anything else in a FASTA file
+    // (wrapped sequences) is irregular to them.  The count path joins the lines of a FASTA record (genomes).
+    const bool reads2 = fasta && detect;
+    if (reads2) fasta = false;
     IngChunkArgs a;
     a.new_bytes = ch.text_len; a.first_chunk = ch.first ? 1u : 0u; a.last_chunk = ch.last ? 1u : 0u; a.inc = inc; a.fasta = fasta ? 1u : 0u;
+    a.lsh = reads2 ? 1u : 2u;
     a.n_files = ch.n_files; a.n_dblocks = (unsigned)n_db;
     a.file_end = (const ull *)s.d_meta; a.isz = (const unsigned *)(s.d_meta + (size_t)ING_MAX_FILES * 8); a.act = s.d_act;
     const unsigned n_blocks = (unsigned)(((size_t)ING_MAXCARRY + ch.text_len) / ING_BLOCK + 1);      // covers [0, t1] of the text buffer
-    const bool detect = mode == ING_DETECT;
     ing_index_count<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_masks, a, g->max_lines, g->d_tickets + 0);
     ing_index_scatter<<<n_blocks, ING_THREADS, 0, st>>>(g->d_masks, g->d_block_nl, g->d_line_end, g->max_lines);
     if (want_result && ingest_result_claim(g)) return -1;
@@ -1205,11 +1226,11 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
         ing_fastq_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a,
                                                              detect ? g->d_rec_off : nullptr, g->d_tickets + 1);
         ing_fastq_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat,
-                                                          detect ? g->d_rec_off : nullptr, detect ? 0u : 1u, res, g->d_tickets + 2);
+                                                          detect ? g->d_rec_off : nullptr, detect ? 0u : 1u, a.lsh, res, g->d_tickets + 2);
         if (!detect) {
             if (ingest_launch_count(g, t, dev, col)) return -1;
         } else {
-            const size_t max_rec = (size_t)g->max_lines / 4 + 4;
+            const size_t max_rec = (size_t)g->max_lines / 2 + 4;
             CK(cudaMemsetAsync(g->d_hits_c, 0, max_rec * sizeof(unsigned), st));
             CK(cudaMemsetAsync(g->d_inf_c, 0, max_rec * sizeof(unsigned), st));
             CK(cudaMemsetAsync(g->d_cnt_c, 0, sizeof(ull), st));
@@ -1220,7 +1241,7 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
             ing_collect_inf<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_flat, g->d_rec_off, g->d_pos_c, g->d_cnt_c, ING_CAP_C,
                                                                   g->d_frec, g->d_foff, g->d_fkmer, g->d_fcnt, g->f_cap);
             ing_store_records<<<c->n_sm * 2, ING_THREADS, 0, st>>>(g->d_state, g->d_line_end, g->d_hits_c, g->d_inf_c, g->d_len_all, g->d_hits_all,
-                                                                    g->d_inf_all, g->rec_cap);
+                                                                    g->d_inf_all, g->rec_cap, a.lsh);
             ing_finish<<<1, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_flat, 0u, res);
         }
     }
@@ -1233,11 +1254,168 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     return 0;
 }
 
+// detect mode: the file-level per-record arrays grow with the text seen so far
+static int ingest_grow_records(s2_ingest *g, const IngSource &src, ull text_total)
+{
+    if (text_total / 64 + 1024 <= g->rec_cap) return 0;      // records shorter than 64 bytes of text on average overflow the lists (-> host path)
+    // sized once from the file's size where possible (FASTQ deflates about 5 : 1) instead of growing step by step
+    const ssize_t fsize = src.size();
+    const ull guess = fsize > 0 ? (ull)fsize * (src.bgzf || src.gz ? 6 : 1) / 64 + 4096 : 0;
+    const ull want = std::max<ull>(std::max<ull>(text_total / 32 + 4096, g->rec_cap * 2), std::min<ull>(guess, 1ull << 28));
+    unsigned *nl = nullptr, *nh = nullptr, *ni = nullptr;
+    if (cudaMalloc((void **)&nl, want * 4) || cudaMalloc((void **)&nh, want * 4) || cudaMalloc((void **)&ni, want * 4)) { s2_set_error("out of device memory"); return -1; }
+    CK(cudaStreamSynchronize(g->stream));
+    if (g->rec_cap) {
+        CK(cudaMemcpy(nl, g->d_len_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(nh, g->d_hits_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(ni, g->d_inf_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all);
+    g->d_len_all = nl; g->d_hits_all = nh; g->d_inf_all = ni; g->rec_cap = want;
+    return 0;
+}
+
+static int ingest_gz_stage_init(s2_ingest *g)
+{
+    GzStage &z = g->gz;
+    if (z.d_comp) return 0;
+    z.comp_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_BATCH_MB", 128), 1), 2048) << 20;
+    z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 32), 4), 4096) << 10;
+    // symbols one sub-chunk may produce: S2_GZ_RATIO x its compressed bytes (FASTQ deflates 4-6 : 1, FASTA 3.5 : 1) plus the
+    // run-on to the first block boundary behind the next cut; a sub-chunk that needs more makes its file the host reader's
+    z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 10), 2), 64) + (384u << 10);
+    z.max_files = ING_MAX_FILES;
+    z.max_sub = (uint32_t)(z.comp_cap / z.sub_bytes) + z.max_files;
+    CK(cudaMalloc((void **)&z.d_comp, z.comp_cap + (size_t)z.max_files * 32 + 256));
+    CK(cudaMalloc((void **)&z.d_sym, (size_t)z.max_sub * z.sub_cap * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&z.d_res, (size_t)z.max_sub * gz_sub_result_bytes()));
+    CK(cudaMalloc((void **)&z.d_win, ((size_t)z.max_sub + z.max_files + 1) * 32768));
+    CK(cudaMemset(z.d_win, 0, ((size_t)z.max_sub + z.max_files + 1) * 32768));
+    CK(cudaMalloc((void **)&z.d_sub_off, (size_t)z.max_sub * sizeof(uint64_t)));
+    CK(cudaHostAlloc((void **)&z.h_files, (size_t)z.max_files * sizeof(GzFileDesc), cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&z.d_files, (size_t)z.max_files * sizeof(GzFileDesc)));
+    CK(cudaHostAlloc((void **)&z.h_sub_file, (size_t)z.max_sub * sizeof(uint32_t), cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&z.d_sub_file, (size_t)z.max_sub * sizeof(uint32_t)));
+    CK(cudaHostAlloc((void **)&z.h_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t), cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&z.d_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&z.d_fres, (size_t)z.max_files * sizeof(GzFileResult)));
+    CK(cudaMalloc((void **)&z.d_crc_acc, (size_t)z.max_files * sizeof(uint32_t)));
+    CK(cudaMemset(z.d_crc_acc, 0, (size_t)z.max_files * sizeof(uint32_t)));
+    CK(cudaEventCreateWithFlags(&z.idle, cudaEventDisableTiming));
+    return 0;
+}
+
+static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk &ch, bool bgzf, bool fasta, int mode, int col, unsigned inc, bool want_result);
+
+// ---- one big ordinary .gz file, streamed: PIECES of S2_GZ_BATCH_MB through the gz stage, each piece's text in slices
+// through the ring.  A piece is decoded like a batch of one file; its first sub-chunk finds its own block start, the
+// chain continues where the previous piece ended (with that piece's last window), the stream's size and CRC-32 are
+// checked when the last piece is decoded - by then the earlier pieces' text has been counted, so a mismatch there makes the
+// caller take them back out with increment -1, as for any streamed file that turns irregular.  Same returns as ingest_stream.
+static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int mode, int col, unsigned inc, IngResult *res, uint64_t *chunks_done)
+{
+    if (ingest_gz_stage_init(g)) return -1;
+    GzStage &z = g->gz;
+    g->call_chunk0 = g->n_chunks;
+    const size_t tail = std::min<size_t>(4u << 20, z.comp_cap / 4);             // bytes of the next piece the last sub-chunk may run on into
+    const size_t piece_bytes = (z.comp_cap - tail) / z.sub_bytes * z.sub_bytes;
+    if (!z.d_piece_text) {
+        z.piece_text_cap = (size_t)std::min<uint64_t>((uint64_t)z.comp_cap * s2_env_u64("S2_GZ_RATIO", 10), 4ull << 30);
+        CK(cudaMalloc((void **)&z.d_piece_text, z.piece_text_cap + 64));
+        CK(cudaHostAlloc((void **)&z.h_fres, sizeof(GzFileResult), cudaHostAllocDefault));
+    }
+    const ssize_t size = src.size();
+    uint8_t head[4096];
+    const ssize_t hn = src.peek(head, sizeof head, 0);
+    const uint64_t hl = hn > 0 ? s2_gzip_header_len(head, (uint64_t)hn) : 0;
+    uint64_t n = 0;
+    bool broken = size < 18 || hl == 0, first_chunk = true, finished = false;
+    ull text_total = 0;
+    uint64_t chain_abs = hl * 8;
+    uint32_t crc_raw = 0;
+    uint8_t *d_carry = z.d_win + ((size_t)z.max_sub + z.max_files) * 32768;       // the last window slot of the stage
+    for (off_t base = 0; !broken && !finished && base < size; base += (off_t)piece_bytes) {
+        const bool last_piece = (size_t)base + piece_bytes >= (size_t)size;
+        const size_t want = std::min<size_t>(piece_bytes + tail, (size_t)size - (size_t)base);
+        CK(cudaEventSynchronize(z.idle));                                        // the previous piece's text has left the stage
+        if (src.mem) {
+            CK(cudaMemcpyAsync(z.d_comp, src.mem + base, want, cudaMemcpyHostToDevice, g->copy_stream));
+        } else {
+            if (!z.h_comp) CK(cudaHostAlloc((void **)&z.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
+            if (pread(src.fd, z.h_comp, want, base) != (ssize_t)want) { s2_set_error("read failed"); return -1; }
+            CK(cudaMemcpyAsync(z.d_comp, z.h_comp, want, cudaMemcpyHostToDevice, g->copy_stream));
+        }
+        CK(cudaMemsetAsync(z.d_comp + want, 0, 64, g->copy_stream));
+        GzFileDesc &d = z.h_files[0];
+        d.comp_off = 0; d.comp_len = want; d.first_bit = base == 0 ? hl * 8 : ~0ull; d.chain_bit = chain_abs - (uint64_t)base * 8;
+        d.text_off = 0; d.text_len = z.piece_text_cap; d.text_before = text_total; d.sub0 = 0;
+        d.n_sub = (uint32_t)((std::min<size_t>(piece_bytes, (size_t)size - (size_t)base) + z.sub_bytes - 1) / z.sub_bytes);
+        d.piece = last_piece ? 2u : 1u; d.pad_ = 0;
+        for (uint32_t k = 0; k < d.n_sub; ++k) z.h_sub_file[k] = 0;
+        z.h_slice0[0] = 0; z.h_slice0[1] = 0xFFFFFFFFu;
+        CK(cudaMemcpyAsync(z.d_files, z.h_files, sizeof(GzFileDesc), cudaMemcpyHostToDevice, g->copy_stream));
+        CK(cudaMemcpyAsync(z.d_sub_file, z.h_sub_file, (size_t)d.n_sub * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+        CK(cudaMemcpyAsync(z.d_slice0, z.h_slice0, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+        cudaEvent_t up = g->slot[0].h2d_done;
+        CK(cudaEventRecord(up, g->copy_stream));
+        CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
+        if (base) CK(cudaMemcpyAsync(z.d_win, d_carry, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));      // the window the previous piece left
+        gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, d.n_sub, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
+        gz_launch_chain(z.d_comp, z.d_files, 1, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
+        gz_launch_translate(z.d_files, z.d_sub_file, 0, d.n_sub, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres, z.d_piece_text, g->inflate_stream);
+        gz_launch_crc(z.d_files, 0, 1, z.d_slice0, (uint32_t)(z.piece_text_cap / 4096) + 1, z.d_piece_text, z.d_fres, z.d_crc_acc, nullptr, g->inflate_stream);
+        CK(cudaMemcpyAsync(d_carry, z.d_win + (size_t)d.n_sub * 32768, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));
+        CK(cudaMemcpyAsync(z.h_fres, z.d_fres, sizeof(GzFileResult), cudaMemcpyDeviceToHost, g->inflate_stream));
+        CK(cudaStreamSynchronize(g->inflate_stream));
+        const GzFileResult fr = *z.h_fres;
+        if (fr.status != 0 || fr.text_len > z.piece_text_cap) { broken = true; break; }       // (the translate kernel wrote nothing past the symbols' own count)
+        chain_abs = (uint64_t)base * 8 + fr.end_bit;
+        crc_raw = gz_crc_append(crc_raw, fr.crc_raw, fr.text_len);
+        const ull L = fr.text_len;
+        if (last_piece) {
+            // size and CRC-32 of the whole stream: a mismatch is known before the last piece's text is counted - the earlier
+            // pieces were, and the caller takes them back out (same pieces, increment -1)
+            if (gz_crc_finish(crc_raw, text_total + L) != fr.crc) { broken = true; break; }
+            finished = true;
+        }
+        // the piece's text, in slices, through the ring
+        ull off = 0;
+        do {
+            IngSlot *sp;
+            if (ingest_slot_begin(g, &sp)) return -1;
+            IngChunk ch;
+            ch.dev_src = z.d_piece_text + off;
+            ch.text_len = (size_t)std::min<ull>(g->text_cap, L - off);
+            ch.comp_len = 0; ch.first = first_chunk; ch.last = last_piece && off + ch.text_len == L; ch.n_files = 0;
+            if (!ch.text_len && !ch.last) break;
+            if (mode == ING_DETECT && ingest_grow_records(g, src, text_total + off + ch.text_len)) return -1;
+            if (ingest_enqueue(g, t, *sp, ch, false, src.fasta, mode, col, inc, ch.last)) return -1;
+            first_chunk = false;
+            ++n;
+            off += ch.text_len;
+        } while (off < L);
+        CK(cudaEventRecord(z.idle, g->inflate_stream));
+        text_total += L;
+    }
+    if (chunks_done) *chunks_done = n;
+    if (broken || !finished) {
+        CK(cudaMemsetAsync(g->d_state, 0, sizeof(IngState), g->stream));        // no last chunk came to tidy up
+        CK(cudaStreamSynchronize(g->stream));
+        memset(res, 0, sizeof *res);
+        res->irregular = 1;
+        return 1;
+    }
+    CK(cudaStreamSynchronize(g->stream));
+    *res = ingest_result_take(g, g->res_seq - 1);                   // the last chunk's verdict
+    return 0;
+}
+
 // ---- a file too big for one chunk: streamed through the ring ----------------------------------------------
 // Returns 0 ok (verdict in *res), 1 not BGZF after all (nothing enqueued for the offending chunk; the verdict then
 // says irregular), -1 error.  Synchronous at the end.  *chunks_done: chunks that went to the device.
 static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mode, int col, unsigned inc, IngResult *res, uint64_t *chunks_done)
 {
+    if (src.gz) return ingest_stream_gz(g, t, src, mode, col, inc, res, chunks_done);
     g->call_chunk0 = g->n_chunks;
     off_t file_off = 0;
     bool first = true, eof = false, broken = false;
@@ -1274,22 +1452,7 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
         ch.comp_len = used; ch.first = first; ch.last = eof; ch.n_files = 0;
         file_off += (off_t)used;
         text_total += ch.text_len;
-        if (mode == ING_DETECT && text_total / 64 + 1024 > g->rec_cap) {        // records shorter than 64 bytes of text on average overflow the lists (-> host path)
-            // sized once from the file's size where possible (FASTQ deflates about 5 : 1) instead of growing step by step
-            const ssize_t fsize = src.size();
-            const ull guess = fsize > 0 ? (ull)fsize * (src.bgzf ? 6 : 1) / 64 + 4096 : 0;
-            const ull want = std::max<ull>(std::max<ull>(text_total / 32 + 4096, g->rec_cap * 2), std::min<ull>(guess, 1ull << 28));
-            unsigned *nl = nullptr, *nh = nullptr, *ni = nullptr;
-            if (cudaMalloc((void **)&nl, want * 4) || cudaMalloc((void **)&nh, want * 4) || cudaMalloc((void **)&ni, want * 4)) { s2_set_error("out of device memory"); return -1; }
-            CK(cudaStreamSynchronize(g->stream));
-            if (g->rec_cap) {
-                CK(cudaMemcpy(nl, g->d_len_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
-                CK(cudaMemcpy(nh, g->d_hits_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
-                CK(cudaMemcpy(ni, g->d_inf_all, g->rec_cap * 4, cudaMemcpyDeviceToDevice));
-            }
-            cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all);
-            g->d_len_all = nl; g->d_hits_all = nh; g->d_inf_all = ni; g->rec_cap = want;
-        }
+        if (mode == ING_DETECT && ingest_grow_records(g, src, text_total)) return -1;
         if (used) CK(cudaMemcpyAsync(s.d_comp, h, used, cudaMemcpyHostToDevice, g->copy_stream));
         if (ingest_enqueue(g, t, s, ch, src.bgzf, src.fasta, mode, col, inc, eof)) return -1;
         first = false;
@@ -1386,41 +1549,12 @@ struct s2_ingest_job {
         return 0;
     }
     // ---- ordinary .gz sources: batches through the gz stage, then ordinary groups of whole files ---------------------
-    int gz_stage_init()
-    {
-        GzStage &z = g->gz;
-        if (z.d_comp) return 0;
-        z.comp_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_BATCH_MB", 128), 1), 2048) << 20;
-        z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 32), 4), 4096) << 10;
-        // symbols one sub-chunk may produce: S2_GZ_RATIO x its compressed bytes (FASTQ deflates 4-6 : 1, FASTA 3.5 : 1) plus the
-        // run-on to the first block boundary behind the next cut; a sub-chunk that needs more makes its file the host reader's
-        z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 10), 2), 64) + (192u << 10);
-        z.max_files = ING_MAX_FILES;
-        z.max_sub = (uint32_t)(z.comp_cap / z.sub_bytes) + z.max_files;
-        CK(cudaMalloc((void **)&z.d_comp, z.comp_cap + (size_t)z.max_files * 32 + 256));
-        CK(cudaMalloc((void **)&z.d_sym, (size_t)z.max_sub * z.sub_cap * sizeof(uint16_t)));
-        CK(cudaMalloc((void **)&z.d_res, (size_t)z.max_sub * gz_sub_result_bytes()));
-        CK(cudaMalloc((void **)&z.d_win, ((size_t)z.max_sub + z.max_files + 1) * 32768));
-        CK(cudaMemset(z.d_win, 0, ((size_t)z.max_sub + z.max_files + 1) * 32768));
-        CK(cudaMalloc((void **)&z.d_sub_off, (size_t)z.max_sub * sizeof(uint64_t)));
-        CK(cudaHostAlloc((void **)&z.h_files, (size_t)z.max_files * sizeof(GzFileDesc), cudaHostAllocDefault));
-        CK(cudaMalloc((void **)&z.d_files, (size_t)z.max_files * sizeof(GzFileDesc)));
-        CK(cudaHostAlloc((void **)&z.h_sub_file, (size_t)z.max_sub * sizeof(uint32_t), cudaHostAllocDefault));
-        CK(cudaMalloc((void **)&z.d_sub_file, (size_t)z.max_sub * sizeof(uint32_t)));
-        CK(cudaHostAlloc((void **)&z.h_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t), cudaHostAllocDefault));
-        CK(cudaMalloc((void **)&z.d_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t)));
-        CK(cudaMalloc((void **)&z.d_fres, (size_t)z.max_files * sizeof(GzFileResult)));
-        CK(cudaMalloc((void **)&z.d_crc_acc, (size_t)z.max_files * sizeof(uint32_t)));
-        CK(cudaMemset(z.d_crc_acc, 0, (size_t)z.max_files * sizeof(uint32_t)));
-        CK(cudaEventCreateWithFlags(&z.idle, cudaEventDisableTiming));
-        return 0;
-    }
     // the listed sources (all ordinary .gz, classified).  Files that cannot go this way (larger than a batch or than a
     // chunk's text, no readable gzip header) are left to the host reader (rc stays 1).  Returns 0 / -1.
     int gz_run(const std::vector<int> &list)
     {
         if (flush()) return -1;                                     // the group being assembled goes first
-        if (gz_stage_init()) return -1;
+        if (ingest_gz_stage_init(g)) return -1;
         GzStage &z = g->gz;
         size_t at = 0;
         while (at < list.size()) {
@@ -1432,7 +1566,9 @@ struct s2_ingest_job {
                 IngSource &src = srcs[list[end]];
                 const ssize_t size = src.size();
                 const uint32_t subs = size > 0 ? (uint32_t)(((size_t)size + z.sub_bytes - 1) / z.sub_bytes) : 0;
-                if (size < 18 || (size_t)size > z.comp_cap || (size_t)src.gz_isize > g->text_cap) { rc[list[end]] = 1; continue; }     // host reader
+                if (size < 18) { rc[list[end]] = 1; continue; }                               // host reader
+                // too big for a group of whole files (ISIZE is the size modulo 4 GiB: trusted only for small files): streamed in pieces
+                if ((size_t)size > z.comp_cap / 2 || (size_t)src.gz_isize > g->text_cap) { streamed.push_back(list[end]); continue; }
                 const size_t need = ((size_t)size + 15) / 16 * 16 + 16;
                 if (n_files && (comp_used + need > z.comp_cap || n_sub + subs > z.max_sub || n_files + 1 > z.max_files)) break;
                 comp_used += need; n_sub += subs; ++n_files;
@@ -1460,7 +1596,8 @@ struct s2_ingest_job {
                 if (!hl) { rc[i] = 1; continue; }                   // not a gzip member after all
                 const uint32_t subs = (uint32_t)((size + z.sub_bytes - 1) / z.sub_bytes);
                 GzFileDesc &d = z.h_files[nf];
-                d.comp_off = off; d.comp_len = size; d.first_bit = hl * 8; d.text_off = 0; d.text_len = src.gz_isize; d.sub0 = sub0; d.n_sub = subs;
+                d.comp_off = off; d.comp_len = size; d.first_bit = hl * 8; d.chain_bit = hl * 8; d.text_off = 0; d.text_len = src.gz_isize; d.text_before = 0;
+                d.sub0 = sub0; d.n_sub = subs; d.piece = 0; d.pad_ = 0;
                 for (uint32_t k = 0; k < subs; ++k) z.h_sub_file[sub0 + k] = nf;
                 if (src.mem) CK(cudaMemcpyAsync(z.d_comp + off, h, size, cudaMemcpyHostToDevice, g->copy_stream));
                 off += (size + 15) / 16 * 16 + 16;
@@ -1805,6 +1942,8 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
 {
     memset(out, 0, sizeof *out);
     if (t->partitioned) return 1;
+    const bool trace = s2_env_int("S2_INGEST_TRACE", 0) != 0;
+    const double t_begin = ing_now();
     s2_ingest *g = ingest_acquire(c);
     if (!g) return -1;
     std::lock_guard<std::mutex> pipeline_lock(g->mu, std::adopt_lock);     // ours for the whole call
@@ -1813,8 +1952,8 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     if (src.fd < 0) return 1;
     struct FdGuard { int fd; ~FdGuard() { close(fd); } } guard{ src.fd };          // closed on every way out
     ingest_classify(src);
-    if (!src.eligible || src.fasta || src.gz || (src.bgzf && !g->hw_deflate)) return 1;      // per-read results are a FASTQ feature here
-    const size_t max_rec = (size_t)g->max_lines / 4 + 4;
+    if (!src.eligible || (src.bgzf && !g->hw_deflate)) return 1;
+    const size_t max_rec = (size_t)g->max_lines / 2 + 4;
     auto dev_alloc = [](void **p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
     if (dev_alloc((void **)&g->d_hits_c, max_rec * 4) || dev_alloc((void **)&g->d_inf_c, max_rec * 4) ||
         dev_alloc((void **)&g->d_rec_off, (max_rec + 1) * 8) || dev_alloc((void **)&g->d_pos_c, (ING_CAP_C + 1) * 8) ||
@@ -1823,6 +1962,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     IngResult r;
     memset(&r, 0, sizeof r);
     int rc = 0;
+    const double t_ready = ing_now();
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!g->d_frec) {
             if (!g->f_cap) g->f_cap = 1ull << 20;
@@ -1843,7 +1983,8 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     if (rc == 2) s2_set_error("the list of informative windows kept growing");
     if (rc) return rc == 2 ? -1 : rc;
     const ull n_rec = r.records;
-    out->n_records = n_rec; out->n_inf = n_inf; out->bases = r.bases;
+    const double t_streamed = ing_now();
+    out->n_records = n_rec; out->n_inf = n_inf; out->bases = r.bases; out->fasta = src.fasta ? 1u : 0u;
     out->len = (uint32_t *)malloc((n_rec + 1) * 4); out->hits = (uint32_t *)malloc((n_rec + 1) * 4); out->inf = (uint32_t *)malloc((n_rec + 1) * 4);
     out->inf_rec = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_off = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_kmer = (uint64_t *)malloc((n_inf + 1) * 8);
     if (!out->len || !out->hits || !out->inf || !out->inf_rec || !out->inf_off || !out->inf_kmer) {
@@ -1858,6 +1999,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
         s2_ingest_detect_free(out);
         return -1;
     }
+    const double t_fetched = ing_now();
     // the kernels append in arbitrary order: sort by (record, offset) = the order pass 2 prints them
     std::vector<uint32_t> perm(n_inf);
     for (uint32_t i = 0; i < n_inf; ++i) perm[i] = i;
@@ -1867,6 +2009,8 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     std::vector<uint32_t> r2(n_inf), o2(n_inf); std::vector<uint64_t> k2(n_inf);
     for (uint64_t i = 0; i < n_inf; ++i) { r2[i] = out->inf_rec[perm[i]]; o2[i] = out->inf_off[perm[i]]; k2[i] = out->inf_kmer[perm[i]]; }
     if (n_inf) { memcpy(out->inf_rec, r2.data(), n_inf * 4); memcpy(out->inf_off, o2.data(), n_inf * 4); memcpy(out->inf_kmer, k2.data(), n_inf * 8); }
+    if (trace) fprintf(stderr, "[s2 ingest] detect %s: %llu records, %llu informative windows, %.0f Mbases; pipeline %.0f us, stream %.0f us, results to the host %.0f us, sort %.0f us\n",
+                       path, (unsigned long long)n_rec, (unsigned long long)n_inf, r.bases / 1e6, t_ready - t_begin, t_streamed - t_ready, t_fetched - t_streamed, ing_now() - t_fetched);
     return 0;
 }
 

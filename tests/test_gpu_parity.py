@@ -794,9 +794,18 @@ def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path, monk
     open(os.path.join(tmp, "cut.fastq.gz"), "wb").write(whole[:len(whole) * 3 // 4])
     assert ctx.ingest_count_file(t, os.path.join(tmp, "cut.fastq.gz"), 1)[0] == 1
     assert int(t.counts(1).sum()) == 0 and ctx.sync().hits == 0
-    # a plain single-member gzip is not BGZF: host reader
+    # a plain single-member gzip is not BGZF: the hardware engine cannot take it - host reader when the software gunzip is
+    # switched off (round 1's only behaviour), else the chunk-parallel gunzip of s2_gunzip.cu
     synth.write_reads_fastq(os.path.join(tmp, "plain.fastq.gz"), reads[:3000])
+    monkeypatch.setenv("S2_GPU_GUNZIP", "0")
     assert ctx.ingest_count_file(t, os.path.join(tmp, "plain.fastq.gz"), 1)[0] == 1
+    assert int(t.counts(1).sum()) == 0 and ctx.sync().hits == 0
+    monkeypatch.delenv("S2_GPU_GUNZIP")
+    t.clear_counts(3)
+    want3 = ctx.scan_count(t, synth.reads_to_flat(reads[:3000]), 3)
+    assert ctx.ingest_count_file(t, os.path.join(tmp, "plain.fastq.gz"), 1)[0] == 0
+    assert ctx.sync().hits == want3.hits and np.array_equal(t.counts(1), t.counts(3))
+    t.clear_counts(1)
     # and the regular file itself is counted
     synth.write_bgzf(os.path.join(tmp, "good.fastq.gz"), good)
     assert ctx.ingest_count_file(t, os.path.join(tmp, "good.fastq.gz"), 1)[0] == 0
@@ -921,8 +930,8 @@ def test_gpu_ingest_groups_of_small_files(s2, ctx, tmp_path, monkeypatch):
             text += b"@half\nACGT\n"
         files.append(("r%d.fq.gz" % i, synth.bgzf_bytes(text)))
         handled.append(i not in (2, 4))
-    files.append(("ordinary.fa.gz", __import__("gzip").compress(synth.fasta_bytes(strain))))
-    handled.append(False)
+    files.append(("ordinary.fa.gz", __import__("gzip").compress(synth.fasta_bytes(strain))))      # single-member .gz: software gunzip stage
+    handled.append(True)
     files.append(("big.fa.gz", synth.bgzf_bytes(synth.fasta_bytes([synth.mutate(np.concatenate(clean), 0.02, rng)] * 30, 80))))    # 9 MB of text: streamed
     handled.append(True)
     for name, data in files:
@@ -1035,6 +1044,68 @@ def test_strain_detect_gpu_ingest_matches_oracle_including_stale_state(s2, tmp_p
     p = s2.run_strain_detect(["-r", "strain.fa", "-a", "inf.txt", "-b", "a_R1.fastq.gz", "-c", "e_R2.fastq.gz", "-t", "PE", "-o", os.path.join(tmp, "x.gz")], cwd=tmp)
     assert o.returncode == 1 and p.returncode == 1
     assert p.stderr == o.stderr
+
+
+@pytest.mark.parametrize("small_pieces", [False, True], ids=["defaults", "streamed_in_pieces"])
+def test_strain_detect_gpu_ingest_of_fasta_reads_and_ordinary_gz(s2, tmp_path, small_pieces):
+    """strain_detect on what the reference's own test/target_metagenomes.txt holds - two-line FASTA reads in ordinary
+    single-member .gz - plus BGZF / plain FASTA reads and ordinary-.gz FASTQ: all of them inflated and split on the GPU
+    (chunk-parallel gunzip, record kernels with two lines per record), short reads and the stale-state rules included;
+    a FASTA file with wrapped sequences is not two-line and goes to the host parser.  Output equals the oracle's"""
+    import gzip
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    rng = synth.rng_for(9, 1)
+    strain = synth.genome(rng, 200_000, 4, n_runs=2)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    clean = [np.where(c == ord("N"), ord("G"), c).astype(np.uint8) for c in strain]
+    c0 = clean[0].tobytes()
+    with open(os.path.join(tmp, "inf.txt"), "wb") as f:
+        for i in range(0, len(c0) - 31, 60):
+            f.write(c0[i:i + 31] + b"\n")
+
+    def recs(reads, shorten_every, seed, fasta):
+        r = np.random.default_rng(seed)
+        out = []
+        for i, x in enumerate(reads):
+            q = x.tobytes()
+            if i % shorten_every == 3:
+                q = q[:int(r.choice([0, 7, 30]))]
+            out.append(b">r%d 1\n%s\n" % (i, q) if fasta else b"@r%d\n%s\n+\n%s\n" % (i, q, b"I" * len(q)))
+        return out
+
+    n = 40_000                                                            # 6 MB of FASTA text, 10 MB of FASTQ per file
+    a1 = synth.sample_reads(rng, clean + synth.genome(rng, 200_000, 2), n, 150, sub_rate=0.004, n_rate=3e-4)
+    a2 = synth.sample_reads(rng, clean + synth.genome(rng, 200_000, 2), n, 150, sub_rate=0.004, n_rate=3e-4)
+    f1, f2 = recs(a1, 9, 1, True), recs(a2, 11, 2, True)
+    q1, q2 = recs(a1, 7, 3, False), recs(a2, 13, 4, False)
+    w = lambda name, data: open(os.path.join(tmp, name), "wb").write(data)
+    w("a_PE1.fasta.gz", gzip.compress(b"".join(f1), 6))
+    w("a_PE2.fasta.gz", gzip.compress(b"".join(f2), 6))
+    w("b_se.fasta", b"".join(f1[:9000]))
+    synth.write_bgzf(os.path.join(tmp, "c_inter.fasta.gz"), b"".join(x for pair in zip(f1[:5000], f2[:5000]) for x in pair))
+    w("d_R1.fastq.gz", gzip.compress(b"".join(q1), 1))
+    w("d_R2.fastq.gz", gzip.compress(b"".join(q2), 9))
+    w("e_R2_short.fasta.gz", gzip.compress(b"".join(f2[:1500]) + b">s\nACGT\n", 6))       # PE2 runs out on a short read: silent
+    wrapped = b"".join(b">w%d\n%s\n%s\n" % (i, x.tobytes()[:80], x.tobytes()[80:]) for i, x in enumerate(a1[:2000]))
+    w("f_wrapped.fasta.gz", gzip.compress(wrapped, 6))
+    open(os.path.join(tmp, "batch.txt"), "w").write(
+        "PE\ta_PE1.fasta.gz\ta_PE2.fasta.gz\nSE\tb_se.fasta\nPEI\tc_inter.fasta.gz\nPE\td_R1.fastq.gz\td_R2.fastq.gz\n"
+        "PE\ta_PE1.fasta.gz\te_R2_short.fasta.gz\nSE\tf_wrapped.fasta.gz\nse\ta_PE2.fasta.gz\n")
+    args = ["-r", "strain.fa", "-a", "inf.txt", "-B", "batch.txt"]
+    o = ou.oracle_cli(["detect"] + args + ["-m", os.path.join(tmp, "msg")], cwd=tmp)
+    assert o.returncode == 0, o.stderr
+    assert o.stdout.count(b"\n") > 2000
+    small = {"S2_GZ_BATCH_MB": "1", "S2_INGEST_CHUNK_MB": "1", "S2_INGEST_TEXT_MB": "4"} if small_pieces else {}
+    for env in ({"S2_STATS": "1"}, {"S2_THREADS": "1"}, {"S2_GPU_INGEST": "0"}, {"S2_GPU_GUNZIP": "0"}):
+        env = dict(env, **small)
+        out = os.path.join(tmp, "hits.gz")
+        p = s2.run_strain_detect(args + ["-o", out], cwd=tmp, env=env)
+        assert p.returncode == 0, p.stderr
+        assert ou.gunzip(out) == o.stdout, env
+        assert p.stdout == open(os.path.join(tmp, "msg"), "rb").read()
+        if "S2_STATS" in env:                                             # 10 file reads, all but the wrapped one on the GPU
+            assert b"files_gpu_ingest=9 files_host_reader=1" in p.stderr, p.stderr
 
 
 @pytest.mark.parametrize("chunk_mb", [(2, 8), None], ids=["streamed", "one_chunk"])

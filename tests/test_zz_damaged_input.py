@@ -130,3 +130,57 @@ def test_gpu_gunzip_of_ordinary_gz_files_equals_host_reader(s2, tmp_path, monkey
     assert st.hits == want_two and np.array_equal(t.counts(2), t.counts(3))
     t.free()
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch_mb,text_mb", [(4, 8), (2, 64)])
+def test_gpu_gunzip_streams_a_big_gz_file_in_pieces(s2, tmp_path, monkeypatch, batch_mb, text_mb):
+    """one ordinary .gz file larger than a gz batch (config #3's shape: one long DEFLATE stream of FASTQ) goes through the gz
+    stage in PIECES - the block finder starts every later piece, the chain and the 32 KB window carry over, the stream's
+    size and CRC-32 are checked over all pieces - and each piece's text through the ring in slices; FASTA alike.  A stream
+    whose CRC-32 is wrong at the very end is taken back out (increment -1) and handed to the host reader"""
+    import gzip
+    from strainer2_b200 import synth
+    monkeypatch.setenv("S2_GZ_BATCH_MB", str(batch_mb))
+    monkeypatch.setenv("S2_INGEST_TEXT_MB", str(text_mb))
+    tmp = str(tmp_path)
+    rng = synth.rng_for(17, 3)
+    strain = synth.genome(rng, 300_000, 4, n_runs=2)
+    clean = [np.where(c == ord("N"), ord("A"), c).astype(np.uint8) for c in strain]
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    ctx = s2.Context(0, batch_bytes=8 << 20, n_lanes=2)
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    reads = synth.sample_reads(rng, clean + synth.genome(rng, 600_000, 2), 150_000, 150, sub_rate=0.005, n_rate=1e-4)
+    fq = os.path.join(tmp, "big.fastq.gz")
+    zq = gzip.compress(synth.fastq_bytes(reads), 6)                     # 47 MB of text, about 10 MB of .gz: several pieces
+    open(fq, "wb").write(zq)
+    fa = os.path.join(tmp, "big.fa.gz")
+    genomes = [c for i in range(6) for c in (clean if i % 2 else synth.genome(rng, 2_000_000, 3))]
+    open(fa, "wb").write(gzip.compress(synth.fasta_bytes(genomes, 80), 6))
+    assert os.path.getsize(fq) > 2 * (batch_mb << 20) * 3 // 4
+    for path, n_bases in ((fq, reads.size), (fa, sum(c.size for c in genomes))):
+        t.clear_counts(1); t.clear_counts(2)
+        want = ctx.scan_count(t, s2.load_flat(path), 1)
+        rc, bases, lookups = ctx.ingest_count_files(t, [path], 2)
+        st = ctx.sync()
+        assert rc == [0] and bases == n_bases, (path, rc, bases)
+        assert st.hits == want.hits > 1000 and np.array_equal(t.counts(1), t.counts(2))
+        # as an image in host memory
+        t.clear_counts(2)
+        image = np.fromfile(path, dtype=np.uint8)
+        rc, bases, lookups = ctx.ingest_count_mem_batch(t, [image.ctypes.data], [image.size], 2)
+        st = ctx.sync()
+        assert list(rc) == [0] and st.hits == want.hits and np.array_equal(t.counts(1), t.counts(2))
+    # damaged at the very end / in the middle / a second member behind it: nothing stays counted
+    t.clear_counts(2)
+    mid = len(zq) // 2
+    bad = {"wrong_crc.fastq.gz": zq[:-8] + bytes([zq[-8] ^ 1]) + zq[-7:], "wrong_isize.fastq.gz": zq[:-4] + bytes([zq[-4] ^ 1]) + zq[-3:],
+           "flipped.fastq.gz": zq[:mid] + bytes([zq[mid] ^ 0x10]) + zq[mid + 1:], "two_members.fastq.gz": zq + zq, "cut.fastq.gz": zq[:mid]}
+    for name, data in bad.items():
+        open(os.path.join(tmp, name), "wb").write(data)
+        rc, _, _ = ctx.ingest_count_files(t, [os.path.join(tmp, name)], 2)
+        st = ctx.sync()
+        assert rc == [1], (name, rc)
+        assert not t.counts(2).any(), name
+    t.free()
+    ctx.close()
