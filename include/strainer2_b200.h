@@ -149,7 +149,8 @@ s2_ingest_job *s2_ingest_submit_files(s2_ctx *ctx, s2_table *t, const char *cons
 int         s2_ingest_wait(s2_ingest_job *job, int *rc_each, uint64_t *bases, uint64_t *lookups);
 /* the detect form: pass 1 of quantify_hits_PE for every read of one file.  len / hits / inf are per record in
  * file order (ALL records, also those shorter than 31, which the pairing loop needs); inf_* list the informative
- * windows sorted by (record, offset) with their canonical k-mer.  Arrays are malloc()ed by the call.  FASTQ (four lines
+ * windows sorted by (record, offset) with their canonical k-mer.  The arrays live in one pinned host buffer owned by the library
+ * until s2_ingest_detect_free gives it back (do not free() them).  FASTQ (four lines
  * per record) and FASTA reads (two lines per record: test/target_metagenomes.txt), uncompressed, BGZF or ordinary .gz. */
 typedef struct s2_ingest_detect_result {
     uint64_t n_records, n_inf, bases;

@@ -531,6 +531,10 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     d.ctx = background_file ? s2_init(s2_env_int("S2_DEVICE", 0), s2_env_u64("S2_BATCH_MB", 16) << 20, n_threads + 2)
                             : s2_init(s2_env_int("S2_DEVICE", 0), 8u << 20, 2);
     if (!d.ctx) { fprintf(stderr, "%s\n", s2_last_error()); return EXIT_FAILURE; }
+    // the context's ingest pipelines (350 MB of device memory and 48 MB of pinned staging each: tens of milliseconds)
+    // come into being beside the table build and the labelling instead of in front of the first metagenome
+    struct Warmer { std::thread t; ~Warmer() { if (t.joinable()) t.join(); } } warmer;
+    if (d.gpu_ingest) warmer.t = std::thread([&d, n_threads]() { s2_ingest_warm(d.ctx, std::min(n_threads, std::max(1, s2_env_int("S2_INGEST_PIPES", 3)))); });
 
     // GEN_hash_sequences_set_count_vec(r_file, 31, h, NON_INFORMATIVE, 0, 0, 6)             :139
     std::vector<uint8_t> flat;
@@ -616,6 +620,8 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
 
     // worker threads read + scan files concurrently; this thread writes the finished blocks in order
     int rc = 0;
+    const auto t_phase = std::chrono::steady_clock::now();
+    double phase_s = 0;
     {
         std::mutex mu; std::condition_variable cv;
         std::atomic<size_t> next(0);
@@ -647,6 +653,7 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
             }
         }
         for (auto &t : pool) t.join();
+        phase_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_phase).count();
     }
     // on a fatal error the reference exit()s with the gz stream unfinished; we close it either way
     s2_gz_writer_close(d.gzout);
@@ -654,9 +661,11 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     if (s2_env_int("S2_STATS", 0)) {
         double kms = 0; uint64_t kl = 0;
         for (s2_ctx *gc : ctxs) { double k1 = 0; uint64_t l1 = 0; s2_kernel_time(gc, &k1, &l1, 0); kms += k1; kl += l1; }
-        fprintf(stderr, "[s2 detect] gpus=%zu keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu files_gpu_ingest=%llu files_host_reader=%llu\n",
+        fprintf(stderr, "[s2 detect] gpus=%zu keys=%u informative=%u bytes=%llu read=%.3fs gpu_call=%.3fs emit=%.3fs kernel_ms=%.3f launches=%llu files_gpu_ingest=%llu files_host_reader=%llu "
+                        "detect_phase=%.3fs detect_Gbases_per_s=%.3f\n",
                 ctxs.size(), d.genome_kmers, d.genome_informative, (unsigned long long)d.n_bases, d.t_read, d.t_gpu, d.t_emit, kms, (unsigned long long)kl,
-                (unsigned long long)d.files_gpu, (unsigned long long)d.files_host);
+                (unsigned long long)d.files_gpu, (unsigned long long)d.files_host, phase_s, phase_s > 0 ? d.n_bases / phase_s / 1e9 : 0.0);
+        // (read / gpu_call / emit are SUMS over the worker threads; detect_phase is the wall time of the whole batch list)
     }
     s2_exotic_free(d.exotic);
     for (size_t g = 0; g < ctxs.size(); ++g) { s2_table_free(tables[g]); s2_shutdown(ctxs[g]); }

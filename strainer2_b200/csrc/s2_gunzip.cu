@@ -19,13 +19,16 @@
 // shifts and a branch) - no tensor cores, little HBM traffic (5 bytes per byte of text).
 #include "s2_gunzip.h"
 #include "s2_gunzip.cuh"
+#include <cstdlib>
 
 #define GZ_WARPS 4                       /* decoding warps per CTA: 4 x 6.4 KB of tables */
 #define GZ_CHAIN_THREADS 1024
 
-// (the symbol loop is a dependent chain of about 100 cycles for 40-100 instructions: four warps per scheduler already
-// fill the issue slots, so the kernel takes the registers - no re-computed addresses in the loop - rather than the occupancy)
-__global__ void __launch_bounds__(GZ_WARPS * 32, 4)
+// Occupancy against registers (profiles/r2f_gz_decode_ncu.txt): a warp's instruction stream is one dependent chain - it issues
+// about once in nine cycles - so the schedulers fill up only with eight or more warps each; 64 registers (8 CTAs per SM,
+// which is also what the tables' shared memory allows) beat 93 registers without re-computed addresses at 5 CTAs.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(GZ_WARPS * 32, MIN_CTAS)
 gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const uint32_t *__restrict__ sub_file, uint32_t n_sub,
                  uint32_t sub_bytes, uint16_t *sym, uint32_t sub_cap, GzSubResult *res, uint64_t search_limit_bits)
 {
@@ -40,42 +43,114 @@ gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict_
                 (uint64_t)(j + 1) * sub_bytes * 8ull, search_limit_bits, sym + (uint64_t)sub * sub_cap, sub_cap, tables[warp], res + sub, (int)lane, 32);
 }
 
-// one CTA per file
+// one CTA per file.  Phase 0, in parallel over the file's sub-chunks: the chain test (sub-chunk j must start where j-1
+// ended), the first sub-chunk that ends the stream or breaks the chain, text offsets by a block scan.  Phase 1, in order:
+// window j+1 from the last 32 KB of sub-chunk j's symbols and window j.  That loop is the serial part of a big file
+// (3,000 steps per 96 MB piece), so a step is one global round trip and one barrier: both windows live in shared memory
+// (ping-pong), the symbols of step j+1 are pulled towards L2 while step j runs, and window j goes out to global memory
+// (for the translate pass) with 128-bit stores during step j+1.
 __global__ void __launch_bounds__(GZ_CHAIN_THREADS)
 gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const uint16_t *__restrict__ sym, uint32_t sub_cap,
                 const GzSubResult *__restrict__ res, uint8_t *win, uint64_t *__restrict__ sub_off, GzFileResult *__restrict__ out)
 {
+    extern __shared__ __align__(16) uint8_t s_win[];            // 2 x GZ_WINDOW
     const GzFileDesc f = files[blockIdx.x];
-    __shared__ int s_state;                 // 0 going on, 1 the stream ended, < 0 error
-    __shared__ uint64_t s_cur, s_total;
-    __shared__ uint32_t s_len;
-    if (threadIdx.x == 0) { s_state = 0; s_cur = f.chain_bit; s_total = 0; }
+    __shared__ uint32_t s_first;                                 // first sub-chunk that is not a plain link of the chain
+    __shared__ uint64_t s_warp[GZ_CHAIN_THREADS / 32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const GzSubResult *r = res + f.sub0;
+    if (tid == 0) { s_first = f.n_sub; s_carry = 0; }
     __syncthreads();
-    uint8_t *w0 = win + ((uint64_t)f.sub0 + blockIdx.x) * GZ_WINDOW;          // n_sub + 1 windows of this file
-    for (uint32_t j = 0; j < f.n_sub; ++j) {
-        const uint32_t sub = f.sub0 + j;
-        if (threadIdx.x == 0) {
-            s_len = 0;
-            sub_off[sub] = s_total;
-            if (s_state == 0) {
-                const GzSubResult r = res[sub];
-                if (r.start_bit != s_cur) s_state = GZ_CHAIN_BROKEN;
-                else if (r.status < 0) s_state = r.status;
-                else {
-                    s_len = r.n_out; s_total += r.n_out; s_cur = r.end_bit;
-                    if (r.status == GZ_FINAL) s_state = 1;
-                }
-            }
-        }
+    for (uint32_t j = tid; j < f.n_sub; j += GZ_CHAIN_THREADS) {
+        const uint64_t expect = j ? r[j - 1].end_bit : f.chain_bit;
+        if (r[j].start_bit != expect || r[j].status != GZ_OK) atomicMin(&s_first, j);
+    }
+    __syncthreads();
+    const uint32_t first = s_first;
+    int state = 0;                                               // 0 the stream goes on, 1 it ended, < 0 error
+    uint32_t n_steps = first;                                    // sub-chunks that contribute text
+    if (first < f.n_sub) {
+        const uint64_t expect = first ? r[first - 1].end_bit : f.chain_bit;
+        const int st = r[first].status;
+        if (r[first].start_bit != expect) state = GZ_CHAIN_BROKEN;
+        else if (st < 0) state = st;
+        else { state = 1; n_steps = first + 1; }                 // GZ_FINAL: the stream's last block ended here
+    }
+    // text offsets: exclusive scan of the lengths (0 behind the end of the stream / the break)
+    for (uint32_t j0 = 0; j0 < f.n_sub; j0 += GZ_CHAIN_THREADS) {
+        const uint32_t j = j0 + tid;
+        const uint64_t len = j < n_steps ? r[j].n_out : 0u;
+        uint64_t inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint64_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (uint32_t)o) inc += n; }
+        if (lane == 31) s_warp[wid] = inc;
         __syncthreads();
-        if (s_state < 0) break;
-        const uint32_t len = s_len;
-        // (after the end of the stream nothing more is decoded: later sub-chunks keep length 0 and need no window)
-        if (len || s_state == 0) gz_next_window(w0 + (uint64_t)j * GZ_WINDOW, sym + (uint64_t)sub * sub_cap, len, w0 + (uint64_t)(j + 1) * GZ_WINDOW, threadIdx.x, GZ_CHAIN_THREADS);
-        __threadfence_block();
+        uint64_t base = s_carry;
+        for (uint32_t w = 0; w < wid; ++w) base += s_warp[w];
+        if (j < f.n_sub) sub_off[f.sub0 + j] = base + inc - len;
+        __syncthreads();
+        if (tid == GZ_CHAIN_THREADS - 1) s_carry = base + inc;
         __syncthreads();
     }
+    const uint64_t total = s_carry;
+    // windows, in order
+    uint8_t *w0 = win + ((uint64_t)f.sub0 + blockIdx.x) * GZ_WINDOW;          // n_sub + 1 windows of this file
+    if (state >= 0) {                                            // (a broken file's windows are nobody's business)
+        for (uint32_t i = tid; i < GZ_WINDOW / 16; i += GZ_CHAIN_THREADS) reinterpret_cast<uint4 *>(s_win)[i] = reinterpret_cast<const uint4 *>(w0)[i];
+        __syncthreads();
+        for (uint32_t j = 0; j < n_steps; ++j) {
+            const uint8_t *prev = s_win + (j & 1u) * GZ_WINDOW;
+            uint8_t *next = s_win + ((j + 1u) & 1u) * GZ_WINDOW;
+            const uint32_t len = r[j].n_out;
+            const uint16_t *sy = sym + (uint64_t)(f.sub0 + j) * sub_cap;
+            // the symbols that matter: the last min(len, 32 K); aligned 32-bit loads of two symbols, 17 per thread in flight
+            const uint32_t used = len < GZ_WINDOW ? len : GZ_WINDOW;
+            const uint32_t s_lo = len - used;                                  // first symbol that lands in the window ...
+            const uint32_t k_lo = GZ_WINDOW - used;                            // ... at this place
+            const uint32_t a = s_lo & ~1u;
+            const uint32_t n_words = (len - a + 1u) / 2u;                      // <= 16385
+            uint32_t wv[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                const uint32_t w = (uint32_t)i * GZ_CHAIN_THREADS + tid;
+                wv[i] = w < n_words ? *reinterpret_cast<const uint32_t *>(sy + a + 2u * w) : 0u;
+            }
+            if (j + 1 < n_steps) {                                             // next step's symbols -> L2
+                const uint32_t len2 = r[j + 1].n_out, used2 = len2 < GZ_WINDOW ? len2 : GZ_WINDOW;
+                const uint8_t *p2 = reinterpret_cast<const uint8_t *>(sym + (uint64_t)(f.sub0 + j + 1) * sub_cap + (len2 - used2));
+                if (tid * 128u < used2 * 2u) asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + tid * 128u));
+            }
+            // window j (complete since the last barrier) -> global memory, for the translate pass
+            {
+                uint4 *g = reinterpret_cast<uint4 *>(w0 + (uint64_t)j * GZ_WINDOW);
+                const uint4 *sp = reinterpret_cast<const uint4 *>(prev);
+                g[tid] = sp[tid]; g[tid + GZ_CHAIN_THREADS] = sp[tid + GZ_CHAIN_THREADS];
+            }
+            // where this sub-chunk produced fewer than 32 K symbols the window begins with the tail of the previous one
+            for (uint32_t k = tid; k < k_lo; k += GZ_CHAIN_THREADS) next[k] = prev[k + used];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                const uint32_t w = (uint32_t)i * GZ_CHAIN_THREADS + tid;
+                if (w < n_words) {
+                    const uint32_t s0 = a + 2u * w;                            // symbol index of the low half
+                    const uint32_t lo = wv[i] & 0xFFFFu, hi = wv[i] >> 16;
+                    if (s0 >= s_lo) next[k_lo + (s0 - s_lo)] = lo < 256u ? (uint8_t)lo : prev[lo - 256u];
+                    if (s0 + 1u < len) next[k_lo + (s0 + 1u - s_lo)] = hi < 256u ? (uint8_t)hi : prev[hi - 256u];
+                }
+            }
+            __syncthreads();
+        }
+        {                                                                      // the last window (a later piece of the file starts from it)
+            uint4 *g = reinterpret_cast<uint4 *>(w0 + (uint64_t)n_steps * GZ_WINDOW);
+            const uint4 *sp = reinterpret_cast<const uint4 *>(s_win + (n_steps & 1u) * GZ_WINDOW);
+            g[tid] = sp[tid]; g[tid + GZ_CHAIN_THREADS] = sp[tid + GZ_CHAIN_THREADS];
+        }
+    }
     if (threadIdx.x == 0) {
+        const uint64_t s_total = total;
+        const uint64_t s_cur = n_steps ? r[n_steps - 1].end_bit : f.chain_bit;
+        const int s_state = state;
         GzFileResult r;
         r.text_len = s_total; r.end_bit = s_cur; r.crc = 0; r.crc_ok = 0; r.crc_raw = 0;
         r.status = s_state == 1 ? 0 : (s_state == 0 ? (f.piece == 1 ? 0 : GZ_STREAM_OPEN) : s_state);
@@ -213,14 +288,19 @@ void gz_launch_decode(const uint8_t *comp, const GzFileDesc *files, const uint32
                       uint32_t sub_cap, GzSubResult *res, cudaStream_t st)
 {
     if (!n_sub) return;
-    gz_decode_kernel<<<(n_sub + GZ_WARPS - 1) / GZ_WARPS, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
+    static const int ctas = getenv("S2_GZ_DECODE_CTAS") ? atoi(getenv("S2_GZ_DECODE_CTAS")) : 8;      // (experiments; 8 is the measured best)
+    const dim3 grid((n_sub + GZ_WARPS - 1) / GZ_WARPS);
+    if (ctas <= 5) gz_decode_kernel<5><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
+    else if (ctas == 6) gz_decode_kernel<6><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
+    else gz_decode_kernel<8><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
 }
 
 void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint16_t *sym, uint32_t sub_cap, const GzSubResult *res,
                      uint8_t *win, uint64_t *sub_off, GzFileResult *fres, cudaStream_t st)
 {
     if (!n_files) return;
-    gz_chain_kernel<<<n_files, GZ_CHAIN_THREADS, 0, st>>>(comp, files, sym, sub_cap, res, win, sub_off, fres);
+    cudaFuncSetAttribute(gz_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GZ_WINDOW);       // (per device: every launch)
+    gz_chain_kernel<<<n_files, GZ_CHAIN_THREADS, 2 * GZ_WINDOW, st>>>(comp, files, sym, sub_cap, res, win, sub_off, fres);
 }
 
 size_t gz_sub_result_bytes(void) { return sizeof(GzSubResult); }

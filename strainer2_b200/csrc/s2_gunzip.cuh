@@ -351,6 +351,8 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
 {
     uint32_t o = 0;
     int rc = GZ_OK;
+    uint32_t p_at = ~0u;                                                 // this lane's copied symbol that is still to be stored, and where
+    uint16_t p_val = 0;
     GZ_KEEP64(out);
     GZ_KEEP64(b.w);
     for (;;) {
@@ -419,19 +421,25 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
                 gz_skip(b, used + xd);
                 if (dist > o + window) { rc = GZ_ERR_DISTANCE; break; }
                 if (o + len >= cap) { rc = GZ_ERR_OUTPUT; break; }
+                // A copied symbol is loaded now and stored when the NEXT match arrives (or the blocks end): the symbols were
+                // written past L1, so the load is an L2 round trip, and a store right behind it would hold the warp - in-order
+                // issue - for all of it.  Nothing reads the place in between: literals only store, and the next match stores
+                // the pending symbol before it loads.  (First nl symbols of a match; the rest of a long one is copied at once -
+                // it never reads this match's own output: every source index lies before o.)
+                if (p_at != ~0u) { out[p_at] = p_val; p_at = ~0u; }
                 GZ_SYNC();                                               // the lanes' earlier stores, before anybody reads them
                 const int32_t s0 = (int32_t)o - (int32_t)dist;           // >= -32768: before out[0] lies the unknown window
                 uint16_t *dst = out + o;
-                if (dist >= len) {
+                const bool overlap = dist < len;                         // the match overlaps itself: a repeating pattern of `dist` symbols
+                if ((uint32_t)lane < len) {
+                    const int32_t src = s0 + (int32_t)(overlap ? (uint32_t)lane % dist : (uint32_t)lane);
+                    p_val = src >= 0 ? out[src] : (uint16_t)(256 + (int32_t)GZ_WINDOW + src);
+                    p_at = o + (uint32_t)lane;
+                }
+                if (len > (uint32_t)nl) {
                     GZ_NOUNROLL
-                    for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) {
-                        const int32_t src = s0 + (int32_t)i;
-                        dst[i] = src >= 0 ? out[src] : (uint16_t)(256 + (int32_t)GZ_WINDOW + src);
-                    }
-                } else {                                                 // the match overlaps itself: a repeating pattern of `dist` symbols
-                    GZ_NOUNROLL
-                    for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) {
-                        const int32_t src = s0 + (int32_t)(i % dist);
+                    for (uint32_t i = (uint32_t)(lane + nl); i < len; i += (uint32_t)nl) {
+                        const int32_t src = s0 + (int32_t)(overlap ? i % dist : i);
                         dst[i] = src >= 0 ? out[src] : (uint16_t)(256 + (int32_t)GZ_WINDOW + src);
                     }
                 }
@@ -442,6 +450,7 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
         }
         if (last) { rc = GZ_FINAL; break; }
     }
+    if (p_at != ~0u) out[p_at] = p_val;
     GZ_SYNC();
     *n_out = o;
     *end_bit = gz_bits_pos(b);

@@ -47,6 +47,10 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <thread>
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
@@ -877,6 +881,88 @@ static bool is_bgzf_header(const uint8_t *p, ssize_t n)
            p[12] == 'B' && p[13] == 'C' && p[14] == 2 && p[15] == 0;
 }
 
+// ---- big reads on several threads ----------------------------------------------------------------------------
+// One thread copies a file out of the page cache at 4-6 GB/s; a 16 MB chunk of a big BGZF file, or a 100 MB piece of a big
+// .gz, read by the thread that also drives the pipeline left the GPU waiting for the file (strain_detect on one 60 MB
+// file: 13 ms, nearly all of it pread - profiles/r2f_detect_bench.txt).  Reads of more than 4 MB are split over a small
+// pool of helper threads (S2_READ_THREADS, default 6; 0 = none).
+struct ReadPool {
+    std::mutex mu; std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    std::vector<std::thread> th;
+    bool stop = false;
+    explicit ReadPool(int n)
+    {
+        for (int i = 0; i < n; ++i)
+            th.emplace_back([this]() {
+                for (;;) {
+                    std::function<void()> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [this]() { return stop || !q.empty(); });
+                        if (q.empty()) return;
+                        f = std::move(q.front()); q.pop_front();
+                    }
+                    f();
+                }
+            });
+    }
+    ~ReadPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+};
+static ReadPool *read_pool(void)
+{
+    static ReadPool *pool = []() -> ReadPool * {
+        const int n = std::min(std::max(s2_env_int("S2_READ_THREADS", 6), 0), 32);
+        return n ? new ReadPool(n) : nullptr;             // (lives as long as the process: its threads sleep when there is nothing to read)
+    }();
+    return pool;
+}
+// pread of exactly what is there: returns the bytes read (short only at the end of the file) or -1
+static ssize_t ing_pread(int fd, uint8_t *dst, size_t len, off_t off)
+{
+    ReadPool *pool = len > (4u << 20) ? read_pool() : nullptr;
+    auto read_all = [fd](uint8_t *d, size_t n, off_t o) -> ssize_t {
+        size_t done = 0;
+        while (done < n) {
+            const ssize_t r = pread(fd, d + done, n - done, o + (off_t)done);
+            if (r < 0) return -1;
+            if (r == 0) break;
+            done += (size_t)r;
+        }
+        return (ssize_t)done;
+    };
+    if (!pool) return read_all(dst, len, off);
+    const size_t n_parts = std::min<size_t>(pool->th.size() + 1, (len + (2u << 20) - 1) / (2u << 20));
+    const size_t part = (len / n_parts + 4095) & ~(size_t)4095;
+    std::vector<ssize_t> got(n_parts, 0);
+    std::mutex mu; std::condition_variable cv; size_t pending = 0;
+    for (size_t k = 1; k < n_parts; ++k) {
+        if (k * part >= len) break;
+        { std::lock_guard<std::mutex> lk(mu); ++pending; }
+        auto task = [&, k]() {
+            got[k] = read_all(dst + k * part, std::min(part, len - k * part), off + (off_t)(k * part));
+            std::lock_guard<std::mutex> lk(mu);
+            if (--pending == 0) cv.notify_one();
+        };
+        { std::lock_guard<std::mutex> lk(pool->mu); pool->q.emplace_back(task); }
+        pool->cv.notify_one();
+    }
+    got[0] = read_all(dst, std::min(part, len), off);
+    { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return pending == 0; }); }
+    ssize_t total = 0;
+    for (size_t k = 0; k < n_parts; ++k) {
+        if (got[k] < 0) return -1;
+        total += got[k];
+        if ((size_t)got[k] < std::min(part, len > k * part ? len - k * part : 0)) break;       // the file ends inside this part
+    }
+    return total;
+}
+
 // where the compressed (or plain) bytes come from: a file read chunk by chunk into pinned staging buffers, or a
 // caller's host buffer (pinned for full PCIe rate) that is copied to the device directly
 struct IngSource {
@@ -1342,7 +1428,7 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
             CK(cudaMemcpyAsync(z.d_comp, src.mem + base, want, cudaMemcpyHostToDevice, g->copy_stream));
         } else {
             if (!z.h_comp) CK(cudaHostAlloc((void **)&z.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
-            if (pread(src.fd, z.h_comp, want, base) != (ssize_t)want) { s2_set_error("read failed"); return -1; }
+            if (ing_pread(src.fd, z.h_comp, want, base) != (ssize_t)want) { s2_set_error("read failed"); return -1; }
             CK(cudaMemcpyAsync(z.d_comp, z.h_comp, want, cudaMemcpyHostToDevice, g->copy_stream));
         }
         CK(cudaMemsetAsync(z.d_comp + want, 0, 64, g->copy_stream));
@@ -1433,7 +1519,7 @@ static int ingest_stream(s2_ingest *g, s2_table *t, const IngSource &src, int mo
             got = (size_t)file_off < src.mem_len ? (ssize_t)std::min<size_t>(want_bytes, src.mem_len - (size_t)file_off) : 0;
         } else {
             if (ingest_staging(s, g->comp_chunk)) return -1;
-            got = pread(src.fd, s.h_comp, want_bytes, file_off);
+            got = ing_pread(src.fd, s.h_comp, want_bytes, file_off);
             if (got < 0) { s2_set_error("read failed"); return -1; }
             h = s.h_comp;
         }
@@ -1588,7 +1674,7 @@ struct s2_ingest_job {
                 const size_t size = (size_t)src.size();
                 const uint8_t *h = src.mem;
                 if (!src.mem) {
-                    if (pread(src.fd, z.h_comp + off, size, 0) != (ssize_t)size) { s2_set_error("read failed"); return -1; }
+                    if (ing_pread(src.fd, z.h_comp + off, size, 0) != (ssize_t)size) { s2_set_error("read failed"); return -1; }
                     memset(z.h_comp + off + size, 0, (size + 15) / 16 * 16 + 16 - size);
                     h = z.h_comp + off;
                 }
@@ -1679,7 +1765,7 @@ struct s2_ingest_job {
             const uint8_t *h = src.mem;
             if (!src.mem) {
                 if (ingest_staging(*s, g->comp_chunk)) return -1;
-                if (pread(src.fd, s->h_comp + ch.comp_len, (size_t)size, 0) != size) { s2_set_error("read failed"); return -1; }
+                if (ing_pread(src.fd, s->h_comp + ch.comp_len, (size_t)size, 0) != size) { s2_set_error("read failed"); return -1; }
                 h = s->h_comp + ch.comp_len;
             }
             size_t text_len = ch.text_len;
@@ -1934,6 +2020,46 @@ extern "C" int s2_ingest_count_files(s2_ctx *c, s2_table *t, const char *const *
     return job ? s2_ingest_wait(job, rc_each, bases, lookups) : -1;
 }
 
+// Per-read results come back into pinned host buffers (one device -> host copy at link rate instead of six staged ones
+// into pageable memory) that are kept for the next file: taken here, given back by s2_ingest_detect_free.
+struct DetHostBuf { void *p = nullptr; size_t cap = 0; };
+static std::mutex g_det_mu;
+static std::vector<DetHostBuf> g_det_free;                          // idle buffers
+static std::vector<DetHostBuf> g_det_out;                           // handed out (base pointer = result.len)
+static void *det_buf_take(size_t bytes)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_det_mu);
+        size_t best = g_det_free.size();
+        for (size_t i = 0; i < g_det_free.size(); ++i)
+            if (g_det_free[i].cap >= bytes && (best == g_det_free.size() || g_det_free[i].cap < g_det_free[best].cap)) best = i;
+        if (best < g_det_free.size()) {
+            DetHostBuf b = g_det_free[best];
+            g_det_free.erase(g_det_free.begin() + (long)best);
+            g_det_out.push_back(b);
+            return b.p;
+        }
+    }
+    DetHostBuf b;
+    b.cap = (bytes + bytes / 4 + (1u << 20)) & ~(size_t)4095;
+    if (cudaHostAlloc(&b.p, b.cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_det_mu);
+    g_det_out.push_back(b);
+    return b.p;
+}
+static void det_buf_give(void *p)
+{
+    std::lock_guard<std::mutex> lk(g_det_mu);
+    for (size_t i = 0; i < g_det_out.size(); ++i)
+        if (g_det_out[i].p == p) {
+            g_det_free.push_back(g_det_out[i]);
+            g_det_out.erase(g_det_out.begin() + (long)i);
+            // a handful of idle buffers is plenty (one per worker thread and mate file)
+            while (g_det_free.size() > 40) { cudaFreeHost(g_det_free.front().p); g_det_free.erase(g_det_free.begin()); }
+            return;
+        }
+}
+
 // Pass 1 of quantify_hits_PE (src/strain_detect.c:465-491) for every read of one file, inflated and split on the
 // GPU.  out->len / hits / inf are per record in file order (all records, also those shorter than 31);
 // out->inf_* list the informative windows sorted by (record, offset) with their canonical k-mer.  The arrays are
@@ -1985,16 +2111,16 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     const ull n_rec = r.records;
     const double t_streamed = ing_now();
     out->n_records = n_rec; out->n_inf = n_inf; out->bases = r.bases; out->fasta = src.fasta ? 1u : 0u;
-    out->len = (uint32_t *)malloc((n_rec + 1) * 4); out->hits = (uint32_t *)malloc((n_rec + 1) * 4); out->inf = (uint32_t *)malloc((n_rec + 1) * 4);
-    out->inf_rec = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_off = (uint32_t *)malloc((n_inf + 1) * 4); out->inf_kmer = (uint64_t *)malloc((n_inf + 1) * 8);
-    if (!out->len || !out->hits || !out->inf || !out->inf_rec || !out->inf_off || !out->inf_kmer) {
-        s2_set_error("out of host memory");
-        s2_ingest_detect_free(out);
-        return -1;
-    }
-    auto d2h = [](void *dst, const void *from, size_t bytes) { return !bytes || cudaMemcpy(dst, from, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
+    // one pinned buffer: [len | hits | inf | inf_rec | inf_off | inf_kmer], six asynchronous copies, one wait
+    const size_t r4 = ((size_t)n_rec + 4) & ~(size_t)3, i4 = ((size_t)n_inf + 4) & ~(size_t)3;          // (keeps inf_kmer 8-byte aligned)
+    uint8_t *hb = (uint8_t *)det_buf_take(r4 * 12 + i4 * 16);
+    if (!hb) { s2_set_error("out of pinned host memory"); return -1; }
+    out->len = (uint32_t *)hb; out->hits = out->len + r4; out->inf = out->hits + r4;
+    out->inf_rec = out->inf + r4; out->inf_off = out->inf_rec + i4; out->inf_kmer = (uint64_t *)(out->inf_off + i4);
+    auto d2h = [&](void *dst, const void *from, size_t bytes) { return !bytes || cudaMemcpyAsync(dst, from, bytes, cudaMemcpyDeviceToHost, g->stream) == cudaSuccess; };
     if (!d2h(out->len, g->d_len_all, n_rec * 4) || !d2h(out->hits, g->d_hits_all, n_rec * 4) || !d2h(out->inf, g->d_inf_all, n_rec * 4) ||
-        !d2h(out->inf_rec, g->d_frec, n_inf * 4) || !d2h(out->inf_off, g->d_foff, n_inf * 4) || !d2h(out->inf_kmer, g->d_fkmer, n_inf * 8)) {
+        !d2h(out->inf_rec, g->d_frec, n_inf * 4) || !d2h(out->inf_off, g->d_foff, n_inf * 4) || !d2h(out->inf_kmer, g->d_fkmer, n_inf * 8) ||
+        cudaStreamSynchronize(g->stream) != cudaSuccess) {
         s2_set_error("reading the per-read results back failed: %s", cudaGetErrorString(cudaGetLastError()));
         s2_ingest_detect_free(out);
         return -1;
@@ -2017,7 +2143,7 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
 extern "C" void s2_ingest_detect_free(s2_ingest_detect_result *r)
 {
     if (!r) return;
-    free(r->len); free(r->hits); free(r->inf); free(r->inf_rec); free(r->inf_off); free(r->inf_kmer);
+    if (r->len) det_buf_give(r->len);                    // (the six arrays are one pinned buffer)
     memset(r, 0, sizeof *r);
 }
 

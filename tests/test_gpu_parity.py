@@ -1105,7 +1105,7 @@ def test_strain_detect_gpu_ingest_of_fasta_reads_and_ordinary_gz(s2, tmp_path, s
         assert ou.gunzip(out) == o.stdout, env
         assert p.stdout == open(os.path.join(tmp, "msg"), "rb").read()
         if "S2_STATS" in env:                                             # 10 file reads, all but the wrapped one on the GPU
-            assert b"files_gpu_ingest=9 files_host_reader=1" in p.stderr, p.stderr
+            assert b"files_gpu_ingest=9 files_host_reader=1 " in p.stderr, p.stderr
 
 
 @pytest.mark.parametrize("chunk_mb", [(2, 8), None], ids=["streamed", "one_chunk"])
