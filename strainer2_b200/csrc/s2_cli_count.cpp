@@ -12,6 +12,7 @@
 #include "s2_internal.h"
 
 #include <getopt.h>
+#include <fcntl.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -156,7 +157,12 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
     // at most) so that small files share a chunk; everything it does not handle goes through the host reader below
     const size_t max_run = gpu_ingest && !exotic ? (size_t)std::max(1, s2_env_int("S2_INGEST_BATCH", 16)) : 1;
     const uint64_t run_bytes = s2_env_u64("S2_INGEST_BATCH_MB", 32) << 20;
-    struct Taken { std::string path; s2_reader *r; };
+    struct Taken { std::string path; s2_reader *r; uint64_t size; };
+    // Reader threads read whole files into pinned ARENAS of their own (two per thread: one being filled while the job
+    // on the other is in flight) and hand the images to the ingest pipeline, which copies them to the device from
+    // there.  (Handing over paths made the pipeline read the files itself, under its lock: three pipelines = three
+    // threads reading, 15 GB/s for all sixteen reader threads - profiles/r2d_bench_n1.json, cli leg.)
+    const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 32), 1) << 20 : 0;
 
     auto reader = [&](int tid) {
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
@@ -164,6 +170,32 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
         // drains between runs); whatever the ingest hands back is then read by the host parser below
         struct Pending { std::vector<Taken> run; int col = 0; s2_ingest_job *job = nullptr; };
         Pending pending;
+        uint8_t *arena[2] = { nullptr, nullptr };
+        int arena_at = 0;
+        struct ArenaGuard { uint8_t **a; ~ArenaGuard() { s2_pinned_free(a[0]); s2_pinned_free(a[1]); } } arena_guard{ arena };
+        // the run's files, back to back in the arena; false: something did not fit or changed size (the run goes by path)
+        auto read_run = [&](std::vector<Taken> &run, uint8_t *dst, std::vector<const void *> &images, std::vector<uint64_t> &sizes) -> bool {
+            uint64_t at = 0;
+            images.clear(); sizes.clear();
+            for (auto &x : run) {
+                if (at + x.size > arena_bytes) return false;
+                const int fd = open(x.path.c_str(), O_RDONLY);
+                if (fd < 0) return false;
+                uint64_t done = 0;
+                while (done < x.size) {
+                    const ssize_t r = pread(fd, dst + at + done, x.size - done, (off_t)done);
+                    if (r <= 0) break;
+                    done += (uint64_t)r;
+                }
+                uint8_t extra;
+                const bool grown = done == x.size && pread(fd, &extra, 1, (off_t)done) > 0;
+                close(fd);
+                if (done != x.size || grown) return false;
+                images.push_back(dst + at); sizes.push_back(x.size);
+                at += x.size;
+            }
+            return true;
+        };
         auto host_read = [&](std::vector<Taken> &run, const std::vector<int> &handled, int col) {
             for (size_t k = 0; k < run.size(); ++k) {
                 s2_reader *r = run[k].r;
@@ -220,6 +252,9 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                 while (run.size() < max_run && bytes < run_bytes) {
                     if (stop.load() || next >= work.size()) break;
                     if (!run.empty() && work[next].col != col) break;
+                    struct stat sb_next;
+                    const uint64_t size_next = stat(work[next].path.c_str(), &sb_next) == 0 ? (uint64_t)sb_next.st_size : run_bytes;
+                    if (!run.empty() && arena_bytes && !work[next].skip && bytes + size_next > arena_bytes) break;      // the run must fit an arena
                     S2WorkItem &it = work[next++];
                     if (progress) {
                         time_t now = time(nullptr);
@@ -233,9 +268,8 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                         break;
                     }
                     col = it.col;
-                    run.push_back({ it.path, r });
-                    struct stat sb;
-                    bytes += stat(it.path.c_str(), &sb) == 0 ? (uint64_t)sb.st_size : run_bytes;
+                    run.push_back({ it.path, r, size_next });
+                    bytes += size_next;
                 }
             }
             if (run.empty()) break;
@@ -243,7 +277,15 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                 // BGZF / plain strict FASTQ + FASTA: hardware inflate + record splitting on the GPU, nothing parsed here
                 std::vector<const char *> paths;
                 for (auto &x : run) paths.push_back(x.path.c_str());
-                s2_ingest_job *job = s2_ingest_submit_files(w.ctx, w.table, paths.data(), (int)paths.size(), col);
+                std::vector<const void *> images; std::vector<uint64_t> sizes;
+                if (arena_bytes && !arena[arena_at]) arena[arena_at] = (uint8_t *)s2_pinned_alloc(arena_bytes);
+                s2_ingest_job *job;
+                if (arena_bytes && arena[arena_at] && read_run(run, arena[arena_at], images, sizes)) {
+                    job = s2_ingest_submit_mem_batch(w.ctx, w.table, images.data(), sizes.data(), (int)images.size(), col);
+                    arena_at ^= 1;                           // the job before this one is finished below, before its arena is filled again
+                } else {
+                    job = s2_ingest_submit_files(w.ctx, w.table, paths.data(), (int)paths.size(), col);      // (a file bigger than an arena: streamed from the file)
+                }
                 if (!job) {
                     std::lock_guard<std::mutex> g(mu);
                     if (open_error.empty()) open_error = s2_last_error();
