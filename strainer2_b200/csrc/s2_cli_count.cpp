@@ -162,7 +162,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
     // on the other is in flight) and hand the images to the ingest pipeline, which copies them to the device from
     // there.  (Handing over paths made the pipeline read the files itself, under its lock: three pipelines = three
     // threads reading, 15 GB/s for all sixteen reader threads - profiles/r2d_bench_n1.json, cli leg.)
-    const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 32), 1) << 20 : 0;
+    const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 16), 1) << 20 : 0;
 
     auto reader = [&](int tid) {
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };

@@ -709,6 +709,9 @@ struct GzStage {
     uint16_t *d_sym = nullptr;
     GzSubResult *d_res = nullptr;
     uint8_t *d_win = nullptr;
+    uint8_t *d_carry = nullptr;          // streamed files: the window a piece leaves to the next one
+    uint32_t *d_ml = nullptr, *d_ml_count = nullptr;      // per sub-chunk: the bytes its window copies from the window before (gz_tail_kernel)
+    size_t sym_subs = 0, win_slots = 0;  // what d_sym / d_win hold now (they grow with the batches: gz_stage_reserve)
     uint64_t *d_sub_off = nullptr;
     GzFileDesc *h_files = nullptr, *d_files = nullptr;
     uint32_t *h_sub_file = nullptr, *d_sub_file = nullptr, *h_slice0 = nullptr, *d_slice0 = nullptr;
@@ -781,7 +784,7 @@ static void ingest_free(s2_ingest *g)
     }
     {
         GzStage &z = g->gz;
-        cudaFreeHost(z.h_comp); cudaFree(z.d_comp); cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_sub_off);
+        cudaFreeHost(z.h_comp); cudaFree(z.d_comp); cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_carry); cudaFree(z.d_ml); cudaFree(z.d_ml_count); cudaFree(z.d_sub_off);
         cudaFreeHost(z.h_files); cudaFree(z.d_files); cudaFreeHost(z.h_sub_file); cudaFree(z.d_sub_file); cudaFreeHost(z.h_slice0); cudaFree(z.d_slice0);
         cudaFree(z.d_fres); cudaFree(z.d_crc_acc); cudaFree(z.d_piece_text); cudaFreeHost(z.h_fres);
         if (z.idle) cudaEventDestroy(z.idle);
@@ -1369,14 +1372,16 @@ static int ingest_gz_stage_init(s2_ingest *g)
     z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 32), 4), 4096) << 10;
     // symbols one sub-chunk may produce: S2_GZ_RATIO x its compressed bytes (FASTQ deflates 4-6 : 1, FASTA 3.5 : 1) plus the
     // run-on to the first block boundary behind the next cut; a sub-chunk that needs more makes its file the host reader's
-    z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 10), 2), 64) + (384u << 10);
+    z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64) + (256u << 10);
     z.max_files = ING_MAX_FILES;
     z.max_sub = (uint32_t)(z.comp_cap / z.sub_bytes) + z.max_files;
     CK(cudaMalloc((void **)&z.d_comp, z.comp_cap + (size_t)z.max_files * 32 + 256));
-    CK(cudaMalloc((void **)&z.d_sym, (size_t)z.max_sub * z.sub_cap * sizeof(uint16_t)));
+    // (the symbol area - 1 MB per sub-chunk - and the windows are sized by the batches that come: gz_stage_reserve.  Round 2's
+    // first version took them for the largest batch there could be, 12 GB per pipeline, and three strain_detect workers
+    // spent 0.8 s each in cudaMalloc - profiles/r2g_detect_bench.txt)
     CK(cudaMalloc((void **)&z.d_res, (size_t)z.max_sub * gz_sub_result_bytes()));
-    CK(cudaMalloc((void **)&z.d_win, ((size_t)z.max_sub + z.max_files + 1) * 32768));
-    CK(cudaMemset(z.d_win, 0, ((size_t)z.max_sub + z.max_files + 1) * 32768));
+    CK(cudaMalloc((void **)&z.d_carry, 32768));
+    CK(cudaMalloc((void **)&z.d_ml_count, (size_t)z.max_sub * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&z.d_sub_off, (size_t)z.max_sub * sizeof(uint64_t)));
     CK(cudaHostAlloc((void **)&z.h_files, (size_t)z.max_files * sizeof(GzFileDesc), cudaHostAllocDefault));
     CK(cudaMalloc((void **)&z.d_files, (size_t)z.max_files * sizeof(GzFileDesc)));
@@ -1393,6 +1398,31 @@ static int ingest_gz_stage_init(s2_ingest *g)
 
 static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk &ch, bool bgzf, bool fasta, int mode, int col, unsigned inc, bool want_result);
 
+// room for a batch of n_sub sub-chunks in n_files files.  The stage must be idle (z.idle waited for).
+static int gz_stage_reserve(s2_ingest *g, uint32_t n_sub, uint32_t n_files)
+{
+    GzStage &z = g->gz;
+    const size_t want_win = (size_t)n_sub + n_files + 1;
+    if (n_sub <= z.sym_subs && want_win <= z.win_slots) return 0;
+    CK(cudaStreamSynchronize(g->inflate_stream));
+    if (n_sub > z.sym_subs) {
+        const size_t subs = std::min<size_t>(z.max_sub, (size_t)n_sub + n_sub / 4 + 64);
+        cudaFree(z.d_sym); z.d_sym = nullptr; z.sym_subs = 0;
+        cudaFree(z.d_ml); z.d_ml = nullptr;
+        if (cudaMalloc((void **)&z.d_sym, subs * z.sub_cap * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&z.d_ml, subs * 32768 * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip symbols)"); return -1; }
+        z.sym_subs = subs;
+    }
+    if (want_win > z.win_slots) {
+        const size_t slots = std::min<size_t>((size_t)z.max_sub + z.max_files + 1, want_win + want_win / 4 + 64);
+        cudaFree(z.d_win); z.d_win = nullptr; z.win_slots = 0;
+        if (cudaMalloc((void **)&z.d_win, slots * 32768) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip windows)"); return -1; }
+        CK(cudaMemsetAsync(z.d_win, 0, slots * 32768, g->inflate_stream));
+        z.win_slots = slots;
+    }
+    return 0;
+}
+
 // ---- one big ordinary .gz file, streamed: PIECES of S2_GZ_BATCH_MB through the gz stage, each piece's text in slices
 // through the ring.  A piece is decoded like a batch of one file; its first sub-chunk finds its own block start, the
 // chain continues where the previous piece ended (with that piece's last window), the stream's size and CRC-32 are
@@ -1405,12 +1435,20 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
     g->call_chunk0 = g->n_chunks;
     const size_t tail = std::min<size_t>(4u << 20, z.comp_cap / 4);             // bytes of the next piece the last sub-chunk may run on into
     const size_t piece_bytes = (z.comp_cap - tail) / z.sub_bytes * z.sub_bytes;
-    if (!z.d_piece_text) {
-        z.piece_text_cap = (size_t)std::min<uint64_t>((uint64_t)z.comp_cap * s2_env_u64("S2_GZ_RATIO", 10), 4ull << 30);
-        CK(cudaMalloc((void **)&z.d_piece_text, z.piece_text_cap + 64));
-        CK(cudaHostAlloc((void **)&z.h_fres, sizeof(GzFileResult), cudaHostAllocDefault));
-    }
     const ssize_t size = src.size();
+    {
+        // the text of one piece: S2_GZ_RATIO x its compressed bytes (more makes the file the host reader's), for the pieces this file will have
+        const uint64_t ratio = std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64);
+        const size_t want_cap = (size_t)std::min<uint64_t>((uint64_t)std::min<size_t>(piece_bytes, (size_t)std::max<ssize_t>(size, 0)) * ratio + (1u << 20), 4ull << 30);
+        if (want_cap > z.piece_text_cap) {
+            CK(cudaEventSynchronize(z.idle));
+            CK(cudaStreamSynchronize(g->inflate_stream));
+            cudaFree(z.d_piece_text); z.d_piece_text = nullptr; z.piece_text_cap = 0;
+            if (cudaMalloc((void **)&z.d_piece_text, want_cap + 64) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip text)"); return -1; }
+            z.piece_text_cap = want_cap;
+        }
+        if (!z.h_fres) CK(cudaHostAlloc((void **)&z.h_fres, sizeof(GzFileResult), cudaHostAllocDefault));
+    }
     uint8_t head[4096];
     const ssize_t hn = src.peek(head, sizeof head, 0);
     const uint64_t hl = hn > 0 ? s2_gzip_header_len(head, (uint64_t)hn) : 0;
@@ -1419,11 +1457,12 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
     ull text_total = 0;
     uint64_t chain_abs = hl * 8;
     uint32_t crc_raw = 0;
-    uint8_t *d_carry = z.d_win + ((size_t)z.max_sub + z.max_files) * 32768;       // the last window slot of the stage
+    uint8_t *d_carry = z.d_carry;
     for (off_t base = 0; !broken && !finished && base < size; base += (off_t)piece_bytes) {
         const bool last_piece = (size_t)base + piece_bytes >= (size_t)size;
         const size_t want = std::min<size_t>(piece_bytes + tail, (size_t)size - (size_t)base);
         CK(cudaEventSynchronize(z.idle));                                        // the previous piece's text has left the stage
+        if (gz_stage_reserve(g, (uint32_t)((std::min<size_t>(piece_bytes, (size_t)size - (size_t)base) + z.sub_bytes - 1) / z.sub_bytes), 1)) return -1;
         if (src.mem) {
             CK(cudaMemcpyAsync(z.d_comp, src.mem + base, want, cudaMemcpyHostToDevice, g->copy_stream));
         } else {
@@ -1447,7 +1486,7 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
         CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
         if (base) CK(cudaMemcpyAsync(z.d_win, d_carry, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));      // the window the previous piece left
         gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, d.n_sub, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
-        gz_launch_chain(z.d_comp, z.d_files, 1, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
+        gz_launch_chain(z.d_comp, z.d_files, 1, z.d_sub_file, d.n_sub, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_ml, z.d_ml_count, z.d_sub_off, z.d_fres, g->inflate_stream);
         gz_launch_translate(z.d_files, z.d_sub_file, 0, d.n_sub, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres, z.d_piece_text, g->inflate_stream);
         gz_launch_crc(z.d_files, 0, 1, z.d_slice0, (uint32_t)(z.piece_text_cap / 4096) + 1, z.d_piece_text, z.d_fres, z.d_crc_acc, nullptr, g->inflate_stream);
         CK(cudaMemcpyAsync(d_carry, z.d_win + (size_t)d.n_sub * 32768, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));
@@ -1664,6 +1703,7 @@ struct s2_ingest_job {
             if (members.empty()) continue;
             // ---- bytes: caller's memory goes straight to the device, files through the stage's pinned buffer ----------
             CK(cudaEventSynchronize(z.idle));                       // the previous batch is out of the stage's buffers
+            if (gz_stage_reserve(g, n_sub, n_files)) return -1;
             if (!srcs[members[0]].mem && !z.h_comp) CK(cudaHostAlloc((void **)&z.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
             CK(cudaMemsetAsync(z.d_comp, 0, comp_used + 64, g->copy_stream));              // zero padding behind every file
             size_t off = 0;
@@ -1719,7 +1759,7 @@ struct s2_ingest_job {
             CK(cudaEventRecord(up, g->copy_stream));
             CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
             gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, sub0, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
-            gz_launch_chain(z.d_comp, z.d_files, nf, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
+            gz_launch_chain(z.d_comp, z.d_files, nf, z.d_sub_file, sub0, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_ml, z.d_ml_count, z.d_sub_off, z.d_fres, g->inflate_stream);
             CK(cudaGetLastError());
             // ---- one ordinary group per plan ------------------------------------------------------------------------------
             for (const Plan &p : plans) {
@@ -2089,6 +2129,8 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     memset(&r, 0, sizeof r);
     int rc = 0;
     const double t_ready = ing_now();
+    tr_wait = tr_h2d = tr_decomp = tr_launch = 0;
+    tr_on = s2_env_int("S2_INGEST_TRACE", 0) >= 2;
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!g->d_frec) {
             if (!g->f_cap) g->f_cap = 1ull << 20;
@@ -2110,6 +2152,8 @@ extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s
     if (rc) return rc == 2 ? -1 : rc;
     const ull n_rec = r.records;
     const double t_streamed = ing_now();
+    if (tr_on) fprintf(stderr, "[s2 ingest] detect %s: host time in ring wait %.0f us, inflate calls %.0f us, launches %.0f us\n", path, tr_wait, tr_decomp, tr_launch);
+    ingest_trace_timeline();
     out->n_records = n_rec; out->n_inf = n_inf; out->bases = r.bases; out->fasta = src.fasta ? 1u : 0u;
     // one pinned buffer: [len | hits | inf | inf_rec | inf_off | inf_kmer], six asynchronous copies, one wait
     const size_t r4 = ((size_t)n_rec + 4) & ~(size_t)3, i4 = ((size_t)n_inf + 4) & ~(size_t)3;          // (keeps inf_kmer 8-byte aligned)
