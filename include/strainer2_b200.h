@@ -166,6 +166,9 @@ int         s2_ingest_detect_file(s2_ctx *ctx, s2_table *t, const char *path, s2
 void        s2_ingest_detect_free(s2_ingest_detect_result *r);
 void        s2_ingest_thread_cleanup(void);               /* no-op since the pipelines belong to the context */
 int         s2_ingest_warm(s2_ctx *ctx, int n_pipes);
+/* the same for the gunzip stage of those pipelines (ordinary .gz inputs): its symbol area is 1 MB per 32 KB of compressed
+ * bytes, and cudaMalloc maps about 10 GB/s - worth doing beside the table build when the first listed file is a .gz */
+int         s2_ingest_warm_gz(s2_ctx *ctx, int n_pipes, uint64_t batch_comp_bytes);
 void        s2_ingest_reset(s2_ctx *ctx);                 /* releases the context's pipelines (no job may be in flight); the next call makes new ones */
 /* 1 after the hardware decompression engine met a DEFLATE block it cannot decode (a damaged BGZF member): the engine
  * reports that as a sticky launch failure (measured, profiles/r1s_hw_decompression_error_probe.txt), the CUDA context

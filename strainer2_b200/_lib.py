@@ -76,6 +76,7 @@ SIGNATURES = {
     "s2_ingest_detect_free": (None, [C.c_void_p]),
     "s2_ingest_thread_cleanup": (None, []),
     "s2_ingest_warm": (C.c_int, [C.c_void_p, C.c_int]),
+    "s2_ingest_warm_gz": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),
     "s2_ingest_reset": (None, [C.c_void_p]),
     "s2_ingest_engine_failed": (C.c_int, []),
     "s2_gz_writer_open": (C.c_void_p, [C.c_char_p, C.c_int]),

@@ -128,6 +128,33 @@ int s2_default_reader_threads()
 }
 
 // The list drivers GEN_all_kmer_counts / GEN_all_kmer_counts_skip_file (src/genome_compare.c:115-177) for a
+// does the first file a list names begin like an ordinary (not block-) gzip file?  Nothing is reported here: the list is
+// read again, with the reference's messages, when its turn comes
+bool s2_list_starts_with_plain_gz(const char *list_file)
+{
+    if (!list_file) return false;
+    FILE *fp = fopen(list_file, "r");
+    if (!fp) return false;
+    char *line = nullptr; size_t cap = 0;
+    bool gz = false;
+    if (getline(&line, &cap, fp) > 0) {
+        char *pos = strchr(line, '\n');
+        if (pos) *pos = '\0';
+        const char *path = line;
+        if (const char *tab = strrchr(line, '\t')) path = tab + 1;          // (strain_detect batch lines: the last column is a file)
+        FILE *f = fopen(path, "rb");
+        if (f) {
+            unsigned char h[16];
+            const size_t n = fread(h, 1, sizeof h, f);
+            gz = n >= 16 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && !((h[3] & 4) && h[12] == 'B' && h[13] == 'C');
+            fclose(f);
+        }
+    }
+    free(line);
+    fclose(fp);
+    return gz;
+}
+
 // whole work list: reader threads take files in list order (progress line and "skipping" note written
 // at dispatch, under the lock, so their order is the reference's), inflate + parse them straight into
 // pinned batches and submit those to the GPU.  Returns false after a failure; open_error carries the
@@ -155,14 +182,14 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
 
     // GPU ingest takes runs of files (same counter column, S2_INGEST_BATCH files / S2_INGEST_BATCH_MB compressed bytes
     // at most) so that small files share a chunk; everything it does not handle goes through the host reader below
-    const size_t max_run = gpu_ingest && !exotic ? (size_t)std::max(1, s2_env_int("S2_INGEST_BATCH", 16)) : 1;
+    const size_t max_run = gpu_ingest && !exotic ? (size_t)std::max(1, s2_env_int("S2_INGEST_BATCH", 32)) : 1;
     const uint64_t run_bytes = s2_env_u64("S2_INGEST_BATCH_MB", 32) << 20;
     struct Taken { std::string path; s2_reader *r; uint64_t size; };
     // Reader threads read whole files into pinned ARENAS of their own (two per thread: one being filled while the job
     // on the other is in flight) and hand the images to the ingest pipeline, which copies them to the device from
     // there.  (Handing over paths made the pipeline read the files itself, under its lock: three pipelines = three
     // threads reading, 15 GB/s for all sixteen reader threads - profiles/r2d_bench_n1.json, cli leg.)
-    const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 16), 1) << 20 : 0;
+    const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 32), 1) << 20 : 0;
 
     auto reader = [&](int tid) {
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
@@ -385,7 +412,11 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
         fprintf(stderr, "could not read file %s GEN_hash_sequences_set_count_vec()\n", r_file);   // src/genome_compare.c:986
         return fail(nullptr);
     }
-    for (int g = 0; g < n_gpus && warm_pipes; ++g) warmers.emplace_back([&, g]() { s2_ingest_warm(ctxs[g], warm_pipes); });
+    // (an ordinary .gz at the head of a list: the pipelines' gunzip stages are made ready as well - s2_ingest_warm_gz)
+    const bool gz_inputs = warm_pipes && (s2_list_starts_with_plain_gz(A_file) || s2_list_starts_with_plain_gz(B_file));
+    const uint64_t arena_mb = std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 32), 1);
+    for (int g = 0; g < n_gpus && warm_pipes; ++g)
+        warmers.emplace_back([&, g]() { if (gz_inputs) s2_ingest_warm_gz(ctxs[g], warm_pipes, arena_mb << 20); else s2_ingest_warm(ctxs[g], warm_pipes); });
     struct JoinGuard { std::vector<std::thread> &v; ~JoinGuard() { for (auto &t : v) if (t.joinable()) t.join(); } } warm_guard{ warmers };
     // windows of the -r genome with a byte outside ACGTN become string keys on the host;
     // nullptr (the normal case) means no such window exists and the host never looks at a window again
@@ -414,6 +445,21 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     if (s2_read_list(B_file, 2, nullptr, work)) return fail(nullptr);
     if (C_file && s2_read_list(C_file, 3, r_file, work)) return fail(nullptr);
 
+    // The order of the output rows (the reference table's slot order, replayed from the keys' djb2 values: 0.2 s of
+    // sequential host work for 5 M keys) depends on the -r genome alone: it is worked out beside the scan.
+    const bool host_format = exotic != nullptr || s2_env_int("S2_HOST_FORMAT", 0);
+    std::vector<uint32_t> early_order;
+    int early_rc = 0; std::string early_err;
+    std::thread order_thread;
+    struct OrderGuard { std::thread &t; ~OrderGuard() { if (t.joinable()) t.join(); } } order_guard{ order_thread };
+    if (!exotic && !host_format)
+        order_thread = std::thread([&]() {
+            const uint64_t nk = s2_table_n_keys(table);
+            std::vector<uint32_t> h(nk);
+            early_order.resize(nk);
+            if (s2_table_export(table, nullptr, h.data(), nullptr) || s2_roworder_emulate(h.data(), nk, 0, early_order.data(), nullptr)) { early_rc = -1; early_err = s2_last_error(); }
+        });
+
     std::string open_error;
     uint64_t total_bases = 0, total_lookups = 0;
     join_all(warmers);
@@ -437,7 +483,8 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     std::vector<uint64_t> keys;
     std::vector<uint32_t> djb2(n), pos, cols[4];
     const uint32_t *colp[4] = { nullptr, nullptr, nullptr, nullptr };
-    const bool host_format = exotic != nullptr || s2_env_int("S2_HOST_FORMAT", 0);
+    if (order_thread.joinable()) order_thread.join();
+    if (early_rc) return fail(early_err.c_str());
     if (host_format) {
         keys.resize(n);
         if (exotic) pos.resize(n);
@@ -447,11 +494,14 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
             if (s2_table_counts_fetch(table, k, cols[k].data())) return fail(s2_last_error());
             colp[k] = cols[k].data();
         }
-    } else if (s2_table_export(table, nullptr, djb2.data(), nullptr)) return fail(s2_last_error());
+    }
     if (!exotic) {
         // only the djb2 values leave the device for the row-order replay; the text is formatted on the GPU
-        std::vector<uint32_t> order(n);
-        if (s2_roworder_emulate(djb2.data(), n, 0, order.data(), nullptr)) return fail(s2_last_error());
+        std::vector<uint32_t> order;
+        if (host_format) {
+            order.resize(n);
+            if (s2_roworder_emulate(djb2.data(), n, 0, order.data(), nullptr)) return fail(s2_last_error());
+        } else order.swap(early_order);
         if (host_format ? s2_format_count_table(stdout, keys.data(), order.data(), n, colp, n_print, n_threads)
                         : s2_table_format(table, order.data(), n_print, stdout)) return fail(s2_last_error());
     } else {

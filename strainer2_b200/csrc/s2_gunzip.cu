@@ -23,6 +23,7 @@
 
 #define GZ_WARPS 4                       /* decoding warps per CTA: 4 x 6.4 KB of tables */
 #define GZ_CHAIN_THREADS 1024
+#define GZ_CHAIN_LENS 8192u
 
 // Occupancy against registers (profiles/r2f_gz_decode_ncu.txt): a warp's instruction stream is one dependent chain - it issues
 // about once in nine cycles - so the schedulers fill up only with eight or more warps each; 64 registers (8 CTAs per SM,
@@ -43,62 +44,18 @@ gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict_
                 (uint64_t)(j + 1) * sub_bytes * 8ull, search_limit_bits, sym + (uint64_t)sub * sub_cap, sub_cap, tables[warp], res + sub, (int)lane, 32);
 }
 
-// The window behind sub-chunk j (the last 32 KB of text up to its end) is, byte for byte, either a literal of the sub-chunk's
-// own last symbols - known now, for every sub-chunk at once - or a copy of one byte of the window before it: a marker, or
-// the tail of that window where the sub-chunk produced fewer than 32 K symbols.  gz_tail_kernel writes the literal bytes
-// of every window and lists the copies (place << 16 | place in the previous window); the chain kernel, which must go
-// through a file's sub-chunks in order, then only moves the listed bytes - a few per cent of a window - instead of
-// building 32 KB per step (a 96 MB piece of a big file is 3,000 steps: 43 ms when each step built a window through global
-// memory, 8.8 ms with the windows in shared memory, profiles/r2g_pgunzip_probe.txt).
-#define GZ_TAIL_THREADS 256
-__global__ void __launch_bounds__(GZ_TAIL_THREADS)
-gz_tail_kernel(const GzFileDesc *__restrict__ files, const uint32_t *__restrict__ sub_file, const uint16_t *__restrict__ sym, uint32_t sub_cap,
-               const GzSubResult *__restrict__ res, uint8_t *win, uint32_t *__restrict__ ml, uint32_t *__restrict__ ml_count)
-{
-    const uint32_t sub = blockIdx.x, fi = sub_file[sub];
-    const uint32_t n_out = res[sub].n_out;
-    const uint16_t *sy = sym + (uint64_t)sub * sub_cap;
-    uint8_t *wn = win + ((uint64_t)sub + fi + 1u) * GZ_WINDOW;                  // window j + 1 of its file = behind sub-chunk j
-    uint32_t *list = ml + (uint64_t)sub * GZ_WINDOW;
-    __shared__ uint32_t s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t k0 = threadIdx.x * 4u; k0 < GZ_WINDOW; k0 += GZ_TAIL_THREADS * 4u) {
-        uint32_t bytes = 0, copies[4]; bool is_copy[4];
-#pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
-            const uint32_t k = k0 + u;
-            const int32_t idx = (int32_t)n_out - (int32_t)GZ_WINDOW + (int32_t)k;
-            const uint32_t sy_k = idx >= 0 ? sy[idx] : 0u;
-            is_copy[u] = idx < 0 || sy_k >= 256u;
-            copies[u] = k << 16 | (idx < 0 ? k + n_out : sy_k - 256u);
-            bytes |= (is_copy[u] ? 0u : sy_k) << (8u * u);
-        }
-        *reinterpret_cast<uint32_t *>(wn + k0) = bytes;
-#pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {                                      // warp-aggregated append
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_copy[u]);
-            if (m) {
-                uint32_t base = 0;
-                if (lane == (uint32_t)__ffs(m) - 1u) base = atomicAdd(&s_n, (uint32_t)__popc(m));
-                base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-                if (is_copy[u]) list[base + __popc(m & ((1u << lane) - 1u))] = copies[u];
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) ml_count[sub] = s_n;
-}
-
 // one CTA per file.  Phase 0, in parallel over the file's sub-chunks: the chain test (sub-chunk j must start where j-1
 // ended), the first sub-chunk that ends the stream or breaks the chain, text offsets by a block scan.  Phase 1, in order:
-// the copies of window j+1 (gz_tail_kernel's list) from window j; the next step's list is loaded while this one's bytes move.
-#define GZ_CHAIN_PRE 4
+// window j+1 from the last 32 KB of sub-chunk j's symbols and window j.  That loop is the serial part of a big file
+// (3,000 steps per 96 MB piece), so a step is one global round trip and one barrier: both windows live in shared memory
+// (ping-pong), the symbols of step j+1 are pulled towards L2 while step j runs, and window j goes out to global memory
+// (for the translate pass) with 128-bit stores during step j+1.
 __global__ void __launch_bounds__(GZ_CHAIN_THREADS)
-gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const GzSubResult *__restrict__ res, uint8_t *win,
-                const uint32_t *__restrict__ ml, const uint32_t *__restrict__ ml_count, uint64_t *__restrict__ sub_off, GzFileResult *__restrict__ out)
+gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const uint16_t *__restrict__ sym, uint32_t sub_cap,
+                const GzSubResult *__restrict__ res, uint8_t *win, uint64_t *__restrict__ sub_off, GzFileResult *__restrict__ out)
 {
+    extern __shared__ __align__(16) uint8_t s_win[];            // 2 x GZ_WINDOW, then GZ_CHAIN_LENS lengths
+    uint32_t *s_lens = reinterpret_cast<uint32_t *>(s_win + 2 * GZ_WINDOW);      // symbols per sub-chunk (the loop below must not wait for global memory to learn them)
     const GzFileDesc f = files[blockIdx.x];
     __shared__ uint32_t s_first;                                 // first sub-chunk that is not a plain link of the chain
     __shared__ uint64_t s_warp[GZ_CHAIN_THREADS / 32];
@@ -126,6 +83,7 @@ gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__
     for (uint32_t j0 = 0; j0 < f.n_sub; j0 += GZ_CHAIN_THREADS) {
         const uint32_t j = j0 + tid;
         const uint64_t len = j < n_steps ? r[j].n_out : 0u;
+        if (j < GZ_CHAIN_LENS) s_lens[j] = (uint32_t)len;
         uint64_t inc = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint64_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (uint32_t)o) inc += n; }
@@ -141,33 +99,55 @@ gz_chain_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__
     const uint64_t total = s_carry;
     // windows, in order
     uint8_t *w0 = win + ((uint64_t)f.sub0 + blockIdx.x) * GZ_WINDOW;          // n_sub + 1 windows of this file
-    if (state >= 0 && n_steps) {                                 // (a broken file's windows are nobody's business)
-        const uint32_t *cnt = ml_count + f.sub0;
-        const uint32_t *lists = ml + (uint64_t)f.sub0 * GZ_WINDOW;
-        uint32_t n_cur = cnt[0], e_cur[GZ_CHAIN_PRE];
-#pragma unroll
-        for (int u = 0; u < GZ_CHAIN_PRE; ++u) e_cur[u] = lists[u * GZ_CHAIN_THREADS + tid];          // (a list has room for 32 K entries: always readable)
+    if (state >= 0) {                                            // (a broken file's windows are nobody's business)
+        for (uint32_t i = tid; i < GZ_WINDOW / 16; i += GZ_CHAIN_THREADS) reinterpret_cast<uint4 *>(s_win)[i] = reinterpret_cast<const uint4 *>(w0)[i];
+        __syncthreads();
         for (uint32_t j = 0; j < n_steps; ++j) {
-            const uint8_t *wp = w0 + (uint64_t)j * GZ_WINDOW;
-            uint8_t *wn = w0 + (uint64_t)(j + 1u) * GZ_WINDOW;
-            const uint32_t *list = lists + (uint64_t)j * GZ_WINDOW;
-            uint32_t n_nxt = 0, e_nxt[GZ_CHAIN_PRE];
-            if (j + 1u < n_steps) {
-                n_nxt = cnt[j + 1u];
+            const uint8_t *prev = s_win + (j & 1u) * GZ_WINDOW;
+            uint8_t *next = s_win + ((j + 1u) & 1u) * GZ_WINDOW;
+            const uint32_t len = j < GZ_CHAIN_LENS ? s_lens[j] : r[j].n_out;
+            const uint16_t *sy = sym + (uint64_t)(f.sub0 + j) * sub_cap;
+            // the symbols that matter: the last min(len, 32 K); aligned 32-bit loads of two symbols, 17 per thread in flight
+            const uint32_t used = len < GZ_WINDOW ? len : GZ_WINDOW;
+            const uint32_t s_lo = len - used;                                  // first symbol that lands in the window ...
+            const uint32_t k_lo = GZ_WINDOW - used;                            // ... at this place
+            const uint32_t a = s_lo & ~1u;
+            const uint32_t n_words = (len - a + 1u) / 2u;                      // <= 16385
+            uint32_t wv[17];
 #pragma unroll
-                for (int u = 0; u < GZ_CHAIN_PRE; ++u) e_nxt[u] = list[GZ_WINDOW + u * GZ_CHAIN_THREADS + tid];
+            for (int i = 0; i < 17; ++i) {
+                const uint32_t w = (uint32_t)i * GZ_CHAIN_THREADS + tid;
+                wv[i] = w < n_words ? *reinterpret_cast<const uint32_t *>(sy + a + 2u * w) : 0u;
             }
-#pragma unroll
-            for (int u = 0; u < GZ_CHAIN_PRE; ++u)
-                if (u * GZ_CHAIN_THREADS + tid < n_cur) wn[e_cur[u] >> 16] = __ldcg(wp + (e_cur[u] & 0xFFFFu));
-            for (uint32_t i = GZ_CHAIN_PRE * GZ_CHAIN_THREADS + tid; i < n_cur; i += GZ_CHAIN_THREADS) {
-                const uint32_t e = list[i];
-                wn[e >> 16] = __ldcg(wp + (e & 0xFFFFu));
+            if (j + 1 < n_steps) {                                             // next step's symbols -> L2
+                const uint32_t len2 = j + 1 < GZ_CHAIN_LENS ? s_lens[j + 1] : r[j + 1].n_out, used2 = len2 < GZ_WINDOW ? len2 : GZ_WINDOW;
+                const uint8_t *p2 = reinterpret_cast<const uint8_t *>(sym + (uint64_t)(f.sub0 + j + 1) * sub_cap + (len2 - used2));
+                if (tid * 128u < used2 * 2u) asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + tid * 128u));
             }
-            __syncthreads();                                     // window j + 1 is complete (and visible to the block) before step j + 1 reads it
-            n_cur = n_nxt;
+            // window j (complete since the last barrier) -> global memory, for the translate pass
+            {
+                uint4 *g = reinterpret_cast<uint4 *>(w0 + (uint64_t)j * GZ_WINDOW);
+                const uint4 *sp = reinterpret_cast<const uint4 *>(prev);
+                g[tid] = sp[tid]; g[tid + GZ_CHAIN_THREADS] = sp[tid + GZ_CHAIN_THREADS];
+            }
+            // where this sub-chunk produced fewer than 32 K symbols the window begins with the tail of the previous one
+            for (uint32_t k = tid; k < k_lo; k += GZ_CHAIN_THREADS) next[k] = prev[k + used];
 #pragma unroll
-            for (int u = 0; u < GZ_CHAIN_PRE; ++u) e_cur[u] = e_nxt[u];
+            for (int i = 0; i < 17; ++i) {
+                const uint32_t w = (uint32_t)i * GZ_CHAIN_THREADS + tid;
+                if (w < n_words) {
+                    const uint32_t s0 = a + 2u * w;                            // symbol index of the low half
+                    const uint32_t lo = wv[i] & 0xFFFFu, hi = wv[i] >> 16;
+                    if (s0 >= s_lo) next[k_lo + (s0 - s_lo)] = lo < 256u ? (uint8_t)lo : prev[lo - 256u];
+                    if (s0 + 1u < len) next[k_lo + (s0 + 1u - s_lo)] = hi < 256u ? (uint8_t)hi : prev[hi - 256u];
+                }
+            }
+            __syncthreads();
+        }
+        {                                                                      // the last window (a later piece of the file starts from it)
+            uint4 *g = reinterpret_cast<uint4 *>(w0 + (uint64_t)n_steps * GZ_WINDOW);
+            const uint4 *sp = reinterpret_cast<const uint4 *>(s_win + (n_steps & 1u) * GZ_WINDOW);
+            g[tid] = sp[tid]; g[tid + GZ_CHAIN_THREADS] = sp[tid + GZ_CHAIN_THREADS];
         }
     }
     if (threadIdx.x == 0) {
@@ -318,13 +298,12 @@ void gz_launch_decode(const uint8_t *comp, const GzFileDesc *files, const uint32
     else gz_decode_kernel<8><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
 }
 
-void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint32_t *sub_file, uint32_t n_sub, const uint16_t *sym,
-                     uint32_t sub_cap, const GzSubResult *res, uint8_t *win, uint32_t *ml, uint32_t *ml_count, uint64_t *sub_off, GzFileResult *fres,
-                     cudaStream_t st)
+void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint16_t *sym, uint32_t sub_cap, const GzSubResult *res,
+                     uint8_t *win, uint64_t *sub_off, GzFileResult *fres, cudaStream_t st)
 {
     if (!n_files) return;
-    if (n_sub) gz_tail_kernel<<<n_sub, GZ_TAIL_THREADS, 0, st>>>(files, sub_file, sym, sub_cap, res, win, ml, ml_count);
-    gz_chain_kernel<<<n_files, GZ_CHAIN_THREADS, 0, st>>>(comp, files, res, win, ml, ml_count, sub_off, fres);
+    cudaFuncSetAttribute(gz_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GZ_WINDOW + GZ_CHAIN_LENS * 4);       // (per device: every launch)
+    gz_chain_kernel<<<n_files, GZ_CHAIN_THREADS, 2 * GZ_WINDOW + GZ_CHAIN_LENS * 4, st>>>(comp, files, sym, sub_cap, res, win, sub_off, fres);
 }
 
 size_t gz_sub_result_bytes(void) { return sizeof(GzSubResult); }

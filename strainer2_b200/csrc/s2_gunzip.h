@@ -35,11 +35,9 @@ size_t gz_tables_bytes(void);
 size_t gz_sub_result_bytes(void);
 void gz_launch_decode(const uint8_t *comp, const GzFileDesc *files, const uint32_t *sub_file, uint32_t n_sub, uint32_t sub_bytes, uint16_t *sym,
                       uint32_t sub_cap, GzSubResult *res, cudaStream_t st);
-// sub_file / n_sub: all sub-chunks of the batch.  ml: 32 K entries of 4 bytes per sub-chunk (the copies each window takes from the window
-// before it), ml_count: one counter per sub-chunk.
-void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint32_t *sub_file, uint32_t n_sub, const uint16_t *sym,
-                     uint32_t sub_cap, const GzSubResult *res, uint8_t *win, uint32_t *ml, uint32_t *ml_count, uint64_t *sub_off, GzFileResult *fres,
-                     cudaStream_t st);
+void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint16_t *sym, uint32_t sub_cap, const GzSubResult *res,
+                     uint8_t *win, uint64_t *sub_off, GzFileResult *fres, cudaStream_t st);
+// text of the files whose sub-chunks are [sub_lo, sub_hi) -> text + desc.text_off (files whose chain failed are skipped)
 void gz_launch_translate(const GzFileDesc *files, const uint32_t *sub_file, uint32_t sub_lo, uint32_t sub_hi, const uint16_t *sym, uint32_t sub_cap,
                          const uint8_t *win, const uint64_t *sub_off, const GzFileResult *fres, uint8_t *text, cudaStream_t st);
 // CRC-32 of the text of files [file0, file0 + n) (already translated at text + desc.text_off) against their trailers: sets

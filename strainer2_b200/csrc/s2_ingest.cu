@@ -710,7 +710,6 @@ struct GzStage {
     GzSubResult *d_res = nullptr;
     uint8_t *d_win = nullptr;
     uint8_t *d_carry = nullptr;          // streamed files: the window a piece leaves to the next one
-    uint32_t *d_ml = nullptr, *d_ml_count = nullptr;      // per sub-chunk: the bytes its window copies from the window before (gz_tail_kernel)
     size_t sym_subs = 0, win_slots = 0;  // what d_sym / d_win hold now (they grow with the batches: gz_stage_reserve)
     uint64_t *d_sub_off = nullptr;
     GzFileDesc *h_files = nullptr, *d_files = nullptr;
@@ -784,7 +783,7 @@ static void ingest_free(s2_ingest *g)
     }
     {
         GzStage &z = g->gz;
-        cudaFreeHost(z.h_comp); cudaFree(z.d_comp); cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_carry); cudaFree(z.d_ml); cudaFree(z.d_ml_count); cudaFree(z.d_sub_off);
+        cudaFreeHost(z.h_comp); cudaFree(z.d_comp); cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_carry); cudaFree(z.d_sub_off);
         cudaFreeHost(z.h_files); cudaFree(z.d_files); cudaFreeHost(z.h_sub_file); cudaFree(z.d_sub_file); cudaFreeHost(z.h_slice0); cudaFree(z.d_slice0);
         cudaFree(z.d_fres); cudaFree(z.d_crc_acc); cudaFree(z.d_piece_text); cudaFreeHost(z.h_fres);
         if (z.idle) cudaEventDestroy(z.idle);
@@ -1136,6 +1135,25 @@ extern "C" int s2_ingest_warm(s2_ctx *c, int n_pipes)
     return 0;
 }
 
+static int ingest_gz_stage_init(s2_ingest *g);
+static int gz_stage_reserve(s2_ingest *g, uint32_t n_sub, uint32_t n_files);
+extern "C" int s2_ingest_warm_gz(s2_ctx *c, int n_pipes, uint64_t batch_comp_bytes)
+{
+    if (s2_ingest_warm(c, n_pipes)) return -1;
+    IngPool *pool = ingest_pool(c);
+    std::vector<s2_ingest *> pipes;
+    { std::lock_guard<std::mutex> lk(pool->mu); pipes = pool->pipes; }
+    for (size_t i = 0; i < pipes.size() && (int)i < n_pipes; ++i) {
+        s2_ingest *g = pipes[i];
+        std::lock_guard<std::mutex> lk(g->mu);
+        if (ingest_gz_stage_init(g)) return -1;
+        const uint32_t files = 64;
+        const uint32_t subs = (uint32_t)std::min<uint64_t>(batch_comp_bytes / g->gz.sub_bytes + files, g->gz.max_sub);
+        if (gz_stage_reserve(g, subs, files)) return -1;
+    }
+    return 0;
+}
+
 // a verdict-ring entry for the chunk about to be enqueued (caller holds g->mu); fails instead of overwriting a verdict
 // that nobody has read yet (thousands of jobs submitted and never waited for)
 static int ingest_result_claim(s2_ingest *g)
@@ -1381,7 +1399,6 @@ static int ingest_gz_stage_init(s2_ingest *g)
     // spent 0.8 s each in cudaMalloc - profiles/r2g_detect_bench.txt)
     CK(cudaMalloc((void **)&z.d_res, (size_t)z.max_sub * gz_sub_result_bytes()));
     CK(cudaMalloc((void **)&z.d_carry, 32768));
-    CK(cudaMalloc((void **)&z.d_ml_count, (size_t)z.max_sub * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&z.d_sub_off, (size_t)z.max_sub * sizeof(uint64_t)));
     CK(cudaHostAlloc((void **)&z.h_files, (size_t)z.max_files * sizeof(GzFileDesc), cudaHostAllocDefault));
     CK(cudaMalloc((void **)&z.d_files, (size_t)z.max_files * sizeof(GzFileDesc)));
@@ -1408,9 +1425,7 @@ static int gz_stage_reserve(s2_ingest *g, uint32_t n_sub, uint32_t n_files)
     if (n_sub > z.sym_subs) {
         const size_t subs = std::min<size_t>(z.max_sub, (size_t)n_sub + n_sub / 4 + 64);
         cudaFree(z.d_sym); z.d_sym = nullptr; z.sym_subs = 0;
-        cudaFree(z.d_ml); z.d_ml = nullptr;
-        if (cudaMalloc((void **)&z.d_sym, subs * z.sub_cap * sizeof(uint16_t)) != cudaSuccess ||
-            cudaMalloc((void **)&z.d_ml, subs * 32768 * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip symbols)"); return -1; }
+        if (cudaMalloc((void **)&z.d_sym, subs * z.sub_cap * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip symbols)"); return -1; }
         z.sym_subs = subs;
     }
     if (want_win > z.win_slots) {
@@ -1486,7 +1501,7 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
         CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
         if (base) CK(cudaMemcpyAsync(z.d_win, d_carry, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));      // the window the previous piece left
         gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, d.n_sub, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
-        gz_launch_chain(z.d_comp, z.d_files, 1, z.d_sub_file, d.n_sub, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_ml, z.d_ml_count, z.d_sub_off, z.d_fres, g->inflate_stream);
+        gz_launch_chain(z.d_comp, z.d_files, 1, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
         gz_launch_translate(z.d_files, z.d_sub_file, 0, d.n_sub, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres, z.d_piece_text, g->inflate_stream);
         gz_launch_crc(z.d_files, 0, 1, z.d_slice0, (uint32_t)(z.piece_text_cap / 4096) + 1, z.d_piece_text, z.d_fres, z.d_crc_acc, nullptr, g->inflate_stream);
         CK(cudaMemcpyAsync(d_carry, z.d_win + (size_t)d.n_sub * 32768, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));
@@ -1759,7 +1774,7 @@ struct s2_ingest_job {
             CK(cudaEventRecord(up, g->copy_stream));
             CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
             gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, sub0, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
-            gz_launch_chain(z.d_comp, z.d_files, nf, z.d_sub_file, sub0, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_ml, z.d_ml_count, z.d_sub_off, z.d_fres, g->inflate_stream);
+            gz_launch_chain(z.d_comp, z.d_files, nf, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
             CK(cudaGetLastError());
             // ---- one ordinary group per plan ------------------------------------------------------------------------------
             for (const Plan &p : plans) {

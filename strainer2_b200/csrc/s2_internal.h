@@ -4,6 +4,8 @@
 #include <string>
 #include <vector>
 
+bool s2_list_starts_with_plain_gz(const char *list_file);      // s2_cli_count.cpp
+
 void s2_set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 
 // environment knobs (argv of the drop-in executables stays identical to the reference's)

@@ -607,6 +607,181 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
     if (sink == 0x12345679u) atomicOr(pv.overflow + 1, sink);     // never true; keeps the prefetch loads alive
 }
 
+// ---- second versions (S2_PART_A=2 / S2_PART_B=2; profiles/r2d_two_phase_128_partitions_ncu_metrics.csv showed phase A
+// waiting for its tile loads and at its barriers, phase B waiting for probes that miss L2 and at two barriers per item) ----
+// Phase A, v2: the next round's tile is on its way while this round's windows are staged (as in the scan kernel), and a
+// round has three barriers instead of four (the counters are cleared by the threads that read them for the reservation).
+__global__ void __launch_bounds__(S2_THREADS, 3)
+s2_partition_kernel_v2(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartView pv, unsigned long long *__restrict__ stats,
+                       const S2DevBatch *__restrict__ dev)
+{
+    long long sign = 1;
+    if (dev) {
+        if (dev->skip) return;
+        n_bytes = dev->n_bytes;
+        sign = (int)dev->inc;
+    }
+    extern __shared__ uint64_t stage[];                           // [S2_NPART][S2_PSTAGE]
+    __shared__ uint32_t cnt[S2_NPART], cnt_c[S2_NPART];
+    __shared__ unsigned long long gbase[S2_NPART];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t n_tiles = (n_bytes + 511) / 512;
+    const uint64_t n_rounds = (n_tiles + S2_WARPS - 1) / S2_WARPS;
+    uint32_t n_valid = 0;
+    uint64_t policy;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (threadIdx.x < S2_NPART) cnt[threadIdx.x] = 0;
+    uint64_t round = blockIdx.x;
+    uint4 raw = make_uint4(0, 0, 0, 0), rawx = make_uint4(0, 0, 0, 0);
+    if (round < n_rounds) {
+        const uint64_t tile = round * S2_WARPS + wid;
+        if (tile < n_tiles) {
+            raw = ld_stream16(bases, n_bytes, tile * 32 + lane, policy);
+            if (lane < 2) rawx = ld_stream16(bases, n_bytes, tile * 32 + 32 + lane, policy);
+        }
+    }
+    __syncthreads();
+    for (; round < n_rounds; round += gridDim.x) {
+        const uint64_t tile = round * S2_WARPS + wid;
+        uint32_t w0 = 0, w1 = 0, w2 = 0, m0 = 0, m1 = 0, m2 = 0;
+        {
+            uint32_t wx = 0, mx = 0;
+            if (tile < n_tiles) {
+                pack_chunk(raw, n_bytes, tile * 32 + lane, w0, m0);
+                if (lane < 2) pack_chunk(rawx, n_bytes, tile * 32 + 32 + lane, wx, mx);
+            }
+            const uint64_t nt = (round + gridDim.x) * S2_WARPS + wid;
+            raw = make_uint4(0, 0, 0, 0); rawx = raw;
+            if (round + gridDim.x < n_rounds && nt < n_tiles) {
+                raw = ld_stream16(bases, n_bytes, nt * 32 + lane, policy);
+                if (lane < 2) rawx = ld_stream16(bases, n_bytes, nt * 32 + 32 + lane, policy);
+            }
+            const uint32_t a1 = __shfl_sync(0xFFFFFFFFu, w0, (lane + 1) & 31), b1 = __shfl_sync(0xFFFFFFFFu, wx, (lane + 1) & 31);
+            const uint32_t a2 = __shfl_sync(0xFFFFFFFFu, w0, (lane + 2) & 31), b2 = __shfl_sync(0xFFFFFFFFu, wx, (lane + 2) & 31);
+            const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, m0, (lane + 1) & 31), d1 = __shfl_sync(0xFFFFFFFFu, mx, (lane + 1) & 31);
+            const uint32_t c2 = __shfl_sync(0xFFFFFFFFu, m0, (lane + 2) & 31), d2 = __shfl_sync(0xFFFFFFFFu, mx, (lane + 2) & 31);
+            w1 = lane < 31 ? a1 : b1;  m1 = lane < 31 ? c1 : d1;
+            w2 = lane < 30 ? a2 : b2;  m2 = lane < 30 ? c2 : d2;
+        }
+        if (tile < n_tiles) {
+            const uint32_t r0 = s2_rc16(w2), r1 = s2_rc16(w1), r2 = s2_rc16(w0);
+#pragma unroll 4
+            for (unsigned j = 0; j < 16; ++j) {
+                if (s2_window_valid(m0, m1, m2, j)) {
+                    const uint64_t canon = window_canon(w0, w1, w2, r0, r1, r2, j);
+                    const uint32_t p = s2_hash(canon).h >> (32 - S2_NPART_LOG2);
+                    const uint32_t at = atomicAdd(&cnt[p], 1u);
+                    ++n_valid;
+                    if (at < S2_PSTAGE) {
+                        stage[p * S2_PSTAGE + at] = canon;
+                    } else {
+                        const unsigned long long g = atomicAdd(&pv.cursor[p], 1ull);
+                        if (g < pv.region_cap) pv.pool[(uint64_t)p * pv.region_cap + g] = canon;
+                        else atomicOr(pv.overflow, 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < S2_NPART) {                             // one global reservation per partition and round
+            const uint32_t c = min(cnt[threadIdx.x], (uint32_t)S2_PSTAGE);
+            cnt[threadIdx.x] = 0;
+            cnt_c[threadIdx.x] = c;
+            gbase[threadIdx.x] = c ? atomicAdd(&pv.cursor[threadIdx.x], (unsigned long long)c) : 0ull;
+        }
+        __syncthreads();
+        for (int p = wid; p < S2_NPART; p += S2_WARPS) {
+            const uint32_t c = cnt_c[p];
+            const unsigned long long g = gbase[p];
+            if (g + c > pv.region_cap) { if (lane == 0 && c) atomicOr(pv.overflow, 1u); continue; }
+            uint64_t *dst = pv.pool + (uint64_t)p * pv.region_cap + g;
+            for (uint32_t i = lane; i < c; i += 32) __stcs(dst + i, stage[p * S2_PSTAGE + i]);
+        }
+        __syncthreads();
+    }
+    n_valid = __reduce_add_sync(0xFFFFFFFFu, n_valid);
+    if (lane == 0 && stats && n_valid) atomicAdd(&stats[1], (unsigned long long)(sign * (long long)n_valid));
+}
+
+// Phase B, v2: WARPS draw the work items (no barrier inside the loop), and the share of the next partition's slice that an
+// item pulls into L2 is one bulk prefetch instruction instead of loads whose results somebody has to wait for.
+__global__ void __launch_bounds__(S2_THREADS, 4)
+s2_probe_all_kernel_v2(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_col,
+                       unsigned long long *__restrict__ stats, unsigned long long *__restrict__ work_counter, const S2DevBatch *__restrict__ dev, uint32_t flags)
+{
+    if (*pv.overflow) return;
+    uint32_t inc = 1u;
+    if (dev) { if (dev->skip) return; inc = dev->inc; }
+    __shared__ unsigned long long pre[S2_NPART + 1];
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int p = 0; p < S2_NPART; ++p) { pre[p] = acc; acc += (pv.cursor[p] + S2_PITEM - 1) / S2_PITEM; }
+        pre[S2_NPART] = acc;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned long long total = pre[S2_NPART];
+    uint32_t n_hits = 0;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1ull);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= total) break;
+        int part = 0;
+#pragma unroll
+        for (int step = S2_NPART / 2; step > 0; step >>= 1) if (pre[part + step] <= item) part += step;
+        const uint64_t n = pv.cursor[part];
+        const uint64_t off = (item - pre[part]) * S2_PITEM;
+        const uint64_t *__restrict__ src = pv.pool + (uint64_t)part * pv.region_cap;
+        if (part + 1 < S2_NPART && !(flags & 1u) && lane == 0) {
+            const uint64_t items_here = pre[part + 1] - pre[part];
+            const uint64_t lo = ((uint64_t)(part + 1) * t.n_buckets + S2_NPART - 1) / S2_NPART;
+            const uint64_t hi = ((uint64_t)(part + 2) * t.n_buckets + S2_NPART - 1) / S2_NPART;
+            const uint64_t share = (hi - lo + items_here - 1) / items_here;
+            const uint64_t b0 = lo + (item - pre[part]) * share;
+            const uint64_t b1 = min(b0 + share, hi);
+            if (b1 > b0) {
+                const uint16_t *a = t.fp + b0 * S2_BUCKET_SLOTS;                // buckets are 32 bytes: the range is 16-byte aligned
+                const uint32_t bytes = (uint32_t)((b1 - b0) * S2_BUCKET_SLOTS * sizeof(uint16_t));
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"(bytes) : "memory");
+            }
+        }
+#pragma unroll 1
+        for (int round = 0; round < S2_PITEM / (4 * 32); ++round) {
+            uint64_t canon[4]; uint32_t x[4][8], fp2[4], bucket[4]; bool have[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t i = off + (uint64_t)(round * 4 + u) * 32 + lane;
+                have[u] = i < n;
+                canon[u] = have[u] ? __ldcs(src + i) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const s2_hash_t hh = s2_hash(canon[u]);
+                fp2[u] = hh.fp * 0x00010001u;
+                bucket[u] = s2_bucket_of(hh.h, t.n_buckets);
+                if (flags & 2u) ld_bucket256_plain(t.fp, bucket[u], x[u]); else ld_bucket256(t.fp, bucket[u], x[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t m = fp_match_bits(x[u], fp2[u]);
+                const bool full = x[u][7] > 0xFFFFu;
+                if (have[u] && (m != 0 || full)) {
+                    const uint32_t b = 31u - (uint32_t)__clz(m);
+                    uint32_t slot = bucket[u] * S2_BUCKET_SLOTS + ((((b & 15u) << 1) | ((b >> 4) & 1u)) & 15u);
+                    uint64_t key = t.keys[slot];
+                    bool hit = (key & S2_KMER_MASK) == canon[u] && key != S2_EMPTY_KEY;
+                    if (!hit) hit = probe_exact(t, canon[u], slot, key);
+                    if (hit) { atomicAdd(&counts_col[slot], inc); ++n_hits; }
+                }
+            }
+            if (off + (uint64_t)(round + 1) * 128 >= n) break;
+        }
+    }
+    n_hits = __reduce_add_sync(0xFFFFFFFFu, n_hits);
+    if (lane == 0 && n_hits && stats) atomicAdd(&stats[0], (unsigned long long)((long long)(int)inc * (long long)n_hits));
+}
+
 // pull one partition's slice of the fingerprint array into L2 with sequential 256-bit loads (evict-last):
 // the probes that follow then find it there instead of fetching it at random, sector by sector
 __global__ void __launch_bounds__(S2_THREADS)
@@ -641,6 +816,11 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     cudaMemsetAsync(cursor, 0, S2_NPART * sizeof(unsigned long long), stream);
     cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
     S2PartView pv = { part_pool, region_cap, cursor, overflow };
+    static const int ver_a = getenv("S2_PART_A") ? atoi(getenv("S2_PART_A")) : 2, ver_b = getenv("S2_PART_B") ? atoi(getenv("S2_PART_B")) : 2;
+    if (ver_a == 2) {
+        cudaFuncSetAttribute(s2_partition_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_partition_smem_bytes());
+        s2_partition_kernel_v2<<<n_sm * 3, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
+    } else
     s2_partition_kernel<<<n_sm * 3, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
     uint32_t *counts_col = t.counts + (uint64_t)col * t.n_slots;
     // buckets whose hash has top bits == p: [ceil(p * nb / 32), ceil((p+1) * nb / 32)); slice 0 is prefetched
@@ -649,6 +829,8 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     s2_prefetch_slice_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(t.fp, 0, hi0, overflow + 1);
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     static const uint32_t probe_flags = getenv("S2_PROBE_FLAGS") ? (uint32_t)atoi(getenv("S2_PROBE_FLAGS")) : 0u;
+    if (ver_b == 2) s2_probe_all_kernel_v2<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter, dev, probe_flags);
+    else
     s2_probe_all_kernel<<<n_sm * 4, S2_THREADS, 0, stream>>>(pv, t, counts_col, stats, work_counter, dev, probe_flags);
     S2DetectOut none = {};
     g_variants[g_variant].count_fn<<<grid_blocks, S2_THREADS, 0, stream>>>(bases, n_bytes, t, counts_col, none, stats, overflow, dev);

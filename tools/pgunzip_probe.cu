@@ -81,13 +81,13 @@ int main(int argc, char **argv)
     printf("%d %s files (level %d), %.1f MB of .gz -> %.1f MB of text, %u sub-chunks of %u KB, symbol area %.1f MB, tables %zu bytes per warp\n", n,
            fastq ? "FASTQ" : "FASTA", level, coff / 1e6, toff / 1e6, sub0, sub_bytes >> 10, (double)sub0 * sub_cap * 2 / 1e6, gz_tables_bytes());
     uint8_t *d_comp, *d_text, *d_win; uint16_t *d_sym; GzSubResult *d_res; uint64_t *d_sub_off; GzFileDesc *d_files; uint32_t *d_sub_file, *d_slice0, *d_crc; GzFileResult *d_fres;
-    unsigned *d_act; uint32_t *d_ml, *d_ml_count;
+    unsigned *d_act;
     CKP(cudaMalloc(&d_comp, coff + 64)); CKP(cudaMemset(d_comp, 0, coff + 64));
     CKP(cudaMalloc(&d_text, toff + 64)); CKP(cudaMalloc(&d_sym, (size_t)sub0 * sub_cap * 2)); CKP(cudaMalloc(&d_res, (size_t)sub0 * gz_sub_result_bytes()));
     CKP(cudaMalloc(&d_win, ((size_t)sub0 + n + 1) * 32768)); CKP(cudaMemset(d_win, 0, ((size_t)sub0 + n + 1) * 32768));
     CKP(cudaMalloc(&d_sub_off, (size_t)sub0 * 8)); CKP(cudaMalloc(&d_files, n * sizeof(GzFileDesc))); CKP(cudaMalloc(&d_sub_file, sub0 * 4));
     CKP(cudaMalloc(&d_slice0, (n + 1) * 4)); CKP(cudaMalloc(&d_crc, n * 4)); CKP(cudaMemset(d_crc, 0, n * 4)); CKP(cudaMalloc(&d_fres, n * sizeof(GzFileResult)));
-    CKP(cudaMalloc(&d_act, n * 4)); CKP(cudaMalloc(&d_ml, (size_t)sub0 * 32768 * 4)); CKP(cudaMalloc(&d_ml_count, (size_t)sub0 * 4));
+    CKP(cudaMalloc(&d_act, n * 4));
     for (int i = 0; i < n; ++i) CKP(cudaMemcpy(d_comp + files[i].comp_off, comps[i % distinct].data(), comps[i % distinct].size(), cudaMemcpyHostToDevice));
     CKP(cudaMemcpy(d_files, files.data(), n * sizeof(GzFileDesc), cudaMemcpyHostToDevice));
     CKP(cudaMemcpy(d_sub_file, sub_file.data(), sub0 * 4, cudaMemcpyHostToDevice));
@@ -98,7 +98,7 @@ int main(int argc, char **argv)
         cudaEventRecord(e[0]);
         gz_launch_decode(d_comp, d_files, d_sub_file, sub0, sub_bytes, d_sym, sub_cap, d_res, 0);
         cudaEventRecord(e[1]);
-        gz_launch_chain(d_comp, d_files, n, d_sub_file, sub0, d_sym, sub_cap, d_res, d_win, d_ml, d_ml_count, d_sub_off, d_fres, 0);
+        gz_launch_chain(d_comp, d_files, n, d_sym, sub_cap, d_res, d_win, d_sub_off, d_fres, 0);
         cudaEventRecord(e[2]);
         gz_launch_translate(d_files, d_sub_file, 0, sub0, d_sym, sub_cap, d_win, d_sub_off, d_fres, d_text, 0);
         cudaEventRecord(e[3]);
