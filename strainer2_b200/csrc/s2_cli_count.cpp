@@ -128,6 +128,11 @@ int s2_default_reader_threads()
 }
 
 // The list drivers GEN_all_kmer_counts / GEN_all_kmer_counts_skip_file (src/genome_compare.c:115-177) for a
+// Size of a reader thread's arena.  Pinning memory costs (profiles/r2g_pinned_probe.txt: 7 GB/s on huge pages), and sixteen
+// threads pin two arenas each while the scan is running: 16 MB is one full pipeline chunk of BGZF.  Ordinary .gz wants
+// larger batches for its decode kernel (one warp per 32 KB of compressed bytes) and runs long enough to pay for them.
+static uint64_t g_arena_default_mb = 16;
+
 // does the first file a list names begin like an ordinary (not block-) gzip file?  Nothing is reported here: the list is
 // read again, with the reference's messages, when its turn comes
 bool s2_list_starts_with_plain_gz(const char *list_file)
@@ -189,7 +194,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
     // on the other is in flight) and hand the images to the ingest pipeline, which copies them to the device from
     // there.  (Handing over paths made the pipeline read the files itself, under its lock: three pipelines = three
     // threads reading, 15 GB/s for all sixteen reader threads - profiles/r2d_bench_n1.json, cli leg.)
-    const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 32), 1) << 20 : 0;
+    const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", g_arena_default_mb), 1) << 20 : 0;
 
     auto reader = [&](int tid) {
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
@@ -391,7 +396,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     // The CUDA contexts come up side by side (each takes the better part of a second) while this thread inflates and
     // parses the -r genome; each starter then creates its context's ingest pipelines, which goes on beside the table build.
     const bool gpu_ingest_on = s2_env_int("S2_GPU_INGEST", 1) != 0;
-    const int warm_pipes = gpu_ingest_on ? std::min((n_threads + n_gpus - 1) / n_gpus, std::max(1, s2_env_int("S2_INGEST_PIPES", 3))) : 0;
+    const int warm_pipes = gpu_ingest_on ? std::min((n_threads + n_gpus - 1) / n_gpus, std::max(1, s2_env_int("S2_INGEST_PIPES", 2))) : 0;
     std::vector<std::thread> starters, warmers;
     std::vector<std::string> start_errs(n_gpus);
     for (int g = 0; g < n_gpus; ++g)
@@ -414,7 +419,8 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     }
     // (an ordinary .gz at the head of a list: the pipelines' gunzip stages are made ready as well - s2_ingest_warm_gz)
     const bool gz_inputs = warm_pipes && (s2_list_starts_with_plain_gz(A_file) || s2_list_starts_with_plain_gz(B_file));
-    const uint64_t arena_mb = std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", 32), 1);
+    if (gz_inputs) g_arena_default_mb = 48;
+    const uint64_t arena_mb = std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", g_arena_default_mb), 1);
     for (int g = 0; g < n_gpus && warm_pipes; ++g)
         warmers.emplace_back([&, g]() { if (gz_inputs) s2_ingest_warm_gz(ctxs[g], warm_pipes, arena_mb << 20); else s2_ingest_warm(ctxs[g], warm_pipes); });
     struct JoinGuard { std::vector<std::thread> &v; ~JoinGuard() { for (auto &t : v) if (t.joinable()) t.join(); } } warm_guard{ warmers };

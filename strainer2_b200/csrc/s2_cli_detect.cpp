@@ -534,6 +534,8 @@ extern "C" int s2_strain_detect_main(int argc, char **argv)
     // the context's ingest pipelines (350 MB of device memory and 48 MB of pinned staging each: tens of milliseconds)
     // come into being beside the table build and the labelling instead of in front of the first metagenome
     struct Warmer { std::thread t; ~Warmer() { if (t.joinable()) t.join(); } } warmer;
+    // (a detect call keeps its pipeline for a whole file - per-read results come back at its end - so three files in flight)
+    setenv("S2_INGEST_PIPES", "3", 0);
     const bool gz_inputs = d.gpu_ingest && (B_file ? s2_list_starts_with_plain_gz(B_file) : false);
     if (d.gpu_ingest) warmer.t = std::thread([&d, n_threads, gz_inputs]() {
         const int pipes = std::min(n_threads, std::max(1, s2_env_int("S2_INGEST_PIPES", 3)));

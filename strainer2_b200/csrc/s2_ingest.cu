@@ -1061,9 +1061,10 @@ static void ingest_classify(IngSource &src)
     if (!src.bgzf && !src.gz && !s2_env_int("S2_GPU_INGEST_PLAIN", 1)) src.eligible = false;
 }
 
-// The pipelines of a context: a small pool (S2_INGEST_PIPES, default 3) shared by every thread that calls in.  One
-// pipeline already overlaps copy engine, inflate engine and kernels; the others exist so that several reader threads can
-// read files into pinned staging and build launch lists at the same time.  (Round 1 had one pipeline per calling thread:
+// The pipelines of a context: a small pool (S2_INGEST_PIPES, default 2; strain_detect asks for 3) shared by every thread that
+// calls in.  One pipeline already overlaps copy engine, inflate engine and kernels; the second exists so that one thread can
+// build its launch lists while another one's are being enqueued (reading the files is the callers' business: the executables'
+// reader threads fill pinned arenas of their own).  (Round 1 had one pipeline per calling thread:
 // 16 reader threads allocated 16 rings - 5 GB of HBM, 0.8 GB of pinned staging - and the allocation alone made the
 // executables 18x slower than with one thread, profiles/r1n_e2e_cli.txt.)
 struct IngPool {
@@ -1079,7 +1080,7 @@ static IngPool *ingest_pool(s2_ctx *c)
     std::lock_guard<std::mutex> lk(g_pool_mu);
     if (!c->ingest_pool) {
         IngPool *p = new IngPool();
-        p->max_pipes = (unsigned)std::min(std::max(s2_env_int("S2_INGEST_PIPES", 3), 1), 16);
+        p->max_pipes = (unsigned)std::min(std::max(s2_env_int("S2_INGEST_PIPES", 2), 1), 16);
         c->ingest_pool = p;
     }
     return (IngPool *)c->ingest_pool;
@@ -1127,9 +1128,8 @@ extern "C" int s2_ingest_warm(s2_ctx *c, int n_pipes)
     while (pool->pipes.size() < std::min<size_t>((size_t)std::max(n_pipes, 0), pool->max_pipes)) {
         s2_ingest *g = new s2_ingest();
         if (ingest_init(g, c)) { ingest_free(g); return -1; }
-        for (auto &sl : g->slot) if (!sl.h_comp && cudaHostAlloc((void **)&sl.h_comp, g->comp_chunk, cudaHostAllocDefault) != cudaSuccess) {
-            s2_set_error("out of pinned memory"); ingest_free(g); return -1;
-        }
+        // (the slots' pinned staging - for sources that are files, not memory images - comes with the first such source:
+        // the executables hand over images from their reader threads' arenas)
         pool->pipes.push_back(g);
     }
     return 0;
@@ -1390,7 +1390,9 @@ static int ingest_gz_stage_init(s2_ingest *g)
     z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 32), 4), 4096) << 10;
     // symbols one sub-chunk may produce: S2_GZ_RATIO x its compressed bytes (FASTQ deflates 4-6 : 1, FASTA 3.5 : 1) plus the
     // run-on to the first block boundary behind the next cut; a sub-chunk that needs more makes its file the host reader's
-    z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64) + (256u << 10);
+    // (the run-on is one DEFLATE block: 16 K symbols, which are 30-100 KB of text for real reads and genomes but 300 KB for
+    // FASTQ whose quality lines are all alike - every match 258 bytes long; hence the half million symbols of slack)
+    z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64) + (512u << 10);
     z.max_files = ING_MAX_FILES;
     z.max_sub = (uint32_t)(z.comp_cap / z.sub_bytes) + z.max_files;
     CK(cudaMalloc((void **)&z.d_comp, z.comp_cap + (size_t)z.max_files * 32 + 256));

@@ -566,12 +566,28 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
             const uint64_t items_here = pre[part + 1] - pre[part];
             const uint64_t lo = ((uint64_t)(part + 1) * t.n_buckets + S2_NPART - 1) / S2_NPART;
             const uint64_t hi = ((uint64_t)(part + 2) * t.n_buckets + S2_NPART - 1) / S2_NPART;
-            const uint64_t share = (hi - lo + items_here - 1) / items_here;
-            const uint64_t b0 = lo + (item - pre[part]) * share;
-            for (uint64_t b = b0 + threadIdx.x; b < b0 + share && b < hi; b += S2_THREADS) {
-                uint32_t x[8];
-                if (flags & 4u) ld_bucket256_plain(t.fp, (uint32_t)b, x); else ld_bucket256(t.fp, (uint32_t)b, x);
-                sink |= x[0] ^ x[7];
+            if (flags & 8u) {                                     // (round 1's form: loads whose results a thread waits for)
+                const uint64_t share = (hi - lo + items_here - 1) / items_here;
+                const uint64_t b0 = lo + (item - pre[part]) * share;
+                for (uint64_t b = b0 + threadIdx.x; b < b0 + share && b < hi; b += S2_THREADS) {
+                    uint32_t x[8];
+                    if (flags & 4u) ld_bucket256_plain(t.fp, (uint32_t)b, x); else ld_bucket256(t.fp, (uint32_t)b, x);
+                    sink |= x[0] ^ x[7];
+                }
+            } else if (threadIdx.x == 0) {
+                // one bulk prefetch per item, nobody waits for it; the first half of a partition's items bring in the whole next
+                // slice, so that it is there when the grid moves on
+                const uint64_t half = (items_here + 1) / 2;
+                const uint64_t k = item - pre[part];
+                if (k < half) {
+                    const uint64_t share = (hi - lo + half - 1) / half;
+                    const uint64_t b0 = lo + k * share, b1 = min(b0 + share, hi);
+                    if (b1 > b0) {
+                        const uint16_t *a = t.fp + b0 * S2_BUCKET_SLOTS;
+                        const uint32_t bytes = (uint32_t)((b1 - b0) * S2_BUCKET_SLOTS * sizeof(uint16_t));
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"(bytes) : "memory");
+                    }
+                }
             }
         }
 #pragma unroll 1
@@ -611,7 +627,8 @@ s2_probe_all_kernel(S2PartView pv, S2TableView t, uint32_t *__restrict__ counts_
 // waiting for its tile loads and at its barriers, phase B waiting for probes that miss L2 and at two barriers per item) ----
 // Phase A, v2: the next round's tile is on its way while this round's windows are staged (as in the scan kernel), and a
 // round has three barriers instead of four (the counters are cleared by the threads that read them for the reservation).
-__global__ void __launch_bounds__(S2_THREADS, 3)
+template <int PSTAGE, int MINB>
+__global__ void __launch_bounds__(S2_THREADS, MINB)
 s2_partition_kernel_v2(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2PartView pv, unsigned long long *__restrict__ stats,
                        const S2DevBatch *__restrict__ dev)
 {
@@ -621,7 +638,7 @@ s2_partition_kernel_v2(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2Pa
         n_bytes = dev->n_bytes;
         sign = (int)dev->inc;
     }
-    extern __shared__ uint64_t stage[];                           // [S2_NPART][S2_PSTAGE]
+    extern __shared__ uint64_t stage[];                           // [S2_NPART][PSTAGE]
     __shared__ uint32_t cnt[S2_NPART], cnt_c[S2_NPART];
     __shared__ unsigned long long gbase[S2_NPART];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -672,8 +689,8 @@ s2_partition_kernel_v2(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2Pa
                     const uint32_t p = s2_hash(canon).h >> (32 - S2_NPART_LOG2);
                     const uint32_t at = atomicAdd(&cnt[p], 1u);
                     ++n_valid;
-                    if (at < S2_PSTAGE) {
-                        stage[p * S2_PSTAGE + at] = canon;
+                    if (at < PSTAGE) {
+                        stage[p * PSTAGE + at] = canon;
                     } else {
                         const unsigned long long g = atomicAdd(&pv.cursor[p], 1ull);
                         if (g < pv.region_cap) pv.pool[(uint64_t)p * pv.region_cap + g] = canon;
@@ -684,7 +701,7 @@ s2_partition_kernel_v2(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2Pa
         }
         __syncthreads();
         if (threadIdx.x < S2_NPART) {                             // one global reservation per partition and round
-            const uint32_t c = min(cnt[threadIdx.x], (uint32_t)S2_PSTAGE);
+            const uint32_t c = min(cnt[threadIdx.x], (uint32_t)PSTAGE);
             cnt[threadIdx.x] = 0;
             cnt_c[threadIdx.x] = c;
             gbase[threadIdx.x] = c ? atomicAdd(&pv.cursor[threadIdx.x], (unsigned long long)c) : 0ull;
@@ -695,7 +712,7 @@ s2_partition_kernel_v2(const uint8_t *__restrict__ bases, uint64_t n_bytes, S2Pa
             const unsigned long long g = gbase[p];
             if (g + c > pv.region_cap) { if (lane == 0 && c) atomicOr(pv.overflow, 1u); continue; }
             uint64_t *dst = pv.pool + (uint64_t)p * pv.region_cap + g;
-            for (uint32_t i = lane; i < c; i += 32) __stcs(dst + i, stage[p * S2_PSTAGE + i]);
+            for (uint32_t i = lane; i < c; i += 32) __stcs(dst + i, stage[p * PSTAGE + i]);
         }
         __syncthreads();
     }
@@ -816,10 +833,14 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     cudaMemsetAsync(cursor, 0, S2_NPART * sizeof(unsigned long long), stream);
     cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
     S2PartView pv = { part_pool, region_cap, cursor, overflow };
-    static const int ver_a = getenv("S2_PART_A") ? atoi(getenv("S2_PART_A")) : 2, ver_b = getenv("S2_PART_B") ? atoi(getenv("S2_PART_B")) : 2;
+    static const int ver_a = getenv("S2_PART_A") ? atoi(getenv("S2_PART_A")) : 2, ver_b = getenv("S2_PART_B") ? atoi(getenv("S2_PART_B")) : 1;
     if (ver_a == 2) {
-        cudaFuncSetAttribute(s2_partition_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_partition_smem_bytes());
-        s2_partition_kernel_v2<<<n_sm * 3, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
+        cudaFuncSetAttribute(s2_partition_kernel_v2<S2_PSTAGE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_partition_smem_bytes());
+        s2_partition_kernel_v2<S2_PSTAGE, 3><<<n_sm * 3, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
+    } else if (ver_a == 3) {             // 52 staged entries per partition and round (1.6 x the even share): four CTAs per SM
+        const size_t smem = (size_t)S2_NPART * 52 * sizeof(uint64_t);
+        cudaFuncSetAttribute(s2_partition_kernel_v2<52, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        s2_partition_kernel_v2<52, 4><<<n_sm * 4, S2_THREADS, smem, stream>>>(bases, n_bytes, pv, stats, dev);
     } else
     s2_partition_kernel<<<n_sm * 3, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
     uint32_t *counts_col = t.counts + (uint64_t)col * t.n_slots;

@@ -77,7 +77,7 @@ int main(int argc, char **argv)
         coff += (c.size() + 15) / 16 * 16 + 16; toff += t.size(); sub0 += d.n_sub;
     }
     slice0[n] = slices;
-    const uint32_t sub_cap = sub_bytes * 8 + (256u << 10);
+    const uint32_t sub_cap = sub_bytes * 8 + (512u << 10);
     printf("%d %s files (level %d), %.1f MB of .gz -> %.1f MB of text, %u sub-chunks of %u KB, symbol area %.1f MB, tables %zu bytes per warp\n", n,
            fastq ? "FASTQ" : "FASTA", level, coff / 1e6, toff / 1e6, sub0, sub_bytes >> 10, (double)sub0 * sub_cap * 2 / 1e6, gz_tables_bytes());
     uint8_t *d_comp, *d_text, *d_win; uint16_t *d_sym; GzSubResult *d_res; uint64_t *d_sub_off; GzFileDesc *d_files; uint32_t *d_sub_file, *d_slice0, *d_crc; GzFileResult *d_fres;
