@@ -34,6 +34,9 @@ gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict_
                  uint32_t sub_bytes, uint16_t *sym, uint32_t sub_cap, GzSubResult *res, uint64_t search_limit_bits)
 {
     __shared__ GzTables tables[GZ_WARPS];
+    __shared__ uint8_t kraft9[512];
+    gz_kraft9_fill(kraft9, threadIdx.x, GZ_WARPS * 32);
+    __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t sub = blockIdx.x * GZ_WARPS + warp;
     if (sub >= n_sub) return;
@@ -41,7 +44,7 @@ gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict_
     const uint32_t j = sub - f.sub0;                                            // sub-chunk j of its file
     const uint64_t n_words = (f.comp_len + 3) / 4;
     gz_subchunk(reinterpret_cast<const uint32_t *>(comp + f.comp_off), n_words, j == 0 ? f.first_bit : ~0ull, (uint64_t)j * sub_bytes * 8ull,
-                (uint64_t)(j + 1) * sub_bytes * 8ull, search_limit_bits, sym + (uint64_t)sub * sub_cap, sub_cap, tables[warp], res + sub, (int)lane, 32);
+                (uint64_t)(j + 1) * sub_bytes * 8ull, search_limit_bits, sym + (uint64_t)sub * sub_cap, sub_cap, tables[warp], kraft9, res + sub, (int)lane, 32);
 }
 
 // one CTA per file.  Phase 0, in parallel over the file's sub-chunks: the chain test (sub-chunk j must start where j-1
@@ -222,17 +225,21 @@ __device__ __forceinline__ uint32_t crc_xpow8(uint64_t n)
 }
 
 #define GZ_CRC_SLICE 4096u
-// one warp per 4 KB slice of a file's text, 128 bytes per lane: the remainder of each piece (byte-wise table), moved to its
-// place by a multiplication with x^(8 x bytes behind it), XORed into the file's accumulator (the CRC is linear)
+// one warp per 4 KB slice of a file's text, 128 bytes per lane: the remainder of each lane's run - four bytes per step with
+// four tables (slicing-by-4: the dependent chain is 32 table steps instead of 128), head and tail bytes one at a time -
+// moved to its place by a multiplication with x^(8 x bytes behind it), XORed into the file's accumulator (the CRC is linear)
 __global__ void __launch_bounds__(256)
 gz_crc_kernel(const GzFileDesc *__restrict__ files, uint32_t file0, uint32_t n_files, const uint32_t *__restrict__ file_slice0, uint32_t n_slices,
               const uint8_t *__restrict__ text, const GzFileResult *__restrict__ fres, uint32_t *crc_acc)
 {
-    __shared__ uint32_t table[256];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-        uint32_t c = i;
+    __shared__ uint32_t table[4][256];
+    {
+        uint32_t c = threadIdx.x;                                                // (256 threads)
         for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
-        table[i] = c;
+        table[0][threadIdx.x] = c;
+        __syncthreads();
+        uint32_t v = c;
+        for (int t = 1; t < 4; ++t) { v = (v >> 8) ^ table[0][v & 0xFFu]; table[t][threadIdx.x] = v; }
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
@@ -249,7 +256,13 @@ gz_crc_kernel(const GzFileDesc *__restrict__ files, uint32_t file0, uint32_t n_f
     if (s0 < len) {
         const uint64_t s1 = s0 + GZ_CRC_SLICE / 32 < len ? s0 + GZ_CRC_SLICE / 32 : len;
         const uint8_t *p = text + f.text_off;
-        for (uint64_t i = s0; i < s1; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+        uint64_t i = s0;
+        for (; i < s1 && ((uintptr_t)(p + i) & 3u); ++i) c = table[0][(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+        for (; i + 4 <= s1; i += 4) {
+            c ^= *reinterpret_cast<const uint32_t *>(p + i);
+            c = table[3][c & 0xFFu] ^ table[2][(c >> 8) & 0xFFu] ^ table[1][(c >> 16) & 0xFFu] ^ table[0][c >> 24];
+        }
+        for (; i < s1; ++i) c = table[0][(c ^ p[i]) & 0xFFu] ^ (c >> 8);
         c = crc_mulmod(c, crc_xpow8(len - s1));
     }
 #pragma unroll

@@ -34,9 +34,17 @@
 #define GZ_NOUNROLL _Pragma("unroll 1")
 // The symbol loop addresses its tables and buffers through values the compiler must keep in registers: left to itself it
 // re-derives them from the kernel parameters, block and thread ids inside the loop (a dozen instructions per symbol).
-#define GZ_KEEP64(p) asm volatile("" : "+l"(p))
+// (An empty asm statement is not enough: it leaves no trace in the PTX, and ptxas - which does the re-deriving under the 64
+// register limit - sees through the copies.  A value that has been through a VOLATILE shared-memory slot has no other
+// derivation.  Once per block: four instructions.)
+#define GZ_KEEP64(p) do { unsigned long long v_ = (unsigned long long)(p); asm volatile("{ .reg .b64 t; mov.b64 t, %0; st.volatile.shared.b64 [%1], t; ld.volatile.shared.b64 %0, [%1]; }" : "+l"(v_) : "r"(gz_keep_slot) : "memory"); (p) = reinterpret_cast<decltype(p)>(v_); } while (0)
 typedef uint32_t gz_tab_t;                                                  // shared-memory address of a table
-__device__ __forceinline__ gz_tab_t gz_tab(const uint32_t *t) { uint32_t a = (uint32_t)__cvta_generic_to_shared(t); asm volatile("" : "+r"(a)); return a; }
+__device__ __forceinline__ gz_tab_t gz_tab(const uint32_t *t, uint32_t slot)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(t);
+    asm volatile("st.volatile.shared.b32 [%1], %0; ld.volatile.shared.b32 %0, [%1];" : "+r"(a) : "r"(slot) : "memory");
+    return a;
+}
 __device__ __forceinline__ uint32_t gz_tab_at(gz_tab_t t, uint32_t i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(t + (i << 2))); return v; }
 #else
 #define GZ_SYNC() do { } while (0)
@@ -44,7 +52,7 @@ __device__ __forceinline__ uint32_t gz_tab_at(gz_tab_t t, uint32_t i) { uint32_t
 #define GZ_NOUNROLL
 #define GZ_KEEP64(p) do { } while (0)
 typedef const uint32_t *gz_tab_t;
-inline gz_tab_t gz_tab(const uint32_t *t) { return t; }
+inline gz_tab_t gz_tab(const uint32_t *t, uint32_t) { return t; }
 inline uint32_t gz_tab_at(gz_tab_t t, uint32_t i) { return t[i]; }
 #endif
 
@@ -353,6 +361,11 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
     int rc = GZ_OK;
     uint32_t p_at = ~0u;                                                 // this lane's copied symbol that is still to be stored, and where
     uint16_t p_val = 0;
+#if defined(__CUDA_ARCH__)
+    const uint32_t gz_keep_slot = (uint32_t)__cvta_generic_to_shared(t.scratch + 64);       // 8 bytes of the tables' scratch area (free between table builds)
+#else
+    const uint32_t gz_keep_slot = 0;
+#endif
     GZ_KEEP64(out);
     GZ_KEEP64(b.w);
     for (;;) {
@@ -380,7 +393,7 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
             if (rc) break;
             // The symbol loop.  One peek holds a literal/length code and its extra bits (15 + 5), a second one the distance
             // code and its extra bits (15 + 13); everything is 32-bit arithmetic.
-            const gz_tab_t lit = gz_tab(t.lit), dtab = gz_tab(t.dist);
+            const gz_tab_t lit = gz_tab(t.lit, gz_keep_slot), dtab = gz_tab(t.dist, gz_keep_slot);
             for (;;) {
                 uint32_t bits = gz_peek(b);
                 uint32_t e = gz_tab_at(lit, bits & ((1u << GZ_LIT_ROOT) - 1u)), used = 0;
@@ -415,12 +428,14 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
                     d = gz_tab_at(dtab, (d >> 16) + ((bits >> GZ_DIST_ROOT) & ((1u << ((d >> 4) & 15u)) - 1u)));
                 }
                 used += d & 15u;
-                if (!(d & GZ_F_BASE)) { rc = GZ_ERR_SYMBOL; break; }
-                const uint32_t xd = (d >> 4) & 15u;
+                const uint32_t xd = (d >> 4) & 15u;                       // (garbage, but small, when d is no distance code)
                 const uint32_t dist = (d >> 16) + ((bits >> used) & ((1u << xd) - 1u));
                 gz_skip(b, used + xd);
-                if (dist > o + window) { rc = GZ_ERR_DISTANCE; break; }
-                if (o + len >= cap) { rc = GZ_ERR_OUTPUT; break; }
+                // one branch for the three things that can be wrong with a match (which one is sorted out on the cold side)
+                if (!(d & GZ_F_BASE) | (dist > o + window) | (o + len >= cap)) {
+                    rc = !(d & GZ_F_BASE) ? GZ_ERR_SYMBOL : dist > o + window ? GZ_ERR_DISTANCE : GZ_ERR_OUTPUT;
+                    break;
+                }
                 // A copied symbol is loaded now and stored when the NEXT match arrives (or the blocks end): the symbols were
                 // written past L1, so the load is an L2 round trip, and a store right behind it would hold the warp - in-order
                 // issue - for all of it.  Nothing reads the place in between: literals only store, and the next match stores
@@ -471,8 +486,20 @@ GZ_HD inline void gz_peek96(const GzBits &b, uint64_t p, uint64_t *lo, uint32_t 
     *hi = (uint32_t)(c >> s);
 }
 
+// Kraft sum (in units of 1/128) of three 3-bit code lengths at once: kraft9[v] for the 9 bits v.  512 bytes, filled once per
+// CTA / process; the finder's test of a position is then seven lookups instead of a loop over up to 19 lengths - with 32
+// lanes on 32 positions nearly every warp iteration ran that loop in full, a tenth to a quarter of the decode kernel's work.
+GZ_HD inline void gz_kraft9_fill(uint8_t *kraft9, uint32_t tid, uint32_t n_threads)
+{
+    for (uint32_t v = tid; v < 512u; v += n_threads) {
+        uint32_t sum = 0;
+        for (uint32_t i = 0; i < 3u; ++i) { const uint32_t l = (v >> (3u * i)) & 7u; sum += l ? 128u >> l : 0u; }
+        kraft9[v] = (uint8_t)sum;                                        // <= 192
+    }
+}
+
 // cheap test of one position: not-final dynamic block, sane code counts, complete code-length code
-GZ_HD inline bool gz_candidate(const GzBits &b, uint64_t p)
+GZ_HD inline bool gz_candidate(const GzBits &b, uint64_t p, const uint8_t *kraft9)
 {
     uint64_t lo; uint32_t hi;
     gz_peek96(b, p, &lo, &hi);
@@ -480,21 +507,19 @@ GZ_HD inline bool gz_candidate(const GzBits &b, uint64_t p)
     if ((h & 7u) != 4u) return false;                                   // BFINAL = 0, BTYPE = 2
     if (((h >> 3) & 31u) > 29u || ((h >> 8) & 31u) > 29u) return false;
     const uint32_t ncode = ((h >> 13) & 15u) + 4u;
-    uint64_t bits = lo >> 17 | (uint64_t)hi << 47;                      // 3 bits per code length
-    uint32_t sum = 0;
-    for (uint32_t i = 0; i < ncode; ++i) {
-        const uint32_t l = (uint32_t)bits & 7u;
-        bits >>= 3;
-        sum += l ? 128u >> l : 0u;                                       // (19 x 3 = 57 bits: all inside `bits`)
-    }
+    uint64_t bits = lo >> 17 | (uint64_t)hi << 47;                      // 3 bits per code length (19 x 3 = 57 bits: all inside `bits`)
+    bits &= (1ull << (3u * ncode)) - 1ull;                               // lengths that are not there count as 0
+    const uint32_t x0 = (uint32_t)bits, x1 = (uint32_t)(bits >> 27), x2 = (uint32_t)(bits >> 54);
+    const uint32_t sum = kraft9[x0 & 511u] + kraft9[(x0 >> 9) & 511u] + kraft9[(x0 >> 18) & 511u] +
+                         kraft9[x1 & 511u] + kraft9[(x1 >> 9) & 511u] + kraft9[(x1 >> 18) & 511u] + kraft9[x2 & 511u];
     return sum == 128u;
 }
 
-GZ_HD inline int gz_find_block(GzBits &b, GzTables &t, uint64_t from_bit, uint64_t limit_bit, uint64_t *found, int lane, int nl)
+GZ_HD inline int gz_find_block(GzBits &b, GzTables &t, const uint8_t *kraft9, uint64_t from_bit, uint64_t limit_bit, uint64_t *found, int lane, int nl)
 {
     for (uint64_t base = from_bit; base < limit_bit; base += (uint64_t)nl) {
         const uint64_t p = base + (uint64_t)lane;
-        const bool cand = p < limit_bit && gz_candidate(b, p);
+        const bool cand = p < limit_bit && gz_candidate(b, p, kraft9);
 #if defined(__CUDA_ARCH__)
         uint32_t m = __ballot_sync(0xFFFFFFFFu, cand);
 #else
@@ -527,7 +552,7 @@ struct GzSubResult {
 // first block for the sub-chunk that begins a member, else ~0.  cut_bit / next_cut_bit: this sub-chunk's and the next
 // one's cut.  search_limit_bits: how far past the cut the finder looks.
 GZ_HD inline void gz_subchunk(const uint32_t *words, uint64_t n_words, uint64_t known_start, uint64_t cut_bit, uint64_t next_cut_bit,
-                              uint64_t search_limit_bits, uint16_t *out, uint32_t cap, GzTables &t, GzSubResult *res, int lane, int nl)
+                              uint64_t search_limit_bits, uint16_t *out, uint32_t cap, GzTables &t, const uint8_t *kraft9, GzSubResult *res, int lane, int nl)
 {
     GzBits b;
     b.w = words; b.n_words = (uint32_t)n_words;
@@ -537,7 +562,7 @@ GZ_HD inline void gz_subchunk(const uint32_t *words, uint64_t n_words, uint64_t 
         const uint64_t end_bits = (uint64_t)n_words * 32u;
         uint64_t limit = cut_bit + search_limit_bits;
         if (limit > end_bits) limit = end_bits;
-        rc = gz_find_block(b, t, cut_bit, limit, &start, lane, nl);
+        rc = gz_find_block(b, t, kraft9, cut_bit, limit, &start, lane, nl);
     }
     uint32_t n_out = 0;
     uint64_t end_bit = start;

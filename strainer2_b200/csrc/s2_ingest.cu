@@ -702,21 +702,25 @@ enum { ING_COUNT = 1, ING_DETECT = 2 };
 // CRC-checked, and from there on a gz group is a BGZF group whose "blocks" are whole files: isz[f] = ISIZE as the host read
 // it, act[f] = what the file inflated to (all ones on any doubt: chain broken, size or CRC-32 mismatch, a second member),
 // so ing_check_chunk's act == isz test vetoes the scan exactly as it does for a damaged BGZF member.
+struct GzBufSet {                        // what one batch brings along: two sets, so that the next batch's bytes travel while this one is decoded
+    uint8_t *h_comp = nullptr, *d_comp = nullptr;
+    GzFileDesc *h_files = nullptr, *d_files = nullptr;
+    uint32_t *h_sub_file = nullptr, *d_sub_file = nullptr, *h_slice0 = nullptr, *d_slice0 = nullptr;
+    cudaEvent_t idle = nullptr;          // inflate stream: the last chunk of the batch that used this set has been translated
+};
 struct GzStage {
     size_t comp_cap = 0;
     uint32_t sub_bytes = 0, sub_cap = 0, max_sub = 0, max_files = 0;
-    uint8_t *h_comp = nullptr, *d_comp = nullptr;
+    GzBufSet set[2];
+    unsigned batch_no = 0;
     uint16_t *d_sym = nullptr;
     GzSubResult *d_res = nullptr;
     uint8_t *d_win = nullptr;
     uint8_t *d_carry = nullptr;          // streamed files: the window a piece leaves to the next one
     size_t sym_subs = 0, win_slots = 0;  // what d_sym / d_win hold now (they grow with the batches: gz_stage_reserve)
     uint64_t *d_sub_off = nullptr;
-    GzFileDesc *h_files = nullptr, *d_files = nullptr;
-    uint32_t *h_sub_file = nullptr, *d_sub_file = nullptr, *h_slice0 = nullptr, *d_slice0 = nullptr;
     GzFileResult *d_fres = nullptr;
     uint32_t *d_crc_acc = nullptr;
-    cudaEvent_t idle = nullptr;          // inflate stream: the last chunk of the previous batch has been translated
     uint8_t *d_piece_text = nullptr; size_t piece_text_cap = 0;      // streamed files: the text of one piece
     GzFileResult *h_fres = nullptr;      // pinned: a piece's result
     bool used = false;
@@ -783,10 +787,13 @@ static void ingest_free(s2_ingest *g)
     }
     {
         GzStage &z = g->gz;
-        cudaFreeHost(z.h_comp); cudaFree(z.d_comp); cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_carry); cudaFree(z.d_sub_off);
-        cudaFreeHost(z.h_files); cudaFree(z.d_files); cudaFreeHost(z.h_sub_file); cudaFree(z.d_sub_file); cudaFreeHost(z.h_slice0); cudaFree(z.d_slice0);
+        cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_carry); cudaFree(z.d_sub_off);
+        for (auto &zs : z.set) {
+            cudaFreeHost(zs.h_comp); cudaFree(zs.d_comp);
+            cudaFreeHost(zs.h_files); cudaFree(zs.d_files); cudaFreeHost(zs.h_sub_file); cudaFree(zs.d_sub_file); cudaFreeHost(zs.h_slice0); cudaFree(zs.d_slice0);
+            if (zs.idle) cudaEventDestroy(zs.idle);
+        }
         cudaFree(z.d_fres); cudaFree(z.d_crc_acc); cudaFree(z.d_piece_text); cudaFreeHost(z.h_fres);
-        if (z.idle) cudaEventDestroy(z.idle);
     }
     cudaFree(g->d_flat);
     cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end); cudaFree(g->d_masks); cudaFree(g->d_tickets);
@@ -1189,6 +1196,7 @@ struct IngChunk {
     unsigned n_files = 0;         // > 0: a group of whole files (their ends are in the slot's meta)
     bool gz = false;              // the group's files are ordinary .gz, decoded by the pipeline's gz stage: its files [gz_file0, +n_files)
     uint32_t gz_file0 = 0, gz_sub_lo = 0, gz_sub_hi = 0, gz_slice0 = 0, gz_slices = 0;      // and their sub-chunks / CRC slices
+    unsigned gz_set = 0;          // which of the stage's two buffer sets the batch sits in
     const uint8_t *dev_src = nullptr;   // the chunk's text is already on the device (a slice of a streamed .gz piece's text)
 };
 
@@ -1291,9 +1299,10 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     } else if (ch.gz) {
         // the batch was decoded and chained on this stream already: symbols -> text of this chunk's files, then their CRC-32
         GzStage &z = g->gz;
-        gz_launch_translate(z.d_files, z.d_sub_file, ch.gz_sub_lo, ch.gz_sub_hi, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres,
+        const GzBufSet &zs = z.set[ch.gz_set];
+        gz_launch_translate(zs.d_files, zs.d_sub_file, ch.gz_sub_lo, ch.gz_sub_hi, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres,
                             s.d_text + ING_MAXCARRY, g->inflate_stream);
-        gz_launch_crc(z.d_files, ch.gz_file0, ch.n_files, z.d_slice0 + ch.gz_slice0, ch.gz_slices, s.d_text + ING_MAXCARRY, z.d_fres, z.d_crc_acc, s.d_act,
+        gz_launch_crc(zs.d_files, ch.gz_file0, ch.n_files, zs.d_slice0 + ch.gz_slice0, ch.gz_slices, s.d_text + ING_MAXCARRY, z.d_fres, z.d_crc_acc, s.d_act,
                       g->inflate_stream);
     } else if (ch.dev_src) {
         if (ch.text_len) CK(cudaMemcpyAsync(s.d_text + ING_MAXCARRY, ch.dev_src, ch.text_len, cudaMemcpyDeviceToDevice, g->inflate_stream));
@@ -1385,7 +1394,7 @@ static int ingest_grow_records(s2_ingest *g, const IngSource &src, ull text_tota
 static int ingest_gz_stage_init(s2_ingest *g)
 {
     GzStage &z = g->gz;
-    if (z.d_comp) return 0;
+    if (z.d_res) return 0;
     z.comp_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_BATCH_MB", 128), 1), 2048) << 20;
     z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 32), 4), 4096) << 10;
     // symbols one sub-chunk may produce: S2_GZ_RATIO x its compressed bytes (FASTQ deflates 4-6 : 1, FASTA 3.5 : 1) plus the
@@ -1395,29 +1404,31 @@ static int ingest_gz_stage_init(s2_ingest *g)
     z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64) + (512u << 10);
     z.max_files = ING_MAX_FILES;
     z.max_sub = (uint32_t)(z.comp_cap / z.sub_bytes) + z.max_files;
-    CK(cudaMalloc((void **)&z.d_comp, z.comp_cap + (size_t)z.max_files * 32 + 256));
+    for (auto &zs : z.set) {
+        CK(cudaMalloc((void **)&zs.d_comp, z.comp_cap + (size_t)z.max_files * 32 + 256));
+        CK(cudaHostAlloc((void **)&zs.h_files, (size_t)z.max_files * sizeof(GzFileDesc), cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&zs.d_files, (size_t)z.max_files * sizeof(GzFileDesc)));
+        CK(cudaHostAlloc((void **)&zs.h_sub_file, (size_t)z.max_sub * sizeof(uint32_t), cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&zs.d_sub_file, (size_t)z.max_sub * sizeof(uint32_t)));
+        CK(cudaHostAlloc((void **)&zs.h_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t), cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&zs.d_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t)));
+        CK(cudaEventCreateWithFlags(&zs.idle, cudaEventDisableTiming));
+    }
     // (the symbol area - 1 MB per sub-chunk - and the windows are sized by the batches that come: gz_stage_reserve.  Round 2's
     // first version took them for the largest batch there could be, 12 GB per pipeline, and three strain_detect workers
     // spent 0.8 s each in cudaMalloc - profiles/r2g_detect_bench.txt)
     CK(cudaMalloc((void **)&z.d_res, (size_t)z.max_sub * gz_sub_result_bytes()));
     CK(cudaMalloc((void **)&z.d_carry, 32768));
     CK(cudaMalloc((void **)&z.d_sub_off, (size_t)z.max_sub * sizeof(uint64_t)));
-    CK(cudaHostAlloc((void **)&z.h_files, (size_t)z.max_files * sizeof(GzFileDesc), cudaHostAllocDefault));
-    CK(cudaMalloc((void **)&z.d_files, (size_t)z.max_files * sizeof(GzFileDesc)));
-    CK(cudaHostAlloc((void **)&z.h_sub_file, (size_t)z.max_sub * sizeof(uint32_t), cudaHostAllocDefault));
-    CK(cudaMalloc((void **)&z.d_sub_file, (size_t)z.max_sub * sizeof(uint32_t)));
-    CK(cudaHostAlloc((void **)&z.h_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t), cudaHostAllocDefault));
-    CK(cudaMalloc((void **)&z.d_slice0, ((size_t)z.max_files * 2 + 2) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&z.d_fres, (size_t)z.max_files * sizeof(GzFileResult)));
     CK(cudaMalloc((void **)&z.d_crc_acc, (size_t)z.max_files * sizeof(uint32_t)));
     CK(cudaMemset(z.d_crc_acc, 0, (size_t)z.max_files * sizeof(uint32_t)));
-    CK(cudaEventCreateWithFlags(&z.idle, cudaEventDisableTiming));
     return 0;
 }
 
 static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk &ch, bool bgzf, bool fasta, int mode, int col, unsigned inc, bool want_result);
 
-// room for a batch of n_sub sub-chunks in n_files files.  The stage must be idle (z.idle waited for).
+// room for a batch of n_sub sub-chunks in n_files files (growing waits for whatever the stage still has in flight)
 static int gz_stage_reserve(s2_ingest *g, uint32_t n_sub, uint32_t n_files)
 {
     GzStage &z = g->gz;
@@ -1449,6 +1460,7 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
 {
     if (ingest_gz_stage_init(g)) return -1;
     GzStage &z = g->gz;
+    GzBufSet &zs = z.set[0];                                                     // pieces go one at a time: one set is enough
     g->call_chunk0 = g->n_chunks;
     const size_t tail = std::min<size_t>(4u << 20, z.comp_cap / 4);             // bytes of the next piece the last sub-chunk may run on into
     const size_t piece_bytes = (z.comp_cap - tail) / z.sub_bytes * z.sub_bytes;
@@ -1458,7 +1470,7 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
         const uint64_t ratio = std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64);
         const size_t want_cap = (size_t)std::min<uint64_t>((uint64_t)std::min<size_t>(piece_bytes, (size_t)std::max<ssize_t>(size, 0)) * ratio + (1u << 20), 4ull << 30);
         if (want_cap > z.piece_text_cap) {
-            CK(cudaEventSynchronize(z.idle));
+            CK(cudaEventSynchronize(z.set[0].idle)); CK(cudaEventSynchronize(z.set[1].idle));
             CK(cudaStreamSynchronize(g->inflate_stream));
             cudaFree(z.d_piece_text); z.d_piece_text = nullptr; z.piece_text_cap = 0;
             if (cudaMalloc((void **)&z.d_piece_text, want_cap + 64) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip text)"); return -1; }
@@ -1478,34 +1490,34 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
     for (off_t base = 0; !broken && !finished && base < size; base += (off_t)piece_bytes) {
         const bool last_piece = (size_t)base + piece_bytes >= (size_t)size;
         const size_t want = std::min<size_t>(piece_bytes + tail, (size_t)size - (size_t)base);
-        CK(cudaEventSynchronize(z.idle));                                        // the previous piece's text has left the stage
+        CK(cudaEventSynchronize(z.set[0].idle)); CK(cudaEventSynchronize(z.set[1].idle));      // the previous piece's (or batch's) text has left the stage
         if (gz_stage_reserve(g, (uint32_t)((std::min<size_t>(piece_bytes, (size_t)size - (size_t)base) + z.sub_bytes - 1) / z.sub_bytes), 1)) return -1;
         if (src.mem) {
-            CK(cudaMemcpyAsync(z.d_comp, src.mem + base, want, cudaMemcpyHostToDevice, g->copy_stream));
+            CK(cudaMemcpyAsync(zs.d_comp, src.mem + base, want, cudaMemcpyHostToDevice, g->copy_stream));
         } else {
-            if (!z.h_comp) CK(cudaHostAlloc((void **)&z.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
-            if (ing_pread(src.fd, z.h_comp, want, base) != (ssize_t)want) { s2_set_error("read failed"); return -1; }
-            CK(cudaMemcpyAsync(z.d_comp, z.h_comp, want, cudaMemcpyHostToDevice, g->copy_stream));
+            if (!zs.h_comp) CK(cudaHostAlloc((void **)&zs.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
+            if (ing_pread(src.fd, zs.h_comp, want, base) != (ssize_t)want) { s2_set_error("read failed"); return -1; }
+            CK(cudaMemcpyAsync(zs.d_comp, zs.h_comp, want, cudaMemcpyHostToDevice, g->copy_stream));
         }
-        CK(cudaMemsetAsync(z.d_comp + want, 0, 64, g->copy_stream));
-        GzFileDesc &d = z.h_files[0];
+        CK(cudaMemsetAsync(zs.d_comp + want, 0, 64, g->copy_stream));
+        GzFileDesc &d = zs.h_files[0];
         d.comp_off = 0; d.comp_len = want; d.first_bit = base == 0 ? hl * 8 : ~0ull; d.chain_bit = chain_abs - (uint64_t)base * 8;
         d.text_off = 0; d.text_len = z.piece_text_cap; d.text_before = text_total; d.sub0 = 0;
         d.n_sub = (uint32_t)((std::min<size_t>(piece_bytes, (size_t)size - (size_t)base) + z.sub_bytes - 1) / z.sub_bytes);
         d.piece = last_piece ? 2u : 1u; d.pad_ = 0;
-        for (uint32_t k = 0; k < d.n_sub; ++k) z.h_sub_file[k] = 0;
-        z.h_slice0[0] = 0; z.h_slice0[1] = 0xFFFFFFFFu;
-        CK(cudaMemcpyAsync(z.d_files, z.h_files, sizeof(GzFileDesc), cudaMemcpyHostToDevice, g->copy_stream));
-        CK(cudaMemcpyAsync(z.d_sub_file, z.h_sub_file, (size_t)d.n_sub * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
-        CK(cudaMemcpyAsync(z.d_slice0, z.h_slice0, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+        for (uint32_t k = 0; k < d.n_sub; ++k) zs.h_sub_file[k] = 0;
+        zs.h_slice0[0] = 0; zs.h_slice0[1] = 0xFFFFFFFFu;
+        CK(cudaMemcpyAsync(zs.d_files, zs.h_files, sizeof(GzFileDesc), cudaMemcpyHostToDevice, g->copy_stream));
+        CK(cudaMemcpyAsync(zs.d_sub_file, zs.h_sub_file, (size_t)d.n_sub * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+        CK(cudaMemcpyAsync(zs.d_slice0, zs.h_slice0, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
         cudaEvent_t up = g->slot[0].h2d_done;
         CK(cudaEventRecord(up, g->copy_stream));
         CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
         if (base) CK(cudaMemcpyAsync(z.d_win, d_carry, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));      // the window the previous piece left
-        gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, d.n_sub, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
-        gz_launch_chain(z.d_comp, z.d_files, 1, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
-        gz_launch_translate(z.d_files, z.d_sub_file, 0, d.n_sub, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres, z.d_piece_text, g->inflate_stream);
-        gz_launch_crc(z.d_files, 0, 1, z.d_slice0, (uint32_t)(z.piece_text_cap / 4096) + 1, z.d_piece_text, z.d_fres, z.d_crc_acc, nullptr, g->inflate_stream);
+        gz_launch_decode(zs.d_comp, zs.d_files, zs.d_sub_file, d.n_sub, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
+        gz_launch_chain(zs.d_comp, zs.d_files, 1, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
+        gz_launch_translate(zs.d_files, zs.d_sub_file, 0, d.n_sub, z.d_sym, z.sub_cap, z.d_win, z.d_sub_off, z.d_fres, z.d_piece_text, g->inflate_stream);
+        gz_launch_crc(zs.d_files, 0, 1, zs.d_slice0, (uint32_t)(z.piece_text_cap / 4096) + 1, z.d_piece_text, z.d_fres, z.d_crc_acc, nullptr, g->inflate_stream);
         CK(cudaMemcpyAsync(d_carry, z.d_win + (size_t)d.n_sub * 32768, 32768, cudaMemcpyDeviceToDevice, g->inflate_stream));
         CK(cudaMemcpyAsync(z.h_fres, z.d_fres, sizeof(GzFileResult), cudaMemcpyDeviceToHost, g->inflate_stream));
         CK(cudaStreamSynchronize(g->inflate_stream));
@@ -1536,7 +1548,7 @@ static int ingest_stream_gz(s2_ingest *g, s2_table *t, const IngSource &src, int
             ++n;
             off += ch.text_len;
         } while (off < L);
-        CK(cudaEventRecord(z.idle, g->inflate_stream));
+        CK(cudaEventRecord(zs.idle, g->inflate_stream));
         text_total += L;
     }
     if (chunks_done) *chunks_done = n;
@@ -1719,10 +1731,13 @@ struct s2_ingest_job {
             at = end;
             if (members.empty()) continue;
             // ---- bytes: caller's memory goes straight to the device, files through the stage's pinned buffer ----------
-            CK(cudaEventSynchronize(z.idle));                       // the previous batch is out of the stage's buffers
+            GzBufSet &zs = z.set[z.batch_no & 1u];                  // (the other set belongs to the batch before this one, which may still be decoding)
+            const unsigned set_no = z.batch_no & 1u;
+            ++z.batch_no;
+            CK(cudaEventSynchronize(zs.idle));                      // the batch before the previous one is out of this set's buffers
             if (gz_stage_reserve(g, n_sub, n_files)) return -1;
-            if (!srcs[members[0]].mem && !z.h_comp) CK(cudaHostAlloc((void **)&z.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
-            CK(cudaMemsetAsync(z.d_comp, 0, comp_used + 64, g->copy_stream));              // zero padding behind every file
+            if (!srcs[members[0]].mem && !zs.h_comp) CK(cudaHostAlloc((void **)&zs.h_comp, z.comp_cap + (size_t)z.max_files * 32 + 256, cudaHostAllocDefault));
+            CK(cudaMemsetAsync(zs.d_comp, 0, comp_used + 64, g->copy_stream));              // zero padding behind every file
             size_t off = 0;
             uint32_t sub0 = 0, nf = 0;
             std::vector<int> good;
@@ -1731,52 +1746,52 @@ struct s2_ingest_job {
                 const size_t size = (size_t)src.size();
                 const uint8_t *h = src.mem;
                 if (!src.mem) {
-                    if (ing_pread(src.fd, z.h_comp + off, size, 0) != (ssize_t)size) { s2_set_error("read failed"); return -1; }
-                    memset(z.h_comp + off + size, 0, (size + 15) / 16 * 16 + 16 - size);
-                    h = z.h_comp + off;
+                    if (ing_pread(src.fd, zs.h_comp + off, size, 0) != (ssize_t)size) { s2_set_error("read failed"); return -1; }
+                    memset(zs.h_comp + off + size, 0, (size + 15) / 16 * 16 + 16 - size);
+                    h = zs.h_comp + off;
                 }
                 const uint64_t hl = s2_gzip_header_len(h, size);
                 if (!hl) { rc[i] = 1; continue; }                   // not a gzip member after all
                 const uint32_t subs = (uint32_t)((size + z.sub_bytes - 1) / z.sub_bytes);
-                GzFileDesc &d = z.h_files[nf];
+                GzFileDesc &d = zs.h_files[nf];
                 d.comp_off = off; d.comp_len = size; d.first_bit = hl * 8; d.chain_bit = hl * 8; d.text_off = 0; d.text_len = src.gz_isize; d.text_before = 0;
                 d.sub0 = sub0; d.n_sub = subs; d.piece = 0; d.pad_ = 0;
-                for (uint32_t k = 0; k < subs; ++k) z.h_sub_file[sub0 + k] = nf;
-                if (src.mem) CK(cudaMemcpyAsync(z.d_comp + off, h, size, cudaMemcpyHostToDevice, g->copy_stream));
+                for (uint32_t k = 0; k < subs; ++k) zs.h_sub_file[sub0 + k] = nf;
+                if (src.mem) CK(cudaMemcpyAsync(zs.d_comp + off, h, size, cudaMemcpyHostToDevice, g->copy_stream));
                 off += (size + 15) / 16 * 16 + 16;
                 sub0 += subs; ++nf;
                 good.push_back(i);
             }
             if (good.empty()) continue;
-            if (!srcs[good[0]].mem) CK(cudaMemcpyAsync(z.d_comp, z.h_comp, off, cudaMemcpyHostToDevice, g->copy_stream));
+            if (!srcs[good[0]].mem) CK(cudaMemcpyAsync(zs.d_comp, zs.h_comp, off, cudaMemcpyHostToDevice, g->copy_stream));
             // ---- plan the pipeline chunks: groups of whole files of one kind whose texts fit a chunk --------------------
             struct Plan { uint32_t f0, f1, sub_lo, sub_hi, slice0, slices; size_t text; bool fasta; };
             std::vector<Plan> plans;
             uint32_t slice_at = 0;
             for (uint32_t f = 0; f < nf;) {
-                Plan p; p.f0 = f; p.sub_lo = z.h_files[f].sub0; p.text = 0; p.fasta = srcs[good[f]].fasta; p.slice0 = slice_at + (uint32_t)plans.size();
+                Plan p; p.f0 = f; p.sub_lo = zs.h_files[f].sub0; p.text = 0; p.fasta = srcs[good[f]].fasta; p.slice0 = slice_at + (uint32_t)plans.size();
                 uint32_t local = 0;
-                while (f < nf && srcs[good[f]].fasta == p.fasta && p.text + z.h_files[f].text_len <= g->text_cap && f - p.f0 < ING_MAX_FILES) {
-                    z.h_files[f].text_off = p.text;
-                    z.h_slice0[p.slice0 + (f - p.f0)] = local;
-                    local += (uint32_t)((z.h_files[f].text_len + 4095) / 4096);
-                    p.text += z.h_files[f].text_len;
+                while (f < nf && srcs[good[f]].fasta == p.fasta && p.text + zs.h_files[f].text_len <= g->text_cap && f - p.f0 < ING_MAX_FILES) {
+                    zs.h_files[f].text_off = p.text;
+                    zs.h_slice0[p.slice0 + (f - p.f0)] = local;
+                    local += (uint32_t)((zs.h_files[f].text_len + 4095) / 4096);
+                    p.text += zs.h_files[f].text_len;
                     ++f;
                 }
-                z.h_slice0[p.slice0 + (f - p.f0)] = local;
-                p.f1 = f; p.sub_hi = f < nf ? z.h_files[f].sub0 : sub0; p.slices = local;
+                zs.h_slice0[p.slice0 + (f - p.f0)] = local;
+                p.f1 = f; p.sub_hi = f < nf ? zs.h_files[f].sub0 : sub0; p.slices = local;
                 slice_at += f - p.f0;
                 plans.push_back(p);
             }
-            CK(cudaMemcpyAsync(z.d_files, z.h_files, (size_t)nf * sizeof(GzFileDesc), cudaMemcpyHostToDevice, g->copy_stream));
-            CK(cudaMemcpyAsync(z.d_sub_file, z.h_sub_file, (size_t)sub0 * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
-            CK(cudaMemcpyAsync(z.d_slice0, z.h_slice0, ((size_t)nf + plans.size()) * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+            CK(cudaMemcpyAsync(zs.d_files, zs.h_files, (size_t)nf * sizeof(GzFileDesc), cudaMemcpyHostToDevice, g->copy_stream));
+            CK(cudaMemcpyAsync(zs.d_sub_file, zs.h_sub_file, (size_t)sub0 * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
+            CK(cudaMemcpyAsync(zs.d_slice0, zs.h_slice0, ((size_t)nf + plans.size()) * sizeof(uint32_t), cudaMemcpyHostToDevice, g->copy_stream));
             // ---- decode + chain of the whole batch, on the inflate stream -------------------------------------------------
             cudaEvent_t up = g->slot[0].h2d_done;                   // (any event will do: recorded and waited for right here)
             CK(cudaEventRecord(up, g->copy_stream));
             CK(cudaStreamWaitEvent(g->inflate_stream, up, 0));
-            gz_launch_decode(z.d_comp, z.d_files, z.d_sub_file, sub0, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
-            gz_launch_chain(z.d_comp, z.d_files, nf, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
+            gz_launch_decode(zs.d_comp, zs.d_files, zs.d_sub_file, sub0, z.sub_bytes, z.d_sym, z.sub_cap, z.d_res, g->inflate_stream);
+            gz_launch_chain(zs.d_comp, zs.d_files, nf, z.d_sym, z.sub_cap, z.d_res, z.d_win, z.d_sub_off, z.d_fres, g->inflate_stream);
             CK(cudaGetLastError());
             // ---- one ordinary group per plan ------------------------------------------------------------------------------
             for (const Plan &p : plans) {
@@ -1785,18 +1800,18 @@ struct s2_ingest_job {
                 if (ingest_slot_begin(g, &sl)) return -1;
                 IngChunk c2;
                 c2.comp_len = 0; c2.text_len = p.text; c2.first = true; c2.last = true; c2.n_files = p.f1 - p.f0; c2.gz = true;
-                c2.gz_file0 = p.f0; c2.gz_sub_lo = p.sub_lo; c2.gz_sub_hi = p.sub_hi; c2.gz_slice0 = p.slice0; c2.gz_slices = p.slices;
+                c2.gz_set = set_no; c2.gz_file0 = p.f0; c2.gz_sub_lo = p.sub_lo; c2.gz_sub_hi = p.sub_hi; c2.gz_slice0 = p.slice0; c2.gz_slices = p.slices;
                 IngGroup gr;
                 for (uint32_t f = p.f0; f < p.f1; ++f) {
-                    ((ull *)sl->h_meta)[f - p.f0] = z.h_files[f].text_off + z.h_files[f].text_len;                    // where file f's text ends
-                    ((unsigned *)(sl->h_meta + (size_t)ING_MAX_FILES * 8))[f - p.f0] = (unsigned)z.h_files[f].text_len;       // isz
+                    ((ull *)sl->h_meta)[f - p.f0] = zs.h_files[f].text_off + zs.h_files[f].text_len;                    // where file f's text ends
+                    ((unsigned *)(sl->h_meta + (size_t)ING_MAX_FILES * 8))[f - p.f0] = (unsigned)zs.h_files[f].text_len;       // isz
                     gr.members.push_back(good[f]);
                 }
                 gr.result = g->res_seq;
                 if (ingest_enqueue(g, t, *sl, c2, false, p.fasta, ING_COUNT, col, 1u, true)) return -1;
                 groups.push_back(gr);
             }
-            CK(cudaEventRecord(z.idle, g->inflate_stream));
+            CK(cudaEventRecord(zs.idle, g->inflate_stream));
         }
         return 0;
     }

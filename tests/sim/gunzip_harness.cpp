@@ -27,9 +27,11 @@ int sim_pgunzip(const unsigned char *src, unsigned long long n, unsigned sub_byt
     std::vector<uint16_t> sym((size_t)n_sub * sub_cap);
     std::vector<GzSubResult> res(n_sub);
     static GzTables t;
+    static uint8_t kraft9[512];
+    gz_kraft9_fill(kraft9, 0, 1);
     for (uint64_t i = 0; i < n_sub; ++i)
         gz_subchunk(words.data(), n_words, i == 0 ? hl * 8 : ~0ull, i * sub_bytes * 8ull, (i + 1) * sub_bytes * 8ull, 8ull << 20, sym.data() + i * sub_cap,
-                    sub_cap, t, &res[i], 0, 1);
+                    sub_cap, t, kraft9, &res[i], 0, 1);
     // chain
     uint64_t cur = hl * 8, total = 0, end_bit = 0;
     bool done = false;
