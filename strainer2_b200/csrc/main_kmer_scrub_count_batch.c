@@ -1,11 +1,26 @@
 /* drop-in executable: everything lives in libstrainer2_b200.so.  The process ends with _exit() after flushing its
- * streams: tearing the CUDA context down at exit costs up to seconds and frees nothing the OS does not free anyway. */
+ * streams: tearing the CUDA context down at exit costs up to seconds and frees nothing the OS does not free anyway.
+ * One case starts over: the hardware decompression engine met a BGZF member it cannot decode.  It reports that as a sticky
+ * launch failure - the CUDA context is gone, and nothing says which of the files in flight it was - so the program runs
+ * again with host inflate (S2_GPU_INGEST=0), where zlib names the damaged file (the run still ends with exit code 1). */
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <unistd.h>
 int s2_kmer_scrub_count_batch_main(int argc, char **argv);
+int s2_ingest_engine_failed(void);
 int main(int argc, char **argv)
 {
     const int rc = s2_kmer_scrub_count_batch_main(argc, argv);
     fflush(NULL);
+    if (rc != 0 && s2_ingest_engine_failed()) {
+        const char *gi = getenv("S2_GPU_INGEST");
+        if (!gi || strcmp(gi, "0")) {
+            fprintf(stderr, "[s2] starting over with host inflate (S2_GPU_INGEST=0) to name the damaged file\n");
+            fflush(NULL);
+            setenv("S2_GPU_INGEST", "0", 1);
+            execv("/proc/self/exe", argv);
+        }
+    }
     _exit(rc);
 }

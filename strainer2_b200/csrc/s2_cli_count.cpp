@@ -187,8 +187,8 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
 
     // GPU ingest takes runs of files (same counter column, S2_INGEST_BATCH files / S2_INGEST_BATCH_MB compressed bytes
     // at most) so that small files share a chunk; everything it does not handle goes through the host reader below
-    const size_t max_run = gpu_ingest && !exotic ? (size_t)std::max(1, s2_env_int("S2_INGEST_BATCH", 32)) : 1;
-    const uint64_t run_bytes = s2_env_u64("S2_INGEST_BATCH_MB", 32) << 20;
+    const size_t max_run = gpu_ingest && !exotic ? (size_t)std::max(1, s2_env_int("S2_INGEST_BATCH", 256)) : 1;
+    const uint64_t run_bytes = s2_env_u64("S2_INGEST_BATCH_MB", std::max<uint64_t>(g_arena_default_mb, 16)) << 20;      // a run fills an arena
     struct Taken { std::string path; s2_reader *r; uint64_t size; };
     // Reader threads read whole files into pinned ARENAS of their own (two per thread: one being filled while the job
     // on the other is in flight) and hand the images to the ingest pipeline, which copies them to the device from
@@ -419,7 +419,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     }
     // (an ordinary .gz at the head of a list: the pipelines' gunzip stages are made ready as well - s2_ingest_warm_gz)
     const bool gz_inputs = warm_pipes && (s2_list_starts_with_plain_gz(A_file) || s2_list_starts_with_plain_gz(B_file));
-    if (gz_inputs) g_arena_default_mb = 48;
+    if (gz_inputs) g_arena_default_mb = 96;
     const uint64_t arena_mb = std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", g_arena_default_mb), 1);
     for (int g = 0; g < n_gpus && warm_pipes; ++g)
         warmers.emplace_back([&, g]() { if (gz_inputs) s2_ingest_warm_gz(ctxs[g], warm_pipes, arena_mb << 20); else s2_ingest_warm(ctxs[g], warm_pipes); });
@@ -469,7 +469,9 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     std::string open_error;
     uint64_t total_bases = 0, total_lookups = 0;
     join_all(warmers);
-    const bool pool_ok = s2_scan_work_items_multi(ctxs, tables, exotic, work, n_threads, progress, open_error, &total_bases, &total_lookups);
+    // (ordinary .gz: fewer readers with larger arenas - a 96 MB run is 3,000 decoding warps, and eight threads read faster than the GPU decodes)
+    const int scan_threads = gz_inputs ? std::max(n_gpus, std::min(n_threads, 8 * n_gpus)) : n_threads;
+    const bool pool_ok = s2_scan_work_items_multi(ctxs, tables, exotic, work, scan_threads, progress, open_error, &total_bases, &total_lookups);
     s2_scan_stats st = {};
     for (int g = 0; g < n_gpus; ++g) {
         s2_scan_stats sg = {};

@@ -296,6 +296,64 @@ __global__ void gz_crc_finish_kernel(const GzFileDesc *__restrict__ files, uint3
 }
 
 // ------------------------------------------------------------------------------------------------
+// CRC-32 of the members of a BGZF chunk (the hardware engine inflates them and checks nothing: a member that is damaged
+// but still inflates to its stated size would be counted silently, while the same file through zlib ends the run -
+// ADVICE r1).  One CTA per member (<= 64 KB of text): 128-byte runs with slicing-by-4, each moved into place by
+// x^(8 x 128 x runs behind it) from a table and x^(8 x length of the last run); a mismatch turns the member's
+// "bytes produced" into all ones, which ing_check_chunk's act == isz test turns into a veto of the chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void gz_xp128_kernel(uint32_t *xp128)                 // xp128[j] = x^(8 * 128 * j) mod P, j = 0 .. 512
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= 512u) xp128[j] = crc_xpow8(128ull * j);
+}
+
+__global__ void __launch_bounds__(256)
+gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ isz, const uint32_t *__restrict__ want_crc,
+                     const uint32_t *__restrict__ toff, unsigned *act, const uint32_t *__restrict__ xp128)
+{
+    __shared__ uint32_t table[4][256];
+    __shared__ uint32_t s_acc, s_xl;
+    {
+        uint32_t c = threadIdx.x;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+        table[0][threadIdx.x] = c;
+        __syncthreads();
+        uint32_t v = c;
+        for (int t = 1; t < 4; ++t) { v = (v >> 8) ^ table[0][v & 0xFFu]; table[t][threadIdx.x] = v; }
+    }
+    const uint32_t m = blockIdx.x;
+    const uint32_t len = isz[m];
+    if (len == 0 || len > 65536u) return;                               // (uniform; the host lists no empty members)
+    const uint32_t n_runs = (len + 127u) / 128u, last_len = len - 128u * (n_runs - 1u);
+    if (threadIdx.x == 0) { s_acc = 0; s_xl = crc_xpow8(last_len); }
+    __syncthreads();
+    const uint8_t *p = text + toff[m];
+    uint32_t acc = 0;
+    for (uint32_t k = threadIdx.x; k < n_runs; k += 256u) {
+        const uint32_t s0 = 128u * k, s1 = s0 + 128u < len ? s0 + 128u : len;
+        uint32_t c = 0, i = s0;
+        for (; i < s1 && ((uintptr_t)(p + i) & 3u); ++i) c = table[0][(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+        for (; i + 4u <= s1; i += 4u) {
+            c ^= *reinterpret_cast<const uint32_t *>(p + i);
+            c = table[3][c & 0xFFu] ^ table[2][(c >> 8) & 0xFFu] ^ table[1][(c >> 16) & 0xFFu] ^ table[0][c >> 24];
+        }
+        for (; i < s1; ++i) c = table[0][(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+        if (k + 1u < n_runs) c = crc_mulmod(crc_mulmod(c, xp128[n_runs - 2u - k]), s_xl);      // bytes behind this run: 128 (n_runs - 2 - k) + last_len
+        acc ^= c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31u) == 0 && acc) atomicXor(&s_acc, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t xlen = crc_mulmod(xp128[n_runs - 1u], s_xl);                          // x^(8 len)
+        const uint32_t got = s_acc ^ crc_mulmod(0xFFFFFFFFu, xlen) ^ 0xFFFFFFFFu;
+        if (got != want_crc[m]) act[m] = 0xFFFFFFFFu;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 size_t gz_tables_bytes(void) { return sizeof(GzTables); }
@@ -334,4 +392,12 @@ void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, co
     if (!n_files) return;
     if (n_slices) gz_crc_kernel<<<(n_slices + 7) / 8, 256, 0, st>>>(files, file0, n_files, file_slice0, n_slices, text, fres, crc_acc);
     gz_crc_finish_kernel<<<(n_files + 127) / 128, 128, 0, st>>>(files, file0, n_files, fres, crc_acc, act);
+}
+
+void gz_launch_xp128_init(uint32_t *xp128, cudaStream_t st) { gz_xp128_kernel<<<3, 256, 0, st>>>(xp128); }
+
+void gz_launch_member_crc(const uint8_t *text, const uint32_t *isz, const uint32_t *want_crc, const uint32_t *toff, uint32_t n_members, unsigned *act,
+                          const uint32_t *xp128, cudaStream_t st)
+{
+    if (n_members) gz_member_crc_kernel<<<n_members, 256, 0, st>>>(text, isz, want_crc, toff, act, xp128);
 }

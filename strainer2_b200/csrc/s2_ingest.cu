@@ -762,6 +762,8 @@ struct s2_ingest {
     uint64_t res_seq = 0;                // verdicts handed out so far; slot = res_seq % ING_MAX_RESULTS
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
+    bool bgzf_crc = true;                // S2_BGZF_CRC=0: trust the members' ISIZE alone (round 1's behaviour)
+    uint32_t *d_xp128 = nullptr;         // x^(8 * 128 * j) mod P for the member CRC kernel
     int grid_scan = 0;                   // CTAs of the count scan launched from this pipeline
     GzStage gz;                          // ordinary .gz batches (allocated on first use)
     // detect mode: chunk-local and file-level result arrays
@@ -798,14 +800,18 @@ static void ingest_free(s2_ingest *g)
     cudaFree(g->d_flat);
     cudaFree(g->d_block_nl); cudaFree(g->d_block_out); cudaFree(g->d_line_end); cudaFree(g->d_masks); cudaFree(g->d_tickets);
     cudaFree(g->part_pool); cudaFree(g->part_cursor); cudaFree(g->part_overflow);
-    cudaFree(g->d_state); cudaFreeHost(g->h_results);
+    cudaFree(g->d_state); cudaFreeHost(g->h_results); cudaFree(g->d_xp128);
     cudaFree(g->d_hits_c); cudaFree(g->d_inf_c); cudaFree(g->d_rec_off); cudaFree(g->d_pos_c); cudaFree(g->d_cnt_c); cudaFree(g->d_fcnt);
     cudaFree(g->d_len_all); cudaFree(g->d_hits_all); cudaFree(g->d_inf_all); cudaFree(g->d_frec); cudaFree(g->d_foff); cudaFree(g->d_fkmer);
     cudaGetLastError();
     delete g;
 }
 
-#define ING_META_BYTES ((size_t)ING_MAX_FILES * 8 + (size_t)ING_MAX_DBLOCKS * 4)
+// per chunk: [file_end: u64 x MAX_FILES][isz: u32 x MAX_DBLOCKS][BGZF members' CRC-32: u32 x MAX_DBLOCKS][where their text starts: u32 x MAX_DBLOCKS]
+#define ING_META_ISZ ((size_t)ING_MAX_FILES * 8)
+#define ING_META_CRC (ING_META_ISZ + (size_t)ING_MAX_DBLOCKS * 4)
+#define ING_META_TOFF (ING_META_CRC + (size_t)ING_MAX_DBLOCKS * 4)
+#define ING_META_BYTES (ING_META_TOFF + (size_t)ING_MAX_DBLOCKS * 4)
 static int ingest_init(s2_ingest *g, s2_ctx *c)
 {
     g->ctx = c; g->device = c->device;
@@ -836,6 +842,9 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     CK(cudaMalloc((void **)&g->d_line_end, (size_t)g->max_lines * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_state, sizeof(IngState)));
     CK(cudaMemset(g->d_state, 0, sizeof(IngState)));                   // afterwards every finished file leaves a clean state behind
+    g->bgzf_crc = s2_env_int("S2_BGZF_CRC", 1) != 0;
+    CK(cudaMalloc((void **)&g->d_xp128, 513 * sizeof(uint32_t)));
+    gz_launch_xp128_init(g->d_xp128, g->inflate_stream);
     CK(cudaMalloc((void **)&g->d_tickets, 4 * sizeof(unsigned)));
     CK(cudaMemset(g->d_tickets, 0, 4 * sizeof(unsigned)));
     CK(cudaHostAlloc((void **)&g->h_results, ING_MAX_RESULTS * sizeof(IngResult), cudaHostAllocMapped));
@@ -1229,7 +1238,7 @@ static int ingest_staging(IngSlot &s, size_t bytes)
 static size_t ingest_walk_bgzf(s2_ingest *g, IngSlot &s, const uint8_t *h, size_t avail, size_t comp_off, size_t *text_len, bool *full)
 {
     size_t used = 0;
-    unsigned *isz_list = (unsigned *)(s.h_meta + (size_t)ING_MAX_FILES * 8);
+    unsigned *isz_list = (unsigned *)(s.h_meta + ING_META_ISZ), *crc_list = (unsigned *)(s.h_meta + ING_META_CRC), *toff_list = (unsigned *)(s.h_meta + ING_META_TOFF);
     *full = false;
     while (used < avail) {
         size_t bs = 0, doff = 0, dlen = 0; uint32_t isz = 0;
@@ -1245,6 +1254,9 @@ static size_t ingest_walk_bgzf(s2_ingest *g, IngSlot &s, const uint8_t *h, size_
             p.dst = s.d_text + ING_MAXCARRY + *text_len;
             p.algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
             isz_list[s.params.size()] = isz;
+            const uint8_t *tr = h + used + bs - 8;                           // the member's trailer: CRC-32, ISIZE
+            crc_list[s.params.size()] = (uint32_t)tr[0] | (uint32_t)tr[1] << 8 | (uint32_t)tr[2] << 16 | (uint32_t)tr[3] << 24;
+            toff_list[s.params.size()] = (unsigned)*text_len;
             s.params.push_back(p);
             *text_len += isz;
         }
@@ -1282,7 +1294,12 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     // meta (group file ends, expected block sizes) travels with the chunk
     const size_t n_db = bgzf ? s.params.size() : ch.gz ? (size_t)ch.n_files : 0;
     if (ch.n_files) CK(cudaMemcpyAsync(s.d_meta, s.h_meta, (size_t)ch.n_files * 8, cudaMemcpyHostToDevice, g->copy_stream));
-    if (n_db) CK(cudaMemcpyAsync(s.d_meta + (size_t)ING_MAX_FILES * 8, s.h_meta + (size_t)ING_MAX_FILES * 8, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
+    if (n_db) CK(cudaMemcpyAsync(s.d_meta + ING_META_ISZ, s.h_meta + ING_META_ISZ, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
+    const bool member_crc = bgzf && n_db && g->bgzf_crc;
+    if (member_crc) {
+        CK(cudaMemcpyAsync(s.d_meta + ING_META_CRC, s.h_meta + ING_META_CRC, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
+        CK(cudaMemcpyAsync(s.d_meta + ING_META_TOFF, s.h_meta + ING_META_TOFF, n_db * 4, cudaMemcpyHostToDevice, g->copy_stream));
+    }
     tr_record(1, g->copy_stream);
     if (tr_on && !tr_events.empty()) { tr_events.back().comp = ch.comp_len; tr_events.back().text = ch.text_len; }
     CK(cudaEventRecord(s.h2d_done, g->copy_stream));
@@ -1296,6 +1313,10 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
             const CUresult r = g->decompress(s.params.data() + i, n, 0, &err_index, (CUstream)g->inflate_stream);
             if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, i + err_index); return -1; }
         }
+        // the engine checks no CRC: every member's text against its trailer, before the chunk's verdict is formed
+        if (member_crc)
+            gz_launch_member_crc(s.d_text + ING_MAXCARRY, (const uint32_t *)(s.d_meta + ING_META_ISZ), (const uint32_t *)(s.d_meta + ING_META_CRC),
+                                 (const uint32_t *)(s.d_meta + ING_META_TOFF), (uint32_t)n_db, s.d_act, g->d_xp128, g->inflate_stream);
     } else if (ch.gz) {
         // the batch was decoded and chained on this stream already: symbols -> text of this chunk's files, then their CRC-32
         GzStage &z = g->gz;
@@ -1327,7 +1348,7 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     a.new_bytes = ch.text_len; a.first_chunk = ch.first ? 1u : 0u; a.last_chunk = ch.last ? 1u : 0u; a.inc = inc; a.fasta = fasta ? 1u : 0u;
     a.lsh = reads2 ? 1u : 2u;
     a.n_files = ch.n_files; a.n_dblocks = (unsigned)n_db;
-    a.file_end = (const ull *)s.d_meta; a.isz = (const unsigned *)(s.d_meta + (size_t)ING_MAX_FILES * 8); a.act = s.d_act;
+    a.file_end = (const ull *)s.d_meta; a.isz = (const unsigned *)(s.d_meta + ING_META_ISZ); a.act = s.d_act;
     const unsigned n_blocks = (unsigned)(((size_t)ING_MAXCARRY + ch.text_len) / ING_BLOCK + 1);      // covers [0, t1] of the text buffer
     ing_index_count<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_masks, a, g->max_lines, g->d_tickets + 0);
     ing_index_scatter<<<n_blocks, ING_THREADS, 0, st>>>(g->d_masks, g->d_block_nl, g->d_line_end, g->max_lines);
@@ -1804,7 +1825,7 @@ struct s2_ingest_job {
                 IngGroup gr;
                 for (uint32_t f = p.f0; f < p.f1; ++f) {
                     ((ull *)sl->h_meta)[f - p.f0] = zs.h_files[f].text_off + zs.h_files[f].text_len;                    // where file f's text ends
-                    ((unsigned *)(sl->h_meta + (size_t)ING_MAX_FILES * 8))[f - p.f0] = (unsigned)zs.h_files[f].text_len;       // isz
+                    ((unsigned *)(sl->h_meta + ING_META_ISZ))[f - p.f0] = (unsigned)zs.h_files[f].text_len;       // isz
                     gr.members.push_back(good[f]);
                 }
                 gr.result = g->res_seq;
@@ -1881,7 +1902,7 @@ static void ingest_quiesce(s2_ingest *g)
 // all, cut short, or followed by other bytes inside the stated length - is not reported per stream: it surfaces as a
 // sticky cudaErrorLaunchFailure and the CUDA context is lost.  The host walk only hands over complete BGZF members,
 // so this takes a member whose payload is damaged.  Say so (the callers' generic message would be a bare CUDA error)
-// and remember it: the executables start over with host inflate (main_kmer_scrub_count.c).
+// and remember it: the executables then start over with host inflate (main_*.c: execv with S2_GPU_INGEST=0), where zlib names the file.
 static std::atomic<int> g_engine_failed{0};
 static void ingest_engine_failed_message(void)
 {

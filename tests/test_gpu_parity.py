@@ -789,6 +789,26 @@ def test_gpu_ingest_hands_irregular_files_back_untouched(s2, ctx, tmp_path, monk
         assert rc == 1, name
         assert int(t.counts(1).sum()) == 0, name                     # nothing counted, or everything taken back
         assert st.hits == 0, name
+    # a member whose CRC-32 does not match its text (the hardware engine checks none; zlib would end the run): the member
+    # CRC pass vetoes the chunk, the file is handed back - streamed: after the earlier chunks were taken back out
+    whole = bytearray(synth.bgzf_bytes(good))
+    members, pos = [], 0
+    while pos + 18 <= len(whole):
+        bsize = (whole[pos + 16] | whole[pos + 17] << 8) + 1
+        members.append((pos, bsize))
+        pos += bsize
+    m_pos, m_size = members[len(members) * 2 // 3]
+    whole[m_pos + m_size - 8] ^= 0x40
+    open(os.path.join(tmp, "bad_crc.fastq.gz"), "wb").write(bytes(whole))
+    assert ctx.ingest_count_file(t, os.path.join(tmp, "bad_crc.fastq.gz"), 1)[0] == 1
+    assert int(t.counts(1).sum()) == 0 and ctx.sync().hits == 0
+    monkeypatch.setenv("S2_BGZF_CRC", "0")                                # (read when a pipeline is created)
+    ctx.ingest_reset()
+    assert ctx.ingest_count_file(t, os.path.join(tmp, "bad_crc.fastq.gz"), 1)[0] == 0          # round 1's behaviour: ISIZE alone
+    assert ctx.sync().hits == want.hits
+    t.clear_counts(1)
+    monkeypatch.delenv("S2_BGZF_CRC")
+    ctx.ingest_reset()
     # a BGZF file cut in the middle of a member (streamed: the earlier chunks are taken back)
     whole = synth.bgzf_bytes(good)
     open(os.path.join(tmp, "cut.fastq.gz"), "wb").write(whole[:len(whole) * 3 // 4])
