@@ -224,9 +224,18 @@ extern "C" void s2_table_free(s2_table *t)
     delete t;
 }
 
+// temporaries of one call: released on every way out (the CK() macro returns from the middle of a function)
+struct DevTemps {
+    std::vector<void *> dev, host;
+    template <typename T> cudaError_t alloc(T **p, size_t bytes) { const cudaError_t e = cudaMalloc((void **)p, bytes); if (e == cudaSuccess) dev.push_back(*p); return e; }
+    template <typename T> cudaError_t alloc_host(T **p, size_t bytes) { const cudaError_t e = cudaHostAlloc((void **)p, bytes, cudaHostAllocDefault); if (e == cudaSuccess) host.push_back(*p); return e; }
+    ~DevTemps() { for (void *p : dev) cudaFree(p); for (void *p : host) cudaFreeHost(p); }
+};
+
 static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t n_bytes, int n_cols,
                             double load, int on_device)
 {
+    DevTemps tmp;
     CK(cudaSetDevice(c->device));
     if (n_bytes >= 0xFFFFFFF0ull) { s2_set_error("reference genome of %llu bytes exceeds the 4 GiB build limit", (unsigned long long)n_bytes); return -1; }
     if (n_cols < 1 || n_cols > 8) { s2_set_error("n_cols must be 1..8"); return -1; }
@@ -237,7 +246,7 @@ static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t 
     const uint8_t *d_bases = (const uint8_t *)bases;
     uint8_t *tmp_bases = nullptr;
     if (!on_device && n_bytes) {
-        CK(cudaMalloc((void **)&tmp_bases, n_bytes + 64));
+        CK(tmp.alloc(&tmp_bases, n_bytes + 64));
         CK(cudaMemcpyAsync(tmp_bases, bases, n_bytes, cudaMemcpyHostToDevice, st));
         d_bases = tmp_bases;
     }
@@ -258,12 +267,12 @@ static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t 
     uint32_t *first_pos = nullptr, *slot_of_pos = nullptr, *block_sums = nullptr, *rank_tmp = nullptr, *pos_tmp = nullptr;
     unsigned long long *d_n = nullptr;
     const uint32_t n_blocks = (uint32_t)((n_bytes + 1023) / 1024);
-    CK(cudaMalloc((void **)&first_pos, t->v.n_slots * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&slot_of_pos, (n_bytes + 1) * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&block_sums, (n_blocks + 1) * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&rank_tmp, (upper + 1) * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&pos_tmp, (upper + 1) * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&d_n, sizeof(unsigned long long)));
+    CK(tmp.alloc(&first_pos, t->v.n_slots * sizeof(uint32_t)));
+    CK(tmp.alloc(&slot_of_pos, (n_bytes + 1) * sizeof(uint32_t)));
+    CK(tmp.alloc(&block_sums, (n_blocks + 1) * sizeof(uint32_t)));
+    CK(tmp.alloc(&rank_tmp, (upper + 1) * sizeof(uint32_t)));
+    CK(tmp.alloc(&pos_tmp, (upper + 1) * sizeof(uint32_t)));
+    CK(tmp.alloc(&d_n, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(first_pos, 0xFF, t->v.n_slots * sizeof(uint32_t), st));
 
     s2_launch_build_insert(d_bases, n_bytes, t->v, first_pos, slot_of_pos, st);
@@ -280,9 +289,7 @@ static int table_build_impl(s2_ctx *c, s2_table *t, const void *bases, uint64_t 
     CK(cudaMemcpyAsync(t->rank_slot, rank_tmp, n_keys * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(t->rank_pos, pos_tmp, n_keys * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(first_pos); cudaFree(slot_of_pos); cudaFree(block_sums); cudaFree(rank_tmp); cudaFree(pos_tmp); cudaFree(d_n);
-    if (tmp_bases) cudaFree(tmp_bases);
-    return 0;
+    return 0;                                        // (the temporaries go with `tmp`)
 }
 
 extern "C" s2_table *s2_table_build(s2_ctx *c, const void *bases, uint64_t n_bytes, int n_cols,
@@ -305,15 +312,15 @@ extern "C" int s2_table_export(s2_table *t, uint64_t *keys, uint32_t *djb2, uint
     if (t->n_keys == 0) return 0;
     cudaStream_t st = c->lanes[0].stream;
     uint64_t *d_keys = nullptr; uint32_t *d_h = nullptr;
-    CK(cudaMalloc((void **)&d_keys, t->n_keys * sizeof(uint64_t)));
-    CK(cudaMalloc((void **)&d_h, t->n_keys * sizeof(uint32_t)));
+    DevTemps tmp;
+    CK(tmp.alloc(&d_keys, t->n_keys * sizeof(uint64_t)));
+    CK(tmp.alloc(&d_h, t->n_keys * sizeof(uint32_t)));
     s2_launch_export(t->v, t->rank_slot, t->n_keys, d_keys, d_h, st);
     CK(cudaGetLastError());
     if (keys) CK(cudaMemcpyAsync(keys, d_keys, t->n_keys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     if (djb2) CK(cudaMemcpyAsync(djb2, d_h, t->n_keys * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (first_pos) CK(cudaMemcpyAsync(first_pos, t->rank_pos, t->n_keys * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(d_keys); cudaFree(d_h);
     return 0;
 }
 
@@ -335,15 +342,16 @@ extern "C" int s2_table_format(s2_table *t, const uint32_t *order, int n_print_c
     unsigned long long *d_sums = nullptr, *d_total = nullptr;
     char *d_text = nullptr, *h_stage = nullptr;
     const uint32_t n_blocks = (uint32_t)((n + 1023) / 1024);
-    CK(cudaMalloc((void **)&d_keys, n * sizeof(uint64_t)));
-    CK(cudaMalloc((void **)&d_djb2, n * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&d_order, n * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&d_sums, (n_blocks + 1) * sizeof(unsigned long long)));
-    CK(cudaMalloc((void **)&d_total, sizeof(unsigned long long)));
+    DevTemps tmp;
+    CK(tmp.alloc(&d_keys, n * sizeof(uint64_t)));
+    CK(tmp.alloc(&d_djb2, n * sizeof(uint32_t)));
+    CK(tmp.alloc(&d_order, n * sizeof(uint32_t)));
+    CK(tmp.alloc(&d_sums, (n_blocks + 1) * sizeof(unsigned long long)));
+    CK(tmp.alloc(&d_total, sizeof(unsigned long long)));
     CK(cudaMemcpyAsync(d_order, order, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     s2_launch_export(t->v, t->rank_slot, n, d_keys, d_djb2, st);
     for (int k = 0; k < n_print_cols; ++k) {
-        CK(cudaMalloc((void **)&d_cols[k], n * sizeof(uint32_t)));
+        CK(tmp.alloc(&d_cols[k], n * sizeof(uint32_t)));
         s2_launch_gather_counts(t->v, k, t->rank_slot, n, d_cols[k], st);
     }
     s2_launch_format(d_keys, d_order, n, d_cols, n_print_cols, d_sums, d_total, nullptr, 0, st);
@@ -351,11 +359,11 @@ extern "C" int s2_table_format(s2_table *t, const uint32_t *order, int n_print_c
     unsigned long long total = 0;
     CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaMalloc((void **)&d_text, total + 1));
+    CK(tmp.alloc(&d_text, total + 1));
     s2_launch_format(d_keys, d_order, n, d_cols, n_print_cols, d_sums, d_total, d_text, 1, st);
     CK(cudaGetLastError());
     const size_t stage = 32u << 20;
-    CK(cudaHostAlloc((void **)&h_stage, stage, cudaHostAllocDefault));
+    CK(tmp.alloc_host(&h_stage, stage));
     int rc = 0;
     for (unsigned long long off = 0; off < total && rc == 0; off += stage) {
         const size_t take = (size_t)std::min<unsigned long long>(stage, total - off);
@@ -363,9 +371,6 @@ extern "C" int s2_table_format(s2_table *t, const uint32_t *order, int n_print_c
         CK(cudaStreamSynchronize(st));
         if (fwrite(h_stage, 1, take, out) != take) { s2_set_error("write failed"); rc = -1; }
     }
-    cudaFreeHost(h_stage);
-    cudaFree(d_text); cudaFree(d_keys); cudaFree(d_djb2); cudaFree(d_order); cudaFree(d_sums); cudaFree(d_total);
-    for (auto p : d_cols) if (p) cudaFree(p);
     return rc;
 }
 

@@ -310,7 +310,7 @@ __global__ void gz_xp128_kernel(uint32_t *xp128)                 // xp128[j] = x
 
 __global__ void __launch_bounds__(256)
 gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ isz, const uint32_t *__restrict__ want_crc,
-                     const uint32_t *__restrict__ toff, unsigned *act, const uint32_t *__restrict__ xp128)
+                     const uint32_t *__restrict__ toff, unsigned *act, uint32_t *bad_flag, const uint32_t *__restrict__ xp128)
 {
     __shared__ uint32_t table[4][256];
     __shared__ uint32_t s_acc, s_xl;
@@ -349,7 +349,7 @@ gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restric
     if (threadIdx.x == 0) {
         const uint32_t xlen = crc_mulmod(xp128[n_runs - 1u], s_xl);                          // x^(8 len)
         const uint32_t got = s_acc ^ crc_mulmod(0xFFFFFFFFu, xlen) ^ 0xFFFFFFFFu;
-        if (got != want_crc[m]) act[m] = 0xFFFFFFFFu;
+        if (got != want_crc[m]) { if (act) act[m] = 0xFFFFFFFFu; if (bad_flag) *bad_flag = 1u; }
     }
 }
 
@@ -397,7 +397,7 @@ void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, co
 void gz_launch_xp128_init(uint32_t *xp128, cudaStream_t st) { gz_xp128_kernel<<<3, 256, 0, st>>>(xp128); }
 
 void gz_launch_member_crc(const uint8_t *text, const uint32_t *isz, const uint32_t *want_crc, const uint32_t *toff, uint32_t n_members, unsigned *act,
-                          const uint32_t *xp128, cudaStream_t st)
+                          uint32_t *bad_flag, const uint32_t *xp128, cudaStream_t st)
 {
-    if (n_members) gz_member_crc_kernel<<<n_members, 256, 0, st>>>(text, isz, want_crc, toff, act, xp128);
+    if (n_members) gz_member_crc_kernel<<<n_members, 256, 0, st>>>(text, isz, want_crc, toff, act, bad_flag, xp128);
 }

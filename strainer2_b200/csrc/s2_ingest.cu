@@ -636,6 +636,17 @@ __global__ void __launch_bounds__(ING_THREADS) ing_fasta_copy(const uint8_t *tex
     ing_finish_body(text, text_next, st, flat, 1u, res);
 }
 
+// A BGZF member whose CRC-32 does not match (checked beside the kernels above, on another stream): the chunk is not
+// scanned and the file counts as irregular.  `res` was already written by the copy kernel's last block (count mode);
+// a file that goes on (not the last chunk) stays irregular for its later chunks, a finished one has left a clean state.
+__global__ void ing_crc_veto(IngState *st, const uint32_t *bad, IngResult *res, unsigned last_chunk)
+{
+    if (!*bad) return;
+    st->skip = 1;
+    if (res) res->irregular = 1;
+    if (!last_chunk || !res) st->irregular = 1;          // (detect mode: ing_finish reads and clears it after the scan)
+}
+
 // detect mode: the per-record results are stored after the scan, so the end-of-chunk step is a launch of its own
 __global__ void __launch_bounds__(ING_THREADS) ing_finish(const uint8_t *text, uint8_t *text_next, IngState *st, const uint8_t *flat, unsigned fasta, IngResult *res)
 {
@@ -736,6 +747,8 @@ struct IngSlot {                       // a chunk travels through one slot of th
     cudaEvent_t h2d_done = nullptr;    // copy stream: the chunk's bytes are on the device
     cudaEvent_t inflated = nullptr;    // inflate stream: the text is in d_text
     cudaEvent_t consumed = nullptr;    // kernel stream: the chunk's kernels are through with this slot
+    cudaEvent_t crc_done = nullptr;    // crc stream: the BGZF members' CRC-32 have been compared
+    uint32_t *d_crc_bad = nullptr;     // ... and this is 1 if one of them did not match
 };
 
 struct s2_ingest {
@@ -746,7 +759,7 @@ struct s2_ingest {
     std::mutex mu;
     std::mutex res_mu; std::set<uint64_t> res_live;      // verdict-ring entries handed out and not read yet
     // three streams, one per engine, so that the copy of chunk i+2, the inflate of chunk i+1 and the kernels of chunk i overlap
-    cudaStream_t stream = nullptr, copy_stream = nullptr, inflate_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, inflate_stream = nullptr, crc_stream = nullptr;
     size_t comp_chunk = 0, text_cap = 0; unsigned max_lines = 0;
     IngSlot slot[ING_SLOTS];
     uint64_t n_chunks = 0;             // chunks enqueued so far (slot = n_chunks % ING_SLOTS)
@@ -762,7 +775,7 @@ struct s2_ingest {
     uint64_t res_seq = 0;                // verdicts handed out so far; slot = res_seq % ING_MAX_RESULTS
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
-    bool bgzf_crc = true;                // S2_BGZF_CRC=0: trust the members' ISIZE alone (round 1's behaviour)
+    int bgzf_crc = 2;                    // S2_BGZF_CRC: 0 trust the members' ISIZE alone (round 1), 1 check on the inflate stream, 2 (default) on a stream of its own, beside the chunk's other kernels
     uint32_t *d_xp128 = nullptr;         // x^(8 * 128 * j) mod P for the member CRC kernel
     int grid_scan = 0;                   // CTAs of the count scan launched from this pipeline
     GzStage gz;                          // ordinary .gz batches (allocated on first use)
@@ -780,12 +793,15 @@ static void ingest_free(s2_ingest *g)
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
     if (g->inflate_stream) { cudaStreamSynchronize(g->inflate_stream); cudaStreamDestroy(g->inflate_stream); }
+    if (g->crc_stream) { cudaStreamSynchronize(g->crc_stream); cudaStreamDestroy(g->crc_stream); }
     if (g->stream) cudaStreamDestroy(g->stream);
     for (auto &s : g->slot) {
         cudaFreeHost(s.h_comp); cudaFree(s.d_comp); cudaFree(s.d_text); cudaFreeHost(s.h_meta); cudaFree(s.d_meta); cudaFree(s.d_act);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.inflated) cudaEventDestroy(s.inflated);
         if (s.consumed) cudaEventDestroy(s.consumed);
+        if (s.crc_done) cudaEventDestroy(s.crc_done);
+        cudaFree(s.d_crc_bad);
     }
     {
         GzStage &z = g->gz;
@@ -833,6 +849,8 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
         CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&s.inflated, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.crc_done, cudaEventDisableTiming));
+        CK(cudaMalloc((void **)&s.d_crc_bad, sizeof(uint32_t)));
     }
     CK(cudaMalloc((void **)&g->d_flat, g->text_cap + ING_MAXCARRY + 4096));
     const size_t n_blocks = ((size_t)ING_MAXCARRY + g->text_cap) / ING_BLOCK + 4;
@@ -842,7 +860,8 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     CK(cudaMalloc((void **)&g->d_line_end, (size_t)g->max_lines * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_state, sizeof(IngState)));
     CK(cudaMemset(g->d_state, 0, sizeof(IngState)));                   // afterwards every finished file leaves a clean state behind
-    g->bgzf_crc = s2_env_int("S2_BGZF_CRC", 1) != 0;
+    g->bgzf_crc = s2_env_int("S2_BGZF_CRC", 2);
+    CK(cudaStreamCreateWithFlags(&g->crc_stream, cudaStreamNonBlocking));
     CK(cudaMalloc((void **)&g->d_xp128, 513 * sizeof(uint32_t)));
     gz_launch_xp128_init(g->d_xp128, g->inflate_stream);
     CK(cudaMalloc((void **)&g->d_tickets, 4 * sizeof(unsigned)));
@@ -1314,9 +1333,9 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
             if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, i + err_index); return -1; }
         }
         // the engine checks no CRC: every member's text against its trailer, before the chunk's verdict is formed
-        if (member_crc)
+        if (member_crc && g->bgzf_crc == 1)
             gz_launch_member_crc(s.d_text + ING_MAXCARRY, (const uint32_t *)(s.d_meta + ING_META_ISZ), (const uint32_t *)(s.d_meta + ING_META_CRC),
-                                 (const uint32_t *)(s.d_meta + ING_META_TOFF), (uint32_t)n_db, s.d_act, g->d_xp128, g->inflate_stream);
+                                 (const uint32_t *)(s.d_meta + ING_META_TOFF), (uint32_t)n_db, s.d_act, nullptr, g->d_xp128, g->inflate_stream);
     } else if (ch.gz) {
         // the batch was decoded and chained on this stream already: symbols -> text of this chunk's files, then their CRC-32
         GzStage &z = g->gz;
@@ -1333,6 +1352,17 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     tr_record(3, g->inflate_stream);
     CK(cudaEventRecord(s.inflated, g->inflate_stream));
     CK(cudaStreamWaitEvent(st, s.inflated, 0));
+    // The members' CRC-32 beside the chunk's index / measure / copy kernels, on a stream of its own: only the SCAN waits for
+    // it (ing_crc_veto below).  On the inflate stream the pass made that stage - one of three equally loaded ones - the
+    // slowest: 132 -> 110 Gbases/s end to end (profiles/r2m_bench_n1.json).
+    const bool crc_async = member_crc && g->bgzf_crc >= 2;
+    if (crc_async) {
+        CK(cudaStreamWaitEvent(g->crc_stream, s.inflated, 0));
+        CK(cudaMemsetAsync(s.d_crc_bad, 0, sizeof(uint32_t), g->crc_stream));
+        gz_launch_member_crc(s.d_text + ING_MAXCARRY, (const uint32_t *)(s.d_meta + ING_META_ISZ), (const uint32_t *)(s.d_meta + ING_META_CRC),
+                             (const uint32_t *)(s.d_meta + ING_META_TOFF), (uint32_t)n_db, nullptr, s.d_crc_bad, g->d_xp128, g->crc_stream);
+        CK(cudaEventRecord(s.crc_done, g->crc_stream));
+    }
     tr_record(4, st);
     const double t_launch = ing_now();
     tr_decomp += t_launch - t_dec;
@@ -1358,12 +1388,14 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     if (fasta) {
         ing_fasta_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a, g->d_tickets + 1);
         ing_fasta_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat, res, g->d_tickets + 2);
+        if (crc_async) { CK(cudaStreamWaitEvent(st, s.crc_done, 0)); ing_crc_veto<<<1, 1, 0, st>>>(g->d_state, s.d_crc_bad, res, a.last_chunk); }
         if (ingest_launch_count(g, t, dev, col)) return -1;
     } else {
         ing_fastq_measure<<<n_blocks, ING_THREADS, 0, st>>>(d_text, g->d_state, g->d_block_nl, g->d_line_end, g->d_block_out, a,
                                                              detect ? g->d_rec_off : nullptr, g->d_tickets + 1);
         ing_fastq_copy<<<n_blocks, ING_THREADS, 0, st>>>(d_text, d_text_next, g->d_state, g->d_block_nl, g->d_block_out, g->d_line_end, g->d_flat,
                                                           detect ? g->d_rec_off : nullptr, detect ? 0u : 1u, a.lsh, res, g->d_tickets + 2);
+        if (crc_async) { CK(cudaStreamWaitEvent(st, s.crc_done, 0)); ing_crc_veto<<<1, 1, 0, st>>>(g->d_state, s.d_crc_bad, detect ? nullptr : res, a.last_chunk); }
         if (!detect) {
             if (ingest_launch_count(g, t, dev, col)) return -1;
         } else {
