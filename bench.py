@@ -431,6 +431,40 @@ def run_cli_leg(s2, strain, images, n_files, tmp_root, env_extra=None, threads=N
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_detect_leg(s2, strain, images, n_files, reads_per_file, tmp_root, ext):
+    """strain_detect (the drop-in executable) on FILES of 150-bp reads: config #4's shape, scaled - every 100th k-mer of the
+    strain's first contig is informative, one SE batch line per file.  -> dict with the phase wall and what went where"""
+    import re
+    import shutil
+    tmp = tempfile.mkdtemp(prefix="s2bench_det_", dir=tmp_root)
+    try:
+        synth = _synth()
+        synth.write_fasta(os.path.join(tmp, "strain.fa"), strain, gz=False)
+        c0 = bytes(strain[0]).replace(b"N", b"A")
+        with open(os.path.join(tmp, "inf.txt"), "wb") as f:
+            for i in range(0, len(c0) - 31, 100):
+                f.write(c0[i:i + 31] + b"\n")
+        names = []
+        for i, z in enumerate(images):
+            names.append("m%d.%s" % (i, ext))
+            open(os.path.join(tmp, names[-1]), "wb").write(z)
+        open(os.path.join(tmp, "batch.txt"), "w").write("".join("SE\t%s\n" % names[i % len(names)] for i in range(n_files)))
+        t0 = time.perf_counter()
+        p = s2.run_strain_detect(["-r", "strain.fa", "-a", "inf.txt", "-B", "batch.txt", "-o", "hits.gz"], cwd=tmp, env={"S2_STATS": "1"}, timeout=900)
+        wall = time.perf_counter() - t0
+        err = p.stderr.decode(errors="replace")
+        m = re.search(r"bytes=(\d+) .*files_gpu_ingest=(\d+) files_host_reader=(\d+) detect_phase=([0-9.]+)s", err)
+        out = {"rc": p.returncode, "process_wall_s": wall, "files": n_files, "reads_per_file": reads_per_file,
+               "kmer_hits_gz_bytes": os.path.getsize(os.path.join(tmp, "hits.gz")) if os.path.exists(os.path.join(tmp, "hits.gz")) else None}
+        if m:
+            bases, phase = int(m.group(1)), float(m.group(4))
+            out.update({"bases": bases, "detect_phase_s": phase, "value": bases / 1e9 / max(phase, 1e-9), "unit": "Gbases/s (batch list, wall)",
+                        "files_gpu_ingest": int(m.group(2)), "files_host_reader": int(m.group(3))})
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -694,6 +728,19 @@ def main():
             "gpu_launches": int(r_n),
         }
         del rdev
+        if "cli" in legs and rank == 0 and world == 1:
+            # config #4's shape through the strain_detect executable: 64 files of 100,000 reads (cycled from the 16 distinct ones)
+            try:
+                shm_d = "/dev/shm" if os.path.isdir("/dev/shm") else None
+                det = run_detect_leg(s2, strain, r_bgzf, 64, READS_PER_FILE, shm_d, "fastq.bgz")
+                det_gz = run_detect_leg(s2, strain, r_gz, 64, READS_PER_FILE, shm_d, "fastq.gz") if r_gz else None
+                workloads["config4_detect"] = {
+                    "workload": "config4: strain_detect (pass 1 on the GPU, pairing loop replayed on the host) of 1,250 informative k-mers over 64 files of "
+                                f"{READS_PER_FILE} 150-bp reads, through the drop-in executable on files in /dev/shm",
+                    "value": det.get("value"), "unit": "Gbases/s (wall time of the batch list)", "cli": det, "cli_gz": det_gz,
+                }
+            except Exception as e:
+                workloads["config4_detect"] = {"error": repr(e)}
 
     if "union" in legs and world == 1:
         # config #5's shape: ONE table of 64 strains (320 M keys, 1.28 GB of fingerprints: HBM resident), genome batches

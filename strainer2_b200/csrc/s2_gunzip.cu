@@ -302,18 +302,28 @@ __global__ void gz_crc_finish_kernel(const GzFileDesc *__restrict__ files, uint3
 // x^(8 x 128 x runs behind it) from a table and x^(8 x length of the last run); a mismatch turns the member's
 // "bytes produced" into all ones, which ing_check_chunk's act == isz test turns into a veto of the chunk.
 // ------------------------------------------------------------------------------------------------
-__global__ void gz_xp128_kernel(uint32_t *xp128)                 // xp128[j] = x^(8 * 128 * j) mod P, j = 0 .. 512
+// xp[j] = x^(8 * 128 * j) mod P for j = 0 .. 512, then xp[513 + j] = x^(8 * j) for j = 0 .. 128
+__global__ void gz_xp128_kernel(uint32_t *xp)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j <= 512u) xp128[j] = crc_xpow8(128ull * j);
+    if (j <= 512u) xp[j] = crc_xpow8(128ull * j);
+    else if (j <= 513u + 128u) xp[j] = crc_xpow8(j - 513u);
 }
 
-__global__ void __launch_bounds__(256)
+// A warp takes 4 KB of a member at a time: 32 rows of 128 bytes come in with coalesced aligned loads (the member starts at
+// any byte: two neighbouring words and a funnel shift give the word at the member's own alignment) into a padded
+// shared-memory tile, then lane L runs slicing-by-4 over row L out of shared memory.  (First version: every lane read its
+// own 128-byte run straight from global memory, 4 bytes at a time - 32 sectors per load instruction, eight times the
+// text in L2 traffic: 130 us per 50 MB chunk, which made the inflate stage the slowest of the pipeline's three,
+// profiles/r2n_ingest_crc_modes.txt.)
+#define GZ_MC_WARPS 8
+__global__ void __launch_bounds__(GZ_MC_WARPS * 32)
 gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ isz, const uint32_t *__restrict__ want_crc,
-                     const uint32_t *__restrict__ toff, unsigned *act, uint32_t *bad_flag, const uint32_t *__restrict__ xp128)
+                     const uint32_t *__restrict__ toff, unsigned *act, uint32_t *bad_flag, const uint32_t *__restrict__ xp)
 {
     __shared__ uint32_t table[4][256];
-    __shared__ uint32_t s_acc, s_xl;
+    __shared__ uint32_t tile[GZ_MC_WARPS][32 * 33];
+    __shared__ uint32_t s_acc;
     {
         uint32_t c = threadIdx.x;
         for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
@@ -325,29 +335,47 @@ gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restric
     const uint32_t m = blockIdx.x;
     const uint32_t len = isz[m];
     if (len == 0 || len > 65536u) return;                               // (uniform; the host lists no empty members)
-    const uint32_t n_runs = (len + 127u) / 128u, last_len = len - 128u * (n_runs - 1u);
-    if (threadIdx.x == 0) { s_acc = 0; s_xl = crc_xpow8(last_len); }
+    const uint32_t n_rows = (len + 127u) / 128u, last_len = len - 128u * (n_rows - 1u);
+    const uint32_t x_last = xp[513u + last_len];                        // x^(8 last_len)
+    if (threadIdx.x == 0) s_acc = 0;
     __syncthreads();
     const uint8_t *p = text + toff[m];
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 3u) * 8u;              // the member's misalignment, in bits
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t *tl = tile[wid];
     uint32_t acc = 0;
-    for (uint32_t k = threadIdx.x; k < n_runs; k += 256u) {
-        const uint32_t s0 = 128u * k, s1 = s0 + 128u < len ? s0 + 128u : len;
-        uint32_t c = 0, i = s0;
-        for (; i < s1 && ((uintptr_t)(p + i) & 3u); ++i) c = table[0][(c ^ p[i]) & 0xFFu] ^ (c >> 8);
-        for (; i + 4u <= s1; i += 4u) {
-            c ^= *reinterpret_cast<const uint32_t *>(p + i);
-            c = table[3][c & 0xFFu] ^ table[2][(c >> 8) & 0xFFu] ^ table[1][(c >> 16) & 0xFFu] ^ table[0][c >> 24];
+    for (uint32_t g0 = wid * 32u; g0 < n_rows; g0 += GZ_MC_WARPS * 32u) {             // rows g0 .. g0 + 31 of the member
+        const uint32_t rows = n_rows - g0 < 32u ? n_rows - g0 : 32u;
+        for (uint32_t i = 0; i < rows; ++i) {
+            const uint32_t w = (g0 + i) * 32u + lane;                                   // word of the member (its own alignment)
+            uint32_t w0 = pw[w], w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+            if (lane == 31u && sh) w1 = pw[w + 1u];
+            tl[i * 33u + lane] = sh ? __funnelshift_r(w0, w1, sh) : w0;
         }
-        for (; i < s1; ++i) c = table[0][(c ^ p[i]) & 0xFFu] ^ (c >> 8);
-        if (k + 1u < n_runs) c = crc_mulmod(crc_mulmod(c, xp128[n_runs - 2u - k]), s_xl);      // bytes behind this run: 128 (n_runs - 2 - k) + last_len
-        acc ^= c;
+        __syncwarp();
+        if (lane < rows) {
+            const uint32_t q = g0 + lane;                                               // this lane's row
+            const uint32_t run = q + 1u < n_rows ? 128u : last_len;
+            const uint32_t *row = tl + lane * 33u;
+            uint32_t c = 0, j = 0;
+            for (; 4u * (j + 1u) <= run; ++j) {
+                c ^= row[j];
+                c = table[3][c & 0xFFu] ^ table[2][(c >> 8) & 0xFFu] ^ table[1][(c >> 16) & 0xFFu] ^ table[0][c >> 24];
+            }
+            uint32_t rest = run & 3u, wv = rest ? row[j] : 0u;
+            for (; rest; --rest, wv >>= 8) c = table[0][(c ^ wv) & 0xFFu] ^ (c >> 8);
+            if (q + 1u < n_rows) c = crc_mulmod(crc_mulmod(c, xp[n_rows - 2u - q]), x_last);      // bytes behind this row: 128 (n_rows - 2 - q) + last_len
+            acc ^= c;
+        }
+        __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-    if ((threadIdx.x & 31u) == 0 && acc) atomicXor(&s_acc, acc);
+    if (lane == 0 && acc) atomicXor(&s_acc, acc);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t xlen = crc_mulmod(xp128[n_runs - 1u], s_xl);                          // x^(8 len)
+        const uint32_t xlen = crc_mulmod(xp[n_rows - 1u], x_last);                           // x^(8 len)
         const uint32_t got = s_acc ^ crc_mulmod(0xFFFFFFFFu, xlen) ^ 0xFFFFFFFFu;
         if (got != want_crc[m]) { if (act) act[m] = 0xFFFFFFFFu; if (bad_flag) *bad_flag = 1u; }
     }
@@ -394,10 +422,10 @@ void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, co
     gz_crc_finish_kernel<<<(n_files + 127) / 128, 128, 0, st>>>(files, file0, n_files, fres, crc_acc, act);
 }
 
-void gz_launch_xp128_init(uint32_t *xp128, cudaStream_t st) { gz_xp128_kernel<<<3, 256, 0, st>>>(xp128); }
+void gz_launch_xp128_init(uint32_t *xp128, cudaStream_t st) { gz_xp128_kernel<<<3, 256, 0, st>>>(xp128); }        // 513 + 129 words
 
 void gz_launch_member_crc(const uint8_t *text, const uint32_t *isz, const uint32_t *want_crc, const uint32_t *toff, uint32_t n_members, unsigned *act,
                           uint32_t *bad_flag, const uint32_t *xp128, cudaStream_t st)
 {
-    if (n_members) gz_member_crc_kernel<<<n_members, 256, 0, st>>>(text, isz, want_crc, toff, act, bad_flag, xp128);
+    if (n_members) gz_member_crc_kernel<<<n_members, GZ_MC_WARPS * 32, 0, st>>>(text, isz, want_crc, toff, act, bad_flag, xp128);
 }
