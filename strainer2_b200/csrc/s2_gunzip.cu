@@ -347,11 +347,17 @@ gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restric
     uint32_t acc = 0;
     for (uint32_t g0 = wid * 32u; g0 < n_rows; g0 += GZ_MC_WARPS * 32u) {             // rows g0 .. g0 + 31 of the member
         const uint32_t rows = n_rows - g0 < 32u ? n_rows - g0 : 32u;
-        for (uint32_t i = 0; i < rows; ++i) {
-            const uint32_t w = (g0 + i) * 32u + lane;                                   // word of the member (its own alignment)
-            uint32_t w0 = pw[w], w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
-            if (lane == 31u && sh) w1 = pw[w + 1u];
-            tl[i * 33u + lane] = sh ? __funnelshift_r(w0, w1, sh) : w0;
+        // all the rows' words first (33 independent coalesced loads in flight per lane: a loop that loads, shifts and stores
+        // row by row waits for memory 32 times), then the shift to the member's alignment: the word behind lane 31's is
+        // lane 0's of the next row
+        uint32_t wv[33];
+#pragma unroll
+        for (uint32_t i = 0; i < 33u; ++i) wv[i] = i <= rows ? pw[(g0 + i) * 32u + lane] : 0u;
+#pragma unroll
+        for (uint32_t i = 0; i < 32u; ++i) {
+            const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, wv[i], 1), wrap = __shfl_sync(0xFFFFFFFFu, wv[i + 1u], 0);
+            const uint32_t w1 = lane == 31u ? wrap : nxt;
+            if (i < rows) tl[i * 33u + lane] = sh ? __funnelshift_r(wv[i], w1, sh) : wv[i];
         }
         __syncwarp();
         if (lane < rows) {

@@ -775,7 +775,7 @@ struct s2_ingest {
     uint64_t res_seq = 0;                // verdicts handed out so far; slot = res_seq % ING_MAX_RESULTS
     decompress_fn decompress = nullptr;
     bool hw_deflate = false;
-    int bgzf_crc = 2;                    // S2_BGZF_CRC: 0 trust the members' ISIZE alone (round 1), 1 check on the inflate stream, 2 (default) on a stream of its own, beside the chunk's other kernels
+    int bgzf_crc = 1;                    // S2_BGZF_CRC: 0 trust the members' ISIZE alone (round 1), 1 (default) check on the kernel stream, in front of the chunk's other kernels, 2 on a stream of its own
     uint32_t *d_xp128 = nullptr;         // x^(8 * 128 * j) mod P for the member CRC kernel
     int grid_scan = 0;                   // CTAs of the count scan launched from this pipeline
     GzStage gz;                          // ordinary .gz batches (allocated on first use)
@@ -860,7 +860,7 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     CK(cudaMalloc((void **)&g->d_line_end, (size_t)g->max_lines * sizeof(unsigned)));
     CK(cudaMalloc((void **)&g->d_state, sizeof(IngState)));
     CK(cudaMemset(g->d_state, 0, sizeof(IngState)));                   // afterwards every finished file leaves a clean state behind
-    g->bgzf_crc = s2_env_int("S2_BGZF_CRC", 2);
+    g->bgzf_crc = s2_env_int("S2_BGZF_CRC", 1);
     CK(cudaStreamCreateWithFlags(&g->crc_stream, cudaStreamNonBlocking));
     CK(cudaMalloc((void **)&g->d_xp128, (513 + 129 + 126) * sizeof(uint32_t)));      // (3 x 256 threads fill it)
     gz_launch_xp128_init(g->d_xp128, g->inflate_stream);
@@ -1332,10 +1332,7 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
             const CUresult r = g->decompress(s.params.data() + i, n, 0, &err_index, (CUstream)g->inflate_stream);
             if (r != CUDA_SUCCESS) { s2_set_error("hardware decompression failed (driver error %d at block %zu)", (int)r, i + err_index); return -1; }
         }
-        // the engine checks no CRC: every member's text against its trailer, before the chunk's verdict is formed
-        if (member_crc && g->bgzf_crc == 1)
-            gz_launch_member_crc(s.d_text + ING_MAXCARRY, (const uint32_t *)(s.d_meta + ING_META_ISZ), (const uint32_t *)(s.d_meta + ING_META_CRC),
-                                 (const uint32_t *)(s.d_meta + ING_META_TOFF), (uint32_t)n_db, s.d_act, nullptr, g->d_xp128, g->inflate_stream);
+
     } else if (ch.gz) {
         // the batch was decoded and chained on this stream already: symbols -> text of this chunk's files, then their CRC-32
         GzStage &z = g->gz;
@@ -1352,9 +1349,15 @@ static int ingest_enqueue(s2_ingest *g, s2_table *t, IngSlot &s, const IngChunk 
     tr_record(3, g->inflate_stream);
     CK(cudaEventRecord(s.inflated, g->inflate_stream));
     CK(cudaStreamWaitEvent(st, s.inflated, 0));
-    // The members' CRC-32 beside the chunk's index / measure / copy kernels, on a stream of its own: only the SCAN waits for
-    // it (ing_crc_veto below).  On the inflate stream the pass made that stage - one of three equally loaded ones - the
-    // slowest: 132 -> 110 Gbases/s end to end (profiles/r2m_bench_n1.json).
+    // The engine checks no CRC: every member's text against its trailer, before the chunk's verdict is formed.  WHERE the
+    // kernel runs matters more than how fast it is (profiles/r2n_ingest_crc_modes.txt, r2o): the scan kernel of the chunk
+    // before is a persistent grid that holds every register of every SM for 250 us, so a kernel on another stream - the
+    // inflate stream, or one of its own - waits for it; that wait, not the 20 us of CRC work, made the inflate stage the
+    // slowest of the three (132 -> 100-112 Gbases/s end to end).  On the kernel stream it queues behind that scan anyway
+    // and costs its own duration only.  (S2_BGZF_CRC=2 keeps the separate-stream form with its veto kernel.)
+    if (member_crc && g->bgzf_crc == 1)
+        gz_launch_member_crc(s.d_text + ING_MAXCARRY, (const uint32_t *)(s.d_meta + ING_META_ISZ), (const uint32_t *)(s.d_meta + ING_META_CRC),
+                             (const uint32_t *)(s.d_meta + ING_META_TOFF), (uint32_t)n_db, s.d_act, nullptr, g->d_xp128, st);
     const bool crc_async = member_crc && g->bgzf_crc >= 2;
     if (crc_async) {
         CK(cudaStreamWaitEvent(g->crc_stream, s.inflated, 0));
