@@ -302,87 +302,83 @@ __global__ void gz_crc_finish_kernel(const GzFileDesc *__restrict__ files, uint3
 // x^(8 x 128 x runs behind it) from a table and x^(8 x length of the last run); a mismatch turns the member's
 // "bytes produced" into all ones, which ing_check_chunk's act == isz test turns into a veto of the chunk.
 // ------------------------------------------------------------------------------------------------
-// xp[j] = x^(8 * 128 * j) mod P for j = 0 .. 512, then xp[513 + j] = x^(8 * j) for j = 0 .. 128
+// Constants of the member CRC kernel, filled once per pipeline (2,048 words):
+//   xp[j]          j = 0 .. 512   x^(8 * 128 * j)     a distance of j rows of 128 bytes
+//   xp[513 + j]    j = 0 .. 128   x^(8 * j)
+//   xp[768 + j]    j = 0 .. 64    x^(32 * j)          a distance of j words
+//   xp[1024 + 256 t + b]          (byte b in place t of a register) * x^1024: multiplication by x^1024 as four lookups
 __global__ void gz_xp128_kernel(uint32_t *xp)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j <= 512u) xp[j] = crc_xpow8(128ull * j);
     else if (j <= 513u + 128u) xp[j] = crc_xpow8(j - 513u);
+    else if (j >= 768u && j <= 768u + 64u) xp[j] = crc_xpow8(4ull * (j - 768u));
+    else if (j >= 1024u && j < 2048u) xp[j] = crc_mulmod(((j - 1024u) & 255u) << (8u * ((j - 1024u) >> 8)), crc_xpow8(128));
 }
 
-// A warp takes 4 KB of a member at a time: 32 rows of 128 bytes come in with coalesced aligned loads (the member starts at
-// any byte: two neighbouring words and a funnel shift give the word at the member's own alignment) into a padded
-// shared-memory tile, then lane L runs slicing-by-4 over row L out of shared memory.  (First version: every lane read its
-// own 128-byte run straight from global memory, 4 bytes at a time - 32 sectors per load instruction, eight times the
-// text in L2 traffic: 130 us per 50 MB chunk, which made the inflate stage the slowest of the pipeline's three,
-// profiles/r2n_ingest_crc_modes.txt.)
+// One CTA per member.  The member's words (at its own alignment: two aligned loads and a funnel shift) are taken COLUMN-wise:
+// lane k of a warp runs Horner's rule over words k, k + 32, k + 64 ... of the warp's rows - Y = Y * x^1024 + W, the
+// multiplication being four table lookups - so every load is coalesced, nothing is staged and there is one modular
+// multiplication per lane at the end (to move the column to its place) instead of two per 128 bytes.  (Earlier forms,
+// profiles/r2n_ingest_crc_modes.txt, r2q: per-lane 128-byte runs straight from global memory, then through padded
+// shared-memory tiles - 16 us per member whatever the access pattern: 0.5 warp instructions per byte, a serial chain per
+// row, two multiplications per row.  14 % of the end-to-end rate.)
 #define GZ_MC_WARPS 8
 __global__ void __launch_bounds__(GZ_MC_WARPS * 32)
 gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ isz, const uint32_t *__restrict__ want_crc,
                      const uint32_t *__restrict__ toff, unsigned *act, uint32_t *bad_flag, const uint32_t *__restrict__ xp)
 {
-    __shared__ uint32_t table[4][256];
-    __shared__ uint32_t tile[GZ_MC_WARPS][32 * 33];
+    __shared__ uint32_t V[4][256];
     __shared__ uint32_t s_acc;
-    {
-        uint32_t c = threadIdx.x;
-        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
-        table[0][threadIdx.x] = c;
-        __syncthreads();
-        uint32_t v = c;
-        for (int t = 1; t < 4; ++t) { v = (v >> 8) ^ table[0][v & 0xFFu]; table[t][threadIdx.x] = v; }
-    }
+    for (uint32_t i = threadIdx.x; i < 1024u; i += GZ_MC_WARPS * 32) (&V[0][0])[i] = xp[1024u + i];
+    if (threadIdx.x == 0) s_acc = 0;
+    __syncthreads();
     const uint32_t m = blockIdx.x;
     const uint32_t len = isz[m];
     if (len == 0 || len > 65536u) return;                               // (uniform; the host lists no empty members)
-    const uint32_t n_rows = (len + 127u) / 128u, last_len = len - 128u * (n_rows - 1u);
-    const uint32_t x_last = xp[513u + last_len];                        // x^(8 last_len)
-    if (threadIdx.x == 0) s_acc = 0;
-    __syncthreads();
     const uint8_t *p = text + toff[m];
     const uint32_t sh = (uint32_t)((uintptr_t)p & 3u) * 8u;              // the member's misalignment, in bits
     const uint32_t *pw = reinterpret_cast<const uint32_t *>((uintptr_t)p & ~(uintptr_t)3);
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    uint32_t *tl = tile[wid];
+    const uint32_t nw = len >> 2, n_rows = nw >> 5, rw = nw & 31u;       // whole words, whole rows of 32 words, words of the last partial row
+    const uint32_t rpw = (n_rows + GZ_MC_WARPS - 1u) / GZ_MC_WARPS;
+    const uint32_t r0 = wid * rpw < n_rows ? wid * rpw : n_rows, r1 = r0 + rpw < n_rows ? r0 + rpw : n_rows;
     uint32_t acc = 0;
-    for (uint32_t g0 = wid * 32u; g0 < n_rows; g0 += GZ_MC_WARPS * 32u) {             // rows g0 .. g0 + 31 of the member
-        const uint32_t rows = n_rows - g0 < 32u ? n_rows - g0 : 32u;
-        // all the rows' words first (33 independent coalesced loads in flight per lane: a loop that loads, shifts and stores
-        // row by row waits for memory 32 times), then the shift to the member's alignment: the word behind lane 31's is
-        // lane 0's of the next row
-        uint32_t wv[33];
-#pragma unroll
-        for (uint32_t i = 0; i < 33u; ++i) wv[i] = i <= rows ? pw[(g0 + i) * 32u + lane] : 0u;
-#pragma unroll
-        for (uint32_t i = 0; i < 32u; ++i) {
-            const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, wv[i], 1), wrap = __shfl_sync(0xFFFFFFFFu, wv[i + 1u], 0);
-            const uint32_t w1 = lane == 31u ? wrap : nxt;
-            if (i < rows) tl[i * 33u + lane] = sh ? __funnelshift_r(wv[i], w1, sh) : wv[i];
+    if (r0 < r1) {
+        uint32_t y = 0;
+#pragma unroll 4
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint32_t j = r * 32u + lane;
+            const uint32_t w = sh ? __funnelshift_r(pw[j], pw[j + 1u], sh) : pw[j];
+            y = V[0][y & 0xFFu] ^ V[1][(y >> 8) & 0xFFu] ^ V[2][(y >> 16) & 0xFFu] ^ V[3][y >> 24] ^ w;
         }
-        __syncwarp();
-        if (lane < rows) {
-            const uint32_t q = g0 + lane;                                               // this lane's row
-            const uint32_t run = q + 1u < n_rows ? 128u : last_len;
-            const uint32_t *row = tl + lane * 33u;
-            uint32_t c = 0, j = 0;
-            for (; 4u * (j + 1u) <= run; ++j) {
-                c ^= row[j];
-                c = table[3][c & 0xFFu] ^ table[2][(c >> 8) & 0xFFu] ^ table[1][(c >> 16) & 0xFFu] ^ table[0][c >> 24];
-            }
-            uint32_t rest = run & 3u, wv = rest ? row[j] : 0u;
-            for (; rest; --rest, wv >>= 8) c = table[0][(c ^ wv) & 0xFFu] ^ (c >> 8);
-            if (q + 1u < n_rows) c = crc_mulmod(crc_mulmod(c, xp[n_rows - 2u - q]), x_last);      // bytes behind this row: 128 (n_rows - 2 - q) + last_len
-            acc ^= c;
-        }
-        __syncwarp();
+        // the column's last word is word 32 (r1 - 1) + lane of nw: (rw + 32 - lane) words from the end of the words, plus the rows of the warps behind
+        acc = crc_mulmod(y, xp[768u + rw + 32u - lane]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (r0 < r1 && r1 < n_rows) acc = crc_mulmod(acc, xp[n_rows - r1]);                        // (every lane: no divergence, lane 0's is used)
+    if (wid == GZ_MC_WARPS - 1 && rw) {                                                        // the last, partial row
+        uint32_t c = 0;
+        if (lane < rw) {
+            const uint32_t j = n_rows * 32u + lane;
+            const uint32_t w = sh ? __funnelshift_r(pw[j], pw[j + 1u], sh) : pw[j];
+            c = crc_mulmod(w, xp[768u + rw - lane]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        acc ^= c;
+    }
     if (lane == 0 && acc) atomicXor(&s_acc, acc);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t xlen = crc_mulmod(xp[n_rows - 1u], x_last);                           // x^(8 len)
-        const uint32_t got = s_acc ^ crc_mulmod(0xFFFFFFFFu, xlen) ^ 0xFFFFFFFFu;
+        uint32_t c = s_acc;                                                                    // the state behind the last whole word
+        for (uint32_t i = nw * 4u; i < len; ++i) {                                             // up to three bytes
+            c ^= p[i];
+            for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+        }
+        const uint32_t xlen = crc_mulmod(xp[len >> 7], xp[513u + (len & 127u)]);               // x^(8 len)
+        const uint32_t got = c ^ crc_mulmod(0xFFFFFFFFu, xlen) ^ 0xFFFFFFFFu;
         if (got != want_crc[m]) { if (act) act[m] = 0xFFFFFFFFu; if (bad_flag) *bad_flag = 1u; }
     }
 }
@@ -428,7 +424,7 @@ void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, co
     gz_crc_finish_kernel<<<(n_files + 127) / 128, 128, 0, st>>>(files, file0, n_files, fres, crc_acc, act);
 }
 
-void gz_launch_xp128_init(uint32_t *xp128, cudaStream_t st) { gz_xp128_kernel<<<3, 256, 0, st>>>(xp128); }        // 513 + 129 words
+void gz_launch_xp128_init(uint32_t *xp128, cudaStream_t st) { gz_xp128_kernel<<<8, 256, 0, st>>>(xp128); }        // 2,048 words
 
 void gz_launch_member_crc(const uint8_t *text, const uint32_t *isz, const uint32_t *want_crc, const uint32_t *toff, uint32_t n_members, unsigned *act,
                           uint32_t *bad_flag, const uint32_t *xp128, cudaStream_t st)

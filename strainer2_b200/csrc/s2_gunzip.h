@@ -47,7 +47,7 @@ void gz_launch_crc(const GzFileDesc *files, uint32_t file0, uint32_t n_files, co
                    GzFileResult *fres, uint32_t *crc_acc, unsigned *act, cudaStream_t st);
 
 // CRC-32 of the members of a BGZF chunk against their trailers (isz / want_crc / toff: per member - inflated size, the trailer's CRC-32,
-// where its text starts; xp128: 768 words, of which gz_launch_xp128_init fills 642, once).  A mismatch sets act[m] to all ones (act != NULL) and / or
+// where its text starts; xp128: 2,048 words of constants, filled once by gz_launch_xp128_init).  A mismatch sets act[m] to all ones (act != NULL) and / or
 // *bad_flag to 1 (bad_flag != NULL).
 void gz_launch_xp128_init(uint32_t *xp128, cudaStream_t st);
 void gz_launch_member_crc(const uint8_t *text, const uint32_t *isz, const uint32_t *want_crc, const uint32_t *toff, uint32_t n_members, unsigned *act,

@@ -862,7 +862,7 @@ static int ingest_init(s2_ingest *g, s2_ctx *c)
     CK(cudaMemset(g->d_state, 0, sizeof(IngState)));                   // afterwards every finished file leaves a clean state behind
     g->bgzf_crc = s2_env_int("S2_BGZF_CRC", 1);
     CK(cudaStreamCreateWithFlags(&g->crc_stream, cudaStreamNonBlocking));
-    CK(cudaMalloc((void **)&g->d_xp128, (513 + 129 + 126) * sizeof(uint32_t)));      // (3 x 256 threads fill it)
+    CK(cudaMalloc((void **)&g->d_xp128, 2048 * sizeof(uint32_t)));                   // constants of the member CRC kernel (s2_gunzip.cu)
     gz_launch_xp128_init(g->d_xp128, g->inflate_stream);
     CK(cudaMalloc((void **)&g->d_tickets, 4 * sizeof(unsigned)));
     CK(cudaMemset(g->d_tickets, 0, 4 * sizeof(unsigned)));
