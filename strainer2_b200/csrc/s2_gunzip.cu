@@ -346,11 +346,22 @@ gz_member_crc_kernel(const uint8_t *__restrict__ text, const uint32_t *__restric
     uint32_t acc = 0;
     if (r0 < r1) {
         uint32_t y = 0;
-#pragma unroll 4
-        for (uint32_t r = r0; r < r1; ++r) {
-            const uint32_t j = r * 32u + lane;
-            const uint32_t w = sh ? __funnelshift_r(pw[j], pw[j + 1u], sh) : pw[j];
-            y = V[0][y & 0xFFu] ^ V[1][(y >> 8) & 0xFFu] ^ V[2][(y >> 16) & 0xFFu] ^ V[3][y >> 24] ^ w;
+        for (uint32_t r = r0; r < r1; r += 8u) {
+            // eight rows' words first - sixteen independent loads in flight when the member is misaligned - then the eight
+            // Horner steps (left to itself the compiler issues each load one step ahead of its use: 64 memory latencies per warp)
+            uint32_t wa[8], wb[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; ++u) {
+                const uint32_t j = (r + u) * 32u + lane;
+                wa[u] = r + u < r1 ? pw[j] : 0u;
+                wb[u] = sh && r + u < r1 ? pw[j + 1u] : 0u;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; ++u)
+                if (r + u < r1) {
+                    const uint32_t w = sh ? __funnelshift_r(wa[u], wb[u], sh) : wa[u];
+                    y = V[0][y & 0xFFu] ^ V[1][(y >> 8) & 0xFFu] ^ V[2][(y >> 16) & 0xFFu] ^ V[3][y >> 24] ^ w;
+                }
         }
         // the column's last word is word 32 (r1 - 1) + lane of nw: (rw + 32 - lane) words from the end of the words, plus the rows of the warps behind
         acc = crc_mulmod(y, xp[768u + rw + 32u - lane]);
