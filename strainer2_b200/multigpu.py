@@ -35,6 +35,12 @@ def allreduce_counts_(vec, dist=None):
         import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        # NCCL runs on torch's own stream and only torch's CURRENT stream waits for it; the library's gather / scatter
+        # kernels run on the context's streams, which know nothing of either: wait here, on the host, before the
+        # caller scatters the sums (without this the scatter raced the collective - bench.py's allreduce_sum_check
+        # caught it at N = 2, profiles/r2u_bench_n2.json)
+        if vec.is_cuda:
+            torch.cuda.current_stream(vec.device).synchronize()
     return vec
 
 
