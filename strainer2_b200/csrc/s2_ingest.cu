@@ -2195,7 +2195,8 @@ static void det_buf_give(void *p)
 extern "C" int s2_ingest_detect_file(s2_ctx *c, s2_table *t, const char *path, s2_ingest_detect_result *out)
 {
     memset(out, 0, sizeof *out);
-    if (t->partitioned) return 1;
+    // (a table too large for L2 - a -r genome beyond 16 Mb - is probed by the direct detect kernel: there is no two-phase
+    // form of the detect scan, so the probes are DRAM bound there, which still leaves the host parser far behind)
     const bool trace = s2_env_int("S2_INGEST_TRACE", 0) != 0;
     const double t_begin = ing_now();
     s2_ingest *g = ingest_acquire(c);

@@ -1117,7 +1117,8 @@ def test_strain_detect_gpu_ingest_of_fasta_reads_and_ordinary_gz(s2, tmp_path, s
     assert o.returncode == 0, o.stderr
     assert o.stdout.count(b"\n") > 2000
     small = {"S2_GZ_BATCH_MB": "1", "S2_INGEST_CHUNK_MB": "1", "S2_INGEST_TEXT_MB": "4"} if small_pieces else {}
-    for env in ({"S2_STATS": "1"}, {"S2_THREADS": "1"}, {"S2_GPU_INGEST": "0"}, {"S2_GPU_GUNZIP": "0"}):
+    # (S2_PARTITION_MIN_MB=0: the table counts as "larger than L2" - the GPU ingest then probes it with the direct detect kernel)
+    for env in ({"S2_STATS": "1"}, {"S2_THREADS": "1"}, {"S2_GPU_INGEST": "0"}, {"S2_GPU_GUNZIP": "0"}, {"S2_STATS": "1", "S2_PARTITION_MIN_MB": "0"}):
         env = dict(env, **small)
         out = os.path.join(tmp, "hits.gz")
         p = s2.run_strain_detect(args + ["-o", out], cwd=tmp, env=env)
