@@ -31,8 +31,10 @@
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(GZ_WARPS * 32, MIN_CTAS)
 gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict__ files, const uint32_t *__restrict__ sub_file, uint32_t n_sub,
-                 uint32_t sub_bytes, uint16_t *sym, uint32_t sub_cap, GzSubResult *res, uint64_t search_limit_bits)
+                 uint32_t sub_bytes, uint16_t *sym, uint32_t sub_cap, uint32_t sub_syms, GzSubResult *res, uint64_t search_limit_bits)
 {
+    // sub_cap: slots per sub-chunk region; its last 32,768 hold the NEXT region's marker prefix (gz_launch_sym_init), the one
+    // before them is the decoder's guard slot: sub_syms = sub_cap - 32,769 symbols may be produced
     __shared__ GzTables tables[GZ_WARPS];
     __shared__ uint8_t kraft9[512];
     gz_kraft9_fill(kraft9, threadIdx.x, GZ_WARPS * 32);
@@ -44,7 +46,7 @@ gz_decode_kernel(const uint8_t *__restrict__ comp, const GzFileDesc *__restrict_
     const uint32_t j = sub - f.sub0;                                            // sub-chunk j of its file
     const uint64_t n_words = (f.comp_len + 3) / 4;
     gz_subchunk(reinterpret_cast<const uint32_t *>(comp + f.comp_off), n_words, j == 0 ? f.first_bit : ~0ull, (uint64_t)j * sub_bytes * 8ull,
-                (uint64_t)(j + 1) * sub_bytes * 8ull, search_limit_bits, sym + (uint64_t)sub * sub_cap, sub_cap, tables[warp], kraft9, res + sub, (int)lane, 32);
+                (uint64_t)(j + 1) * sub_bytes * 8ull, search_limit_bits, sym + (uint64_t)sub * sub_cap, sub_syms, tables[warp], kraft9, res + sub, (int)lane, 32);
 }
 
 // one CTA per file.  Phase 0, in parallel over the file's sub-chunks: the chain test (sub-chunk j must start where j-1
@@ -405,9 +407,9 @@ void gz_launch_decode(const uint8_t *comp, const GzFileDesc *files, const uint32
     if (!n_sub) return;
     static const int ctas = getenv("S2_GZ_DECODE_CTAS") ? atoi(getenv("S2_GZ_DECODE_CTAS")) : 8;      // (experiments; 8 is the measured best)
     const dim3 grid((n_sub + GZ_WARPS - 1) / GZ_WARPS);
-    if (ctas <= 5) gz_decode_kernel<5><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
-    else if (ctas == 6) gz_decode_kernel<6><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
-    else gz_decode_kernel<8><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, res, 8ull << 20);
+    if (ctas <= 5) gz_decode_kernel<5><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, 8ull << 20);
+    else if (ctas == 6) gz_decode_kernel<6><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, 8ull << 20);
+    else gz_decode_kernel<8><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, 8ull << 20);
 }
 
 void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint16_t *sym, uint32_t sub_cap, const GzSubResult *res,
@@ -419,6 +421,18 @@ void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_fi
 }
 
 size_t gz_sub_result_bytes(void) { return sizeof(GzSubResult); }
+
+// The symbol area of n_sub regions of sub_cap slots: 32,768 more in front, and in front of EVERY region (= the tail of its
+// predecessor, which the decoder leaves alone) the markers of the unknown window, written once here.
+size_t gz_sym_slots(size_t n_sub, uint32_t sub_cap) { return n_sub * sub_cap + GZ_WINDOW; }
+
+__global__ void gz_marker_kernel(uint16_t *alloc, uint32_t sub_cap) { gz_marker_prefix(alloc + (uint64_t)blockIdx.x * sub_cap, threadIdx.x, blockDim.x); }
+
+uint16_t *gz_launch_sym_init(uint16_t *alloc, size_t n_sub, uint32_t sub_cap, cudaStream_t st)
+{
+    if (n_sub) gz_marker_kernel<<<(unsigned)n_sub, 256, 0, st>>>(alloc, sub_cap);
+    return alloc + GZ_WINDOW;
+}
 
 void gz_launch_translate(const GzFileDesc *files, const uint32_t *sub_file, uint32_t sub_lo, uint32_t sub_hi, const uint16_t *sym, uint32_t sub_cap,
                          const uint8_t *win, const uint64_t *sub_off, const GzFileResult *fres, uint8_t *text, cudaStream_t st)

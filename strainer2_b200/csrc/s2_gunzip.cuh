@@ -28,8 +28,10 @@
 #else
 #define GZ_HD
 #endif
+#define GZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #if defined(__CUDA_ARCH__)
 #define GZ_SYNC() __syncwarp()
+#define GZ_FENCE() asm volatile("" ::: "memory")
 #define GZ_UNROLL _Pragma("unroll")
 #define GZ_NOUNROLL _Pragma("unroll 1")
 // The symbol loop addresses its tables and buffers through values the compiler must keep in registers: left to itself it
@@ -39,15 +41,15 @@
 // derivation.  Once per block: four instructions.)
 #define GZ_KEEP64(p) do { unsigned long long v_ = (unsigned long long)(p); asm volatile("{ .reg .b64 t; mov.b64 t, %0; st.volatile.shared.b64 [%1], t; ld.volatile.shared.b64 %0, [%1]; }" : "+l"(v_) : "r"(gz_keep_slot) : "memory"); (p) = reinterpret_cast<decltype(p)>(v_); } while (0)
 typedef uint32_t gz_tab_t;                                                  // shared-memory address of a table
-__device__ __forceinline__ gz_tab_t gz_tab(const uint32_t *t, uint32_t slot)
+__device__ __forceinline__ gz_tab_t gz_tab(const uint32_t *t, uint32_t)
 {
-    uint32_t a = (uint32_t)__cvta_generic_to_shared(t);
-    asm volatile("st.volatile.shared.b32 [%1], %0; ld.volatile.shared.b32 %0, [%1];" : "+r"(a) : "r"(slot) : "memory");
-    return a;
+    // the same for every lane, and said so: the address then lives in a uniform register and is the offset of the LDS
+    return __shfl_sync(0xFFFFFFFFu, (uint32_t)__cvta_generic_to_shared(t), 0);
 }
 __device__ __forceinline__ uint32_t gz_tab_at(gz_tab_t t, uint32_t i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(t + (i << 2))); return v; }
 #else
 #define GZ_SYNC() do { } while (0)
+#define GZ_FENCE() do { } while (0)
 #define GZ_UNROLL
 #define GZ_NOUNROLL
 #define GZ_KEEP64(p) do { } while (0)
@@ -131,6 +133,48 @@ GZ_HD inline uint32_t gz_take(GzBits &b, uint32_t k)          // k <= 32 bits
     const uint32_t v = gz_peek(b) & (k >= 32u ? 0xFFFFFFFFu : ((1u << k) - 1u));
     gz_skip(b, k);
     return v;
+}
+
+// back to pos < 32 after a symbol's bits were added to pos: one step for pos < 64, two for pos < 96
+GZ_HD inline void gz_norm1(GzBits &b)
+{
+    if (b.pos >= 32u) { b.pos -= 32u; b.lo = b.hi; b.hi = b.nxt; ++b.wi; b.nxt = gz_word(b, b.wi + 2u); }
+}
+GZ_HD inline void gz_norm2(GzBits &b)
+{
+    if (b.pos >= 32u) {
+        b.pos -= 32u; b.lo = b.hi; b.hi = b.nxt; ++b.wi; b.nxt = gz_word(b, b.wi + 2u);
+        if (b.pos >= 32u) { b.pos -= 32u; b.lo = b.hi; b.hi = b.nxt; ++b.wi; b.nxt = gz_word(b, b.wi + 2u); }
+    }
+}
+// 32 bits of the stream from bit q of the words in registers, q < 64
+GZ_HD inline uint32_t gz_peek_at(const GzBits &b, uint32_t q)
+{
+    const bool second = q >= 32u;
+    const uint32_t a = second ? b.hi : b.lo, c = second ? b.nxt : b.hi;
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(a, c, q);                                     // (shift amount modulo 32)
+#else
+    const uint32_t s = q & 31u;
+    return s ? (a >> s) | (c << (32u - s)) : a;
+#endif
+}
+// n bits (n < 32) of v from bit `from` (from < 32): a shift and one zero-extension (SGXT; PTX bfe clamps its byte-sized
+// operands first - five instructions)
+GZ_HD inline uint32_t gz_bfe(uint32_t v, uint32_t from, uint32_t n)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("szext.clamp.u32 %0, %1, %2;" : "=r"(r) : "r"(v >> from), "r"(n));
+    return r;
+#else
+    return (v >> from) & ((1u << n) - 1u);
+#endif
+}
+// the markers in front of a symbol region: prefix[j] for j in [0, 32768) = 256 + j = "byte j of the unknown window"
+GZ_HD inline void gz_marker_prefix(uint16_t *prefix, uint32_t tid, uint32_t n_threads)
+{
+    for (uint32_t j = tid; j < 32768u; j += n_threads) prefix[j] = (uint16_t)(256u + j);
 }
 
 GZ_HD inline uint32_t gz_bitrev(uint32_t v, int n)
@@ -351,7 +395,9 @@ GZ_HD inline int gz_fixed_header(GzTables &t, int lane, int nl)
 // ------------------------------------------------------------------------------------------------
 // decode from a block start to the first block boundary at or after stop_bit (or the end of the stream)
 // ------------------------------------------------------------------------------------------------
-// out[0..cap): 16-bit symbols; window: how many bytes before out[0] a match may reach (32768 for a sub-chunk in the
+// out[-32768..cap]: 16-bit symbols - out[0..cap) count, out[cap] is a guard slot (literals and the pending copy store
+// without a test), out[-j] holds the marker of the unknown window's j-th last byte (gz_marker_prefix: a match that reaches
+// back before the sub-chunk copies its markers like any other symbol); window: how many bytes before out[0] a match may reach (32768 for a sub-chunk in the
 // middle of a stream, 0 at the start of a member).  Returns GZ_OK (stopped at a boundary: *end_bit), GZ_FINAL (the last
 // block ended at *end_bit) or an error.  *n_out = symbols written.
 GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_t cap, uint32_t window, uint64_t stop_bit,
@@ -359,8 +405,8 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
 {
     uint32_t o = 0;
     int rc = GZ_OK;
-    uint32_t p_at = ~0u;                                                 // this lane's copied symbol that is still to be stored, and where
-    uint16_t p_val = 0;
+    uint32_t p_at = cap;                                                 // this lane's copied symbol that is still to be stored, and where
+    uint16_t p_val = 0;                                                  // (nothing yet: the guard slot)
 #if defined(__CUDA_ARCH__)
     const uint32_t gz_keep_slot = (uint32_t)__cvta_generic_to_shared(t.scratch + 64);       // 8 bytes of the tables' scratch area (free between table builds)
 #else
@@ -391,81 +437,91 @@ GZ_HD inline int gz_decode_blocks(GzBits &b, GzTables &t, uint16_t *out, uint32_
         } else {
             rc = type == 1 ? gz_fixed_header(t, lane, nl) : gz_dynamic_header(b, t, false, false, lane, nl);
             if (rc) break;
-            // The symbol loop.  One peek holds a literal/length code and its extra bits (15 + 5), a second one the distance
-            // code and its extra bits (15 + 13); everything is 32-bit arithmetic.
+            // The symbol loop.  The three words in registers hold 64 valid bits behind `pos`, a literal/length code with its
+            // extra bits and the distance code with its extra bits are 48 at most: both are read from the words as they
+            // stand (the second peek picks its pair of words), and the reader is brought back to pos < 32 once per symbol.
+            // Everything is 32-bit arithmetic; the conditional load / store of the match copy are predicated instructions,
+            // not branches (a warp's instruction stream is one dependent chain: the kernel is bound by instructions per symbol).
             const gz_tab_t lit = gz_tab(t.lit, gz_keep_slot), dtab = gz_tab(t.dist, gz_keep_slot);
             for (;;) {
+                gz_norm1(b);                                              // the one place where the words move on
                 uint32_t bits = gz_peek(b);
-                uint32_t e = gz_tab_at(lit, bits & ((1u << GZ_LIT_ROOT) - 1u)), used = 0;
-                if (e & GZ_F_SUB) {
-                    used = GZ_LIT_ROOT;
-                    e = gz_tab_at(lit, (e >> 16) + ((bits >> GZ_LIT_ROOT) & ((1u << ((e >> 4) & 15u)) - 1u)));
+                uint32_t e = gz_tab_at(lit, bits & ((1u << GZ_LIT_ROOT) - 1u));
+                uint32_t used = e & 15u;
+                if (GZ_UNLIKELY(e & GZ_F_SUB)) {
+                    // (written as a loop - second-level entries never point on - so that it stays a branch: as predicated
+                    // instructions its eight issue slots would be spent on every symbol)
+                    GZ_NOUNROLL
+                    do e = gz_tab_at(lit, (e >> 16) + gz_bfe(bits, GZ_LIT_ROOT, (e >> 4) & 15u)); while (GZ_UNLIKELY(e & GZ_F_SUB));
+                    used = GZ_LIT_ROOT + (e & 15u);
                 }
-                used += e & 15u;
-                if (e & GZ_F_LIT) {
-                    // every lane stores the same value to the same place (one transaction, no branch around it); a full
-                    // region stops `o` at cap - reported when the block ends or the next match arrives
-                    gz_skip(b, used);
-                    const bool room = o < cap;
-                    if (room) out[o] = (uint16_t)(e >> 16);
-                    o += room ? 1u : 0u;
+                if (e & GZ_F_BASE) {
+                    const uint32_t xl = (e >> 4) & 15u;
+                    const uint32_t len = (e >> 16) + gz_bfe(bits, used, xl);
+                    const uint32_t q = b.pos + used + xl;                 // <= 31 + 15 + 5
+                    bits = gz_peek_at(b, q);
+                    uint32_t d = gz_tab_at(dtab, bits & ((1u << GZ_DIST_ROOT) - 1u));
+                    used = d & 15u;
+                    if (GZ_UNLIKELY(d & GZ_F_SUB)) {
+                        GZ_NOUNROLL
+                        do d = gz_tab_at(dtab, (d >> 16) + gz_bfe(bits, GZ_DIST_ROOT, (d >> 4) & 15u)); while (GZ_UNLIKELY(d & GZ_F_SUB));
+                        used = GZ_DIST_ROOT + (d & 15u);
+                    }
+                    const uint32_t xd = (d >> 4) & 15u;
+                    // a pattern that is no distance code has an entry without a value and without extra bits: distance 0
+                    const uint32_t dist = (d >> 16) + gz_bfe(bits, used, xd);
+                    b.pos = q + used + xd;                                // <= 51 + 15 + 13
+                    if (GZ_UNLIKELY(b.pos >= 64u)) { b.pos -= 32u; b.lo = b.hi; b.hi = b.nxt; ++b.wi; b.nxt = gz_word(b, b.wi + 2u); }
+                    // A copied symbol is loaded now and stored when the NEXT match arrives (or the blocks end): the symbols
+                    // were written past L1, so the load is an L2 round trip, and a store right behind it would hold the warp -
+                    // in-order issue - for all of it.  Nothing reads the place in between: literals only store, and the next
+                    // match stores the pending symbol before it loads.  Lanes behind the end of a match do what its last
+                    // lane does (the same value to the same place); before the first match the pending store goes to the
+                    // guard slot: no lane ever needs a predicate.  A source before out[0] is a place in the marker prefix.
+                    out[p_at] = p_val;
+                    GZ_FENCE();                                          // (the lanes run in step: a barrier would be a test and a no-op)
+                    uint32_t k = len - 1u < (uint32_t)lane ? len - 1u : (uint32_t)lane;
+                    const uint32_t at = o + k;
+                    // ONE branch for everything that is not a plain short match: the three things that can be wrong with it
+                    // (sorted out on the cold side), a match that overlaps itself (a repeating pattern of `dist` symbols) or is
+                    // longer than the warp is wide
+                    if (GZ_UNLIKELY((dist - 1u >= o + window) | (o + len >= cap) | (dist < len) | (len > (uint32_t)nl))) {
+                        if ((dist - 1u >= o + window) | (o + len >= cap)) {
+                            rc = dist == 0u ? GZ_ERR_SYMBOL : dist > o + window ? GZ_ERR_DISTANCE : GZ_ERR_OUTPUT;
+                            p_at = cap;                                   // (nothing pending any more)
+                            break;
+                        }
+                        const bool overlap = dist < len;
+                        GZ_SYNC();
+                        GZ_NOUNROLL
+                        for (uint32_t i = (uint32_t)(lane + nl); i < len; i += (uint32_t)nl)
+                            out[o + i] = out[(int32_t)(o - dist) + (int32_t)(overlap ? i % dist : i)];
+                        if (overlap) k %= dist;
+                    }
+                    p_val = out[(int32_t)(o - dist) + (int32_t)k];        // >= -32768: before out[0] lies the unknown window
+                    p_at = at;
+                    o += len;
                     continue;
                 }
-                if (!(e & GZ_F_BASE)) {
-                    gz_skip(b, used);
-                    if (!(e & GZ_F_EOB)) rc = GZ_ERR_SYMBOL;
-                    else if (o >= cap) rc = GZ_ERR_OUTPUT;              // (a region filled to the last symbol counts as overflowed)
-                    break;
+                b.pos += used;
+                if (e & GZ_F_LIT) {
+                    // every lane stores the same value to the same place (one transaction, no branch around it); a full
+                    // region keeps `o` at cap (the guard slot takes the stores) - reported when the block ends or a match arrives
+                    out[o] = (uint16_t)(e >> 16);
+                    o = o + 1u < cap ? o + 1u : cap;
+                    continue;
                 }
-                const uint32_t xl = (e >> 4) & 15u;
-                const uint32_t len = (e >> 16) + ((bits >> used) & ((1u << xl) - 1u));
-                gz_skip(b, used + xl);
-                bits = gz_peek(b);
-                uint32_t d = gz_tab_at(dtab, bits & ((1u << GZ_DIST_ROOT) - 1u));
-                used = 0;
-                if (d & GZ_F_SUB) {
-                    used = GZ_DIST_ROOT;
-                    d = gz_tab_at(dtab, (d >> 16) + ((bits >> GZ_DIST_ROOT) & ((1u << ((d >> 4) & 15u)) - 1u)));
-                }
-                used += d & 15u;
-                const uint32_t xd = (d >> 4) & 15u;                       // (garbage, but small, when d is no distance code)
-                const uint32_t dist = (d >> 16) + ((bits >> used) & ((1u << xd) - 1u));
-                gz_skip(b, used + xd);
-                // one branch for the three things that can be wrong with a match (which one is sorted out on the cold side)
-                if (!(d & GZ_F_BASE) | (dist > o + window) | (o + len >= cap)) {
-                    rc = !(d & GZ_F_BASE) ? GZ_ERR_SYMBOL : dist > o + window ? GZ_ERR_DISTANCE : GZ_ERR_OUTPUT;
-                    break;
-                }
-                // A copied symbol is loaded now and stored when the NEXT match arrives (or the blocks end): the symbols were
-                // written past L1, so the load is an L2 round trip, and a store right behind it would hold the warp - in-order
-                // issue - for all of it.  Nothing reads the place in between: literals only store, and the next match stores
-                // the pending symbol before it loads.  (First nl symbols of a match; the rest of a long one is copied at once -
-                // it never reads this match's own output: every source index lies before o.)
-                if (p_at != ~0u) { out[p_at] = p_val; p_at = ~0u; }
-                GZ_SYNC();                                               // the lanes' earlier stores, before anybody reads them
-                const int32_t s0 = (int32_t)o - (int32_t)dist;           // >= -32768: before out[0] lies the unknown window
-                uint16_t *dst = out + o;
-                const bool overlap = dist < len;                         // the match overlaps itself: a repeating pattern of `dist` symbols
-                if ((uint32_t)lane < len) {
-                    const int32_t src = s0 + (int32_t)(overlap ? (uint32_t)lane % dist : (uint32_t)lane);
-                    p_val = src >= 0 ? out[src] : (uint16_t)(256 + (int32_t)GZ_WINDOW + src);
-                    p_at = o + (uint32_t)lane;
-                }
-                if (len > (uint32_t)nl) {
-                    GZ_NOUNROLL
-                    for (uint32_t i = (uint32_t)(lane + nl); i < len; i += (uint32_t)nl) {
-                        const int32_t src = s0 + (int32_t)(overlap ? i % dist : i);
-                        dst[i] = src >= 0 ? out[src] : (uint16_t)(256 + (int32_t)GZ_WINDOW + src);
-                    }
-                }
-                o += len;
+                gz_norm1(b);
+                if (!(e & GZ_F_EOB)) rc = GZ_ERR_SYMBOL;
+                else if (o >= cap) rc = GZ_ERR_OUTPUT;                 // (a region filled to the last symbol counts as overflowed)
+                break;
             }
             if (rc) break;
             if (gz_bits_pos(b) > (uint64_t)b.n_words * 32u) { rc = GZ_ERR_INPUT; break; }
         }
         if (last) { rc = GZ_FINAL; break; }
     }
-    if (p_at != ~0u) out[p_at] = p_val;
+    out[p_at] = p_val;
     GZ_SYNC();
     *n_out = o;
     *end_bit = gz_bits_pos(b);

@@ -33,6 +33,11 @@ struct GzFileResult {
 
 size_t gz_tables_bytes(void);
 size_t gz_sub_result_bytes(void);
+// The symbol area: cudaMalloc gz_sym_slots(n_sub, sub_cap) 16-bit slots, then gz_launch_sym_init once - it writes the window
+// markers in front of every region and returns the pointer the other launches take as `sym` (region i = sym + i * sub_cap).
+// sub_cap must exceed 32,769 + what a sub-chunk can produce: the last 32,768 slots of a region are its successor's markers.
+size_t gz_sym_slots(size_t n_sub, uint32_t sub_cap);
+uint16_t *gz_launch_sym_init(uint16_t *alloc, size_t n_sub, uint32_t sub_cap, cudaStream_t st);
 void gz_launch_decode(const uint8_t *comp, const GzFileDesc *files, const uint32_t *sub_file, uint32_t n_sub, uint32_t sub_bytes, uint16_t *sym,
                       uint32_t sub_cap, GzSubResult *res, cudaStream_t st);
 void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint16_t *sym, uint32_t sub_cap, const GzSubResult *res,

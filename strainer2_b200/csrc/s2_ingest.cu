@@ -724,7 +724,7 @@ struct GzStage {
     uint32_t sub_bytes = 0, sub_cap = 0, max_sub = 0, max_files = 0;
     GzBufSet set[2];
     unsigned batch_no = 0;
-    uint16_t *d_sym = nullptr;
+    uint16_t *d_sym = nullptr, *d_sym_alloc = nullptr;                 // (d_sym = what gz_launch_sym_init made of the allocation)
     GzSubResult *d_res = nullptr;
     uint8_t *d_win = nullptr;
     uint8_t *d_carry = nullptr;          // streamed files: the window a piece leaves to the next one
@@ -805,7 +805,7 @@ static void ingest_free(s2_ingest *g)
     }
     {
         GzStage &z = g->gz;
-        cudaFree(z.d_sym); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_carry); cudaFree(z.d_sub_off);
+        cudaFree(z.d_sym_alloc); cudaFree(z.d_res); cudaFree(z.d_win); cudaFree(z.d_carry); cudaFree(z.d_sub_off);
         for (auto &zs : z.set) {
             cudaFreeHost(zs.h_comp); cudaFree(zs.d_comp);
             cudaFreeHost(zs.h_files); cudaFree(zs.d_files); cudaFreeHost(zs.h_sub_file); cudaFree(zs.d_sub_file); cudaFreeHost(zs.h_slice0); cudaFree(zs.d_slice0);
@@ -1457,7 +1457,7 @@ static int ingest_gz_stage_init(s2_ingest *g)
     // run-on to the first block boundary behind the next cut; a sub-chunk that needs more makes its file the host reader's
     // (the run-on is one DEFLATE block: 16 K symbols, which are 30-100 KB of text for real reads and genomes but 300 KB for
     // FASTQ whose quality lines are all alike - every match 258 bytes long; hence the half million symbols of slack)
-    z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64) + (512u << 10);
+    z.sub_cap = z.sub_bytes * (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_RATIO", 8), 2), 64) + (512u << 10) + 32768u;      // (+ the next region's marker prefix)
     z.max_files = ING_MAX_FILES;
     z.max_sub = (uint32_t)(z.comp_cap / z.sub_bytes) + z.max_files;
     for (auto &zs : z.set) {
@@ -1493,8 +1493,9 @@ static int gz_stage_reserve(s2_ingest *g, uint32_t n_sub, uint32_t n_files)
     CK(cudaStreamSynchronize(g->inflate_stream));
     if (n_sub > z.sym_subs) {
         const size_t subs = std::min<size_t>(z.max_sub, (size_t)n_sub + n_sub / 4 + 64);
-        cudaFree(z.d_sym); z.d_sym = nullptr; z.sym_subs = 0;
-        if (cudaMalloc((void **)&z.d_sym, subs * z.sub_cap * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip symbols)"); return -1; }
+        cudaFree(z.d_sym_alloc); z.d_sym = z.d_sym_alloc = nullptr; z.sym_subs = 0;
+        if (cudaMalloc((void **)&z.d_sym_alloc, gz_sym_slots(subs, z.sub_cap) * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); s2_set_error("out of device memory (gunzip symbols)"); return -1; }
+        z.d_sym = gz_launch_sym_init(z.d_sym_alloc, subs, z.sub_cap, g->inflate_stream);
         z.sym_subs = subs;
     }
     if (want_win > z.win_slots) {

@@ -23,15 +23,17 @@ int sim_pgunzip(const unsigned char *src, unsigned long long n, unsigned sub_byt
     std::vector<uint32_t> words(n_words + 4, 0u);
     memcpy(words.data(), src, n);
     const uint64_t n_sub = (n + sub_bytes - 1) / sub_bytes;
-    const uint32_t sub_cap = sub_bytes * cap_ratio + (1u << 19);     // a sub-chunk runs on to the first block boundary behind the next cut
-    std::vector<uint16_t> sym((size_t)n_sub * sub_cap);
+    const uint32_t sub_cap = sub_bytes * cap_ratio + (1u << 19) + GZ_WINDOW;     // a sub-chunk runs on to the first block boundary behind the next cut
+    std::vector<uint16_t> sym_alloc((size_t)n_sub * sub_cap + GZ_WINDOW);             // (the layout of gz_launch_sym_init)
+    for (uint64_t i = 0; i < n_sub; ++i) gz_marker_prefix(sym_alloc.data() + i * sub_cap, 0, 1);
+    uint16_t *const sym = sym_alloc.data() + GZ_WINDOW;
     std::vector<GzSubResult> res(n_sub);
     static GzTables t;
     static uint8_t kraft9[512];
     gz_kraft9_fill(kraft9, 0, 1);
     for (uint64_t i = 0; i < n_sub; ++i)
-        gz_subchunk(words.data(), n_words, i == 0 ? hl * 8 : ~0ull, i * sub_bytes * 8ull, (i + 1) * sub_bytes * 8ull, 8ull << 20, sym.data() + i * sub_cap,
-                    sub_cap, t, kraft9, &res[i], 0, 1);
+        gz_subchunk(words.data(), n_words, i == 0 ? hl * 8 : ~0ull, i * sub_bytes * 8ull, (i + 1) * sub_bytes * 8ull, 8ull << 20, sym + i * sub_cap,
+                    sub_cap - GZ_WINDOW - 1u, t, kraft9, &res[i], 0, 1);
     // chain
     uint64_t cur = hl * 8, total = 0, end_bit = 0;
     bool done = false;
@@ -46,7 +48,7 @@ int sim_pgunzip(const unsigned char *src, unsigned long long n, unsigned sub_byt
         if (res[i].start_bit != cur) return -101;
         if (res[i].status < 0) return res[i].status;
         len[i] = res[i].n_out;
-        gz_next_window(prev, sym.data() + i * sub_cap, len[i], next, 0, 1);
+        gz_next_window(prev, sym + i * sub_cap, len[i], next, 0, 1);
         total += len[i];
         cur = res[i].end_bit;
         if (len[i]) ++stats[1];
@@ -56,7 +58,7 @@ int sim_pgunzip(const unsigned char *src, unsigned long long n, unsigned sub_byt
     }
     if (!done) return -102;
     if (total > cap) return GZ_ERR_OUTPUT;
-    for (uint64_t i = 0; i < n_sub; ++i) gz_translate(win.data() + i * GZ_WINDOW, sym.data() + i * sub_cap, len[i], dst + off[i], 0, 1);
+    for (uint64_t i = 0; i < n_sub; ++i) gz_translate(win.data() + i * GZ_WINDOW, sym + i * sub_cap, len[i], dst + off[i], 0, 1);
     *out_len = total;
     const uint64_t trailer = (end_bit + 7) / 8;
     if (trailer + 8 > n) return -102;

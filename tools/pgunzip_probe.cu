@@ -77,13 +77,13 @@ int main(int argc, char **argv)
         coff += (c.size() + 15) / 16 * 16 + 16; toff += t.size(); sub0 += d.n_sub;
     }
     slice0[n] = slices;
-    const uint32_t sub_cap = sub_bytes * 8 + (512u << 10);
+    const uint32_t sub_cap = sub_bytes * 8 + (512u << 10) + 32768u;
     printf("%d %s files (level %d), %.1f MB of .gz -> %.1f MB of text, %u sub-chunks of %u KB, symbol area %.1f MB, tables %zu bytes per warp\n", n,
            fastq ? "FASTQ" : "FASTA", level, coff / 1e6, toff / 1e6, sub0, sub_bytes >> 10, (double)sub0 * sub_cap * 2 / 1e6, gz_tables_bytes());
     uint8_t *d_comp, *d_text, *d_win; uint16_t *d_sym; GzSubResult *d_res; uint64_t *d_sub_off; GzFileDesc *d_files; uint32_t *d_sub_file, *d_slice0, *d_crc; GzFileResult *d_fres;
     unsigned *d_act;
     CKP(cudaMalloc(&d_comp, coff + 64)); CKP(cudaMemset(d_comp, 0, coff + 64));
-    CKP(cudaMalloc(&d_text, toff + 64)); CKP(cudaMalloc(&d_sym, (size_t)sub0 * sub_cap * 2)); CKP(cudaMalloc(&d_res, (size_t)sub0 * gz_sub_result_bytes()));
+    CKP(cudaMalloc(&d_text, toff + 64)); CKP(cudaMalloc(&d_sym, gz_sym_slots(sub0, sub_cap) * 2)); d_sym = gz_launch_sym_init(d_sym, sub0, sub_cap, 0); CKP(cudaMalloc(&d_res, (size_t)sub0 * gz_sub_result_bytes()));
     CKP(cudaMalloc(&d_win, ((size_t)sub0 + n + 1) * 32768)); CKP(cudaMemset(d_win, 0, ((size_t)sub0 + n + 1) * 32768));
     CKP(cudaMalloc(&d_sub_off, (size_t)sub0 * 8)); CKP(cudaMalloc(&d_files, n * sizeof(GzFileDesc))); CKP(cudaMalloc(&d_sub_file, sub0 * 4));
     CKP(cudaMalloc(&d_slice0, (n + 1) * 4)); CKP(cudaMalloc(&d_crc, n * 4)); CKP(cudaMemset(d_crc, 0, n * 4)); CKP(cudaMalloc(&d_fres, n * sizeof(GzFileResult)));
