@@ -130,7 +130,7 @@ int s2_default_reader_threads()
 // The list drivers GEN_all_kmer_counts / GEN_all_kmer_counts_skip_file (src/genome_compare.c:115-177) for a
 // Size of a reader thread's arena.  Pinning memory costs (profiles/r2g_pinned_probe.txt: 7 GB/s on huge pages), and sixteen
 // threads pin two arenas each while the scan is running: 16 MB is one full pipeline chunk of BGZF.  Ordinary .gz wants
-// larger batches for its decode kernel (one warp per 32 KB of compressed bytes) and runs long enough to pay for them.
+// larger batches for its decode kernel (one warp per 64 KB of compressed bytes) and runs long enough to pay for them.
 static uint64_t g_arena_default_mb = 16;
 
 // does the first file a list names begin like an ordinary (not block-) gzip file?  Nothing is reported here: the list is
@@ -419,7 +419,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     }
     // (an ordinary .gz at the head of a list: the pipelines' gunzip stages are made ready as well - s2_ingest_warm_gz)
     const bool gz_inputs = warm_pipes && (s2_list_starts_with_plain_gz(A_file) || s2_list_starts_with_plain_gz(B_file));
-    if (gz_inputs) g_arena_default_mb = 96;
+    if (gz_inputs) g_arena_default_mb = 192;
     const uint64_t arena_mb = std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", g_arena_default_mb), 1);
     for (int g = 0; g < n_gpus && warm_pipes; ++g)
         warmers.emplace_back([&, g]() { if (gz_inputs) s2_ingest_warm_gz(ctxs[g], warm_pipes, arena_mb << 20); else s2_ingest_warm(ctxs[g], warm_pipes); });
@@ -469,7 +469,7 @@ extern "C" int s2_kmer_scrub_count_main(int argc, char **argv)
     std::string open_error;
     uint64_t total_bases = 0, total_lookups = 0;
     join_all(warmers);
-    // (ordinary .gz: fewer readers with larger arenas - a 96 MB run is 3,000 decoding warps, and eight threads read faster than the GPU decodes)
+    // (ordinary .gz: fewer readers with larger arenas - a 192 MB run is 3,000 decoding warps, and eight threads read faster than the GPU decodes)
     const int scan_threads = gz_inputs ? std::max(n_gpus, std::min(n_threads, 8 * n_gpus)) : n_threads;
     const bool pool_ok = s2_scan_work_items_multi(ctxs, tables, exotic, work, scan_threads, progress, open_error, &total_bases, &total_lookups);
     s2_scan_stats st = {};

@@ -407,9 +407,10 @@ void gz_launch_decode(const uint8_t *comp, const GzFileDesc *files, const uint32
     if (!n_sub) return;
     static const int ctas = getenv("S2_GZ_DECODE_CTAS") ? atoi(getenv("S2_GZ_DECODE_CTAS")) : 8;      // (experiments; 8 is the measured best)
     const dim3 grid((n_sub + GZ_WARPS - 1) / GZ_WARPS);
-    if (ctas <= 5) gz_decode_kernel<5><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, 8ull << 20);
-    else if (ctas == 6) gz_decode_kernel<6><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, 8ull << 20);
-    else gz_decode_kernel<8><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, 8ull << 20);
+    static const uint64_t limit = (8ull << 20) | (getenv("S2_GZ_FIND_ONLY") && atoi(getenv("S2_GZ_FIND_ONLY")) ? 1ull << 63 : 0ull);   // (bit 63: find, do not decode - profiling)
+    if (ctas <= 5) gz_decode_kernel<5><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, limit);
+    else if (ctas == 6) gz_decode_kernel<6><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, limit);
+    else gz_decode_kernel<8><<<grid, GZ_WARPS * 32, 0, st>>>(comp, files, sub_file, n_sub, sub_bytes, sym, sub_cap, sub_cap - GZ_WINDOW - 1u, res, limit);
 }
 
 void gz_launch_chain(const uint8_t *comp, const GzFileDesc *files, uint32_t n_files, const uint16_t *sym, uint32_t sub_cap, const GzSubResult *res,

@@ -261,6 +261,7 @@ GZ_HD inline int gz_build(uint32_t *tab, uint32_t cap, int root, int kind, const
             left = (left << 1) - (int)count[l];
             if (left < 0) rc = GZ_ERR_HEADER;
         }
+        bool any_long = false;
         if (rc == 0)
             for (int s = 0; s < n; ++s) {
                 const int l = lens[s];
@@ -270,11 +271,12 @@ GZ_HD inline int gz_build(uint32_t *tab, uint32_t cap, int root, int kind, const
                 if (l > root) {
                     const uint32_t prefix = code[s] & (rsize - 1u);
                     if (submax[prefix] < l - root) submax[prefix] = (uint8_t)(l - root);
+                    any_long = true;
                 }
             }
-        // second-level tables, in prefix order
+        // second-level tables, in prefix order (none for a code without long words: the code-length code, most distance codes)
         uint32_t at = rsize;
-        for (uint32_t p = 0; p < rsize && rc == 0; ++p)
+        for (uint32_t p = 0; any_long && p < rsize && rc == 0; ++p)
             if (submax[p]) {
                 if (at + (1u << submax[p]) > cap) { rc = GZ_ERR_TABLE; break; }
                 tab[p] = at << 16 | GZ_F_SUB | (uint32_t)submax[p] << 4 | (uint32_t)root;
@@ -571,26 +573,73 @@ GZ_HD inline bool gz_candidate(const GzBits &b, uint64_t p, const uint8_t *kraft
     return sum == 128u;
 }
 
+// Two stages, because the stages' costs differ by an order of magnitude and one position in nine passes the first: every
+// lane tests its own position for the 13 header bits alone (not final, dynamic codes, sane code counts) and the survivors
+// are QUEUED; whenever the queue holds a warp's worth, every lane runs the Kraft test of the code-length code on one of
+// them - all 32 lanes busy, instead of the three or four whose position happened to pass - and what survives that gets the
+// whole header parsed, in position order, so the first hit is the first block start.  The queue (positions relative to
+// from_bit, 2 x nl words) lives in the literal/length table, which nothing else uses before a block is decoded.
 GZ_HD inline int gz_find_block(GzBits &b, GzTables &t, const uint8_t *kraft9, uint64_t from_bit, uint64_t limit_bit, uint64_t *found, int lane, int nl)
 {
-    for (uint64_t base = from_bit; base < limit_bit; base += (uint64_t)nl) {
-        const uint64_t p = base + (uint64_t)lane;
-        const bool cand = p < limit_bit && gz_candidate(b, p, kraft9);
+    uint32_t *queue = t.lit;
+    uint32_t count = 0;
+    // the scan runs on 32-bit offsets from from_bit (the search limit is a few megabytes) over the words from from_bit's own
+    if (limit_bit <= from_bit) return GZ_ERR_NOT_FOUND;
+    const uint32_t *wp = b.w + (from_bit >> 5);
+    const uint32_t nw = b.n_words - (uint32_t)(from_bit >> 5), s0 = (uint32_t)from_bit & 31u;
+    const uint32_t n_off = limit_bit - from_bit > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)(limit_bit - from_bit);
 #if defined(__CUDA_ARCH__)
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, cand);
-#else
-        uint32_t m = cand ? 1u : 0u;
+    const uint32_t lt = (1u << lane) - 1u;
 #endif
-        while (m) {                                                      // survivors in order, the whole warp on each
+    for (uint32_t off = 0;; off += (uint32_t)nl) {
+        const bool more = off < n_off;
+        if (more) {
+            const uint32_t q = s0 + off + (uint32_t)lane;
+            const uint32_t wi = q >> 5;
+            const uint32_t w0 = wi < nw ? wp[wi] : 0u, w1 = wi + 1u < nw ? wp[wi + 1u] : 0u;
 #if defined(__CUDA_ARCH__)
-            const int k = __ffs(m) - 1;
+            const uint32_t h = __funnelshift_r(w0, w1, q);
 #else
-            const int k = 0;
+            const uint32_t h = (q & 31u) ? (w0 >> (q & 31u)) | (w1 << (32u - (q & 31u))) : w0;
 #endif
-            m &= m - 1u;
-            gz_bits_seek(b, base + (uint64_t)k + 3u);
-            if (gz_dynamic_header(b, t, true, true, lane, nl) == 0) { *found = base + (uint64_t)k; return 0; }
+            const bool pass = off + (uint32_t)lane < n_off && (h & 7u) == 4u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;
+#if defined(__CUDA_ARCH__)
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
+            if (pass) queue[count + (uint32_t)__popc(m & lt)] = off + (uint32_t)lane;
+            count += (uint32_t)__popc(m);
+#else
+            if (pass) queue[count++] = off + (uint32_t)lane;
+#endif
         }
+        if (count >= (uint32_t)nl || (!more && count)) {
+            GZ_SYNC();
+            const uint32_t take = count < (uint32_t)nl ? count : (uint32_t)nl;
+            const bool mine = (uint32_t)lane < take;
+            const bool cand = mine && gz_candidate(b, from_bit + queue[mine ? lane : 0], kraft9);
+#if defined(__CUDA_ARCH__)
+            uint32_t c = __ballot_sync(0xFFFFFFFFu, cand);
+#else
+            uint32_t c = cand ? 1u : 0u;
+#endif
+            while (c) {                                                  // survivors in order, the whole warp on each
+#if defined(__CUDA_ARCH__)
+                const int k = __ffs(c) - 1;
+#else
+                const int k = 0;
+#endif
+                c &= c - 1u;
+                const uint64_t at = from_bit + queue[k];
+                gz_bits_seek(b, at + 3u);
+                if (gz_dynamic_header(b, t, true, true, lane, nl) == 0) { *found = at; return 0; }
+            }
+            const uint32_t rest = count - take;                          // < nl: they move to the front
+            const uint32_t v = (uint32_t)lane < rest ? queue[take + (uint32_t)lane] : 0u;
+            GZ_SYNC();
+            if ((uint32_t)lane < rest) queue[lane] = v;
+            GZ_SYNC();
+            count = rest;
+        }
+        if (!more && !count) break;
     }
     return GZ_ERR_NOT_FOUND;
 }
@@ -614,6 +663,8 @@ GZ_HD inline void gz_subchunk(const uint32_t *words, uint64_t n_words, uint64_t 
     b.w = words; b.n_words = (uint32_t)n_words;
     uint64_t start = known_start;
     int rc = 0;
+    const bool find_only = (search_limit_bits >> 63) != 0;              // (profiling: the finder's share of the kernel - S2_GZ_FIND_ONLY)
+    search_limit_bits &= ~(1ull << 63);
     if (known_start == ~0ull) {
         const uint64_t end_bits = (uint64_t)n_words * 32u;
         uint64_t limit = cut_bit + search_limit_bits;
@@ -622,7 +673,7 @@ GZ_HD inline void gz_subchunk(const uint32_t *words, uint64_t n_words, uint64_t 
     }
     uint32_t n_out = 0;
     uint64_t end_bit = start;
-    if (rc == 0) {
+    if (rc == 0 && !find_only) {
         gz_bits_seek(b, start);
         rc = gz_decode_blocks(b, t, out, cap, known_start == ~0ull ? GZ_WINDOW : 0u, next_cut_bit, &n_out, &end_bit, lane, nl);
     }

@@ -1451,8 +1451,8 @@ static int ingest_gz_stage_init(s2_ingest *g)
 {
     GzStage &z = g->gz;
     if (z.d_res) return 0;
-    z.comp_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_BATCH_MB", 128), 1), 2048) << 20;
-    z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 32), 4), 4096) << 10;
+    z.comp_cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_BATCH_MB", 256), 1), 2048) << 20;
+    z.sub_bytes = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s2_env_u64("S2_GZ_SUB_KB", 64), 4), 4096) << 10;
     // symbols one sub-chunk may produce: S2_GZ_RATIO x its compressed bytes (FASTQ deflates 4-6 : 1, FASTA 3.5 : 1) plus the
     // run-on to the first block boundary behind the next cut; a sub-chunk that needs more makes its file the host reader's
     // (the run-on is one DEFLATE block: 16 K symbols, which are 30-100 KB of text for real reads and genomes but 300 KB for
