@@ -66,7 +66,7 @@ def test_executables_fail_loudly_on_damaged_gzip_data(s2, tmp_path, capsys):
     assert s2.run_kmer_scrub_count(["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"], cwd=tmp).returncode == 0
 
 
-@pytest.mark.parametrize("sub_kb", [8, 32, 256])
+@pytest.mark.parametrize("sub_kb", [8, 64, 256])
 def test_gpu_gunzip_of_ordinary_gz_files_equals_host_reader(s2, tmp_path, monkeypatch, sub_kb):
     """ordinary single-member .gz files (FASTA genomes at several compression levels, FASTQ files of several MB) decoded by
     the chunk-parallel gunzip (s2_gunzip.cu: block finder, speculative decode, chain, translate, CRC-32) inside the ingest
@@ -182,5 +182,42 @@ def test_gpu_gunzip_streams_a_big_gz_file_in_pieces(s2, tmp_path, monkeypatch, b
         st = ctx.sync()
         assert rc == [1], (name, rc)
         assert not t.counts(2).any(), name
+    t.free()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_gunzip_symbol_region_that_overflows_hands_the_file_back(s2, tmp_path):
+    """a .gz whose sub-chunks inflate to more symbols than a region holds (a short unit repeated: 250 : 1) - literals and the
+    deferred copies of the decoder store into the region's guard slot from then on, the sub-chunk reports the overflow, the
+    file is NOT handled (rc 1, nothing counted: the host reader takes it) - and the files decoded beside it in the same
+    launch, whose regions lie behind the overflowing ones, are counted exactly as the host reader counts them"""
+    import gzip
+    from strainer2_b200 import synth
+    tmp = str(tmp_path)
+    rng = synth.rng_for(23, 5)
+    strain = synth.genome(rng, 300_000, 4)
+    synth.write_fasta(os.path.join(tmp, "strain.fa"), strain)
+    ctx = s2.Context(0, batch_bytes=8 << 20, n_lanes=2)
+    t = s2.StrainTable(ctx, s2.load_flat(os.path.join(tmp, "strain.fa")), n_cols=4)
+    unit = bytes(strain[0][:1000])
+    rep = os.path.join(tmp, "repeat.fa.gz")
+    open(rep, "wb").write(gzip.compress(b">r\n" + b"\n".join(unit * 50 for _ in range(400)) + b"\n", 6))      # 20 MB of text in 80 KB
+    good = []
+    for i in range(3):
+        p = os.path.join(tmp, "g%d.fa.gz" % i)
+        open(p, "wb").write(gzip.compress(synth.fasta_bytes([c.copy() for c in strain] if i == 1 else synth.genome(rng, 400_000, 3), 80), 6))
+        good.append(p)
+    want = sum(ctx.scan_count(t, s2.load_flat(p), 1).hits for p in good)
+    rc, bases, lookups = ctx.ingest_count_files(t, [good[0], rep, good[1], rep, good[2]], 2)
+    st = ctx.sync()
+    assert list(rc) == [0, 1, 0, 1, 0], rc
+    assert st.hits == want > 1000 and np.array_equal(t.counts(1), t.counts(2))
+    # through the executable the file is simply read by the host instead: same table as with the GPU ingest switched off
+    open(os.path.join(tmp, "A.txt"), "w").write("repeat.fa.gz\ng1.fa.gz\n")
+    open(os.path.join(tmp, "B.txt"), "w").write("")
+    a = s2.run_kmer_scrub_count(["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"], cwd=tmp)
+    b = s2.run_kmer_scrub_count(["-r", "strain.fa", "-A", "A.txt", "-B", "B.txt"], cwd=tmp, env={"S2_GPU_INGEST": "0"})
+    assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout and len(a.stdout) > 1000
     t.free()
     ctx.close()
