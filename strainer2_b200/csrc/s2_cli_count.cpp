@@ -132,6 +132,9 @@ int s2_default_reader_threads()
 // threads pin two arenas each while the scan is running: 16 MB is one full pipeline chunk of BGZF.  Ordinary .gz wants
 // larger batches for its decode kernel (one warp per 64 KB of compressed bytes) and runs long enough to pay for them.
 static uint64_t g_arena_default_mb = 16;
+// Arenas per reader thread (S2_READ_ARENAS): two let a thread fill one while the job on the other is in flight; with one, the
+// thread waits for its job before it reads on - half the memory to pin, which is what the big arenas of ordinary .gz cost.
+static int g_arenas_default = 2;
 
 // does the first file a list names begin like an ordinary (not block-) gzip file?  Nothing is reported here: the list is
 // read again, with the reference's messages, when its turn comes
@@ -195,6 +198,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
     // there.  (Handing over paths made the pipeline read the files itself, under its lock: three pipelines = three
     // threads reading, 15 GB/s for all sixteen reader threads - profiles/r2d_bench_n1.json, cli leg.)
     const uint64_t arena_bytes = gpu_ingest && !exotic ? std::max<uint64_t>(s2_env_u64("S2_READ_ARENA_MB", g_arena_default_mb), 1) << 20 : 0;
+    const bool one_arena = s2_env_int("S2_READ_ARENAS", g_arenas_default) < 2;
 
     auto reader = [&](int tid) {
         BatchWriter w{ ctxs[tid % ctxs.size()], tables[tid % tables.size()] };
@@ -312,9 +316,11 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                 std::vector<const void *> images; std::vector<uint64_t> sizes;
                 if (arena_bytes && !arena[arena_at]) arena[arena_at] = (uint8_t *)s2_pinned_alloc(arena_bytes);
                 s2_ingest_job *job;
+                bool from_arena = false;
                 if (arena_bytes && arena[arena_at] && read_run(run, arena[arena_at], images, sizes)) {
                     job = s2_ingest_submit_mem_batch(w.ctx, w.table, images.data(), sizes.data(), (int)images.size(), col);
-                    arena_at ^= 1;                           // the job before this one is finished below, before its arena is filled again
+                    from_arena = true;
+                    if (!one_arena) arena_at ^= 1;           // the job before this one is finished below, before its arena is filled again
                 } else {
                     job = s2_ingest_submit_files(w.ctx, w.table, paths.data(), (int)paths.size(), col);      // (a file bigger than an arena: streamed from the file)
                 }
@@ -327,6 +333,7 @@ bool s2_scan_work_items_multi(std::vector<s2_ctx *> &ctxs, std::vector<s2_table 
                 }
                 if (!finish_pending()) { pending.run.swap(run); pending.col = col; pending.job = job; break; }
                 pending.run.swap(run); pending.col = col; pending.job = job;
+                if (one_arena && from_arena && !finish_pending()) break;      // the one arena is free again when its job is done
             } else {
                 host_read(run, std::vector<int>(run.size(), 1), col);
             }
