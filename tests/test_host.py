@@ -268,6 +268,22 @@ def test_inflate_fuzz_under_sanitizers(tmp_path):
     assert b"fuzz done" in p.stdout
 
 
+def test_gunzip_fuzz_under_sanitizers(tmp_path):
+    """the chunk-parallel gunzip's sub-chunk decoder (block finder + symbol loop of s2_gunzip.cuh, host build of the device
+    source) on intact, damaged and truncated streams, built with -fsanitize=address,undefined: every sub-chunk gets a symbol
+    region of its own allocated to the slot (32,768 markers, cap symbols, the guard slot) and the compressed words are
+    allocated to the word, regions are sometimes far too small - no access outside them, intact streams chain to their
+    exact size"""
+    exe = tmp_path / "gunzip_fuzz"
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                         os.path.join(ROOT, "tests", "sim", "gunzip_fuzz.cpp"), "-o", str(exe), "-lz"], capture_output=True)
+    if cc.returncode != 0:
+        pytest.skip("no sanitizer runtime for this g++: " + cc.stderr.decode()[-200:])
+    p = subprocess.run([str(exe), "40"], capture_output=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr).decode()[-2000:]
+    assert b"fuzz done" in p.stdout
+
+
 def _djb2_str(s: bytes) -> int:
     h = 5381
     for c in s:
