@@ -32,6 +32,10 @@
 #if defined(__CUDA_ARCH__)
 #define GZ_SYNC() __syncwarp()
 #define GZ_FENCE() asm volatile("" ::: "memory")
+#define GZ_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))                        /* the lanes' predicates as a mask */
+#define GZ_BCAST0(v) __shfl_sync(0xFFFFFFFFu, (v), 0)                       /* lane 0's value */
+#define GZ_POPC(m) ((uint32_t)__popc(m))
+#define GZ_CTZ(m) (__ffs((int)(m)) - 1)
 #define GZ_UNROLL _Pragma("unroll")
 #define GZ_NOUNROLL _Pragma("unroll 1")
 // The symbol loop addresses its tables and buffers through values the compiler must keep in registers: left to itself it
@@ -48,8 +52,17 @@ __device__ __forceinline__ gz_tab_t gz_tab(const uint32_t *t, uint32_t)
 }
 __device__ __forceinline__ uint32_t gz_tab_at(gz_tab_t t, uint32_t i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(t + (i << 2))); return v; }
 #else
+// Host builds: one "warp" of one lane (tests/sim/gunzip_harness.cpp, gunzip_fuzz.cpp), or - GZ_EMULATE_WARP, tests/sim/
+// gunzip_warp_emu.cpp - 32 threads that run the lanes' code with barriers where the lanes of a warp synchronise (the
+// harness defines GZ_SYNC / GZ_FENCE / GZ_BALLOT / GZ_BCAST0 before it includes this file).
+#if !defined(GZ_EMULATE_WARP)
 #define GZ_SYNC() do { } while (0)
 #define GZ_FENCE() do { } while (0)
+#define GZ_BALLOT(p) ((p) ? 1u : 0u)
+#define GZ_BCAST0(v) (v)
+#endif
+#define GZ_POPC(m) ((uint32_t)__builtin_popcount(m))
+#define GZ_CTZ(m) __builtin_ctz(m)
 #define GZ_UNROLL
 #define GZ_NOUNROLL
 #define GZ_KEEP64(p) do { } while (0)
@@ -284,9 +297,7 @@ GZ_HD inline int gz_build(uint32_t *tab, uint32_t cap, int root, int kind, const
             }
     }
     GZ_SYNC();
-#if defined(__CUDA_ARCH__)
-    rc = __shfl_sync(0xFFFFFFFFu, rc, 0);
-#endif
+    rc = GZ_BCAST0(rc);
     if (rc) return rc;
     for (int s = lane; s < n; s += nl) {
         const int l = lens[s];
@@ -588,9 +599,7 @@ GZ_HD inline int gz_find_block(GzBits &b, GzTables &t, const uint8_t *kraft9, ui
     const uint32_t *wp = b.w + (from_bit >> 5);
     const uint32_t nw = b.n_words - (uint32_t)(from_bit >> 5), s0 = (uint32_t)from_bit & 31u;
     const uint32_t n_off = limit_bit - from_bit > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)(limit_bit - from_bit);
-#if defined(__CUDA_ARCH__)
-    const uint32_t lt = (1u << lane) - 1u;
-#endif
+    const uint32_t lt = (1u << lane) - 1u;                              // the lanes below this one
     for (uint32_t off = 0;; off += (uint32_t)nl) {
         const bool more = off < n_off;
         if (more) {
@@ -603,30 +612,18 @@ GZ_HD inline int gz_find_block(GzBits &b, GzTables &t, const uint8_t *kraft9, ui
             const uint32_t h = (q & 31u) ? (w0 >> (q & 31u)) | (w1 << (32u - (q & 31u))) : w0;
 #endif
             const bool pass = off + (uint32_t)lane < n_off && (h & 7u) == 4u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;
-#if defined(__CUDA_ARCH__)
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-            if (pass) queue[count + (uint32_t)__popc(m & lt)] = off + (uint32_t)lane;
-            count += (uint32_t)__popc(m);
-#else
-            if (pass) queue[count++] = off + (uint32_t)lane;
-#endif
+            const uint32_t m = GZ_BALLOT(pass);
+            if (pass) queue[count + GZ_POPC(m & lt)] = off + (uint32_t)lane;
+            count += GZ_POPC(m);
         }
         if (count >= (uint32_t)nl || (!more && count)) {
             GZ_SYNC();
             const uint32_t take = count < (uint32_t)nl ? count : (uint32_t)nl;
             const bool mine = (uint32_t)lane < take;
             const bool cand = mine && gz_candidate(b, from_bit + queue[mine ? lane : 0], kraft9);
-#if defined(__CUDA_ARCH__)
-            uint32_t c = __ballot_sync(0xFFFFFFFFu, cand);
-#else
-            uint32_t c = cand ? 1u : 0u;
-#endif
+            uint32_t c = GZ_BALLOT(cand);
             while (c) {                                                  // survivors in order, the whole warp on each
-#if defined(__CUDA_ARCH__)
-                const int k = __ffs(c) - 1;
-#else
-                const int k = 0;
-#endif
+                const int k = GZ_CTZ(c);
                 c &= c - 1u;
                 const uint64_t at = from_bit + queue[k];
                 gz_bits_seek(b, at + 3u);

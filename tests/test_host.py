@@ -284,6 +284,19 @@ def test_gunzip_fuzz_under_sanitizers(tmp_path):
     assert b"fuzz done" in p.stdout
 
 
+def test_gunzip_device_control_flow_on_32_emulated_lanes(tmp_path):
+    """the DEVICE branches of s2_gunzip.cuh on the CPU: 32 threads are the lanes of a warp, barriers stand where the lanes
+    synchronise (__syncwarp, the ballots and broadcasts, the places that rely on the lanes running in step).  The block
+    finder's queue of survivors, a lane's share of a match copy (lanes behind its end, the deferred store, the guard slot),
+    table builds and header parsing over 32 lanes: the text of every stream is zlib's (FASTA, FASTQ, self-overlapping
+    matches, long codes; levels 1 / 6 / 9; sub-chunks of 8 and 64 KB)"""
+    exe = tmp_path / "gunzip_warp_emu"
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-pthread", os.path.join(ROOT, "tests", "sim", "gunzip_warp_emu.cpp"), "-o", str(exe), "-lz"])
+    p = subprocess.run([str(exe)], capture_output=True, timeout=900)
+    assert p.returncode == 0, (p.stdout + p.stderr).decode()[-2000:]
+    assert b"warp emulation done" in p.stdout
+
+
 def _djb2_str(s: bytes) -> int:
     h = 5381
     for c in s:
